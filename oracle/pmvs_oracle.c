@@ -1,0 +1,907 @@
+/*
+ * oracle/pmvs_oracle.c -- TEST INFRASTRUCTURE (see pmvs_oracle.h).
+ *
+ * Plain-C restatement of the reference's patch-optimisation path.  Each function cites the reference
+ * lines it follows (paths relative to /root/reference).  Float semantics are kept deliberately:
+ * f32 operations in source order, no FMA (-ffp-contract=off), and f64 exactly where the reference's
+ * unqualified sin/cos/asin/acos/log resolve to the double libm entry points.
+ */
+#include "pmvs_oracle.h"
+
+#include <limits.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "nm3.h"
+
+#define MAXIMG_LOCAL 256
+
+typedef struct {
+  float P[8][3][4]; /* per level */
+  float centre[4];
+  float oaxis[4];
+  float xaxis[3], yaxis[3], zaxis[3];
+  float ipscale;
+} cam_t;
+
+struct pmvso_ctx {
+  int num, tnum, level, csize, wsize, min_image_num, tau, nlevels;
+  float ncc_threshold, ncc_threshold_before;
+  float angle_threshold0, angle_threshold1, max_angle_threshold;
+  double xtol, step;
+  int maxeval;
+  cam_t* cams;
+  unsigned char** pix; /* [index*nlevels + level] */
+  int* w;
+  int* h;
+  int** vis2;
+  int* nvis2;
+};
+
+/* ---------------------------------------------------------------- small vector helpers (f32, source order) */
+static float dot4(const float* u, const float* v) { /* include/numeric/vec4.hpp:199-201 */
+  return u[0] * v[0] + u[1] * v[1] + u[2] * v[2] + u[3] * v[3];
+}
+static float dot3(const float* u, const float* v) { /* include/numeric/vec3.hpp:191-193 */
+  return u[0] * v[0] + u[1] * v[1] + u[2] * v[2];
+}
+static void cross3(const float* u, const float* v, float* o) { /* vec3.hpp:195-202 */
+  o[0] = u[1] * v[2] - v[1] * u[2];
+  o[1] = -u[0] * v[2] + v[0] * u[2];
+  o[2] = u[0] * v[1] - v[0] * u[1];
+}
+static void unitize3(float* v) { /* vec3.hpp:233-238 */
+  const float l = dot3(v, v);
+  if (l != 1.0 && l != 0.0) {
+    const float s = sqrtf(l);
+    v[0] /= s; v[1] /= s; v[2] /= s;
+  }
+}
+static void unitize4(float* v) { /* vec4.hpp:252-257 */
+  const float l = dot4(v, v);
+  if (l != 1.0 && l != 0.0) {
+    const float s = sqrtf(l);
+    v[0] /= s; v[1] /= s; v[2] /= s; v[3] /= s;
+  }
+}
+static float norm3(const float* v) { return sqrtf(dot3(v, v)); }
+static float norm4(const float* v) { return sqrtf(dot4(v, v)); }
+static float fminf_(float a, float b) { return b < a ? b : a; } /* std::min */
+static float fmaxf_(float a, float b) { return a < b ? b : a; } /* std::max */
+
+/* ---------------------------------------------------------------- context */
+pmvso_ctx* pmvso_create(int num, int tnum, int level, int csize, int wsize, int min_image_num,
+                        float threshold, float max_angle_deg) {
+  pmvso_ctx* c = (pmvso_ctx*)calloc(1, sizeof(*c));
+  c->num = num; c->tnum = tnum; c->level = level; c->csize = csize; c->wsize = wsize;
+  c->min_image_num = min_image_num;
+  c->tau = min_image_num * 2 < num ? min_image_num * 2 : num; /* source/pmvs/findMatch.cpp:56 */
+  c->nlevels = level + 3;                                     /* findMatch.cpp:72 */
+  c->ncc_threshold = threshold;
+  c->ncc_threshold_before = threshold - 0.3f;                 /* findMatch.cpp:104 */
+  c->angle_threshold0 = 60.0f * M_PI / 180.0f;               /* findMatch.cpp:92-93 */
+  c->angle_threshold1 = 60.0f * M_PI / 180.0f;
+  c->max_angle_threshold = max_angle_deg;                     /* source/pmvs/option.cpp:105-106 */
+  c->max_angle_threshold *= M_PI / 180.0f;
+  c->xtol = 1.0e-4; c->step = 1.0; c->maxeval = 1000;
+  c->cams = (cam_t*)calloc(num, sizeof(cam_t));
+  c->pix = (unsigned char**)calloc((size_t)num * c->nlevels, sizeof(unsigned char*));
+  c->w = (int*)calloc((size_t)num * c->nlevels, sizeof(int));
+  c->h = (int*)calloc((size_t)num * c->nlevels, sizeof(int));
+  c->vis2 = (int**)calloc(num, sizeof(int*));
+  c->nvis2 = (int*)calloc(num, sizeof(int));
+  for (int i = 0; i < num; ++i) { /* option.cpp initVisdata: every other image */
+    c->vis2[i] = (int*)malloc(sizeof(int) * (num > 1 ? num - 1 : 1));
+    int k = 0;
+    for (int j = 0; j < num; ++j)
+      if (j != i) c->vis2[i][k++] = j;
+    c->nvis2[i] = k;
+  }
+  return c;
+}
+
+void pmvso_destroy(pmvso_ctx* c) {
+  if (!c) return;
+  for (int i = 0; i < c->num * c->nlevels; ++i) free(c->pix[i]);
+  for (int i = 0; i < c->num; ++i) free(c->vis2[i]);
+  free(c->pix); free(c->w); free(c->h); free(c->vis2); free(c->nvis2); free(c->cams); free(c);
+}
+
+void pmvso_set_thresholds(pmvso_ctx* c, float ncc, float ncc_before) { c->ncc_threshold = ncc; c->ncc_threshold_before = ncc_before; }
+void pmvso_set_xtol(pmvso_ctx* c, double xtol, double step, int maxeval) { c->xtol = xtol; c->step = step; c->maxeval = maxeval; }
+void pmvso_set_visdata2(pmvso_ctx* c, int index, const int* list, int n) {
+  free(c->vis2[index]);
+  c->vis2[index] = (int*)malloc(sizeof(int) * (n > 0 ? n : 1));
+  memcpy(c->vis2[index], list, sizeof(int) * n);
+  c->nvis2[index] = n;
+}
+
+/* source/image/camera.cpp:56-68 (levels), 109-136 (updateCamera), 138-175 (getOpticalCenter),
+ * source/pmvs/optim.cpp:43-64 (setAxesScales) */
+void pmvso_set_camera(pmvso_ctx* c, int index, const float* P) {
+  cam_t* cam = &c->cams[index];
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 4; ++k) cam->P[0][r][k] = P[4 * r + k];
+  for (int l = 1; l < c->nlevels && l < 8; ++l) {
+    memcpy(cam->P[l], cam->P[l - 1], sizeof(cam->P[0]));
+    for (int k = 0; k < 4; ++k) { cam->P[l][0][k] /= 2.0f; cam->P[l][1][k] /= 2.0f; }
+  }
+  /* optical axis */
+  float oa[4] = {cam->P[0][2][0], cam->P[0][2][1], cam->P[0][2][2], 0.0f};
+  const float ftmp = norm4(oa);
+  oa[3] = cam->P[0][2][3];
+  for (int k = 0; k < 4; ++k) cam->oaxis[k] = oa[k] / ftmp;
+  /* optical centre: -A^-1 b in double via adjoint (include/numeric/mat3.hpp:275-292) */
+  if (cam->P[0][2][0] == 0.0 && cam->P[0][2][1] == 0.0 && cam->P[0][2][2] == 0.0) {
+    float v0[3] = {cam->P[0][0][0], cam->P[0][0][1], cam->P[0][0][2]};
+    float v1[3] = {cam->P[0][1][0], cam->P[0][1][1], cam->P[0][1][2]};
+    float v2[3];
+    cross3(v0, v1, v2);
+    unitize3(v2);
+    cam->centre[0] = v2[0]; cam->centre[1] = v2[1]; cam->centre[2] = v2[2]; cam->centre[3] = 0.f;
+  } else {
+    double A[3][3], adj[3][3], b[3], inv[3][3];
+    for (int y = 0; y < 3; ++y) {
+      for (int x = 0; x < 3; ++x) A[y][x] = cam->P[0][y][x];
+      b[y] = -cam->P[0][y][3];
+    }
+#define CROSSD(u, v, o)                      \
+  do {                                       \
+    (o)[0] = (u)[1] * (v)[2] - (v)[1] * (u)[2]; \
+    (o)[1] = -(u)[0] * (v)[2] + (v)[0] * (u)[2]; \
+    (o)[2] = (u)[0] * (v)[1] - (v)[0] * (u)[1]; \
+  } while (0)
+    CROSSD(A[1], A[2], adj[0]);
+    CROSSD(A[2], A[0], adj[1]);
+    CROSSD(A[0], A[1], adj[2]);
+    const double d = adj[0][0] * A[0][0] + adj[0][1] * A[0][1] + adj[0][2] * A[0][2];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) inv[i][j] = adj[j][i] / d;
+    for (int y = 0; y < 3; ++y)
+      cam->centre[y] = (float)(inv[y][0] * b[0] + inv[y][1] * b[1] + inv[y][2] * b[2]);
+    cam->centre[3] = 1.f;
+  }
+  /* COptim axes (optim.cpp:47-53) */
+  cam->zaxis[0] = cam->oaxis[0]; cam->zaxis[1] = cam->oaxis[1]; cam->zaxis[2] = cam->oaxis[2];
+  float xa[3] = {cam->P[0][0][0], cam->P[0][0][1], cam->P[0][0][2]};
+  cross3(cam->zaxis, xa, cam->yaxis);
+  unitize3(cam->yaxis);
+  cross3(cam->yaxis, cam->zaxis, cam->xaxis);
+  /* ipscale (optim.cpp:56-63) */
+  const float xe[4] = {cam->xaxis[0], cam->xaxis[1], cam->xaxis[2], 0.0f};
+  const float ye[4] = {cam->yaxis[0], cam->yaxis[1], cam->yaxis[2], 0.0f};
+  const float fx = dot4(xe, cam->P[0][0]);
+  const float fy = dot4(ye, cam->P[0][1]);
+  cam->ipscale = fx + fy;
+}
+
+/* source/image/image.cpp:136-139 (sizes), 228-325 (buildImage, filter 0).
+ * Weights are k/64 in double; every partial sum is an exact dyadic rational, so integer arithmetic
+ * reproduces (unsigned char)(int)floor(sum/denom + 0.5f) exactly: floor((2S + D) / (2D)). */
+void pmvso_set_image(pmvso_ctx* c, int index, int w, int h, const unsigned char* rgb) {
+  static const int wt[4] = {1, 3, 3, 1};
+  const int base = index * c->nlevels;
+  c->w[base] = w; c->h[base] = h;
+  free(c->pix[base]);
+  c->pix[base] = (unsigned char*)malloc((size_t)w * h * 3);
+  memcpy(c->pix[base], rgb, (size_t)w * h * 3);
+  for (int l = 1; l < c->nlevels; ++l) {
+    const int pw = c->w[base + l - 1], ph = c->h[base + l - 1];
+    const int nw = pw / 2, nh = ph / 2;
+    c->w[base + l] = nw; c->h[base + l] = nh;
+    free(c->pix[base + l]);
+    c->pix[base + l] = (unsigned char*)malloc((size_t)(nw > 0 ? nw : 1) * (nh > 0 ? nh : 1) * 3);
+    const unsigned char* src = c->pix[base + l - 1];
+    unsigned char* dst = c->pix[base + l];
+    for (int y = 0; y < nh; ++y)
+      for (int x = 0; x < nw; ++x) {
+        long S[3] = {0, 0, 0};
+        long D = 0;
+        for (int j = -1; j < 3; ++j) {
+          const int yt = 2 * y + j;
+          if (yt < 0 || ph - 1 < yt) continue;
+          for (int i = -1; i < 3; ++i) {
+            const int xt = 2 * x + i;
+            if (xt < 0 || pw - 1 < xt) continue;
+            const int k = wt[j + 1] * wt[i + 1];
+            const unsigned char* p = src + ((size_t)yt * pw + xt) * 3;
+            S[0] += k * p[0]; S[1] += k * p[1]; S[2] += k * p[2];
+            D += k;
+          }
+        }
+        for (int k = 0; k < 3; ++k) dst[((size_t)y * nw + x) * 3 + k] = (unsigned char)((2 * S[k] + D) / (2 * D));
+      }
+  }
+}
+
+void pmvso_image_dims(const pmvso_ctx* c, int index, int level, int* w, int* h) {
+  *w = c->w[index * c->nlevels + level]; *h = c->h[index * c->nlevels + level];
+}
+void pmvso_image_bytes(const pmvso_ctx* c, int index, int level, unsigned char* out) {
+  const int k = index * c->nlevels + level;
+  memcpy(out, c->pix[k], (size_t)c->w[k] * c->h[k] * 3);
+}
+void pmvso_camera(const pmvso_ctx* c, int index, int level, float* P, float* centre, float* oaxis,
+                  float* xaxis, float* yaxis, float* zaxis, float* ipscale) {
+  const cam_t* cam = &c->cams[index];
+  memcpy(P, cam->P[level], sizeof(float) * 12);
+  memcpy(centre, cam->centre, sizeof(float) * 4);
+  memcpy(oaxis, cam->oaxis, sizeof(float) * 4);
+  memcpy(xaxis, cam->xaxis, sizeof(float) * 3);
+  memcpy(yaxis, cam->yaxis, sizeof(float) * 3);
+  memcpy(zaxis, cam->zaxis, sizeof(float) * 3);
+  *ipscale = cam->ipscale;
+}
+
+/* ---------------------------------------------------------------- geometry primitives */
+/* include/image/camera.hpp:89-108 */
+static void project(const pmvso_ctx* c, int index, const float* X, int level, float* o) {
+  const cam_t* cam = &c->cams[index];
+  for (int i = 0; i < 3; ++i) o[i] = dot4(cam->P[level][i], X);
+  if (o[2] <= 0.0) {
+    o[0] = -0xffff; o[1] = -0xffff; o[2] = -1.0f;
+    return;
+  }
+  const float z = o[2];
+  o[0] /= z; o[1] /= z; o[2] /= z;
+  o[0] = fmaxf_((float)(INT_MIN + 3.0f), fminf_((float)(INT_MAX - 3.0f), o[0]));
+  o[1] = fmaxf_((float)(INT_MIN + 3.0f), fminf_((float)(INT_MAX - 3.0f), o[1]));
+}
+void pmvso_project(const pmvso_ctx* c, int index, const float* coord, int level, float* out3) { project(c, index, coord, level, out3); }
+
+/* source/pmvs/optim.cpp:1116-1124 */
+static float get_unit(const pmvso_ctx* c, int index, const float* X) {
+  const cam_t* cam = &c->cams[index];
+  const float d[4] = {X[0] - cam->centre[0], X[1] - cam->centre[1], X[2] - cam->centre[2], X[3] - cam->centre[3]};
+  const float fz = norm4(d);
+  const float ftmp = cam->ipscale;
+  if (ftmp == 0.0) return 1.0;
+  return (float)(2.0 * fz * (0x0001 << c->level) / ftmp);
+}
+float pmvso_get_unit(const pmvso_ctx* c, int index, const float* coord) { return get_unit(c, index, coord); }
+
+/* include/image/image.hpp:435-476 (bilinear branch) */
+static void get_color(const pmvso_ctx* c, int index, float x, float y, int level, float* rgb) {
+  const int k = index * c->nlevels + level;
+  const int W = c->w[k];
+  const unsigned char* im = c->pix[k];
+  const int lx = (int)x;
+  const int ly = (int)y;
+  const int idx = 3 * (ly * W + lx);
+  const float dx1 = x - lx; const float dx0 = 1.0f - dx1;
+  const float dy1 = y - ly; const float dy0 = 1.0f - dy1;
+  const float f00 = dx0 * dy0; const float f01 = dx0 * dy1;
+  const float f10 = dx1 * dy0; const float f11 = dx1 * dy1;
+  const int idx2 = idx + 3 * W;
+  const unsigned char* p0 = im + idx;
+  const unsigned char* p1 = im + idx2;
+  for (int ch = 0; ch < 3; ++ch) {
+    float r = 0.0f;
+    r += p0[ch] * f00 + p1[ch] * f01;
+    r += p0[ch + 3] * f10 + p1[ch + 3] * f11;
+    rgb[ch] = r;
+  }
+}
+void pmvso_get_color(const pmvso_ctx* c, int index, float x, float y, int level, float* rgb) { get_color(c, index, x, y, level, rgb); }
+
+/* optim.cpp:1127-1144 */
+static void get_paxes(const pmvso_ctx* c, int index, const float* coord, const float* normal, float* px, float* py) {
+  const cam_t* cam = &c->cams[index];
+  const float pscale = get_unit(c, index, coord);
+  const float n3[3] = {normal[0], normal[1], normal[2]};
+  float y3[3], x3[3];
+  cross3(n3, cam->xaxis, y3);
+  unitize3(y3);
+  cross3(y3, n3, x3);
+  px[0] = x3[0]; px[1] = x3[1]; px[2] = x3[2]; px[3] = 0.0f;
+  py[0] = y3[0]; py[1] = y3[1]; py[2] = y3[2]; py[3] = 0.0f;
+  for (int k = 0; k < 4; ++k) { px[k] *= pscale; py[k] *= pscale; }
+  float c0[3], c1[3], d[3], t[4];
+  project(c, index, coord, c->level, c0);
+  for (int k = 0; k < 4; ++k) t[k] = coord[k] + px[k];
+  project(c, index, t, c->level, c1);
+  for (int k = 0; k < 3; ++k) d[k] = c1[k] - c0[k];
+  const float xdis = norm3(d);
+  for (int k = 0; k < 4; ++k) t[k] = coord[k] + py[k];
+  project(c, index, t, c->level, c1);
+  for (int k = 0; k < 3; ++k) d[k] = c1[k] - c0[k];
+  const float ydis = norm3(d);
+  for (int k = 0; k < 4; ++k) { px[k] /= xdis; py[k] /= ydis; }
+}
+void pmvso_get_paxes(const pmvso_ctx* c, int index, const float* coord, const float* normal, float* px, float* py) { get_paxes(c, index, coord, normal, px, py); }
+
+/* optim.cpp:808-811 */
+static float my_pow2(int x) {
+  static const float answers[] = {0.0625, 0.125, 0.25, 0.5, 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024};
+  return answers[x + 4];
+}
+
+/* optim.cpp:783-805 */
+static int grab_safe(const pmvso_ctx* c, int index, int size, const float* center, const float* dx, const float* dy, int level) {
+  const int margin = size / 2;
+  float tl[2], tr[2], bl[2], br[2];
+  for (int k = 0; k < 2; ++k) {
+    tl[k] = center[k] - dx[k] * margin - dy[k] * margin;
+    tr[k] = center[k] + dx[k] * margin - dy[k] * margin;
+    bl[k] = center[k] - dx[k] * margin + dy[k] * margin;
+    br[k] = center[k] + dx[k] * margin + dy[k] * margin;
+  }
+  const float minx = fminf_(tl[0], fminf_(tr[0], fminf_(bl[0], br[0])));
+  const float maxx = fmaxf_(tl[0], fmaxf_(tr[0], fmaxf_(bl[0], br[0])));
+  const float miny = fminf_(tl[1], fminf_(tr[1], fminf_(bl[1], br[1])));
+  const float maxy = fmaxf_(tl[1], fmaxf_(tr[1], fmaxf_(bl[1], br[1])));
+  const int margin2 = 3;
+  const int k = index * c->nlevels + level;
+  if (minx < margin2 || c->w[k] - 1 - margin2 <= maxx || miny < margin2 || c->h[k] - 1 - margin2 <= maxy) return 0;
+  return 1;
+}
+
+/* optim.cpp:815-863.  Returns 1 = rejected (tex untouched), 0 = ok. */
+static int grab_tex(const pmvso_ctx* c, const float* coord, const float* pxaxis, const float* pyaxis,
+                    const float* pzaxis, int index, int size, float* tex, int* newlevel_out) {
+  const cam_t* cam = &c->cams[index];
+  if (newlevel_out) *newlevel_out = -1;
+  float ray[4] = {cam->centre[0] - coord[0], cam->centre[1] - coord[1], cam->centre[2] - coord[2], cam->centre[3] - coord[3]};
+  unitize4(ray);
+  const float weight = fmaxf_(0.0f, dot4(ray, pzaxis));
+  if (weight < cos(c->angle_threshold1)) return 1;
+  const int margin = size / 2;
+  float center[3], dx[3], dy[3], t[4], q[3];
+  project(c, index, coord, c->level, center);
+  for (int k = 0; k < 4; ++k) t[k] = coord[k] + pxaxis[k];
+  project(c, index, t, c->level, q);
+  for (int k = 0; k < 3; ++k) dx[k] = q[k] - center[k];
+  for (int k = 0; k < 4; ++k) t[k] = coord[k] + pyaxis[k];
+  project(c, index, t, c->level, q);
+  for (int k = 0; k < 3; ++k) dy[k] = q[k] - center[k];
+  const float ratio = (norm3(dx) + norm3(dy)) / 2.0f;
+  static const float Log2 = 0.693147180559945309417f; /* static float Log2 = log(2.0f); optim.cpp:813 */
+  const double lv = floor(log(ratio) / Log2 + 0.5f);
+  int leveldif;
+  if (!(lv > -1.0e9)) leveldif = INT_MIN; /* (int) of -inf / NaN: cvttsd2si yields INT_MIN */
+  else if (lv > 1.0e9) leveldif = INT_MIN;
+  else leveldif = (int)lv;
+  leveldif = leveldif < 2 ? leveldif : 2;                    /* std::min(2, leveldif) */
+  leveldif = -c->level < leveldif ? leveldif : -c->level;    /* std::max(-level, .) */
+  const float scale = my_pow2(leveldif);
+  const int newlevel = c->level + leveldif;
+  for (int k = 0; k < 3; ++k) { center[k] /= scale; dx[k] /= scale; dy[k] /= scale; }
+  if (grab_safe(c, index, size, center, dx, dy, newlevel) == 0) return 1;
+  if (newlevel_out) *newlevel_out = newlevel;
+  float left[3];
+  for (int k = 0; k < 3; ++k) left[k] = center[k] - dx[k] * margin - dy[k] * margin;
+  float* tp = tex;
+  for (int y = 0; y < size; ++y) {
+    float v[3] = {left[0], left[1], left[2]};
+    for (int k = 0; k < 3; ++k) left[k] += dy[k];
+    for (int x = 0; x < size; ++x) {
+      get_color(c, index, v[0], v[1], newlevel, tp);
+      tp += 3;
+      for (int k = 0; k < 3; ++k) v[k] += dx[k];
+    }
+  }
+  return 0;
+}
+
+int pmvso_grab_tex(const pmvso_ctx* c, const float* coord, const float* normal, int ref, int index, float* tex, int* newlevel) {
+  float px[4], py[4];
+  get_paxes(c, ref, coord, normal, px, py);
+  return grab_tex(c, coord, px, py, normal, index, c->wsize, tex, newlevel);
+}
+
+/* optim.cpp:1031-1067 */
+static void normalize_tex(float* tex, int size) {
+  const int size3 = size / 3;
+  float ave[3] = {0.f, 0.f, 0.f};
+  for (int i = 0; i < size3; ++i) { ave[0] += tex[3 * i]; ave[1] += tex[3 * i + 1]; ave[2] += tex[3 * i + 2]; }
+  ave[0] /= (float)size3; ave[1] /= (float)size3; ave[2] /= (float)size3;
+  float ave2 = 0.0f;
+  for (int i = 0; i < size3; ++i) {
+    const float f0 = ave[0] - tex[3 * i];
+    const float f1 = ave[1] - tex[3 * i + 1];
+    const float f2 = ave[2] - tex[3 * i + 2];
+    ave2 += f0 * f0 + f1 * f1 + f2 * f2;
+  }
+  ave2 = sqrtf(ave2 / size);
+  if (ave2 == 0.0f) ave2 = 1.0f;
+  for (int i = 0; i < size3; ++i)
+    for (int k = 0; k < 3; ++k) { tex[3 * i + k] -= ave[k]; tex[3 * i + k] /= ave2; }
+}
+void pmvso_normalize(float* tex, int n) { normalize_tex(tex, n); }
+
+/* optim.cpp:1069-1077 */
+static float dot_tex(const float* a, const float* b, int size) {
+  float ans = 0.0f;
+  for (int i = 0; i < size; ++i) ans += a[i] * b[i];
+  return ans / size;
+}
+float pmvso_dot(const float* a, const float* b, int n) { return dot_tex(a, b, n); }
+
+/* include/pmvs/optim.hpp:86-92 */
+static float robustincc(const float rhs) { return rhs / (1 + 3 * rhs); }
+static float unrobustincc(const float rhs) { return rhs / (1 - 3 * rhs); }
+
+/* ---------------------------------------------------------------- per-refinement context (optim.cpp:584-596) */
+typedef struct {
+  const pmvso_ctx* c;
+  float centre[4], ray[4];
+  const int* images;
+  int n;
+  float dscale, ascale;
+  float weights[MAXIMG_LOCAL];
+  float* texs; /* tau * tsize floats */
+  unsigned char valid[MAXIMG_LOCAL];
+} rctx_t;
+
+/* optim.cpp:446-471 + 1146-1152 */
+static void set_weights(const pmvso_ctx* c, const float* coord, const float* normal, const int* images, int n, float* w) {
+  for (int i = 0; i < n; ++i) {
+    const cam_t* cam = &c->cams[images[i]];
+    float u = get_unit(c, images[i], coord);
+    float ray[4] = {cam->centre[0] - coord[0], cam->centre[1] - coord[1], cam->centre[2] - coord[2], cam->centre[3] - coord[3]};
+    unitize4(ray);
+    const float denom = dot4(ray, normal);
+    if (0.0 < denom) u /= denom; else u = INT_MAX / 2;
+    w[i] = u;
+  }
+  for (int i = 1; i < n; ++i) w[i] = fminf_(1.0f, w[0] / w[i]);
+  if (n > 0) w[0] = 1.0f;
+}
+
+static void rctx_init(rctx_t* r, const pmvso_ctx* c, const float* coord, const float* normal, const int* images, int n, float dscale) {
+  r->c = c;
+  memcpy(r->centre, coord, sizeof(float) * 4);
+  const cam_t* cam = &c->cams[images[0]];
+  for (int k = 0; k < 4; ++k) r->ray[k] = coord[k] - cam->centre[k];
+  unitize4(r->ray);
+  r->images = images; r->n = n;
+  r->dscale = dscale;
+  r->ascale = (float)(M_PI / 48.0f);
+  set_weights(c, coord, normal, images, n < MAXIMG_LOCAL ? n : MAXIMG_LOCAL, r->weights);
+}
+
+/* optim.cpp:690-707 */
+static void decode(const rctx_t* r, const double* x, float* coord, float* normal) {
+  const cam_t* cam = &r->c->cams[r->images[0]];
+  const double s = r->dscale * x[0];
+  for (int k = 0; k < 4; ++k) coord[k] = r->centre[k] + (float)(r->ray[k] * s);
+  const float angle1 = (float)(x[1] * r->ascale);
+  const float angle2 = (float)(x[2] * r->ascale);
+  const float fx = (float)(sin(angle1) * cos(angle2));
+  const float fy = (float)sin(angle2);
+  const float fz = (float)(-cos(angle1) * cos(angle2));
+  for (int k = 0; k < 3; ++k) normal[k] = cam->xaxis[k] * fx + cam->yaxis[k] * fy + cam->zaxis[k] * fz;
+  normal[3] = 0.0f;
+}
+
+/* optim.cpp:660-688 */
+static void encode(const rctx_t* r, const float* coord, const float* normal, double* x) {
+  const cam_t* cam = &r->c->cams[r->images[0]];
+  const float d[4] = {coord[0] - r->centre[0], coord[1] - r->centre[1], coord[2] - r->centre[2], coord[3] - r->centre[3]};
+  x[0] = dot4(d, r->ray) / r->dscale;
+  float n3[3] = {normal[0], normal[1], normal[2]};
+  if (normal[3] != 1.0 && normal[3] != 0.0) { n3[0] /= normal[3]; n3[1] /= normal[3]; n3[2] /= normal[3]; }
+  const float fx = dot3(cam->xaxis, n3);
+  const float fy = dot3(cam->yaxis, n3);
+  const float fz = dot3(cam->zaxis, n3);
+  x[2] = asin(fmaxf_(-1.0f, fminf_(1.0f, fy)));
+  const float cosb = (float)cos(x[2]);
+  if (cosb == 0.0) {
+    x[1] = 0.0;
+  } else {
+    const float sina = fx / cosb;
+    const float cosa = -fz / cosb;
+    x[1] = acos(fmaxf_(-1.0f, fminf_(1.0f, cosa)));
+    if (sina < 0.0) x[1] = -x[1];
+  }
+  x[1] = x[1] / r->ascale;
+  x[2] = x[2] / r->ascale;
+}
+
+/* grab + normalise textures of the first `size` images; valid[i] = texture present */
+static void grab_all(const pmvso_ctx* c, const float* coord, const float* normal, const float* px, const float* py,
+                     const int* images, int size, float* texs, unsigned char* valid) {
+  const int tsize = 3 * c->wsize * c->wsize;
+  for (int i = 0; i < size; ++i) {
+    const int flag = grab_tex(c, coord, px, py, normal, images[i], c->wsize, texs + (size_t)i * tsize, NULL);
+    valid[i] = (flag == 0);
+    if (flag == 0) normalize_tex(texs + (size_t)i * tsize, tsize);
+  }
+}
+
+/* optim.cpp:507-578 (pairwise == 0 branch) */
+static double my_f(unsigned nn, const double* x, void* data) {
+  rctx_t* r = (rctx_t*)data;
+  const pmvso_ctx* c = r->c;
+  (void)nn;
+  float coord[4], normal[4], px[4], py[4];
+  decode(r, x, coord, normal);
+  get_paxes(c, r->images[0], coord, normal, px, py);
+  const int size = c->tau < r->n ? c->tau : r->n;
+  const int mininum = c->min_image_num < size ? c->min_image_num : size;
+  const int tsize = 3 * c->wsize * c->wsize;
+  grab_all(c, coord, normal, px, py, r->images, size, r->texs, r->valid);
+  if (!r->valid[0]) return 2.0;
+  double ans = 0.0f;
+  int denom = 0;
+  for (int i = 1; i < size; ++i) {
+    if (!r->valid[i]) continue;
+    ans += robustincc((float)(1.0 - dot_tex(r->texs, r->texs + (size_t)i * tsize, tsize)));
+    denom++;
+  }
+  if (denom < mininum - 1) return 2.0f;
+  return ans / denom + 0.0;
+}
+
+/* optim.cpp:865-938 (non-PAIRNCC branch) */
+static double compute_incc(rctx_t* r, const float* coord, const float* normal, int robust) {
+  const pmvso_ctx* c = r->c;
+  if (r->n < 2) return 2.0;
+  float px[4], py[4];
+  get_paxes(c, r->images[0], coord, normal, px, py);
+  const int size = c->tau < r->n ? c->tau : r->n;
+  const int tsize = 3 * c->wsize * c->wsize;
+  grab_all(c, coord, normal, px, py, r->images, size, r->texs, r->valid);
+  if (!r->valid[0]) return 2.0;
+  double score = 0.0;
+  float totalweight = 0.0;
+  for (int i = 1; i < size; ++i) {
+    if (!r->valid[i]) continue;
+    totalweight += r->weights[i];
+    const float d = dot_tex(r->texs, r->texs + (size_t)i * tsize, tsize);
+    if (robust) score += robustincc((float)(1.0 - d)) * r->weights[i];
+    else score += (1.0 - d) * r->weights[i];
+  }
+  if (totalweight == 0.0) score = 2.0; else score /= totalweight;
+  return score;
+}
+
+static float* alloc_texs(const pmvso_ctx* c, int n) {
+  return (float*)malloc(sizeof(float) * 3 * c->wsize * c->wsize * (size_t)(n > 1 ? n : 1));
+}
+
+void pmvso_encode(const pmvso_ctx* c, const float* coord, const float* normal, const int* images, int n, float dscale, double* x) {
+  rctx_t r; rctx_init(&r, c, coord, normal, images, n, dscale);
+  encode(&r, coord, normal, x);
+}
+void pmvso_decode(const pmvso_ctx* c, const float* coord, const float* normal, const int* images, int n, float dscale,
+                  const double* x, float* ocoord, float* onormal) {
+  rctx_t r; rctx_init(&r, c, coord, normal, images, n, dscale);
+  decode(&r, x, ocoord, onormal);
+}
+double pmvso_my_f(const pmvso_ctx* c, const float* coord, const float* normal, const int* images, int n, float dscale, const double* x) {
+  rctx_t r; rctx_init(&r, c, coord, normal, images, n, dscale);
+  r.texs = alloc_texs(c, c->tau);
+  const double f = my_f(3, x, &r);
+  free(r.texs);
+  return f;
+}
+double pmvso_compute_incc(const pmvso_ctx* c, const float* coord, const float* normal, const int* images, int n, int robust) {
+  rctx_t r; rctx_init(&r, c, coord, normal, images, n, 1.0f);
+  r.texs = alloc_texs(c, c->tau);
+  const double f = compute_incc(&r, coord, normal, robust);
+  free(r.texs);
+  return f;
+}
+
+/* optim.cpp:580-658 with nm3 in place of nlopt.  texs scratch supplied by caller. */
+static int refine_one(const pmvso_ctx* c, float* coord, float* normal, const int* images, int n, float dscale,
+                      float* ncc, int* evals, float* texs) {
+  rctx_t r; rctx_init(&r, c, coord, normal, images, n, dscale);
+  r.texs = texs;
+  double p[3];
+  encode(&r, coord, normal, p);
+  const double lb[3] = {-HUGE_VAL, -23.99999, -23.99999};
+  const double ub[3] = {HUGE_VAL, 23.99999, 23.99999};
+  double x[3];
+  for (int i = 0; i < 3; ++i) x[i] = fmax(fmin(p[i], ub[i]), lb[i]);
+  double minf;
+  int nev = 0;
+  const int res = nm3_minimize(3, my_f, &r, lb, ub, x, &minf, c->step, c->xtol, c->maxeval, &nev);
+  if (evals) *evals = nev;
+  if (res != NM3_XTOL_REACHED) return 0;
+  decode(&r, x, coord, normal);
+  *ncc = (float)(1.0 - unrobustincc((float)compute_incc(&r, coord, normal, 1)));
+  return 1;
+}
+
+int pmvso_refine(const pmvso_ctx* c, float* coord, float* normal, const int* images, int n, float dscale, float* ncc, int* evals) {
+  float* texs = alloc_texs(c, c->tau);
+  const int ok = refine_one(c, coord, normal, images, n, dscale, ncc, evals, texs);
+  free(texs);
+  return ok;
+}
+
+typedef struct {
+  const pmvso_ctx* c; int P, V; float* coords; float* normals; const int* images; const float* dscales;
+  float* nccs; int* evals; unsigned char* ok; int* next; pthread_mutex_t* mu;
+} batch_t;
+
+static void* batch_worker(void* arg) {
+  batch_t* b = (batch_t*)arg;
+  float* texs = alloc_texs(b->c, b->c->tau);
+  for (;;) {
+    pthread_mutex_lock(b->mu);
+    const int s = *b->next; *b->next += 64;
+    pthread_mutex_unlock(b->mu);
+    if (s >= b->P) break;
+    const int e = s + 64 < b->P ? s + 64 : b->P;
+    for (int p = s; p < e; ++p) {
+      int ev = 0;
+      float ncc = -1.0f;
+      b->ok[p] = (unsigned char)refine_one(b->c, b->coords + 4 * p, b->normals + 4 * p, b->images + (size_t)b->V * p, b->V,
+                                           b->dscales[p], &ncc, &ev, texs);
+      b->nccs[p] = ncc; b->evals[p] = ev;
+    }
+  }
+  free(texs);
+  return NULL;
+}
+
+double pmvso_refine_batch(const pmvso_ctx* c, int P, int V, float* coords, float* normals, const int* images,
+                          const float* dscales, float* nccs, int* evals, unsigned char* ok, int threads) {
+  if (threads < 1) threads = 1;
+  if (threads > 256) threads = 256;
+  pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+  int next = 0;
+  batch_t b = {c, P, V, coords, normals, images, dscales, nccs, evals, ok, &next, &mu};
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  pthread_t th[256];
+  for (int i = 1; i < threads; ++i) pthread_create(&th[i], NULL, batch_worker, &b);
+  batch_worker(&b);
+  for (int i = 1; i < threads; ++i) pthread_join(th[i], NULL);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* ---------------------------------------------------------------- setINCCs (optim.cpp:709-744, 746-781) */
+void pmvso_set_inccs(const pmvso_ctx* c, const float* coord, const float* normal, const int* images, int n, int robust, float* out) {
+  float px[4], py[4];
+  get_paxes(c, images[0], coord, normal, px, py);
+  const int tsize = 3 * c->wsize * c->wsize;
+  float* texs = alloc_texs(c, n);
+  unsigned char* valid = (unsigned char*)malloc(n > 0 ? n : 1);
+  grab_all(c, coord, normal, px, py, images, n, texs, valid);
+  if (!valid[0]) {
+    for (int i = 0; i < n; ++i) out[i] = 2.0f;
+  } else {
+    for (int i = 0; i < n; ++i) {
+      if (i == 0) out[i] = 0.0f;
+      else if (valid[i]) {
+        const float d = dot_tex(texs, texs + (size_t)i * tsize, tsize);
+        out[i] = robust == 0 ? 1.0f - d : robustincc(1.0f - d);
+      } else out[i] = 2.0f;
+    }
+  }
+  free(texs); free(valid);
+}
+
+void pmvso_set_inccs_matrix(const pmvso_ctx* c, const float* coord, const float* normal, const int* images, int n, int robust, float* out) {
+  float px[4], py[4];
+  get_paxes(c, images[0], coord, normal, px, py);
+  const int tsize = 3 * c->wsize * c->wsize;
+  float* texs = alloc_texs(c, n);
+  unsigned char* valid = (unsigned char*)malloc(n > 0 ? n : 1);
+  grab_all(c, coord, normal, px, py, images, n, texs, valid);
+  for (int i = 0; i < n; ++i) {
+    out[i * n + i] = 0.0f;
+    for (int j = i + 1; j < n; ++j) {
+      float v;
+      if (valid[i] && valid[j]) {
+        const float d = dot_tex(texs + (size_t)i * tsize, texs + (size_t)j * tsize, tsize);
+        v = robust == 0 ? 1.0f - d : robustincc(1.0f - d);
+      } else v = 2.0f;
+      out[j * n + i] = out[i * n + j] = v;
+    }
+  }
+  free(texs); free(valid);
+}
+
+/* ---------------------------------------------------------------- setScales (patchOrganizerS.cpp:663-684) */
+static void set_scales(const pmvso_ctx* c, const float* coord, const int* images, int n, float* dscale_io, float* ascale) {
+  const cam_t* cam = &c->cams[images[0]];
+  const float unit = get_unit(c, images[0], coord);
+  const float unit2 = 2.0f * unit;
+  float ray[4];
+  for (int k = 0; k < 4; ++k) ray[k] = coord[k] - cam->centre[k];
+  unitize4(ray);
+  const int inum = c->tau < n ? c->tau : n;
+  float ds = *dscale_io;
+  for (int i = 1; i < inum; ++i) {
+    float a[3], b[3], t[4], d[3];
+    project(c, images[i], coord, c->level, a);
+    for (int k = 0; k < 4; ++k) t[k] = coord[k] - ray[k] * unit2;
+    project(c, images[i], t, c->level, b);
+    for (int k = 0; k < 3; ++k) d[k] = a[k] - b[k];
+    ds += norm3(d);
+  }
+  ds /= inum - 1;
+  ds = unit2 / ds;
+  *dscale_io = ds;
+  *ascale = (float)atan(ds / (unit * c->wsize / 2.0f));
+}
+void pmvso_set_scales(const pmvso_ctx* c, const float* coord, const int* images, int n, float* dscale, float* ascale) {
+  *dscale = 0.0f; /* CPatch() zero-initialises _dscale (include/pmvs/patch.hpp:24) */
+  set_scales(c, coord, images, n, dscale, ascale);
+}
+
+/* ---------------------------------------------------------------- image-set selection */
+/* optim.cpp:398-444.  No edge images in scope (getEdge == 1 when _edges is empty, photo.hpp:52-53). */
+static int add_images(const pmvso_ctx* c, const float* coord, const float* normal, int* images, int n, int cap) {
+  unsigned char used[MAXIMG_LOCAL];
+  memset(used, 0, sizeof(used));
+  for (int i = 0; i < n; ++i) used[images[i]] = 1;
+  const int ref = images[0];
+  const float athreshold = (float)cos(c->angle_threshold0); /* optim.cpp:416 narrows to float */
+  for (int k = 0; k < c->nvis2[ref]; ++k) {
+    const int im = c->vis2[ref][k];
+    if (used[im]) continue;
+    float ic[3];
+    project(c, im, coord, c->level, ic);
+    const int W = c->w[im * c->nlevels + c->level], H = c->h[im * c->nlevels + c->level];
+    if (ic[0] < 0.0f || W - 1 <= ic[0] || ic[1] < 0.0f || H - 1 <= ic[1]) continue;
+    const cam_t* cam = &c->cams[im];
+    float ray[4] = {cam->centre[0] - coord[0], cam->centre[1] - coord[1], cam->centre[2] - coord[2], cam->centre[3] - coord[3]};
+    unitize4(ray);
+    const float ftmp = dot4(ray, normal);
+    if (athreshold <= ftmp && n < cap) images[n++] = im;
+  }
+  return n;
+}
+
+/* optim.cpp:192-206 */
+static int constraint_images(const pmvso_ctx* c, const float* coord, const float* normal, int* images, int n, float ncc_threshold) {
+  float* inccs = (float*)malloc(sizeof(float) * (n > 0 ? n : 1));
+  pmvso_set_inccs(c, coord, normal, images, n, 0, inccs);
+  int m = 1;
+  for (int i = 1; i < n; ++i)
+    if (inccs[i] < 1.0f - ncc_threshold) images[m++] = images[i];
+  free(inccs);
+  return m;
+}
+
+/* optim.cpp:284-321 (newm == 1) with computeUnits 473-494 */
+static int sort_images(const pmvso_ctx* c, const float* coord, const float* normal, int* images, int n) {
+  const float threshold = (float)(1.0f - cos(10.0 * M_PI / 180.0));
+  int idx[MAXIMG_LOCAL]; float units[MAXIMG_LOCAL]; float rays[MAXIMG_LOCAL][4];
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    const cam_t* cam = &c->cams[images[i]];
+    float ray[4] = {cam->centre[0] - coord[0], cam->centre[1] - coord[1], cam->centre[2] - coord[2], cam->centre[3] - coord[3]};
+    unitize4(ray);
+    const float d = dot4(ray, normal);
+    if (d <= 0.0f) continue;
+    const float scale = get_unit(c, images[i], coord);
+    idx[m] = images[i]; units[m] = scale / d; memcpy(rays[m], ray, sizeof(ray)); ++m;
+  }
+  if (m < 2) return 0;
+  units[0] = 0.0f;
+  int out = 0;
+  while (m > 0) {
+    int best = 0;
+    for (int j = 1; j < m; ++j)
+      if (units[j] < units[best]) best = j;
+    images[out++] = idx[best];
+    float br[4]; memcpy(br, rays[best], sizeof(br));
+    int k = 0;
+    for (int j = 0; j < m; ++j) {
+      if (j == best) continue;
+      const float ftmp = fminf_(threshold, fmaxf_(threshold / 2.0f, 1.0f - dot4(br, rays[j])));
+      const float u = units[j] * (threshold / ftmp);
+      idx[k] = idx[j]; memcpy(rays[k], rays[j], sizeof(br)); units[k] = u; ++k;
+    }
+    m = k;
+  }
+  return out;
+}
+
+/* source/image/photoSetS.cpp:164-189 */
+static int check_angles(const pmvso_ctx* c, const float* coord, const int* images, int n, float min_angle, float max_angle) {
+  float rays[MAXIMG_LOCAL][4];
+  for (int i = 0; i < n; ++i) {
+    const cam_t* cam = &c->cams[images[i]];
+    for (int k = 0; k < 4; ++k) rays[i][k] = cam->centre[k] - coord[k];
+    unitize4(rays[i]);
+  }
+  int count = 0;
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j) {
+      const float d = fmaxf_(-1.0f, fminf_(1.0f, dot4(rays[i], rays[j])));
+      const float angle = (float)acos(d);
+      if (min_angle < angle && angle < max_angle) ++count;
+    }
+  return count < 1 ? 1 : 0;
+}
+
+/* optim.cpp:95-122 */
+int pmvso_pre_process(const pmvso_ctx* c, const float* coord, const float* normal, int* images, int* n, int cap,
+                      float* dscale, float* ascale) {
+  int m = *n;
+  *dscale = 0.0f; *ascale = 0.0f;
+  m = add_images(c, coord, normal, images, m, cap);
+  m = constraint_images(c, coord, normal, images, m, c->ncc_threshold_before);
+  m = sort_images(c, coord, normal, images, m);
+  if (m > 0) set_scales(c, coord, images, m, dscale, ascale);
+  *n = m;
+  if (m < c->min_image_num) return 1;
+  if (check_angles(c, coord, images, m, c->max_angle_threshold, c->angle_threshold1)) { *n = 0; return 1; }
+  return 0;
+}
+
+/* optim.cpp:124-148 */
+static int filter_images_by_angle(const pmvso_ctx* c, const float* coord, const float* normal, int* images, int n) {
+  int m = 0;
+  const double th = cos(c->angle_threshold1);
+  for (int i = 0; i < n; ++i) {
+    const cam_t* cam = &c->cams[images[i]];
+    float ray[4] = {cam->centre[0] - coord[0], cam->centre[1] - coord[1], cam->centre[2] - coord[2], cam->centre[3] - coord[3]};
+    unitize4(ray);
+    if (dot4(ray, normal) < th) {
+      if (i == 0) return 0;
+    } else images[m++] = images[i];
+  }
+  return m;
+}
+
+/* patchOrganizerS.cpp:400-414 */
+static void set_grids(const pmvso_ctx* c, const float* coord, const int* images, int n, int* grids) {
+  for (int i = 0; i < n; ++i) {
+    float ic[3];
+    project(c, images[i], coord, c->level, ic);
+    grids[2 * i] = ((int)floorf(ic[0] + 0.5f)) / c->csize;
+    grids[2 * i + 1] = ((int)floorf(ic[1] + 0.5f)) / c->csize;
+  }
+}
+
+/* optim.cpp:208-254 */
+static int set_ref_image(const pmvso_ctx* c, const float* coord, const float* normal, int* images, int n) {
+  int idx[MAXIMG_LOCAL]; int m = 0;
+  for (int i = 0; i < n; ++i)
+    if (images[i] < c->tnum) idx[m++] = images[i];
+  if (m == 0) return 0;
+  float* inccs = (float*)malloc(sizeof(float) * m * m);
+  pmvso_set_inccs_matrix(c, coord, normal, idx, m, 1, inccs);
+  int refindex = -1;
+  float refncc = INT_MAX / 2;
+  for (int i = 0; i < m; ++i) {
+    float sum = 0.0f;
+    for (int j = 0; j < m; ++j) sum += inccs[i * m + j];
+    if (sum < refncc) { refncc = sum; refindex = i; }
+  }
+  free(inccs);
+  const int refIndex = idx[refindex];
+  for (int i = 0; i < n; ++i)
+    if (images[i] == refIndex) { const int t = images[0]; images[0] = refIndex; images[i] = t; break; }
+  return n;
+}
+
+/* optim.cpp:150-190 at _depth == 0; no masks / bounding images in scope (getMask == 1) */
+int pmvso_post_process(const pmvso_ctx* c, const float* coord, const float* normal, float ncc, int* images, int* n,
+                       int cap, int* grids, int* timages, float* tmp) {
+  int m = *n;
+  *timages = 0; *tmp = 0.0f;
+  if (m < c->min_image_num) return 1;
+  m = add_images(c, coord, normal, images, m, cap);
+  m = constraint_images(c, coord, normal, images, m, c->ncc_threshold);
+  m = filter_images_by_angle(c, coord, normal, images, m);
+  *n = m;
+  if (m < c->min_image_num) return 1;
+  set_grids(c, coord, images, m, grids);
+  m = set_ref_image(c, coord, normal, images, m);
+  *n = m;
+  if (m == 0) return 1;
+  m = constraint_images(c, coord, normal, images, m, c->ncc_threshold);
+  *n = m;
+  if (m < c->min_image_num) return 1;
+  set_grids(c, coord, images, m, grids);
+  int t = 0;
+  for (int i = 0; i < m; ++i)
+    if (images[i] < c->tnum) ++t;
+  *timages = t;
+  *tmp = fmaxf_(0.0f, ncc - c->ncc_threshold) * t; /* include/pmvs/patch.hpp:48-50 score2 */
+  return 0;
+}

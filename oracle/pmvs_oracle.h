@@ -1,0 +1,71 @@
+/*
+ * oracle/pmvs_oracle.h -- TEST INFRASTRUCTURE.  CPU restatement (plain C) of the PMVS patch-optimisation
+ * hot path of /root/reference, used ONLY as the checker by tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline leg.  The product path (cmvs-pmvs_b200/csrc) never links or calls it.
+ *
+ * Pinning: checked against the reference's own objects (oracle/_ref/libpmvs_ref.so, built from
+ * /root/reference by oracle/Makefile) and against tests/golden/ vectors generated from them
+ * (tests/golden/make_golden.py).  The optimiser is oracle/nm3.h on both sides: PARITY UNPINNED for
+ * optimiser iterates (nlopt 2.6.1 LN_BOBYQA is not vendored by the reference and absent here).
+ */
+#ifndef PMVS_ORACLE_H
+#define PMVS_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pmvso_ctx pmvso_ctx;
+
+/* option values as in /root/reference/source/pmvs/option.cpp:10-28 and findMatch.cpp:30-106 */
+pmvso_ctx* pmvso_create(int num, int tnum, int level, int csize, int wsize, int min_image_num,
+                        float threshold, float max_angle_deg);
+void pmvso_destroy(pmvso_ctx* c);
+/* P: 3x4 row-major float32 as parsed from txt/%08d.txt (CONTOUR) */
+void pmvso_set_camera(pmvso_ctx* c, int index, const float* P);
+/* rgb: interleaved uint8, builds level+3 pyramid levels (image.cpp:228-325) */
+void pmvso_set_image(pmvso_ctx* c, int index, int w, int h, const unsigned char* rgb);
+/* visdata2[index] = list; default (never set) = all other images */
+void pmvso_set_visdata2(pmvso_ctx* c, int index, const int* list, int n);
+void pmvso_set_thresholds(pmvso_ctx* c, float ncc, float ncc_before);
+void pmvso_set_xtol(pmvso_ctx* c, double xtol, double step, int maxeval);
+
+void pmvso_image_dims(const pmvso_ctx* c, int index, int level, int* w, int* h);
+void pmvso_image_bytes(const pmvso_ctx* c, int index, int level, unsigned char* out);
+void pmvso_camera(const pmvso_ctx* c, int index, int level, float* P, float* centre, float* oaxis,
+                  float* xaxis, float* yaxis, float* zaxis, float* ipscale);
+
+void pmvso_project(const pmvso_ctx* c, int index, const float* coord, int level, float* out3);
+float pmvso_get_unit(const pmvso_ctx* c, int index, const float* coord);
+void pmvso_get_color(const pmvso_ctx* c, int index, float x, float y, int level, float* rgb);
+void pmvso_get_paxes(const pmvso_ctx* c, int index, const float* coord, const float* normal, float* px, float* py);
+/* returns 0 ok / 1 rejected; *newlevel gets the pyramid level that was sampled (or -1) */
+int pmvso_grab_tex(const pmvso_ctx* c, const float* coord, const float* normal, int ref, int index,
+                   float* tex, int* newlevel);
+void pmvso_normalize(float* tex, int n);
+float pmvso_dot(const float* a, const float* b, int n);
+
+void pmvso_set_scales(const pmvso_ctx* c, const float* coord, const int* images, int n, float* dscale, float* ascale);
+void pmvso_encode(const pmvso_ctx* c, const float* coord, const float* normal, const int* images, int n, float dscale, double* x);
+void pmvso_decode(const pmvso_ctx* c, const float* coord, const float* normal, const int* images, int n, float dscale,
+                  const double* x, float* ocoord, float* onormal);
+double pmvso_my_f(const pmvso_ctx* c, const float* coord, const float* normal, const int* images, int n,
+                  float dscale, const double* x);
+double pmvso_compute_incc(const pmvso_ctx* c, const float* coord, const float* normal, const int* images, int n, int robust);
+void pmvso_set_inccs(const pmvso_ctx* c, const float* coord, const float* normal, const int* images, int n, int robust, float* out);
+void pmvso_set_inccs_matrix(const pmvso_ctx* c, const float* coord, const float* normal, const int* images, int n, int robust, float* out);
+int pmvso_refine(const pmvso_ctx* c, float* coord, float* normal, const int* images, int n, float dscale, float* ncc, int* evals);
+/* OpenMP-free batched loop, `threads` pthreads; returns seconds */
+double pmvso_refine_batch(const pmvso_ctx* c, int P, int V, float* coords, float* normals, const int* images,
+                          const float* dscales, float* nccs, int* evals, unsigned char* ok, int threads);
+
+int pmvso_pre_process(const pmvso_ctx* c, const float* coord, const float* normal, int* images, int* n, int cap,
+                      float* dscale, float* ascale);
+/* postProcess at _depth == 0 (no depth maps yet): image-set selection, grids, timages, score2 */
+int pmvso_post_process(const pmvso_ctx* c, const float* coord, const float* normal, float ncc, int* images, int* n,
+                       int cap, int* grids, int* timages, float* tmp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
