@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- refined patches/sec of the PMVS patch-optimisation path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[4] on the configs[2] scene): DTU-shaped synthetic scene,
+48 calibrated views 1600x1200, pmvs level 1 / csize 2 / wsize 7 / minImageNum 3; per GPU 1 048 576 seed
+patches x 5 visible views (surface point displaced along the reference ray, normal rotated up to 20 degrees);
+one step = refinePatch + final computeINCC for every patch of the batch in ONE kernel launch.
+
+  python bench.py [--gpus N --steps K --warmup W]          the CUDA path (this repository)
+  python bench.py --impl reference [...]                   the reference's own CPU code (oracle/_ref)
+
+`value`   : whole-job patches/s with inputs resident in HBM (CUDA events around the K steps, max over ranks)
+`e2e`     : the same through pmvsb_refine_batch with pinned HOST buffers (H2D + kernel + D2H inside the timing)
+`roofline`: algorithmic gather bytes 588*V*(E+1) per patch / kernel time vs measured HBM peak
+N > 1     : patches are sharded across ranks (weak scaling: per-GPU batch fixed), images replicated, and the
+            per-wave exchange of refined patch records is an NCCL all-gather inside the step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "refined_patches_per_sec"
+UNIT = "patches/s"
+VIEWS = 5
+BYTES_PER_VIEW_EVAL = 588  # 49 bilinear samples x 4 texels x 3 B (include/image/image.hpp:467-475)
+
+
+# --------------------------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--patches", type=int, default=1 << 20, help="seed patches per GPU per step")
+    ap.add_argument("--views", type=int, default=48)
+    ap.add_argument("--width", type=int, default=1600)
+    ap.add_argument("--height", type=int, default=1200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nme in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------------------
+def build_scene(args, device):
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    synth = pkg.synth
+    scene = synth.dtu_scene(views=args.views, width=args.width, height=args.height, seed=2)
+    synth.render(scene, device=device, rows_per_chunk=400)
+    return pkg, scene
+
+
+def make_seed_patches(scene, gpu_lib, n, seed, device):
+    """Config-5 seed patches: exactly VIEWS views per patch picked with sortImages' greedy rule
+    (/root/reference/source/pmvs/optim.cpp:284-321), depth noise N(0,(2 dscale)^2) along the reference ray,
+    normal rotated by U(0,20 deg).  Returns host numpy arrays."""
+    import torch
+    import __graft_entry__ as g
+    synth = g.load_package().synth
+    pts, nrm = synth.surface_samples(scene, n, seed, device=device)
+    gen = torch.Generator(device="cpu").manual_seed(seed + 17)
+    C = torch.tensor(scene.C, dtype=torch.float64, device=device)                      # (V,3)
+    rays = C[None, :, :] - pts[:, None, :]                                              # (n,V,3)
+    dist = rays.norm(dim=2)
+    rays = rays / dist[:, :, None]
+    dots = (rays * nrm[:, None, :]).sum(2)
+    units = torch.where(dots > 0.2, dist / dots.clamp(min=1e-6), torch.full_like(dist, 1e30))
+    t = 1.0 - math.cos(math.radians(10.0))
+    ref = torch.argmin(units, dim=1)
+    units.scatter_(1, ref[:, None], 0.0)
+    chosen = []
+    for _ in range(VIEWS):
+        sel = torch.argmin(units, dim=1)
+        chosen.append(sel)
+        rs = torch.gather(rays, 1, sel[:, None, None].expand(-1, 1, 3))                # (n,1,3)
+        f = (1.0 - (rays * rs).sum(2)).clamp(min=t / 2.0, max=t)
+        units = units * (t / f)
+        units.scatter_(1, sel[:, None], 1e30)
+    images = torch.stack(chosen, dim=1).to(torch.int32).cpu().numpy()
+    coords = np.ones((n, 4), np.float32)
+    coords[:, :3] = pts.cpu().numpy()
+    dsc, _ = gpu_lib.set_scales_batch(coords, images)
+    # displace along the reference ray, rotate the normal
+    refC = scene.C[images[:, 0]]
+    ray = coords[:, :3].astype(np.float64) - refC
+    ray /= np.linalg.norm(ray, axis=1, keepdims=True)
+    noise = torch.randn(n, generator=gen, dtype=torch.float64).numpy() * 2.0 * dsc
+    coords[:, :3] = (coords[:, :3].astype(np.float64) + ray * noise[:, None]).astype(np.float32)
+    ang = torch.rand(n, generator=gen, dtype=torch.float64).numpy() * math.radians(20.0)
+    axis = torch.randn(n, 3, generator=gen, dtype=torch.float64).numpy()
+    nn = nrm.cpu().numpy()
+    axis -= (axis * nn).sum(1, keepdims=True) * nn
+    axis /= np.linalg.norm(axis, axis=1, keepdims=True)
+    rot = nn * np.cos(ang)[:, None] + axis * np.sin(ang)[:, None]
+    normals = np.zeros((n, 4), np.float32)
+    normals[:, :3] = rot
+    dsc, _ = gpu_lib.set_scales_batch(coords, images)
+    return coords, normals, images, dsc.astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU code (oracle/_ref), bounded sample per step
+# --------------------------------------------------------------------------------------------------------
+def write_scene_for_reference(scene, cpu_threads):
+    import __graft_entry__ as g
+    synth = g.load_package().synth
+    prefix = "/tmp/pmvs_b200_bench_scene_%d/" % os.getpid()
+    scene.option = dict(scene.option)
+    scene.option["CPU"] = cpu_threads
+    synth.write_scene(scene, prefix)
+    return prefix
+
+
+def reference_rate(scene, patches, seconds, steps=1, warmup=0):
+    """Times COptim::refinePatch of the reference build over a bounded sample on all host cores.
+    Returns dict(value, cores, kind, sample, ms_per_step, evals_per_patch)."""
+    from oracle import bindings as ob
+    cores = os.cpu_count() or 1
+    coords, normals, images, dsc = patches
+    kind = "reference"
+    if os.path.exists(ob.REF_SO):
+        prefix = write_scene_for_reference(scene, cores)
+        lib = ob.RefLib(prefix, num=scene.num, level=scene.option["level"])
+    else:  # the reference build did not travel: time the C port instead
+        kind = "port"
+        lib = ob.OracleLib.from_scene(scene)
+    probe = min(len(coords), 2048)
+    r = lib.refine_batch(coords[:probe], normals[:probe], images[:probe], dsc[:probe], threads=cores)
+    rate = probe / max(r["seconds"], 1e-6)
+    per_step = int(max(probe, min(len(coords), rate * seconds / max(1, steps + warmup))))
+    times, evals = [], []
+    for it in range(warmup + steps):
+        lo = (it * per_step) % max(1, len(coords) - per_step + 1)
+        r = lib.refine_batch(coords[lo:lo + per_step], normals[lo:lo + per_step], images[lo:lo + per_step], dsc[lo:lo + per_step], threads=cores)
+        if it >= warmup:
+            times.append(r["seconds"]); evals.append(float(r["evals"].mean()))
+    total = float(sum(times))
+    return dict(value=per_step * len(times) / total, cores=cores, kind=kind,
+                sample="%d of the %d bench patches per step x %d steps, COptim::refinePatch on %d host threads" % (per_step, len(coords), len(times), cores),
+                ms_per_step=1000.0 * total / len(times), evals_per_patch=float(np.mean(evals)), unit=UNIT)
+
+
+# --------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "patch-refinement microbench (BASELINE configs[4]) on the DTU-shaped synthetic scene (configs[2]): "
+                          "%d views %dx%d, level 1 csize 2 wsize 7 minImageNum 3; %d seed patches x %d views per GPU per step, "
+                          "refinePatch + computeINCC" % (args.views, args.width, args.height, args.patches, VIEWS),
+              "patches_per_gpu": args.patches, "views_per_patch": VIEWS, "optimizer": "in-kernel Nelder-Mead, xtol 1e-4, maxeval 1000",
+              "l2": "inputs larger than L2 (RGBA pyramids of 48 views = 0.49 GB + patch arrays); no explicit flush",
+              "parallelism": "patches sharded over %d GPU(s), images replicated, NCCL all-gather of refined records per step" % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import torch
+        dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+        pkg, scene = build_scene(args, dev)
+        n = min(args.patches, 1 << 16)
+        if torch.cuda.is_available():
+            lib = pkg.PmvsB200.from_scene(scene)
+            patches = make_seed_patches(scene, lib, n, seed=4, device=dev)
+            lib.close()
+        else:
+            from oracle import bindings as ob
+            orc = ob.OracleLib.from_scene(scene)
+
+            class _S:  # set_scales through the oracle when no GPU exists (CPU-only debugging)
+                def set_scales_batch(self, c, im):
+                    d = np.array([orc.set_scales(c[i], im[i])[0] for i in range(len(c))], np.float32)
+                    return d, d
+            patches = make_seed_patches(scene, _S(), n, seed=4, device=dev)
+        r = reference_rate(scene, patches, seconds=max(20.0, 8.0 * (args.steps + args.warmup)), steps=args.steps, warmup=args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                                 "evals_per_patch": r["evals_per_patch"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = "cuda:%d" % local_rank
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    pkg, scene = build_scene(args, dev)
+    lib = pkg.PmvsB200.from_scene(scene, device=local_rank)
+    P = args.patches
+    coords, normals, images, dsc = make_seed_patches(scene, lib, P, seed=4 + rank, device=dev)
+
+    # ---- resident inputs --------------------------------------------------------------------------
+    stream = torch.cuda.current_stream()
+    lib.set_stream(stream.cuda_stream)
+    d_coords0 = torch.from_numpy(coords).to(dev); d_normals0 = torch.from_numpy(normals).to(dev)
+    d_images = torch.from_numpy(images).to(dev); d_dsc = torch.from_numpy(dsc).to(dev)
+    d_coords = torch.empty_like(d_coords0); d_normals = torch.empty_like(d_normals0)
+    d_ncc = torch.empty(P, dtype=torch.float32, device=dev); d_evals = torch.empty(P, dtype=torch.int32, device=dev)
+    d_ok = torch.empty(P, dtype=torch.uint8, device=dev)
+    rec = torch.empty(P, 12, dtype=torch.float32, device=dev)          # refined record exchanged per wave
+    rec_all = torch.empty(world * P, 12, dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step_resident():
+        d_coords.copy_(d_coords0); d_normals.copy_(d_normals0)
+        lib.refine_batch_dev(P, VIEWS, d_coords.data_ptr(), d_normals.data_ptr(), d_images.data_ptr(), 0, d_dsc.data_ptr(),
+                             d_ncc.data_ptr(), d_evals.data_ptr(), d_ok.data_ptr())
+        if world > 1:
+            rec[:, 0:4] = d_coords; rec[:, 4:8] = d_normals; rec[:, 8] = d_ncc; rec[:, 9] = d_ok.to(torch.float32)
+            dist.all_gather_into_tensor(rec_all, rec)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = lib.launch_count()
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    barrier()
+    launches_before = lib.launch_count()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    launches = lib.launch_count() - launches_before
+    clocks = sampler.stop()
+    # kernel duration of the last launch (CUDA events recorded by the library on the same stream)
+    kernel_ms.append(lib.last_refine_ms())
+    evals_sum = int(d_evals.to(torch.int64).sum().item())
+    ok_frac = float(d_ok.to(torch.float32).mean().item())
+    ncc_med = float(d_ncc[d_ok.bool()].median().item()) if ok_frac > 0 else float("nan")
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * P * args.steps / (total_ms / 1000.0)
+
+    # ---- end to end through the host-pointer ABI call ------------------------------------------------
+    h_coords = torch.from_numpy(coords).pin_memory(); h_normals = torch.from_numpy(normals).pin_memory()
+    h_images = torch.from_numpy(images).pin_memory(); h_dsc = torch.from_numpy(dsc).pin_memory()
+    w_coords = torch.empty_like(h_coords).pin_memory(); w_normals = torch.empty_like(h_normals).pin_memory()
+    h_ncc = torch.empty(P, dtype=torch.float32).pin_memory(); h_evals = torch.empty(P, dtype=torch.int32).pin_memory()
+    h_ok = torch.empty(P, dtype=torch.uint8).pin_memory()
+    import ctypes as C
+    vp = lambda tns: C.c_void_p(tns.data_ptr())
+
+    def step_e2e():
+        w_coords.copy_(h_coords); w_normals.copy_(h_normals)      # host-side reset of the in/out arrays
+        r = lib.lib.pmvsb_refine_batch(lib.ctx, P, VIEWS, vp(w_coords), vp(w_normals), vp(h_images), None, vp(h_dsc), vp(h_ncc),
+                                       vp(h_evals), vp(h_ok))
+        if r != 0:
+            raise RuntimeError(lib.lib.pmvsb_last_error(lib.ctx).decode())
+
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * P * e2e_steps / float(t.item())
+    h2d = P * (16 + 16 + 4 * VIEWS + 4)
+    d2h = P * (16 + 16 + 4 + 4 + 1)
+
+    # ---- roofline of the dominant kernel (k_refine) ----------------------------------------------------
+    peak, peak_kind = peaks()
+    alg_bytes = BYTES_PER_VIEW_EVAL * VIEWS * (evals_sum + P)          # 588 * V * (E + 1) summed over the launch
+    k_ms = float(np.mean(kernel_ms))
+    achieved = alg_bytes / (k_ms / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_refine<7>", "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth",
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "kernel_ms": k_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "evals_per_patch": evals_sum / P,
+                "note": "algorithmic bytes = 588 B x views x (evaluations + 1) per patch (SURVEY.md 8d); most gathers hit L1/L2, "
+                        "so HBM traffic is far below this figure and the kernel is FP32/issue bound"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": int(launches), "roofline": roofline,
+            "quality": {"ok_fraction": ok_frac, "median_ncc": ncc_med}}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n = min(P, 1 << 16)
+        r = reference_rate(scene, (coords[:n], normals[:n], images[:n], dsc[:n]), seconds=args.cpu_seconds)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                                "evals_per_patch": r["evals_per_patch"]}
+    if rank == 0:
+        print(json.dumps(line))
+    lib.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

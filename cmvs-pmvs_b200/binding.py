@@ -1,0 +1,212 @@
+"""ctypes binding of the C ABI in include/pmvs_b200.h (cmvs-pmvs_b200/lib/libpmvs_b200.so).
+
+This is plumbing for tests/, bench.py and __graft_entry__: it only marshals numpy arrays (or raw device
+pointers) into the library.  There is no fallback: if the CUDA library is missing, or no CUDA device can be
+opened, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libpmvs_b200.so")
+
+# every symbol include/pmvs_b200.h declares
+SYMBOLS = [
+    "pmvsb_create", "pmvsb_destroy", "pmvsb_last_error", "pmvsb_version", "pmvsb_upload_camera", "pmvsb_upload_image",
+    "pmvsb_set_visdata2", "pmvsb_finalize_scene", "pmvsb_set_thresholds", "pmvsb_set_optimizer", "pmvsb_image_dims",
+    "pmvsb_download_image", "pmvsb_get_camera", "pmvsb_project_batch", "pmvsb_grab_tex_batch", "pmvsb_eval_objective_batch",
+    "pmvsb_compute_incc_batch", "pmvsb_set_inccs_batch", "pmvsb_set_scales_batch", "pmvsb_refine_batch",
+    "pmvsb_refine_batch_dev", "pmvsb_sync", "pmvsb_stream", "pmvsb_set_stream", "pmvsb_launch_count", "pmvsb_last_refine_ms",
+]
+
+
+class PmvsError(RuntimeError):
+    pass
+
+
+def load_library() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise PmvsError("CUDA library not built: %s (run `python -c 'import __graft_entry__ as g; g.build()'`)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.pmvsb_last_error.restype = C.c_char_p
+    lib.pmvsb_version.restype = C.c_char_p
+    lib.pmvsb_stream.restype = C.c_void_p
+    lib.pmvsb_launch_count.restype = C.c_uint64
+    lib.pmvsb_last_refine_ms.restype = C.c_float
+    return lib
+
+
+def _vp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+def _patch_arrays(coords, normals, images, nimages=None, dscales=None):
+    coords = _f32(coords).reshape(-1, 4)
+    P = coords.shape[0]
+    normals = None if normals is None else _f32(normals).reshape(P, 4)
+    images = np.ascontiguousarray(images, dtype=np.int32)
+    if images.ndim != 2 or images.shape[0] != P:
+        images = images.reshape(P, -1) if P else images.reshape(0, max(1, images.shape[-1] if images.ndim else 1))
+    nimages = None if nimages is None else np.ascontiguousarray(nimages, dtype=np.int32).reshape(P)
+    dscales = None if dscales is None else _f32(dscales).reshape(P)
+    return P, images.shape[1], coords, normals, images, nimages, dscales
+
+
+class PmvsB200:
+    """One context = one GPU holding the image pyramids and camera tables of one scene."""
+
+    def __init__(self, num_images, num_target=None, level=1, csize=2, wsize=7, min_image_num=3, threshold=0.7,
+                 max_angle_deg=10.0, device=0):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        r = self.lib.pmvsb_create(C.byref(self.ctx), device, num_images, num_images if num_target is None else num_target,
+                                  level, csize, wsize, min_image_num, C.c_float(threshold), C.c_float(max_angle_deg))
+        if r != 0:
+            self.ctx = None
+            raise PmvsError("pmvsb_create failed (%d): no CUDA device or bad arguments -- there is no CPU fallback" % r)
+        self.num = num_images
+        self.level = level
+        self.wsize = wsize
+        self.tau = min(2 * min_image_num, num_images)
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _ck(self, r):
+        if r != 0:
+            raise PmvsError("pmvs_b200 error %d: %s" % (r, self.lib.pmvsb_last_error(self.ctx).decode()))
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.pmvsb_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @classmethod
+    def from_scene(cls, scene, device=0):
+        o = scene.option
+        self = cls(scene.num, level=o["level"], csize=o["csize"], wsize=o["wsize"], min_image_num=o["minImageNum"],
+                   threshold=o["threshold"], device=device)
+        for i in range(scene.num):
+            self.upload_camera(i, scene.P[i])
+            self.upload_image(i, scene.images[i])
+        self.finalize_scene()
+        return self
+
+    # -- scene -------------------------------------------------------------------------------------
+    def upload_camera(self, index, P):
+        P = _f32(P).reshape(12)
+        self._ck(self.lib.pmvsb_upload_camera(self.ctx, int(index), _vp(P)))
+
+    def upload_image(self, index, rgb):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        self._ck(self.lib.pmvsb_upload_image(self.ctx, int(index), rgb.shape[1], rgb.shape[0], _vp(rgb)))
+
+    def finalize_scene(self):
+        self._ck(self.lib.pmvsb_finalize_scene(self.ctx))
+
+    def set_thresholds(self, ncc, ncc_before):
+        self._ck(self.lib.pmvsb_set_thresholds(self.ctx, C.c_float(ncc), C.c_float(ncc_before)))
+
+    def set_optimizer(self, xtol=1e-4, step=1.0, maxeval=1000):
+        self._ck(self.lib.pmvsb_set_optimizer(self.ctx, C.c_double(xtol), C.c_double(step), int(maxeval)))
+
+    def image(self, index, level):
+        w, h = C.c_int(), C.c_int()
+        self._ck(self.lib.pmvsb_image_dims(self.ctx, int(index), level, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value, 3), np.uint8)
+        self._ck(self.lib.pmvsb_download_image(self.ctx, int(index), level, _vp(out)))
+        return out
+
+    def camera(self, index, level=0):
+        P = np.zeros(12, np.float32); ce = np.zeros(4, np.float32); oa = np.zeros(4, np.float32)
+        xa = np.zeros(3, np.float32); ya = np.zeros(3, np.float32); za = np.zeros(3, np.float32); ips = C.c_float()
+        self._ck(self.lib.pmvsb_get_camera(self.ctx, int(index), level, _vp(P), _vp(ce), _vp(oa), _vp(xa), _vp(ya), _vp(za), C.byref(ips)))
+        return dict(P=P.reshape(3, 4), centre=ce, oaxis=oa, xaxis=xa, yaxis=ya, zaxis=za, ipscale=np.float32(ips.value))
+
+    # -- batched calls (host arrays) -----------------------------------------------------------------
+    def project_batch(self, coords, image, level):
+        coords = _f32(coords).reshape(-1, 4)
+        image = np.ascontiguousarray(image, dtype=np.int32).reshape(-1)
+        out = np.zeros((coords.shape[0], 3), np.float32)
+        self._ck(self.lib.pmvsb_project_batch(self.ctx, coords.shape[0], _vp(coords), _vp(image), level, _vp(out)))
+        return out
+
+    def grab_tex_batch(self, coords, normals, images, nimages=None):
+        P, stride, coords, normals, images, nimages, _ = _patch_arrays(coords, normals, images, nimages)
+        tsz = 3 * self.wsize * self.wsize
+        tex = np.zeros((P, stride, tsz), np.float32); flag = np.zeros((P, stride), np.int32); nl = np.zeros((P, stride), np.int32)
+        self._ck(self.lib.pmvsb_grab_tex_batch(self.ctx, P, stride, _vp(coords), _vp(normals), _vp(images), _vp(nimages),
+                                               _vp(tex), _vp(flag), _vp(nl)))
+        return tex, flag, nl
+
+    def eval_objective_batch(self, coords, normals, images, dscales, x, nimages=None):
+        P, stride, coords, normals, images, nimages, dscales = _patch_arrays(coords, normals, images, nimages, dscales)
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(P, 3)
+        f = np.zeros(P, np.float64)
+        self._ck(self.lib.pmvsb_eval_objective_batch(self.ctx, P, stride, _vp(coords), _vp(normals), _vp(images), _vp(nimages),
+                                                     _vp(dscales), _vp(x), _vp(f)))
+        return f
+
+    def compute_incc_batch(self, coords, normals, images, robust=1, nimages=None):
+        P, stride, coords, normals, images, nimages, _ = _patch_arrays(coords, normals, images, nimages)
+        out = np.zeros(P, np.float64)
+        self._ck(self.lib.pmvsb_compute_incc_batch(self.ctx, P, stride, _vp(coords), _vp(normals), _vp(images), _vp(nimages),
+                                                   int(robust), _vp(out)))
+        return out
+
+    def set_inccs_batch(self, coords, normals, images, robust=0, nimages=None):
+        P, stride, coords, normals, images, nimages, _ = _patch_arrays(coords, normals, images, nimages)
+        out = np.zeros((P, stride), np.float32)
+        self._ck(self.lib.pmvsb_set_inccs_batch(self.ctx, P, stride, _vp(coords), _vp(normals), _vp(images), _vp(nimages),
+                                                int(robust), _vp(out)))
+        return out
+
+    def set_scales_batch(self, coords, images, nimages=None):
+        P, stride, coords, _, images, nimages, _ = _patch_arrays(coords, None, images, nimages)
+        d = np.zeros(P, np.float32); a = np.zeros(P, np.float32)
+        self._ck(self.lib.pmvsb_set_scales_batch(self.ctx, P, stride, _vp(coords), _vp(images), _vp(nimages), _vp(d), _vp(a)))
+        return d, a
+
+    def refine_batch(self, coords, normals, images, dscales, nimages=None):
+        """-> dict(coords, normals, ncc, evals, ok); inputs are not modified."""
+        P, stride, coords, normals, images, nimages, dscales = _patch_arrays(coords, normals, images, nimages, dscales)
+        co = coords.copy(); no = normals.copy()
+        ncc = np.zeros(P, np.float32); ev = np.zeros(P, np.int32); ok = np.zeros(P, np.uint8)
+        self._ck(self.lib.pmvsb_refine_batch(self.ctx, P, stride, _vp(co), _vp(no), _vp(images), _vp(nimages), _vp(dscales),
+                                             _vp(ncc), _vp(ev), _vp(ok)))
+        return dict(coords=co, normals=no, ncc=ncc, evals=ev, ok=ok)
+
+    # -- device-pointer path (bench / multi-GPU plumbing) ------------------------------------------------
+    def refine_batch_dev(self, P, stride, d_coords, d_normals, d_images, d_nimages, d_dscales, d_ncc, d_evals, d_ok):
+        """All arguments are integer device addresses (e.g. torch.Tensor.data_ptr()); asynchronous."""
+        p = lambda v: C.c_void_p(int(v)) if v else None
+        self._ck(self.lib.pmvsb_refine_batch_dev(self.ctx, int(P), int(stride), p(d_coords), p(d_normals), p(d_images), p(d_nimages),
+                                                 p(d_dscales), p(d_ncc), p(d_evals), p(d_ok)))
+
+    def sync(self):
+        self._ck(self.lib.pmvsb_sync(self.ctx))
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self.lib.pmvsb_set_stream(self.ctx, C.c_void_p(int(cuda_stream)) if cuda_stream else None))
+
+    def stream(self) -> int:
+        return int(self.lib.pmvsb_stream(self.ctx) or 0)
+
+    def launch_count(self) -> int:
+        return int(self.lib.pmvsb_launch_count(self.ctx))
+
+    def last_refine_ms(self) -> float:
+        return float(self.lib.pmvsb_last_refine_ms(self.ctx))

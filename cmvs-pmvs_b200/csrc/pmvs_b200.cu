@@ -1,0 +1,896 @@
+// cmvs-pmvs_b200/csrc/pmvs_b200.cu -- kernels + C ABI (include/pmvs_b200.h) for sm_100a.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false (see __graft_entry__.build).
+// No CPU fallback: every entry point needs a live CUDA context.
+#include "../../include/pmvs_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pmvs_device.cuh"
+
+using namespace pmvsb;
+
+// =====================================================================================================
+// kernels
+// =====================================================================================================
+namespace {
+
+// interleaved RGB (host layout, CImage::_images) -> RGBA8 words
+__global__ void k_rgb_to_rgba(const uint8_t* __restrict__ rgb, uchar4* __restrict__ out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint8_t* p = rgb + 3 * i;
+    out[i] = make_uchar4(p[0], p[1], p[2], 0);
+  }
+}
+__global__ void k_rgba_to_rgb(const uchar4* __restrict__ in, uint8_t* __restrict__ rgb, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uchar4 v = in[i];
+    rgb[3 * i] = v.x; rgb[3 * i + 1] = v.y; rgb[3 * i + 2] = v.z;
+  }
+}
+
+// K1: one pyramid level (CImage::buildImage, source/image/image.cpp:228-325, filter 0).
+// Weights [1 3 3 1]^2/64 in double with renormalisation over the taps inside the source; all partial
+// sums are exact dyadic rationals, so (unsigned char)(int)floor(sum/denom + 0.5f) == (2S + D) / (2D)
+// in integers.  One thread per output pixel; rows of the source are read as coalesced uchar4.
+__global__ void k_pyr_down(const uchar4* __restrict__ src, int sw, int sh, uchar4* __restrict__ dst, int dw, int dh) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dw || y >= dh) return;
+  const int wt[4] = {1, 3, 3, 1};
+  int S0 = 0, S1 = 0, S2 = 0, D = 0;
+#pragma unroll
+  for (int j = -1; j < 3; ++j) {
+    const int yt = 2 * y + j;
+    if (yt < 0 || sh - 1 < yt) continue;
+#pragma unroll
+    for (int i = -1; i < 3; ++i) {
+      const int xt = 2 * x + i;
+      if (xt < 0 || sw - 1 < xt) continue;
+      const int k = wt[j + 1] * wt[i + 1];
+      const uchar4 p = __ldg(src + (size_t)yt * sw + xt);
+      S0 += k * p.x; S1 += k * p.y; S2 += k * p.z;
+      D += k;
+    }
+  }
+  dst[(size_t)y * dw + x] = make_uchar4((unsigned char)((2 * S0 + D) / (2 * D)), (unsigned char)((2 * S1 + D) / (2 * D)),
+                                        (unsigned char)((2 * S2 + D) / (2 * D)), 0);
+}
+
+__global__ void k_project(SceneDev s, int n, const float* __restrict__ coords, const int32_t* __restrict__ image, int level,
+                          float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  CamDev cam;
+  load_cam(s, image[i], cam);
+  // s.cams holds P at the working level; other levels scale rows 0,1 by exact powers of two (camera.cpp:56-68)
+  const int dl = level - s.level;
+  const float sc = dl >= 0 ? 1.0f / (float)(1 << dl) : (float)(1 << (-dl));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { cam.P[0][k] *= sc; cam.P[1][k] *= sc; }
+  const float X[4] = {coords[4 * i], coords[4 * i + 1], coords[4 * i + 2], coords[4 * i + 3]};
+  float o[3];
+  project(cam, X, o);
+  out[3 * i] = o[0]; out[3 * i + 1] = o[1]; out[3 * i + 2] = o[2];
+}
+
+__device__ __forceinline__ void load_patch(const float* coords, const float* normals, int p, float* coord, float* normal) {
+  const float4 c = __ldg(reinterpret_cast<const float4*>(coords) + p);
+  const float4 n = __ldg(reinterpret_cast<const float4*>(normals) + p);
+  coord[0] = c.x; coord[1] = c.y; coord[2] = c.z; coord[3] = c.w;
+  normal[0] = n.x; normal[1] = n.y; normal[2] = n.z; normal[3] = n.w;
+}
+
+// parity hook: raw textures per (patch, view).  One warp per patch.
+template <int WSIZE>
+__global__ void k_grab_tex(SceneDev s, int P, int stride, const float* __restrict__ coords, const float* __restrict__ normals,
+                           const int32_t* __restrict__ images, const int32_t* __restrict__ nimages, float* __restrict__ tex,
+                           int32_t* __restrict__ flag, int32_t* __restrict__ newlevel) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= P) return;
+  const int p = warp;
+  float coord[4], normal[4];
+  load_patch(coords, normals, p, coord, normal);
+  const int n = nimages ? min(nimages[p], stride) : stride;
+  const int32_t* im = images + (size_t)p * stride;
+  CamDev refcam;
+  load_cam(s, im[0], refcam);
+  float px[4], py[4];
+  get_paxes(refcam, s.level, coord, normal, px, py);
+  constexpr int N = WSIZE * WSIZE;
+  for (int v = 0; v < n; ++v) {
+    CamDev cam;
+    load_cam(s, im[v], cam);
+    const ViewWin w = view_window<WSIZE>(s, cam, im[v], coord, px, py, normal);
+    if (lane == 0) {
+      flag[(size_t)p * stride + v] = w.newlevel >= 0 ? 0 : 1;
+      newlevel[(size_t)p * stride + v] = w.newlevel;
+    }
+    if (w.newlevel < 0) continue;
+    WarpTex<WSIZE> t;
+    grab_and_normalize<WSIZE>(s, im[v], w, lane, t, false);
+    float* o = tex + ((size_t)p * stride + v) * (3 * N);
+#pragma unroll
+    for (int j = 0; j < WarpTex<WSIZE>::J; ++j) {
+      const int ti = lane + 32 * j;
+      if (ti < N) { o[3 * ti] = t.v[j][0]; o[3 * ti + 1] = t.v[j][1]; o[3 * ti + 2] = t.v[j][2]; }
+    }
+  }
+}
+
+// my_f / computeINCC hooks.  mode 0: my_f(x); 1/2: computeINCC robust / plain.
+template <int WSIZE>
+__global__ void k_score(SceneDev s, int P, int stride, const float* __restrict__ coords, const float* __restrict__ normals,
+                        const int32_t* __restrict__ images, const int32_t* __restrict__ nimages, const float* __restrict__ dscales,
+                        const double* __restrict__ xs, int mode, double* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= P) return;
+  const int p = warp;
+  float coord[4], normal[4];
+  load_patch(coords, normals, p, coord, normal);
+  const int n = nimages ? min(nimages[p], stride) : stride;
+  PatchCtx pc;
+  CamDev refcam;
+  patch_ctx_init(s, pc, coord, normal, images + (size_t)p * stride, n, dscales ? dscales[p] : 1.0f, lane, refcam);
+  double f;
+  if (mode == 0) {
+    const double x[3] = {xs[3 * p], xs[3 * p + 1], xs[3 * p + 2]};
+    f = objective<WSIZE>(s, pc, refcam, x, lane);
+  } else {
+    f = n < 2 ? 2.0 : photo_score<WSIZE>(s, pc, refcam, coord, normal, lane, mode);
+  }
+  if (lane == 0) out[p] = f;
+}
+
+// COptim::setINCCs, vector form (optim.cpp:709-744) over ALL images of the patch (not capped at tau).
+template <int WSIZE>
+__global__ void k_set_inccs(SceneDev s, int P, int stride, const float* __restrict__ coords, const float* __restrict__ normals,
+                            const int32_t* __restrict__ images, const int32_t* __restrict__ nimages, int robust,
+                            float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= P) return;
+  const int p = warp;
+  float coord[4], normal[4];
+  load_patch(coords, normals, p, coord, normal);
+  const int n = nimages ? min(nimages[p], stride) : stride;
+  const int32_t* im = images + (size_t)p * stride;
+  float* o = out + (size_t)p * stride;
+  if (n <= 0) return;
+  CamDev refcam;
+  load_cam(s, im[0], refcam);
+  float px[4], py[4];
+  get_paxes(refcam, s.level, coord, normal, px, py);
+  WarpTex<WSIZE> ref, cur;
+  const ViewWin w0 = view_window<WSIZE>(s, refcam, im[0], coord, px, py, normal);
+  if (w0.newlevel < 0) {
+    for (int v = lane; v < n; v += 32) o[v] = 2.0f;
+    return;
+  }
+  grab_and_normalize<WSIZE>(s, im[0], w0, lane, ref);
+  if (lane == 0) o[0] = 0.0f;
+  for (int v = 1; v < n; ++v) {
+    CamDev cam;
+    load_cam(s, im[v], cam);
+    const ViewWin w = view_window<WSIZE>(s, cam, im[v], coord, px, py, normal);
+    float r = 2.0f;
+    if (w.newlevel >= 0) {
+      grab_and_normalize<WSIZE>(s, im[v], w, lane, cur);
+      const float d = tex_dot<WSIZE>(ref, cur);
+      r = robust ? robustincc(1.0f - d) : 1.0f - d;
+    }
+    if (lane == 0) o[v] = r;
+  }
+}
+
+// CPatchOrganizerS::setScales (patchOrganizerS.cpp:663-684); one thread per patch.
+__global__ void k_set_scales(SceneDev s, int P, int stride, const float* __restrict__ coords, const int32_t* __restrict__ images,
+                             const int32_t* __restrict__ nimages, float* __restrict__ dscale, float* __restrict__ ascale) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float coord[4] = {coords[4 * p], coords[4 * p + 1], coords[4 * p + 2], coords[4 * p + 3]};
+  const int n = nimages ? min(nimages[p], stride) : stride;
+  const int32_t* im = images + (size_t)p * stride;
+  CamDev cam;
+  load_cam(s, im[0], cam);
+  const float unit = get_unit(cam, s.level, coord);
+  const float unit2 = 2.0f * unit;
+  float ray[4] = {coord[0] - cam.centre[0], coord[1] - cam.centre[1], coord[2] - cam.centre[2], coord[3] - cam.centre[3]};
+  unitize4(ray);
+  const int inum = s.tau < n ? s.tau : n;
+  float ds = 0.0f;
+  for (int i = 1; i < inum; ++i) {
+    load_cam(s, im[i], cam);
+    float a[3], b[3];
+    project(cam, coord, a);
+    const float t[4] = {coord[0] - ray[0] * unit2, coord[1] - ray[1] * unit2, coord[2] - ray[2] * unit2, coord[3] - ray[3] * unit2};
+    project(cam, t, b);
+    const float d[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+    ds += sqrtf(dot3(d, d));
+  }
+  ds /= (float)(inum - 1);
+  ds = unit2 / ds;
+  dscale[p] = ds;
+  ascale[p] = (float)atan((double)(ds / (unit * (float)s.wsize / 2.0f)));
+}
+
+// K3: COptim::refinePatch for a whole frontier.  Persistent warps pull patches from a global counter
+// (evaluation counts differ 2x between patches, so static assignment would leave SMs idle at the tail).
+template <int WSIZE>
+__global__ void __launch_bounds__(128) k_refine(SceneDev s, int P, int stride, float* __restrict__ coords, float* __restrict__ normals,
+                                                const int32_t* __restrict__ images, const int32_t* __restrict__ nimages,
+                                                const float* __restrict__ dscales, float* __restrict__ ncc_out,
+                                                int32_t* __restrict__ evals_out, uint8_t* __restrict__ ok_out,
+                                                int* __restrict__ counter) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    int p = 0;
+    if (lane == 0) p = atomicAdd(counter, 1);
+    p = __shfl_sync(kFull, p, 0);
+    if (p >= P) return;
+
+    float coord[4], normal[4];
+    load_patch(coords, normals, p, coord, normal);
+    const int n = nimages ? min(nimages[p], stride) : stride;
+    PatchCtx pc;
+    CamDev refcam;
+    patch_ctx_init(s, pc, coord, normal, images + (size_t)p * stride, n, dscales[p], lane, refcam);
+
+    double x[3];
+    encode(s, pc, refcam, coord, normal, x);
+    // NLOPT refuses a start outside the box; the reference clamps first (optim.cpp:629-634)
+    x[1] = clampd(x[1], -23.99999, 23.99999);
+    x[2] = clampd(x[2], -23.99999, 23.99999);
+    int evals = 0;
+    const bool ok = nelder_mead3<WSIZE>(s, pc, refcam, lane, x, evals);
+    float ncc = -1.0f;
+    if (ok) {
+      decode(s, pc, refcam, x, lane, coord, normal);
+      const double incc = n < 2 ? 2.0 : photo_score<WSIZE>(s, pc, refcam, coord, normal, lane, 1);
+      ncc = (float)(1.0 - (double)unrobustincc((float)incc));  // optim.cpp:652
+      if (lane == 0) {
+        reinterpret_cast<float4*>(coords)[p] = make_float4(coord[0], coord[1], coord[2], coord[3]);
+        reinterpret_cast<float4*>(normals)[p] = make_float4(normal[0], normal[1], normal[2], normal[3]);
+      }
+    }
+    if (lane == 0) {
+      ncc_out[p] = ncc;
+      evals_out[p] = evals;
+      ok_out[p] = ok ? 1 : 0;
+    }
+  }
+}
+
+}  // namespace
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+struct HostCam {
+  float P0[3][4];
+  float centre[4], oaxis[4], xaxis[3], yaxis[3], zaxis[3], ipscale;
+  bool set = false;
+};
+struct HostImage {
+  std::vector<uchar4*> levels;
+  std::vector<int> w, h;
+  bool set = false;
+};
+
+struct pmvsb_ctx {
+  int device = 0;
+  int num = 0, tnum = 0, level = 1, csize = 2, wsize = 7, min_image_num = 3, tau = 0, nlevels = 0;
+  float threshold = 0.7f, ncc_threshold = 0.7f, ncc_threshold_before = 0.4f;
+  float angle_threshold0 = 0, angle_threshold1 = 0, max_angle_threshold = 0;
+  double xtol = 1.0e-4, step = 1.0;
+  int maxeval = 1000;
+  std::vector<HostCam> cams;
+  std::vector<HostImage> images;
+  std::vector<std::vector<int32_t>> visdata2;
+  CamDev* d_cams = nullptr;
+  LevelDev* d_levels = nullptr;
+  int* d_counter = nullptr;
+  bool finalized = false;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool refine_timed = false;
+  int sm_count = 148;
+  int refine_blocks_per_sm = 0;
+  uint64_t launches = 0;
+  std::string err;
+  SceneDev scene;
+};
+
+namespace {
+
+int fail(pmvsb_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, PMVSB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+// ---- host camera maths (CCamera::updateCamera, getOpticalCenter; COptim::setAxesScales) ----------
+float h_dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+float h_dot4(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3]; }
+void h_cross3(const float* u, const float* v, float* o) {
+  o[0] = u[1] * v[2] - v[1] * u[2];
+  o[1] = -u[0] * v[2] + v[0] * u[2];
+  o[2] = u[0] * v[1] - v[0] * u[1];
+}
+void h_unitize3(float* v) {
+  const float l = h_dot3(v, v);
+  if (l != 1.0f && l != 0.0f) {
+    const float s = std::sqrt(l);
+    v[0] /= s; v[1] /= s; v[2] /= s;
+  }
+}
+void d_cross3(const double* u, const double* v, double* o) {
+  o[0] = u[1] * v[2] - v[1] * u[2];
+  o[1] = -u[0] * v[2] + v[0] * u[2];
+  o[2] = u[0] * v[1] - v[0] * u[1];
+}
+
+void derive_camera(HostCam& c) {
+  // optical axis: third row, xyz normalised, w scaled alike (source/image/camera.cpp:112-118)
+  float oa[4] = {c.P0[2][0], c.P0[2][1], c.P0[2][2], 0.0f};
+  const float len = std::sqrt(h_dot4(oa, oa));
+  oa[3] = c.P0[2][3];
+  for (int k = 0; k < 4; ++k) c.oaxis[k] = oa[k] / len;
+  // optical centre (camera.cpp:138-175)
+  if (c.P0[2][0] == 0.0f && c.P0[2][1] == 0.0f && c.P0[2][2] == 0.0f) {
+    float v2[3];
+    h_cross3(c.P0[0], c.P0[1], v2);
+    h_unitize3(v2);
+    c.centre[0] = v2[0]; c.centre[1] = v2[1]; c.centre[2] = v2[2]; c.centre[3] = 0.0f;
+  } else {
+    double A[3][3], b[3], adj[3][3];
+    for (int y = 0; y < 3; ++y) {
+      for (int x = 0; x < 3; ++x) A[y][x] = c.P0[y][x];
+      b[y] = -c.P0[y][3];
+    }
+    d_cross3(A[1], A[2], adj[0]);
+    d_cross3(A[2], A[0], adj[1]);
+    d_cross3(A[0], A[1], adj[2]);
+    const double det = adj[0][0] * A[0][0] + adj[0][1] * A[0][1] + adj[0][2] * A[0][2];
+    for (int y = 0; y < 3; ++y) {
+      const double r0 = adj[0][y] / det, r1 = adj[1][y] / det, r2 = adj[2][y] / det;  // row y of inverse
+      c.centre[y] = (float)(r0 * b[0] + r1 * b[1] + r2 * b[2]);
+    }
+    c.centre[3] = 1.0f;
+  }
+  // optimiser axes and image-plane scale (source/pmvs/optim.cpp:43-64)
+  c.zaxis[0] = c.oaxis[0]; c.zaxis[1] = c.oaxis[1]; c.zaxis[2] = c.oaxis[2];
+  const float xa[3] = {c.P0[0][0], c.P0[0][1], c.P0[0][2]};
+  h_cross3(c.zaxis, xa, c.yaxis);
+  h_unitize3(c.yaxis);
+  h_cross3(c.yaxis, c.zaxis, c.xaxis);
+  const float xe[4] = {c.xaxis[0], c.xaxis[1], c.xaxis[2], 0.0f};
+  const float ye[4] = {c.yaxis[0], c.yaxis[1], c.yaxis[2], 0.0f};
+  c.ipscale = h_dot4(xe, c.P0[0]) + h_dot4(ye, c.P0[1]);
+}
+
+// the reference's pyramid-level decision for one ratio (optim.cpp:813, 831-835), host libm
+int leveldif_of(float ratio, int level) {
+  static const float Log2 = (float)std::log(2.0);
+  const double lv = std::floor(std::log((double)ratio) / (double)Log2 + 0.5);
+  int ld;
+  if (!(lv > -1.0e9) || lv > 1.0e9) ld = INT32_MIN;  // what cvttsd2si yields for -inf / NaN / overflow
+  else ld = (int)lv;
+  ld = ld < 2 ? ld : 2;
+  ld = -level < ld ? ld : -level;
+  return ld;
+}
+// smallest positive float whose decision is >= target (decision is monotone in ratio)
+float level_threshold(int target, int level) {
+  uint32_t lo = 0x00000001u, hi = 0x7f7fffffu;  // positive finite floats are ordered like their bits
+  auto val = [](uint32_t b) { float f; std::memcpy(&f, &b, 4); return f; };
+  if (leveldif_of(val(hi), level) < target) return INFINITY;
+  while (lo < hi) {
+    const uint32_t mid = lo + (hi - lo) / 2;
+    if (leveldif_of(val(mid), level) >= target) hi = mid; else lo = mid + 1;
+  }
+  return val(lo);
+}
+
+void fill_scene(pmvsb_ctx* c) {
+  SceneDev& s = c->scene;
+  s.cams = c->d_cams;
+  s.levels = c->d_levels;
+  s.num = c->num; s.tnum = c->tnum; s.level = c->level; s.nlevels = c->nlevels; s.csize = c->csize;
+  s.wsize = c->wsize; s.tau = c->tau; s.min_image_num = c->min_image_num;
+  // weight < cos(angleThreshold1) with a double right-hand side <=> weight < smallest float >= that double
+  const double ca = std::cos((double)c->angle_threshold1);
+  float cf = (float)ca;
+  if ((double)cf < ca) cf = std::nextafterf(cf, INFINITY);
+  s.cos_angle1 = cf;
+  s.n_level_thr = c->level + 2;
+  for (int k = 0; k < kMaxLevels; ++k) s.level_thr[k] = INFINITY;
+  for (int k = 0; k < s.n_level_thr && k < kMaxLevels; ++k) s.level_thr[k] = level_threshold(-c->level + k + 1, c->level);
+  s.ascale = (float)(M_PI / 48.0f);
+  s.xtol = c->xtol; s.step = c->step; s.maxeval = c->maxeval;
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, sizeof(T) * (n ? n : 1)); }
+};
+
+int check_ready(pmvsb_ctx* ctx) {
+  if (!ctx) return PMVSB_EINVAL;
+  if (!ctx->finalized) return fail(ctx, PMVSB_ESTATE, "scene not finalised: call pmvsb_finalize_scene first");
+  if (ctx->wsize != 7 && ctx->wsize != 5 && ctx->wsize != 9) return fail(ctx, PMVSB_EINVAL, "wsize must be 5, 7 or 9");
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return fail(ctx, PMVSB_ECUDA, cudaGetErrorString(e));
+  return PMVSB_OK;
+}
+
+#define DISPATCH_WSIZE(ctx, KERNEL, grid, block, ...)                                           \
+  do {                                                                                          \
+    switch ((ctx)->wsize) {                                                                     \
+      case 5: KERNEL<5><<<grid, block, 0, (ctx)->stream>>>(__VA_ARGS__); break;                 \
+      case 9: KERNEL<9><<<grid, block, 0, (ctx)->stream>>>(__VA_ARGS__); break;                 \
+      default: KERNEL<7><<<grid, block, 0, (ctx)->stream>>>(__VA_ARGS__); break;                \
+    }                                                                                           \
+    ++(ctx)->launches;                                                                          \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+const char* pmvsb_version(void) { return "pmvs-b200 0.1 (sm_100a)"; }
+
+const char* pmvsb_last_error(const pmvsb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int pmvsb_create(pmvsb_ctx** out, int device, int num_images, int num_target, int level, int csize, int wsize,
+                 int min_image_num, float threshold, float max_angle_deg) {
+  if (!out) return PMVSB_EINVAL;
+  *out = nullptr;
+  if (num_images < 1 || num_target < 1 || num_target > num_images || level < 0 || level > 5 || csize < 1 ||
+      min_image_num < 2 || (wsize != 5 && wsize != 7 && wsize != 9))
+    return PMVSB_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return PMVSB_ECUDA;
+  pmvsb_ctx* ctx = new pmvsb_ctx();
+  ctx->device = device;
+  ctx->num = num_images; ctx->tnum = num_target; ctx->level = level; ctx->csize = csize; ctx->wsize = wsize;
+  ctx->min_image_num = min_image_num;
+  ctx->tau = std::min(min_image_num * 2, num_images);  // findMatch.cpp:56
+  if (ctx->tau > kMaxTau) { delete ctx; return PMVSB_EINVAL; }
+  ctx->nlevels = level + 3;                            // findMatch.cpp:72
+  ctx->threshold = threshold;
+  ctx->ncc_threshold = threshold;
+  ctx->ncc_threshold_before = threshold - 0.3f;       // findMatch.cpp:104
+  ctx->angle_threshold0 = 60.0f * M_PI / 180.0f;      // findMatch.cpp:92-93
+  ctx->angle_threshold1 = 60.0f * M_PI / 180.0f;
+  ctx->max_angle_threshold = max_angle_deg;
+  ctx->max_angle_threshold *= M_PI / 180.0f;          // option.cpp:105-106
+  ctx->cams.resize(num_images);
+  ctx->images.resize(num_images);
+  ctx->visdata2.resize(num_images);
+  for (int i = 0; i < num_images; ++i)
+    for (int j = 0; j < num_images; ++j)
+      if (j != i) ctx->visdata2[i].push_back(j);
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  ctx->stream = ctx->own_stream;
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_counter, sizeof(int));
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) { delete ctx; return PMVSB_ECUDA; }
+  *out = ctx;
+  return PMVSB_OK;
+}
+
+int pmvsb_destroy(pmvsb_ctx* ctx) {
+  if (!ctx) return PMVSB_EINVAL;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto& im : ctx->images)
+    for (auto* p : im.levels) cudaFree(p);
+  cudaFree(ctx->d_cams); cudaFree(ctx->d_levels); cudaFree(ctx->d_counter);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return PMVSB_OK;
+}
+
+int pmvsb_upload_camera(pmvsb_ctx* ctx, int index, const float* P) {
+  if (!ctx || !P || index < 0 || index >= ctx->num) return fail(ctx, PMVSB_EINVAL, "upload_camera: bad index or pointer");
+  HostCam& c = ctx->cams[index];
+  std::memcpy(c.P0, P, sizeof(float) * 12);
+  derive_camera(c);
+  c.set = true;
+  ctx->finalized = false;
+  return PMVSB_OK;
+}
+
+int pmvsb_upload_image(pmvsb_ctx* ctx, int index, int width, int height, const uint8_t* rgb) {
+  if (!ctx || !rgb || index < 0 || index >= ctx->num || width < 1 || height < 1)
+    return fail(ctx, PMVSB_EINVAL, "upload_image: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  HostImage& im = ctx->images[index];
+  for (auto* p : im.levels) cudaFree(p);
+  im.levels.assign(ctx->nlevels, nullptr);
+  im.w.assign(ctx->nlevels, 0);
+  im.h.assign(ctx->nlevels, 0);
+  const size_t n0 = (size_t)width * height;
+  DevBuf<uint8_t> staging;
+  CK(staging.alloc(n0 * 3));
+  CK(cudaMemcpyAsync(staging.p, rgb, n0 * 3, cudaMemcpyHostToDevice, ctx->stream));
+  im.w[0] = width; im.h[0] = height;
+  CK(cudaMalloc((void**)&im.levels[0], n0 * sizeof(uchar4)));
+  const int blocks = (int)std::min<size_t>((n0 + 255) / 256, (size_t)ctx->sm_count * 16);
+  k_rgb_to_rgba<<<blocks, 256, 0, ctx->stream>>>(staging.p, im.levels[0], n0);
+  ++ctx->launches;
+  for (int l = 1; l < ctx->nlevels; ++l) {
+    im.w[l] = im.w[l - 1] / 2;  // image.cpp:136-139
+    im.h[l] = im.h[l - 1] / 2;
+    const size_t nl = (size_t)std::max(im.w[l], 1) * std::max(im.h[l], 1);
+    CK(cudaMalloc((void**)&im.levels[l], nl * sizeof(uchar4)));
+    if (im.w[l] > 0 && im.h[l] > 0) {
+      dim3 block(32, 8), grid((im.w[l] + 31) / 32, (im.h[l] + 7) / 8);
+      k_pyr_down<<<grid, block, 0, ctx->stream>>>(im.levels[l - 1], im.w[l - 1], im.h[l - 1], im.levels[l], im.w[l], im.h[l]);
+      ++ctx->launches;
+    }
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  im.set = true;
+  ctx->finalized = false;
+  return PMVSB_OK;
+}
+
+int pmvsb_set_visdata2(pmvsb_ctx* ctx, int index, const int32_t* list, int n) {
+  if (!ctx || index < 0 || index >= ctx->num || n < 0 || (n > 0 && !list)) return fail(ctx, PMVSB_EINVAL, "set_visdata2: bad argument");
+  for (int i = 0; i < n; ++i)
+    if (list[i] < 0 || list[i] >= ctx->num) return fail(ctx, PMVSB_EINVAL, "set_visdata2: image index out of range");
+  ctx->visdata2[index].assign(list, list + n);
+  return PMVSB_OK;
+}
+
+int pmvsb_finalize_scene(pmvsb_ctx* ctx) {
+  if (!ctx) return PMVSB_EINVAL;
+  for (int i = 0; i < ctx->num; ++i) {
+    if (!ctx->cams[i].set) return fail(ctx, PMVSB_ESTATE, "finalize_scene: camera " + std::to_string(i) + " missing");
+    if (!ctx->images[i].set) return fail(ctx, PMVSB_ESTATE, "finalize_scene: image " + std::to_string(i) + " missing");
+  }
+  CK(cudaSetDevice(ctx->device));
+  std::vector<CamDev> hc(ctx->num);
+  std::vector<LevelDev> hl((size_t)ctx->num * ctx->nlevels);
+  const float sc = 1.0f / (float)(1 << ctx->level);  // rows 0,1 halved per level: exact (camera.cpp:56-68)
+  for (int i = 0; i < ctx->num; ++i) {
+    const HostCam& c = ctx->cams[i];
+    std::memset(&hc[i], 0, sizeof(CamDev));
+    for (int k = 0; k < 4; ++k) {
+      hc[i].P[0][k] = c.P0[0][k] * sc;
+      hc[i].P[1][k] = c.P0[1][k] * sc;
+      hc[i].P[2][k] = c.P0[2][k];
+    }
+    std::memcpy(hc[i].centre, c.centre, 16); std::memcpy(hc[i].oaxis, c.oaxis, 16);
+    std::memcpy(hc[i].xaxis, c.xaxis, 12); std::memcpy(hc[i].yaxis, c.yaxis, 12); std::memcpy(hc[i].zaxis, c.zaxis, 12);
+    hc[i].ipscale = c.ipscale;
+    for (int l = 0; l < ctx->nlevels; ++l) {
+      LevelDev& d = hl[(size_t)i * ctx->nlevels + l];
+      d.pix = ctx->images[i].levels[l]; d.w = ctx->images[i].w[l]; d.h = ctx->images[i].h[l];
+    }
+  }
+  cudaFree(ctx->d_cams); cudaFree(ctx->d_levels);
+  ctx->d_cams = nullptr; ctx->d_levels = nullptr;
+  CK(cudaMalloc((void**)&ctx->d_cams, sizeof(CamDev) * hc.size()));
+  CK(cudaMalloc((void**)&ctx->d_levels, sizeof(LevelDev) * hl.size()));
+  CK(cudaMemcpy(ctx->d_cams, hc.data(), sizeof(CamDev) * hc.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_levels, hl.data(), sizeof(LevelDev) * hl.size(), cudaMemcpyHostToDevice));
+  fill_scene(ctx);
+  ctx->finalized = true;
+  return PMVSB_OK;
+}
+
+int pmvsb_set_thresholds(pmvsb_ctx* ctx, float ncc_threshold, float ncc_threshold_before) {
+  if (!ctx) return PMVSB_EINVAL;
+  ctx->ncc_threshold = ncc_threshold;
+  ctx->ncc_threshold_before = ncc_threshold_before;
+  return PMVSB_OK;
+}
+
+int pmvsb_set_optimizer(pmvsb_ctx* ctx, double xtol, double step, int maxeval) {
+  if (!ctx || !(xtol > 0.0) || !(step > 0.0) || maxeval < 1) return fail(ctx, PMVSB_EINVAL, "set_optimizer: bad argument");
+  ctx->xtol = xtol; ctx->step = step; ctx->maxeval = maxeval;
+  ctx->scene.xtol = xtol; ctx->scene.step = step; ctx->scene.maxeval = maxeval;
+  return PMVSB_OK;
+}
+
+int pmvsb_image_dims(pmvsb_ctx* ctx, int index, int level, int* width, int* height) {
+  if (!ctx || index < 0 || index >= ctx->num || level < 0 || level >= ctx->nlevels || !ctx->images[index].set)
+    return fail(ctx, PMVSB_EINVAL, "image_dims: bad argument");
+  *width = ctx->images[index].w[level];
+  *height = ctx->images[index].h[level];
+  return PMVSB_OK;
+}
+
+int pmvsb_download_image(pmvsb_ctx* ctx, int index, int level, uint8_t* rgb) {
+  if (!ctx || !rgb || index < 0 || index >= ctx->num || level < 0 || level >= ctx->nlevels || !ctx->images[index].set)
+    return fail(ctx, PMVSB_EINVAL, "download_image: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)ctx->images[index].w[level] * ctx->images[index].h[level];
+  if (n == 0) return PMVSB_OK;
+  DevBuf<uint8_t> tmp;
+  CK(tmp.alloc(n * 3));
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
+  k_rgba_to_rgb<<<blocks, 256, 0, ctx->stream>>>(ctx->images[index].levels[level], tmp.p, n);
+  ++ctx->launches;
+  CK(cudaMemcpyAsync(rgb, tmp.p, n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_get_camera(pmvsb_ctx* ctx, int index, int level, float* P, float* centre, float* oaxis, float* xaxis, float* yaxis,
+                     float* zaxis, float* ipscale) {
+  if (!ctx || index < 0 || index >= ctx->num || level < 0 || level >= ctx->nlevels || !ctx->cams[index].set)
+    return fail(ctx, PMVSB_EINVAL, "get_camera: bad argument");
+  const HostCam& c = ctx->cams[index];
+  const float sc = 1.0f / (float)(1 << level);
+  for (int k = 0; k < 4; ++k) { P[k] = c.P0[0][k] * sc; P[4 + k] = c.P0[1][k] * sc; P[8 + k] = c.P0[2][k]; }
+  std::memcpy(centre, c.centre, 16); std::memcpy(oaxis, c.oaxis, 16);
+  std::memcpy(xaxis, c.xaxis, 12); std::memcpy(yaxis, c.yaxis, 12); std::memcpy(zaxis, c.zaxis, 12);
+  *ipscale = c.ipscale;
+  return PMVSB_OK;
+}
+
+// ---- batched calls with host pointers: stage, launch, copy back ------------------------------------
+struct PatchStage {
+  DevBuf<float> coords, normals, dscales;
+  DevBuf<int32_t> images, nimages;
+};
+
+static int stage_patches(pmvsb_ctx* ctx, PatchStage& st, int P, int stride, const float* coords, const float* normals,
+                         const int32_t* images, const int32_t* nimages, const float* dscales) {
+  if (P < 0 || stride < 1 || !coords || !images) return fail(ctx, PMVSB_EINVAL, "bad patch batch");
+  CK(st.coords.alloc((size_t)4 * P));
+  CK(cudaMemcpyAsync(st.coords.p, coords, sizeof(float) * 4 * P, cudaMemcpyHostToDevice, ctx->stream));
+  if (normals) {
+    CK(st.normals.alloc((size_t)4 * P));
+    CK(cudaMemcpyAsync(st.normals.p, normals, sizeof(float) * 4 * P, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(st.images.alloc((size_t)stride * P));
+  CK(cudaMemcpyAsync(st.images.p, images, sizeof(int32_t) * (size_t)stride * P, cudaMemcpyHostToDevice, ctx->stream));
+  if (nimages) {
+    CK(st.nimages.alloc(P));
+    CK(cudaMemcpyAsync(st.nimages.p, nimages, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (dscales) {
+    CK(st.dscales.alloc(P));
+    CK(cudaMemcpyAsync(st.dscales.p, dscales, sizeof(float) * P, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  // image indexes are trusted by the kernels: validate on the host
+  for (size_t i = 0; i < (size_t)stride * P; ++i) {
+    const int p = (int)(i / stride), k = (int)(i % stride);
+    const int n = nimages ? std::min(nimages[p], stride) : stride;
+    if (k < n && (images[i] < 0 || images[i] >= ctx->num)) return fail(ctx, PMVSB_EINVAL, "image index out of range in patch batch");
+  }
+  return PMVSB_OK;
+}
+
+int pmvsb_project_batch(pmvsb_ctx* ctx, int n, const float* coords, const int32_t* image, int level, float* out) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (n < 0 || !coords || !image || !out || level < 0 || level >= ctx->nlevels) return fail(ctx, PMVSB_EINVAL, "project_batch: bad argument");
+  if (n == 0) return PMVSB_OK;
+  for (int i = 0; i < n; ++i)
+    if (image[i] < 0 || image[i] >= ctx->num) return fail(ctx, PMVSB_EINVAL, "project_batch: image index out of range");
+  DevBuf<float> dc, dout;
+  DevBuf<int32_t> di;
+  CK(dc.alloc((size_t)4 * n)); CK(di.alloc(n)); CK(dout.alloc((size_t)3 * n));
+  CK(cudaMemcpyAsync(dc.p, coords, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(di.p, image, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+  k_project<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, n, dc.p, di.p, level, dout.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, dout.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_grab_tex_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals, const int32_t* images,
+                         const int32_t* nimages, float* tex, int32_t* flag, int32_t* newlevel) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (!normals || !tex || !flag || !newlevel) return fail(ctx, PMVSB_EINVAL, "grab_tex_batch: null pointer");
+  if (P == 0) return PMVSB_OK;
+  PatchStage st;
+  r = stage_patches(ctx, st, P, stride, coords, normals, images, nimages, nullptr);
+  if (r) return r;
+  const size_t tsz = (size_t)3 * ctx->wsize * ctx->wsize;
+  DevBuf<float> dt;
+  DevBuf<int32_t> df, dl;
+  CK(dt.alloc((size_t)P * stride * tsz)); CK(df.alloc((size_t)P * stride)); CK(dl.alloc((size_t)P * stride));
+  CK(cudaMemsetAsync(dt.p, 0, sizeof(float) * (size_t)P * stride * tsz, ctx->stream));
+  CK(cudaMemsetAsync(df.p, 0xff, sizeof(int32_t) * (size_t)P * stride, ctx->stream));
+  CK(cudaMemsetAsync(dl.p, 0xff, sizeof(int32_t) * (size_t)P * stride, ctx->stream));
+  const int blocks = (P + 3) / 4;
+  DISPATCH_WSIZE(ctx, k_grab_tex, blocks, 128, ctx->scene, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, dt.p, df.p, dl.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(tex, dt.p, sizeof(float) * (size_t)P * stride * tsz, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(flag, df.p, sizeof(int32_t) * (size_t)P * stride, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(newlevel, dl.p, sizeof(int32_t) * (size_t)P * stride, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+static int score_common(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals, const int32_t* images,
+                        const int32_t* nimages, const float* dscales, const double* x, int mode, double* out) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (!normals || !out || (mode == 0 && (!x || !dscales))) return fail(ctx, PMVSB_EINVAL, "score: null pointer");
+  if (P == 0) return PMVSB_OK;
+  PatchStage st;
+  r = stage_patches(ctx, st, P, stride, coords, normals, images, nimages, dscales);
+  if (r) return r;
+  DevBuf<double> dx, dout;
+  CK(dout.alloc(P));
+  if (x) {
+    CK(dx.alloc((size_t)3 * P));
+    CK(cudaMemcpyAsync(dx.p, x, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  const int blocks = (P + 3) / 4;
+  DISPATCH_WSIZE(ctx, k_score, blocks, 128, ctx->scene, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, st.dscales.p, dx.p, mode, dout.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, dout.p, sizeof(double) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_eval_objective_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals, const int32_t* images,
+                               const int32_t* nimages, const float* dscales, const double* x, double* f) {
+  return score_common(ctx, P, stride, coords, normals, images, nimages, dscales, x, 0, f);
+}
+
+int pmvsb_compute_incc_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals, const int32_t* images,
+                             const int32_t* nimages, int robust, double* out) {
+  return score_common(ctx, P, stride, coords, normals, images, nimages, nullptr, nullptr, robust ? 1 : 2, out);
+}
+
+int pmvsb_set_inccs_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals, const int32_t* images,
+                          const int32_t* nimages, int robust, float* out) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (!normals || !out) return fail(ctx, PMVSB_EINVAL, "set_inccs_batch: null pointer");
+  if (P == 0) return PMVSB_OK;
+  PatchStage st;
+  r = stage_patches(ctx, st, P, stride, coords, normals, images, nimages, nullptr);
+  if (r) return r;
+  DevBuf<float> dout;
+  CK(dout.alloc((size_t)P * stride));
+  CK(cudaMemsetAsync(dout.p, 0, sizeof(float) * (size_t)P * stride, ctx->stream));
+  const int blocks = (P + 3) / 4;
+  DISPATCH_WSIZE(ctx, k_set_inccs, blocks, 128, ctx->scene, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, robust, dout.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, dout.p, sizeof(float) * (size_t)P * stride, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_set_scales_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const int32_t* images, const int32_t* nimages,
+                           float* dscale, float* ascale) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (!dscale || !ascale) return fail(ctx, PMVSB_EINVAL, "set_scales_batch: null pointer");
+  if (P == 0) return PMVSB_OK;
+  PatchStage st;
+  r = stage_patches(ctx, st, P, stride, coords, nullptr, images, nimages, nullptr);
+  if (r) return r;
+  DevBuf<float> dd, da;
+  CK(dd.alloc(P)); CK(da.alloc(P));
+  k_set_scales<<<(P + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, P, stride, st.coords.p, st.images.p, st.nimages.p, dd.p, da.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(dscale, dd.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ascale, da.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_refine_batch_dev(pmvsb_ctx* ctx, int P, int stride, float* d_coords, float* d_normals, const int32_t* d_images,
+                           const int32_t* d_nimages, const float* d_dscales, float* d_ncc, int32_t* d_evals, uint8_t* d_ok) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (P < 0 || stride < 1 || !d_coords || !d_normals || !d_images || !d_dscales || !d_ncc || !d_evals || !d_ok)
+    return fail(ctx, PMVSB_EINVAL, "refine_batch_dev: bad argument");
+  if (P == 0) return PMVSB_OK;
+  if (ctx->refine_blocks_per_sm == 0) {
+    int nb = 0;
+    switch (ctx->wsize) {
+      case 5: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_refine<5>, 128, 0)); break;
+      case 9: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_refine<9>, 128, 0)); break;
+      default: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_refine<7>, 128, 0)); break;
+    }
+    ctx->refine_blocks_per_sm = nb > 0 ? nb : 1;
+  }
+  CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+  // persistent grid: a whole number of resident CTAs per SM (148 SMs on B200)
+  int grid = ctx->sm_count * ctx->refine_blocks_per_sm;
+  const int needed = (P + 3) / 4;
+  if (grid > needed) grid = needed;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  DISPATCH_WSIZE(ctx, k_refine, grid, 128, ctx->scene, P, stride, d_coords, d_normals, d_images, d_nimages, d_dscales, d_ncc, d_evals,
+                 d_ok, ctx->d_counter);
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->refine_timed = true;
+  CK(cudaGetLastError());
+  return PMVSB_OK;
+}
+
+int pmvsb_refine_batch(pmvsb_ctx* ctx, int P, int stride, float* coords, float* normals, const int32_t* images, const int32_t* nimages,
+                       const float* dscales, float* ncc, int32_t* evals, uint8_t* ok) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (!normals || !dscales || !ncc || !evals || !ok) return fail(ctx, PMVSB_EINVAL, "refine_batch: null pointer");
+  if (P == 0) return PMVSB_OK;
+  PatchStage st;
+  r = stage_patches(ctx, st, P, stride, coords, normals, images, nimages, dscales);
+  if (r) return r;
+  DevBuf<float> dn;
+  DevBuf<int32_t> de;
+  DevBuf<uint8_t> dk;
+  CK(dn.alloc(P)); CK(de.alloc(P)); CK(dk.alloc(P));
+  r = pmvsb_refine_batch_dev(ctx, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, st.dscales.p, dn.p, de.p, dk.p);
+  if (r) return r;
+  CK(cudaMemcpyAsync(coords, st.coords.p, sizeof(float) * 4 * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(normals, st.normals.p, sizeof(float) * 4 * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ncc, dn.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(evals, de.p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ok, dk.p, sizeof(uint8_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_sync(pmvsb_ctx* ctx) {
+  if (!ctx) return PMVSB_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+void* pmvsb_stream(pmvsb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int pmvsb_set_stream(pmvsb_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return PMVSB_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return PMVSB_OK;
+}
+
+uint64_t pmvsb_launch_count(const pmvsb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+float pmvsb_last_refine_ms(pmvsb_ctx* ctx) {
+  if (!ctx || !ctx->refine_timed) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0f;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+/*
+ * include/pmvs_b200.h -- C ABI of the B200-native PMVS patch-optimisation path.
+ *
+ * The reference has no FFI layer: its hot path is the in-process C++ contract
+ *     if (preProcess(patch,id,seed)) fail; refinePatch(patch,id,100); if (postProcess(patch,id,seed)) fail;
+ * (/root/reference/source/pmvs/seed.cpp:397-409, source/pmvs/expand.cpp:225-237) on top of
+ * CPhotoSetS (images + cameras).  This header is the boundary a maintainer binds instead
+ * (INTEGRATION.md shows the stub): one opaque context per GPU owns the image pyramids and camera
+ * tables in HBM; every hot call is BATCHED over patches (structure-of-arrays, plain pointers).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative PMVSB_E* code otherwise; pmvsb_last_error()
+ *     returns the message of the last failure on that context (never throws across the boundary);
+ *   - the caller owns all host buffers, the library owns all device memory;
+ *   - one context is used by one host thread at a time; multi-GPU = one context per device;
+ *   - calls return after the work is complete (stream-synchronised) unless suffixed _dev, which take
+ *     DEVICE pointers, enqueue on the context's stream and return immediately (pmvsb_sync to wait);
+ *   - there is NO CPU fallback: a context cannot be created without a CUDA device.
+ *
+ * Patch batch layout (P patches):
+ *   coords   float[4*P]   x y z 1            (Patch::CPatch::_coord, include/pmvs/patch.hpp:32)
+ *   normals  float[4*P]   nx ny nz 0         (CPatch::_normal, patch.hpp:34)
+ *   images   int32[stride*P]  image indexes, reference image first   (CPatch::_images, patch.hpp:38)
+ *   nimages  int32[P] or NULL (= stride for every patch)
+ *   dscales  float[P]     depth step per pixel (CPatch::_dscale, patch.hpp:72; set by setScales)
+ */
+#ifndef PMVS_B200_H
+#define PMVS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMVSB_OK 0
+#define PMVSB_EINVAL (-1)   /* bad argument */
+#define PMVSB_ECUDA (-2)    /* CUDA runtime error */
+#define PMVSB_ESTATE (-3)   /* call out of order (e.g. scene not finalised) */
+#define PMVSB_ENOMEM (-4)
+
+#define PMVSB_MAX_TAU 8     /* views used by refinePatch / computeINCC (tau = min(2*minImageNum, num)) */
+#define PMVSB_MAX_VIEWS 64  /* views per patch accepted by set_inccs / pre- and post-process kernels */
+
+typedef struct pmvsb_ctx pmvsb_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------
+ * Replaces CFindMatch::init's option plumbing (/root/reference/source/pmvs/findMatch.cpp:30-106):
+ * level, csize, wsize, minImageNum, threshold, maxAngle as in the option file
+ * (source/pmvs/option.cpp:47-109); tau, nccThresholdBefore, the 60-degree angle thresholds and the
+ * level+3 pyramid depth are derived exactly as the reference derives them. */
+int pmvsb_create(pmvsb_ctx** out, int device, int num_images, int num_target, int level, int csize,
+                 int wsize, int min_image_num, float threshold, float max_angle_deg);
+int pmvsb_destroy(pmvsb_ctx* ctx);
+const char* pmvsb_last_error(const pmvsb_ctx* ctx);
+const char* pmvsb_version(void);
+
+/* Image::CCamera::init + updateCamera (source/image/camera.cpp:13-54,109-136) and
+ * COptim::setAxesScales (source/pmvs/optim.cpp:43-64): P = 3x4 row-major float32 of txt/%08d.txt. */
+int pmvsb_upload_camera(pmvsb_ctx* ctx, int index, const float* P);
+/* Image::CImage::alloc + buildImage (source/image/image.cpp:113-180,228-325): rgb = interleaved
+ * uint8 w*h*3 (what readAnyImage produces); the level+3 pyramid is built on the device. */
+int pmvsb_upload_image(pmvsb_ctx* ctx, int index, int width, int height, const uint8_t* rgb);
+/* SOption::_visdata2 (source/pmvs/option.cpp:202-299): candidate images for addImages. Default: all. */
+int pmvsb_set_visdata2(pmvsb_ctx* ctx, int index, const int32_t* list, int n);
+/* After all cameras and images are uploaded: builds the device tables.  Required before any batch call. */
+int pmvsb_finalize_scene(pmvsb_ctx* ctx);
+
+/* CFindMatch::_nccThreshold / _nccThresholdBefore / _depth (updateThreshold, findMatch.cpp:23-28,196,216) */
+int pmvsb_set_thresholds(pmvsb_ctx* ctx, float ncc_threshold, float ncc_threshold_before);
+/* Optimiser knobs replacing nlopt's set_xtol_rel / set_maxeval (optim.cpp:623-624). Defaults 1e-4, 1.0, 1000. */
+int pmvsb_set_optimizer(pmvsb_ctx* ctx, double xtol, double step, int maxeval);
+
+/* ---- parity hooks (small, synchronous, host pointers) ------------------------------------------- */
+int pmvsb_image_dims(pmvsb_ctx* ctx, int index, int level, int* width, int* height);
+/* pyramid level back as interleaved RGB (CImage::getImage, include/image/image.hpp:197-209) */
+int pmvsb_download_image(pmvsb_ctx* ctx, int index, int level, uint8_t* rgb);
+/* derived camera constants: P at `level` (12), centre (4), oaxis (4), x/y/z axes (3 each), ipscale */
+int pmvsb_get_camera(pmvsb_ctx* ctx, int index, int level, float* P, float* centre, float* oaxis,
+                     float* xaxis, float* yaxis, float* zaxis, float* ipscale);
+/* CPhotoSetS::project (include/image/photoSetS.hpp:81-83): N points, image index per point -> float[3*N] */
+int pmvsb_project_batch(pmvsb_ctx* ctx, int n, const float* coords, const int32_t* image, int level, float* out);
+/* COptim::grabTex as my_f calls it (optim.cpp:815-863): for patch p and its k-th image
+ * (k < min(stride, nimages[p])) writes flag[p*stride+k] (0 grabbed / 1 rejected),
+ * newlevel[p*stride+k] and the raw wsize*wsize*3 texture. */
+int pmvsb_grab_tex_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals,
+                         const int32_t* images, const int32_t* nimages, float* tex, int32_t* flag,
+                         int32_t* newlevel);
+/* COptim::my_f (optim.cpp:507-578): x = double[3*P] (depth/dscale, angle1/ascale, angle2/ascale),
+ * coords/normals = the START patch (centre, ray, reference axes).  f = double[P]. */
+int pmvsb_eval_objective_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals,
+                               const int32_t* images, const int32_t* nimages, const float* dscales,
+                               const double* x, double* f);
+/* COptim::computeINCC (optim.cpp:865-938) with setWeightsT weights: out = double[P] */
+int pmvsb_compute_incc_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals,
+                             const int32_t* images, const int32_t* nimages, int robust, double* out);
+/* COptim::setINCCs vector form (optim.cpp:709-744): out = float[stride*P] */
+int pmvsb_set_inccs_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals,
+                          const int32_t* images, const int32_t* nimages, int robust, float* out);
+/* CPatchOrganizerS::setScales (source/pmvs/patchOrganizerS.cpp:663-684): dscale, ascale = float[P] */
+int pmvsb_set_scales_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const int32_t* images,
+                           const int32_t* nimages, float* dscale, float* ascale);
+
+/* ---- the hot call -------------------------------------------------------------------------------
+ * COptim::refinePatch for a whole seed / expansion frontier in one launch (optim.cpp:496-502,580-658):
+ * in-kernel bounded Nelder-Mead over (depth, angle1, angle2) around my_f, then the final
+ * computeINCC.  coords/normals are updated in place for patches with ok=1 and left untouched otherwise
+ * (optim.cpp:649-655).  ncc = 1 - unrobustincc(computeINCC(robust)), evals = objective evaluations,
+ * ok = 1 iff the optimiser stopped on its x-tolerance (MAXEVAL = failure, optim.cpp:644). */
+int pmvsb_refine_batch(pmvsb_ctx* ctx, int P, int stride, float* coords, float* normals,
+                       const int32_t* images, const int32_t* nimages, const float* dscales,
+                       float* ncc, int32_t* evals, uint8_t* ok);
+/* Same with DEVICE pointers; asynchronous on the context stream. */
+int pmvsb_refine_batch_dev(pmvsb_ctx* ctx, int P, int stride, float* d_coords, float* d_normals,
+                           const int32_t* d_images, const int32_t* d_nimages, const float* d_dscales,
+                           float* d_ncc, int32_t* d_evals, uint8_t* d_ok);
+int pmvsb_sync(pmvsb_ctx* ctx);
+/* the CUDA stream (cudaStream_t) the context launches on, for event timing by the caller */
+void* pmvsb_stream(pmvsb_ctx* ctx);
+/* launch on a caller-owned stream instead (e.g. the stream a collective will be ordered after);
+ * NULL restores the context's own stream */
+int pmvsb_set_stream(pmvsb_ctx* ctx, void* cuda_stream);
+/* launches issued by this context since creation (bench.py's gpu_launches) */
+uint64_t pmvsb_launch_count(const pmvsb_ctx* ctx);
+/* duration in ms of the most recent pmvsb_refine_batch[_dev] kernel, measured with CUDA events on the
+ * context stream (valid after pmvsb_sync) */
+float pmvsb_last_refine_ms(pmvsb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
