@@ -268,7 +268,8 @@ def main():
     coords, normals, images, dsc = make_seed_patches(scene, lib, P, seed=4 + rank, device=dev)
 
     # ---- resident inputs --------------------------------------------------------------------------
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # a real (non-default) stream shared by torch ops, NCCL ordering and the library
+    torch.cuda.set_stream(stream)
     lib.set_stream(stream.cuda_stream)
     d_coords0 = torch.from_numpy(coords).to(dev); d_normals0 = torch.from_numpy(normals).to(dev)
     d_images = torch.from_numpy(images).to(dev); d_dsc = torch.from_numpy(dsc).to(dev)

@@ -147,7 +147,8 @@ __global__ void k_score(SceneDev s, int P, int stride, const float* __restrict__
   double f;
   if (mode == 0) {
     const double x[3] = {xs[3 * p], xs[3 * p + 1], xs[3 * p + 2]};
-    f = objective<WSIZE>(s, pc, refcam, x, lane);
+    float c2[4], n2[4];
+    f = objective<WSIZE>(s, pc, refcam, x, lane, 0, c2, n2);
   } else {
     f = n < 2 ? 2.0 : photo_score<WSIZE>(s, pc, refcam, coord, normal, lane, mode);
   }
@@ -254,15 +255,16 @@ __global__ void __launch_bounds__(128) k_refine(SceneDev s, int P, int stride, f
     x[1] = clampd(x[1], -23.99999, 23.99999);
     x[2] = clampd(x[2], -23.99999, 23.99999);
     int evals = 0;
-    const bool ok = nelder_mead3<WSIZE>(s, pc, refcam, lane, x, evals);
+    double incc = 2.0;
+    float rc[4], rn[4];
+    const bool ok = nelder_mead3<WSIZE>(s, pc, refcam, lane, x, evals, incc, rc, rn);
     float ncc = -1.0f;
     if (ok) {
-      decode(s, pc, refcam, x, lane, coord, normal);
-      const double incc = n < 2 ? 2.0 : photo_score<WSIZE>(s, pc, refcam, coord, normal, lane, 1);
+      if (n < 2) incc = 2.0;  // computeINCC's early exit (optim.cpp:866)
       ncc = (float)(1.0 - (double)unrobustincc((float)incc));  // optim.cpp:652
       if (lane == 0) {
-        reinterpret_cast<float4*>(coords)[p] = make_float4(coord[0], coord[1], coord[2], coord[3]);
-        reinterpret_cast<float4*>(normals)[p] = make_float4(normal[0], normal[1], normal[2], normal[3]);
+        reinterpret_cast<float4*>(coords)[p] = make_float4(rc[0], rc[1], rc[2], rc[3]);
+        reinterpret_cast<float4*>(normals)[p] = make_float4(rn[0], rn[1], rn[2], rn[3]);
       }
     }
     if (lane == 0) {

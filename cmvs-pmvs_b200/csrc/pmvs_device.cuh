@@ -456,127 +456,168 @@ __device__ __forceinline__ double photo_score(const SceneDev& s, const PatchCtx&
   return acc / (double)totalweight;
 }
 
-// my_f(x) (optim.cpp:507-578)
+// my_f(x) (optim.cpp:507-578) when mode == 0; computeINCC at decode(x) when mode == 1 / 2.
+// Kept as ONE call site inside the optimiser loop so the (large, unrolled) sampling code exists once
+// per kernel and stays inside the instruction cache.
 template <int WSIZE>
-__device__ __forceinline__ double objective(const SceneDev& s, const PatchCtx& pc, const CamDev& refcam, const double* x, int lane) {
-  float coord[4], normal[4];
+__device__ __forceinline__ double objective(const SceneDev& s, const PatchCtx& pc, const CamDev& refcam, const double* x, int lane,
+                                            int mode, float* coord, float* normal) {
   decode(s, pc, refcam, x, lane, coord, normal);
-  return photo_score<WSIZE>(s, pc, refcam, coord, normal, lane, 0);
+  return photo_score<WSIZE>(s, pc, refcam, coord, normal, lane, mode);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // Bounded Nelder-Mead, n = 3; the written definition is oracle/nm3.h (same steps, same tie rules).
-// All state is warp-uniform.  Returns true on the x-tolerance stop, false when maxeval was hit.
+// Written as a state machine with a single evaluation site; the simplex lives in registers (all
+// indexes are compile-time after unrolling).  All state is warp-uniform.
+// On return: ok = stopped on the x-tolerance; x = best vertex; if ok, `final_score` holds
+// computeINCC(robust) at the best vertex and coord/normal its decoded patch (optim.cpp:649-652).
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+struct Simplex3 {
+  double p[4][3];
+  double f[4];
+  // vertex `k` currently holds a new point: move it down past strictly worse predecessors
+  // (stable: it stays behind equal values), considering only slots [0, k].
+  __device__ __forceinline__ void insert(int k) {
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, tf = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q == k) { t0 = p[q][0]; t1 = p[q][1]; t2 = p[q][2]; tf = f[q]; }
+    int pos = k;
+#pragma unroll
+    for (int q = 3; q >= 1; --q) {
+      if (q == pos && tf < f[q - 1]) {
+        p[q][0] = p[q - 1][0]; p[q][1] = p[q - 1][1]; p[q][2] = p[q - 1][2];
+        f[q] = f[q - 1];
+        pos = q - 1;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q == pos) { p[q][0] = t0; p[q][1] = t1; p[q][2] = t2; f[q] = tf; }
+  }
+  __device__ __forceinline__ void get(int k, double* x) const {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q == k) { x[0] = p[q][0]; x[1] = p[q][1]; x[2] = p[q][2]; }
+  }
+  __device__ __forceinline__ void set(int k, const double* x, double fx) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q == k) { p[q][0] = x[0]; p[q][1] = x[1]; p[q][2] = x[2]; f[q] = fx; }
+  }
+};
+
 template <int WSIZE>
 __device__ __forceinline__ bool nelder_mead3(const SceneDev& s, const PatchCtx& pc, const CamDev& refcam, int lane,
-                                             double* x, int& evals) {
-  const double lb[3] = {-1.0e300, -23.99999, -23.99999};
-  const double ub[3] = {1.0e300, 23.99999, 23.99999};
-  double p[4][3];
-  double fv[4];
-  int cnt = 0;
-  bool ok = true;
-  const int maxeval = s.maxeval;
-
-  auto insert = [&](int k) {
-    const double tf = fv[k];
-    const double t0 = p[k][0], t1 = p[k][1], t2 = p[k][2];
-    int q = k;
-    while (q > 0 && tf < fv[q - 1]) {
-      p[q][0] = p[q - 1][0]; p[q][1] = p[q - 1][1]; p[q][2] = p[q - 1][2];
-      fv[q] = fv[q - 1];
-      --q;
-    }
-    p[q][0] = t0; p[q][1] = t1; p[q][2] = t2;
-    fv[q] = tf;
-  };
-
+                                             double* x, int& evals, double& final_score, float* coord, float* normal) {
+  const double lb1 = -23.99999, ub1 = 23.99999;  // optim.cpp:601-602; the depth variable is unbounded
+  enum { INIT, REFLECT, EXPAND, CONTRACT, SHRINK, FINAL };
+  Simplex3 sx;
+  {
+    const double x0 = x[0], x1 = clampd(x[1], lb1, ub1), x2 = clampd(x[2], lb1, ub1);
 #pragma unroll
-  for (int j = 0; j < 3; ++j) p[0][j] = clampd(x[j], lb[j], ub[j]);
-#pragma unroll
-  for (int i = 1; i <= 3; ++i) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) p[i][j] = p[0][j];
-    if (p[0][i - 1] + s.step > ub[i - 1]) p[i][i - 1] = p[0][i - 1] - s.step;
-    else p[i][i - 1] = p[0][i - 1] + s.step;
+    for (int i = 0; i < 4; ++i) { sx.p[i][0] = x0; sx.p[i][1] = x1; sx.p[i][2] = x2; sx.f[i] = 1.0e300; }
+    sx.p[1][0] = x0 + s.step;
+    sx.p[2][1] = (x1 + s.step > ub1) ? x1 - s.step : x1 + s.step;
+    sx.p[3][2] = (x2 + s.step > ub1) ? x2 - s.step : x2 + s.step;
   }
-#pragma unroll
-  for (int i = 0; i <= 3; ++i) fv[i] = 1.0e300;
-  for (int i = 0; i <= 3 && ok; ++i) {
-    if (cnt >= maxeval) { ok = false; break; }
-    fv[i] = objective<WSIZE>(s, pc, refcam, p[i], lane);
+  int state = INIT, idx = 0, cnt = 0;
+  double xt[3] = {sx.p[0][0], sx.p[0][1], sx.p[0][2]};
+  double c[3] = {0, 0, 0}, xr[3] = {0, 0, 0}, fr = 0.0, fref = 0.0;
+  bool ok = false;
+  final_score = 2.0;
+
+  for (;;) {
+    if (state != FINAL && cnt >= s.maxeval) break;  // budget is checked before each evaluation (nm3.h)
+    const double fx = objective<WSIZE>(s, pc, refcam, xt, lane, state == FINAL ? 1 : 0, coord, normal);
+    if (state == FINAL) { final_score = fx; ok = true; break; }
     ++cnt;
-    insert(i);
-  }
-
-  while (ok) {
-    double size = 0.0;
-#pragma unroll
-    for (int i = 1; i <= 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const double d = fabs(p[i][j] - p[0][j]);
-        if (d > size) size = d;
-      }
-    if (size <= s.xtol) break;
-
-    double c[3], xr[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      c[j] = ((p[0][j] + p[1][j]) + p[2][j]) / 3.0;
-      xr[j] = clampd(c[j] + (c[j] - p[3][j]), lb[j], ub[j]);
-    }
-    if (cnt >= maxeval) { ok = false; break; }
-    const double fr = objective<WSIZE>(s, pc, refcam, xr, lane);
-    ++cnt;
-
-    if (fr < fv[0]) {
-      double xe[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) xe[j] = clampd(c[j] + 2.0 * (c[j] - p[3][j]), lb[j], ub[j]);
-      if (cnt >= maxeval) { ok = false; break; }
-      const double fe = objective<WSIZE>(s, pc, refcam, xe, lane);
-      ++cnt;
-      if (fe < fr) { p[3][0] = xe[0]; p[3][1] = xe[1]; p[3][2] = xe[2]; fv[3] = fe; }
-      else { p[3][0] = xr[0]; p[3][1] = xr[1]; p[3][2] = xr[2]; fv[3] = fr; }
-      insert(3);
-    } else if (fr < fv[2]) {
-      p[3][0] = xr[0]; p[3][1] = xr[1]; p[3][2] = xr[2]; fv[3] = fr;
-      insert(3);
-    } else {
-      double xc[3], fref;
-      if (fr < fv[3]) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) xc[j] = c[j] + 0.5 * (xr[j] - c[j]);
-        fref = fr;
+    bool new_iter = false;
+    if (state == INIT) {
+      sx.set(idx, xt, fx);
+      sx.insert(idx);
+      ++idx;
+      if (idx <= 3) sx.get(idx, xt); else new_iter = true;
+    } else if (state == REFLECT) {
+      fr = fx;
+      if (fr < sx.f[0]) {
+        xt[0] = c[0] + 2.0 * (c[0] - sx.p[3][0]);
+        xt[1] = clampd(c[1] + 2.0 * (c[1] - sx.p[3][1]), lb1, ub1);
+        xt[2] = clampd(c[2] + 2.0 * (c[2] - sx.p[3][2]), lb1, ub1);
+        state = EXPAND;
+      } else if (fr < sx.f[2]) {
+        sx.set(3, xr, fr);
+        sx.insert(3);
+        new_iter = true;
       } else {
+        if (fr < sx.f[3]) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) xc[j] = c[j] + 0.5 * (p[3][j] - c[j]);
-        fref = fv[3];
-      }
-      if (cnt >= maxeval) { ok = false; break; }
-      const double fc = objective<WSIZE>(s, pc, refcam, xc, lane);
-      ++cnt;
-      if (fc < fref) {
-        p[3][0] = xc[0]; p[3][1] = xc[1]; p[3][2] = xc[2]; fv[3] = fc;
-        insert(3);
-      } else {
-        for (int i = 1; i <= 3; ++i) {
+          for (int j = 0; j < 3; ++j) xt[j] = c[j] + 0.5 * (xr[j] - c[j]);
+          fref = fr;
+        } else {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) p[i][j] = p[0][j] + 0.5 * (p[i][j] - p[0][j]);
-          if (cnt >= maxeval) { ok = false; break; }
-          fv[i] = objective<WSIZE>(s, pc, refcam, p[i], lane);
-          ++cnt;
+          for (int j = 0; j < 3; ++j) xt[j] = c[j] + 0.5 * (sx.p[3][j] - c[j]);
+          fref = sx.f[3];
         }
-        if (!ok) break;
-        insert(1); insert(2); insert(3);
+        state = CONTRACT;
+      }
+    } else if (state == EXPAND) {
+      if (fx < fr) sx.set(3, xt, fx); else sx.set(3, xr, fr);
+      sx.insert(3);
+      new_iter = true;
+    } else if (state == CONTRACT) {
+      if (fx < fref) {
+        sx.set(3, xt, fx);
+        sx.insert(3);
+        new_iter = true;
+      } else {
+#pragma unroll
+        for (int i = 1; i <= 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) sx.p[i][j] = sx.p[0][j] + 0.5 * (sx.p[i][j] - sx.p[0][j]);
+        state = SHRINK;
+        idx = 1;
+        sx.get(1, xt);
+      }
+    } else {  // SHRINK
+      double keep[3];
+      sx.get(idx, keep);
+      sx.set(idx, keep, fx);
+      ++idx;
+      if (idx <= 3) {
+        sx.get(idx, xt);
+      } else {
+        sx.insert(1); sx.insert(2); sx.insert(3);
+        new_iter = true;
+      }
+    }
+    if (new_iter) {
+      double size = 0.0;
+#pragma unroll
+      for (int i = 1; i <= 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double d = fabs(sx.p[i][j] - sx.p[0][j]);
+          if (d > size) size = d;
+        }
+      if (size <= s.xtol) {
+        state = FINAL;
+        xt[0] = sx.p[0][0]; xt[1] = sx.p[0][1]; xt[2] = sx.p[0][2];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) c[j] = ((sx.p[0][j] + sx.p[1][j]) + sx.p[2][j]) / 3.0;
+        xr[0] = c[0] + (c[0] - sx.p[3][0]);
+        xr[1] = clampd(c[1] + (c[1] - sx.p[3][1]), lb1, ub1);
+        xr[2] = clampd(c[2] + (c[2] - sx.p[3][2]), lb1, ub1);
+        xt[0] = xr[0]; xt[1] = xr[1]; xt[2] = xr[2];
+        state = REFLECT;
       }
     }
   }
-  x[0] = p[0][0]; x[1] = p[0][1]; x[2] = p[0][2];
+  x[0] = sx.p[0][0]; x[1] = sx.p[0][1]; x[2] = sx.p[0][2];
   evals = cnt;
   return ok;
 }

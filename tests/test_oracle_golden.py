@@ -1,0 +1,130 @@
+"""CPU suite: the plain-C oracle (oracle/pmvs_oracle.c) against golden vectors produced by the REFERENCE'S
+OWN objects (tests/golden/make_golden.py).  Everything here must be bit-exact: the oracle restates the
+reference's arithmetic operation by operation."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def G():
+    return np.load(os.path.join(HERE, "golden", "pmvs_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def scene_checked(scene, G):
+    got = scene.sha256()
+    want = bytes(G["scene_sha256"]).hex()
+    assert got == want, "synthetic scene is not bit-reproducible on this machine: %s != %s" % (got, want)
+    return scene
+
+
+def test_scene_reproducible(scene_checked):
+    assert scene_checked.num == 16
+
+
+def test_cameras(oracle, scene_checked, G):
+    for i in range(scene_checked.num):
+        c = oracle.camera(i, 1)
+        for k in ("P", "centre", "oaxis", "xaxis", "yaxis", "zaxis", "ipscale"):
+            assert np.array_equal(np.atleast_1d(c[k]).ravel(), G["cam_" + k][i].ravel()), (i, k)
+
+
+def test_pyramid(oracle, scene_checked, G):
+    k = 0
+    for i in range(scene_checked.num):
+        for l in range(scene_checked.option["level"] + 3):
+            d = np.frombuffer(hashlib.sha256(oracle.image(i, l).tobytes()).digest(), np.uint8)
+            assert np.array_equal(d, G["pyr_sha256"][k]), (i, l)
+            k += 1
+    assert np.array_equal(oracle.image(3, 3), G["pyr_img3_level3"])
+
+
+def test_project_unit_scales(oracle, scene_checked, G):
+    n = len(G["coords"])
+    for l in (0, 1, 2):
+        got = np.stack([oracle.project(G["proj_image"][i], G["coords"][i], l) for i in range(n)])
+        assert np.array_equal(got, G["proj_l%d" % l])
+    unit = np.array([oracle.get_unit(G["proj_image"][i], G["coords"][i]) for i in range(n)], np.float32)
+    assert np.array_equal(unit, G["unit"])
+    for i in range(n):
+        d, a = oracle.set_scales(G["coords"][i], G["images"][i])
+        assert d == G["dscale"][i] and a == G["ascale"][i], i
+
+
+def test_grab_tex_normalize_dot(oracle, scene_checked, G):
+    nviews = G["images"].shape[1]
+    for i in range(G["tex"].shape[0]):
+        for v in range(nviews):
+            f, t, nl = oracle.grab_tex(G["coords"][i], G["normals"][i], G["images"][i, 0], G["images"][i, v])
+            assert f == G["tex_flag"][i, v], (i, v)
+            if f == 0:
+                assert np.array_equal(t, G["tex"][i, v]), (i, v)
+                assert 0 <= nl <= 3
+    for k in range(len(G["norm_in"])):
+        assert np.array_equal(oracle.normalize(G["norm_in"][k]), G["norm_out"][k])
+        assert oracle.dot(G["norm_out"][k], G["norm_out"][(k + 1) % len(G["norm_in"])]) == G["dot_out"][k]
+    # a constant texture has sigma 0 -> treated as 1 (optim.cpp:1057-1059)
+    flat = np.full(147, 93.0, np.float32)
+    assert np.array_equal(oracle.normalize(flat), np.zeros(147, np.float32))
+
+
+def test_encode_decode_objective(oracle, scene_checked, G):
+    n = len(G["coords"])
+    for i in range(n):
+        c, nm, im, ds = G["coords"][i], G["normals"][i], G["images"][i], G["dscale"][i]
+        assert np.array_equal(oracle.encode(c, nm, im, ds), G["encode"][i]), i
+        oc, on = oracle.decode(c, nm, im, ds, G["x"][i])
+        assert np.array_equal(oc, G["decode_coord"][i]) and np.array_equal(on, G["decode_normal"][i]), i
+        assert oracle.my_f(c, nm, im, ds, G["x"][i]) == G["my_f"][i], i
+        assert oracle.compute_incc(c, nm, im, 1) == G["incc_robust"][i], i
+        assert oracle.compute_incc(c, nm, im, 0) == G["incc_plain"][i], i
+        assert np.array_equal(oracle.set_inccs(c, nm, im, 0), G["set_inccs"][i]), i
+        assert np.array_equal(oracle.set_inccs_matrix(c, nm, im, 1), G["set_inccs_matrix"][i]), i
+    assert (G["my_f"] < 2.0).sum() > n // 2 and (G["my_f"] == 2.0).sum() > 0   # both branches are pinned
+    # fewer than two images: computeINCC returns 2.0 before touching any texture (optim.cpp:866)
+    assert oracle.compute_incc(G["coords"][0], G["normals"][0], G["images"][0][:1], 1) == 2.0
+
+
+def test_refine(oracle, scene_checked, G):
+    m = len(G["refine_ok"])
+    for i in range(m):
+        ok, c, nm, ncc, ev = oracle.refine(G["coords"][i], G["normals"][i], G["images"][i], G["dscale"][i])
+        assert ok == G["refine_ok"][i] and ev == G["refine_evals"][i], i
+        assert np.array_equal(c, G["refine_coord"][i]) and np.array_equal(nm, G["refine_normal"][i]), i
+        assert ncc == G["refine_ncc"][i], i
+    # batched entry point (threads) gives the same answers as the scalar one
+    r = oracle.refine_batch(G["coords"][:m], G["normals"][:m], G["images"][:m], G["dscale"][:m], threads=4)
+    assert np.array_equal(r["ok"], G["refine_ok"]) and np.array_equal(r["evals"], G["refine_evals"])
+    assert np.array_equal(r["coords"], G["refine_coord"]) and np.array_equal(r["ncc"], G["refine_ncc"])
+
+
+def test_refine_maxeval_is_failure(oracle, scene_checked, G):
+    """MAXEVAL_REACHED is not a success: the patch stays untouched (optim.cpp:644-655)."""
+    oracle.set_xtol(1e-4, 1.0, 10)
+    try:
+        ok, c, nm, ncc, ev = oracle.refine(G["coords"][5], G["normals"][5], G["images"][5], G["dscale"][5])
+        assert ok == 0 and ev == 10
+        assert np.array_equal(c, G["coords"][5]) and np.array_equal(nm, G["normals"][5])
+    finally:
+        oracle.set_xtol(1e-4, 1.0, 1000)
+
+
+def test_pre_post_process(oracle, scene_checked, G):
+    n = len(G["pp_coords"])
+    for i in range(n):
+        v, im, d, a = oracle.pre_process(G["pp_coords"][i], G["pp_normals"][i], G["pp_images"][i])
+        assert v == G["pre_verdict"][i], i
+        assert np.array_equal(im, G["pre_images"][i, : G["pre_n"][i]]), i
+        assert d == G["pre_dscale"][i] and a == G["pre_ascale"][i], i
+        if v == 0:
+            pv, pim, pgr, pt, ptmp = oracle.post_process(G["post_in_coord"][i], G["post_in_normal"][i], G["post_in_ncc"][i], im)
+            assert pv == G["post_verdict"][i], i
+            assert np.array_equal(pim, G["post_images"][i, : G["post_n"][i]]), i
+            assert np.array_equal(pgr, G["post_grids"][i, : G["post_n"][i]]), i
+            assert pt == G["post_timages"][i] and ptmp == G["post_tmp"][i], i
+    assert (G["pre_verdict"] == 0).sum() > 50 and (G["pre_verdict"] == 1).sum() > 10
