@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "pmvs_device.cuh"
+#include "pmvs_group.cuh"
 
 using namespace pmvsb;
 
@@ -275,6 +276,123 @@ __global__ void __launch_bounds__(128) k_refine(SceneDev s, int P, int stride, f
   }
 }
 
+
+// ---- second-generation kernels: 8 lanes per patch, 4 patches per warp (pmvs_group.cuh) ---------------
+template <int WSIZE>
+__global__ void __launch_bounds__(128) k_score_g(SceneDev s, int P, int stride, const float* __restrict__ coords,
+                                                 const float* __restrict__ normals, const int32_t* __restrict__ images,
+                                                 const int32_t* __restrict__ nimages, const float* __restrict__ dscales,
+                                                 const double* __restrict__ xs, int mode, double* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
+  const unsigned gmask = 0xffu << (g * kGroup);
+  const int p = warp * 4 + g;
+  GroupCtx gc;
+  gc.size = 0; gc.nimages = 0; gc.ref = 0; gc.my_image = -1; gc.my_weight = 0.f; gc.dscale = 1.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { gc.centre[k] = 0.f; gc.ray[k] = 0.f; }
+  float coord[4] = {0, 0, 0, 1}, normal[4] = {0, 0, 1, 0};
+  double x[3] = {0, 0, 0};
+  if (p < P) {
+    load_patch(coords, normals, p, coord, normal);
+    const int n = nimages ? min(nimages[p], stride) : stride;
+    group_ctx_init(s, gc, coord, normal, images + (size_t)p * stride, n, dscales ? dscales[p] : 1.0f, gl, gmask);
+    if (mode == 0) { x[0] = xs[3 * p]; x[1] = xs[3 * p + 1]; x[2] = xs[3 * p + 2]; }
+  }
+  __syncwarp();
+  double f;
+  if (mode == 0) {
+    float c2[4], n2[4];
+    f = group_objective<WSIZE>(s, gc, x, gl, g, 0, c2, n2);
+  } else {
+    CamDev refcam;
+    load_cam(s, gc.size > 0 ? gc.ref : 0, refcam);
+    f = group_photo_score<WSIZE>(s, gc, refcam, coord, normal, gl, g, mode);
+  }
+  if (p < P && gl == 0) out[p] = f;
+}
+
+// K3 (v2): COptim::refinePatch for a whole frontier.  Each 8-lane group pulls patches from a global counter
+// and runs its own Nelder-Mead (state in shared memory, advanced by the group leader); the four groups of a
+// warp evaluate their objectives in lock step.
+template <int WSIZE>
+__global__ void __launch_bounds__(128, 4) k_refine_g(SceneDev s, int P, int stride, float* __restrict__ coords, float* __restrict__ normals,
+                                                     const int32_t* __restrict__ images, const int32_t* __restrict__ nimages,
+                                                     const float* __restrict__ dscales, float* __restrict__ ncc_out,
+                                                     int32_t* __restrict__ evals_out, uint8_t* __restrict__ ok_out,
+                                                     int* __restrict__ counter) {
+  __shared__ NMShared nms[4][4];  // [warp in CTA][group in warp]
+  const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
+  const unsigned gmask = 0xffu << (g * kGroup);
+  NMShared& nm = nms[threadIdx.x >> 5][g];
+  GroupCtx gc;
+  gc.size = 0; gc.nimages = 0; gc.ref = 0; gc.my_image = -1; gc.my_weight = 0.f; gc.dscale = 1.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { gc.centre[k] = 0.f; gc.ray[k] = 0.f; }
+  if (gl == 0) {
+    const double z[3] = {0.0, 0.0, 0.0};
+    nm_start(nm, z, 1.0);
+  }
+  int p = -1;
+  bool have = false, exhausted = false;
+  for (;;) {
+    if (!have && !exhausted) {  // this group needs a patch (divergent between groups; shuffles name the group only)
+      int q = 0;
+      if (gl == 0) q = atomicAdd(counter, 1);
+      q = __shfl_sync(gmask, q, 0, kGroup);
+      if (q >= P) {
+        exhausted = true;
+        gc.size = 0;
+        if (gl == 0) { nm.xt[0] = nm.xt[1] = nm.xt[2] = 0.0; nm.state = NM_INIT; }
+      } else {
+        p = q;
+        float coord[4], normal[4];
+        load_patch(coords, normals, p, coord, normal);
+        const int n = nimages ? min(nimages[p], stride) : stride;
+        group_ctx_init(s, gc, coord, normal, images + (size_t)p * stride, n, dscales[p], gl, gmask);
+        if (gl == 0) {
+          CamDev refcam;
+          load_cam(s, gc.ref, refcam);
+          double x[3];
+          encode(s, gc, refcam, coord, normal, x);
+          nm_start(nm, x, s.step);  // clamps the start into the box as optim.cpp:629-634 does
+        }
+        have = true;
+      }
+    }
+    __syncwarp();
+    if (!__any_sync(kFull, have)) break;
+
+    const int mode = (have && nm.state == NM_FINAL) ? 1 : 0;
+    const double xt[3] = {nm.xt[0], nm.xt[1], nm.xt[2]};
+    float rc[4], rn[4];
+    const double fx = group_objective<WSIZE>(s, gc, xt, gl, g, mode, rc, rn);
+    __syncwarp();
+    if (have && gl == 0) nm_advance(nm, fx, s.xtol);
+    __syncwarp();
+    if (have) {
+      const int st = nm.state;
+      const bool ok = st == NM_DONE_OK;
+      if (ok || (st != NM_FINAL && nm.cnt >= s.maxeval)) {  // budget is checked before each evaluation (nm3.h)
+        if (gl == 0) {
+          float ncc = -1.0f;
+          if (ok) {
+            ncc = (float)(1.0 - (double)unrobustincc((float)nm.fr));  // optim.cpp:652
+            reinterpret_cast<float4*>(coords)[p] = make_float4(rc[0], rc[1], rc[2], rc[3]);
+            reinterpret_cast<float4*>(normals)[p] = make_float4(rn[0], rn[1], rn[2], rn[3]);
+          }
+          ncc_out[p] = ncc;
+          evals_out[p] = nm.cnt;
+          ok_out[p] = ok ? 1 : 0;
+        }
+        have = false;
+        gc.size = 0;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -445,6 +563,17 @@ int check_ready(pmvsb_ctx* ctx) {
   if (e != cudaSuccess) return fail(ctx, PMVSB_ECUDA, cudaGetErrorString(e));
   return PMVSB_OK;
 }
+
+// group kernels (8 lanes per patch) cover wsize <= 8; wsize 9 falls back to the warp-per-patch kernels
+#define DISPATCH_GROUP(ctx, KG, KW, gridg, gridw, block, ...)                                   \
+  do {                                                                                          \
+    switch ((ctx)->wsize) {                                                                     \
+      case 5: KG<5><<<gridg, block, 0, (ctx)->stream>>>(__VA_ARGS__); break;                    \
+      case 9: KW<9><<<gridw, block, 0, (ctx)->stream>>>(__VA_ARGS__); break;                    \
+      default: KG<7><<<gridg, block, 0, (ctx)->stream>>>(__VA_ARGS__); break;                   \
+    }                                                                                           \
+    ++(ctx)->launches;                                                                          \
+  } while (0)
 
 #define DISPATCH_WSIZE(ctx, KERNEL, grid, block, ...)                                           \
   do {                                                                                          \
@@ -756,8 +885,10 @@ static int score_common(pmvsb_ctx* ctx, int P, int stride, const float* coords, 
     CK(dx.alloc((size_t)3 * P));
     CK(cudaMemcpyAsync(dx.p, x, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, ctx->stream));
   }
-  const int blocks = (P + 3) / 4;
-  DISPATCH_WSIZE(ctx, k_score, blocks, 128, ctx->scene, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, st.dscales.p, dx.p, mode, dout.p);
+  const int blocks = (P + 3) / 4;       // warp per patch
+  const int blocksg = (P + 15) / 16;    // 8 lanes per patch
+  DISPATCH_GROUP(ctx, k_score_g, k_score, blocksg, blocks, 128, ctx->scene, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p,
+                 st.dscales.p, dx.p, mode, dout.p);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, dout.p, sizeof(double) * P, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -824,20 +955,21 @@ int pmvsb_refine_batch_dev(pmvsb_ctx* ctx, int P, int stride, float* d_coords, f
   if (ctx->refine_blocks_per_sm == 0) {
     int nb = 0;
     switch (ctx->wsize) {
-      case 5: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_refine<5>, 128, 0)); break;
+      case 5: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_refine_g<5>, 128, 0)); break;
       case 9: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_refine<9>, 128, 0)); break;
-      default: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_refine<7>, 128, 0)); break;
+      default: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_refine_g<7>, 128, 0)); break;
     }
     ctx->refine_blocks_per_sm = nb > 0 ? nb : 1;
   }
   CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   // persistent grid: a whole number of resident CTAs per SM (148 SMs on B200)
   int grid = ctx->sm_count * ctx->refine_blocks_per_sm;
-  const int needed = (P + 3) / 4;
+  const int per_block = ctx->wsize == 9 ? 4 : 16;  // patches a CTA works on at a time
+  const int needed = (P + per_block - 1) / per_block;
   if (grid > needed) grid = needed;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  DISPATCH_WSIZE(ctx, k_refine, grid, 128, ctx->scene, P, stride, d_coords, d_normals, d_images, d_nimages, d_dscales, d_ncc, d_evals,
-                 d_ok, ctx->d_counter);
+  DISPATCH_GROUP(ctx, k_refine_g, k_refine, grid, grid, 128, ctx->scene, P, stride, d_coords, d_normals, d_images, d_nimages, d_dscales,
+                 d_ncc, d_evals, d_ok, ctx->d_counter);
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->refine_timed = true;
   CK(cudaGetLastError());

@@ -345,7 +345,8 @@ __device__ __forceinline__ void decode(const SceneDev& s, const PatchCtx& pc, co
 }
 
 // COptim::encode (optim.cpp:660-688); uniform across the warp (called once per patch)
-__device__ __forceinline__ void encode(const SceneDev& s, const PatchCtx& pc, const CamDev& refcam, const float* coord,
+template <class Ctx>
+__device__ __forceinline__ void encode(const SceneDev& s, const Ctx& pc, const CamDev& refcam, const float* coord,
                                        const float* normal, double* x) {
   const float d[4] = {coord[0] - pc.centre[0], coord[1] - pc.centre[1], coord[2] - pc.centre[2], coord[3] - pc.centre[3]};
   x[0] = (double)(dot4(d, pc.ray) / pc.dscale);

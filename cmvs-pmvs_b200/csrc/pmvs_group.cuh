@@ -1,0 +1,472 @@
+// cmvs-pmvs_b200/csrc/pmvs_group.cuh
+//
+// Second-generation mapping of the patch-optimisation path: EIGHT lanes own one patch, so a warp
+// refines four patches in lock step.  Within a group, lane c (< wsize) owns column c of the
+// wsize x wsize sampling window and walks its rows; lane v (< tau) prepares view v's window.
+// Why: with one warp per patch (pmvs_device.cuh) ~35% of the issued instructions were warp-uniform
+// bookkeeping (decode, patch axes, window set-up, simplex arithmetic) executed for 32 lanes on behalf
+// of one patch, the 49 texels filled 49 of 64 lane slots, and every reduction was a 5-step shuffle
+// chain.  Here the uniform work is shared by four patches, 49 of 56 slots are filled and reductions are
+// 3 steps (ncu evidence: profiles/).
+//
+// Arithmetic policy is unchanged for everything that decides an integer (angle gate, level pick,
+// grabSafe, sample positions: reference f32 operation order, IEEE div/sqrt, no FMA).  The texture
+// statistics are evaluated as   NCC = sum_c sum_k (a_k - mean_a)(b_k - mean_b) / (147 sd_a sd_b)
+// with two-pass means, i.e. without the reference's per-element division (optim.cpp:1061-1066); that
+// differs from the reference by rounding only (~1e-7, bar 1e-4).
+#pragma once
+#include "pmvs_device.cuh"
+
+namespace pmvsb {
+
+constexpr int kGroup = 8;  // lanes per patch
+
+__device__ __forceinline__ float group_sum(float v) {
+  v += __shfl_xor_sync(kFull, v, 4);
+  v += __shfl_xor_sync(kFull, v, 2);
+  v += __shfl_xor_sync(kFull, v, 1);
+  return v;
+}
+
+// u8 -> f32 without the conversion (XU) pipe: splice the byte under the exponent of 2^23, subtract 2^23.
+__device__ __forceinline__ float byte_to_float(uint32_t word, uint32_t selector) {
+  return __uint_as_float(__byte_perm(word, 0x4B000000u, selector)) - 8388608.0f;
+}
+
+// CImage::getColor (include/image/image.hpp:435-476) on RGBA8 words; same operation order as get_color().
+__device__ __forceinline__ void get_color_fast(const LevelDev& lv, float x, float y, float* rgb) {
+  const int lx = (int)x;
+  const int ly = (int)y;
+  const float dx1 = x - (float)lx, dx0 = 1.0f - dx1;
+  const float dy1 = y - (float)ly, dy0 = 1.0f - dy1;
+  const float f00 = dx0 * dy0, f01 = dx0 * dy1, f10 = dx1 * dy0, f11 = dx1 * dy1;
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(lv.pix) + (size_t)ly * lv.w + lx;
+  const uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + lv.w), d = __ldg(p + lv.w + 1);
+  rgb[0] = (byte_to_float(a, 0x7540) * f00 + byte_to_float(c, 0x7540) * f01) + (byte_to_float(b, 0x7540) * f10 + byte_to_float(d, 0x7540) * f11);
+  rgb[1] = (byte_to_float(a, 0x7541) * f00 + byte_to_float(c, 0x7541) * f01) + (byte_to_float(b, 0x7541) * f10 + byte_to_float(d, 0x7541) * f11);
+  rgb[2] = (byte_to_float(a, 0x7542) * f00 + byte_to_float(c, 0x7542) * f01) + (byte_to_float(b, 0x7542) * f10 + byte_to_float(d, 0x7542) * f11);
+}
+
+// ---- compact (code-size conscious) variants: the refine loop must stay inside the instruction cache ----
+// Same operations in the same order as get_paxes() / view_window() of pmvs_device.cuh; the two axis
+// projections run as a 2-trip loop around ONE inlined copy of project().
+__device__ __forceinline__ void get_paxes_c(const CamDev& cam, int level, const float* coord, const float* normal,
+                                            float* px, float* py) {
+  const float pscale = get_unit(cam, level, coord);
+  const float n3[3] = {normal[0], normal[1], normal[2]};
+  float y3[3], x3[3];
+  cross3(n3, cam.xaxis, y3);
+  unitize3(y3);
+  cross3(y3, n3, x3);
+  px[0] = x3[0] * pscale; px[1] = x3[1] * pscale; px[2] = x3[2] * pscale; px[3] = 0.0f * pscale;
+  py[0] = y3[0] * pscale; py[1] = y3[1] * pscale; py[2] = y3[2] * pscale; py[3] = 0.0f * pscale;
+  float c0[3];
+  project(cam, coord, c0);
+  float dis0 = 1.0f, dis1 = 1.0f;
+#pragma unroll 1
+  for (int a = 0; a < 2; ++a) {
+    float t[4], c1[3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] = coord[k] + (a == 0 ? px[k] : py[k]);
+    project(cam, t, c1);
+    const float d[3] = {c1[0] - c0[0], c1[1] - c0[1], c1[2] - c0[2]};
+    const float dis = sqrtf(dot3(d, d));
+    if (a == 0) dis0 = dis; else dis1 = dis;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { px[k] /= dis0; py[k] /= dis1; }
+}
+
+template <int WSIZE>
+__device__ __forceinline__ ViewWin view_window_c(const SceneDev& s, const CamDev& cam, int index, const float* coord,
+                                                 const float* px, const float* py, const float* pz) {
+  ViewWin w;
+  w.newlevel = -1;
+  w.lx = w.ly = w.dxx = w.dxy = w.dyx = w.dyy = 0.0f;
+  float ray[4] = {cam.centre[0] - coord[0], cam.centre[1] - coord[1], cam.centre[2] - coord[2], cam.centre[3] - coord[3]};
+  unitize4(ray);
+  const float weight = smax(0.0f, dot4(ray, pz));
+  if (weight < s.cos_angle1) return w;  // optim.cpp:823
+
+  float center[3], dx[3] = {0, 0, 0}, dy[3] = {0, 0, 0};
+  project(cam, coord, center);
+  float nrm = 0.0f;
+#pragma unroll 1
+  for (int a = 0; a < 2; ++a) {
+    float t[4], q[3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] = coord[k] + (a == 0 ? px[k] : py[k]);
+    project(cam, t, q);
+    const float d[3] = {q[0] - center[0], q[1] - center[1], q[2] - center[2]};
+    const float len = sqrtf(dot3(d, d));
+    if (a == 0) { dx[0] = d[0]; dx[1] = d[1]; nrm = len; }
+    else { dy[0] = d[0]; dy[1] = d[1]; nrm = nrm + len; }   // norm(dx) + norm(dy), optim.cpp:831
+  }
+  const float ratio = nrm / 2.0f;
+  int leveldif = -s.level;
+#pragma unroll 1
+  for (int k = 0; k < s.n_level_thr; ++k)
+    if (ratio >= s.level_thr[k]) ++leveldif;
+  const int newlevel = s.level + leveldif;
+  const float scale = (leveldif >= 0) ? (float)(1 << leveldif) : 1.0f / (float)(1 << (-leveldif));  // MyPow2
+  center[0] /= scale; center[1] /= scale;
+  dx[0] /= scale; dx[1] /= scale;
+  dy[0] /= scale; dy[1] /= scale;
+
+  constexpr float m = (float)(WSIZE / 2);
+  float lo[2], hi[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float tl = center[k] - dx[k] * m - dy[k] * m, tr = center[k] + dx[k] * m - dy[k] * m;
+    const float bl = center[k] - dx[k] * m + dy[k] * m, br = center[k] + dx[k] * m + dy[k] * m;
+    lo[k] = smin(tl, smin(tr, smin(bl, br)));
+    hi[k] = smax(tl, smax(tr, smax(bl, br)));
+  }
+  const LevelDev lv = s.levels[index * s.nlevels + newlevel];
+  const bool safe = (lo[0] >= 3.0f) && (hi[0] < (float)(lv.w - 1 - 3)) && (lo[1] >= 3.0f) && (hi[1] < (float)(lv.h - 1 - 3));
+  if (!safe) return w;
+  w.lx = center[0] - dx[0] * m - dy[0] * m;
+  w.ly = center[1] - dx[1] * m - dy[1] * m;
+  w.dxx = dx[0]; w.dxy = dx[1];
+  w.dyx = dy[0]; w.dyy = dy[1];
+  w.newlevel = newlevel;
+  return w;
+}
+
+// A view's texture held by one group: lane = column, v[row][channel].
+template <int WSIZE>
+struct GroupTex {
+  float v[WSIZE][3];
+};
+
+// grabTex's sampling loop (optim.cpp:846-860) for the group's current view.  `w` is group-uniform;
+// `on` = this group samples this view.  Returns per-channel means (group-uniform) in ave[].
+// The row base advances by the reference's `left += dy`; the column offset replays `vftmp += dx`.
+template <int WSIZE>
+__device__ __forceinline__ void group_grab(const SceneDev& s, int index, const ViewWin& w, int gl, bool on, GroupTex<WSIZE>& tex,
+                                           float* ave) {
+  LevelDev lv;
+  lv.pix = nullptr; lv.w = 0; lv.h = 0;
+  if (on) lv = s.levels[index * s.nlevels + w.newlevel];
+  const bool mine = on && gl < WSIZE;
+  float bx = w.lx, by = w.ly;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int row = 0; row < WSIZE; ++row) {
+    float x = bx, y = by;
+#pragma unroll
+    for (int i = 0; i < WSIZE - 1; ++i)
+      if (i < gl) { x += w.dxx; y += w.dxy; }
+    if (mine) {
+      get_color_fast(lv, x, y, tex.v[row]);
+    } else {
+      tex.v[row][0] = tex.v[row][1] = tex.v[row][2] = 0.0f;
+    }
+    s0 += tex.v[row][0]; s1 += tex.v[row][1]; s2 += tex.v[row][2];
+    bx += w.dyx; by += w.dyy;
+  }
+  constexpr float invn = 1.0f;  // keep the division below: mean = sum / N as in optim.cpp:1043
+  (void)invn;
+  ave[0] = group_sum(s0) / (float)(WSIZE * WSIZE);
+  ave[1] = group_sum(s1) / (float)(WSIZE * WSIZE);
+  ave[2] = group_sum(s2) / (float)(WSIZE * WSIZE);
+}
+
+// subtract the means in place and return the group's sum of squared deviations (optim.cpp:1045-1053)
+template <int WSIZE>
+__device__ __forceinline__ float group_center(GroupTex<WSIZE>& tex, const float* ave, int gl) {
+  float sq = 0.0f;
+  const bool mine = gl < WSIZE;
+#pragma unroll
+  for (int row = 0; row < WSIZE; ++row) {
+    const float d0 = mine ? tex.v[row][0] - ave[0] : 0.0f;
+    const float d1 = mine ? tex.v[row][1] - ave[1] : 0.0f;
+    const float d2 = mine ? tex.v[row][2] - ave[2] : 0.0f;
+    tex.v[row][0] = d0; tex.v[row][1] = d1; tex.v[row][2] = d2;
+    sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq);
+  }
+  return group_sum(sq);
+}
+
+template <int WSIZE>
+__device__ __forceinline__ float group_cross(const GroupTex<WSIZE>& a, const GroupTex<WSIZE>& b) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int row = 0; row < WSIZE; ++row) {
+    acc = fmaf(a.v[row][0], b.v[row][0], acc);
+    acc = fmaf(a.v[row][1], b.v[row][1], acc);
+    acc = fmaf(a.v[row][2], b.v[row][2], acc);
+  }
+  return group_sum(acc);
+}
+
+// per-group patch context; every lane of the group holds the same values except my_image / my_weight
+struct GroupCtx {
+  float centre[4];
+  float ray[4];
+  float dscale;
+  int size;         // min(tau, nimages); 0 = group idle
+  int nimages;
+  int ref;
+  int my_image;     // lane v < size: images[v]; else -1
+  float my_weight;  // lane v: _weightsT[v]
+};
+
+// refinePatchBFGS's per-thread set-up (optim.cpp:584-596).  Called by one group at a time (divergent),
+// so shuffles name only the group's lanes.
+__device__ __forceinline__ void group_ctx_init(const SceneDev& s, GroupCtx& gc, const float* coord, const float* normal,
+                                               const int32_t* images, int nimages, float dscale, int gl, unsigned gmask) {
+  gc.nimages = nimages;
+  gc.size = nimages < s.tau ? nimages : s.tau;
+  gc.dscale = dscale;
+  gc.ref = images[0];
+  CamDev cam;
+  load_cam(s, gc.ref, cam);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { gc.centre[k] = coord[k]; gc.ray[k] = coord[k] - cam.centre[k]; }
+  unitize4(gc.ray);
+  gc.my_image = gl < gc.size ? images[gl] : -1;
+  float unit = 1.0f;
+  if (gl < gc.size) {
+    load_cam(s, gc.my_image, cam);
+    unit = get_unit(cam, s.level, coord);
+    float ray[4] = {cam.centre[0] - coord[0], cam.centre[1] - coord[1], cam.centre[2] - coord[2], cam.centre[3] - coord[3]};
+    unitize4(ray);
+    const float denom = dot4(ray, normal);
+    if (0.0f < denom) unit /= denom; else unit = 1073741824.0f;  // (float)(INT_MAX/2)
+  }
+  const float u0 = __shfl_sync(gmask, unit, 0, kGroup);
+  gc.my_weight = gl == 0 ? 1.0f : smin(1.0f, u0 / unit);
+}
+
+// COptim::decode (optim.cpp:690-707) for four groups at once; lanes 0/1 of each group evaluate the
+// double-precision sincos of angle1/angle2.
+__device__ __forceinline__ void group_decode(const SceneDev& s, const GroupCtx& gc, const float* xaxis, const float* yaxis,
+                                             const float* zaxis, const double* x, int gl, float* coord, float* normal) {
+  const double sd = (double)gc.dscale * x[0];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) coord[k] = gc.centre[k] + (float)((double)gc.ray[k] * sd);
+  const float angle1 = (float)(x[1] * (double)s.ascale);
+  const float angle2 = (float)(x[2] * (double)s.ascale);
+  double sn = 0.0, cs = 0.0;
+  if (gl < 2) sincos((double)(gl == 0 ? angle1 : angle2), &sn, &cs);
+  const double s1 = __shfl_sync(kFull, sn, 0, kGroup), c1 = __shfl_sync(kFull, cs, 0, kGroup);
+  const double s2 = __shfl_sync(kFull, sn, 1, kGroup), c2 = __shfl_sync(kFull, cs, 1, kGroup);
+  const float fx = (float)(s1 * c2);
+  const float fy = (float)s2;
+  const float fz = (float)(-c1 * c2);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) normal[k] = xaxis[k] * fx + yaxis[k] * fy + zaxis[k] * fz;
+  normal[3] = 0.0f;
+}
+
+// my_f's scoring (mode 0, optim.cpp:530-574) or computeINCC (mode 1 robust / 2 plain, optim.cpp:865-938) of the
+// patch (coord, normal) for the four groups of a warp.  Must be called by all 32 lanes; groups with
+// gc.size == 0 idle through.
+template <int WSIZE>
+__device__ __forceinline__ double group_photo_score(const SceneDev& s, const GroupCtx& gc, const CamDev& refcam, const float* coord,
+                                                    const float* normal, int gl, int g, int mode) {
+  const bool live = gc.size > 0;
+  float px[4], py[4];
+  get_paxes_c(refcam, s.level, coord, normal, px, py);
+  ViewWin mine;
+  mine.newlevel = -1;
+  mine.lx = mine.ly = mine.dxx = mine.dxy = mine.dyx = mine.dyy = 0.0f;
+  if (gl < gc.size) {
+    CamDev cam;
+    load_cam(s, gc.my_image, cam);
+    mine = view_window_c<WSIZE>(s, cam, gc.my_image, coord, px, py, normal);
+  }
+  const unsigned validmask = (__ballot_sync(kFull, mine.newlevel >= 0) >> (g * kGroup)) & 0xffu;
+  const bool have_ref = live && (validmask & 1u);
+
+  GroupTex<WSIZE> ref, cur;
+  float sq_ref = 1.0f;
+  double acc = 0.0;
+  float totalweight = 0.0f;
+  int denom = 0;
+  const int vmax = s.tau;
+  for (int v = 0; v < vmax; ++v) {
+    const bool on = have_ref && ((validmask >> v) & 1u);
+    if (!__any_sync(kFull, on)) continue;
+    ViewWin w;
+    w.lx = __shfl_sync(kFull, mine.lx, v, kGroup);   w.ly = __shfl_sync(kFull, mine.ly, v, kGroup);
+    w.dxx = __shfl_sync(kFull, mine.dxx, v, kGroup); w.dxy = __shfl_sync(kFull, mine.dxy, v, kGroup);
+    w.dyx = __shfl_sync(kFull, mine.dyx, v, kGroup); w.dyy = __shfl_sync(kFull, mine.dyy, v, kGroup);
+    w.newlevel = __shfl_sync(kFull, mine.newlevel, v, kGroup);
+    const int index = __shfl_sync(kFull, gc.my_image, v, kGroup);
+    const float wv = __shfl_sync(kFull, gc.my_weight, v, kGroup);
+    float ave[3];
+    group_grab<WSIZE>(s, index, w, gl, on, cur, ave);
+    const float sq_cur = group_center<WSIZE>(cur, ave, gl);
+    if (v == 0) {  // the reference view stays resident; the other views stream past it
+      ref = cur;
+      sq_ref = sq_cur;
+      continue;
+    }
+    const float cross = group_cross<WSIZE>(ref, cur);
+    if (on) {
+      // sd = sqrt(sq / 147), 0 -> 1 (optim.cpp:1055-1059); dot = sum(t_ref t_cur) / 147 (optim.cpp:1069-1077)
+      constexpr float n3 = (float)(3 * WSIZE * WSIZE);
+      float sda = sqrtf(sq_ref / n3), sdb = sqrtf(sq_cur / n3);
+      if (sda == 0.0f) sda = 1.0f;
+      if (sdb == 0.0f) sdb = 1.0f;
+      const float d = cross / (sda * sdb) / n3;
+      if (mode == 0) {
+        acc += (double)robustincc(1.0f - d);
+        ++denom;
+      } else if (mode == 1) {
+        totalweight += wv;
+        acc += (double)(robustincc(1.0f - d) * wv);
+      } else {
+        totalweight += wv;
+        acc += (1.0 - (double)d) * (double)wv;
+      }
+    }
+  }
+  if (!have_ref) return 2.0;
+  if (mode == 0) {
+    const int mininum = s.min_image_num < gc.size ? s.min_image_num : gc.size;
+    if (denom < mininum - 1) return 2.0;
+    return acc / (double)denom;
+  }
+  if (gc.nimages < 2) return 2.0;
+  if (totalweight == 0.0f) return 2.0;
+  return acc / (double)totalweight;
+}
+
+// my_f(x) / computeINCC at decode(x); coord/normal receive the decoded patch.
+template <int WSIZE>
+__device__ __forceinline__ double group_objective(const SceneDev& s, const GroupCtx& gc, const double* x, int gl, int g, int mode,
+                                                  float* coord, float* normal) {
+  CamDev refcam;
+  load_cam(s, gc.size > 0 ? gc.ref : 0, refcam);  // 128 B, L1-resident; not kept in registers across the loop
+  group_decode(s, gc, refcam.xaxis, refcam.yaxis, refcam.zaxis, x, gl, coord, normal);
+  return group_photo_score<WSIZE>(s, gc, refcam, coord, normal, gl, g, mode);
+}
+
+// The Nelder-Mead state of one group, kept in SHARED memory (216 B per patch) and advanced by the group's
+// leader lane only: the simplex costs no registers in the sampling loop and its bookkeeping is a few
+// dozen instructions of compact, loop-based code.  Same steps and tie rules as oracle/nm3.h.
+struct NMShared {
+  double p[4][3];
+  double f[4];
+  double xt[3], c[3], xr[3];
+  double fr, fref;
+  int state, idx, cnt, pad;
+};
+enum { NM_INIT, NM_REFLECT, NM_EXPAND, NM_CONTRACT, NM_SHRINK, NM_FINAL, NM_DONE_OK };
+
+__device__ __forceinline__ void nm_start(NMShared& n, const double* x, double step) {
+  const double lb1 = -23.99999, ub1 = 23.99999;  // optim.cpp:601-602; depth is unbounded
+  const double x0[3] = {x[0], clampd(x[1], lb1, ub1), clampd(x[2], lb1, ub1)};
+  for (int i = 0; i < 4; ++i) {
+    for (int j = 0; j < 3; ++j) n.p[i][j] = x0[j];
+    n.f[i] = 1.0e300;
+  }
+  n.p[1][0] = x0[0] + step;
+  n.p[2][1] = (x0[1] + step > ub1) ? x0[1] - step : x0[1] + step;
+  n.p[3][2] = (x0[2] + step > ub1) ? x0[2] - step : x0[2] + step;
+  n.state = NM_INIT; n.idx = 0; n.cnt = 0;
+  for (int j = 0; j < 3; ++j) { n.xt[j] = x0[j]; n.c[j] = 0.0; n.xr[j] = 0.0; }
+  n.fr = 0.0; n.fref = 0.0;
+}
+
+// vertex k holds a new point: move it down past strictly worse predecessors (stable)
+__device__ __noinline__ void nm_insert(NMShared& n, int k) {
+  const double t0 = n.p[k][0], t1 = n.p[k][1], t2 = n.p[k][2], tf = n.f[k];
+  int q = k;
+  while (q > 0 && tf < n.f[q - 1]) {
+    n.p[q][0] = n.p[q - 1][0]; n.p[q][1] = n.p[q - 1][1]; n.p[q][2] = n.p[q - 1][2];
+    n.f[q] = n.f[q - 1];
+    --q;
+  }
+  n.p[q][0] = t0; n.p[q][1] = t1; n.p[q][2] = t2; n.f[q] = tf;
+}
+
+// consume f(xt) and choose the next point (leader lane only)
+__device__ __noinline__ void nm_advance(NMShared& n, double fx, double xtol) {
+  const double lb1 = -23.99999, ub1 = 23.99999;
+  if (n.state == NM_FINAL) { n.fr = fx; n.state = NM_DONE_OK; return; }
+  ++n.cnt;
+  bool new_iter = false;
+  switch (n.state) {
+    case NM_INIT:
+      n.f[n.idx] = fx;
+      nm_insert(n, n.idx);
+      ++n.idx;
+      if (n.idx <= 3) { for (int j = 0; j < 3; ++j) n.xt[j] = n.p[n.idx][j]; }
+      else new_iter = true;
+      break;
+    case NM_REFLECT:
+      n.fr = fx;
+      if (fx < n.f[0]) {
+        n.xt[0] = n.c[0] + 2.0 * (n.c[0] - n.p[3][0]);
+        n.xt[1] = clampd(n.c[1] + 2.0 * (n.c[1] - n.p[3][1]), lb1, ub1);
+        n.xt[2] = clampd(n.c[2] + 2.0 * (n.c[2] - n.p[3][2]), lb1, ub1);
+        n.state = NM_EXPAND;
+      } else if (fx < n.f[2]) {
+        for (int j = 0; j < 3; ++j) n.p[3][j] = n.xr[j];
+        n.f[3] = fx;
+        nm_insert(n, 3);
+        new_iter = true;
+      } else {
+        if (fx < n.f[3]) {
+          for (int j = 0; j < 3; ++j) n.xt[j] = n.c[j] + 0.5 * (n.xr[j] - n.c[j]);
+          n.fref = fx;
+        } else {
+          for (int j = 0; j < 3; ++j) n.xt[j] = n.c[j] + 0.5 * (n.p[3][j] - n.c[j]);
+          n.fref = n.f[3];
+        }
+        n.state = NM_CONTRACT;
+      }
+      break;
+    case NM_EXPAND:
+      if (fx < n.fr) { for (int j = 0; j < 3; ++j) n.p[3][j] = n.xt[j]; n.f[3] = fx; }
+      else { for (int j = 0; j < 3; ++j) n.p[3][j] = n.xr[j]; n.f[3] = n.fr; }
+      nm_insert(n, 3);
+      new_iter = true;
+      break;
+    case NM_CONTRACT:
+      if (fx < n.fref) {
+        for (int j = 0; j < 3; ++j) n.p[3][j] = n.xt[j];
+        n.f[3] = fx;
+        nm_insert(n, 3);
+        new_iter = true;
+      } else {
+        for (int i = 1; i <= 3; ++i)
+          for (int j = 0; j < 3; ++j) n.p[i][j] = n.p[0][j] + 0.5 * (n.p[i][j] - n.p[0][j]);
+        n.state = NM_SHRINK;
+        n.idx = 1;
+        for (int j = 0; j < 3; ++j) n.xt[j] = n.p[1][j];
+      }
+      break;
+    default:  // NM_SHRINK
+      n.f[n.idx] = fx;
+      ++n.idx;
+      if (n.idx <= 3) { for (int j = 0; j < 3; ++j) n.xt[j] = n.p[n.idx][j]; }
+      else { nm_insert(n, 1); nm_insert(n, 2); nm_insert(n, 3); new_iter = true; }
+      break;
+  }
+  if (new_iter) {
+    double size = 0.0;
+    for (int i = 1; i <= 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        const double d = fabs(n.p[i][j] - n.p[0][j]);
+        if (d > size) size = d;
+      }
+    if (size <= xtol) {
+      n.state = NM_FINAL;
+      for (int j = 0; j < 3; ++j) n.xt[j] = n.p[0][j];
+    } else {
+      for (int j = 0; j < 3; ++j) n.c[j] = ((n.p[0][j] + n.p[1][j]) + n.p[2][j]) / 3.0;
+      n.xr[0] = n.c[0] + (n.c[0] - n.p[3][0]);
+      n.xr[1] = clampd(n.c[1] + (n.c[1] - n.p[3][1]), lb1, ub1);
+      n.xr[2] = clampd(n.c[2] + (n.c[2] - n.p[3][2]), lb1, ub1);
+      for (int j = 0; j < 3; ++j) n.xt[j] = n.xr[j];
+      n.state = NM_REFLECT;
+    }
+  }
+}
+
+}  // namespace pmvsb
