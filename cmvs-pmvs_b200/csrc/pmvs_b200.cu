@@ -300,14 +300,16 @@ __global__ void __launch_bounds__(128) k_score_g(SceneDev s, int P, int stride, 
     if (mode == 0) { x[0] = xs[3 * p]; x[1] = xs[3 * p + 1]; x[2] = xs[3 * p + 2]; }
   }
   __syncwarp();
+  __shared__ float4 reftex_s[WSIZE * 128];
+  float4* reftex = reftex_s + threadIdx.x;
   double f;
   if (mode == 0) {
     float c2[4], n2[4];
-    f = group_objective<WSIZE>(s, gc, x, gl, g, 0, c2, n2);
+    f = group_objective<WSIZE>(s, gc, x, gl, g, 0, c2, n2, reftex, 128);
   } else {
     CamDev refcam;
     load_cam(s, gc.size > 0 ? gc.ref : 0, refcam);
-    f = group_photo_score<WSIZE>(s, gc, refcam, coord, normal, gl, g, mode);
+    f = group_photo_score<WSIZE>(s, gc, refcam, coord, normal, gl, g, mode, reftex, 128);
   }
   if (p < P && gl == 0) out[p] = f;
 }
@@ -316,12 +318,14 @@ __global__ void __launch_bounds__(128) k_score_g(SceneDev s, int P, int stride, 
 // and runs its own Nelder-Mead (state in shared memory, advanced by the group leader); the four groups of a
 // warp evaluate their objectives in lock step.
 template <int WSIZE>
-__global__ void __launch_bounds__(128, 4) k_refine_g(SceneDev s, int P, int stride, float* __restrict__ coords, float* __restrict__ normals,
+__global__ void __launch_bounds__(128, 5) k_refine_g(SceneDev s, int P, int stride, float* __restrict__ coords, float* __restrict__ normals,
                                                      const int32_t* __restrict__ images, const int32_t* __restrict__ nimages,
                                                      const float* __restrict__ dscales, float* __restrict__ ncc_out,
                                                      int32_t* __restrict__ evals_out, uint8_t* __restrict__ ok_out,
                                                      int* __restrict__ counter) {
   __shared__ NMShared nms[4][4];  // [warp in CTA][group in warp]
+  __shared__ float4 reftex_s[WSIZE * 128];  // reference-view deviations, [row][thread]
+  float4* reftex = reftex_s + threadIdx.x;
   const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
   const unsigned gmask = 0xffu << (g * kGroup);
   NMShared& nm = nms[threadIdx.x >> 5][g];
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(128, 4) k_refine_g(SceneDev s, int P, int stri
     const int mode = (have && nm.state == NM_FINAL) ? 1 : 0;
     const double xt[3] = {nm.xt[0], nm.xt[1], nm.xt[2]};
     float rc[4], rn[4];
-    const double fx = group_objective<WSIZE>(s, gc, xt, gl, g, mode, rc, rn);
+    const double fx = group_objective<WSIZE>(s, gc, xt, gl, g, mode, rc, rn, reftex, 128);
     __syncwarp();
     if (have && gl == 0) nm_advance(nm, fx, s.xtol);
     __syncwarp();

@@ -40,7 +40,7 @@ __device__ __forceinline__ void get_color_fast(const LevelDev& lv, float x, floa
   const float dx1 = x - (float)lx, dx0 = 1.0f - dx1;
   const float dy1 = y - (float)ly, dy0 = 1.0f - dy1;
   const float f00 = dx0 * dy0, f01 = dx0 * dy1, f10 = dx1 * dy0, f11 = dx1 * dy1;
-  const uint32_t* p = reinterpret_cast<const uint32_t*>(lv.pix) + (size_t)ly * lv.w + lx;
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(lv.pix) + (ly * lv.w + lx);  // < 2^31 texels per level
   const uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + lv.w), d = __ldg(p + lv.w + 1);
   rgb[0] = (byte_to_float(a, 0x7540) * f00 + byte_to_float(c, 0x7540) * f01) + (byte_to_float(b, 0x7540) * f10 + byte_to_float(d, 0x7540) * f11);
   rgb[1] = (byte_to_float(a, 0x7541) * f00 + byte_to_float(c, 0x7541) * f01) + (byte_to_float(b, 0x7541) * f10 + byte_to_float(d, 0x7541) * f11);
@@ -133,71 +133,16 @@ __device__ __forceinline__ ViewWin view_window_c(const SceneDev& s, const CamDev
   return w;
 }
 
-// A view's texture held by one group: lane = column, v[row][channel].
+// One row of grabTex's sampling loop (optim.cpp:850-859) for a group: lane = column.  (bx, by) is the row's
+// first sample (the reference's running `left`), the column offset replays `vftmp += dx` add by add.
 template <int WSIZE>
-struct GroupTex {
-  float v[WSIZE][3];
-};
-
-// grabTex's sampling loop (optim.cpp:846-860) for the group's current view.  `w` is group-uniform;
-// `on` = this group samples this view.  Returns per-channel means (group-uniform) in ave[].
-// The row base advances by the reference's `left += dy`; the column offset replays `vftmp += dx`.
-template <int WSIZE>
-__device__ __forceinline__ void group_grab(const SceneDev& s, int index, const ViewWin& w, int gl, bool on, GroupTex<WSIZE>& tex,
-                                           float* ave) {
-  LevelDev lv;
-  lv.pix = nullptr; lv.w = 0; lv.h = 0;
-  if (on) lv = s.levels[index * s.nlevels + w.newlevel];
-  const bool mine = on && gl < WSIZE;
-  float bx = w.lx, by = w.ly;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+__device__ __forceinline__ void sample_row(const LevelDev& lv, const ViewWin& w, float bx, float by, int gl, bool mine, float* rgb) {
+  float x = bx, y = by;
 #pragma unroll
-  for (int row = 0; row < WSIZE; ++row) {
-    float x = bx, y = by;
-#pragma unroll
-    for (int i = 0; i < WSIZE - 1; ++i)
-      if (i < gl) { x += w.dxx; y += w.dxy; }
-    if (mine) {
-      get_color_fast(lv, x, y, tex.v[row]);
-    } else {
-      tex.v[row][0] = tex.v[row][1] = tex.v[row][2] = 0.0f;
-    }
-    s0 += tex.v[row][0]; s1 += tex.v[row][1]; s2 += tex.v[row][2];
-    bx += w.dyx; by += w.dyy;
-  }
-  constexpr float invn = 1.0f;  // keep the division below: mean = sum / N as in optim.cpp:1043
-  (void)invn;
-  ave[0] = group_sum(s0) / (float)(WSIZE * WSIZE);
-  ave[1] = group_sum(s1) / (float)(WSIZE * WSIZE);
-  ave[2] = group_sum(s2) / (float)(WSIZE * WSIZE);
-}
-
-// subtract the means in place and return the group's sum of squared deviations (optim.cpp:1045-1053)
-template <int WSIZE>
-__device__ __forceinline__ float group_center(GroupTex<WSIZE>& tex, const float* ave, int gl) {
-  float sq = 0.0f;
-  const bool mine = gl < WSIZE;
-#pragma unroll
-  for (int row = 0; row < WSIZE; ++row) {
-    const float d0 = mine ? tex.v[row][0] - ave[0] : 0.0f;
-    const float d1 = mine ? tex.v[row][1] - ave[1] : 0.0f;
-    const float d2 = mine ? tex.v[row][2] - ave[2] : 0.0f;
-    tex.v[row][0] = d0; tex.v[row][1] = d1; tex.v[row][2] = d2;
-    sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq);
-  }
-  return group_sum(sq);
-}
-
-template <int WSIZE>
-__device__ __forceinline__ float group_cross(const GroupTex<WSIZE>& a, const GroupTex<WSIZE>& b) {
-  float acc = 0.0f;
-#pragma unroll
-  for (int row = 0; row < WSIZE; ++row) {
-    acc = fmaf(a.v[row][0], b.v[row][0], acc);
-    acc = fmaf(a.v[row][1], b.v[row][1], acc);
-    acc = fmaf(a.v[row][2], b.v[row][2], acc);
-  }
-  return group_sum(acc);
+  for (int i = 0; i < WSIZE - 1; ++i)
+    if (i < gl) { x += w.dxx; y += w.dxy; }
+  rgb[0] = rgb[1] = rgb[2] = 0.0f;
+  if (mine) get_color_fast(lv, x, y, rgb);
 }
 
 // per-group patch context; every lane of the group holds the same values except my_image / my_weight
@@ -263,9 +208,19 @@ __device__ __forceinline__ void group_decode(const SceneDev& s, const GroupCtx& 
 // my_f's scoring (mode 0, optim.cpp:530-574) or computeINCC (mode 1 robust / 2 plain, optim.cpp:865-938) of the
 // patch (coord, normal) for the four groups of a warp.  Must be called by all 32 lanes; groups with
 // gc.size == 0 idle through.
+//
+// Texture statistics are STREAMED so that no texture lives in registers and the row loop can stay rolled
+// (code size: the refine loop has to fit the instruction cache; registers: occupancy):
+//   reference view : pass 1 samples the 7 rows, stores them in shared memory and sums them; pass 2 turns the
+//                    stored values into deviations from the channel means (normalize's two passes,
+//                    optim.cpp:1036-1053) and accumulates sum d^2;
+//   other views    : one pass; each sample b is pivoted by the REFERENCE view's channel mean (all views see the
+//                    same surface, so b' = b - mean_ref is almost centred and the raw-moment variance
+//                    sum b'^2 - (sum b')^2/N does not cancel), and sum d_ref * b' is the covariance.
+// `reftex` points at this thread's column of a [WSIZE][blockDim.x] float4 array in shared memory.
 template <int WSIZE>
 __device__ __forceinline__ double group_photo_score(const SceneDev& s, const GroupCtx& gc, const CamDev& refcam, const float* coord,
-                                                    const float* normal, int gl, int g, int mode) {
+                                                    const float* normal, int gl, int g, int mode, float4* reftex, int rstride) {
   const bool live = gc.size > 0;
   float px[4], py[4];
   get_paxes_c(refcam, s.level, coord, normal, px, py);
@@ -280,12 +235,17 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
   const unsigned validmask = (__ballot_sync(kFull, mine.newlevel >= 0) >> (g * kGroup)) & 0xffu;
   const bool have_ref = live && (validmask & 1u);
 
-  GroupTex<WSIZE> ref, cur;
+  constexpr float N = (float)(WSIZE * WSIZE);
+  constexpr float N3 = (float)(3 * WSIZE * WSIZE);
+  float ra0 = 0.f, ra1 = 0.f, ra2 = 0.f;   // reference channel means
+  float rd0 = 0.f, rd1 = 0.f, rd2 = 0.f;   // sum of reference deviations per channel (rounding residue, ~0)
   float sq_ref = 1.0f;
   double acc = 0.0;
   float totalweight = 0.0f;
   int denom = 0;
+  const bool col = gl < WSIZE;
   const int vmax = s.tau;
+#pragma unroll 1
   for (int v = 0; v < vmax; ++v) {
     const bool on = have_ref && ((validmask >> v) & 1u);
     if (!__any_sync(kFull, on)) continue;
@@ -296,22 +256,56 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
     w.newlevel = __shfl_sync(kFull, mine.newlevel, v, kGroup);
     const int index = __shfl_sync(kFull, gc.my_image, v, kGroup);
     const float wv = __shfl_sync(kFull, gc.my_weight, v, kGroup);
-    float ave[3];
-    group_grab<WSIZE>(s, index, w, gl, on, cur, ave);
-    const float sq_cur = group_center<WSIZE>(cur, ave, gl);
-    if (v == 0) {  // the reference view stays resident; the other views stream past it
-      ref = cur;
-      sq_ref = sq_cur;
+    LevelDev lv;
+    lv.pix = nullptr; lv.w = 0; lv.h = 0;
+    if (on) lv = s.levels[index * s.nlevels + w.newlevel];
+    const bool smp = on && col;
+    float bx = w.lx, by = w.ly;
+    if (v == 0) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int row = 0; row < WSIZE; ++row) {
+        float rgb[3];
+        sample_row<WSIZE>(lv, w, bx, by, gl, smp, rgb);
+        reftex[row * rstride] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+        s0 += rgb[0]; s1 += rgb[1]; s2 += rgb[2];
+        bx += w.dyx; by += w.dyy;
+      }
+      ra0 = group_sum(s0) / N; ra1 = group_sum(s1) / N; ra2 = group_sum(s2) / N;
+      float q = 0.f, d0s = 0.f, d1s = 0.f, d2s = 0.f;
+#pragma unroll 1
+      for (int row = 0; row < WSIZE; ++row) {
+        const float4 t = reftex[row * rstride];
+        const float d0 = smp ? t.x - ra0 : 0.0f, d1 = smp ? t.y - ra1 : 0.0f, d2 = smp ? t.z - ra2 : 0.0f;
+        reftex[row * rstride] = make_float4(d0, d1, d2, 0.0f);
+        q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q);
+        d0s += d0; d1s += d1; d2s += d2;
+      }
+      sq_ref = group_sum(q);
+      rd0 = group_sum(d0s); rd1 = group_sum(d1s); rd2 = group_sum(d2s);
       continue;
     }
-    const float cross = group_cross<WSIZE>(ref, cur);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, q = 0.f, cr = 0.f;
+#pragma unroll 1
+    for (int row = 0; row < WSIZE; ++row) {
+      float rgb[3];
+      sample_row<WSIZE>(lv, w, bx, by, gl, smp, rgb);
+      const float4 d = reftex[row * rstride];
+      const float b0 = smp ? rgb[0] - ra0 : 0.0f, b1 = smp ? rgb[1] - ra1 : 0.0f, b2 = smp ? rgb[2] - ra2 : 0.0f;
+      s0 += b0; s1 += b1; s2 += b2;
+      q = fmaf(b0, b0, q); q = fmaf(b1, b1, q); q = fmaf(b2, b2, q);
+      cr = fmaf(d.x, b0, cr); cr = fmaf(d.y, b1, cr); cr = fmaf(d.z, b2, cr);
+      bx += w.dyx; by += w.dyy;
+    }
+    s0 = group_sum(s0); s1 = group_sum(s1); s2 = group_sum(s2); q = group_sum(q); cr = group_sum(cr);
     if (on) {
-      // sd = sqrt(sq / 147), 0 -> 1 (optim.cpp:1055-1059); dot = sum(t_ref t_cur) / 147 (optim.cpp:1069-1077)
-      constexpr float n3 = (float)(3 * WSIZE * WSIZE);
-      float sda = sqrtf(sq_ref / n3), sdb = sqrtf(sq_cur / n3);
+      // sd = sqrt(sum dev^2 / 147), 0 -> 1 (optim.cpp:1055-1059); dot = sum(t_ref t_cur) / 147 (optim.cpp:1069-1077)
+      const float sq_cur = fmaxf(q - (s0 * s0 + s1 * s1 + s2 * s2) / N, 0.0f);
+      const float cross = cr - (s0 * rd0 + s1 * rd1 + s2 * rd2) / N;
+      float sda = sqrtf(sq_ref / N3), sdb = sqrtf(sq_cur / N3);
       if (sda == 0.0f) sda = 1.0f;
       if (sdb == 0.0f) sdb = 1.0f;
-      const float d = cross / (sda * sdb) / n3;
+      const float d = cross / (sda * sdb) / N3;
       if (mode == 0) {
         acc += (double)robustincc(1.0f - d);
         ++denom;
@@ -338,11 +332,11 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
 // my_f(x) / computeINCC at decode(x); coord/normal receive the decoded patch.
 template <int WSIZE>
 __device__ __forceinline__ double group_objective(const SceneDev& s, const GroupCtx& gc, const double* x, int gl, int g, int mode,
-                                                  float* coord, float* normal) {
+                                                  float* coord, float* normal, float4* reftex, int rstride) {
   CamDev refcam;
   load_cam(s, gc.size > 0 ? gc.ref : 0, refcam);  // 128 B, L1-resident; not kept in registers across the loop
   group_decode(s, gc, refcam.xaxis, refcam.yaxis, refcam.zaxis, x, gl, coord, normal);
-  return group_photo_score<WSIZE>(s, gc, refcam, coord, normal, gl, g, mode);
+  return group_photo_score<WSIZE>(s, gc, refcam, coord, normal, gl, g, mode, reftex, rstride);
 }
 
 // The Nelder-Mead state of one group, kept in SHARED memory (216 B per patch) and advanced by the group's
