@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libpmvs_b200.so")
+LIB_PATH = os.environ.get("PMVS_B200_LIB") or os.path.join(HERE, "lib", "libpmvs_b200.so")  # override: kernel experiments
 
 # every symbol include/pmvs_b200.h declares
 SYMBOLS = [

@@ -17,6 +17,10 @@
 #include "pmvs_device.cuh"
 #include "pmvs_group.cuh"
 
+#ifndef PMVS_MINBLOCKS
+#define PMVS_MINBLOCKS 6
+#endif
+
 using namespace pmvsb;
 
 // =====================================================================================================
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(128) k_score_g(SceneDev s, int P, int stride, 
 // and runs its own Nelder-Mead (state in shared memory, advanced by the group leader); the four groups of a
 // warp evaluate their objectives in lock step.
 template <int WSIZE>
-__global__ void __launch_bounds__(128, 5) k_refine_g(SceneDev s, int P, int stride, float* __restrict__ coords, float* __restrict__ normals,
+__global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, int P, int stride, float* __restrict__ coords, float* __restrict__ normals,
                                                      const int32_t* __restrict__ images, const int32_t* __restrict__ nimages,
                                                      const float* __restrict__ dscales, float* __restrict__ ncc_out,
                                                      int32_t* __restrict__ evals_out, uint8_t* __restrict__ ok_out,
@@ -550,6 +554,8 @@ void fill_scene(pmvsb_ctx* c) {
   for (int k = 0; k < s.n_level_thr && k < kMaxLevels; ++k) s.level_thr[k] = level_threshold(-c->level + k + 1, c->level);
   s.ascale = (float)(M_PI / 48.0f);
   s.xtol = c->xtol; s.step = c->step; s.maxeval = c->maxeval;
+  s.f32_2p23 = 0x4B000000u;
+  s.dummy_pix = c->images.empty() || c->images[0].levels.empty() ? nullptr : c->images[0].levels[0];
 }
 
 template <typename T>

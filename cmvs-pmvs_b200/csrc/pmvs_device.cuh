@@ -46,7 +46,22 @@ struct SceneDev {
   float ascale;            // (float)(M_PI / 48.0f)   (optim.cpp:590)
   double xtol, step;       // Nelder-Mead knobs (oracle/nm3.h is the written definition)
   int maxeval;
+  uint32_t f32_2p23;       // 0x4B000000, passed as data so PRMT keeps its immediate slot for the byte selector
+  const uchar4* dummy_pix; // any valid level (image 0, level 0): idle lanes sample texel (0,0) of it instead of branching
 };
+
+// IEEE f32 division / square root.  With PMVS_NOINLINE_DIV the ~13-instruction expansions (60 of them in the
+// refine loop) become calls to one shared copy: code size vs call overhead, decided by measurement.
+#ifndef PMVS_NOINLINE_DIV
+#define PMVS_NOINLINE_DIV 0
+#endif
+#if PMVS_NOINLINE_DIV
+__device__ __noinline__ float fdiv(float a, float b) { return a / b; }
+__device__ __noinline__ float fsqrt(float a) { return sqrtf(a); }
+#else
+__device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
+__device__ __forceinline__ float fsqrt(float a) { return sqrtf(a); }
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // small f32 helpers in reference operation order (include/numeric/vec3.hpp, vec4.hpp)
@@ -65,15 +80,15 @@ __device__ __forceinline__ void cross3(const float* u, const float* v, float* o)
 __device__ __forceinline__ void unitize3(float* v) {
   const float l = dot3(v, v);
   if (l != 1.0f && l != 0.0f) {
-    const float s = sqrtf(l);
-    v[0] /= s; v[1] /= s; v[2] /= s;
+    const float s = fsqrt(l);
+    v[0] = fdiv(v[0], s); v[1] = fdiv(v[1], s); v[2] = fdiv(v[2], s);
   }
 }
 __device__ __forceinline__ void unitize4(float* v) {
   const float l = dot4(v, v);
   if (l != 1.0f && l != 0.0f) {
-    const float s = sqrtf(l);
-    v[0] /= s; v[1] /= s; v[2] /= s; v[3] /= s;
+    const float s = fsqrt(l);
+    v[0] = fdiv(v[0], s); v[1] = fdiv(v[1], s); v[2] = fdiv(v[2], s); v[3] = fdiv(v[3], s);
   }
 }
 // std::min / std::max semantics (NaN handling differs from fminf/fmaxf)
@@ -97,7 +112,7 @@ __device__ __forceinline__ void project(const CamDev& cam, const float* X, float
     return;
   }
   const float z = o[2];
-  o[0] /= z; o[1] /= z; o[2] /= z;
+  o[0] = fdiv(o[0], z); o[1] = fdiv(o[1], z); o[2] = 1.0f;  // z / z == 1 exactly for finite z > 0
   const float lim = 2147483648.0f;  // (float)(INT_MAX - 3.0f) and -(float)(INT_MIN + 3.0f)
   o[0] = smax(-lim, smin(lim, o[0]));
   o[1] = smax(-lim, smin(lim, o[1]));
@@ -106,7 +121,7 @@ __device__ __forceinline__ void project(const CamDev& cam, const float* X, float
 // COptim::getUnit (optim.cpp:1116-1124): 2.0 * |X - C| * 2^level / ipscale, evaluated in double
 __device__ __forceinline__ float get_unit(const CamDev& cam, int level, const float* X) {
   const float d[4] = {X[0] - cam.centre[0], X[1] - cam.centre[1], X[2] - cam.centre[2], X[3] - cam.centre[3]};
-  const float fz = sqrtf(dot4(d, d));
+  const float fz = fsqrt(dot4(d, d));
   if (cam.ipscale == 0.0f) return 1.0f;
   return (float)(2.0 * (double)fz * (double)(1 << level) / (double)cam.ipscale);
 }

@@ -29,22 +29,23 @@ __device__ __forceinline__ float group_sum(float v) {
 }
 
 // u8 -> f32 without the conversion (XU) pipe: splice the byte under the exponent of 2^23, subtract 2^23.
-__device__ __forceinline__ float byte_to_float(uint32_t word, uint32_t selector) {
-  return __uint_as_float(__byte_perm(word, 0x4B000000u, selector)) - 8388608.0f;
+// `magic` = 0x4B000000 comes in as data (SceneDev::f32_2p23) so the selector can be PRMT's immediate.
+__device__ __forceinline__ float byte_to_float(uint32_t word, uint32_t magic, uint32_t selector) {
+  return __uint_as_float(__byte_perm(word, magic, selector)) - 8388608.0f;
 }
 
 // CImage::getColor (include/image/image.hpp:435-476) on RGBA8 words; same operation order as get_color().
-__device__ __forceinline__ void get_color_fast(const LevelDev& lv, float x, float y, float* rgb) {
+__device__ __forceinline__ void get_color_fast(const uint32_t* __restrict__ pix, int w, uint32_t magic, float x, float y, float* rgb) {
   const int lx = (int)x;
   const int ly = (int)y;
   const float dx1 = x - (float)lx, dx0 = 1.0f - dx1;
   const float dy1 = y - (float)ly, dy0 = 1.0f - dy1;
   const float f00 = dx0 * dy0, f01 = dx0 * dy1, f10 = dx1 * dy0, f11 = dx1 * dy1;
-  const uint32_t* p = reinterpret_cast<const uint32_t*>(lv.pix) + (ly * lv.w + lx);  // < 2^31 texels per level
-  const uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + lv.w), d = __ldg(p + lv.w + 1);
-  rgb[0] = (byte_to_float(a, 0x7540) * f00 + byte_to_float(c, 0x7540) * f01) + (byte_to_float(b, 0x7540) * f10 + byte_to_float(d, 0x7540) * f11);
-  rgb[1] = (byte_to_float(a, 0x7541) * f00 + byte_to_float(c, 0x7541) * f01) + (byte_to_float(b, 0x7541) * f10 + byte_to_float(d, 0x7541) * f11);
-  rgb[2] = (byte_to_float(a, 0x7542) * f00 + byte_to_float(c, 0x7542) * f01) + (byte_to_float(b, 0x7542) * f10 + byte_to_float(d, 0x7542) * f11);
+  const uint32_t* p = pix + (ly * w + lx);  // < 2^31 texels per level
+  const uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + w), d = __ldg(p + w + 1);
+  rgb[0] = (byte_to_float(a, magic, 0x7540) * f00 + byte_to_float(c, magic, 0x7540) * f01) + (byte_to_float(b, magic, 0x7540) * f10 + byte_to_float(d, magic, 0x7540) * f11);
+  rgb[1] = (byte_to_float(a, magic, 0x7541) * f00 + byte_to_float(c, magic, 0x7541) * f01) + (byte_to_float(b, magic, 0x7541) * f10 + byte_to_float(d, magic, 0x7541) * f11);
+  rgb[2] = (byte_to_float(a, magic, 0x7542) * f00 + byte_to_float(c, magic, 0x7542) * f01) + (byte_to_float(b, magic, 0x7542) * f10 + byte_to_float(d, magic, 0x7542) * f11);
 }
 
 // ---- compact (code-size conscious) variants: the refine loop must stay inside the instruction cache ----
@@ -70,11 +71,11 @@ __device__ __forceinline__ void get_paxes_c(const CamDev& cam, int level, const 
     for (int k = 0; k < 4; ++k) t[k] = coord[k] + (a == 0 ? px[k] : py[k]);
     project(cam, t, c1);
     const float d[3] = {c1[0] - c0[0], c1[1] - c0[1], c1[2] - c0[2]};
-    const float dis = sqrtf(dot3(d, d));
+    const float dis = fsqrt(dot3(d, d));
     if (a == 0) dis0 = dis; else dis1 = dis;
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { px[k] /= dis0; py[k] /= dis1; }
+  for (int k = 0; k < 4; ++k) { px[k] = fdiv(px[k], dis0); py[k] = fdiv(py[k], dis1); }
 }
 
 template <int WSIZE>
@@ -98,7 +99,7 @@ __device__ __forceinline__ ViewWin view_window_c(const SceneDev& s, const CamDev
     for (int k = 0; k < 4; ++k) t[k] = coord[k] + (a == 0 ? px[k] : py[k]);
     project(cam, t, q);
     const float d[3] = {q[0] - center[0], q[1] - center[1], q[2] - center[2]};
-    const float len = sqrtf(dot3(d, d));
+    const float len = fsqrt(dot3(d, d));
     if (a == 0) { dx[0] = d[0]; dx[1] = d[1]; nrm = len; }
     else { dy[0] = d[0]; dy[1] = d[1]; nrm = nrm + len; }   // norm(dx) + norm(dy), optim.cpp:831
   }
@@ -109,9 +110,11 @@ __device__ __forceinline__ ViewWin view_window_c(const SceneDev& s, const CamDev
     if (ratio >= s.level_thr[k]) ++leveldif;
   const int newlevel = s.level + leveldif;
   const float scale = (leveldif >= 0) ? (float)(1 << leveldif) : 1.0f / (float)(1 << (-leveldif));  // MyPow2
-  center[0] /= scale; center[1] /= scale;
-  dx[0] /= scale; dx[1] /= scale;
-  dy[0] /= scale; dy[1] /= scale;
+  // scale is a power of two: multiplying by its (exact) reciprocal gives the bits of the reference's division
+  const float iscale = (leveldif >= 0) ? 1.0f / (float)(1 << leveldif) : (float)(1 << (-leveldif));
+  center[0] *= iscale; center[1] *= iscale;
+  dx[0] *= iscale; dx[1] *= iscale;
+  dy[0] *= iscale; dy[1] *= iscale;
 
   constexpr float m = (float)(WSIZE / 2);
   float lo[2], hi[2];
@@ -133,16 +136,32 @@ __device__ __forceinline__ ViewWin view_window_c(const SceneDev& s, const CamDev
   return w;
 }
 
-// One row of grabTex's sampling loop (optim.cpp:850-859) for a group: lane = column.  (bx, by) is the row's
-// first sample (the reference's running `left`), the column offset replays `vftmp += dx` add by add.
+// Column offsets of one view for this lane.  The reference walks a row with `vftmp += dx` (optim.cpp:858); lane
+// `gl` replays its first `gl` additions and pads with +0.0f (exact), so every row costs 2*(WSIZE-1) plain FADDs.
 template <int WSIZE>
-__device__ __forceinline__ void sample_row(const LevelDev& lv, const ViewWin& w, float bx, float by, int gl, bool mine, float* rgb) {
+struct ColSteps {
+  float sx[WSIZE - 1], sy[WSIZE - 1];
+  __device__ __forceinline__ void set(const ViewWin& w, int gl) {
+#pragma unroll
+    for (int i = 0; i < WSIZE - 1; ++i) { sx[i] = i < gl ? w.dxx : 0.0f; sy[i] = i < gl ? w.dxy : 0.0f; }
+  }
+};
+
+// One sample of grabTex's loop (optim.cpp:850-859): (bx, by) is the row's first sample (the reference's running
+// `left`).  Idle lanes pass pix = SceneDev::dummy_pix and sample texel (0,0) of it: no branch in the row loop.
+template <int WSIZE>
+__device__ __forceinline__ void sample_row(const uint32_t* __restrict__ pix, int w, uint32_t magic, const ColSteps<WSIZE>& cs,
+                                           float bx, float by, float* rgb) {
+#if PMVS_FAST_POS
   float x = bx, y = by;
 #pragma unroll
-  for (int i = 0; i < WSIZE - 1; ++i)
-    if (i < gl) { x += w.dxx; y += w.dxy; }
-  rgb[0] = rgb[1] = rgb[2] = 0.0f;
-  if (mine) get_color_fast(lv, x, y, rgb);
+  for (int i = 0; i < WSIZE - 1; ++i) { x += cs.sx[i]; y += cs.sy[i]; }
+#else
+  float x = bx, y = by;
+#pragma unroll
+  for (int i = 0; i < WSIZE - 1; ++i) { x += cs.sx[i]; y += cs.sy[i]; }
+#endif
+  get_color_fast(pix, w, magic, x, y, rgb);
 }
 
 // per-group patch context; every lane of the group holds the same values except my_image / my_weight
@@ -184,6 +203,47 @@ __device__ __forceinline__ void group_ctx_init(const SceneDev& s, GroupCtx& gc, 
   gc.my_weight = gl == 0 ? 1.0f : smin(1.0f, u0 / unit);
 }
 
+#ifndef PMVS_CUSTOM_SINCOS
+#define PMVS_CUSTOM_SINCOS 0
+#endif
+#ifndef PMVS_FAST_POS
+#define PMVS_FAST_POS 0
+#endif
+#ifndef PMVS_ROW_UNROLL
+#define PMVS_ROW_UNROLL 1
+#endif
+#define PMVS_STR2(x) #x
+#define PMVS_STR(x) PMVS_STR2(x)
+#define PMVS_UNROLL_ROWS _Pragma(PMVS_STR(unroll PMVS_ROW_UNROLL))
+
+// sin and cos in double for |a| <= pi/2 (the optimiser's angles are boxed to +-23.99999 * pi/48): one
+// quadrant fold plus the classic degree-13/12 minimax kernels (fdlibm's __kernel_sin / __kernel_cos
+// coefficients), < 2 ulp.  libm-style sincos() costs ~10x the code for range reduction that can never
+// trigger here; code size matters because the refine loop has to stay inside the instruction cache.
+__device__ __forceinline__ void sincos_quadrant(double a, double* sn, double* cs) {
+  const double pio4 = 0.78539816339744828, pio2_hi = 1.57079632673412561417e+00, pio2_lo = 6.07710050650619224932e-11;
+  double r = a;
+  int q = 0;
+  if (a > pio4) { r = (a - pio2_hi) - pio2_lo; q = 1; }
+  else if (a < -pio4) { r = (a + pio2_hi) + pio2_lo; q = -1; }
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double sr = fma(z * r, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double cr = 1.0 - (0.5 * z - z * z * pc);
+  if (q == 0) { *sn = sr; *cs = cr; }
+  else if (q == 1) { *sn = cr; *cs = -sr; }
+  else { *sn = -cr; *cs = sr; }
+}
+
 // COptim::decode (optim.cpp:690-707) for four groups at once; lanes 0/1 of each group evaluate the
 // double-precision sincos of angle1/angle2.
 __device__ __forceinline__ void group_decode(const SceneDev& s, const GroupCtx& gc, const float* xaxis, const float* yaxis,
@@ -194,7 +254,14 @@ __device__ __forceinline__ void group_decode(const SceneDev& s, const GroupCtx& 
   const float angle1 = (float)(x[1] * (double)s.ascale);
   const float angle2 = (float)(x[2] * (double)s.ascale);
   double sn = 0.0, cs = 0.0;
-  if (gl < 2) sincos((double)(gl == 0 ? angle1 : angle2), &sn, &cs);
+  if (gl < 2) {
+    const double a = (double)(gl == 0 ? angle1 : angle2);
+#if PMVS_CUSTOM_SINCOS
+    if (fabs(a) <= 1.5707963267948968) sincos_quadrant(a, &sn, &cs); else sincos(a, &sn, &cs);
+#else
+    sincos(a, &sn, &cs);
+#endif
+  }
   const double s1 = __shfl_sync(kFull, sn, 0, kGroup), c1 = __shfl_sync(kFull, cs, 0, kGroup);
   const double s2 = __shfl_sync(kFull, sn, 1, kGroup), c2 = __shfl_sync(kFull, cs, 1, kGroup);
   const float fx = (float)(s1 * c2);
@@ -256,56 +323,62 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
     w.newlevel = __shfl_sync(kFull, mine.newlevel, v, kGroup);
     const int index = __shfl_sync(kFull, gc.my_image, v, kGroup);
     const float wv = __shfl_sync(kFull, gc.my_weight, v, kGroup);
-    LevelDev lv;
-    lv.pix = nullptr; lv.w = 0; lv.h = 0;
-    if (on) lv = s.levels[index * s.nlevels + w.newlevel];
     const bool smp = on && col;
-    float bx = w.lx, by = w.ly;
-    if (v == 0) {
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-      for (int row = 0; row < WSIZE; ++row) {
-        float rgb[3];
-        sample_row<WSIZE>(lv, w, bx, by, gl, smp, rgb);
-        reftex[row * rstride] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
-        s0 += rgb[0]; s1 += rgb[1]; s2 += rgb[2];
-        bx += w.dyx; by += w.dyy;
-      }
-      ra0 = group_sum(s0) / N; ra1 = group_sum(s1) / N; ra2 = group_sum(s2) / N;
-      float q = 0.f, d0s = 0.f, d1s = 0.f, d2s = 0.f;
-#pragma unroll 1
-      for (int row = 0; row < WSIZE; ++row) {
-        const float4 t = reftex[row * rstride];
-        const float d0 = smp ? t.x - ra0 : 0.0f, d1 = smp ? t.y - ra1 : 0.0f, d2 = smp ? t.z - ra2 : 0.0f;
-        reftex[row * rstride] = make_float4(d0, d1, d2, 0.0f);
-        q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q);
-        d0s += d0; d1s += d1; d2s += d2;
-      }
-      sq_ref = group_sum(q);
-      rd0 = group_sum(d0s); rd1 = group_sum(d1s); rd2 = group_sum(d2s);
-      continue;
+    // lanes that do not sample (8th lane, rejected view, idle group) read texel (0,0) of a dummy level
+    const uint32_t* pix = reinterpret_cast<const uint32_t*>(s.dummy_pix);
+    int lw = 0;
+    float bx = 0.0f, by = 0.0f;
+    ColSteps<WSIZE> cs;
+    ViewWin wz = w;
+    if (!smp) { wz.dxx = wz.dxy = wz.dyx = wz.dyy = 0.0f; }
+    if (on) {
+      const LevelDev lv = s.levels[index * s.nlevels + w.newlevel];
+      if (col) { pix = reinterpret_cast<const uint32_t*>(lv.pix); lw = lv.w; bx = w.lx; by = w.ly; }
     }
+    cs.set(wz, gl);
+    // ONE sampling loop for every view (a second copy of the loop body costs instruction-cache misses):
+    // the reference view (v == 0) runs it with ra = 0, i.e. b = raw sample, and additionally stores the row.
+    const bool is_ref = v == 0;
+    if (is_ref) { ra0 = ra1 = ra2 = 0.0f; }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, q = 0.f, cr = 0.f;
-#pragma unroll 1
+    PMVS_UNROLL_ROWS
     for (int row = 0; row < WSIZE; ++row) {
       float rgb[3];
-      sample_row<WSIZE>(lv, w, bx, by, gl, smp, rgb);
+      sample_row<WSIZE>(pix, lw, s.f32_2p23, cs, bx, by, rgb);
       const float4 d = reftex[row * rstride];
-      const float b0 = smp ? rgb[0] - ra0 : 0.0f, b1 = smp ? rgb[1] - ra1 : 0.0f, b2 = smp ? rgb[2] - ra2 : 0.0f;
+      if (is_ref) reftex[row * rstride] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+      const float b0 = rgb[0] - ra0, b1 = rgb[1] - ra1, b2 = rgb[2] - ra2;
       s0 += b0; s1 += b1; s2 += b2;
       q = fmaf(b0, b0, q); q = fmaf(b1, b1, q); q = fmaf(b2, b2, q);
       cr = fmaf(d.x, b0, cr); cr = fmaf(d.y, b1, cr); cr = fmaf(d.z, b2, cr);
-      bx += w.dyx; by += w.dyy;
+      bx += wz.dyx; by += wz.dyy;
     }
-    s0 = group_sum(s0); s1 = group_sum(s1); s2 = group_sum(s2); q = group_sum(q); cr = group_sum(cr);
+    s0 = group_sum(smp ? s0 : 0.0f); s1 = group_sum(smp ? s1 : 0.0f); s2 = group_sum(smp ? s2 : 0.0f);
+    if (is_ref) {
+      // normalize's two passes (optim.cpp:1036-1053): channel means, then deviations and their squares
+      ra0 = fdiv(s0, N); ra1 = fdiv(s1, N); ra2 = fdiv(s2, N);
+      float qq = 0.f, d0s = 0.f, d1s = 0.f, d2s = 0.f;
+#pragma unroll 1
+      for (int row = 0; row < WSIZE; ++row) {
+        const float4 t = reftex[row * rstride];
+        const float d0 = t.x - ra0, d1 = t.y - ra1, d2 = t.z - ra2;
+        reftex[row * rstride] = make_float4(d0, d1, d2, 0.0f);   // a non-sampling lane's column is read by itself only
+        qq = fmaf(d0, d0, qq); qq = fmaf(d1, d1, qq); qq = fmaf(d2, d2, qq);
+        d0s += d0; d1s += d1; d2s += d2;
+      }
+      sq_ref = group_sum(smp ? qq : 0.0f);
+      rd0 = group_sum(smp ? d0s : 0.0f); rd1 = group_sum(smp ? d1s : 0.0f); rd2 = group_sum(smp ? d2s : 0.0f);
+      continue;
+    }
+    q = group_sum(smp ? q : 0.0f); cr = group_sum(smp ? cr : 0.0f);
     if (on) {
       // sd = sqrt(sum dev^2 / 147), 0 -> 1 (optim.cpp:1055-1059); dot = sum(t_ref t_cur) / 147 (optim.cpp:1069-1077)
       const float sq_cur = fmaxf(q - (s0 * s0 + s1 * s1 + s2 * s2) / N, 0.0f);
       const float cross = cr - (s0 * rd0 + s1 * rd1 + s2 * rd2) / N;
-      float sda = sqrtf(sq_ref / N3), sdb = sqrtf(sq_cur / N3);
+      float sda = fsqrt(fdiv(sq_ref, N3)), sdb = fsqrt(fdiv(sq_cur, N3));
       if (sda == 0.0f) sda = 1.0f;
       if (sdb == 0.0f) sdb = 1.0f;
-      const float d = cross / (sda * sdb) / N3;
+      const float d = fdiv(fdiv(cross, sda * sdb), N3);
       if (mode == 0) {
         acc += (double)robustincc(1.0f - d);
         ++denom;
@@ -366,84 +439,75 @@ __device__ __forceinline__ void nm_start(NMShared& n, const double* x, double st
   n.fr = 0.0; n.fref = 0.0;
 }
 
-// vertex k holds a new point: move it down past strictly worse predecessors (stable)
-__device__ __noinline__ void nm_insert(NMShared& n, int k) {
-  const double t0 = n.p[k][0], t1 = n.p[k][1], t2 = n.p[k][2], tf = n.f[k];
-  int q = k;
-  while (q > 0 && tf < n.f[q - 1]) {
-    n.p[q][0] = n.p[q - 1][0]; n.p[q][1] = n.p[q - 1][1]; n.p[q][2] = n.p[q - 1][2];
-    n.f[q] = n.f[q - 1];
-    --q;
-  }
-  n.p[q][0] = t0; n.p[q][1] = t1; n.p[q][2] = t2; n.f[q] = tf;
-}
-
-// consume f(xt) and choose the next point (leader lane only)
-__device__ __noinline__ void nm_advance(NMShared& n, double fx, double xtol) {
+// consume f(xt) and choose the next point (leader lane only).  Inlined into the kernel so that `n` is known to
+// be shared memory (32-bit LDS/STS), with ONE copy of the insertion loop: every branch only decides which
+// vertices [ins_lo, ins_hi] hold new points that must be moved down past strictly worse predecessors (stable).
+__device__ __forceinline__ void nm_advance(NMShared& n, double fx, double xtol) {
   const double lb1 = -23.99999, ub1 = 23.99999;
   if (n.state == NM_FINAL) { n.fr = fx; n.state = NM_DONE_OK; return; }
   ++n.cnt;
+  int ins_lo = 1, ins_hi = 0;   // empty range
   bool new_iter = false;
-  switch (n.state) {
-    case NM_INIT:
-      n.f[n.idx] = fx;
-      nm_insert(n, n.idx);
-      ++n.idx;
-      if (n.idx <= 3) { for (int j = 0; j < 3; ++j) n.xt[j] = n.p[n.idx][j]; }
-      else new_iter = true;
-      break;
-    case NM_REFLECT:
-      n.fr = fx;
-      if (fx < n.f[0]) {
-        n.xt[0] = n.c[0] + 2.0 * (n.c[0] - n.p[3][0]);
-        n.xt[1] = clampd(n.c[1] + 2.0 * (n.c[1] - n.p[3][1]), lb1, ub1);
-        n.xt[2] = clampd(n.c[2] + 2.0 * (n.c[2] - n.p[3][2]), lb1, ub1);
-        n.state = NM_EXPAND;
-      } else if (fx < n.f[2]) {
-        for (int j = 0; j < 3; ++j) n.p[3][j] = n.xr[j];
-        n.f[3] = fx;
-        nm_insert(n, 3);
-        new_iter = true;
-      } else {
-        if (fx < n.f[3]) {
-          for (int j = 0; j < 3; ++j) n.xt[j] = n.c[j] + 0.5 * (n.xr[j] - n.c[j]);
-          n.fref = fx;
-        } else {
-          for (int j = 0; j < 3; ++j) n.xt[j] = n.c[j] + 0.5 * (n.p[3][j] - n.c[j]);
-          n.fref = n.f[3];
-        }
-        n.state = NM_CONTRACT;
-      }
-      break;
-    case NM_EXPAND:
-      if (fx < n.fr) { for (int j = 0; j < 3; ++j) n.p[3][j] = n.xt[j]; n.f[3] = fx; }
-      else { for (int j = 0; j < 3; ++j) n.p[3][j] = n.xr[j]; n.f[3] = n.fr; }
-      nm_insert(n, 3);
+  const int st = n.state;
+  if (st == NM_INIT) {
+    n.f[n.idx] = fx;
+    ins_lo = ins_hi = n.idx;
+    ++n.idx;
+    if (n.idx <= 3) { for (int j = 0; j < 3; ++j) n.xt[j] = n.p[n.idx][j]; }
+    else new_iter = true;
+  } else if (st == NM_REFLECT) {
+    n.fr = fx;
+    if (fx < n.f[0]) {
+      n.xt[0] = n.c[0] + 2.0 * (n.c[0] - n.p[3][0]);
+      n.xt[1] = clampd(n.c[1] + 2.0 * (n.c[1] - n.p[3][1]), lb1, ub1);
+      n.xt[2] = clampd(n.c[2] + 2.0 * (n.c[2] - n.p[3][2]), lb1, ub1);
+      n.state = NM_EXPAND;
+    } else if (fx < n.f[2]) {
+      for (int j = 0; j < 3; ++j) n.p[3][j] = n.xr[j];
+      n.f[3] = fx;
+      ins_lo = ins_hi = 3;
       new_iter = true;
-      break;
-    case NM_CONTRACT:
-      if (fx < n.fref) {
-        for (int j = 0; j < 3; ++j) n.p[3][j] = n.xt[j];
-        n.f[3] = fx;
-        nm_insert(n, 3);
-        new_iter = true;
-      } else {
-        for (int i = 1; i <= 3; ++i)
-          for (int j = 0; j < 3; ++j) n.p[i][j] = n.p[0][j] + 0.5 * (n.p[i][j] - n.p[0][j]);
-        n.state = NM_SHRINK;
-        n.idx = 1;
-        for (int j = 0; j < 3; ++j) n.xt[j] = n.p[1][j];
-      }
-      break;
-    default:  // NM_SHRINK
-      n.f[n.idx] = fx;
-      ++n.idx;
-      if (n.idx <= 3) { for (int j = 0; j < 3; ++j) n.xt[j] = n.p[n.idx][j]; }
-      else { nm_insert(n, 1); nm_insert(n, 2); nm_insert(n, 3); new_iter = true; }
-      break;
+    } else {
+      const bool outside = fx < n.f[3];
+      for (int j = 0; j < 3; ++j) n.xt[j] = n.c[j] + 0.5 * ((outside ? n.xr[j] : n.p[3][j]) - n.c[j]);
+      n.fref = outside ? fx : n.f[3];
+      n.state = NM_CONTRACT;
+    }
+  } else if (st == NM_EXPAND || st == NM_CONTRACT) {
+    const bool take_xt = st == NM_EXPAND ? (fx < n.fr) : (fx < n.fref);
+    if (take_xt || st == NM_EXPAND) {
+      for (int j = 0; j < 3; ++j) n.p[3][j] = take_xt ? n.xt[j] : n.xr[j];
+      n.f[3] = take_xt ? fx : n.fr;
+      ins_lo = ins_hi = 3;
+      new_iter = true;
+    } else {  // failed contraction: shrink towards the best vertex, re-evaluate vertices 1..3 in order
+      for (int i = 1; i <= 3; ++i)
+        for (int j = 0; j < 3; ++j) n.p[i][j] = n.p[0][j] + 0.5 * (n.p[i][j] - n.p[0][j]);
+      n.state = NM_SHRINK;
+      n.idx = 1;
+      for (int j = 0; j < 3; ++j) n.xt[j] = n.p[1][j];
+    }
+  } else {  // NM_SHRINK
+    n.f[n.idx] = fx;
+    ++n.idx;
+    if (n.idx <= 3) { for (int j = 0; j < 3; ++j) n.xt[j] = n.p[n.idx][j]; }
+    else { ins_lo = 1; ins_hi = 3; new_iter = true; }
+  }
+#pragma unroll 1
+  for (int k = ins_lo; k <= ins_hi; ++k) {
+    const double t0 = n.p[k][0], t1 = n.p[k][1], t2 = n.p[k][2], tf = n.f[k];
+    int q = k;
+#pragma unroll 1
+    while (q > 0 && tf < n.f[q - 1]) {
+      n.p[q][0] = n.p[q - 1][0]; n.p[q][1] = n.p[q - 1][1]; n.p[q][2] = n.p[q - 1][2];
+      n.f[q] = n.f[q - 1];
+      --q;
+    }
+    n.p[q][0] = t0; n.p[q][1] = t1; n.p[q][2] = t2; n.f[q] = tf;
   }
   if (new_iter) {
     double size = 0.0;
+#pragma unroll 1
     for (int i = 1; i <= 3; ++i)
       for (int j = 0; j < 3; ++j) {
         const double d = fabs(n.p[i][j] - n.p[0][j]);
