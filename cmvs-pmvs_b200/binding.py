@@ -19,7 +19,8 @@ SYMBOLS = [
     "pmvsb_create", "pmvsb_destroy", "pmvsb_last_error", "pmvsb_version", "pmvsb_upload_camera", "pmvsb_upload_image",
     "pmvsb_set_visdata2", "pmvsb_finalize_scene", "pmvsb_set_thresholds", "pmvsb_set_optimizer", "pmvsb_image_dims",
     "pmvsb_download_image", "pmvsb_get_camera", "pmvsb_project_batch", "pmvsb_grab_tex_batch", "pmvsb_eval_objective_batch",
-    "pmvsb_compute_incc_batch", "pmvsb_set_inccs_batch", "pmvsb_set_scales_batch", "pmvsb_refine_batch",
+    "pmvsb_compute_incc_batch", "pmvsb_set_inccs_batch", "pmvsb_set_scales_batch", "pmvsb_pre_process_batch",
+    "pmvsb_post_process_batch", "pmvsb_refine_batch",
     "pmvsb_refine_batch_dev", "pmvsb_sync", "pmvsb_stream", "pmvsb_set_stream", "pmvsb_launch_count", "pmvsb_last_refine_ms",
 ]
 
@@ -179,6 +180,24 @@ class PmvsB200:
         d = np.zeros(P, np.float32); a = np.zeros(P, np.float32)
         self._ck(self.lib.pmvsb_set_scales_batch(self.ctx, P, stride, _vp(coords), _vp(images), _vp(nimages), _vp(d), _vp(a)))
         return d, a
+
+    def pre_process_batch(self, coords, normals, images, nimages):
+        """-> dict(images (P,stride), nimages, dscale, ascale, verdict); inputs are not modified."""
+        P, stride, coords, normals, images, nimages, _ = _patch_arrays(coords, normals, images, nimages)
+        im = images.copy(); n = nimages.copy()
+        d = np.zeros(P, np.float32); a = np.zeros(P, np.float32); v = np.zeros(P, np.int32)
+        self._ck(self.lib.pmvsb_pre_process_batch(self.ctx, P, stride, _vp(coords), _vp(normals), _vp(im), _vp(n), _vp(d), _vp(a), _vp(v)))
+        return dict(images=im, nimages=n, dscale=d, ascale=a, verdict=v)
+
+    def post_process_batch(self, coords, normals, ncc, images, nimages):
+        """-> dict(images, nimages, grids (P,stride,2), timages, tmp, verdict)   (_depth == 0 semantics)"""
+        P, stride, coords, normals, images, nimages, _ = _patch_arrays(coords, normals, images, nimages)
+        ncc = _f32(ncc).reshape(P)
+        im = images.copy(); n = nimages.copy()
+        g = np.full((P, stride, 2), -1, np.int32); t = np.zeros(P, np.int32); tmp = np.zeros(P, np.float32); v = np.zeros(P, np.int32)
+        self._ck(self.lib.pmvsb_post_process_batch(self.ctx, P, stride, _vp(coords), _vp(normals), _vp(ncc), _vp(im), _vp(n), _vp(g), _vp(t),
+                                                   _vp(tmp), _vp(v)))
+        return dict(images=im, nimages=n, grids=g, timages=t, tmp=tmp, verdict=v)
 
     def refine_batch(self, coords, normals, images, dscales, nimages=None):
         """-> dict(coords, normals, ncc, evals, ok); inputs are not modified."""

@@ -16,6 +16,7 @@
 
 #include "pmvs_device.cuh"
 #include "pmvs_group.cuh"
+#include "pmvs_select.cuh"
 
 #ifndef PMVS_MINBLOCKS
 #define PMVS_MINBLOCKS 6
@@ -401,6 +402,53 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
   }
 }
 
+
+// ---- K4: visible-image-set selection (pmvs_select.cuh): one warp (= one CTA) per patch ----------------
+template <int WSIZE>
+__global__ void __launch_bounds__(32) k_pre_process(SceneDev s, SelectParams sp, int P, int stride, const float* __restrict__ coords,
+                                                    const float* __restrict__ normals, int32_t* __restrict__ images,
+                                                    int32_t* __restrict__ nimages, float* __restrict__ dscale,
+                                                    float* __restrict__ ascale, int32_t* __restrict__ verdict) {
+  __shared__ SelScratch<WSIZE> sc;
+  const int p = blockIdx.x, lane = threadIdx.x;
+  if (p >= P) return;
+  float coord[4], normal[4];
+  load_patch(coords, normals, p, coord, normal);
+  const int cap = min(stride, kSelMaxViews);
+  int n = min(nimages[p], cap);
+  for (int i = lane; i < n; i += 32) sc.images[i] = images[(size_t)p * stride + i];
+  __syncwarp();
+  float ds = 0.0f, as = 0.0f;
+  int v = 1;
+  if (n > 0) v = sel_pre_process<WSIZE>(s, sp, sc, n, cap, lane, coord, normal, ds, as);
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) images[(size_t)p * stride + i] = sc.images[i];
+  if (lane == 0) { nimages[p] = n; dscale[p] = ds; ascale[p] = as; verdict[p] = v; }
+}
+
+template <int WSIZE>
+__global__ void __launch_bounds__(32) k_post_process(SceneDev s, SelectParams sp, int P, int stride, const float* __restrict__ coords,
+                                                     const float* __restrict__ normals, const float* __restrict__ ncc,
+                                                     int32_t* __restrict__ images, int32_t* __restrict__ nimages,
+                                                     int32_t* __restrict__ grids, int32_t* __restrict__ timages,
+                                                     float* __restrict__ tmp, int32_t* __restrict__ verdict) {
+  __shared__ SelScratch<WSIZE> sc;
+  const int p = blockIdx.x, lane = threadIdx.x;
+  if (p >= P) return;
+  float coord[4], normal[4];
+  load_patch(coords, normals, p, coord, normal);
+  const int cap = min(stride, kSelMaxViews);
+  int n = min(nimages[p], cap);
+  for (int i = lane; i < n; i += 32) sc.images[i] = images[(size_t)p * stride + i];
+  __syncwarp();
+  int t = 0;
+  float tm = 0.0f;
+  const int v = sel_post_process<WSIZE>(s, sp, sc, n, cap, lane, coord, normal, ncc[p], grids + (size_t)2 * p * stride, t, tm);
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) images[(size_t)p * stride + i] = sc.images[i];
+  if (lane == 0) { nimages[p] = n; timages[p] = t; tmp[p] = tm; verdict[p] = v; }
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -430,6 +478,9 @@ struct pmvsb_ctx {
   CamDev* d_cams = nullptr;
   LevelDev* d_levels = nullptr;
   int* d_counter = nullptr;
+  int32_t* d_vis_off = nullptr;
+  int32_t* d_vis_idx = nullptr;
+  SelectParams select;
   bool finalized = false;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
@@ -536,6 +587,41 @@ float level_threshold(int target, int level) {
     if (leveldif_of(val(mid), level) >= target) hi = mid; else lo = mid + 1;
   }
   return val(lo);
+}
+
+
+// ---- float bisection helpers: integer decisions that the reference takes through libm are tabulated -------
+uint32_t float_key(float f) {  // order-preserving map float -> uint32
+  uint32_t b; std::memcpy(&b, &f, 4);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+float key_float(uint32_t k) {
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  float f; std::memcpy(&f, &b, 4);
+  return f;
+}
+// the reference's angle of a clamped dot product (source/image/photoSetS.cpp:176-177)
+float angle_of(float d) { return (float)std::acos((double)d); }
+
+void fill_select(pmvsb_ctx* c) {
+  SelectParams& sp = c->select;
+  sp.vis_off = c->d_vis_off; sp.vis_idx = c->d_vis_idx;
+  sp.cos_angle0_f = (float)std::cos((double)c->angle_threshold0);          // optim.cpp:416
+  sp.sort_threshold = (float)(1.0f - std::cos(10.0 * M_PI / 180.0));      // optim.cpp:287
+  sp.ncc_threshold = c->ncc_threshold; sp.ncc_threshold_before = c->ncc_threshold_before;
+  // checkAngles(minAngle = maxAngleThreshold, maxAngle = angleThreshold1) (optim.cpp:114): angle_of is non-increasing in d
+  const float minA = c->max_angle_threshold, maxA = c->angle_threshold1;
+  const uint32_t klo = float_key(-1.0f), khi = float_key(1.0f);
+  {  // hi = largest d in [-1,1] with angle_of(d) > minA
+    uint32_t lo = klo, hi = khi;
+    if (!(angle_of(key_float(lo)) > minA)) sp.angle_dot_hi = -2.0f;  // empty
+    else { while (lo < hi) { const uint32_t mid = lo + (hi - lo + 1) / 2; if (angle_of(key_float(mid)) > minA) lo = mid; else hi = mid - 1; } sp.angle_dot_hi = key_float(lo); }
+  }
+  {  // lo = smallest d in [-1,1] with angle_of(d) < maxA
+    uint32_t lo = klo, hi = khi;
+    if (!(angle_of(key_float(hi)) < maxA)) sp.angle_dot_lo = 2.0f;   // empty
+    else { while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (angle_of(key_float(mid)) < maxA) hi = mid; else lo = mid + 1; } sp.angle_dot_lo = key_float(lo); }
+  }
 }
 
 void fill_scene(pmvsb_ctx* c) {
@@ -650,7 +736,7 @@ int pmvsb_destroy(pmvsb_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& im : ctx->images)
     for (auto* p : im.levels) cudaFree(p);
-  cudaFree(ctx->d_cams); cudaFree(ctx->d_levels); cudaFree(ctx->d_counter);
+  cudaFree(ctx->d_cams); cudaFree(ctx->d_levels); cudaFree(ctx->d_counter); cudaFree(ctx->d_vis_off); cudaFree(ctx->d_vis_idx);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -709,6 +795,7 @@ int pmvsb_set_visdata2(pmvsb_ctx* ctx, int index, const int32_t* list, int n) {
   for (int i = 0; i < n; ++i)
     if (list[i] < 0 || list[i] >= ctx->num) return fail(ctx, PMVSB_EINVAL, "set_visdata2: image index out of range");
   ctx->visdata2[index].assign(list, list + n);
+  ctx->finalized = false;
   return PMVSB_OK;
 }
 
@@ -744,7 +831,21 @@ int pmvsb_finalize_scene(pmvsb_ctx* ctx) {
   CK(cudaMalloc((void**)&ctx->d_levels, sizeof(LevelDev) * hl.size()));
   CK(cudaMemcpy(ctx->d_cams, hc.data(), sizeof(CamDev) * hc.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->d_levels, hl.data(), sizeof(LevelDev) * hl.size(), cudaMemcpyHostToDevice));
+  {
+    std::vector<int32_t> off(ctx->num + 1, 0), idx;
+    for (int i = 0; i < ctx->num; ++i) {
+      idx.insert(idx.end(), ctx->visdata2[i].begin(), ctx->visdata2[i].end());
+      off[i + 1] = (int32_t)idx.size();
+    }
+    cudaFree(ctx->d_vis_off); cudaFree(ctx->d_vis_idx);
+    ctx->d_vis_off = nullptr; ctx->d_vis_idx = nullptr;
+    CK(cudaMalloc((void**)&ctx->d_vis_off, sizeof(int32_t) * off.size()));
+    CK(cudaMalloc((void**)&ctx->d_vis_idx, sizeof(int32_t) * (idx.size() ? idx.size() : 1)));
+    CK(cudaMemcpy(ctx->d_vis_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice));
+    if (!idx.empty()) CK(cudaMemcpy(ctx->d_vis_idx, idx.data(), sizeof(int32_t) * idx.size(), cudaMemcpyHostToDevice));
+  }
   fill_scene(ctx);
+  fill_select(ctx);
   ctx->finalized = true;
   return PMVSB_OK;
 }
@@ -753,6 +854,8 @@ int pmvsb_set_thresholds(pmvsb_ctx* ctx, float ncc_threshold, float ncc_threshol
   if (!ctx) return PMVSB_EINVAL;
   ctx->ncc_threshold = ncc_threshold;
   ctx->ncc_threshold_before = ncc_threshold_before;
+  ctx->select.ncc_threshold = ncc_threshold;
+  ctx->select.ncc_threshold_before = ncc_threshold_before;
   return PMVSB_OK;
 }
 
@@ -951,6 +1054,61 @@ int pmvsb_set_scales_batch(pmvsb_ctx* ctx, int P, int stride, const float* coord
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(dscale, dd.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ascale, da.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_pre_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals, int32_t* images,
+                            int32_t* nimages, float* dscale, float* ascale, int32_t* verdict) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (!normals || !nimages || !dscale || !ascale || !verdict) return fail(ctx, PMVSB_EINVAL, "pre_process_batch: null pointer");
+  if (ctx->wsize == 9) return fail(ctx, PMVSB_EINVAL, "pre_process_batch: wsize 9 is not supported by the selection kernels");
+  if (P == 0) return PMVSB_OK;
+  PatchStage st;
+  r = stage_patches(ctx, st, P, stride, coords, normals, images, nimages, nullptr);
+  if (r) return r;
+  DevBuf<float> dd, da;
+  DevBuf<int32_t> dv;
+  CK(dd.alloc(P)); CK(da.alloc(P)); CK(dv.alloc(P));
+  if (ctx->wsize == 5) k_pre_process<5><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, dd.p, da.p, dv.p);
+  else k_pre_process<7><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, dd.p, da.p, dv.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(images, st.images.p, sizeof(int32_t) * (size_t)stride * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(nimages, st.nimages.p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(dscale, dd.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ascale, da.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(verdict, dv.p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_post_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals, const float* ncc,
+                             int32_t* images, int32_t* nimages, int32_t* grids, int32_t* timages, float* tmp, int32_t* verdict) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (!normals || !ncc || !nimages || !grids || !timages || !tmp || !verdict) return fail(ctx, PMVSB_EINVAL, "post_process_batch: null pointer");
+  if (ctx->wsize == 9) return fail(ctx, PMVSB_EINVAL, "post_process_batch: wsize 9 is not supported by the selection kernels");
+  if (P == 0) return PMVSB_OK;
+  PatchStage st;
+  r = stage_patches(ctx, st, P, stride, coords, normals, images, nimages, nullptr);
+  if (r) return r;
+  DevBuf<float> dn, dt;
+  DevBuf<int32_t> dg, dti, dv;
+  CK(dn.alloc(P)); CK(dt.alloc(P)); CK(dg.alloc((size_t)2 * stride * P)); CK(dti.alloc(P)); CK(dv.alloc(P));
+  CK(cudaMemcpyAsync(dn.p, ncc, sizeof(float) * P, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(dg.p, 0xff, sizeof(int32_t) * (size_t)2 * stride * P, ctx->stream));
+  if (ctx->wsize == 5) k_post_process<5><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, dn.p, st.images.p, st.nimages.p, dg.p, dti.p, dt.p, dv.p);
+  else k_post_process<7><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, dn.p, st.images.p, st.nimages.p, dg.p, dti.p, dt.p, dv.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(images, st.images.p, sizeof(int32_t) * (size_t)stride * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(nimages, st.nimages.p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(grids, dg.p, sizeof(int32_t) * (size_t)2 * stride * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(timages, dti.p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(tmp, dt.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(verdict, dv.p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return PMVSB_OK;
 }

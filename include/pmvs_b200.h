@@ -101,6 +101,19 @@ int pmvsb_set_inccs_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords
 int pmvsb_set_scales_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const int32_t* images,
                            const int32_t* nimages, float* dscale, float* ascale);
 
+/* ---- visible-image-set selection around the hot call (integer results: bit-exact) -----------------------
+ * COptim::preProcess (optim.cpp:95-122) for a batch of candidates: addImages -> constraintImages(nccThresholdBefore)
+ * -> sortImages -> setScales -> minImageNum check -> checkAngles.  images/nimages are updated in place
+ * (stride = capacity per patch, at most 64 views are kept); verdict 0 = keep, 1 = reject (as the reference returns). */
+int pmvsb_pre_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals,
+                            int32_t* images, int32_t* nimages, float* dscale, float* ascale, int32_t* verdict);
+/* COptim::postProcess (optim.cpp:150-190) at CFindMatch::_depth == 0 (seed round): addImages ->
+ * constraintImages(nccThreshold) -> filterImagesByAngle -> setRefImage -> constraintImages -> setGrids, then
+ * _timages and _tmp = score2.  grids = int32[2*stride*P] (cell x,y per image), ncc = refinePatch's _ncc. */
+int pmvsb_post_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals,
+                             const float* ncc, int32_t* images, int32_t* nimages, int32_t* grids,
+                             int32_t* timages, float* tmp, int32_t* verdict);
+
 /* ---- the hot call -------------------------------------------------------------------------------
  * COptim::refinePatch for a whole seed / expansion frontier in one launch (optim.cpp:496-502,580-658):
  * in-kernel bounded Nelder-Mead over (depth, angle1, angle2) around my_f, then the final
