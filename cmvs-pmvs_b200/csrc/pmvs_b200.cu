@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
                                                      const float* __restrict__ dscales, float* __restrict__ ncc_out,
                                                      int32_t* __restrict__ evals_out, uint8_t* __restrict__ ok_out,
                                                      int* __restrict__ counter) {
+  // counter[0] = next patch to hand out, counter[1] = set to 1 when a patch names an image outside [0, num)
   __shared__ NMShared nms[4][4];  // [warp in CTA][group in warp]
   __shared__ float4 reftex_s[WSIZE * 128];  // reference-view deviations, [row][thread]
   float4* reftex = reftex_s + threadIdx.x;
@@ -358,19 +359,33 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
         float coord[4], normal[4];
         load_patch(coords, normals, p, coord, normal);
         const int n = nimages ? min(nimages[p], stride) : stride;
-        group_ctx_init(s, gc, coord, normal, images + (size_t)p * stride, n, dscales[p], gl, gmask);
-        if (gl == 0) {
-          CamDev refcam;
-          load_cam(s, gc.ref, refcam);
-          double x[3];
-          encode(s, gc, refcam, coord, normal, x);
-          nm_start(nm, x, s.step);  // clamps the start into the box as optim.cpp:629-634 does
+        // image indexes come from the caller: a bad one must not turn into a wild load
+        bool bad = n < 1;
+        for (int k = gl; k < n && k < s.tau; k += kGroup) {
+          const int im = images[(size_t)p * stride + k];
+          bad |= (im < 0 || im >= s.num);
         }
-        have = true;
+        if (__any_sync(gmask, bad)) {
+          if (gl == 0) { atomicExch(counter + 1, 1); ncc_out[p] = -1.0f; evals_out[p] = 0; ok_out[p] = 0; }
+          // this group stays without a patch for one trip and asks again on the next
+        } else {
+          group_ctx_init(s, gc, coord, normal, images + (size_t)p * stride, n, dscales[p], gl, gmask);
+          if (gl == 0) {
+            CamDev refcam;
+            load_cam(s, gc.ref, refcam);
+            double x[3];
+            encode(s, gc, refcam, coord, normal, x);
+            nm_start(nm, x, s.step);  // clamps the start into the box as optim.cpp:629-634 does
+          }
+          have = true;
+        }
       }
     }
     __syncwarp();
-    if (!__any_sync(kFull, have)) break;
+    if (!__any_sync(kFull, have)) {
+      if (__all_sync(kFull, exhausted)) break;
+      continue;
+    }
 
     const int mode = (have && nm.state == NM_FINAL) ? 1 : 0;
     const double xt[3] = {nm.xt[0], nm.xt[1], nm.xt[2]};
@@ -479,6 +494,8 @@ struct pmvsb_ctx {
   LevelDev* d_levels = nullptr;
   int* d_counter = nullptr;
   int32_t* d_vis_off = nullptr;
+  char* arena = nullptr;          // grow-only device staging for the host-pointer entry points
+  size_t arena_cap = 0, arena_used = 0;
   int32_t* d_vis_idx = nullptr;
   SelectParams select;
   bool finalized = false;
@@ -683,6 +700,25 @@ int check_ready(pmvsb_ctx* ctx) {
 
 }  // namespace
 
+// grow-only device arena: the batched host-pointer calls stage through it instead of cudaMalloc/cudaFree per call
+static int arena_reserve(pmvsb_ctx* ctx, size_t bytes) {
+  ctx->arena_used = 0;
+  if (bytes <= ctx->arena_cap) return PMVSB_OK;
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->arena);
+  ctx->arena = nullptr; ctx->arena_cap = 0;
+  const size_t want = bytes + bytes / 4 + (1u << 20);
+  CK(cudaMalloc((void**)&ctx->arena, want));
+  ctx->arena_cap = want;
+  return PMVSB_OK;
+}
+template <typename T>
+static T* arena_take(pmvsb_ctx* ctx, size_t n) {
+  const size_t off = (ctx->arena_used + 255) & ~(size_t)255;
+  ctx->arena_used = off + sizeof(T) * n;
+  return reinterpret_cast<T*>(ctx->arena + off);
+}
+
 extern "C" {
 
 const char* pmvsb_version(void) { return "pmvs-b200 0.1 (sm_100a)"; }
@@ -723,7 +759,7 @@ int pmvsb_create(pmvsb_ctx** out, int device, int num_images, int num_target, in
   ctx->stream = ctx->own_stream;
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_counter, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_counter, 2 * sizeof(int));
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) { delete ctx; return PMVSB_ECUDA; }
   *out = ctx;
@@ -737,6 +773,7 @@ int pmvsb_destroy(pmvsb_ctx* ctx) {
   for (auto& im : ctx->images)
     for (auto* p : im.levels) cudaFree(p);
   cudaFree(ctx->d_cams); cudaFree(ctx->d_levels); cudaFree(ctx->d_counter); cudaFree(ctx->d_vis_off); cudaFree(ctx->d_vis_idx);
+  cudaFree(ctx->arena);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1129,7 +1166,7 @@ int pmvsb_refine_batch_dev(pmvsb_ctx* ctx, int P, int stride, float* d_coords, f
     }
     ctx->refine_blocks_per_sm = nb > 0 ? nb : 1;
   }
-  CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_counter, 0, 2 * sizeof(int), ctx->stream));
   // persistent grid: a whole number of resident CTAs per SM (148 SMs on B200)
   int grid = ctx->sm_count * ctx->refine_blocks_per_sm;
   const int per_block = ctx->wsize == 9 ? 4 : 16;  // patches a CTA works on at a time
@@ -1150,21 +1187,41 @@ int pmvsb_refine_batch(pmvsb_ctx* ctx, int P, int stride, float* coords, float* 
   if (r) return r;
   if (!normals || !dscales || !ncc || !evals || !ok) return fail(ctx, PMVSB_EINVAL, "refine_batch: null pointer");
   if (P == 0) return PMVSB_OK;
-  PatchStage st;
-  r = stage_patches(ctx, st, P, stride, coords, normals, images, nimages, dscales);
+  if (stride < 1 || !coords || !images) return fail(ctx, PMVSB_EINVAL, "refine_batch: bad patch batch");
+  if (ctx->wsize == 9) {  // the warp-per-patch fallback trusts its indexes: validate here
+    for (size_t i = 0; i < (size_t)stride * P; ++i) {
+      const int p = (int)(i / stride), k = (int)(i % stride);
+      const int n = nimages ? std::min(nimages[p], stride) : stride;
+      if (k < n && (images[i] < 0 || images[i] >= ctx->num)) return fail(ctx, PMVSB_EINVAL, "image index out of range in patch batch");
+    }
+  }
+  const size_t nP = (size_t)P;
+  r = arena_reserve(ctx, nP * (16 + 16 + 4 * (size_t)stride + 4 + 4 + 4 + 4 + 1) + 16 * 256);
   if (r) return r;
-  DevBuf<float> dn;
-  DevBuf<int32_t> de;
-  DevBuf<uint8_t> dk;
-  CK(dn.alloc(P)); CK(de.alloc(P)); CK(dk.alloc(P));
-  r = pmvsb_refine_batch_dev(ctx, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, st.dscales.p, dn.p, de.p, dk.p);
+  float* d_coords = arena_take<float>(ctx, 4 * nP);
+  float* d_normals = arena_take<float>(ctx, 4 * nP);
+  int32_t* d_images = arena_take<int32_t>(ctx, (size_t)stride * nP);
+  int32_t* d_nimages = nimages ? arena_take<int32_t>(ctx, nP) : nullptr;
+  float* d_dscales = arena_take<float>(ctx, nP);
+  float* d_ncc = arena_take<float>(ctx, nP);
+  int32_t* d_evals = arena_take<int32_t>(ctx, nP);
+  uint8_t* d_ok = arena_take<uint8_t>(ctx, nP);
+  CK(cudaMemcpyAsync(d_coords, coords, sizeof(float) * 4 * nP, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_normals, normals, sizeof(float) * 4 * nP, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_images, images, sizeof(int32_t) * (size_t)stride * nP, cudaMemcpyHostToDevice, ctx->stream));
+  if (nimages) CK(cudaMemcpyAsync(d_nimages, nimages, sizeof(int32_t) * nP, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_dscales, dscales, sizeof(float) * nP, cudaMemcpyHostToDevice, ctx->stream));
+  r = pmvsb_refine_batch_dev(ctx, P, stride, d_coords, d_normals, d_images, d_nimages, d_dscales, d_ncc, d_evals, d_ok);
   if (r) return r;
-  CK(cudaMemcpyAsync(coords, st.coords.p, sizeof(float) * 4 * P, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(normals, st.normals.p, sizeof(float) * 4 * P, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ncc, dn.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(evals, de.p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ok, dk.p, sizeof(uint8_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  int flags[2] = {0, 0};
+  CK(cudaMemcpyAsync(flags, ctx->d_counter, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(coords, d_coords, sizeof(float) * 4 * nP, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(normals, d_normals, sizeof(float) * 4 * nP, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ncc, d_ncc, sizeof(float) * nP, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(evals, d_evals, sizeof(int32_t) * nP, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ok, d_ok, sizeof(uint8_t) * nP, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (flags[1]) return fail(ctx, PMVSB_EINVAL, "image index out of range in patch batch (those patches were skipped, ok = 0)");
   return PMVSB_OK;
 }
 
