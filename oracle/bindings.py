@@ -226,6 +226,52 @@ class OracleLib(_Common):
                                         grids.ctypes.data_as(C.c_void_p), C.byref(t), C.byref(tmp))
         return int(r), im[: n.value].copy(), grids[: n.value].copy(), t.value, np.float32(tmp.value)
 
+    # -- filter stage --------------------------------------------------------------------------------
+    def set_depth(self, d):
+        self.lib.pmvso_set_depth(self.ctx, int(d))
+
+    def store_set(self, st):
+        """st: dict from RefLib.state() / tests (coords, normals, ncc, dscale, img_off, images, grids, vimg_off, vimages, vgrids, timages)"""
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._store = {k: np.ascontiguousarray(v) for k, v in st.items()}
+        t = self._store
+        self.lib.pmvso_store_set(self.ctx, len(t["ncc"]), vp(t["coords"]), vp(t["normals"]), vp(t["ncc"]), vp(t["dscale"]), vp(t["img_off"]),
+                                 vp(t["images"]), vp(t["grids"]), vp(t["vimg_off"]), vp(t["vimages"]), vp(t["vgrids"]), vp(t["timages"]))
+
+    def grid_dims(self, image):
+        gw, gh = C.c_int(), C.c_int()
+        self.lib.pmvso_grid_dims(self.ctx, int(image), C.byref(gw), C.byref(gh))
+        return gw.value, gh.value
+
+    def build_depth_maps(self):
+        self.lib.pmvso_build_depth_maps(self.ctx)
+
+    def depth_map(self, image):
+        gw, gh = self.grid_dims(image)
+        out = np.zeros(gw * gh, np.int32)
+        self.lib.pmvso_get_depth_map(self.ctx, int(image), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def is_visible_k(self, k, image, ix, iy, strict):
+        t = self._store
+        return self.lib.pmvso_is_visible(self.ctx, t["coords"][k].ctypes.data_as(C.c_void_p), t["normals"][k].ctypes.data_as(C.c_void_p),
+                                         int(image), int(ix), int(iy), C.c_float(strict))
+
+    def set_vimages(self, k, cap=256):
+        vim = np.zeros(cap, np.int32); vgr = np.zeros((cap, 2), np.int32)
+        n = self.lib.pmvso_set_vimages(self.ctx, int(k), vim.ctypes.data_as(C.c_void_p), vgr.ctypes.data_as(C.c_void_p), cap)
+        return vim[:n].copy(), vgr[:n].copy()
+
+    def filter_exact_safe(self, k, image, ix, iy):
+        return self.lib.pmvso_filter_exact_safe(self.ctx, int(k), int(image), int(ix), int(iy))
+
+    def is_neighbor(self, a, b, thr):
+        return self.lib.pmvso_is_neighbor(self.ctx, int(a), int(b), C.c_float(thr))
+
+    def compute_gain(self, k):
+        f = self.lib.pmvso_compute_gain; f.restype = C.c_float
+        return np.float32(f(self.ctx, int(k)))
+
     def close(self):
         if self.ctx:
             self.lib.pmvso_destroy(self.ctx)
@@ -292,6 +338,60 @@ class RefLib(_Common):
                                    vim.ctypes.data_as(C.c_void_p), C.byref(kv))
             images.append(im[: k.value].copy())
         return dict(coords=coords, normals=normals, ncc=nda[:, 0], dscale=nda[:, 1], ascale=nda[:, 2], images=images)
+
+    # -- filter stage (state of the reference after run()) -------------------------------------------------
+    def state(self, cap=256):
+        """All patches after collectPatches(0) as arrays (CSR image lists); index == CPatch::_id."""
+        P = self.lib.ref_collect_patches()
+        coords = np.zeros((P, 4), np.float32); normals = np.zeros((P, 4), np.float32)
+        sc = np.zeros((P, 4), np.float32); misc = np.zeros((P, 3), np.int32)
+        img_off = [0]; vimg_off = [0]; images = []; grids = []; vimages = []; vgrids = []
+        im = np.zeros(cap, np.int32); gr = np.zeros((cap, 2), np.int32); vim = np.zeros(cap, np.int32); vgr = np.zeros((cap, 2), np.int32)
+        n, nv = C.c_int(), C.c_int()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        for k in range(P):
+            self.lib.ref_get_patch_full(k, vp(coords[k]), vp(normals[k]), vp(sc[k]), vp(im), vp(gr), C.byref(n), vp(vim), vp(vgr),
+                                        C.byref(nv), vp(misc[k]), cap)
+            images.append(im[: n.value].copy()); grids.append(gr[: n.value].copy())
+            vimages.append(vim[: nv.value].copy()); vgrids.append(vgr[: nv.value].copy())
+            img_off.append(img_off[-1] + n.value); vimg_off.append(vimg_off[-1] + nv.value)
+        cat = lambda l, shape: (np.concatenate(l) if l and sum(len(x) for x in l) else np.zeros(shape, np.int32)).astype(np.int32)
+        return dict(coords=coords, normals=normals, ncc=sc[:, 0].copy(), dscale=sc[:, 1].copy(), ascale=sc[:, 2].copy(), tmp=sc[:, 3].copy(),
+                    img_off=np.array(img_off, np.int32), images=cat(images, (0,)), grids=cat(grids, (0, 2)),
+                    vimg_off=np.array(vimg_off, np.int32), vimages=cat(vimages, (0,)), vgrids=cat(vgrids, (0, 2)),
+                    timages=misc[:, 0].copy(), fix=misc[:, 1].copy())
+
+    def grid_dims(self, image):
+        gw, gh = C.c_int(), C.c_int()
+        self.lib.ref_grid_dims(int(image), C.byref(gw), C.byref(gh))
+        return gw.value, gh.value
+
+    def build_depth_maps(self):
+        self.lib.ref_set_depth_maps()
+
+    def depth_map(self, image):
+        gw, gh = self.grid_dims(image)
+        out = np.zeros(gw * gh, np.int32)
+        self.lib.ref_get_depth_map(int(image), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def is_visible_k(self, k, image, ix, iy, strict):
+        return self.lib.ref_is_visible(int(k), int(image), int(ix), int(iy), C.c_float(strict))
+
+    def set_vimages(self, k, cap=256):
+        vim = np.zeros(cap, np.int32); vgr = np.zeros((cap, 2), np.int32)
+        n = self.lib.ref_set_vimages(int(k), vim.ctypes.data_as(C.c_void_p), vgr.ctypes.data_as(C.c_void_p), cap)
+        return vim[:n].copy(), vgr[:n].copy()
+
+    def is_neighbor(self, a, b, thr):
+        return self.lib.ref_is_neighbor(int(a), int(b), C.c_float(thr))
+
+    def compute_gain(self, k):
+        f = self.lib.ref_compute_gain; f.restype = C.c_float
+        return np.float32(f(int(k)))
+
+    def depth_flag(self):
+        return self.lib.ref_get_depth_flag()
 
     def counters(self):
         self.lib.ref_total_evals.restype = C.c_ulonglong

@@ -39,6 +39,15 @@ struct pmvso_ctx {
   int* h;
   int** vis2;
   int* nvis2;
+  /* filter-stage state */
+  int depth;
+  int P;
+  float *s_coords, *s_normals, *s_ncc, *s_dscale;
+  int *s_img_off, *s_images, *s_grids, *s_vimg_off, *s_vimages, *s_vgrids, *s_timages;
+  int** dp;        /* [target image][cell] patch id or -1 */
+  int* cell_off;   /* pgrids as CSR over (image, cell): cell_base[image] + cell */
+  int* cell_base;
+  int* cell_patch;
 };
 
 /* ---------------------------------------------------------------- small vector helpers (f32, source order) */
@@ -904,4 +913,197 @@ int pmvso_post_process(const pmvso_ctx* c, const float* coord, const float* norm
   *timages = t;
   *tmp = fmaxf_(0.0f, ncc - c->ncc_threshold) * t; /* include/pmvs/patch.hpp:48-50 score2 */
   return 0;
+}
+
+
+/* ================================================================ filter stage */
+void pmvso_set_depth(pmvso_ctx* c, int depth) { c->depth = depth; }
+
+void pmvso_grid_dims(const pmvso_ctx* c, int image, int* gw, int* gh) { /* patchOrganizerS.cpp:72-77 */
+  const int k = image * c->nlevels + c->level;
+  *gw = (c->w[k] + c->csize - 1) / c->csize;
+  *gh = (c->h[k] + c->csize - 1) / c->csize;
+}
+
+static void* dup_mem(const void* p, size_t n) { void* q = malloc(n ? n : 1); if (n) memcpy(q, p, n); return q; }
+
+void pmvso_store_set(pmvso_ctx* c, int P, const float* coords, const float* normals, const float* ncc, const float* dscale,
+                     const int* img_off, const int* images, const int* grids,
+                     const int* vimg_off, const int* vimages, const int* vgrids, const int* timages) {
+  free(c->s_coords); free(c->s_normals); free(c->s_ncc); free(c->s_dscale); free(c->s_img_off); free(c->s_images); free(c->s_grids);
+  free(c->s_vimg_off); free(c->s_vimages); free(c->s_vgrids); free(c->s_timages); free(c->cell_off); free(c->cell_base); free(c->cell_patch);
+  c->P = P;
+  c->s_coords = dup_mem(coords, sizeof(float) * 4 * P); c->s_normals = dup_mem(normals, sizeof(float) * 4 * P);
+  c->s_ncc = dup_mem(ncc, sizeof(float) * P); c->s_dscale = dup_mem(dscale, sizeof(float) * P);
+  c->s_img_off = dup_mem(img_off, sizeof(int) * (P + 1));
+  c->s_images = dup_mem(images, sizeof(int) * img_off[P]); c->s_grids = dup_mem(grids, sizeof(int) * 2 * img_off[P]);
+  c->s_vimg_off = dup_mem(vimg_off, sizeof(int) * (P + 1));
+  c->s_vimages = dup_mem(vimages, sizeof(int) * vimg_off[P]); c->s_vgrids = dup_mem(vgrids, sizeof(int) * 2 * vimg_off[P]);
+  c->s_timages = dup_mem(timages, sizeof(int) * P);
+  /* _pgrids (patchOrganizerS.cpp:315-331) as CSR; the order inside a cell does not matter for the maxima taken over it */
+  c->cell_base = (int*)malloc(sizeof(int) * (c->tnum + 1));
+  int total = 0;
+  for (int i = 0; i < c->tnum; ++i) { int gw, gh; pmvso_grid_dims(c, i, &gw, &gh); c->cell_base[i] = total; total += gw * gh; }
+  c->cell_base[c->tnum] = total;
+  c->cell_off = (int*)calloc(total + 1, sizeof(int));
+  for (int p = 0; p < P; ++p)
+    for (int e = img_off[p]; e < img_off[p + 1]; ++e) {
+      const int im = images[e];
+      if (c->tnum <= im) continue;
+      int gw, gh; pmvso_grid_dims(c, im, &gw, &gh);
+      c->cell_off[c->cell_base[im] + grids[2 * e + 1] * gw + grids[2 * e] + 1]++;
+    }
+  for (int i = 0; i < total; ++i) c->cell_off[i + 1] += c->cell_off[i];
+  c->cell_patch = (int*)malloc(sizeof(int) * (c->cell_off[total] ? c->cell_off[total] : 1));
+  int* fill = (int*)calloc(total, sizeof(int));
+  for (int p = 0; p < P; ++p)
+    for (int e = img_off[p]; e < img_off[p + 1]; ++e) {
+      const int im = images[e];
+      if (c->tnum <= im) continue;
+      int gw, gh; pmvso_grid_dims(c, im, &gw, &gh);
+      const int cell = c->cell_base[im] + grids[2 * e + 1] * gw + grids[2 * e];
+      c->cell_patch[c->cell_off[cell] + fill[cell]++] = p;
+    }
+  free(fill);
+}
+
+/* CFilter::setDepthMapsThread (filter.cpp:687-732): patches in table order, strictly nearer replaces */
+void pmvso_build_depth_maps(pmvso_ctx* c) {
+  if (!c->dp) c->dp = (int**)calloc(c->tnum, sizeof(int*));
+  for (int index = 0; index < c->tnum; ++index) {
+    int gw, gh; pmvso_grid_dims(c, index, &gw, &gh);
+    free(c->dp[index]);
+    c->dp[index] = (int*)malloc(sizeof(int) * gw * gh);
+    for (int i = 0; i < gw * gh; ++i) c->dp[index][i] = -1;
+    const cam_t* cam = &c->cams[index];
+    for (int p = 0; p < c->P; ++p) {
+      const float* X = c->s_coords + 4 * p;
+      float ic[3];
+      project(c, index, X, c->level, ic);
+      const float fx = ic[0] / c->csize;
+      const int xs[2] = {(int)floor(fx), (int)ceil(fx)};
+      const float fy = ic[1] / c->csize;
+      const int ys[2] = {(int)floor(fy), (int)ceil(fy)};
+      const float depth = dot4(cam->oaxis, X);
+      for (int j = 0; j < 2; ++j)
+        for (int i = 0; i < 2; ++i) {
+          if (xs[i] < 0 || gw <= xs[i] || ys[j] < 0 || gh <= ys[j]) continue;
+          const int cell = ys[j] * gw + xs[i];
+          if (c->dp[index][cell] < 0) c->dp[index][cell] = p;
+          else {
+            const float dtmp = dot4(cam->oaxis, c->s_coords + 4 * c->dp[index][cell]);
+            if (depth < dtmp) c->dp[index][cell] = p;
+          }
+        }
+    }
+  }
+}
+void pmvso_get_depth_map(const pmvso_ctx* c, int image, int* out) {
+  int gw, gh; pmvso_grid_dims(c, image, &gw, &gh);
+  memcpy(out, c->dp[image], sizeof(int) * gw * gh);
+}
+
+/* CPatchOrganizerS::isVisible (patchOrganizerS.cpp:487-526) */
+int pmvso_is_visible(const pmvso_ctx* c, const float* coord, const float* normal, int image, int ix, int iy, float strict) {
+  int gw, gh; pmvso_grid_dims(c, image, &gw, &gh);
+  if (ix < 0 || gw <= ix || iy < 0 || gh <= iy) return 0;
+  if (c->depth == 0) return 1;
+  const int q = c->dp[image][iy * gw + ix];
+  if (q < 0) return 1;
+  const cam_t* cam = &c->cams[image];
+  float ray[4] = {coord[0] - cam->centre[0], coord[1] - cam->centre[1], coord[2] - cam->centre[2], coord[3] - cam->centre[3]};
+  unitize4(ray);
+  const float* Y = c->s_coords + 4 * q;
+  const float d[4] = {coord[0] - Y[0], coord[1] - Y[1], coord[2] - Y[2], coord[3] - Y[3]};
+  const float diff = dot4(ray, d);
+  const double factor = fmin(2.0, 2.0 + dot4(ray, normal));
+  if (diff < get_unit(c, image, coord) * c->csize * strict * factor) return 1;
+  return 0;
+}
+
+/* isVisible0 + setVImagesVGrids (patchOrganizerS.cpp:420-450, 479-485); strict = _neighborThreshold = 0.5 */
+int pmvso_set_vimages(const pmvso_ctx* c, int k, int* vimages, int* vgrids, int cap) {
+  unsigned char used[MAXIMG_LOCAL];
+  memset(used, 0, sizeof(used));
+  for (int e = c->s_img_off[k]; e < c->s_img_off[k + 1]; ++e)
+    if (c->s_images[e] < c->tnum) used[c->s_images[e]] = 1;
+  const float* X = c->s_coords + 4 * k;
+  const float* N = c->s_normals + 4 * k;
+  int n = 0;
+  for (int image = 0; image < c->tnum; ++image) {
+    if (used[image]) continue;
+    float ic[3];
+    project(c, image, X, c->level, ic);
+    const int ix = ((int)floorf(ic[0] + 0.5f)) / c->csize;
+    const int iy = ((int)floorf(ic[1] + 0.5f)) / c->csize;
+    if (pmvso_is_visible(c, X, N, image, ix, iy, 0.5f) == 0) continue;
+    if (n < cap) { vimages[n] = image; vgrids[2 * n] = ix; vgrids[2 * n + 1] = iy; ++n; }
+  }
+  return n;
+}
+
+/* filter.cpp:315-343; strict = _neighborThreshold1 = 1.0 */
+int pmvso_filter_exact_safe(const pmvso_ctx* c, int k, int image, int x, int y) {
+  int w, h; pmvso_grid_dims(c, image, &w, &h);
+  const float* X = c->s_coords + 4 * k;
+  const float* N = c->s_normals + 4 * k;
+  if (pmvso_is_visible(c, X, N, image, x, y, 1.0f)) return 1;
+  if (0 < x && pmvso_is_visible(c, X, N, image, x - 1, y, 1.0f)) return 1;
+  if (x < w - 1 && pmvso_is_visible(c, X, N, image, x + 1, y, 1.0f)) return 1;
+  if (0 < y && pmvso_is_visible(c, X, N, image, x, y - 1, 1.0f)) return 1;
+  if (y < h - 1 && pmvso_is_visible(c, X, N, image, x, y + 1, 1.0f)) return 1;
+  return 0;
+}
+
+/* CFindMatch::isNeighbor (findMatch.cpp:120-149) */
+int pmvso_is_neighbor(const pmvso_ctx* c, int a, int b, float thr) {
+  const float* Xa = c->s_coords + 4 * a; const float* Xb = c->s_coords + 4 * b;
+  const float* Na = c->s_normals + 4 * a; const float* Nb = c->s_normals + 4 * b;
+  const float hunit = (float)((get_unit(c, c->s_images[c->s_img_off[a]], Xa) + get_unit(c, c->s_images[c->s_img_off[b]], Xb)) / 2.0 * c->csize);
+  if (dot4(Na, Nb) < cos(120.0 * M_PI / 180.0)) return 0;
+  const float diff[4] = {Xb[0] - Xa[0], Xb[1] - Xa[1], Xb[2] - Xa[2], Xb[3] - Xa[3]};
+  const float vunit = c->s_dscale[a] + c->s_dscale[b];
+  const float f0 = dot4(Na, diff);
+  const float f1 = dot4(Nb, diff);
+  float ftmp = (float)((fabsf(f0) + fabsf(f1)) / 2.0);
+  ftmp /= vunit;
+  float t[4];
+  for (int k = 0; k < 4; ++k) t[k] = diff[k] * 2 - Na[k] * f0 - Nb[k] * f1;
+  const float hsize = (float)(norm4(t) / 2.0 / hunit);
+  if (1.0 < hsize) ftmp /= fminf_(2.0f, hsize);
+  return ftmp < thr ? 1 : 0;
+}
+
+/* CFilter::computeGain (filter.cpp:88-146); neighbour threshold = _neighborThreshold1 = 1.0 */
+float pmvso_compute_gain(const pmvso_ctx* c, int k) {
+  const float thr = c->ncc_threshold;
+  float gain = fmaxf_(0.0f, c->s_ncc[k] - thr) * c->s_timages[k];   /* score2 */
+  for (int e = c->s_img_off[k]; e < c->s_img_off[k + 1]; ++e) {
+    const int index = c->s_images[e];
+    if (c->tnum <= index) continue;
+    int gw, gh; pmvso_grid_dims(c, index, &gw, &gh);
+    const int cell = c->cell_base[index] + c->s_grids[2 * e + 1] * gw + c->s_grids[2 * e];
+    float maxpressure = 0.0f;
+    for (int j = c->cell_off[cell]; j < c->cell_off[cell + 1]; ++j) {
+      const int q = c->cell_patch[j];
+      if (!pmvso_is_neighbor(c, k, q, 1.0f)) maxpressure = fmaxf_(maxpressure, c->s_ncc[q] - thr);
+    }
+    gain -= maxpressure;
+  }
+  for (int e = c->s_vimg_off[k]; e < c->s_vimg_off[k + 1]; ++e) {
+    const int index = c->s_vimages[e];
+    if (c->tnum <= index) continue;
+    const cam_t* cam = &c->cams[index];
+    const float pdepth = dot4(cam->oaxis, c->s_coords + 4 * k);   /* computeDepth, camera.cpp:445-452 (perspective) */
+    int gw, gh; pmvso_grid_dims(c, index, &gw, &gh);
+    const int cell = c->cell_base[index] + c->s_vgrids[2 * e + 1] * gw + c->s_vgrids[2 * e];
+    float maxpressure = 0.0f;
+    for (int j = c->cell_off[cell]; j < c->cell_off[cell + 1]; ++j) {
+      const int q = c->cell_patch[j];
+      const float bdepth = dot4(cam->oaxis, c->s_coords + 4 * q);
+      if (pdepth < bdepth && !pmvso_is_neighbor(c, k, q, 1.0f)) maxpressure = fmaxf_(maxpressure, c->s_ncc[q] - thr);
+    }
+    gain -= maxpressure;
+  }
+  return gain;
 }

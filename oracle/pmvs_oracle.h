@@ -65,6 +65,24 @@ int pmvso_pre_process(const pmvso_ctx* c, const float* coord, const float* norma
 int pmvso_post_process(const pmvso_ctx* c, const float* coord, const float* normal, float ncc, int* images, int* n,
                        int cap, int* grids, int* timages, float* tmp);
 
+/* ---- filter stage: depth maps, visibility, gains (source/pmvs/filter.cpp, patchOrganizerS.cpp) ----------
+ * The patch table is handed over as arrays (CSR for the per-patch image lists); indexes into it are what the
+ * reference calls CPatch::_id after collectPatches(). */
+void pmvso_set_depth(pmvso_ctx* c, int depth);                       /* CFindMatch::_depth */
+void pmvso_store_set(pmvso_ctx* c, int P, const float* coords, const float* normals, const float* ncc, const float* dscale,
+                     const int* img_off, const int* images, const int* grids,
+                     const int* vimg_off, const int* vimages, const int* vgrids, const int* timages);
+void pmvso_grid_dims(const pmvso_ctx* c, int image, int* gw, int* gh);
+void pmvso_build_depth_maps(pmvso_ctx* c);                           /* CFilter::setDepthMaps, filter.cpp:667-732 */
+void pmvso_get_depth_map(const pmvso_ctx* c, int image, int* out);   /* patch id per cell, -1 = empty */
+int pmvso_is_visible(const pmvso_ctx* c, const float* coord, const float* normal, int image, int ix, int iy, float strict);
+/* CPatchOrganizerS::setVImagesVGrids (patchOrganizerS.cpp:420-450) for store patch k with an empty _vimages */
+int pmvso_set_vimages(const pmvso_ctx* c, int k, int* vimages, int* vgrids, int cap);
+/* CFilter::filterExactThread's test (filter.cpp:315-343) for store patch k in (image, ix, iy): 1 = keep */
+int pmvso_filter_exact_safe(const pmvso_ctx* c, int k, int image, int ix, int iy);
+int pmvso_is_neighbor(const pmvso_ctx* c, int a, int b, float thr);  /* CFindMatch::isNeighbor, findMatch.cpp:120-149 */
+float pmvso_compute_gain(const pmvso_ctx* c, int k);                 /* CFilter::computeGain, filter.cpp:88-146 */
+
 #ifdef __cplusplus
 }
 #endif

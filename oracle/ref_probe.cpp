@@ -304,6 +304,55 @@ void ref_get_patch(int i, float* coord, float* normal, float* ncc_dscale_ascale,
   for (int k = 0; k < *nv; ++k) vimages[k] = p._vimages[k];
 }
 
+// ---- filter-stage state (after ref_run): the reference's own depth maps, visibility test, gains -------------
+// collectPatches(0) numbers the patches: _ppatches[k]->_id == k
+int ref_collect_patches(void) { g_fm->_pos.collectPatches(0); return (int)g_fm->_pos._ppatches.size(); }
+void ref_grid_dims(int image, int* gw, int* gh) { *gw = g_fm->_pos._gwidths[image]; *gh = g_fm->_pos._gheights[image]; }
+// full patch record k: coord4, normal4, [ncc, dscale, ascale, tmp], images+grids, vimages+vgrids, [timages, fix, flag]
+void ref_get_patch_full(int k, float* coord, float* normal, float* scal4, int* images, int* grids, int* n, int* vimages, int* vgrids,
+                        int* nv, int* misc3, int cap) {
+  const Patch::CPatch& p = *g_fm->_pos._ppatches[k];
+  out4(p._coord, coord); out4(p._normal, normal);
+  scal4[0] = p._ncc; scal4[1] = p._dscale; scal4[2] = p._ascale; scal4[3] = p._tmp;
+  *n = std::min((int)p._images.size(), cap);
+  for (int i = 0; i < *n; ++i) { images[i] = p._images[i]; grids[2 * i] = p._grids[i][0]; grids[2 * i + 1] = p._grids[i][1]; }
+  *nv = std::min((int)p._vimages.size(), cap);
+  for (int i = 0; i < *nv; ++i) { vimages[i] = p._vimages[i]; vgrids[2 * i] = p._vgrids[i][0]; vgrids[2 * i + 1] = p._vgrids[i][1]; }
+  misc3[0] = p._timages; misc3[1] = p._fix; misc3[2] = p._flag;
+}
+// CFilter::setDepthMaps over the collected patches; out = patch id per cell of `image` (-1 = empty)
+void ref_set_depth_maps(void) { g_fm->_filter.setDepthMaps(); }
+void ref_get_depth_map(int image, int* out) {
+  const int n = g_fm->_pos._gwidths[image] * g_fm->_pos._gheights[image];
+  for (int i = 0; i < n; ++i) {
+    const Patch::PPatch& q = g_fm->_pos._dpgrids[image][i];
+    out[i] = (q == CPatchOrganizerS::_MAXDEPTH) ? -1 : q->_id;
+  }
+}
+int ref_is_visible(int k, int image, int ix, int iy, float strict) {
+  return g_fm->_pos.isVisible(*g_fm->_pos._ppatches[k], image, ix, iy, strict, 0);
+}
+int ref_is_neighbor(int a, int b, float thr) { return g_fm->isNeighbor(*g_fm->_pos._ppatches[a], *g_fm->_pos._ppatches[b], thr); }
+float ref_compute_gain(int k) { return g_fm->_filter.computeGain(*g_fm->_pos._ppatches[k], 0); }
+// CPatchOrganizerS::setVImagesVGrids on a COPY of patch k whose _vimages were cleared first
+int ref_set_vimages(int k, int* vimages, int* vgrids, int cap) {
+  Patch::CPatch p = *g_fm->_pos._ppatches[k];
+  p._vimages.clear(); p._vgrids.clear();
+  g_fm->_pos.setVImagesVGrids(p);
+  const int n = std::min((int)p._vimages.size(), cap);
+  for (int i = 0; i < n; ++i) { vimages[i] = p._vimages[i]; vgrids[2 * i] = p._vgrids[i][0]; vgrids[2 * i + 1] = p._vgrids[i][1]; }
+  return n;
+}
+// patches of one cell of _pgrids, in list order
+int ref_get_cell(int image, int cell, int* out, int cap) {
+  const std::vector<Patch::PPatch>& v = g_fm->_pos._pgrids[image][cell];
+  const int n = std::min((int)v.size(), cap);
+  for (int i = 0; i < n; ++i) out[i] = v[i]->_id;
+  return (int)v.size();
+}
+int ref_get_depth_flag(void) { return g_fm->_depth; }
+float ref_neighbor_threshold(int which) { return which == 0 ? g_fm->_neighborThreshold : (which == 1 ? g_fm->_neighborThreshold1 : g_fm->_neighborThreshold2); }
+
 unsigned long long ref_total_evals(void) { return nlopt::total_evals(); }
 unsigned long long ref_total_calls(void) { return nlopt::total_calls(); }
 void ref_reset_counters(void) { nlopt::total_evals() = 0; nlopt::total_calls() = 0; }

@@ -1,0 +1,66 @@
+"""Generate tests/golden/pmvs_state.npz: the filter-stage state of the REFERENCE'S OWN run (CFindMatch::run on
+tests/scene_util.small_scene(), CPU 1 -- deterministic) and the reference's answers on it: depth maps
+(CFilter::setDepthMaps), CPatchOrganizerS::isVisible / setVImagesVGrids, CFindMatch::isNeighbor and
+CFilter::computeGain.  Run:  python tests/golden/make_golden_state.py   (needs /root/reference)"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from scene_util import small_scene  # noqa: E402
+import __graft_entry__ as g  # noqa: E402
+from oracle.bindings import RefLib, build_ref  # noqa: E402
+
+
+def main():
+    synth = g.load_package().synth
+    assert build_ref()
+    scene = small_scene()
+    prefix = synth.write_scene(scene, "/tmp/pmvs_golden_state_scene")
+    ref = RefLib(prefix, num=scene.num, level=scene.option["level"], skip_features=False)
+    ref.run()
+    st = ref.state()
+    P = len(st["ncc"])
+    th = np.zeros(6, np.float32)
+    ref.lib.ref_thresholds(th.ctypes.data_as(ctypes.c_void_p))
+    out = {"scene_sha256": np.frombuffer(bytes.fromhex(scene.sha256()), np.uint8), "depth_flag": np.int32(ref.depth_flag()),
+           "ncc_threshold": th[0], "ncc_threshold_before": th[1]}
+    out.update({"st_" + k: v for k, v in st.items()})
+    ref.build_depth_maps()
+    out["depth_maps"] = np.concatenate([ref.depth_map(i) for i in range(scene.num)])
+    rng = np.random.default_rng(99)
+    ks = rng.integers(0, P, 600).astype(np.int32)
+    vis_q, vis_a = [], []
+    vim_off, vim, vgr = [0], [], []
+    for k in ks:
+        for e in range(st["img_off"][k], st["img_off"][k + 1]):
+            im = st["images"][e]; gx, gy = st["grids"][e]
+            for dx, dy in ((0, 0), (1, 0), (-1, 0), (0, 1), (0, -1)):
+                for strict in (0.5, 1.0):
+                    vis_q.append((k, im, gx + dx, gy + dy, strict)); vis_a.append(ref.is_visible_k(k, im, gx + dx, gy + dy, strict))
+        a, b = ref.set_vimages(k)
+        vim.append(a); vgr.append(b); vim_off.append(vim_off[-1] + len(a))
+    out["vis_k"] = ks
+    out["vis_query"] = np.array(vis_q, np.float32); out["vis_answer"] = np.array(vis_a, np.int8)
+    out["vim_off"] = np.array(vim_off, np.int32)
+    out["vim"] = np.concatenate(vim).astype(np.int32); out["vgr"] = np.concatenate(vgr).astype(np.int32)
+    pairs = []
+    for _ in range(4000):
+        a = int(rng.integers(0, P)); b = int(rng.integers(0, P)) if rng.random() < 0.3 else min(P - 1, a + int(rng.integers(1, 30)))
+        pairs.append((a, b, ref.is_neighbor(a, b, 1.0), ref.is_neighbor(a, b, 0.5)))
+    out["nb_pairs"] = np.array(pairs, np.int32)
+    out["gains"] = np.array([ref.compute_gain(k) for k in range(P)], np.float32)
+    path = os.path.join(HERE, "pmvs_state.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes; patches", P, "visible", np.bincount(out["vis_answer"]), "neighbours",
+          out["nb_pairs"][:, 2].mean(), "gain<0", (out["gains"] < 0).mean())
+
+
+if __name__ == "__main__":
+    main()

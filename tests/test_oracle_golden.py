@@ -128,3 +128,50 @@ def test_pre_post_process(oracle, scene_checked, G):
             assert np.array_equal(pgr, G["post_grids"][i, : G["post_n"][i]]), i
             assert pt == G["post_timages"][i] and ptmp == G["post_tmp"][i], i
     assert (G["pre_verdict"] == 0).sum() > 50 and (G["pre_verdict"] == 1).sum() > 10
+
+
+# ---- filter stage: the reference's own run, its depth maps, visibility tests, neighbour tests and gains ------------
+@pytest.fixture(scope="module")
+def S(scene):
+    s = np.load(os.path.join(HERE, "golden", "pmvs_state.npz"))
+    assert scene.sha256() == bytes(s["scene_sha256"]).hex()
+    return s
+
+
+STORE_KEYS = ("coords", "normals", "ncc", "dscale", "img_off", "images", "grids", "vimg_off", "vimages", "vgrids", "timages")
+
+
+@pytest.fixture(scope="module")
+def oracle_state(scene, S):
+    from oracle.bindings import OracleLib
+    o = OracleLib.from_scene(scene)
+    o.set_thresholds(float(S["ncc_threshold"]), float(S["ncc_threshold_before"]))
+    o.set_depth(int(S["depth_flag"]))
+    o.store_set({k: S["st_" + k] for k in STORE_KEYS})
+    o.build_depth_maps()
+    return o
+
+
+def test_depth_maps(oracle_state, scene, S):
+    got = np.concatenate([oracle_state.depth_map(i) for i in range(scene.num)])
+    assert np.array_equal(got, S["depth_maps"])
+    assert (got >= 0).mean() > 0.3
+
+
+def test_is_visible_and_vimages(oracle_state, S):
+    q, a = S["vis_query"], S["vis_answer"]
+    for i in range(len(q)):
+        k, im, ix, iy, strict = int(q[i, 0]), int(q[i, 1]), int(q[i, 2]), int(q[i, 3]), float(q[i, 4])
+        assert oracle_state.is_visible_k(k, im, ix, iy, strict) == a[i], i
+    assert 0.05 < (a == 0).mean() < 0.95
+    for j, k in enumerate(S["vis_k"]):
+        vim, vgr = oracle_state.set_vimages(int(k))
+        lo, hi = S["vim_off"][j], S["vim_off"][j + 1]
+        assert np.array_equal(vim, S["vim"][lo:hi]) and np.array_equal(vgr, S["vgr"].reshape(-1, 2)[lo:hi]), k
+
+
+def test_is_neighbor_and_gain(oracle_state, S):
+    for a, b, n1, n05 in S["nb_pairs"]:
+        assert oracle_state.is_neighbor(a, b, 1.0) == n1 and oracle_state.is_neighbor(a, b, 0.5) == n05, (a, b)
+    gains = np.array([oracle_state.compute_gain(k) for k in range(len(S["gains"]))], np.float32)
+    assert np.array_equal(gains, S["gains"])
