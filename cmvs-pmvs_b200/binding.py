@@ -20,7 +20,8 @@ SYMBOLS = [
     "pmvsb_set_visdata2", "pmvsb_finalize_scene", "pmvsb_set_thresholds", "pmvsb_set_optimizer", "pmvsb_image_dims",
     "pmvsb_download_image", "pmvsb_get_camera", "pmvsb_project_batch", "pmvsb_grab_tex_batch", "pmvsb_eval_objective_batch",
     "pmvsb_compute_incc_batch", "pmvsb_set_inccs_batch", "pmvsb_set_scales_batch", "pmvsb_pre_process_batch",
-    "pmvsb_post_process_batch", "pmvsb_refine_batch",
+    "pmvsb_post_process_batch", "pmvsb_set_depth", "pmvsb_grid_dims", "pmvsb_store_upload", "pmvsb_build_depth_maps",
+    "pmvsb_download_depth_map", "pmvsb_set_vimages_store", "pmvsb_filter_exact_store", "pmvsb_compute_gains_store", "pmvsb_refine_batch",
     "pmvsb_refine_batch_dev", "pmvsb_sync", "pmvsb_stream", "pmvsb_set_stream", "pmvsb_launch_count", "pmvsb_last_refine_ms",
 ]
 
@@ -198,6 +199,49 @@ class PmvsB200:
         self._ck(self.lib.pmvsb_post_process_batch(self.ctx, P, stride, _vp(coords), _vp(normals), _vp(ncc), _vp(im), _vp(n), _vp(g), _vp(t),
                                                    _vp(tmp), _vp(v)))
         return dict(images=im, nimages=n, grids=g, timages=t, tmp=tmp, verdict=v)
+
+    # -- filter stage ------------------------------------------------------------------------------------
+    def set_depth(self, depth):
+        self._ck(self.lib.pmvsb_set_depth(self.ctx, int(depth)))
+
+    def grid_dims(self, image):
+        gw, gh = C.c_int(), C.c_int()
+        self._ck(self.lib.pmvsb_grid_dims(self.ctx, int(image), C.byref(gw), C.byref(gh)))
+        return gw.value, gh.value
+
+    def store_upload(self, st):
+        """st: dict with coords, normals, ncc, dscale, img_off, images, grids, vimg_off, vimages, vgrids, timages"""
+        f = lambda k: np.ascontiguousarray(st[k], dtype=np.float32)
+        i = lambda k: np.ascontiguousarray(st[k], dtype=np.int32)
+        self._store_P = len(st["ncc"]); self._store_E = int(st["img_off"][-1])
+        self._ck(self.lib.pmvsb_store_upload(self.ctx, self._store_P, _vp(f("coords")), _vp(f("normals")), _vp(f("ncc")), _vp(f("dscale")),
+                                             _vp(i("img_off")), _vp(i("images")), _vp(i("grids")), _vp(i("vimg_off")), _vp(i("vimages")),
+                                             _vp(i("vgrids")), _vp(i("timages"))))
+
+    def build_depth_maps(self):
+        self._ck(self.lib.pmvsb_build_depth_maps(self.ctx))
+
+    def depth_map(self, image):
+        gw, gh = self.grid_dims(image)
+        out = np.zeros(gw * gh, np.int32)
+        self._ck(self.lib.pmvsb_download_depth_map(self.ctx, int(image), _vp(out)))
+        return out
+
+    def set_vimages_store(self, vcap):
+        P = self._store_P
+        vim = np.zeros((P, vcap), np.int32); vgr = np.zeros((P, vcap, 2), np.int32); nv = np.zeros(P, np.int32)
+        self._ck(self.lib.pmvsb_set_vimages_store(self.ctx, int(vcap), _vp(vim), _vp(vgr), _vp(nv)))
+        return vim, vgr, nv
+
+    def filter_exact_store(self):
+        safe = np.zeros(self._store_E, np.uint8)
+        self._ck(self.lib.pmvsb_filter_exact_store(self.ctx, _vp(safe)))
+        return safe
+
+    def compute_gains_store(self):
+        g = np.zeros(self._store_P, np.float32)
+        self._ck(self.lib.pmvsb_compute_gains_store(self.ctx, _vp(g)))
+        return g
 
     def refine_batch(self, coords, normals, images, dscales, nimages=None):
         """-> dict(coords, normals, ncc, evals, ok); inputs are not modified."""

@@ -17,6 +17,7 @@
 #include "pmvs_device.cuh"
 #include "pmvs_group.cuh"
 #include "pmvs_select.cuh"
+#include "pmvs_filter.cuh"
 
 #ifndef PMVS_MINBLOCKS
 #define PMVS_MINBLOCKS 6
@@ -494,6 +495,12 @@ struct pmvsb_ctx {
   LevelDev* d_levels = nullptr;
   int* d_counter = nullptr;
   int32_t* d_vis_off = nullptr;
+  // filter-stage patch table
+  StoreDev store;
+  std::vector<void*> store_bufs;
+  int store_entries = 0, store_ventries = 0, store_cells = 0;
+  int depth_flag = 0;
+  bool store_set = false, depth_built = false;
   char* arena = nullptr;          // grow-only device staging for the host-pointer entry points
   size_t arena_cap = 0, arena_used = 0;
   int32_t* d_vis_idx = nullptr;
@@ -706,6 +713,7 @@ static int arena_reserve(pmvsb_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->arena_cap) return PMVSB_OK;
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(ctx->arena);
+  for (void* b : ctx->store_bufs) cudaFree(b);
   ctx->arena = nullptr; ctx->arena_cap = 0;
   const size_t want = bytes + bytes / 4 + (1u << 20);
   CK(cudaMalloc((void**)&ctx->arena, want));
@@ -717,6 +725,16 @@ static T* arena_take(pmvsb_ctx* ctx, size_t n) {
   const size_t off = (ctx->arena_used + 255) & ~(size_t)255;
   ctx->arena_used = off + sizeof(T) * n;
   return reinterpret_cast<T*>(ctx->arena + off);
+}
+
+template <typename T>
+static int store_put(pmvsb_ctx* ctx, const T*& dst, const T* src, size_t n) {
+  T* d = nullptr;
+  CK(cudaMalloc((void**)&d, sizeof(T) * (n ? n : 1)));
+  ctx->store_bufs.push_back(d);
+  if (n) CK(cudaMemcpyAsync(d, src, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
+  dst = d;
+  return PMVSB_OK;
 }
 
 extern "C" {
@@ -774,6 +792,7 @@ int pmvsb_destroy(pmvsb_ctx* ctx) {
     for (auto* p : im.levels) cudaFree(p);
   cudaFree(ctx->d_cams); cudaFree(ctx->d_levels); cudaFree(ctx->d_counter); cudaFree(ctx->d_vis_off); cudaFree(ctx->d_vis_idx);
   cudaFree(ctx->arena);
+  for (void* b : ctx->store_bufs) cudaFree(b);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1091,6 +1110,198 @@ int pmvsb_set_scales_batch(pmvsb_ctx* ctx, int P, int stride, const float* coord
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(dscale, dd.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ascale, da.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+// ---- filter stage -----------------------------------------------------------------------------------------
+int pmvsb_set_depth(pmvsb_ctx* ctx, int depth) {
+  if (!ctx || depth < 0) return fail(ctx, PMVSB_EINVAL, "set_depth: bad argument");
+  ctx->depth_flag = depth;
+  ctx->store.depth_flag = depth;
+  return PMVSB_OK;
+}
+
+int pmvsb_grid_dims(pmvsb_ctx* ctx, int image, int* gwidth, int* gheight) {
+  if (!ctx || image < 0 || image >= ctx->num || !ctx->images[image].set || !gwidth || !gheight)
+    return fail(ctx, PMVSB_EINVAL, "grid_dims: bad argument");
+  *gwidth = (ctx->images[image].w[ctx->level] + ctx->csize - 1) / ctx->csize;
+  *gheight = (ctx->images[image].h[ctx->level] + ctx->csize - 1) / ctx->csize;
+  return PMVSB_OK;
+}
+
+int pmvsb_store_upload(pmvsb_ctx* ctx, int P, const float* coords, const float* normals, const float* ncc, const float* dscale,
+                       const int32_t* img_off, const int32_t* images, const int32_t* grids, const int32_t* vimg_off,
+                       const int32_t* vimages, const int32_t* vgrids, const int32_t* timages) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (P < 0 || !coords || !normals || !ncc || !dscale || !img_off || !vimg_off || !timages) return fail(ctx, PMVSB_EINVAL, "store_upload: null pointer");
+  const int E = img_off[P], VE = vimg_off[P];
+  if ((E > 0 && (!images || !grids)) || (VE > 0 && (!vimages || !vgrids))) return fail(ctx, PMVSB_EINVAL, "store_upload: null list");
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (void* b : ctx->store_bufs) cudaFree(b);
+  ctx->store_bufs.clear();
+  ctx->store_set = false; ctx->depth_built = false;
+  // grid geometry + _pgrids as CSR (patchOrganizerS.cpp:315-331); validate every index the kernels will trust
+  std::vector<int32_t> gw(ctx->num), gh(ctx->num), base(ctx->tnum + 1, 0);
+  for (int i = 0; i < ctx->num; ++i) {
+    gw[i] = (ctx->images[i].w[ctx->level] + ctx->csize - 1) / ctx->csize;
+    gh[i] = (ctx->images[i].h[ctx->level] + ctx->csize - 1) / ctx->csize;
+  }
+  for (int i = 0; i < ctx->tnum; ++i) base[i + 1] = base[i] + gw[i] * gh[i];
+  const int cells = base[ctx->tnum];
+  std::vector<int32_t> entry_patch(E), cell_off(cells + 1, 0);
+  for (int p = 0; p < P; ++p) {
+    if (img_off[p + 1] < img_off[p] || vimg_off[p + 1] < vimg_off[p]) return fail(ctx, PMVSB_EINVAL, "store_upload: offsets not monotone");
+    for (int e = img_off[p]; e < img_off[p + 1]; ++e) {
+      const int im = images[e];
+      if (im < 0 || im >= ctx->num) return fail(ctx, PMVSB_EINVAL, "store_upload: image index out of range");
+      entry_patch[e] = p;
+      if (im < ctx->tnum) {
+        const int x = grids[2 * e], y = grids[2 * e + 1];
+        if (x < 0 || x >= gw[im] || y < 0 || y >= gh[im]) return fail(ctx, PMVSB_EINVAL, "store_upload: grid cell out of range");
+        cell_off[base[im] + y * gw[im] + x + 1]++;
+      }
+    }
+    for (int e = vimg_off[p]; e < vimg_off[p + 1]; ++e) {
+      const int im = vimages[e];
+      if (im < 0 || im >= ctx->tnum) return fail(ctx, PMVSB_EINVAL, "store_upload: vimage index out of range");
+      const int x = vgrids[2 * e], y = vgrids[2 * e + 1];
+      if (x < 0 || x >= gw[im] || y < 0 || y >= gh[im]) return fail(ctx, PMVSB_EINVAL, "store_upload: vgrid cell out of range");
+    }
+  }
+  for (int i = 0; i < cells; ++i) cell_off[i + 1] += cell_off[i];
+  std::vector<int32_t> cell_patch(cell_off[cells] ? cell_off[cells] : 1), fill(cells, 0);
+  for (int p = 0; p < P; ++p)
+    for (int e = img_off[p]; e < img_off[p + 1]; ++e) {
+      const int im = images[e];
+      if (im >= ctx->tnum) continue;
+      const int cell = base[im] + grids[2 * e + 1] * gw[im] + grids[2 * e];
+      cell_patch[cell_off[cell] + fill[cell]++] = p;
+    }
+  StoreDev& st = ctx->store;
+  st.P = P;
+  if ((r = store_put(ctx, st.coords, coords, (size_t)4 * P))) return r;
+  if ((r = store_put(ctx, st.normals, normals, (size_t)4 * P))) return r;
+  if ((r = store_put(ctx, st.ncc, ncc, (size_t)P))) return r;
+  if ((r = store_put(ctx, st.dscale, dscale, (size_t)P))) return r;
+  if ((r = store_put(ctx, st.img_off, img_off, (size_t)P + 1))) return r;
+  if ((r = store_put(ctx, st.images, images, (size_t)E))) return r;
+  if ((r = store_put(ctx, st.grids, grids, (size_t)2 * E))) return r;
+  if ((r = store_put(ctx, st.entry_patch, entry_patch.data(), (size_t)E))) return r;
+  if ((r = store_put(ctx, st.vimg_off, vimg_off, (size_t)P + 1))) return r;
+  if ((r = store_put(ctx, st.vimages, vimages, (size_t)VE))) return r;
+  if ((r = store_put(ctx, st.vgrids, vgrids, (size_t)2 * VE))) return r;
+  if ((r = store_put(ctx, st.timages, timages, (size_t)P))) return r;
+  if ((r = store_put(ctx, st.cell_base, base.data(), base.size()))) return r;
+  if ((r = store_put(ctx, st.gw, gw.data(), gw.size()))) return r;
+  if ((r = store_put(ctx, st.gh, gh.data(), gh.size()))) return r;
+  if ((r = store_put(ctx, st.cell_off, cell_off.data(), cell_off.size()))) return r;
+  if ((r = store_put(ctx, st.cell_patch, cell_patch.data(), cell_patch.size()))) return r;
+  unsigned long long* dp = nullptr;
+  CK(cudaMalloc((void**)&dp, sizeof(unsigned long long) * (cells ? cells : 1)));
+  ctx->store_bufs.push_back(dp);
+  st.dp = dp;
+  st.depth_flag = ctx->depth_flag;
+  st.ncc_threshold = ctx->ncc_threshold;
+  const double c120 = std::cos(120.0 * M_PI / 180.0);   // findMatch.cpp:126
+  float cf = (float)c120;
+  if ((double)cf < c120) cf = std::nextafterf(cf, INFINITY);
+  st.cos120_f = cf;
+  ctx->store_entries = E; ctx->store_ventries = VE; ctx->store_cells = cells;
+  CK(cudaStreamSynchronize(ctx->stream));   // host vectors above go out of scope
+  ctx->store_set = true;
+  return PMVSB_OK;
+}
+
+static int need_store(pmvsb_ctx* ctx, bool depth) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (!ctx->store_set) return fail(ctx, PMVSB_ESTATE, "no patch table: call pmvsb_store_upload first");
+  if (depth && ctx->depth_flag != 0 && !ctx->depth_built) return fail(ctx, PMVSB_ESTATE, "depth maps not built: call pmvsb_build_depth_maps first");
+  ctx->store.depth_flag = ctx->depth_flag;
+  ctx->store.ncc_threshold = ctx->ncc_threshold;
+  return PMVSB_OK;
+}
+
+int pmvsb_build_depth_maps(pmvsb_ctx* ctx) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  CK(cudaMemsetAsync(ctx->store.dp, 0xff, sizeof(unsigned long long) * (ctx->store_cells ? ctx->store_cells : 1), ctx->stream));
+  const long long n = (long long)ctx->store.P * ctx->tnum;
+  if (n > 0) {
+    k_depth_maps<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->scene, ctx->store);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->depth_built = true;
+  return PMVSB_OK;
+}
+
+int pmvsb_download_depth_map(pmvsb_ctx* ctx, int image, int32_t* patch_id) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  if (!ctx->depth_built || image < 0 || image >= ctx->tnum || !patch_id) return fail(ctx, PMVSB_EINVAL, "download_depth_map: bad argument or maps not built");
+  int gw, gh;
+  pmvsb_grid_dims(ctx, image, &gw, &gh);
+  std::vector<int32_t> base(ctx->tnum + 1, 0);
+  for (int i = 0; i < ctx->tnum; ++i) { int a, b; pmvsb_grid_dims(ctx, i, &a, &b); base[i + 1] = base[i] + a * b; }
+  std::vector<unsigned long long> keys((size_t)gw * gh);
+  CK(cudaMemcpyAsync(keys.data(), ctx->store.dp + base[image], sizeof(unsigned long long) * keys.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < keys.size(); ++i) patch_id[i] = keys[i] == ~0ull ? -1 : (int32_t)(keys[i] & 0xffffffffull);
+  return PMVSB_OK;
+}
+
+int pmvsb_set_vimages_store(pmvsb_ctx* ctx, int vcap, int32_t* vimages, int32_t* vgrids, int32_t* nv) {
+  int r = need_store(ctx, true);
+  if (r) return r;
+  if (vcap < 1 || !vimages || !vgrids || !nv) return fail(ctx, PMVSB_EINVAL, "set_vimages_store: bad argument");
+  const int P = ctx->store.P;
+  if (P == 0) return PMVSB_OK;
+  DevBuf<int32_t> dv, dg, dn;
+  CK(dv.alloc((size_t)vcap * P)); CK(dg.alloc((size_t)2 * vcap * P)); CK(dn.alloc(P));
+  CK(cudaMemsetAsync(dv.p, 0xff, sizeof(int32_t) * (size_t)vcap * P, ctx->stream));
+  CK(cudaMemsetAsync(dg.p, 0xff, sizeof(int32_t) * (size_t)2 * vcap * P, ctx->stream));
+  k_set_vimages<<<(P + 3) / 4, 128, 0, ctx->stream>>>(ctx->scene, ctx->store, vcap, dv.p, dg.p, dn.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(vimages, dv.p, sizeof(int32_t) * (size_t)vcap * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(vgrids, dg.p, sizeof(int32_t) * (size_t)2 * vcap * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(nv, dn.p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_filter_exact_store(pmvsb_ctx* ctx, uint8_t* safe) {
+  int r = need_store(ctx, true);
+  if (r) return r;
+  if (!safe) return fail(ctx, PMVSB_EINVAL, "filter_exact_store: null pointer");
+  const int E = ctx->store_entries;
+  if (E == 0) return PMVSB_OK;
+  DevBuf<uint8_t> ds;
+  CK(ds.alloc(E));
+  k_filter_exact<<<(E + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, ctx->store, E, ds.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(safe, ds.p, E, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_compute_gains_store(pmvsb_ctx* ctx, float* gains) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  if (!gains) return fail(ctx, PMVSB_EINVAL, "compute_gains_store: null pointer");
+  const int P = ctx->store.P;
+  if (P == 0) return PMVSB_OK;
+  DevBuf<float> dg;
+  CK(dg.alloc(P));
+  k_gains<<<(P + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, ctx->store, dg.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(gains, dg.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return PMVSB_OK;
 }

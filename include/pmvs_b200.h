@@ -114,6 +114,27 @@ int pmvsb_post_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coo
                              const float* ncc, int32_t* images, int32_t* nimages, int32_t* grids,
                              int32_t* timages, float* tmp, int32_t* verdict);
 
+/* ---- filter stage: depth maps, visibility, gains ----------------------------------------------------------
+ * The host keeps the cell bookkeeping (CPatchOrganizerS) and hands the current patch table over as arrays
+ * (index = CPatch::_id after collectPatches(), source/pmvs/patchOrganizerS.cpp:207-236):
+ *   coords, normals float[4P]; ncc, dscale float[P]; img_off int32[P+1] + images int32[E] + grids int32[2E]
+ *   (CPatch::_images/_grids as CSR); vimg_off/vimages/vgrids likewise (CPatch::_vimages/_vgrids); timages int32[P]. */
+int pmvsb_set_depth(pmvsb_ctx* ctx, int depth);   /* CFindMatch::_depth: 0 makes isVisible trivially true (patchOrganizerS.cpp:493) */
+int pmvsb_grid_dims(pmvsb_ctx* ctx, int image, int* gwidth, int* gheight);   /* patchOrganizerS.cpp:72-77 */
+int pmvsb_store_upload(pmvsb_ctx* ctx, int P, const float* coords, const float* normals, const float* ncc, const float* dscale,
+                       const int32_t* img_off, const int32_t* images, const int32_t* grids,
+                       const int32_t* vimg_off, const int32_t* vimages, const int32_t* vgrids, const int32_t* timages);
+/* CFilter::setDepthMaps (source/pmvs/filter.cpp:667-732): nearest patch per cell of every target image */
+int pmvsb_build_depth_maps(pmvsb_ctx* ctx);
+int pmvsb_download_depth_map(pmvsb_ctx* ctx, int image, int32_t* patch_id);   /* gw*gh ids, -1 = empty */
+/* CPatchOrganizerS::setVImagesVGrids (patchOrganizerS.cpp:420-450) for every table patch, from an empty _vimages:
+ * vimages int32[vcap*P], vgrids int32[2*vcap*P], nv int32[P] */
+int pmvsb_set_vimages_store(pmvsb_ctx* ctx, int vcap, int32_t* vimages, int32_t* vgrids, int32_t* nv);
+/* CFilter::filterExactThread's visibility re-test (filter.cpp:315-343): safe uint8[E], one flag per image entry */
+int pmvsb_filter_exact_store(pmvsb_ctx* ctx, uint8_t* safe);
+/* CFilter::filterOutsideThread / computeGain (filter.cpp:88-201): gains float[P] */
+int pmvsb_compute_gains_store(pmvsb_ctx* ctx, float* gains);
+
 /* ---- the hot call -------------------------------------------------------------------------------
  * COptim::refinePatch for a whole seed / expansion frontier in one launch (optim.cpp:496-502,580-658):
  * in-kernel bounded Nelder-Mead over (depth, angle1, angle2) around my_f, then the final
