@@ -465,6 +465,28 @@ __global__ void __launch_bounds__(32) k_post_process(SceneDev s, SelectParams sp
   if (lane == 0) { nimages[p] = n; timages[p] = t; tmp[p] = tm; verdict[p] = v; }
 }
 
+
+// COptim::setRefImage + setGrids for a batch (filterExact's tail, filter.cpp:277-280)
+template <int WSIZE>
+__global__ void __launch_bounds__(32) k_set_ref_image(SceneDev s, SelectParams sp, int P, int stride, const float* __restrict__ coords,
+                                                      const float* __restrict__ normals, int32_t* __restrict__ images,
+                                                      int32_t* __restrict__ nimages, int32_t* __restrict__ grids) {
+  __shared__ SelScratch<WSIZE> sc;
+  const int p = blockIdx.x, lane = threadIdx.x;
+  if (p >= P) return;
+  float coord[4], normal[4];
+  load_patch(coords, normals, p, coord, normal);
+  const int cap = min(stride, kSelMaxViews);
+  int n = min(nimages[p], cap);
+  for (int i = lane; i < n; i += 32) sc.images[i] = images[(size_t)p * stride + i];
+  __syncwarp();
+  if (n > 0) n = sel_set_ref_image<WSIZE>(s, sc, n, lane, coord, normal);
+  __syncwarp();
+  if (n > 0) sel_set_grids(s, sc, n, lane, coord, grids + (size_t)2 * p * stride);
+  for (int i = lane; i < n; i += 32) images[(size_t)p * stride + i] = sc.images[i];
+  if (lane == 0) nimages[p] = n;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -1302,6 +1324,77 @@ int pmvsb_compute_gains_store(pmvsb_ctx* ctx, float* gains) {
   ++ctx->launches;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(gains, dg.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_set_vimages_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals, const int32_t* images,
+                            const int32_t* nimages, int vstride, int32_t* vimages, int32_t* nv, int32_t* vgrids) {
+  int r = need_store(ctx, true);
+  if (r) return r;
+  if (!normals || !nimages || vstride < 1 || !vimages || !nv || !vgrids) return fail(ctx, PMVSB_EINVAL, "set_vimages_batch: bad argument");
+  if (P == 0) return PMVSB_OK;
+  for (int p = 0; p < P; ++p)
+    for (int e = 0; e < std::min(nv[p], vstride); ++e)
+      if (vimages[(size_t)p * vstride + e] < 0 || vimages[(size_t)p * vstride + e] >= ctx->tnum) return fail(ctx, PMVSB_EINVAL, "set_vimages_batch: vimage out of range");
+  PatchStage st;
+  r = stage_patches(ctx, st, P, stride, coords, normals, images, nimages, nullptr);
+  if (r) return r;
+  DevBuf<int32_t> dv, dg, dn;
+  CK(dv.alloc((size_t)vstride * P)); CK(dg.alloc((size_t)2 * vstride * P)); CK(dn.alloc(P));
+  CK(cudaMemcpyAsync(dv.p, vimages, sizeof(int32_t) * (size_t)vstride * P, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dg.p, vgrids, sizeof(int32_t) * (size_t)2 * vstride * P, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dn.p, nv, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->stream));
+  k_set_vimages_batch<<<(P + 3) / 4, 128, 0, ctx->stream>>>(ctx->scene, ctx->store, P, stride, st.coords.p, st.normals.p, st.images.p,
+                                                             st.nimages.p, vstride, dv.p, dn.p, dg.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(vimages, dv.p, sizeof(int32_t) * (size_t)vstride * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(vgrids, dg.p, sizeof(int32_t) * (size_t)2 * vstride * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(nv, dn.p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_set_ref_image_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals, int32_t* images,
+                              int32_t* nimages, int32_t* grids) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (!normals || !nimages || !grids) return fail(ctx, PMVSB_EINVAL, "set_ref_image_batch: null pointer");
+  if (ctx->wsize == 9) return fail(ctx, PMVSB_EINVAL, "set_ref_image_batch: wsize 9 is not supported by the selection kernels");
+  if (P == 0) return PMVSB_OK;
+  PatchStage st;
+  r = stage_patches(ctx, st, P, stride, coords, normals, images, nimages, nullptr);
+  if (r) return r;
+  DevBuf<int32_t> dg;
+  CK(dg.alloc((size_t)2 * stride * P));
+  CK(cudaMemsetAsync(dg.p, 0xff, sizeof(int32_t) * (size_t)2 * stride * P, ctx->stream));
+  if (ctx->wsize == 5) k_set_ref_image<5><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, dg.p);
+  else k_set_ref_image<7><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, dg.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(images, st.images.p, sizeof(int32_t) * (size_t)stride * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(nimages, st.nimages.p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(grids, dg.p, sizeof(int32_t) * (size_t)2 * stride * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_patch_colors_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const int32_t* images, const int32_t* nimages,
+                             uint8_t* rgb) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (!nimages || !rgb) return fail(ctx, PMVSB_EINVAL, "patch_colors_batch: null pointer");
+  if (P == 0) return PMVSB_OK;
+  PatchStage st;
+  r = stage_patches(ctx, st, P, stride, coords, nullptr, images, nimages, nullptr);
+  if (r) return r;
+  DevBuf<uint8_t> dc;
+  CK(dc.alloc((size_t)3 * P));
+  k_patch_colors<<<(P + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, P, stride, st.coords.p, st.images.p, st.nimages.p, dc.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(rgb, dc.p, (size_t)3 * P, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return PMVSB_OK;
 }

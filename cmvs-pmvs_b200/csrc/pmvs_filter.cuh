@@ -131,6 +131,84 @@ __global__ void k_set_vimages(SceneDev s, StoreDev st, int vcap, int32_t* __rest
   if (lane == 0) nv[p] = n < vcap ? n : vcap;
 }
 
+// setVImagesVGrids for a batch of patches outside the table (candidates inside postProcess, or the table itself in
+// additive mode): images[] and the existing vimages[] count as used, new visible target images are appended.
+__global__ void k_set_vimages_batch(SceneDev s, StoreDev st, int P, int stride, const float* __restrict__ coords,
+                                    const float* __restrict__ normals, const int32_t* __restrict__ images,
+                                    const int32_t* __restrict__ nimages, int vstride, int32_t* __restrict__ vimages,
+                                    int32_t* __restrict__ nv, int32_t* __restrict__ vgrids) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= P) return;
+  const int p = warp;
+  const float4 c4 = __ldg(reinterpret_cast<const float4*>(coords) + p);
+  const float4 n4 = __ldg(reinterpret_cast<const float4*>(normals) + p);
+  const float X[4] = {c4.x, c4.y, c4.z, c4.w}, N[4] = {n4.x, n4.y, n4.z, n4.w};
+  const int ni = min(nimages[p], stride);
+  const int nv0 = min(nv[p], vstride);
+  int n = nv0;
+  for (int base = 0; base < s.tnum; base += 32) {
+    const int image = base + lane;
+    bool ok = false;
+    int ix = 0, iy = 0;
+    if (image < s.tnum) {
+      bool used = false;
+      for (int e = 0; e < ni; ++e) used |= (images[(size_t)p * stride + e] == image);
+      for (int e = 0; e < nv0; ++e) used |= (vimages[(size_t)p * vstride + e] == image);
+      if (!used) {
+        CamDev cam;
+        load_cam(s, image, cam);
+        float ic[3];
+        project(cam, X, ic);
+        ix = ((int)floorf(ic[0] + 0.5f)) / s.csize;
+        iy = ((int)floorf(ic[1] + 0.5f)) / s.csize;
+        ok = is_visible(s, st, cam, X, N, image, ix, iy, 0.5f) != 0;
+      }
+    }
+    const unsigned m = __ballot_sync(kFull, ok);
+    const int pos = n + __popc(m & ((1u << lane) - 1u));
+    if (ok && pos < vstride) {
+      vimages[(size_t)p * vstride + pos] = image;
+      vgrids[((size_t)p * vstride + pos) * 2] = ix;
+      vgrids[((size_t)p * vstride + pos) * 2 + 1] = iy;
+    }
+    n += __popc(m);
+    __syncwarp();
+  }
+  if (lane == 0) nv[p] = n < vstride ? n : vstride;
+}
+
+// writePLY's vertex colour (patchOrganizerS.cpp:713-727): one thread per patch
+__global__ void k_patch_colors(SceneDev s, int P, int stride, const float* __restrict__ coords, const int32_t* __restrict__ images,
+                               const int32_t* __restrict__ nimages, uint8_t* __restrict__ rgb) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float4 c4 = __ldg(reinterpret_cast<const float4*>(coords) + p);
+  const float X[4] = {c4.x, c4.y, c4.z, c4.w};
+  const int n = min(nimages[p], stride);
+  float acc[3] = {0.f, 0.f, 0.f};
+  int denom = 0;
+  for (int i = 0; i < n; ++i) {
+    const int image = images[(size_t)p * stride + i];
+    CamDev cam;
+    load_cam(s, image, cam);
+    float ic[3];
+    project(cam, X, ic);
+    const LevelDev lv = s.levels[image * s.nlevels + s.level];
+    // the reference samples without a bounds test; stay inside the image instead of reading out of it
+    const float x = smin(smax(ic[0], 0.0f), (float)(lv.w - 2)), y = smin(smax(ic[1], 0.0f), (float)(lv.h - 2));
+    float c[3];
+    get_color(lv, x, y, c);
+    acc[0] += c[0]; acc[1] += c[1]; acc[2] += c[2];
+    ++denom;
+  }
+  if (denom == 0) denom = 1;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int v = (int)floorf(acc[k] / (float)denom + 0.5f);
+    rgb[3 * p + k] = (uint8_t)(v < 255 ? (v < 0 ? 0 : v) : 255);
+  }
+}
+
 // CFilter::filterExactThread's test (filter.cpp:315-343): the patch stays in (image, x, y) if it is visible there
 // or in one of the four neighbouring cells.  One thread per image entry.  strict = _neighborThreshold1 = 1.0.
 __global__ void k_filter_exact(SceneDev s, StoreDev st, int nentries, uint8_t* __restrict__ safe) {

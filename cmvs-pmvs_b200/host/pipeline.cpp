@@ -1,0 +1,988 @@
+// cmvs-pmvs_b200/host/pipeline.cpp -- wave-based seed / expand / filter rounds over the C ABI.
+//
+// Reference behaviour followed (paths relative to /root/reference/source/pmvs):
+//   CFindMatch::run        findMatch.cpp:187-220   seed, then 3 x (expand, filter, thresholds -= 0.05)
+//   CSeed                  seed.cpp:40-384         epipolar candidates, <= 2 successes per feature, 1 patch per cell
+//   CExpand                expand.cpp:17-406       6-direction empty-block search, cell counters
+//   CFilter                filter.cpp:13-665       outside / exact / neighbour (quadric) / small groups
+//   CPatchOrganizerS       patchOrganizerS.cpp     cell lists, neighbours, writers
+// Differences by construction: candidates of one wave are generated from one snapshot of the grids and are
+// evaluated together; they are committed in priority order with the cell rules re-checked at commit time.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <list>
+#include <numeric>
+#include <queue>
+#include <random>
+
+#include "pmvs_host.hpp"
+
+namespace pmvs {
+
+namespace {
+inline float dot4(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3]; }
+inline float norm4(const float* a) { return std::sqrt(dot4(a, a)); }
+inline void unitize4(float* v) {
+  const float l = dot4(v, v);
+  if (l != 1.0f && l != 0.0f) { const float s = std::sqrt(l); v[0] /= s; v[1] /= s; v[2] /= s; v[3] /= s; }
+}
+// include/numeric/vec4.hpp:303-322
+void ortho(const float* z, float* x, float* y) {
+  x[0] = x[1] = x[2] = x[3] = 0.0f;
+  y[0] = y[1] = y[2] = y[3] = 0.0f;
+  if (std::fabs(z[0]) > 0.5f) { x[0] = z[1]; x[1] = -z[0]; x[2] = 0; }
+  else if (std::fabs(z[1]) > 0.5f) { x[1] = z[2]; x[2] = -z[1]; x[0] = 0; }
+  else { x[2] = z[0]; x[0] = -z[2]; x[1] = 0; }
+  unitize4(x);
+  y[0] = z[1] * x[2] - z[2] * x[1];
+  y[1] = z[2] * x[0] - z[0] * x[2];
+  y[2] = z[0] * x[1] - z[1] * x[0];
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- geometry
+void Pipeline::project(int image, const float* X, float* o) const {   // include/image/camera.hpp:89-108
+  const Camera& c = cams_[image];
+  for (int i = 0; i < 3; ++i) o[i] = dot4(c.P[i], X);
+  if (o[2] <= 0.0f) { o[0] = -65535.0f; o[1] = -65535.0f; o[2] = -1.0f; return; }
+  const float z = o[2];
+  o[0] /= z; o[1] /= z; o[2] /= z;
+}
+
+float Pipeline::get_unit(int image, const float* X) const {          // optim.cpp:1116-1124
+  const Camera& c = cams_[image];
+  const float d[4] = {X[0] - c.centre[0], X[1] - c.centre[1], X[2] - c.centre[2], X[3] - c.centre[3]};
+  const float fz = norm4(d);
+  if (c.ipscale == 0.0f) return 1.0f;
+  return (float)(2.0 * fz * (1 << opt_.level) / c.ipscale);
+}
+
+bool Pipeline::is_neighbor(const Patch& l, const Patch& r, float hunit, float thr, float radius) const {   // findMatch.cpp:125-185
+  if (dot4(l.normal, r.normal) < std::cos(120.0 * M_PI / 180.0)) return false;
+  float diff[4];
+  for (int k = 0; k < 4; ++k) diff[k] = r.coord[k] - l.coord[k];
+  const float vunit = l.dscale + r.dscale;
+  const float f0 = dot4(l.normal, diff), f1 = dot4(r.normal, diff);
+  float ftmp = (std::fabs(f0) + std::fabs(f1)) / 2.0f;
+  ftmp /= vunit;
+  float t[4];
+  for (int k = 0; k < 4; ++k) t[k] = diff[k] * 2 - l.normal[k] * f0 - r.normal[k] * f1;
+  const float hsize = (float)(norm4(t) / 2.0 / hunit);
+  if (radius >= 0.0f && radius / hunit < hsize) return false;
+  if (1.0f < hsize) ftmp /= std::min(2.0f, hsize);
+  return ftmp < thr;
+}
+
+bool Pipeline::is_neighbor(const Patch& l, const Patch& r, float thr) const {   // findMatch.cpp:120-123
+  const float hunit = (float)((get_unit(l.images[0], l.coord) + get_unit(r.images[0], r.coord)) / 2.0 * opt_.csize);
+  return is_neighbor(l, r, hunit, thr, -1.0f);
+}
+
+float Pipeline::compute_radius(const Patch& p) const {   // expand.cpp:182-198 with COptim::computeUnits (optim.cpp:446-471)
+  std::vector<float> units;
+  for (int im : p.images) {
+    float u = get_unit(im, p.coord);
+    const Camera& c = cams_[im];
+    float ray[4] = {c.centre[0] - p.coord[0], c.centre[1] - p.coord[1], c.centre[2] - p.coord[2], c.centre[3] - p.coord[3]};
+    unitize4(ray);
+    const float d = dot4(ray, p.normal);
+    u = 0.0f < d ? u / d : (float)(INT32_MAX / 2);
+    units.push_back(u);
+  }
+  if (units.size() < 2) return units.empty() ? 0.0f : units[0] * opt_.csize;
+  std::nth_element(units.begin(), units.begin() + 1, units.end());
+  return units[1] * opt_.csize;
+}
+
+void Pipeline::find_neighbors(const Patch& p, std::vector<int>& out, float scale, int margin, bool skipvis) const {   // patchOrganizerS.cpp:528-651
+  out.clear();
+  const float radius = 1.5f * margin * compute_radius(p);
+  float unit = 0.0f;
+  for (int im : p.images) unit += get_unit(im, p.coord);
+  unit /= (int)p.images.size();
+  unit *= opt_.csize;
+  auto scan = [&](int image, int ix, int iy) {
+    const ImageGrid& g = grids_[image];
+    for (int j = -margin; j <= margin; ++j) {
+      const int y = iy + j;
+      if (y < 0 || g.gh <= y) continue;
+      for (int i = -margin; i <= margin; ++i) {
+        const int x = ix + i;
+        if (x < 0 || g.gw <= x) continue;
+        const size_t cell = (size_t)y * g.gw + x;
+        for (int q : g.pg[cell])
+          if (is_neighbor(p, patches_[q], unit, neighbor_threshold_ * scale, radius)) out.push_back(q);
+        for (int q : g.vpg[cell])
+          if (is_neighbor(p, patches_[q], unit, neighbor_threshold_ * scale, radius)) out.push_back(q);
+      }
+    }
+  };
+  for (size_t i = 0; i < p.images.size(); ++i)
+    if (p.images[i] < tnum_) scan(p.images[i], p.grids[i][0], p.grids[i][1]);
+  if (!skipvis)
+    for (size_t i = 0; i < p.vimages.size(); ++i) scan(p.vimages[i], p.vgrids[i][0], p.vgrids[i][1]);
+  std::sort(out.begin(), out.end());
+  out.erase(std::unique(out.begin(), out.end()), out.end());
+}
+
+// CFilter::filterQuad (filter.cpp:394-462): fit z = a x^2 + b y^2 + c xy + d x + e y over the neighbours in the
+// patch's tangent frame (least squares in double, as Cmylapack::lls does through Eigen), residual in units.
+bool Pipeline::filter_quad(const Patch& p, const std::vector<int>& nb) const {
+  float xd[4], yd[4];
+  ortho(p.normal, xd, yd);
+  const int n = (int)nb.size();
+  float hsum = 0.0f;
+  for (int q : nb) {
+    float d[4];
+    for (int k = 0; k < 4; ++k) d[k] = patches_[q].coord[k] - p.coord[k];
+    hsum += norm4(d);
+  }
+  const float h = hsum / n;
+  std::vector<float> fx(n), fy(n), fz(n);
+  double ATA[5][5] = {{0}}, ATb[5] = {0};
+  for (int i = 0; i < n; ++i) {
+    float d[4];
+    for (int k = 0; k < 4; ++k) d[k] = patches_[nb[i]].coord[k] - p.coord[k];
+    fx[i] = dot4(d, xd) / h; fy[i] = dot4(d, yd) / h; fz[i] = dot4(d, p.normal);
+    const double row[5] = {(double)(fx[i] * fx[i]), (double)(fy[i] * fy[i]), (double)(fx[i] * fy[i]), (double)fx[i], (double)fy[i]};
+    for (int a = 0; a < 5; ++a) {
+      for (int b = 0; b < 5; ++b) ATA[a][b] += row[a] * row[b];
+      ATb[a] += row[a] * (double)fz[i];
+    }
+  }
+  // Gaussian elimination with partial pivoting on the 5x5 normal equations
+  double M[5][6];
+  for (int a = 0; a < 5; ++a) { for (int b = 0; b < 5; ++b) M[a][b] = ATA[a][b]; M[a][5] = ATb[a]; }
+  double x[5] = {0, 0, 0, 0, 0};
+  bool singular = false;
+  for (int c = 0; c < 5 && !singular; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 5; ++r) if (std::fabs(M[r][c]) > std::fabs(M[piv][c])) piv = r;
+    if (std::fabs(M[piv][c]) < 1e-300) { singular = true; break; }
+    if (piv != c) for (int k = 0; k < 6; ++k) std::swap(M[c][k], M[piv][k]);
+    for (int r = c + 1; r < 5; ++r) {
+      const double f = M[r][c] / M[c][c];
+      for (int k = c; k < 6; ++k) M[r][k] -= f * M[c][k];
+    }
+  }
+  if (!singular)
+    for (int r = 4; r >= 0; --r) {
+      double s = M[r][5];
+      for (int k = r + 1; k < 5; ++k) s -= M[r][k] * x[k];
+      x[r] = s / M[r][r];
+    }
+  const float xs[5] = {(float)x[0], (float)x[1], (float)x[2], (float)x[3], (float)x[4]};
+  const int inum = std::min(tau_, (int)p.images.size());
+  float unit = 0.0f;
+  for (int i = 0; i < inum; ++i) unit += get_unit(p.images[i], p.coord);
+  unit /= inum;
+  float residual = 0.0f;
+  for (int i = 0; i < n; ++i) {
+    const float res = xs[0] * (fx[i] * fx[i]) + xs[1] * (fy[i] * fy[i]) + xs[2] * (fx[i] * fy[i]) + xs[3] * fx[i] + xs[4] * fy[i] - fz[i];
+    residual += std::fabs(res) / unit;
+  }
+  residual /= (n - 5);
+  return !(residual < opt_.quad);
+}
+
+float Pipeline::compute_gain(const Patch& p) const {   // filter.cpp:88-146 (host copy for COptim::check, optim.cpp:363-383)
+  float gain = std::max(0.0f, p.ncc - ncc_threshold_) * p.timages;
+  for (size_t i = 0; i < p.images.size(); ++i) {
+    const int index = p.images[i];
+    if (tnum_ <= index) continue;
+    const ImageGrid& g = grids_[index];
+    float maxp = 0.0f;
+    for (int q : g.pg[(size_t)p.grids[i][1] * g.gw + p.grids[i][0]])
+      if (!is_neighbor(p, patches_[q], neighbor_threshold1_)) maxp = std::max(maxp, patches_[q].ncc - ncc_threshold_);
+    gain -= maxp;
+  }
+  for (size_t i = 0; i < p.vimages.size(); ++i) {
+    const int index = p.vimages[i];
+    if (tnum_ <= index) continue;
+    const ImageGrid& g = grids_[index];
+    const float pdepth = dot4(cams_[index].oaxis, p.coord);
+    float maxp = 0.0f;
+    for (int q : g.pg[(size_t)p.vgrids[i][1] * g.gw + p.vgrids[i][0]]) {
+      const float bdepth = dot4(cams_[index].oaxis, patches_[q].coord);
+      if (pdepth < bdepth && !is_neighbor(p, patches_[q], neighbor_threshold1_)) maxp = std::max(maxp, patches_[q].ncc - ncc_threshold_);
+    }
+    gain -= maxp;
+  }
+  return gain;
+}
+
+// ---------------------------------------------------------------------------------------------- bookkeeping
+int Pipeline::add_patch(const Patch& p) {   // patchOrganizerS.cpp:312-349
+  const int id = (int)patches_.size();
+  patches_.push_back(p);
+  patches_.back().alive = true;
+  for (size_t i = 0; i < p.images.size(); ++i) {
+    const int im = p.images[i];
+    if (tnum_ <= im) continue;
+    grids_[im].pg[(size_t)p.grids[i][1] * grids_[im].gw + p.grids[i][0]].push_back(id);
+  }
+  if (depth_ != 0)
+    for (size_t i = 0; i < p.vimages.size(); ++i) {
+      const int im = p.vimages[i];
+      grids_[im].vpg[(size_t)p.vgrids[i][1] * grids_[im].gw + p.vgrids[i][0]].push_back(id);
+    }
+  return id;
+}
+
+void Pipeline::remove_patch(int id) {   // patchOrganizerS.cpp:452-477
+  Patch& p = patches_[id];
+  auto drop = [&](std::vector<int>& v) { v.erase(std::remove(v.begin(), v.end(), id), v.end()); };
+  for (size_t i = 0; i < p.images.size(); ++i) {
+    const int im = p.images[i];
+    if (tnum_ <= im) continue;
+    drop(grids_[im].pg[(size_t)p.grids[i][1] * grids_[im].gw + p.grids[i][0]]);
+  }
+  for (size_t i = 0; i < p.vimages.size(); ++i) {
+    const int im = p.vimages[i];
+    drop(grids_[im].vpg[(size_t)p.vgrids[i][1] * grids_[im].gw + p.vgrids[i][0]]);
+  }
+  p.alive = false;
+}
+
+std::vector<int> Pipeline::collect_patches() const {   // patchOrganizerS.cpp:207-236: first appearance in (image, cell) order
+  std::vector<int> ids;
+  std::vector<char> seen(patches_.size(), 0);
+  for (int im = 0; im < tnum_; ++im)
+    for (const auto& cell : grids_[im].pg)
+      for (int q : cell)
+        if (!seen[q]) { seen[q] = 1; ids.push_back(q); }
+  return ids;
+}
+
+void Pipeline::upload_table(const std::vector<int>& ids) {
+  table_ids_ = ids;
+  const int P = (int)ids.size();
+  std::vector<float> coords((size_t)4 * P), normals((size_t)4 * P), ncc(P), dsc(P);
+  std::vector<int32_t> ioff(P + 1, 0), voff(P + 1, 0), images, grids, vimages, vgrids, timages(P);
+  for (int k = 0; k < P; ++k) {
+    const Patch& p = patches_[ids[k]];
+    for (int c = 0; c < 4; ++c) { coords[4 * k + c] = p.coord[c]; normals[4 * k + c] = p.normal[c]; }
+    ncc[k] = p.ncc; dsc[k] = p.dscale; timages[k] = p.timages;
+    for (size_t i = 0; i < p.images.size(); ++i) { images.push_back(p.images[i]); grids.push_back(p.grids[i][0]); grids.push_back(p.grids[i][1]); }
+    for (size_t i = 0; i < p.vimages.size(); ++i) { vimages.push_back(p.vimages[i]); vgrids.push_back(p.vgrids[i][0]); vgrids.push_back(p.vgrids[i][1]); }
+    ioff[k + 1] = (int32_t)images.size(); voff[k + 1] = (int32_t)vimages.size();
+  }
+  if (images.empty()) { images.push_back(0); grids.push_back(0); grids.push_back(0); }
+  if (vimages.empty()) { vimages.push_back(0); vgrids.push_back(0); vgrids.push_back(0); }
+  if (pmvsb_set_thresholds(gpu_, ncc_threshold_, ncc_threshold_before_)) die("set_thresholds");
+  if (pmvsb_set_depth(gpu_, depth_)) die("set_depth");
+  if (pmvsb_store_upload(gpu_, P, coords.data(), normals.data(), ncc.data(), dsc.data(), ioff.data(), images.data(), grids.data(), voff.data(),
+                         vimages.data(), vgrids.data(), timages.data())) die("store_upload");
+  if (pmvsb_build_depth_maps(gpu_)) die("build_depth_maps");
+}
+
+// CFilter::setDepthMapsVGridsVPGridsAddPatchV (filter.cpp:734-783)
+void Pipeline::rebuild_depth_and_vis(bool additive) {
+  const std::vector<int> ids = collect_patches();
+  for (int im = 0; im < tnum_; ++im)
+    for (auto& cell : grids_[im].vpg) cell.clear();
+  if (!additive)
+    for (int id : ids) { patches_[id].vimages.clear(); patches_[id].vgrids.clear(); }
+  upload_table(ids);
+  const int P = (int)ids.size();
+  if (P == 0) return;
+  const int vs = tnum_;
+  int stride = 1;
+  for (int id : ids) stride = std::max(stride, (int)patches_[id].images.size());
+  std::vector<float> coords((size_t)4 * P), normals((size_t)4 * P);
+  std::vector<int32_t> images((size_t)stride * P, 0), nimages(P), vim((size_t)vs * P, 0), nv(P, 0), vgr((size_t)2 * vs * P, 0);
+  for (int k = 0; k < P; ++k) {
+    const Patch& p = patches_[ids[k]];
+    for (int c = 0; c < 4; ++c) { coords[4 * k + c] = p.coord[c]; normals[4 * k + c] = p.normal[c]; }
+    nimages[k] = (int)p.images.size();
+    for (size_t i = 0; i < p.images.size(); ++i) images[(size_t)k * stride + i] = p.images[i];
+    nv[k] = (int)p.vimages.size();
+    for (size_t i = 0; i < p.vimages.size(); ++i) { vim[(size_t)k * vs + i] = p.vimages[i]; vgr[((size_t)k * vs + i) * 2] = p.vgrids[i][0]; vgr[((size_t)k * vs + i) * 2 + 1] = p.vgrids[i][1]; }
+  }
+  if (pmvsb_set_vimages_batch(gpu_, P, stride, coords.data(), normals.data(), images.data(), nimages.data(), vs, vim.data(), nv.data(), vgr.data())) die("set_vimages_batch");
+  for (int k = 0; k < P; ++k) {
+    Patch& p = patches_[ids[k]];
+    p.vimages.clear(); p.vgrids.clear();
+    for (int i = 0; i < nv[k]; ++i) {
+      p.vimages.push_back(vim[(size_t)k * vs + i]);
+      p.vgrids.push_back({vgr[((size_t)k * vs + i) * 2], vgr[((size_t)k * vs + i) * 2 + 1]});
+    }
+  }
+  // addPatchV: per image, patches in table order
+  for (int id : ids) {
+    const Patch& p = patches_[id];
+    for (size_t i = 0; i < p.vimages.size(); ++i)
+      grids_[p.vimages[i]].vpg[(size_t)p.vgrids[i][1] * grids_[p.vimages[i]].gw + p.vgrids[i][0]].push_back(id);
+  }
+  // the vimages changed: give the GPU table the new lists (gains read them)
+  upload_table(ids);
+}
+
+// ---------------------------------------------------------------------------------------------- evaluate a wave
+void Pipeline::evaluate(std::vector<Candidate>& cands, std::vector<int>& verdict) {
+  const int P = (int)cands.size();
+  verdict.assign(P, 1);
+  if (P == 0) return;
+  const int stride = std::min(num_, 64);
+  std::vector<float> coords((size_t)4 * P), normals((size_t)4 * P), dsc(P), asc(P), ncc(P, -1.0f), tmp(P);
+  std::vector<int32_t> images((size_t)stride * P, 0), nimages(P), v0(P), evals(P), grids((size_t)2 * stride * P), timages(P), v1(P);
+  std::vector<uint8_t> ok(P);
+  for (int k = 0; k < P; ++k) {
+    const Patch& p = cands[k].patch;
+    for (int c = 0; c < 4; ++c) { coords[4 * k + c] = p.coord[c]; normals[4 * k + c] = p.normal[c]; }
+    nimages[k] = std::min((int)p.images.size(), stride);
+    for (int i = 0; i < nimages[k]; ++i) images[(size_t)k * stride + i] = p.images[i];
+  }
+  if (pmvsb_set_thresholds(gpu_, ncc_threshold_, ncc_threshold_before_)) die("set_thresholds");
+  if (pmvsb_pre_process_batch(gpu_, P, stride, coords.data(), normals.data(), images.data(), nimages.data(), dsc.data(), asc.data(), v0.data())) die("pre_process_batch");
+  // compact the survivors, refine them (tau images each), post-process them
+  std::vector<int> live;
+  for (int k = 0; k < P; ++k) if (v0[k] == 0) live.push_back(k);
+  const int L = (int)live.size();
+  if (L == 0) return;
+  std::vector<float> lc((size_t)4 * L), ln((size_t)4 * L), ld(L), lncc(L), ltmp(L);
+  std::vector<int32_t> li((size_t)stride * L), lni(L), lev(L), lgr((size_t)2 * stride * L), lti(L), lv(L);
+  std::vector<uint8_t> lok(L);
+  for (int j = 0; j < L; ++j) {
+    const int k = live[j];
+    for (int c = 0; c < 4; ++c) { lc[4 * j + c] = coords[4 * k + c]; ln[4 * j + c] = normals[4 * k + c]; }
+    ld[j] = dsc[k]; lni[j] = nimages[k];
+    for (int i = 0; i < stride; ++i) li[(size_t)j * stride + i] = images[(size_t)k * stride + i];
+  }
+  if (pmvsb_refine_batch(gpu_, L, stride, lc.data(), ln.data(), li.data(), lni.data(), ld.data(), lncc.data(), lev.data(), lok.data())) die("refine_batch");
+  // a failed optimiser leaves the patch untouched and the reference still runs postProcess on it (optim.cpp:496-502)
+  if (pmvsb_post_process_batch(gpu_, L, stride, lc.data(), ln.data(), lncc.data(), li.data(), lni.data(), lgr.data(), lti.data(), ltmp.data(), lv.data())) die("post_process_batch");
+  for (int j = 0; j < L; ++j) {
+    const int k = live[j];
+    Patch& p = cands[k].patch;
+    if (lv[j] != 0) { verdict[k] = 2; continue; }
+    verdict[k] = 0;
+    for (int c = 0; c < 4; ++c) { p.coord[c] = lc[4 * j + c]; p.normal[c] = ln[4 * j + c]; }
+    p.ncc = lok[j] ? lncc[j] : p.ncc;
+    p.dscale = ld[j]; p.ascale = asc[k];
+    p.timages = lti[j]; p.tmp = ltmp[j];
+    p.images.assign(li.begin() + (size_t)j * stride, li.begin() + (size_t)j * stride + lni[j]);
+    p.grids.clear();
+    for (int i = 0; i < lni[j]; ++i) p.grids.push_back({lgr[((size_t)j * stride + i) * 2], lgr[((size_t)j * stride + i) * 2 + 1]});
+    p.vimages.clear(); p.vgrids.clear();
+  }
+  if (depth_ == 0) return;
+  // setVImagesVGrids for the accepted candidates (optim.cpp:184-186) against the current depth maps
+  std::vector<int> acc;
+  for (int k = 0; k < P; ++k) if (verdict[k] == 0) acc.push_back(k);
+  const int A = (int)acc.size();
+  if (A == 0) return;
+  const int vs = tnum_;
+  std::vector<float> ac((size_t)4 * A), an((size_t)4 * A);
+  std::vector<int32_t> ai((size_t)stride * A, 0), ani(A), avim((size_t)vs * A, 0), anv(A, 0), avgr((size_t)2 * vs * A, 0);
+  for (int j = 0; j < A; ++j) {
+    const Patch& p = cands[acc[j]].patch;
+    for (int c = 0; c < 4; ++c) { ac[4 * j + c] = p.coord[c]; an[4 * j + c] = p.normal[c]; }
+    ani[j] = (int)p.images.size();
+    for (size_t i = 0; i < p.images.size(); ++i) ai[(size_t)j * stride + i] = p.images[i];
+  }
+  if (pmvsb_set_vimages_batch(gpu_, A, stride, ac.data(), an.data(), ai.data(), ani.data(), vs, avim.data(), anv.data(), avgr.data())) die("set_vimages_batch");
+  for (int j = 0; j < A; ++j) {
+    Patch& p = cands[acc[j]].patch;
+    for (int i = 0; i < anv[j]; ++i) {
+      p.vimages.push_back(avim[(size_t)j * vs + i]);
+      p.vgrids.push_back({avgr[((size_t)j * vs + i) * 2], avgr[((size_t)j * vs + i) * 2 + 1]});
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- seed round
+namespace {
+// fundamental matrix between two 3x4 projections (rows as double[4]); F[a][b] = det of the two rows of P0 other than a
+// stacked on the two rows of P1 other than b (include/image/camera.hpp:129-151)
+double det4(const double* a, const double* b, const double* c, const double* d) {
+  const double m[4][4] = {{a[0], a[1], a[2], a[3]}, {b[0], b[1], b[2], b[3]}, {c[0], c[1], c[2], c[3]}, {d[0], d[1], d[2], d[3]}};
+  double det = 0.0;
+  for (int j = 0; j < 4; ++j) {
+    double sub[3][3];
+    for (int r = 1; r < 4; ++r) { int cc = 0; for (int k = 0; k < 4; ++k) if (k != j) sub[r - 1][cc++] = m[r][k]; }
+    const double d3 = sub[0][0] * (sub[1][1] * sub[2][2] - sub[1][2] * sub[2][1]) - sub[0][1] * (sub[1][0] * sub[2][2] - sub[1][2] * sub[2][0]) +
+                      sub[0][2] * (sub[1][0] * sub[2][1] - sub[1][1] * sub[2][0]);
+    det += ((j % 2) ? -1.0 : 1.0) * m[0][j] * d3;
+  }
+  return det;
+}
+void fundamental(const std::vector<double>& P0, const std::vector<double>& P1, double F[3][3]) {
+  const double* p0[3] = {&P0[0], &P0[4], &P0[8]};
+  const double* p1[3] = {&P1[0], &P1[4], &P1[8]};
+  const int o[3][2] = {{1, 2}, {2, 0}, {0, 1}};
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) F[a][b] = det4(p0[o[a][0]], p0[o[a][1]], p1[o[b][0]], p1[o[b][1]]);
+}
+}  // namespace
+
+void Pipeline::seed_round() {
+  Stats st;
+  std::vector<int> order(tnum_);
+  std::iota(order.begin(), order.end(), 0);
+  std::mt19937 gen(42);   // seed.cpp:38
+  std::shuffle(order.begin(), order.end(), gen);
+  std::cerr << "adding seeds " << std::endl;
+  for (auto& g : grids_) std::fill(g.counts.begin(), g.counts.end(), 0);
+  for (int im = 0; im < tnum_; ++im)
+    for (size_t c = 0; c < grids_[im].pg.size(); ++c)
+      if (!grids_[im].pg[c].empty()) grids_[im].counts[c] = (unsigned char)count_threshold2_;
+  // features binned by cell (seed.cpp:25-36)
+  std::vector<std::vector<std::vector<int>>> bins(num_);
+  for (int i = 0; i < num_; ++i) {
+    bins[i].assign((size_t)grids_[i].gw * grids_[i].gh, {});
+    for (int f = 0; f < (int)features_[i].size(); ++f) {
+      const int ix = ((int)std::floor(features_[i][f].x + 0.5f)) / opt_.csize, iy = ((int)std::floor(features_[i][f].y + 0.5f)) / opt_.csize;
+      if (ix >= 0 && ix < grids_[i].gw && iy >= 0 && iy < grids_[i].gh) bins[i][(size_t)iy * grids_[i].gw + ix].push_back(f);
+    }
+  }
+  auto can_add = [&](int image, int x, int y) {   // seed.cpp:325-338
+    if (tnum_ <= image) return true;
+    const size_t c = (size_t)y * grids_[image].gw + x;
+    if (!grids_[image].pg[c].empty()) return false;
+    return !(count_threshold2_ <= grids_[image].counts[c]);
+  };
+  const double cos_a0 = std::cos(60.0f * M_PI / 180.0f);
+  for (int index : order) {
+    // COptim::collectImages (optim.cpp:66-93)
+    std::vector<std::pair<float, int>> cand_im;
+    for (int j : opt_.visdata2[index]) {
+      if (opt_.sequence != -1 && opt_.sequence < std::abs(index - j)) continue;
+      const float d = cams_[index].oaxis[0] * cams_[j].oaxis[0] + cams_[index].oaxis[1] * cams_[j].oaxis[1] + cams_[index].oaxis[2] * cams_[j].oaxis[2];
+      if (d < cos_a0) continue;
+      cand_im.push_back({distances_[index][j], j});
+    }
+    std::sort(cand_im.begin(), cand_im.end());
+    std::vector<int> indexes;
+    for (int i = 0; i < std::min(tau_, (int)cand_im.size()); ++i) indexes.push_back(cand_im[i].second);
+    if (indexes.empty()) continue;
+    std::vector<std::array<double, 9>> Fs(indexes.size());
+    for (size_t k = 0; k < indexes.size(); ++k) {
+      double F[3][3];
+      fundamental(P0_[index], P0_[indexes[k]], F);
+      for (int a = 0; a < 9; ++a) Fs[k][a] = F[a / 3][a % 3];
+    }
+    // ---- enumerate the wave: every (cell, feature, candidate) of this image from the current snapshot
+    std::vector<Candidate> wave;
+    const ImageGrid& g = grids_[index];
+    for (int y = 0; y < g.gh; ++y)
+      for (int x = 0; x < g.gw; ++x) {
+        const int cell = y * g.gw + x;
+        if (bins[index][cell].empty() || !can_add(index, x, y)) continue;
+        for (int fi = 0; fi < (int)bins[index][cell].size(); ++fi) {
+          const Feature& p0 = features_[index][bins[index][cell][fi]];
+          struct Hit { float resp; int image, feat; float coord[4]; };
+          std::vector<Hit> hits;
+          for (size_t k = 0; k < indexes.size(); ++k) {
+            const int other = indexes[k];
+            const double* F = Fs[k].data();
+            // epipolar line of p0 in `other`: transpose(F) * p0 (seed.cpp:207-268)
+            const double line[3] = {F[0] * p0.x + F[3] * p0.y + F[6], F[1] * p0.x + F[4] * p0.y + F[7], F[2] * p0.x + F[5] * p0.y + F[8]};
+            if (line[0] == 0.0 && line[1] == 0.0) continue;
+            const ImageGrid& og = grids_[other];
+            std::vector<std::array<int, 2>> cells;
+            if (std::fabs(line[0]) > std::fabs(line[1])) {
+              for (int cy = 0; cy < og.gh; ++cy) {
+                const float fy = (float)((cy + 0.5) * opt_.csize - 0.5f);
+                float fx = (float)((-line[1] * fy - line[2]) / line[0]);
+                fx = std::max(-2147483648.0f, std::min(2147483648.0f, fx));
+                const int ix = ((int)std::floor(fx + 0.5f)) / opt_.csize;
+                for (int d : {0, -1, 1}) if (0 <= ix + d && ix + d < og.gw) cells.push_back({ix + d, cy});
+              }
+            } else {
+              for (int cx = 0; cx < og.gw; ++cx) {
+                const float fx = (float)((cx + 0.5) * opt_.csize - 0.5f);
+                float fy = (float)((-line[0] * fx - line[2]) / line[1]);
+                fy = std::max(-2147483648.0f, std::min(2147483648.0f, fy));
+                const int iy = ((int)std::floor(fy + 0.5f)) / opt_.csize;
+                for (int d : {0, -1, 1}) if (0 <= iy + d && iy + d < og.gh) cells.push_back({cx, iy + d});
+              }
+            }
+            for (const auto& c : cells) {
+              if (!can_add(other, c[0], c[1])) continue;
+              for (int f1 : bins[other][(size_t)c[1] * og.gw + c[0]]) {
+                const Feature& p1 = features_[other][f1];
+                if (p1.type != p0.type) continue;
+                // distance of p0 to the epipolar line of p1 (computeEPD, camera.hpp:118-127)
+                double l[3] = {F[0] * p1.x + F[1] * p1.y + F[2], F[3] * p1.x + F[4] * p1.y + F[5], F[6] * p1.x + F[7] * p1.y + F[8]};
+                const double nn = std::sqrt(l[0] * l[0] + l[1] * l[1]);
+                float epd = 0.0f;
+                if (nn != 0.0) epd = (float)std::fabs((l[0] * p0.x + l[1] * p0.y + l[2]) / nn);
+                if (2.0f <= epd) continue;   // _epThreshold (findMatch.cpp:106)
+                // triangulate (seed.cpp:340-384): normal equations of the 4 x 3 system in double
+                const std::vector<double>& Pa = P0_[index];
+                const std::vector<double>& Pb = P0_[other];
+                double A[4][3], b[4];
+                for (int c3 = 0; c3 < 3; ++c3) {
+                  A[0][c3] = Pa[c3] - p0.x * Pa[8 + c3]; A[1][c3] = Pa[4 + c3] - p0.y * Pa[8 + c3];
+                  A[2][c3] = Pb[c3] - p1.x * Pb[8 + c3]; A[3][c3] = Pb[4 + c3] - p1.y * Pb[8 + c3];
+                }
+                b[0] = p0.x * Pa[11] - Pa[3]; b[1] = p0.y * Pa[11] - Pa[7];
+                b[2] = p1.x * Pb[11] - Pb[3]; b[3] = p1.y * Pb[11] - Pb[7];
+                double M[3][3] = {{0}}, v[3] = {0, 0, 0};
+                for (int r = 0; r < 4; ++r)
+                  for (int i3 = 0; i3 < 3; ++i3) { v[i3] += A[r][i3] * b[r]; for (int j3 = 0; j3 < 3; ++j3) M[i3][j3] += A[r][i3] * A[r][j3]; }
+                const double det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+                                   M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+                if (det == 0.0) continue;
+                double inv[3][3];
+                inv[0][0] = (M[1][1] * M[2][2] - M[1][2] * M[2][1]) / det; inv[0][1] = (M[0][2] * M[2][1] - M[0][1] * M[2][2]) / det; inv[0][2] = (M[0][1] * M[1][2] - M[0][2] * M[1][1]) / det;
+                inv[1][0] = (M[1][2] * M[2][0] - M[1][0] * M[2][2]) / det; inv[1][1] = (M[0][0] * M[2][2] - M[0][2] * M[2][0]) / det; inv[1][2] = (M[0][2] * M[1][0] - M[0][0] * M[1][2]) / det;
+                inv[2][0] = (M[1][0] * M[2][1] - M[1][1] * M[2][0]) / det; inv[2][1] = (M[0][1] * M[2][0] - M[0][0] * M[2][1]) / det; inv[2][2] = (M[0][0] * M[1][1] - M[0][1] * M[1][0]) / det;
+                Hit h;
+                for (int i3 = 0; i3 < 3; ++i3) h.coord[i3] = (float)(inv[i3][0] * v[0] + inv[i3][1] * v[1] + inv[i3][2] * v[2]);
+                h.coord[3] = 1.0f;
+                if (dot4(cams_[index].P[2], h.coord) <= 0.0f) continue;
+                float d0[4], d1[4];
+                for (int c4 = 0; c4 < 4; ++c4) { d0[c4] = h.coord[c4] - cams_[index].centre[c4]; d1[c4] = h.coord[c4] - cams_[other].centre[c4]; }
+                h.resp = std::fabs(norm4(d0) - norm4(d1));
+                h.image = other; h.feat = f1;
+                hits.push_back(h);
+              }
+            }
+          }
+          std::stable_sort(hits.begin(), hits.end(), [](const Hit& a, const Hit& b) { return a.resp < b.resp; });
+          int ord = 0;
+          for (const Hit& h : hits) {
+            Candidate c;
+            for (int k4 = 0; k4 < 4; ++k4) { c.patch.coord[k4] = h.coord[k4]; c.patch.normal[k4] = cams_[index].centre[k4] - h.coord[k4]; }
+            unitize4(c.patch.normal);
+            c.patch.normal[3] = 0.0f;
+            c.patch.images = {index, h.image};
+            c.cell = cell; c.feature = fi; c.order = ord++;
+            c.parent = h.image;   // other image (for the counters)
+            const Feature& p1 = features_[h.image][h.feat];
+            c.dir = (((int)std::floor(p1.y + 0.5f)) / opt_.csize) * grids_[h.image].gw + ((int)std::floor(p1.x + 0.5f)) / opt_.csize;
+            wave.push_back(c);
+          }
+        }
+      }
+    std::vector<int> verdict;
+    evaluate(wave, verdict);
+    // ---- commit: replay the reference's sequential rule per cell (seed.cpp:151-199)
+    int total = 0;
+    size_t k = 0;
+    while (k < wave.size()) {
+      const int cell = wave[k].cell;
+      size_t cell_end = k;
+      while (cell_end < wave.size() && wave[cell_end].cell == cell) ++cell_end;
+      bool placed = false;
+      size_t f0 = k;
+      while (f0 < cell_end && !placed) {
+        size_t f1 = f0;
+        while (f1 < cell_end && wave[f1].feature == wave[f0].feature) ++f1;
+        int count = 0;
+        const Patch* best = nullptr;
+        float best_score = 0.0f;
+        for (size_t c = f0; c < f1; ++c) {
+          // trial counters of both cells (seed.cpp:175-181)
+          if (grids_[index].counts[cell] < 255) ++grids_[index].counts[cell];
+          if (wave[c].parent < tnum_ && grids_[wave[c].parent].counts[wave[c].dir] < 255) ++grids_[wave[c].parent].counts[wave[c].dir];
+          ++st.trial;
+          if (verdict[c] == 1) { ++st.fail0; continue; }
+          if (verdict[c] == 2) { ++st.fail1; continue; }
+          ++st.pass;
+          ++count;
+          const Patch& p = wave[c].patch;
+          const float score = std::max(0.0f, p.ncc - ncc_threshold_) * (int)p.images.size();   // CPatch::score
+          if (!best || best_score < score) { best = &p; best_score = score; }
+          if (count_threshold0_ <= count) break;
+        }
+        if (count != 0 && best) {
+          add_patch(*best);
+          ++total;
+          placed = true;
+        }
+        f0 = f1;
+      }
+      k = cell_end;
+    }
+    std::cerr << '(' << index << ',' << total << ')' << std::flush;
+  }
+  std::cerr << "done" << std::endl;
+  std::cerr << "Total pass fail0 fail1 refinepatch: " << st.trial << ' ' << st.pass << ' ' << st.fail0 << ' ' << st.fail1 << ' ' << st.pass + st.fail1 << std::endl;
+}
+
+// ---------------------------------------------------------------------------------------------- expansion
+bool Pipeline::check_counts(const Patch& p) const {   // expand.cpp:258-323; true = reject
+  int full = 0, empty = 0;
+  for (size_t i = 0; i < p.images.size(); ++i) {
+    const int im = p.images[i];
+    if (tnum_ <= im) continue;
+    const ImageGrid& g = grids_[im];
+    const int ix = p.grids[i][0], iy = p.grids[i][1];
+    if (ix < 0 || g.gw <= ix || iy < 0 || g.gh <= iy) continue;
+    const size_t c = (size_t)iy * g.gw + ix;
+    if (!g.pg[c].empty()) { ++full; continue; }
+    if (count_threshold1_ <= g.counts[c]) ++full; else ++empty;
+  }
+  if (depth_ <= 1) return empty < opt_.minImageNum && full != 0;
+  return empty < opt_.minImageNum - 1 && full != 0;
+}
+
+bool Pipeline::update_counts(const Patch& p) {   // expand.cpp:325-406; true = the new patch joins the queue
+  int empty = 0;
+  auto visit = [&](int im, int ix, int iy) {
+    ImageGrid& g = grids_[im];
+    if (ix < 0 || g.gw <= ix || iy < 0 || g.gh <= iy) return;
+    const size_t c = (size_t)iy * g.gw + ix;
+    if (!(count_threshold1_ <= g.counts[c])) ++empty;
+    ++g.counts[c];   // unsigned char, wraps like the reference's
+  };
+  for (size_t i = 0; i < p.images.size(); ++i)
+    if (p.images[i] < tnum_) visit(p.images[i], p.grids[i][0], p.grids[i][1]);
+  for (size_t i = 0; i < p.vimages.size(); ++i) visit(p.vimages[i], p.vgrids[i][0], p.vgrids[i][1]);
+  return empty != 0;
+}
+
+void Pipeline::expand_round() {
+  Stats st;
+  for (auto& g : grids_) std::fill(g.counts.begin(), g.counts.end(), 0);
+  for (Patch& p : patches_) p.flag = 0;
+  // the queue is ordered by _tmp (patchOrganizerS.hpp:10-15); a wave takes the whole frontier, best first
+  std::vector<int> frontier = collect_patches();
+  for (int id : frontier) patches_[id].flag = 1;
+  std::cerr << "Expanding patches..." << std::flush;
+  const double two_pi = 2 * M_PI;
+  int wave_no = 0;
+  while (!frontier.empty()) {
+    std::stable_sort(frontier.begin(), frontier.end(), [&](int a, int b) { return patches_[a].tmp > patches_[b].tmp; });
+    if (depth_ != 0) upload_table(collect_patches());   // depth maps for setVImagesVGrids of the candidates
+    std::vector<Candidate> wave;
+    for (int id : frontier) {
+      const Patch& pp = patches_[id];
+      if (!pp.alive) continue;
+      // findEmptyBlocks (expand.cpp:108-180)
+      float xdir[4], ydir[4];
+      ortho(pp.normal, xdir, ydir);
+      const int dnum = 6;
+      float fill[6] = {0, 0, 0, 0, 0, 0};
+      const float radius = compute_radius(pp);
+      const float rlow = radius / 6.0f, rhigh = radius * 2.5f;
+      std::vector<int> nb;
+      find_neighbors(pp, nb, 4.0f, 1, false);
+      for (int q : nb) {
+        float diff[4];
+        for (int k = 0; k < 4; ++k) diff[k] = patches_[q].coord[k] - pp.coord[k];
+        float f2[2] = {dot4(diff, xdir), dot4(diff, ydir)};
+        const float len = std::sqrt(f2[0] * f2[0] + f2[1] * f2[1]);
+        if (len < rlow || rhigh < len) continue;
+        f2[0] /= len; f2[1] /= len;
+        float angle = std::atan2(f2[1], f2[0]);
+        if (angle < 0.0) angle += (float)two_pi;
+        const float findex = (float)(angle / (two_pi / dnum));
+        const int lindex = (int)std::floor(findex), hindex = lindex + 1;
+        fill[lindex % dnum] += hindex - findex;
+        fill[hindex % dnum] += findex - lindex;
+      }
+      for (int i = 0; i < dnum; ++i) {
+        if (0.0f < fill[i]) continue;
+        if (pp.dflag & (1 << i)) continue;
+        const float angle = (float)(two_pi * i / dnum);
+        Candidate c;
+        const float cs = (float)(std::cos(angle) * radius), sn = (float)(std::sin(angle) * radius);
+        for (int k = 0; k < 4; ++k) { c.patch.coord[k] = pp.coord[k] + cs * xdir[k] + sn * ydir[k]; c.patch.normal[k] = pp.normal[k]; }
+        c.patch.flag = 1;
+        c.parent = id; c.dir = i;
+        // setGridsImages (patchOrganizerS.cpp:383-398): parent's images that see the candidate inside their grid
+        for (int im : pp.images) {
+          float ic[3];
+          project(im, c.patch.coord, ic);
+          const int ix = ((int)std::floor(ic[0] + 0.5f)) / opt_.csize, iy = ((int)std::floor(ic[1] + 0.5f)) / opt_.csize;
+          if (0 <= ix && ix < grids_[im].gw && 0 <= iy && iy < grids_[im].gh) { c.patch.images.push_back(im); c.patch.grids.push_back({ix, iy}); }
+        }
+        if (c.patch.images.empty()) { patches_[id].dflag |= (unsigned char)(1 << i); continue; }
+        if (check_counts(c.patch)) { patches_[id].dflag |= (unsigned char)(1 << i); continue; }
+        wave.push_back(c);
+      }
+    }
+    std::vector<int> verdict;
+    evaluate(wave, verdict);
+    // commit in parent-priority order; cells may have been taken by an earlier commit of this wave
+    std::vector<int> next;
+    for (size_t k = 0; k < wave.size(); ++k) {
+      Candidate& c = wave[k];
+      ++st.trial;
+      bool fail = false;
+      if (verdict[k] == 1) { ++st.fail0; fail = true; }
+      else if (verdict[k] == 2) { ++st.fail1; fail = true; }
+      else {
+        Patch& p = c.patch;
+        // the cell rules are re-checked against the grids as they are NOW (what a sequential run would have seen)
+        Patch probe = p;
+        if (check_counts(probe)) { ++st.fail0; fail = true; }
+        if (!fail && depth_ >= 2) {   // COptim::check (optim.cpp:363-383)
+          const float gain = compute_gain(p);
+          p.tmp = gain;
+          if (gain < 0.0f) fail = true;
+          if (!fail) {
+            std::vector<int> nb;
+            find_neighbors(p, nb, 4.0f, 2, false);
+            if (6 < (int)nb.size() && filter_quad(p, nb)) fail = true;
+          }
+          if (fail) ++st.fail1;
+        }
+        if (!fail) {
+          ++st.pass;
+          const bool requeue = update_counts(p);
+          p.flag = 1;
+          const int nid = add_patch(p);
+          if (requeue) next.push_back(nid);
+        }
+      }
+      if (fail) patches_[c.parent].dflag |= (unsigned char)(1 << c.dir);
+    }
+    frontier.swap(next);
+    ++wave_no;
+    std::cerr << '[' << wave_no << ':' << wave.size() << "->" << frontier.size() << ']' << std::flush;
+  }
+  std::cerr << std::endl << "Total pass fail0 fail1 refinepatch: " << st.trial << ' ' << st.pass << ' ' << st.fail0 << ' ' << st.fail1 << ' ' << st.pass + st.fail1 << std::endl;
+}
+
+// ---------------------------------------------------------------------------------------------- filters
+void Pipeline::filter_outside() {   // filter.cpp:29-86
+  std::cerr << "FilterOutside" << std::endl;
+  const std::vector<int> ids = table_ids_;   // table uploaded by the preceding rebuild
+  const int P = (int)ids.size();
+  if (P == 0) return;
+  std::vector<float> gains(P);
+  if (pmvsb_compute_gains_store(gpu_, gains.data())) die("compute_gains_store");
+  int count = 0;
+  double ave = 0.0, ave2 = 0.0;
+  for (int k = 0; k < P; ++k) {
+    ave += gains[k]; ave2 += (double)gains[k] * gains[k];
+    if (gains[k] < 0.0f) { remove_patch(ids[k]); ++count; }
+  }
+  ave /= P; ave2 /= P;
+  std::cerr << "Gain (ave/var): " << ave << ' ' << std::sqrt(std::max(0.0, ave2 - ave * ave)) << std::endl;
+  std::cerr << P << " -> " << P - count << " (" << 100.0f * (P - count) / P << "%)" << std::endl;
+}
+
+void Pipeline::filter_exact() {   // filter.cpp:203-355
+  std::cerr << "Filter Exact: " << std::flush;
+  const std::vector<int> ids = table_ids_;
+  const int P = (int)ids.size();
+  if (P == 0) return;
+  size_t E = 0;
+  for (int id : ids) E += patches_[id].images.size();
+  std::vector<uint8_t> safe(std::max<size_t>(E, 1));
+  if (pmvsb_filter_exact_store(gpu_, safe.data())) die("filter_exact_store");
+  // per patch: surviving target images in ascending image order (the reference visits image by image), then the
+  // non-target images in their old order
+  struct Entry { int image, gx, gy; };
+  const int stride = std::min(num_, 64);
+  std::vector<float> coords, normals;
+  std::vector<int32_t> images, nimages;
+  std::vector<int> todo;
+  size_t e = 0;
+  int count = 0;
+  for (int k = 0; k < P; ++k) {
+    Patch& p = patches_[ids[k]];
+    std::vector<Entry> keep, other;
+    for (size_t i = 0; i < p.images.size(); ++i, ++e) {
+      const int im = p.images[i];
+      if (tnum_ <= im) { other.push_back({im, p.grids[i][0], p.grids[i][1]}); continue; }
+      if (safe[e]) keep.push_back({im, p.grids[i][0], p.grids[i][1]});
+      else {
+        auto& cell = grids_[im].pg[(size_t)p.grids[i][1] * grids_[im].gw + p.grids[i][0]];
+        cell.erase(std::remove(cell.begin(), cell.end(), ids[k]), cell.end());
+      }
+    }
+    std::stable_sort(keep.begin(), keep.end(), [](const Entry& a, const Entry& b) { return a.image < b.image; });
+    p.timages = (int)keep.size();
+    keep.insert(keep.end(), other.begin(), other.end());
+    // the cell lists keep the patch where it stays; rebuild the patch's own lists
+    p.images.clear(); p.grids.clear();
+    for (const Entry& en : keep) { p.images.push_back(en.image); p.grids.push_back({en.gx, en.gy}); }
+    if ((int)p.images.size() < opt_.minImageNum) { remove_patch(ids[k]); ++count; continue; }
+    todo.push_back(ids[k]);
+  }
+  // setRefImage + setGrids for the survivors (filter.cpp:277-280)
+  const int T = (int)todo.size();
+  if (T > 0) {
+    coords.resize((size_t)4 * T); normals.resize((size_t)4 * T);
+    images.assign((size_t)stride * T, 0); nimages.resize(T);
+    std::vector<int32_t> grids((size_t)2 * stride * T);
+    for (int j = 0; j < T; ++j) {
+      const Patch& p = patches_[todo[j]];
+      for (int c = 0; c < 4; ++c) { coords[4 * j + c] = p.coord[c]; normals[4 * j + c] = p.normal[c]; }
+      nimages[j] = std::min((int)p.images.size(), stride);
+      for (int i = 0; i < nimages[j]; ++i) images[(size_t)j * stride + i] = p.images[i];
+    }
+    if (pmvsb_set_ref_image_batch(gpu_, T, stride, coords.data(), normals.data(), images.data(), nimages.data(), grids.data())) die("set_ref_image_batch");
+    for (int j = 0; j < T; ++j) {
+      Patch& p = patches_[todo[j]];
+      // the patch moves with its recomputed cells: take it out of the old cells, put it into the new ones
+      for (size_t i = 0; i < p.images.size(); ++i)
+        if (p.images[i] < tnum_) {
+          auto& cell = grids_[p.images[i]].pg[(size_t)p.grids[i][1] * grids_[p.images[i]].gw + p.grids[i][0]];
+          cell.erase(std::remove(cell.begin(), cell.end(), todo[j]), cell.end());
+        }
+      if (nimages[j] == 0) { remove_patch(todo[j]); ++count; continue; }
+      p.images.assign(images.begin() + (size_t)j * stride, images.begin() + (size_t)j * stride + nimages[j]);
+      p.grids.clear();
+      for (int i = 0; i < nimages[j]; ++i) p.grids.push_back({grids[((size_t)j * stride + i) * 2], grids[((size_t)j * stride + i) * 2 + 1]});
+      for (size_t i = 0; i < p.images.size(); ++i)
+        if (p.images[i] < tnum_) {
+          const ImageGrid& g = grids_[p.images[i]];
+          if (p.grids[i][0] >= 0 && p.grids[i][0] < g.gw && p.grids[i][1] >= 0 && p.grids[i][1] < g.gh)
+            grids_[p.images[i]].pg[(size_t)p.grids[i][1] * g.gw + p.grids[i][0]].push_back(todo[j]);
+        }
+    }
+  }
+  std::cerr << std::endl << P << " -> " << P - count << " (" << 100.0f * (P - count) / P << "%)" << std::endl;
+}
+
+void Pipeline::filter_neighbor() {   // filter.cpp:357-392, 464-519 (times = 1)
+  std::cerr << "FilterNeighbor:\t" << std::flush;
+  const std::vector<int> ids = collect_patches();
+  const int P = (int)ids.size();
+  if (P == 0) return;
+  std::vector<char> reject(P, 0);
+  for (int k = 0; k < P; ++k) {
+    const Patch& p = patches_[ids[k]];
+    std::vector<int> nb;
+    find_neighbors(p, nb, 4.0f, 2, true);
+    if ((int)nb.size() < 6) reject[k] = 1;
+    else if (filter_quad(p, nb)) reject[k] = 1;
+  }
+  int count = 0;
+  for (int k = 0; k < P; ++k) if (reject[k]) { remove_patch(ids[k]); ++count; }
+  std::cerr << P << " -> " << P - count << " (" << 100.0f * (P - count) / P << "%)" << std::endl;
+}
+
+void Pipeline::filter_small_groups() {   // filter.cpp:524-665
+  std::cerr << "FilterGroups:\t" << std::flush;
+  const std::vector<int> ids = collect_patches();
+  const int P = (int)ids.size();
+  if (P == 0) return;
+  std::vector<int> index_of(patches_.size(), -1);
+  for (int k = 0; k < P; ++k) index_of[ids[k]] = k;
+  std::vector<int> label(P, -1);
+  int id = -1;
+  for (int start = 0; start < P; ++start) {
+    if (label[start] != -1) continue;
+    label[start] = ++id;
+    std::list<int> work{start};
+    while (!work.empty()) {
+      const int k = work.front();
+      work.pop_front();
+      const Patch& p = patches_[ids[k]];
+      const int im = p.images[0], ix = p.grids[0][0], iy = p.grids[0][1];
+      const ImageGrid& g = grids_[im];
+      if (im >= tnum_) continue;
+      for (int y = -1; y <= 1; ++y) {
+        const int yy = iy + y;
+        if (yy < 0 || g.gh <= yy) continue;
+        for (int x = -1; x <= 1; ++x) {
+          const int xx = ix + x;
+          if (xx < 0 || g.gw <= xx) continue;
+          const size_t cell = (size_t)yy * g.gw + xx;
+          for (const std::vector<int>* lst : {&g.pg[cell], &g.vpg[cell]})
+            for (int q : *lst) {
+              const int kq = index_of[q];
+              if (kq < 0 || label[kq] != -1) continue;
+              if (is_neighbor(p, patches_[q], neighbor_threshold2_)) { label[kq] = id; work.push_back(kq); }
+            }
+        }
+      }
+    }
+  }
+  std::vector<int> size(id + 1, 0);
+  for (int l : label) ++size[l];
+  const int threshold = std::max(20, P / 10000);
+  std::cerr << threshold << std::endl;
+  int count = 0;
+  for (int k = 0; k < P; ++k)
+    if (size[label[k]] < threshold) { remove_patch(ids[k]); ++count; }
+  std::cerr << P << " -> " << P - count << " (" << 100.0f * (P - count) / P << "%)" << std::endl;
+}
+
+void Pipeline::filter_round() {   // filter.cpp:13-27
+  rebuild_depth_and_vis(false);
+  filter_outside();
+  rebuild_depth_and_vis(true);
+  filter_exact();
+  rebuild_depth_and_vis(true);
+  filter_neighbor();
+  rebuild_depth_and_vis(true);
+  filter_small_groups();
+  rebuild_depth_and_vis(true);
+}
+
+void Pipeline::run() {   // findMatch.cpp:187-220
+  seed_round();
+  ++depth_;
+  for (int t = 0; t < 3; ++t) {
+    expand_round();
+    filter_round();
+    ncc_threshold_ -= 0.05f;           // updateThreshold (findMatch.cpp:23-28)
+    ncc_threshold_before_ -= 0.05f;
+    count_threshold1_ = 2;
+    ++depth_;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- writers
+void Pipeline::write(const std::string& base, bool ply, bool patch, bool pset) {   // patchOrganizerS.cpp:89-132, 687-779
+  const std::vector<int> ids = collect_patches();
+  const int P = (int)ids.size();
+  if (ply) {
+    std::vector<uint8_t> rgb((size_t)3 * std::max(P, 1), 0);
+    if (P > 0) {
+      int stride = 1;
+      for (int id : ids) stride = std::max(stride, (int)patches_[id].images.size());
+      std::vector<float> coords((size_t)4 * P);
+      std::vector<int32_t> images((size_t)stride * P, 0), nimages(P);
+      for (int k = 0; k < P; ++k) {
+        const Patch& p = patches_[ids[k]];
+        for (int c = 0; c < 4; ++c) coords[4 * k + c] = p.coord[c];
+        nimages[k] = (int)p.images.size();
+        for (size_t i = 0; i < p.images.size(); ++i) images[(size_t)k * stride + i] = p.images[i];
+      }
+      if (pmvsb_patch_colors_batch(gpu_, P, stride, coords.data(), images.data(), nimages.data(), rgb.data())) die("patch_colors_batch");
+    }
+    std::ofstream o((base + ".ply").c_str());
+    o << std::setprecision(std::numeric_limits<double>::max_digits10);
+    o << "ply\nformat ascii 1.0\nelement vertex " << P << "\nproperty float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\n"
+      << "property float nz\nproperty uchar diffuse_red\nproperty uchar diffuse_green\nproperty uchar diffuse_blue\nproperty float quality\nend_header\n";
+    for (int k = 0; k < P; ++k) {
+      const Patch& p = patches_[ids[k]];
+      o << p.coord[0] << ' ' << p.coord[1] << ' ' << p.coord[2] << ' ' << p.normal[0] << ' ' << p.normal[1] << ' ' << p.normal[2] << ' '
+        << (int)rgb[3 * k] << ' ' << (int)rgb[3 * k + 1] << ' ' << (int)rgb[3 * k + 2] << ' ' << p.ncc << '\n';
+    }
+  }
+  if (patch) {
+    std::ofstream o((base + ".patch").c_str());
+    o << std::setprecision(std::numeric_limits<double>::max_digits10);
+    o << "PATCHES" << std::endl << P << std::endl;
+    for (int k = 0; k < P; ++k) {
+      const Patch& p = patches_[ids[k]];
+      o << "PATCHS" << std::endl
+        << p.coord[0] << ' ' << p.coord[1] << ' ' << p.coord[2] << ' ' << p.coord[3] << std::endl
+        << p.normal[0] << ' ' << p.normal[1] << ' ' << p.normal[2] << ' ' << p.normal[3] << std::endl
+        << p.ncc << ' ' << p.dscale << ' ' << p.ascale << std::endl
+        << (int)p.images.size() << std::endl;
+      for (int im : p.images) o << image_ids_[im] << ' ';
+      o << std::endl << (int)p.vimages.size() << std::endl;
+      for (int im : p.vimages) o << image_ids_[im] << ' ';
+      o << std::endl << "\n";
+    }
+  }
+  if (pset) {
+    std::ofstream o((base + ".pset").c_str());
+    for (int k = 0; k < P; ++k) {
+      const Patch& p = patches_[ids[k]];
+      o << p.coord[0] << ' ' << p.coord[1] << ' ' << p.coord[2] << ' ' << p.normal[0] << ' ' << p.normal[1] << ' ' << p.normal[2] << "\n";
+    }
+  }
+  std::cerr << "wrote " << P << " patches to " << base << ".*" << std::endl;
+}
+
+}  // namespace pmvs

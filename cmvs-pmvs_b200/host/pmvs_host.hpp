@@ -1,0 +1,119 @@
+// cmvs-pmvs_b200/host/pmvs_host.hpp -- host side of the pmvs2 drop-in binary (C++17).
+//
+// What stays on the host (BASELINE.json north_star): option / camera / image file handling, feature detection,
+// seed candidate enumeration, the per-image cell bookkeeping (CPatchOrganizerS's role), the quadric and
+// small-group filters and the output writers.  Everything photometric (pre/postProcess, refinePatch, depth maps,
+// visibility, gains) is a batched call into libpmvs_b200.so (include/pmvs_b200.h).
+//
+// The reference works patch by patch from worker threads; this driver works in WAVES: all candidates that can be
+// generated from the current grid snapshot are evaluated by one launch per stage and then committed in the
+// reference's priority order, re-checking the cell rules at commit time.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/pmvs_b200.h"
+
+namespace pmvs {
+
+struct Options {   // source/pmvs/option.cpp:10-28, 47-109
+  int level = 1, csize = 2, wsize = 7, minImageNum = 3, CPU = 4, useBound = 0, useVisData = 0, sequence = -1;
+  float threshold = 0.7f, setEdge = 0.0f, maxAngleDeg = 10.0f, quad = 2.5f;
+  int tflag = -10, oflag = -10;
+  std::vector<int> timages, oimages;
+  std::vector<std::vector<int>> visdata2;   // indexes into timages ++ oimages
+  std::vector<int> bindexes;
+  std::string prefix, option;
+};
+Options parse_options(const std::string& prefix, const std::string& option);
+
+struct Camera {
+  float P[3][4];       // at the working level
+  float centre[4], oaxis[4], xaxis[3], yaxis[3], zaxis[3], ipscale;
+};
+
+struct Feature {       // PMVS3::CPoint
+  float x, y, response;
+  int type;            // 0 Harris, 1 DoG
+};
+
+struct Patch {         // Patch::CPatch
+  float coord[4] = {0, 0, 0, 1}, normal[4] = {0, 0, 0, 0};
+  float ncc = -1.0f, dscale = 0.0f, ascale = 0.0f, tmp = 0.0f;
+  int timages = 0, flag = 0;
+  unsigned char dflag = 0;
+  bool alive = true;
+  std::vector<int> images, vimages;
+  std::vector<std::array<int, 2>> grids, vgrids;
+};
+
+struct ImageGrid {     // per image: CPatchOrganizerS::_pgrids / _vpgrids / _counts / _dpgrids of that image
+  int gw = 0, gh = 0;
+  std::vector<std::vector<int>> pg, vpg;   // patch ids per cell (target images only)
+  std::vector<unsigned char> counts;
+};
+
+struct Stats { long trial = 0, pass = 0, fail0 = 0, fail1 = 0; };
+
+class Pipeline {
+ public:
+  explicit Pipeline(const Options& o);
+  ~Pipeline();
+  void load();                 // images + cameras -> GPU context, features
+  void run();                  // seed, 3 x (expand, filter)
+  void write(const std::string& base, bool ply, bool patch, bool pset);
+
+ private:
+  // ---- set-up
+  void detect_features();
+  // ---- geometry helpers (f32, the reference's formulas)
+  void project(int image, const float* X, float* out3) const;
+  float get_unit(int image, const float* X) const;
+  bool is_neighbor(const Patch& l, const Patch& r, float hunit, float thr, float radius) const;   // radius < 0: no radius test
+  bool is_neighbor(const Patch& l, const Patch& r, float thr) const;
+  float compute_radius(const Patch& p) const;
+  void find_neighbors(const Patch& p, std::vector<int>& out, float scale, int margin, bool skipvis) const;
+  bool filter_quad(const Patch& p, const std::vector<int>& neighbors) const;
+  float compute_gain(const Patch& p) const;
+  // ---- bookkeeping
+  int add_patch(const Patch& p);            // CPatchOrganizerS::addPatch
+  void remove_patch(int id);                // CPatchOrganizerS::removePatch
+  std::vector<int> collect_patches() const; // ids of live patches in the reference's collectPatches order
+  void rebuild_depth_and_vis(bool additive);
+  void upload_table(const std::vector<int>& ids);
+  // ---- rounds
+  void seed_round();
+  void expand_round();
+  void filter_round();
+  void filter_outside();
+  void filter_exact();
+  void filter_neighbor();
+  void filter_small_groups();
+  bool check_counts(const Patch& p) const;
+  bool update_counts(const Patch& p);
+  struct Candidate { Patch patch; int parent = -1; int dir = -1; int cell = -1; int feature = -1; int order = 0; };
+  // pre -> refine -> post (+ vimages at depth >= 1) for a batch; verdict[i] = 0 accepted, 1 failed in preProcess, 2 in postProcess
+  void evaluate(std::vector<Candidate>& cands, std::vector<int>& verdict);
+  void die(const std::string& where) const;
+
+  Options opt_;
+  pmvsb_ctx* gpu_ = nullptr;
+  int num_ = 0, tnum_ = 0, tau_ = 0, depth_ = 0;
+  float ncc_threshold_ = 0.7f, ncc_threshold_before_ = 0.4f;
+  int count_threshold0_ = 2, count_threshold1_ = 4, count_threshold2_ = 2;
+  float neighbor_threshold_ = 0.5f, neighbor_threshold1_ = 1.0f, neighbor_threshold2_ = 1.0f;
+  std::vector<int> image_ids_;              // file numbers, targets first
+  std::vector<Camera> cams_;
+  std::vector<int> lw_, lh_;                // image size at the working level
+  std::vector<std::vector<unsigned char>> level_rgb_;   // image bytes at the working level (feature detection)
+  std::vector<std::vector<double>> P0_;     // level-`level` projection in double for the epipolar search
+  std::vector<std::vector<float>> distances_;
+  std::vector<std::vector<Feature>> features_;
+  std::vector<ImageGrid> grids_;
+  std::vector<Patch> patches_;
+  std::vector<int> table_ids_;              // ids in the table last uploaded to the GPU
+};
+
+}  // namespace pmvs

@@ -1,0 +1,500 @@
+// cmvs-pmvs_b200/host/setup.cpp -- option file, cameras, images, feature detection (host side).
+//
+// File contracts follow the reference so that existing scene directories work unchanged:
+//   option file   /root/reference/source/pmvs/option.cpp:30-145   (keys, '#' comments, fatal unknown key)
+//   vis.dat       option.cpp:160-299
+//   cameras       <prefix>txt/%08d.txt, "CONTOUR" + 3x4 matrix    (source/image/camera.cpp:13-54, 257-270)
+//   images        <prefix>visualize/%08d.ppm (binary P6)           (source/image/photoSetS.cpp:29-72)
+// Feature detection = Harris (sigma 4) + DoG (scales 1..3), 4 strongest per 32x32 block of the working level
+// (source/pmvs/detectFeatures.cpp:78-81, harris.cpp, dog.cpp, detector.hpp); SURVEY section 8f row 1 keeps it on the host.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include <set>
+#include <sstream>
+#include <thread>
+
+#include "pmvs_host.hpp"
+
+namespace pmvs {
+
+static void fatal(const std::string& msg) {
+  std::cerr << msg << std::endl;
+  std::exit(1);
+}
+
+// ---------------------------------------------------------------------------------------------- options
+Options parse_options(const std::string& prefix, const std::string& option) {
+  Options o;
+  o.prefix = prefix;
+  o.option = option;
+  std::ifstream in((prefix + option).c_str());
+  if (!in.is_open()) fatal("Cannot open option file: " + prefix + option);
+  std::string name;
+  while (in >> name) {
+    if (name[0] == '#') { std::string rest; std::getline(in, rest); continue; }
+    if (name == "level") in >> o.level;
+    else if (name == "csize") in >> o.csize;
+    else if (name == "threshold") in >> o.threshold;
+    else if (name == "wsize") in >> o.wsize;
+    else if (name == "minImageNum") in >> o.minImageNum;
+    else if (name == "CPU") in >> o.CPU;
+    else if (name == "setEdge") in >> o.setEdge;
+    else if (name == "useBound") in >> o.useBound;
+    else if (name == "useVisData") in >> o.useVisData;
+    else if (name == "sequence") in >> o.sequence;
+    else if (name == "quad") in >> o.quad;
+    else if (name == "maxAngle") in >> o.maxAngleDeg;
+    else if (name == "timages") {
+      in >> o.tflag;
+      if (o.tflag == -1) {
+        int a, b;
+        in >> a >> b;
+        for (int i = a; i < b; ++i) o.timages.push_back(i);
+      } else if (0 < o.tflag) {
+        for (int i = 0; i < o.tflag; ++i) { int v; in >> v; o.timages.push_back(v); }
+      } else {
+        fatal("tflag is not valid: " + std::to_string(o.tflag));
+      }
+    } else if (name == "oimages") {
+      in >> o.oflag;
+      if (o.oflag == -1) {
+        int a, b;
+        in >> a >> b;
+        for (int i = a; i < b; ++i) o.oimages.push_back(i);
+      } else if (0 <= o.oflag) {
+        for (int i = 0; i < o.oflag; ++i) { int v; in >> v; o.oimages.push_back(v); }
+      } else if (o.oflag != -2 && o.oflag != -3) {
+        fatal("oflag is not valid: " + std::to_string(o.oflag));
+      }
+    } else {
+      fatal("Unrecognizable option: " + name);
+    }
+  }
+  if (o.tflag == -10 || o.oflag == -10) fatal("_tflag and _oflag not specified: " + std::to_string(o.tflag) + " " + std::to_string(o.oflag));
+
+  std::map<int, int> tdict;
+  for (int i = 0; i < (int)o.timages.size(); ++i) tdict[o.timages[i]] = i;
+
+  // oimages from vis.dat: every image co-visible with a target image that is not itself a target
+  if (o.oflag == -2) {
+    std::ifstream vis((prefix + "vis.dat").c_str());
+    if (!vis.is_open()) fatal("No vis.dat although specified to initOimages: \n" + prefix + "vis.dat");
+    std::string header;
+    int n;
+    vis >> header >> n;
+    o.oimages.clear();
+    for (int c = 0; c < n; ++c) {
+      int id, k;
+      vis >> id >> k;
+      const bool is_target = tdict.count(c) != 0;
+      for (int i = 0; i < k; ++i) {
+        int other;
+        vis >> other;
+        if (is_target && !tdict.count(other)) o.oimages.push_back(other);
+      }
+    }
+    std::sort(o.oimages.begin(), o.oimages.end());
+    o.oimages.erase(std::unique(o.oimages.begin(), o.oimages.end()), o.oimages.end());
+  }
+
+  std::vector<int> images = o.timages;
+  images.insert(images.end(), o.oimages.begin(), o.oimages.end());
+  const int num = (int)images.size();
+  o.visdata2.assign(num, {});
+  if (o.useVisData == 0) {
+    for (int y = 0; y < num; ++y)
+      for (int x = 0; x < num; ++x)
+        if (x != y) o.visdata2[y].push_back(x);
+  } else {
+    std::map<int, int> dict;
+    for (int i = 0; i < num; ++i) dict[images[i]] = i;
+    std::ifstream vis((prefix + "vis.dat").c_str());
+    if (!vis.is_open()) fatal("No vis.dat although specified to initVisdata2: \n" + prefix + "vis.dat");
+    std::string header;
+    int n;
+    vis >> header >> n;
+    std::vector<std::vector<char>> m(num, std::vector<char>(num, 0));
+    for (int c = 0; c < n; ++c) {
+      int id, k;
+      vis >> id >> k;
+      const auto it0 = dict.find(c);
+      for (int i = 0; i < k; ++i) {
+        int other;
+        vis >> other;
+        const auto it1 = dict.find(other);
+        if (it0 != dict.end() && it1 != dict.end()) { o.visdata2[it0->second].push_back(it1->second); m[it0->second][it1->second] = 1; }
+      }
+    }
+    (void)m;   // the symmetrised matrix (_visdata) is not read anywhere on the path; the lists are what addImages uses
+  }
+  if (o.useBound) {
+    std::ifstream b((prefix + "bimages.dat").c_str());
+    if (!b.is_open()) fatal("File not found: " + prefix + "bimages.dat");
+    int n;
+    b >> n;
+    for (int i = 0; i < n; ++i) {
+      int v;
+      b >> v;
+      if (tdict.count(v)) o.bindexes.push_back(tdict[v]);
+    }
+  }
+  std::cerr << "--------------------------------------------------" << std::endl
+            << "--- Summary of specified options ---" << std::endl
+            << "# of timages: " << o.timages.size() << (o.tflag == -1 ? " (range specification)" : " (enumeration)") << std::endl
+            << "# of oimages: " << o.oimages.size() << std::endl
+            << "level: " << o.level << "  csize: " << o.csize << std::endl
+            << "threshold: " << o.threshold << "  wsize: " << o.wsize << std::endl
+            << "minImageNum: " << o.minImageNum << "  CPU: " << o.CPU << std::endl
+            << "useVisData: " << o.useVisData << "  sequence: " << o.sequence << std::endl
+            << "--------------------------------------------------" << std::endl;
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------------- files
+static bool read_camera(const std::string& path, float* P) {
+  std::ifstream in(path.c_str());
+  if (!in.is_open()) return false;
+  std::string header;
+  in >> header;
+  if (header != "CONTOUR") {
+    if (header == "CONTOUR2" || header == "CONTOUR3") fatal("Camera format " + header + " is not supported by pmvs-b200 (use CONTOUR 3x4 matrices): " + path);
+    fatal("Unrecognizable txt format");
+  }
+  for (int i = 0; i < 12; ++i) in >> P[i];
+  return !in.fail();
+}
+
+static bool read_ppm(const std::string& path, std::vector<unsigned char>& rgb, int& w, int& h) {
+  FILE* fp = std::fopen(path.c_str(), "rb");
+  if (!fp) return false;
+  auto next_int = [&](int& v) {
+    for (;;) {
+      int c = std::fgetc(fp);
+      if (c == EOF) return false;
+      if (c == '#') { while (c != '\n' && c != EOF) c = std::fgetc(fp); continue; }
+      if (c == ' ' || c == '\t' || c == '\n' || c == '\r') continue;
+      std::ungetc(c, fp);
+      break;
+    }
+    return std::fscanf(fp, "%d", &v) == 1;
+  };
+  char magic[3] = {0, 0, 0};
+  int maxv = 0;
+  const bool ok = std::fscanf(fp, "%2s", magic) == 1 && std::string(magic) == "P6" && next_int(w) && next_int(h) && next_int(maxv) && maxv == 255 && w > 0 && h > 0;
+  if (!ok) { std::fclose(fp); return false; }
+  std::fgetc(fp);
+  rgb.resize((size_t)w * h * 3);
+  const size_t got = std::fread(rgb.data(), 1, rgb.size(), fp);
+  std::fclose(fp);
+  return got == rgb.size();
+}
+
+void Pipeline::die(const std::string& where) const {
+  std::cerr << where << ": " << (gpu_ ? pmvsb_last_error(gpu_) : "no GPU context") << std::endl;
+  std::exit(1);
+}
+
+Pipeline::Pipeline(const Options& o) : opt_(o) {
+  image_ids_ = o.timages;
+  image_ids_.insert(image_ids_.end(), o.oimages.begin(), o.oimages.end());
+  tnum_ = (int)o.timages.size();
+  num_ = (int)image_ids_.size();
+  tau_ = std::min(o.minImageNum * 2, num_);                 // findMatch.cpp:56
+  ncc_threshold_ = o.threshold;
+  ncc_threshold_before_ = o.threshold - 0.3f;               // findMatch.cpp:104
+}
+
+Pipeline::~Pipeline() {
+  if (gpu_) pmvsb_destroy(gpu_);
+}
+
+void Pipeline::load() {
+  if (num_ == 0 || tnum_ == 0) fatal("No target images");
+  if (pmvsb_create(&gpu_, 0, num_, tnum_, opt_.level, opt_.csize, opt_.wsize, opt_.minImageNum, opt_.threshold, opt_.maxAngleDeg) != 0)
+    fatal("pmvs-b200: cannot create a GPU context (CUDA device required; there is no CPU fallback) or bad options");
+  cams_.resize(num_);
+  lw_.resize(num_); lh_.resize(num_);
+  level_rgb_.resize(num_);
+  std::cerr << "Reading images: " << std::flush;
+  for (int i = 0; i < num_; ++i) {
+    char name[1024];
+    float P[12];
+    std::snprintf(name, sizeof(name), "%stxt/%08d.txt", opt_.prefix.c_str(), image_ids_[i]);
+    if (!read_camera(name, P)) {
+      std::snprintf(name, sizeof(name), "%stxt/%04d.txt", opt_.prefix.c_str(), image_ids_[i]);
+      if (!read_camera(name, P)) fatal(std::string("Cannot read camera: ") + name);
+    }
+    if (pmvsb_upload_camera(gpu_, i, P)) die("upload_camera");
+    std::vector<unsigned char> rgb;
+    int w = 0, h = 0;
+    std::snprintf(name, sizeof(name), "%svisualize/%08d.ppm", opt_.prefix.c_str(), image_ids_[i]);
+    if (!read_ppm(name, rgb, w, h)) {
+      std::snprintf(name, sizeof(name), "%svisualize/%04d.ppm", opt_.prefix.c_str(), image_ids_[i]);
+      if (!read_ppm(name, rgb, w, h)) {
+        std::snprintf(name, sizeof(name), "%svisualize/%08d.jpg", opt_.prefix.c_str(), image_ids_[i]);
+        if (std::ifstream(name)) fatal(std::string("JPEG input is not supported by pmvs-b200 (convert to binary PPM): ") + name);
+        fatal("Unsupported iamge format found. Stop allocation: " + std::string(name));
+      }
+    }
+    if (pmvsb_upload_image(gpu_, i, w, h, rgb.data())) die("upload_image");
+    if (pmvsb_set_visdata2(gpu_, i, opt_.visdata2[i].data(), (int)opt_.visdata2[i].size())) die("set_visdata2");
+    std::cerr << '*' << std::flush;
+  }
+  std::cerr << std::endl;
+  if (pmvsb_finalize_scene(gpu_)) die("finalize_scene");
+  grids_.resize(num_);
+  P0_.resize(num_);
+  for (int i = 0; i < num_; ++i) {
+    float P[12];
+    Camera& c = cams_[i];
+    if (pmvsb_get_camera(gpu_, i, opt_.level, P, c.centre, c.oaxis, c.xaxis, c.yaxis, c.zaxis, &c.ipscale)) die("get_camera");
+    P0_[i].resize(12);
+    for (int k = 0; k < 12; ++k) { c.P[k / 4][k % 4] = P[k]; P0_[i][k] = P[k]; }
+    if (pmvsb_image_dims(gpu_, i, opt_.level, &lw_[i], &lh_[i])) die("image_dims");
+    level_rgb_[i].resize((size_t)lw_[i] * lh_[i] * 3);
+    if (pmvsb_download_image(gpu_, i, opt_.level, level_rgb_[i].data())) die("download_image");
+    ImageGrid& g = grids_[i];
+    if (pmvsb_grid_dims(gpu_, i, &g.gw, &g.gh)) die("grid_dims");
+    if (i < tnum_) {
+      g.pg.assign((size_t)g.gw * g.gh, {});
+      g.vpg.assign((size_t)g.gw * g.gh, {});
+      g.counts.assign((size_t)g.gw * g.gh, 0);
+    }
+  }
+  // CPhotoSetS::setDistances (source/image/photoSetS.cpp:195-235): baseline / mean baseline + axis divergence beyond 10 degrees
+  distances_.assign(num_, std::vector<float>(num_, 0.0f));
+  float avedis = 0.0f;
+  int denom = 0;
+  for (int i = 0; i < num_; ++i)
+    for (int j = 0; j < num_; ++j) {
+      if (i == j) continue;
+      float d[4];
+      for (int k = 0; k < 4; ++k) d[k] = cams_[i].centre[k] - cams_[j].centre[k];
+      const float len = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]);
+      distances_[i][j] = len;
+      avedis += len;
+      ++denom;
+    }
+  if (denom) {
+    avedis /= denom;
+    if (avedis == 0.0f) fatal("All the optical centers are identical..?");
+    const float margin = std::cos(10.0f * M_PI / 180.0f);
+    for (int i = 0; i < num_; ++i)
+      for (int j = 0; j < num_; ++j) {
+        distances_[i][j] /= avedis;
+        const float dot = cams_[i].oaxis[0] * cams_[j].oaxis[0] + cams_[i].oaxis[1] * cams_[j].oaxis[1] + cams_[i].oaxis[2] * cams_[j].oaxis[2];
+        distances_[i][j] += std::max(0.0f, 1.0f - dot - margin);
+      }
+  }
+  detect_features();
+}
+
+// ---------------------------------------------------------------------------------------------- features
+namespace {
+using Plane = std::vector<float>;   // row-major w*h
+
+struct Img3 {
+  int w = 0, h = 0;
+  Plane c[3];
+};
+
+void gauss_kernel(float sigma, std::vector<float>& g) {   // CDetector::setGaussI (detector.cpp)
+  const int margin = (int)std::ceil(2 * sigma);
+  g.resize(2 * margin + 1);
+  float denom = 0.0f;
+  for (int x = 0; x < (int)g.size(); ++x) {
+    const int t = x - margin;
+    const float v = std::exp(-(t * t) / (2 * sigma * sigma));
+    g[x] = v;
+    denom += v;
+  }
+  for (float& v : g) v /= denom;
+}
+
+// the reference's unmasked-path convolutions clamp the coordinate for the Vec3f image (mask.empty() branch of the
+// masked overload, detector.hpp: edges replicate)
+void convolve_x(Plane& img, int w, int h, const std::vector<float>& f, Plane& buf) {
+  const int margin = (int)f.size() / 2;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      float acc = 0.0f;
+      for (int j = 0; j < (int)f.size(); ++j) {
+        int xt = x + j - margin;
+        xt = xt < 0 ? 0 : (xt >= w ? w - 1 : xt);
+        acc += f[j] * img[(size_t)y * w + xt];
+      }
+      buf[(size_t)y * w + x] = acc;
+    }
+  buf.swap(img);
+}
+void convolve_y(Plane& img, int w, int h, const std::vector<float>& f, Plane& buf) {
+  const int margin = (int)f.size() / 2;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      float acc = 0.0f;
+      for (int j = 0; j < (int)f.size(); ++j) {
+        int yt = y + j - margin;
+        yt = yt < 0 ? 0 : (yt >= h ? h - 1 : yt);
+        acc += f[j] * img[(size_t)yt * w + x];
+      }
+      buf[(size_t)y * w + x] = acc;
+    }
+  buf.swap(img);
+}
+
+struct BlockTop {   // keeps the 4 strongest responses of a block (the reference's multiset per result grid)
+  std::multiset<std::pair<float, std::pair<int, int>>> s;
+  void offer(float r, int x, int y, int cap, bool strict_gate) {
+    if ((int)s.size() < cap || !strict_gate || s.begin()->first < r) {
+      s.insert({r, {x, y}});
+      if ((int)s.size() > cap) s.erase(s.begin());
+    }
+  }
+};
+
+void harris(const Img3& im, int gspeedup, float sigma, std::vector<Feature>& out) {
+  const int w = im.w, h = im.h;
+  std::vector<float> gaussI;
+  gauss_kernel(sigma, gaussI);
+  const std::vector<float> dfilter = {-0.5f, 0.0f, 0.5f};
+  const std::vector<float> ifilter = {(float)(1.0 / 3.0), (float)(1.0 / 3.0), (float)(1.0 / 3.0)};
+  Plane buf((size_t)w * h), xx((size_t)w * h, 0.0f), yy((size_t)w * h, 0.0f), xy((size_t)w * h, 0.0f);
+  for (int k = 0; k < 3; ++k) {
+    Plane dx = im.c[k], dy = im.c[k];
+    convolve_x(dx, w, h, dfilter, buf); convolve_y(dx, w, h, ifilter, buf);
+    convolve_x(dy, w, h, ifilter, buf); convolve_y(dy, w, h, dfilter, buf);
+    for (size_t i = 0; i < xx.size(); ++i) { xx[i] += dx[i] * dx[i]; yy[i] += dy[i] * dy[i]; xy[i] += dx[i] * dy[i]; }
+  }
+  convolve_x(xx, w, h, gaussI, buf); convolve_y(xx, w, h, gaussI, buf);
+  convolve_x(yy, w, h, gaussI, buf); convolve_y(yy, w, h, gaussI, buf);
+  convolve_x(xy, w, h, gaussI, buf); convolve_y(xy, w, h, gaussI, buf);
+  Plane resp((size_t)w * h);
+  for (size_t i = 0; i < resp.size(); ++i) {
+    const float D = xx[i] * yy[i] - xy[i] * xy[i];
+    const float tr = xx[i] + yy[i];
+    resp[i] = (float)(D - 0.06 * tr * tr);
+  }
+  Plane nms = resp;
+  for (int y = 1; y < h - 1; ++y)
+    for (int x = 1; x < w - 1; ++x) {
+      const float v = resp[(size_t)y * w + x];
+      if (v < resp[(size_t)y * w + x + 1] || v < resp[(size_t)y * w + x - 1] || v < resp[(size_t)(y + 1) * w + x] || v < resp[(size_t)(y - 1) * w + x])
+        nms[(size_t)y * w + x] = 0.0f;
+    }
+  const int factor = 2, cap = factor * factor, gridsize = gspeedup * factor;
+  const int gw = (w + gridsize - 1) / gridsize, gh = (h + gridsize - 1) / gridsize;
+  std::vector<BlockTop> blocks((size_t)gw * gh);
+  // setGaussD(sigma) has the same support as setGaussI(sigma): margin = ceil(2 sigma)
+  const int margin = (int)std::ceil(2 * sigma);
+  for (int y = margin; y < h - margin; ++y)
+    for (int x = margin; x < w - margin; ++x) {
+      const float v = nms[(size_t)y * w + x];
+      if (v == 0.0f) continue;
+      blocks[(size_t)std::min(y / gridsize, gh - 1) * gw + std::min(x / gridsize, gw - 1)].offer(v, x, y, cap, true);
+    }
+  // CDetectFeatures pushes the points strongest first (detectFeatures.cpp:95-99)
+  std::multiset<std::pair<float, std::pair<int, int>>> all;
+  for (const BlockTop& b : blocks) all.insert(b.s.begin(), b.s.end());
+  for (auto it = all.rbegin(); it != all.rend(); ++it) out.push_back({(float)it->second.first, (float)it->second.second, it->first, 0});
+}
+
+void smooth_norm(const Img3& im, float sigma, Plane& res) {   // CDifferenceOfGaussians::setRes
+  std::vector<float> g;
+  gauss_kernel(sigma, g);
+  Plane buf((size_t)im.w * im.h), ch[3];
+  for (int k = 0; k < 3; ++k) {
+    ch[k] = im.c[k];
+    convolve_x(ch[k], im.w, im.h, g, buf);
+    convolve_y(ch[k], im.w, im.h, g, buf);
+  }
+  res.resize((size_t)im.w * im.h);
+  for (size_t i = 0; i < res.size(); ++i) res[i] = std::sqrt(ch[0][i] * ch[0][i] + ch[1][i] * ch[1][i] + ch[2][i] * ch[2][i]);
+}
+
+void dog(const Img3& im, int gspeedup, float first, float last, std::vector<Feature>& out) {
+  const int w = im.w, h = im.h;
+  const int factor = 2, cap = factor * factor, gridsize = gspeedup * factor;
+  const int gw = (w + gridsize - 1) / gridsize, gh = (h + gridsize - 1) / gridsize;
+  std::vector<BlockTop> blocks((size_t)gw * gh);
+  const float step = std::pow(2.0f, 1 / 2.0f);
+  const int steps = std::max(4, (int)std::ceil(std::log(last / first) / std::log(step)));
+  Plane pdog, cdog, ndog, cres, nres;
+  auto diff = [&](const Plane& a, const Plane& b, Plane& d) { d = b; for (size_t i = 0; i < d.size(); ++i) d[i] -= a[i]; };
+  smooth_norm(im, first, cres);
+  smooth_norm(im, first * step, nres);
+  diff(cres, nres, cdog);
+  cres.swap(nres);
+  smooth_norm(im, first * step * step, nres);
+  diff(cres, nres, ndog);
+  std::vector<unsigned char> seen((size_t)w * h, 0);
+  auto at = [&](const Plane& p, int x, int y) { return p[(size_t)y * w + x]; };
+  for (int i = 2; i <= steps - 1; ++i) {
+    const float cscale = first * std::pow(step, i + 1);
+    cres.swap(nres);
+    smooth_norm(im, cscale, nres);
+    pdog.swap(cdog);
+    cdog.swap(ndog);
+    diff(cres, nres, ndog);
+    const int margin = (int)std::ceil(2 * cscale);
+    for (int y = margin; y < h - margin; ++y)
+      for (int x = margin; x < w - margin; ++x) {
+        const float v = at(cdog, x, y);
+        if (seen[(size_t)y * w + x] || v == 0.0f) continue;
+        bool ext;
+        if (0.0f < v) {
+          ext = at(cdog, x - 1, y - 1) < v && at(cdog, x - 1, y) < v && at(cdog, x - 1, y + 1) < v && at(cdog, x, y - 1) < v &&
+                at(cdog, x, y + 1) < v && at(cdog, x + 1, y - 1) < v && at(cdog, x + 1, y) < v && at(cdog, x + 1, y + 1) < v &&
+                at(pdog, x, y) < v && at(ndog, x, y) < v;
+        } else {
+          ext = at(cdog, x - 1, y - 1) > v && at(cdog, x - 1, y) > v && at(cdog, x - 1, y + 1) > v && at(cdog, x, y - 1) > v &&
+                at(cdog, x, y + 1) > v && at(cdog, x + 1, y - 1) > v && at(cdog, x + 1, y) > v && at(cdog, x + 1, y + 1) > v &&
+                v < at(pdog, x, y) && v < at(ndog, x, y);
+        }
+        if (!ext) continue;
+        seen[(size_t)y * w + x] = 1;
+        blocks[(size_t)std::min(y / gridsize, gh - 1) * gw + std::min(x / gridsize, gw - 1)].offer(std::fabs(v), x, y, cap, false);
+      }
+  }
+  std::multiset<std::pair<float, std::pair<int, int>>> all;
+  for (const BlockTop& b : blocks) all.insert(b.s.begin(), b.s.end());
+  for (auto it = all.rbegin(); it != all.rend(); ++it) out.push_back({(float)it->second.first, (float)it->second.second, it->first, 1});
+}
+}  // namespace
+
+void Pipeline::detect_features() {
+  features_.assign(num_, {});
+  const int fcsize = 16;   // findMatch.cpp:81
+  std::vector<std::thread> th;
+  std::vector<int> next(1, 0);
+  std::mutex* mu = new std::mutex();
+  auto work = [&]() {
+    for (;;) {
+      int i;
+      { std::lock_guard<std::mutex> lk(*mu); i = next[0]++; }
+      if (i >= num_) break;
+      Img3 im;
+      im.w = lw_[i]; im.h = lh_[i];
+      for (int k = 0; k < 3; ++k) im.c[k].resize((size_t)im.w * im.h);
+      for (size_t p = 0; p < (size_t)im.w * im.h; ++p)
+        for (int k = 0; k < 3; ++k) im.c[k][p] = ((int)level_rgb_[i][3 * p + k]) / 255.0f;
+      harris(im, fcsize, 4.0f, features_[i]);
+      dog(im, fcsize, 1.0f, 3.0f, features_[i]);
+    }
+  };
+  const int nth = std::max(1, std::min(opt_.CPU, (int)std::thread::hardware_concurrency()));
+  for (int t = 1; t < nth; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  delete mu;
+  size_t total = 0;
+  for (const auto& f : features_) total += f.size();
+  std::cerr << "features: " << total << " in " << num_ << " images" << std::endl;
+}
+
+}  // namespace pmvs

@@ -135,6 +135,23 @@ int pmvsb_filter_exact_store(pmvsb_ctx* ctx, uint8_t* safe);
 /* CFilter::filterOutsideThread / computeGain (filter.cpp:88-201): gains float[P] */
 int pmvsb_compute_gains_store(pmvsb_ctx* ctx, float* gains);
 
+/* CPatchOrganizerS::setVImagesVGrids (patchOrganizerS.cpp:420-450) for a batch of patches that are not (yet) in the
+ * table -- postProcess calls it on every candidate once _depth >= 1 (optim.cpp:184-186).  Images already in
+ * images[] or vimages[] count as used; newly visible target images are appended to vimages/vgrids (capacity
+ * vstride per patch), nv is updated.  Uses the depth maps of the last pmvsb_build_depth_maps. */
+int pmvsb_set_vimages_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals,
+                            const int32_t* images, const int32_t* nimages, int vstride, int32_t* vimages,
+                            int32_t* nv, int32_t* vgrids);
+/* COptim::setRefImage (optim.cpp:208-254) + setGrids for a batch (what filterExact does after pruning image
+ * lists, filter.cpp:277-280): images reordered in place, grids = int32[2*stride*P]; nimages becomes 0 for a patch
+ * without target images. */
+int pmvsb_set_ref_image_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals,
+                              int32_t* images, int32_t* nimages, int32_t* grids);
+/* vertex colour of writePLY (patchOrganizerS.cpp:713-727): mean over the patch's images of the bilinear colour at
+ * its projection (level = option level), rounded; rgb = uint8[3*P] */
+int pmvsb_patch_colors_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const int32_t* images,
+                             const int32_t* nimages, uint8_t* rgb);
+
 /* ---- the hot call -------------------------------------------------------------------------------
  * COptim::refinePatch for a whole seed / expansion frontier in one launch (optim.cpp:496-502,580-658):
  * in-kernel bounded Nelder-Mead over (depth, angle1, angle2) around my_f, then the final
