@@ -21,7 +21,7 @@ SYMBOLS = [
     "pmvsb_download_image", "pmvsb_get_camera", "pmvsb_project_batch", "pmvsb_grab_tex_batch", "pmvsb_eval_objective_batch",
     "pmvsb_compute_incc_batch", "pmvsb_set_inccs_batch", "pmvsb_set_scales_batch", "pmvsb_pre_process_batch",
     "pmvsb_post_process_batch", "pmvsb_set_depth", "pmvsb_grid_dims", "pmvsb_store_upload", "pmvsb_build_depth_maps",
-    "pmvsb_download_depth_map", "pmvsb_set_vimages_store", "pmvsb_filter_exact_store", "pmvsb_compute_gains_store", "pmvsb_set_vimages_batch", "pmvsb_set_ref_image_batch",
+    "pmvsb_download_depth_map", "pmvsb_depth_maps_add", "pmvsb_set_vimages_store", "pmvsb_filter_exact_store", "pmvsb_compute_gains_store", "pmvsb_set_vimages_batch", "pmvsb_set_ref_image_batch",
     "pmvsb_patch_colors_batch", "pmvsb_refine_batch",
     "pmvsb_refine_batch_dev", "pmvsb_sync", "pmvsb_stream", "pmvsb_set_stream", "pmvsb_launch_count", "pmvsb_last_refine_ms",
 ]
@@ -221,6 +221,10 @@ class PmvsB200:
 
     def build_depth_maps(self):
         self._ck(self.lib.pmvsb_build_depth_maps(self.ctx))
+
+    def depth_maps_add(self, coords):
+        coords = _f32(coords).reshape(-1, 4)
+        self._ck(self.lib.pmvsb_depth_maps_add(self.ctx, coords.shape[0], _vp(coords)))
 
     def depth_map(self, image):
         gw, gh = self.grid_dims(image)

@@ -519,10 +519,14 @@ struct pmvsb_ctx {
   int32_t* d_vis_off = nullptr;
   // filter-stage patch table
   StoreDev store;
-  std::vector<void*> store_bufs;
+  char* store_arena = nullptr;      // one grow-only allocation holds the whole table
+  size_t store_cap = 0, store_used = 0;
+  int coords_cap = 0;               // patches the coords array can hold (spare room for pmvsb_depth_maps_add)
+  bool store_appended = false;
   int store_entries = 0, store_ventries = 0, store_cells = 0;
   int depth_flag = 0;
   bool store_set = false, depth_built = false;
+  std::vector<std::pair<size_t, void*>> pool;   // idle scratch blocks (size, pointer)
   char* arena = nullptr;          // grow-only device staging for the host-pointer entry points
   size_t arena_cap = 0, arena_used = 0;
   int32_t* d_vis_idx = nullptr;
@@ -690,15 +694,43 @@ void fill_scene(pmvsb_ctx* c) {
   s.dummy_pix = c->images.empty() || c->images[0].levels.empty() ? nullptr : c->images[0].levels[0];
 }
 
+// Scratch device buffers of the host-pointer entry points come from a per-context pool: cudaMalloc / cudaFree cost
+// ~0.1-1 ms each and a pipeline makes hundreds of small batched calls.  Every entry point synchronises its stream
+// before returning, so a block released by one call is idle when the next call takes it.
+thread_local pmvsb_ctx* g_current = nullptr;   // context of the entry point running on this thread
+
+void* pool_take(pmvsb_ctx* ctx, size_t bytes, size_t& granted) {
+  size_t want = 256;
+  while (want < bytes) want <<= 1;
+  granted = want;
+  if (ctx) {
+    for (size_t i = 0; i < ctx->pool.size(); ++i)
+      if (ctx->pool[i].first == want) { void* p = ctx->pool[i].second; ctx->pool.erase(ctx->pool.begin() + i); return p; }
+  }
+  void* p = nullptr;
+  if (cudaMalloc(&p, want) != cudaSuccess) return nullptr;
+  return p;
+}
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, sizeof(T) * (n ? n : 1)); }
+  size_t bytes = 0;
+  pmvsb_ctx* owner = nullptr;
+  ~DevBuf() {
+    if (!p) return;
+    if (owner && owner->pool.size() < 64) owner->pool.push_back({bytes, (void*)p}); else cudaFree(p);
+  }
+  cudaError_t alloc(size_t n) {
+    owner = g_current;
+    p = (T*)pool_take(owner, sizeof(T) * (n ? n : 1), bytes);
+    return p ? cudaSuccess : cudaErrorMemoryAllocation;
+  }
 };
 
 int check_ready(pmvsb_ctx* ctx) {
   if (!ctx) return PMVSB_EINVAL;
+  g_current = ctx;
   if (!ctx->finalized) return fail(ctx, PMVSB_ESTATE, "scene not finalised: call pmvsb_finalize_scene first");
   if (ctx->wsize != 7 && ctx->wsize != 5 && ctx->wsize != 9) return fail(ctx, PMVSB_EINVAL, "wsize must be 5, 7 or 9");
   cudaError_t e = cudaSetDevice(ctx->device);
@@ -735,7 +767,6 @@ static int arena_reserve(pmvsb_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->arena_cap) return PMVSB_OK;
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(ctx->arena);
-  for (void* b : ctx->store_bufs) cudaFree(b);
   ctx->arena = nullptr; ctx->arena_cap = 0;
   const size_t want = bytes + bytes / 4 + (1u << 20);
   CK(cudaMalloc((void**)&ctx->arena, want));
@@ -749,11 +780,14 @@ static T* arena_take(pmvsb_ctx* ctx, size_t n) {
   return reinterpret_cast<T*>(ctx->arena + off);
 }
 
+// the table lives in one grow-only arena: bump allocation, no cudaMalloc / cudaFree per upload
 template <typename T>
-static int store_put(pmvsb_ctx* ctx, const T*& dst, const T* src, size_t n) {
-  T* d = nullptr;
-  CK(cudaMalloc((void**)&d, sizeof(T) * (n ? n : 1)));
-  ctx->store_bufs.push_back(d);
+static int store_put(pmvsb_ctx* ctx, const T*& dst, const T* src, size_t n, size_t capacity = 0) {
+  const size_t off = (ctx->store_used + 255) & ~(size_t)255;
+  const size_t bytes = sizeof(T) * std::max<size_t>(std::max(n, capacity), 1);
+  if (off + bytes > ctx->store_cap) return fail(ctx, PMVSB_ENOMEM, "store arena overflow (internal sizing error)");
+  T* d = reinterpret_cast<T*>(ctx->store_arena + off);
+  ctx->store_used = off + bytes;
   if (n) CK(cudaMemcpyAsync(d, src, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
   dst = d;
   return PMVSB_OK;
@@ -814,7 +848,9 @@ int pmvsb_destroy(pmvsb_ctx* ctx) {
     for (auto* p : im.levels) cudaFree(p);
   cudaFree(ctx->d_cams); cudaFree(ctx->d_levels); cudaFree(ctx->d_counter); cudaFree(ctx->d_vis_off); cudaFree(ctx->d_vis_idx);
   cudaFree(ctx->arena);
-  for (void* b : ctx->store_bufs) cudaFree(b);
+  cudaFree(ctx->store_arena);
+  for (auto& b : ctx->pool) cudaFree(b.second);
+  g_current = nullptr;
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -835,6 +871,7 @@ int pmvsb_upload_camera(pmvsb_ctx* ctx, int index, const float* P) {
 int pmvsb_upload_image(pmvsb_ctx* ctx, int index, int width, int height, const uint8_t* rgb) {
   if (!ctx || !rgb || index < 0 || index >= ctx->num || width < 1 || height < 1)
     return fail(ctx, PMVSB_EINVAL, "upload_image: bad argument");
+  g_current = ctx;
   CK(cudaSetDevice(ctx->device));
   HostImage& im = ctx->images[index];
   for (auto* p : im.levels) cudaFree(p);
@@ -955,6 +992,7 @@ int pmvsb_image_dims(pmvsb_ctx* ctx, int index, int level, int* width, int* heig
 int pmvsb_download_image(pmvsb_ctx* ctx, int index, int level, uint8_t* rgb) {
   if (!ctx || !rgb || index < 0 || index >= ctx->num || level < 0 || level >= ctx->nlevels || !ctx->images[index].set)
     return fail(ctx, PMVSB_EINVAL, "download_image: bad argument");
+  g_current = ctx;
   CK(cudaSetDevice(ctx->device));
   const size_t n = (size_t)ctx->images[index].w[level] * ctx->images[index].h[level];
   if (n == 0) return PMVSB_OK;
@@ -1161,9 +1199,7 @@ int pmvsb_store_upload(pmvsb_ctx* ctx, int P, const float* coords, const float* 
   const int E = img_off[P], VE = vimg_off[P];
   if ((E > 0 && (!images || !grids)) || (VE > 0 && (!vimages || !vgrids))) return fail(ctx, PMVSB_EINVAL, "store_upload: null list");
   CK(cudaStreamSynchronize(ctx->stream));
-  for (void* b : ctx->store_bufs) cudaFree(b);
-  ctx->store_bufs.clear();
-  ctx->store_set = false; ctx->depth_built = false;
+  ctx->store_set = false; ctx->depth_built = false; ctx->store_appended = false;
   // grid geometry + _pgrids as CSR (patchOrganizerS.cpp:315-331); validate every index the kernels will trust
   std::vector<int32_t> gw(ctx->num), gh(ctx->num), base(ctx->tnum + 1, 0);
   for (int i = 0; i < ctx->num; ++i) {
@@ -1203,7 +1239,21 @@ int pmvsb_store_upload(pmvsb_ctx* ctx, int P, const float* coords, const float* 
     }
   StoreDev& st = ctx->store;
   st.P = P;
-  if ((r = store_put(ctx, st.coords, coords, (size_t)4 * P))) return r;
+  {
+    const int ccap = P + P / 2 + 65536;
+    const size_t need = (size_t)ccap * 16 + (size_t)P * (16 + 4 + 4 + 4 + 8) + (size_t)E * (4 + 8 + 4 + 4) + (size_t)VE * 12 +
+                        (size_t)cells * (4 + 8) + (size_t)ctx->num * 12 + 64 * 256;
+    if (need > ctx->store_cap) {
+      cudaFree(ctx->store_arena);
+      ctx->store_arena = nullptr; ctx->store_cap = 0;
+      const size_t want = need + need / 2;
+      CK(cudaMalloc((void**)&ctx->store_arena, want));
+      ctx->store_cap = want;
+    }
+    ctx->store_used = 0;
+    ctx->coords_cap = ccap;
+  }
+  if ((r = store_put(ctx, st.coords, coords, (size_t)4 * P, (size_t)4 * ctx->coords_cap))) return r;
   if ((r = store_put(ctx, st.normals, normals, (size_t)4 * P))) return r;
   if ((r = store_put(ctx, st.ncc, ncc, (size_t)P))) return r;
   if ((r = store_put(ctx, st.dscale, dscale, (size_t)P))) return r;
@@ -1220,10 +1270,11 @@ int pmvsb_store_upload(pmvsb_ctx* ctx, int P, const float* coords, const float* 
   if ((r = store_put(ctx, st.gh, gh.data(), gh.size()))) return r;
   if ((r = store_put(ctx, st.cell_off, cell_off.data(), cell_off.size()))) return r;
   if ((r = store_put(ctx, st.cell_patch, cell_patch.data(), cell_patch.size()))) return r;
-  unsigned long long* dp = nullptr;
-  CK(cudaMalloc((void**)&dp, sizeof(unsigned long long) * (cells ? cells : 1)));
-  ctx->store_bufs.push_back(dp);
-  st.dp = dp;
+  {
+    const unsigned long long* dpc = nullptr;
+    if ((r = store_put<unsigned long long>(ctx, dpc, nullptr, 0, (size_t)(cells ? cells : 1)))) return r;
+    st.dp = const_cast<unsigned long long*>(dpc);
+  }
   st.depth_flag = ctx->depth_flag;
   st.ncc_threshold = ctx->ncc_threshold;
   const double c120 = std::cos(120.0 * M_PI / 180.0);   // findMatch.cpp:126
@@ -1241,6 +1292,7 @@ static int need_store(pmvsb_ctx* ctx, bool depth) {
   if (r) return r;
   if (!ctx->store_set) return fail(ctx, PMVSB_ESTATE, "no patch table: call pmvsb_store_upload first");
   if (depth && ctx->depth_flag != 0 && !ctx->depth_built) return fail(ctx, PMVSB_ESTATE, "depth maps not built: call pmvsb_build_depth_maps first");
+  if (!depth && ctx->store_appended) return fail(ctx, PMVSB_ESTATE, "table was extended by pmvsb_depth_maps_add: upload it again before gains / filterExact");
   ctx->store.depth_flag = ctx->depth_flag;
   ctx->store.ncc_threshold = ctx->ncc_threshold;
   return PMVSB_OK;
@@ -1252,7 +1304,7 @@ int pmvsb_build_depth_maps(pmvsb_ctx* ctx) {
   CK(cudaMemsetAsync(ctx->store.dp, 0xff, sizeof(unsigned long long) * (ctx->store_cells ? ctx->store_cells : 1), ctx->stream));
   const long long n = (long long)ctx->store.P * ctx->tnum;
   if (n > 0) {
-    k_depth_maps<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->scene, ctx->store);
+    k_depth_maps<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->scene, ctx->store, 0, ctx->store.P);
     ++ctx->launches;
     CK(cudaGetLastError());
   }
@@ -1261,8 +1313,27 @@ int pmvsb_build_depth_maps(pmvsb_ctx* ctx) {
   return PMVSB_OK;
 }
 
+int pmvsb_depth_maps_add(pmvsb_ctx* ctx, int n, const float* coords) {
+  int r = need_store(ctx, true);
+  if (r) return r;
+  if (n < 0 || (n > 0 && !coords)) return fail(ctx, PMVSB_EINVAL, "depth_maps_add: bad argument");
+  if (!ctx->depth_built) return fail(ctx, PMVSB_ESTATE, "depth maps not built: call pmvsb_build_depth_maps first");
+  if (n == 0) return PMVSB_OK;
+  if (ctx->store.P + n > ctx->coords_cap) return fail(ctx, PMVSB_ENOMEM, "depth_maps_add: table capacity exhausted, upload the table again");
+  float* dst = const_cast<float*>(ctx->store.coords) + (size_t)4 * ctx->store.P;
+  CK(cudaMemcpyAsync(dst, coords, sizeof(float) * 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  const long long t = (long long)n * ctx->tnum;
+  k_depth_maps<<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(ctx->scene, ctx->store, ctx->store.P, n);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->store.P += n;
+  ctx->store_appended = true;
+  return PMVSB_OK;
+}
+
 int pmvsb_download_depth_map(pmvsb_ctx* ctx, int image, int32_t* patch_id) {
-  int r = need_store(ctx, false);
+  int r = need_store(ctx, true);
   if (r) return r;
   if (!ctx->depth_built || image < 0 || image >= ctx->tnum || !patch_id) return fail(ctx, PMVSB_EINVAL, "download_depth_map: bad argument or maps not built");
   int gw, gh;

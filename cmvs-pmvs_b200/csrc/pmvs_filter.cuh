@@ -43,10 +43,10 @@ __device__ __forceinline__ unsigned int float_order(float f) {
 // K5: CFilter::setDepthMapsThread (filter.cpp:687-732).  One thread per (patch, target image); the reference walks
 // the patches in table order and replaces a cell only by a STRICTLY nearer patch, i.e. the winner is the minimum of
 // (depth, patch id) -- a 64-bit atomicMin.
-__global__ void k_depth_maps(SceneDev s, StoreDev st) {
+__global__ void k_depth_maps(SceneDev s, StoreDev st, int p0, int count) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)st.P * s.tnum) return;
-  const int p = (int)(t / s.tnum), image = (int)(t % s.tnum);
+  if (t >= (long long)count * s.tnum) return;
+  const int p = p0 + (int)(t / s.tnum), image = (int)(t % s.tnum);
   CamDev cam;
   load_cam(s, image, cam);
   const float4 c4 = __ldg(reinterpret_cast<const float4*>(st.coords) + p);

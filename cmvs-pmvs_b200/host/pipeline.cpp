@@ -261,6 +261,7 @@ std::vector<int> Pipeline::collect_patches() const {   // patchOrganizerS.cpp:20
 }
 
 void Pipeline::upload_table(const std::vector<int>& ids) {
+  Tick tk(this, "gpu.upload_table+depth_maps");
   table_ids_ = ids;
   const int P = (int)ids.size();
   std::vector<float> coords((size_t)4 * P), normals((size_t)4 * P), ncc(P), dsc(P);
@@ -284,6 +285,7 @@ void Pipeline::upload_table(const std::vector<int>& ids) {
 
 // CFilter::setDepthMapsVGridsVPGridsAddPatchV (filter.cpp:734-783)
 void Pipeline::rebuild_depth_and_vis(bool additive) {
+  Tick tk(this, "filter.rebuild_depth_and_vis");
   const std::vector<int> ids = collect_patches();
   for (int im = 0; im < tnum_; ++im)
     for (auto& cell : grids_[im].vpg) cell.clear();
@@ -340,7 +342,8 @@ void Pipeline::evaluate(std::vector<Candidate>& cands, std::vector<int>& verdict
     for (int i = 0; i < nimages[k]; ++i) images[(size_t)k * stride + i] = p.images[i];
   }
   if (pmvsb_set_thresholds(gpu_, ncc_threshold_, ncc_threshold_before_)) die("set_thresholds");
-  if (pmvsb_pre_process_batch(gpu_, P, stride, coords.data(), normals.data(), images.data(), nimages.data(), dsc.data(), asc.data(), v0.data())) die("pre_process_batch");
+  { Tick tk(this, "gpu.pre_process");
+  if (pmvsb_pre_process_batch(gpu_, P, stride, coords.data(), normals.data(), images.data(), nimages.data(), dsc.data(), asc.data(), v0.data())) die("pre_process_batch"); }
   // compact the survivors, refine them (tau images each), post-process them
   std::vector<int> live;
   for (int k = 0; k < P; ++k) if (v0[k] == 0) live.push_back(k);
@@ -355,9 +358,11 @@ void Pipeline::evaluate(std::vector<Candidate>& cands, std::vector<int>& verdict
     ld[j] = dsc[k]; lni[j] = nimages[k];
     for (int i = 0; i < stride; ++i) li[(size_t)j * stride + i] = images[(size_t)k * stride + i];
   }
-  if (pmvsb_refine_batch(gpu_, L, stride, lc.data(), ln.data(), li.data(), lni.data(), ld.data(), lncc.data(), lev.data(), lok.data())) die("refine_batch");
+  { Tick tk(this, "gpu.refine");
+  if (pmvsb_refine_batch(gpu_, L, stride, lc.data(), ln.data(), li.data(), lni.data(), ld.data(), lncc.data(), lev.data(), lok.data())) die("refine_batch"); }
   // a failed optimiser leaves the patch untouched and the reference still runs postProcess on it (optim.cpp:496-502)
-  if (pmvsb_post_process_batch(gpu_, L, stride, lc.data(), ln.data(), lncc.data(), li.data(), lni.data(), lgr.data(), lti.data(), ltmp.data(), lv.data())) die("post_process_batch");
+  { Tick tk(this, "gpu.post_process");
+  if (pmvsb_post_process_batch(gpu_, L, stride, lc.data(), ln.data(), lncc.data(), li.data(), lni.data(), lgr.data(), lti.data(), ltmp.data(), lv.data())) die("post_process_batch"); }
   for (int j = 0; j < L; ++j) {
     const int k = live[j];
     Patch& p = cands[k].patch;
@@ -423,6 +428,7 @@ void fundamental(const std::vector<double>& P0, const std::vector<double>& P1, d
 }  // namespace
 
 void Pipeline::seed_round() {
+  Tick tk(this, "round.seed");
   Stats st;
   std::vector<int> order(tnum_);
   std::iota(order.begin(), order.end(), 0);
@@ -642,6 +648,7 @@ bool Pipeline::update_counts(const Patch& p) {   // expand.cpp:325-406; true = t
 }
 
 void Pipeline::expand_round() {
+  Tick tk(this, "round.expand");
   Stats st;
   for (auto& g : grids_) std::fill(g.counts.begin(), g.counts.end(), 0);
   for (Patch& p : patches_) p.flag = 0;
@@ -651,9 +658,10 @@ void Pipeline::expand_round() {
   std::cerr << "Expanding patches..." << std::flush;
   const double two_pi = 2 * M_PI;
   int wave_no = 0;
+  if (depth_ != 0) upload_table(collect_patches());   // depth maps for setVImagesVGrids of the candidates
+  size_t last_table_size = patches_.size();
   while (!frontier.empty()) {
     std::stable_sort(frontier.begin(), frontier.end(), [&](int a, int b) { return patches_[a].tmp > patches_[b].tmp; });
-    if (depth_ != 0) upload_table(collect_patches());   // depth maps for setVImagesVGrids of the candidates
     std::vector<Candidate> wave;
     for (int id : frontier) {
       const Patch& pp = patches_[id];
@@ -666,7 +674,7 @@ void Pipeline::expand_round() {
       const float radius = compute_radius(pp);
       const float rlow = radius / 6.0f, rhigh = radius * 2.5f;
       std::vector<int> nb;
-      find_neighbors(pp, nb, 4.0f, 1, false);
+      { Tick tk2(this, "host.expand.find_neighbors"); find_neighbors(pp, nb, 4.0f, 1, false); }
       for (int q : nb) {
         float diff[4];
         for (int k = 0; k < 4; ++k) diff[k] = patches_[q].coord[k] - pp.coord[k];
@@ -737,6 +745,19 @@ void Pipeline::expand_round() {
         }
       }
       if (fail) patches_[c.parent].dflag |= (unsigned char)(1 << c.dir);
+    }
+    // CPatchOrganizerS::updateDepthMaps for the patches committed by this wave (patchOrganizerS.cpp:351-381)
+    if (depth_ != 0) {
+      std::vector<int> fresh;
+      for (size_t id = last_table_size; id < patches_.size(); ++id) fresh.push_back((int)id);
+      if (!fresh.empty()) {
+        Tick tk3(this, "gpu.depth_maps_add");
+        std::vector<float> cc((size_t)4 * fresh.size());
+        for (size_t k = 0; k < fresh.size(); ++k)
+          for (int c4 = 0; c4 < 4; ++c4) cc[4 * k + c4] = patches_[fresh[k]].coord[c4];
+        if (pmvsb_depth_maps_add(gpu_, (int)fresh.size(), cc.data()) != 0) upload_table(collect_patches());   // capacity: full upload
+      }
+      last_table_size = patches_.size();
     }
     frontier.swap(next);
     ++wave_no;
@@ -840,6 +861,7 @@ void Pipeline::filter_exact() {   // filter.cpp:203-355
 }
 
 void Pipeline::filter_neighbor() {   // filter.cpp:357-392, 464-519 (times = 1)
+  Tick tk(this, "host.filter_neighbor");
   std::cerr << "FilterNeighbor:\t" << std::flush;
   const std::vector<int> ids = collect_patches();
   const int P = (int)ids.size();
@@ -858,6 +880,7 @@ void Pipeline::filter_neighbor() {   // filter.cpp:357-392, 464-519 (times = 1)
 }
 
 void Pipeline::filter_small_groups() {   // filter.cpp:524-665
+  Tick tk(this, "host.filter_small_groups");
   std::cerr << "FilterGroups:\t" << std::flush;
   const std::vector<int> ids = collect_patches();
   const int P = (int)ids.size();
@@ -905,6 +928,7 @@ void Pipeline::filter_small_groups() {   // filter.cpp:524-665
 }
 
 void Pipeline::filter_round() {   // filter.cpp:13-27
+  Tick tk(this, "round.filter");
   rebuild_depth_and_vis(false);
   filter_outside();
   rebuild_depth_and_vis(true);
@@ -983,6 +1007,7 @@ void Pipeline::write(const std::string& base, bool ply, bool patch, bool pset) {
     }
   }
   std::cerr << "wrote " << P << " patches to " << base << ".*" << std::endl;
+  for (const auto& kv : seconds_) std::cerr << "time " << kv.first << ' ' << kv.second << " s" << std::endl;
 }
 
 }  // namespace pmvs

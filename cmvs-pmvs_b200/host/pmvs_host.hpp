@@ -10,6 +10,8 @@
 // reference's priority order, re-checking the cell rules at commit time.
 #pragma once
 #include <array>
+#include <chrono>
+#include <map>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -114,6 +116,13 @@ class Pipeline {
   std::vector<ImageGrid> grids_;
   std::vector<Patch> patches_;
   std::vector<int> table_ids_;              // ids in the table last uploaded to the GPU
+  std::map<std::string, double> seconds_;   // wall time per phase (printed by write())
+ public:
+  struct Tick {
+    Pipeline* p; std::string k; std::chrono::steady_clock::time_point t0;
+    Tick(Pipeline* pp, const std::string& kk) : p(pp), k(kk), t0(std::chrono::steady_clock::now()) {}
+    ~Tick() { p->seconds_[k] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+  };
 };
 
 }  // namespace pmvs

@@ -215,6 +215,7 @@ Pipeline::~Pipeline() {
 }
 
 void Pipeline::load() {
+  Tick tk(this, "load.total");
   if (num_ == 0 || tnum_ == 0) fatal("No target images");
   if (pmvsb_create(&gpu_, 0, num_, tnum_, opt_.level, opt_.csize, opt_.wsize, opt_.minImageNum, opt_.threshold, opt_.maxAngleDeg) != 0)
     fatal("pmvs-b200: cannot create a GPU context (CUDA device required; there is no CPU fallback) or bad options");
@@ -468,6 +469,7 @@ void dog(const Img3& im, int gspeedup, float first, float last, std::vector<Feat
 }  // namespace
 
 void Pipeline::detect_features() {
+  Tick tk(this, "host.detect_features");
   features_.assign(num_, {});
   const int fcsize = 16;   // findMatch.cpp:81
   std::vector<std::thread> th;

@@ -127,6 +127,11 @@ int pmvsb_store_upload(pmvsb_ctx* ctx, int P, const float* coords, const float* 
 /* CFilter::setDepthMaps (source/pmvs/filter.cpp:667-732): nearest patch per cell of every target image */
 int pmvsb_build_depth_maps(pmvsb_ctx* ctx);
 int pmvsb_download_depth_map(pmvsb_ctx* ctx, int image, int32_t* patch_id);   /* gw*gh ids, -1 = empty */
+/* CPatchOrganizerS::updateDepthMaps (patchOrganizerS.cpp:351-381) for n patches committed since the last upload:
+ * their coords are appended to the table (ids P, P+1, ...) and merged into the depth maps.  Only the visibility
+ * calls may be used on an appended table; gains / filterExact need a fresh pmvsb_store_upload.  Returns
+ * PMVSB_ENOMEM when the table's spare capacity is exhausted (re-upload instead). */
+int pmvsb_depth_maps_add(pmvsb_ctx* ctx, int n, const float* coords);
 /* CPatchOrganizerS::setVImagesVGrids (patchOrganizerS.cpp:420-450) for every table patch, from an empty _vimages:
  * vimages int32[vcap*P], vgrids int32[2*vcap*P], nv int32[P] */
 int pmvsb_set_vimages_store(pmvsb_ctx* ctx, int vcap, int32_t* vimages, int32_t* vgrids, int32_t* nv);

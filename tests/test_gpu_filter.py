@@ -45,6 +45,25 @@ def test_depth_maps_bit_exact(gpu, scene, S, state):
     assert np.array_equal(np.concatenate([gpu.depth_map(i) for i in range(scene.num)]), S["depth_maps"])   # = the reference's own maps
 
 
+def test_depth_maps_incremental(gpu, scene, S, state):
+    """pmvsb_depth_maps_add (updateDepthMaps) on the second half of the table == building all at once"""
+    st, o = state
+    P = len(st["ncc"])
+    h = P // 2
+    first = {k: st[k] for k in STORE_KEYS}
+    first.update(coords=st["coords"][:h], normals=st["normals"][:h], ncc=st["ncc"][:h], dscale=st["dscale"][:h], timages=st["timages"][:h],
+                 img_off=st["img_off"][: h + 1], vimg_off=st["vimg_off"][: h + 1],
+                 images=st["images"][: st["img_off"][h]], grids=st["grids"][: st["img_off"][h]],
+                 vimages=st["vimages"][: st["vimg_off"][h]], vgrids=st["vgrids"][: st["vimg_off"][h]])
+    gpu.store_upload(first)
+    gpu.build_depth_maps()
+    gpu.depth_maps_add(st["coords"][h:])
+    got = np.concatenate([gpu.depth_map(i) for i in range(scene.num)])
+    assert np.array_equal(got, S["depth_maps"])
+    gpu.store_upload(st)   # restore the full table for the other tests
+    gpu.build_depth_maps()
+
+
 def test_set_vimages_bit_exact(gpu, scene, state):
     st, o = state
     vim, vgr, nv = gpu.set_vimages_store(scene.num)
