@@ -1,5 +1,6 @@
 // cmvs-pmvs_b200/host/main.cpp -- `pmvs2 prefix option_file [PATCH] [PSET]`, the reference binary's command line
 // (/root/reference/source/pmvs.cpp:7-63; genOption's scripts call it pmvs2, this fork's CMake target is pmvs3).
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -27,6 +28,7 @@ int main(int argc, char* argv[]) {
               << "[Optional export] PATCH PSET" << std::endl;
     return 1;
   }
+  const auto t_start = std::chrono::steady_clock::now();
   for (int i = 0; i < argc; ++i) std::cout << std::endl << argv[i];
   std::cout << std::endl;
   const pmvs::Options opt = pmvs::parse_options(argv[1], argv[2]);
@@ -40,5 +42,6 @@ int main(int argc, char* argv[]) {
     if (a == "PSET") pset = true;
   }
   pipe.write(std::string(argv[1]) + "models/" + argv[2], true, patch, pset);
+  std::cerr << "time main.total " << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() << " s" << std::endl;
   return 0;
 }

@@ -955,6 +955,8 @@ void Pipeline::run() {   // findMatch.cpp:187-220
 
 // ---------------------------------------------------------------------------------------------- writers
 void Pipeline::write(const std::string& base, bool ply, bool patch, bool pset) {   // patchOrganizerS.cpp:89-132, 687-779
+  {
+  Tick tk(this, "write.total");
   const std::vector<int> ids = collect_patches();
   const int P = (int)ids.size();
   if (ply) {
@@ -983,20 +985,21 @@ void Pipeline::write(const std::string& base, bool ply, bool patch, bool pset) {
     }
   }
   if (patch) {
+    // same text as the reference's `ofstr << patch` (source/pmvs/patch.cpp:30-48); newlines instead of std::endl flushes
     std::ofstream o((base + ".patch").c_str());
     o << std::setprecision(std::numeric_limits<double>::max_digits10);
-    o << "PATCHES" << std::endl << P << std::endl;
+    o << "PATCHES" << '\n' << P << '\n';
     for (int k = 0; k < P; ++k) {
       const Patch& p = patches_[ids[k]];
-      o << "PATCHS" << std::endl
-        << p.coord[0] << ' ' << p.coord[1] << ' ' << p.coord[2] << ' ' << p.coord[3] << std::endl
-        << p.normal[0] << ' ' << p.normal[1] << ' ' << p.normal[2] << ' ' << p.normal[3] << std::endl
-        << p.ncc << ' ' << p.dscale << ' ' << p.ascale << std::endl
-        << (int)p.images.size() << std::endl;
+      o << "PATCHS" << '\n'
+        << p.coord[0] << ' ' << p.coord[1] << ' ' << p.coord[2] << ' ' << p.coord[3] << '\n'
+        << p.normal[0] << ' ' << p.normal[1] << ' ' << p.normal[2] << ' ' << p.normal[3] << '\n'
+        << p.ncc << ' ' << p.dscale << ' ' << p.ascale << '\n'
+        << (int)p.images.size() << '\n';
       for (int im : p.images) o << image_ids_[im] << ' ';
-      o << std::endl << (int)p.vimages.size() << std::endl;
+      o << '\n' << (int)p.vimages.size() << '\n';
       for (int im : p.vimages) o << image_ids_[im] << ' ';
-      o << std::endl << "\n";
+      o << '\n' << "\n";
     }
   }
   if (pset) {
@@ -1007,6 +1010,7 @@ void Pipeline::write(const std::string& base, bool ply, bool patch, bool pset) {
     }
   }
   std::cerr << "wrote " << P << " patches to " << base << ".*" << std::endl;
+  }
   for (const auto& kv : seconds_) std::cerr << "time " << kv.first << ' ' << kv.second << " s" << std::endl;
 }
 

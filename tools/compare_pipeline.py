@@ -65,7 +65,10 @@ def main():
         if scene.kind == "sphere" and len(pts):
             rad = np.linalg.norm(pts[:, :3], axis=1)
             r["mean_abs_radius_error"] = float(np.abs(rad - 1).mean())
-            r["normal_alignment"] = float((pts[:, 3:] * pts[:, :3] / rad[:, None]).sum(1).mean())
+            al = (pts[:, 3:] * pts[:, :3] / rad[:, None]).sum(1)
+            r["normal_alignment"] = float(al.mean())
+            r["frac_normal_off_by_more_than_10deg"] = float((al < 0.9848).mean())
+            r["frac_radius_error_above_0.005"] = float((np.abs(rad - 1) > 0.005).mean())
         res[k] = r
     if len(runs) == 2 and all(len(v[1]) for v in runs.values()):
         ra, rb = runs[list(runs)[0]][1], runs["pmvs_b200"][1]
