@@ -663,9 +663,13 @@ void Pipeline::expand_round() {
   while (!frontier.empty()) {
     std::stable_sort(frontier.begin(), frontier.end(), [&](int a, int b) { return patches_[a].tmp > patches_[b].tmp; });
     std::vector<Candidate> wave;
-    for (int id : frontier) {
+    std::vector<std::vector<Candidate>> per_parent(frontier.size());
+    { Tick tk2(this, "host.expand.candidates");
+    parallel_for((int)frontier.size(), threads_, [&](int fi) {
+      const int id = frontier[fi];
+      std::vector<Candidate>& wave = per_parent[fi];   // this parent's candidates; concatenated in frontier order below
       const Patch& pp = patches_[id];
-      if (!pp.alive) continue;
+      if (!pp.alive) return;
       // findEmptyBlocks (expand.cpp:108-180)
       float xdir[4], ydir[4];
       ortho(pp.normal, xdir, ydir);
@@ -674,7 +678,7 @@ void Pipeline::expand_round() {
       const float radius = compute_radius(pp);
       const float rlow = radius / 6.0f, rhigh = radius * 2.5f;
       std::vector<int> nb;
-      { Tick tk2(this, "host.expand.find_neighbors"); find_neighbors(pp, nb, 4.0f, 1, false); }
+      find_neighbors(pp, nb, 4.0f, 1, false);
       for (int q : nb) {
         float diff[4];
         for (int k = 0; k < 4; ++k) diff[k] = patches_[q].coord[k] - pp.coord[k];
@@ -709,7 +713,10 @@ void Pipeline::expand_round() {
         if (check_counts(c.patch)) { patches_[id].dflag |= (unsigned char)(1 << i); continue; }
         wave.push_back(c);
       }
+    }, 16);
     }
+    for (auto& v : per_parent) for (auto& c : v) wave.push_back(std::move(c));
+    per_parent.clear();
     std::vector<int> verdict;
     evaluate(wave, verdict);
     // commit in parent-priority order; cells may have been taken by an earlier commit of this wave
@@ -867,13 +874,13 @@ void Pipeline::filter_neighbor() {   // filter.cpp:357-392, 464-519 (times = 1)
   const int P = (int)ids.size();
   if (P == 0) return;
   std::vector<char> reject(P, 0);
-  for (int k = 0; k < P; ++k) {
+  parallel_for(P, threads_, [&](int k) {
     const Patch& p = patches_[ids[k]];
     std::vector<int> nb;
     find_neighbors(p, nb, 4.0f, 2, true);
     if ((int)nb.size() < 6) reject[k] = 1;
     else if (filter_quad(p, nb)) reject[k] = 1;
-  }
+  });
   int count = 0;
   for (int k = 0; k < P; ++k) if (reject[k]) { remove_patch(ids[k]); ++count; }
   std::cerr << P << " -> " << P - count << " (" << 100.0f * (P - count) / P << "%)" << std::endl;

@@ -9,16 +9,40 @@
 // generated from the current grid snapshot are evaluated by one launch per stage and then committed in the
 // reference's priority order, re-checking the cell rules at commit time.
 #pragma once
+#include <algorithm>
 #include <array>
+#include <atomic>
 #include <chrono>
 #include <map>
 #include <cstdint>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pmvs_b200.h"
 
 namespace pmvs {
+
+// The host bookkeeping loops that only READ the grids (neighbour searches, marshalling) run on the option file's
+// `CPU` threads, as the reference's do; body(i) must touch only item i's own data.
+template <typename F>
+void parallel_for(int n, int threads, F body, int chunk = 64) {
+  threads = std::max(1, std::min(threads, (n + chunk - 1) / chunk));
+  if (threads == 1) { for (int i = 0; i < n; ++i) body(i); return; }
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    for (;;) {
+      const int b = next.fetch_add(chunk);
+      if (b >= n) break;
+      const int e = std::min(n, b + chunk);
+      for (int i = b; i < e; ++i) body(i);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < threads; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+}
 
 struct Options {   // source/pmvs/option.cpp:10-28, 47-109
   int level = 1, csize = 2, wsize = 7, minImageNum = 3, CPU = 4, useBound = 0, useVisData = 0, sequence = -1;
@@ -102,7 +126,7 @@ class Pipeline {
 
   Options opt_;
   pmvsb_ctx* gpu_ = nullptr;
-  int num_ = 0, tnum_ = 0, tau_ = 0, depth_ = 0;
+  int num_ = 0, tnum_ = 0, tau_ = 0, depth_ = 0, threads_ = 1;
   float ncc_threshold_ = 0.7f, ncc_threshold_before_ = 0.4f;
   int count_threshold0_ = 2, count_threshold1_ = 4, count_threshold2_ = 2;
   float neighbor_threshold_ = 0.5f, neighbor_threshold1_ = 1.0f, neighbor_threshold2_ = 1.0f;

@@ -208,6 +208,7 @@ Pipeline::Pipeline(const Options& o) : opt_(o) {
   tau_ = std::min(o.minImageNum * 2, num_);                 // findMatch.cpp:56
   ncc_threshold_ = o.threshold;
   ncc_threshold_before_ = o.threshold - 0.3f;               // findMatch.cpp:104
+  threads_ = std::max(1, std::min(o.CPU, (int)std::thread::hardware_concurrency()));
 }
 
 Pipeline::~Pipeline() {

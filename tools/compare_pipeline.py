@@ -1,6 +1,6 @@
 """Run the reference binary (oracle/_ref/pmvs3_ref, CPU) and the drop-in (cmvs-pmvs_b200/bin/pmvs2, GPU) on the same
 synthetic scene directory and compare the clouds: patch count, accuracy against the known surface, and the mean
-nearest-neighbour distance between the two clouds.   usage: python tools/compare_pipeline.py [sphere16|small16|ring47] [--cpu N]"""
+nearest-neighbour distance between the two clouds.   usage: python tools/compare_pipeline.py [sphere16|small16|ring47|dtu48] [--cpu N]"""
 import argparse
 import json
 import os
@@ -40,6 +40,8 @@ def main():
         scene = synth.sphere_scene(views=16, width=320, height=240)
     elif a.scene == "ring47":
         scene = synth.ring_scene()
+    elif a.scene == "dtu48":
+        scene = synth.dtu_scene()
     else:
         raise SystemExit("unknown scene")
     synth.render(scene, device="cuda" if torch.cuda.is_available() else "cpu")
@@ -49,7 +51,9 @@ def main():
         scene.option["CPU"] = a.cpu
         pr = synth.write_scene(scene, "/tmp/cmp_ref_%s" % a.scene)
         t = time.time()
-        subprocess.run([os.path.join(ROOT, "oracle/_ref/pmvs3_ref"), pr, "option.txt", "PSET"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+        pref = subprocess.run([os.path.join(ROOT, "oracle/_ref/pmvs3_ref"), pr, "option.txt", "PSET"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, check=True)
+        if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+            open(os.path.join(ROOT, "gpurun_out", "pmvs3_ref_%s_cpu%d.log" % (a.scene, a.cpu)), "w").write(pref.stderr[-20000:])
         runs["reference_cpu%d" % a.cpu] = (time.time() - t, np.loadtxt(pr + "models/option.txt.pset", dtype=np.float32).reshape(-1, 6))
     scene.option["CPU"] = os.cpu_count() or 4
     pg = synth.write_scene(scene, "/tmp/cmp_gpu_%s" % a.scene)
