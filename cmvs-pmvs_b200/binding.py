@@ -21,7 +21,8 @@ SYMBOLS = [
     "pmvsb_download_image", "pmvsb_get_camera", "pmvsb_project_batch", "pmvsb_grab_tex_batch", "pmvsb_eval_objective_batch",
     "pmvsb_compute_incc_batch", "pmvsb_set_inccs_batch", "pmvsb_set_scales_batch", "pmvsb_pre_process_batch",
     "pmvsb_post_process_batch", "pmvsb_set_depth", "pmvsb_grid_dims", "pmvsb_store_upload", "pmvsb_build_depth_maps",
-    "pmvsb_download_depth_map", "pmvsb_depth_maps_add", "pmvsb_set_vimages_store", "pmvsb_filter_exact_store", "pmvsb_compute_gains_store", "pmvsb_set_vimages_batch", "pmvsb_set_ref_image_batch",
+    "pmvsb_download_depth_map", "pmvsb_depth_maps_add", "pmvsb_store_append", "pmvsb_store_update_vimages",
+    "pmvsb_store_download_vimages", "pmvsb_download_cell_lists", "pmvsb_find_empty_blocks_store", "pmvsb_filter_neighbor_store", "pmvsb_set_vimages_store", "pmvsb_filter_exact_store", "pmvsb_compute_gains_store", "pmvsb_set_vimages_batch", "pmvsb_set_ref_image_batch",
     "pmvsb_patch_colors_batch", "pmvsb_refine_batch",
     "pmvsb_refine_batch_dev", "pmvsb_sync", "pmvsb_stream", "pmvsb_set_stream", "pmvsb_launch_count", "pmvsb_last_refine_ms",
 ]
@@ -77,6 +78,7 @@ class PmvsB200:
             self.ctx = None
             raise PmvsError("pmvsb_create failed (%d): no CUDA device or bad arguments -- there is no CPU fallback" % r)
         self.num = num_images
+        self.num_target = num_images if num_target is None else num_target
         self.level = level
         self.wsize = wsize
         self.tau = min(2 * min_image_num, num_images)
@@ -218,6 +220,45 @@ class PmvsB200:
         self._ck(self.lib.pmvsb_store_upload(self.ctx, self._store_P, _vp(f("coords")), _vp(f("normals")), _vp(f("ncc")), _vp(f("dscale")),
                                              _vp(i("img_off")), _vp(i("images")), _vp(i("grids")), _vp(i("vimg_off")), _vp(i("vimages")),
                                              _vp(i("vgrids")), _vp(i("timages"))))
+
+    def store_append(self, st):
+        """st: the same fields for the patches to append; offsets relative to their first entry"""
+        f = lambda k: np.ascontiguousarray(st[k], dtype=np.float32)
+        i = lambda k: np.ascontiguousarray(st[k], dtype=np.int32)
+        n = len(st["ncc"])
+        self._ck(self.lib.pmvsb_store_append(self.ctx, n, _vp(f("coords")), _vp(f("normals")), _vp(f("ncc")), _vp(f("dscale")),
+                                             _vp(i("img_off")), _vp(i("images")), _vp(i("grids")), _vp(i("vimg_off")), _vp(i("vimages")),
+                                             _vp(i("vgrids")), _vp(i("timages"))))
+        self._store_P += n; self._store_E += int(st["img_off"][-1] - st["img_off"][0])
+
+    def store_update_vimages(self, additive):
+        """setVImagesVGrids for the whole table, in place; returns (vimg_off, vimages, vgrids[:, 2]) as CSR"""
+        total = C.c_int32()
+        self._ck(self.lib.pmvsb_store_update_vimages(self.ctx, int(additive), C.byref(total)))
+        off = np.zeros(self._store_P + 1, np.int32); vim = np.zeros(max(total.value, 1), np.int32); vgr = np.zeros((max(total.value, 1), 2), np.int32)
+        self._ck(self.lib.pmvsb_store_download_vimages(self.ctx, _vp(off), _vp(vim), _vp(vgr)))
+        return off, vim[:total.value], vgr[:total.value]
+
+    def cell_lists(self, visible):
+        cells = sum(self.grid_dims(i)[0] * self.grid_dims(i)[1] for i in range(self.num_target))
+        off = np.zeros(cells + 1, np.int32)
+        self._ck(self.lib.pmvsb_download_cell_lists(self.ctx, int(visible), _vp(off), None))
+        lst = np.zeros(max(int(off[-1]), 1), np.int32)
+        self._ck(self.lib.pmvsb_download_cell_lists(self.ctx, int(visible), _vp(off), _vp(lst)))
+        return off, lst[:int(off[-1])]
+
+    def find_empty_blocks_store(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        mask = np.zeros(len(ids), np.uint8); radius = np.zeros(len(ids), np.float32)
+        self._ck(self.lib.pmvsb_find_empty_blocks_store(self.ctx, len(ids), _vp(ids), _vp(mask), _vp(radius)))
+        return mask, radius
+
+    def filter_neighbor_store(self, quad=2.5):
+        P = self._store_P
+        rej = np.zeros(P, np.uint8); res = np.zeros(P, np.float32); cnt = np.zeros(P, np.int32)
+        ov = C.c_int32()
+        self._ck(self.lib.pmvsb_filter_neighbor_store(self.ctx, C.c_float(quad), _vp(rej), _vp(res), _vp(cnt), C.byref(ov)))
+        return rej, res, cnt, ov.value
 
     def build_depth_maps(self):
         self._ck(self.lib.pmvsb_build_depth_maps(self.ctx))

@@ -18,6 +18,7 @@
 #include "pmvs_group.cuh"
 #include "pmvs_select.cuh"
 #include "pmvs_filter.cuh"
+#include "pmvs_cells.cuh"
 
 #ifndef PMVS_MINBLOCKS
 #define PMVS_MINBLOCKS 6
@@ -503,6 +504,20 @@ struct HostImage {
   bool set = false;
 };
 
+// grow-only device array; the table's fields keep their capacity across uploads and appends
+template <typename T>
+struct DVec {
+  T* p = nullptr;
+  size_t cap = 0;
+};
+struct StoreBufs {
+  DVec<float> coords, normals, ncc, dscale;
+  DVec<int32_t> timages, img_off, images, grids, entry_patch, vimg_off, vimages, vgrids, ventry_patch;
+  DVec<int32_t> alt_voff, alt_vimages, alt_vgrids;                  // double buffers of pmvsb_store_update_vimages
+  DVec<int32_t> cell_base, gw, gh, cell_off, cell_patch, vcell_off, vcell_patch, cursor, tile_sums, counts;
+  DVec<unsigned long long> dp;
+};
+
 struct pmvsb_ctx {
   int device = 0;
   int num = 0, tnum = 0, level = 1, csize = 2, wsize = 7, min_image_num = 3, tau = 0, nlevels = 0;
@@ -519,11 +534,10 @@ struct pmvsb_ctx {
   int32_t* d_vis_off = nullptr;
   // filter-stage patch table
   StoreDev store;
-  char* store_arena = nullptr;      // one grow-only allocation holds the whole table
-  size_t store_cap = 0, store_used = 0;
-  int coords_cap = 0;               // patches the coords array can hold (spare room for pmvsb_depth_maps_add)
-  bool store_appended = false;
+  StoreBufs sb;                     // grow-only device arrays behind `store`
+  bool store_appended = false;      // coords-only append (pmvsb_depth_maps_add): lists are stale
   int store_entries = 0, store_ventries = 0, store_cells = 0;
+  std::vector<int32_t> h_gw, h_gh, h_base;
   int depth_flag = 0;
   bool store_set = false, depth_built = false;
   std::vector<std::pair<size_t, void*>> pool;   // idle scratch blocks (size, pointer)
@@ -780,16 +794,98 @@ static T* arena_take(pmvsb_ctx* ctx, size_t n) {
   return reinterpret_cast<T*>(ctx->arena + off);
 }
 
-// the table lives in one grow-only arena: bump allocation, no cudaMalloc / cudaFree per upload
+// ---- resident patch table: grow-only arrays, cell lists built on the device -----------------------------------
 template <typename T>
-static int store_put(pmvsb_ctx* ctx, const T*& dst, const T* src, size_t n, size_t capacity = 0) {
-  const size_t off = (ctx->store_used + 255) & ~(size_t)255;
-  const size_t bytes = sizeof(T) * std::max<size_t>(std::max(n, capacity), 1);
-  if (off + bytes > ctx->store_cap) return fail(ctx, PMVSB_ENOMEM, "store arena overflow (internal sizing error)");
-  T* d = reinterpret_cast<T*>(ctx->store_arena + off);
-  ctx->store_used = off + bytes;
-  if (n) CK(cudaMemcpyAsync(d, src, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
-  dst = d;
+static int dvec_reserve(pmvsb_ctx* ctx, DVec<T>& v, size_t n, size_t keep = 0) {
+  if (n <= v.cap && v.p) return PMVSB_OK;
+  const size_t want = n + n / 2 + 4096;
+  T* np = nullptr;
+  CK(cudaMalloc((void**)&np, sizeof(T) * want));
+  if (keep && v.p) CK(cudaMemcpyAsync(np, v.p, sizeof(T) * keep, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(v.p);
+  v.p = np; v.cap = want;
+  return PMVSB_OK;
+}
+template <typename T>
+static int dvec_put(pmvsb_ctx* ctx, DVec<T>& v, size_t at, const T* src, size_t n) {
+  int r = dvec_reserve(ctx, v, at + n, at);
+  if (r) return r;
+  if (n) CK(cudaMemcpyAsync(v.p + at, src, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
+  return PMVSB_OK;
+}
+static void store_free(pmvsb_ctx* ctx) {
+  StoreBufs& b = ctx->sb;
+  for (DVec<float>* v : {&b.coords, &b.normals, &b.ncc, &b.dscale}) { cudaFree(v->p); v->p = nullptr; v->cap = 0; }
+  for (DVec<int32_t>* v : {&b.timages, &b.img_off, &b.images, &b.grids, &b.entry_patch, &b.vimg_off, &b.vimages, &b.vgrids, &b.ventry_patch,
+                           &b.alt_voff, &b.alt_vimages, &b.alt_vgrids, &b.cell_base, &b.gw, &b.gh, &b.cell_off, &b.cell_patch, &b.vcell_off,
+                           &b.vcell_patch, &b.cursor, &b.tile_sums, &b.counts}) { cudaFree(v->p); v->p = nullptr; v->cap = 0; }
+  cudaFree(b.dp.p); b.dp.p = nullptr; b.dp.cap = 0;
+}
+static void store_view(pmvsb_ctx* ctx) {   // device pointers may have moved: refresh the struct the kernels take
+  StoreDev& st = ctx->store;
+  const StoreBufs& b = ctx->sb;
+  st.coords = b.coords.p; st.normals = b.normals.p; st.ncc = b.ncc.p; st.dscale = b.dscale.p; st.timages = b.timages.p;
+  st.img_off = b.img_off.p; st.images = b.images.p; st.grids = b.grids.p; st.entry_patch = b.entry_patch.p;
+  st.vimg_off = b.vimg_off.p; st.vimages = b.vimages.p; st.vgrids = b.vgrids.p;
+  st.cell_base = b.cell_base.p; st.gw = b.gw.p; st.gh = b.gh.p;
+  st.cell_off = b.cell_off.p; st.cell_patch = b.cell_patch.p; st.vcell_off = b.vcell_off.p; st.vcell_patch = b.vcell_patch.p;
+  st.dp = b.dp.p;
+}
+// exclusive scan of n int32 in place (n includes the trailing total slot)
+static int device_scan(pmvsb_ctx* ctx, int32_t* data, int n) {
+  const int tiles = (n + kScanTile - 1) / kScanTile;
+  int r = dvec_reserve(ctx, ctx->sb.tile_sums, (size_t)tiles);
+  if (r) return r;
+  k_scan_tile_sums<<<tiles, kScanThreads, 0, ctx->stream>>>(data, n, ctx->sb.tile_sums.p);
+  k_scan_spine<<<1, kScanThreads, 0, ctx->stream>>>(ctx->sb.tile_sums.p, tiles);
+  k_scan_apply<<<tiles, kScanThreads, 0, ctx->stream>>>(data, n, ctx->sb.tile_sums.p, data);
+  ctx->launches += 3;
+  CK(cudaGetLastError());
+  return PMVSB_OK;
+}
+// _pgrids (visible = false) or _vpgrids (true) of the whole table as CSR over the flattened cells
+static int build_cell_lists(pmvsb_ctx* ctx, bool visible) {
+  StoreBufs& b = ctx->sb;
+  const int cells = ctx->store_cells, E = visible ? ctx->store_ventries : ctx->store_entries;
+  DVec<int32_t>& off = visible ? b.vcell_off : b.cell_off;
+  DVec<int32_t>& lst = visible ? b.vcell_patch : b.cell_patch;
+  const int32_t* images = visible ? b.vimages.p : b.images.p;
+  const int32_t* grids = visible ? b.vgrids.p : b.grids.p;
+  const int32_t* owner = visible ? b.ventry_patch.p : b.entry_patch.p;
+  int r;
+  if ((r = dvec_reserve(ctx, off, (size_t)cells + 1))) return r;
+  if ((r = dvec_reserve(ctx, lst, (size_t)std::max(E, 1)))) return r;
+  if ((r = dvec_reserve(ctx, b.cursor, (size_t)cells + 1))) return r;
+  CK(cudaMemsetAsync(off.p, 0, sizeof(int32_t) * ((size_t)cells + 1), ctx->stream));
+  CK(cudaMemsetAsync(b.cursor.p, 0, sizeof(int32_t) * ((size_t)cells + 1), ctx->stream));
+  if (E > 0) {
+    k_cells_count<<<(E + 255) / 256, 256, 0, ctx->stream>>>(ctx->tnum, E, images, grids, b.cell_base.p, b.gw.p, off.p);
+    ++ctx->launches;
+  }
+  if ((r = device_scan(ctx, off.p, cells + 1))) return r;
+  if (E > 0) {
+    k_cells_fill<<<(E + 255) / 256, 256, 0, ctx->stream>>>(ctx->tnum, E, images, grids, owner, b.cell_base.p, b.gw.p, off.p, b.cursor.p, lst.p);
+    k_cells_sort<<<(cells + 255) / 256, 256, 0, ctx->stream>>>(cells, off.p, lst.p);
+    ctx->launches += 2;
+  }
+  CK(cudaGetLastError());
+  store_view(ctx);
+  return PMVSB_OK;
+}
+// validates the lists of `count` patches (offsets relative to off[0]); the kernels trust every index afterwards
+static int check_lists(pmvsb_ctx* ctx, const char* who, int count, const int32_t* off, const int32_t* images, const int32_t* grids, bool visible) {
+  for (int p = 0; p < count; ++p) {
+    if (off[p + 1] < off[p]) return fail(ctx, PMVSB_EINVAL, std::string(who) + ": offsets not monotone");
+    for (int e = off[p] - off[0]; e < off[p + 1] - off[0]; ++e) {
+      const int im = images[e];
+      if (im < 0 || im >= (visible ? ctx->tnum : ctx->num)) return fail(ctx, PMVSB_EINVAL, std::string(who) + (visible ? ": vimage index out of range" : ": image index out of range"));
+      if (im < ctx->tnum) {
+        const int x = grids[2 * e], y = grids[2 * e + 1];
+        if (x < 0 || x >= ctx->h_gw[im] || y < 0 || y >= ctx->h_gh[im]) return fail(ctx, PMVSB_EINVAL, std::string(who) + (visible ? ": vgrid cell out of range" : ": grid cell out of range"));
+      }
+    }
+  }
   return PMVSB_OK;
 }
 
@@ -848,7 +944,7 @@ int pmvsb_destroy(pmvsb_ctx* ctx) {
     for (auto* p : im.levels) cudaFree(p);
   cudaFree(ctx->d_cams); cudaFree(ctx->d_levels); cudaFree(ctx->d_counter); cudaFree(ctx->d_vis_off); cudaFree(ctx->d_vis_idx);
   cudaFree(ctx->arena);
-  cudaFree(ctx->store_arena);
+  store_free(ctx);
   for (auto& b : ctx->pool) cudaFree(b.second);
   g_current = nullptr;
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1197,84 +1293,41 @@ int pmvsb_store_upload(pmvsb_ctx* ctx, int P, const float* coords, const float* 
   if (r) return r;
   if (P < 0 || !coords || !normals || !ncc || !dscale || !img_off || !vimg_off || !timages) return fail(ctx, PMVSB_EINVAL, "store_upload: null pointer");
   const int E = img_off[P], VE = vimg_off[P];
+  if (img_off[0] != 0 || vimg_off[0] != 0) return fail(ctx, PMVSB_EINVAL, "store_upload: offsets must start at 0");
   if ((E > 0 && (!images || !grids)) || (VE > 0 && (!vimages || !vgrids))) return fail(ctx, PMVSB_EINVAL, "store_upload: null list");
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->store_set = false; ctx->depth_built = false; ctx->store_appended = false;
-  // grid geometry + _pgrids as CSR (patchOrganizerS.cpp:315-331); validate every index the kernels will trust
-  std::vector<int32_t> gw(ctx->num), gh(ctx->num), base(ctx->tnum + 1, 0);
-  for (int i = 0; i < ctx->num; ++i) {
-    gw[i] = (ctx->images[i].w[ctx->level] + ctx->csize - 1) / ctx->csize;
-    gh[i] = (ctx->images[i].h[ctx->level] + ctx->csize - 1) / ctx->csize;
+  StoreBufs& b = ctx->sb;
+  if (ctx->h_gw.empty()) {   // grid geometry (patchOrganizerS.cpp:72-77), once per scene
+    ctx->h_gw.resize(ctx->num); ctx->h_gh.resize(ctx->num); ctx->h_base.assign(ctx->tnum + 1, 0);
+    for (int i = 0; i < ctx->num; ++i) {
+      ctx->h_gw[i] = (ctx->images[i].w[ctx->level] + ctx->csize - 1) / ctx->csize;
+      ctx->h_gh[i] = (ctx->images[i].h[ctx->level] + ctx->csize - 1) / ctx->csize;
+    }
+    for (int i = 0; i < ctx->tnum; ++i) ctx->h_base[i + 1] = ctx->h_base[i] + ctx->h_gw[i] * ctx->h_gh[i];
+    if ((r = dvec_put(ctx, b.cell_base, 0, ctx->h_base.data(), ctx->h_base.size()))) return r;
+    if ((r = dvec_put(ctx, b.gw, 0, ctx->h_gw.data(), ctx->h_gw.size()))) return r;
+    if ((r = dvec_put(ctx, b.gh, 0, ctx->h_gh.data(), ctx->h_gh.size()))) return r;
+    if ((r = dvec_reserve(ctx, b.dp, (size_t)std::max(ctx->h_base[ctx->tnum], 1)))) return r;
   }
-  for (int i = 0; i < ctx->tnum; ++i) base[i + 1] = base[i] + gw[i] * gh[i];
-  const int cells = base[ctx->tnum];
-  std::vector<int32_t> entry_patch(E), cell_off(cells + 1, 0);
-  for (int p = 0; p < P; ++p) {
-    if (img_off[p + 1] < img_off[p] || vimg_off[p + 1] < vimg_off[p]) return fail(ctx, PMVSB_EINVAL, "store_upload: offsets not monotone");
-    for (int e = img_off[p]; e < img_off[p + 1]; ++e) {
-      const int im = images[e];
-      if (im < 0 || im >= ctx->num) return fail(ctx, PMVSB_EINVAL, "store_upload: image index out of range");
-      entry_patch[e] = p;
-      if (im < ctx->tnum) {
-        const int x = grids[2 * e], y = grids[2 * e + 1];
-        if (x < 0 || x >= gw[im] || y < 0 || y >= gh[im]) return fail(ctx, PMVSB_EINVAL, "store_upload: grid cell out of range");
-        cell_off[base[im] + y * gw[im] + x + 1]++;
-      }
-    }
-    for (int e = vimg_off[p]; e < vimg_off[p + 1]; ++e) {
-      const int im = vimages[e];
-      if (im < 0 || im >= ctx->tnum) return fail(ctx, PMVSB_EINVAL, "store_upload: vimage index out of range");
-      const int x = vgrids[2 * e], y = vgrids[2 * e + 1];
-      if (x < 0 || x >= gw[im] || y < 0 || y >= gh[im]) return fail(ctx, PMVSB_EINVAL, "store_upload: vgrid cell out of range");
-    }
-  }
-  for (int i = 0; i < cells; ++i) cell_off[i + 1] += cell_off[i];
-  std::vector<int32_t> cell_patch(cell_off[cells] ? cell_off[cells] : 1), fill(cells, 0);
-  for (int p = 0; p < P; ++p)
-    for (int e = img_off[p]; e < img_off[p + 1]; ++e) {
-      const int im = images[e];
-      if (im >= ctx->tnum) continue;
-      const int cell = base[im] + grids[2 * e + 1] * gw[im] + grids[2 * e];
-      cell_patch[cell_off[cell] + fill[cell]++] = p;
-    }
+  const int cells = ctx->h_base[ctx->tnum];
+  if ((r = check_lists(ctx, "store_upload", P, img_off, images, grids, false))) return r;
+  if ((r = check_lists(ctx, "store_upload", P, vimg_off, vimages, vgrids, true))) return r;
+  if ((r = dvec_put(ctx, b.coords, 0, coords, (size_t)4 * P))) return r;
+  if ((r = dvec_put(ctx, b.normals, 0, normals, (size_t)4 * P))) return r;
+  if ((r = dvec_put(ctx, b.ncc, 0, ncc, (size_t)P))) return r;
+  if ((r = dvec_put(ctx, b.dscale, 0, dscale, (size_t)P))) return r;
+  if ((r = dvec_put(ctx, b.timages, 0, timages, (size_t)P))) return r;
+  if ((r = dvec_put(ctx, b.img_off, 0, img_off, (size_t)P + 1))) return r;
+  if ((r = dvec_put(ctx, b.images, 0, images, (size_t)E))) return r;
+  if ((r = dvec_put(ctx, b.grids, 0, grids, (size_t)2 * E))) return r;
+  if ((r = dvec_put(ctx, b.vimg_off, 0, vimg_off, (size_t)P + 1))) return r;
+  if ((r = dvec_put(ctx, b.vimages, 0, vimages, (size_t)VE))) return r;
+  if ((r = dvec_put(ctx, b.vgrids, 0, vgrids, (size_t)2 * VE))) return r;
+  if ((r = dvec_reserve(ctx, b.entry_patch, (size_t)std::max(E, 1)))) return r;
+  if ((r = dvec_reserve(ctx, b.ventry_patch, (size_t)std::max(VE, 1)))) return r;
   StoreDev& st = ctx->store;
   st.P = P;
-  {
-    const int ccap = P + P / 2 + 65536;
-    const size_t need = (size_t)ccap * 16 + (size_t)P * (16 + 4 + 4 + 4 + 8) + (size_t)E * (4 + 8 + 4 + 4) + (size_t)VE * 12 +
-                        (size_t)cells * (4 + 8) + (size_t)ctx->num * 12 + 64 * 256;
-    if (need > ctx->store_cap) {
-      cudaFree(ctx->store_arena);
-      ctx->store_arena = nullptr; ctx->store_cap = 0;
-      const size_t want = need + need / 2;
-      CK(cudaMalloc((void**)&ctx->store_arena, want));
-      ctx->store_cap = want;
-    }
-    ctx->store_used = 0;
-    ctx->coords_cap = ccap;
-  }
-  if ((r = store_put(ctx, st.coords, coords, (size_t)4 * P, (size_t)4 * ctx->coords_cap))) return r;
-  if ((r = store_put(ctx, st.normals, normals, (size_t)4 * P))) return r;
-  if ((r = store_put(ctx, st.ncc, ncc, (size_t)P))) return r;
-  if ((r = store_put(ctx, st.dscale, dscale, (size_t)P))) return r;
-  if ((r = store_put(ctx, st.img_off, img_off, (size_t)P + 1))) return r;
-  if ((r = store_put(ctx, st.images, images, (size_t)E))) return r;
-  if ((r = store_put(ctx, st.grids, grids, (size_t)2 * E))) return r;
-  if ((r = store_put(ctx, st.entry_patch, entry_patch.data(), (size_t)E))) return r;
-  if ((r = store_put(ctx, st.vimg_off, vimg_off, (size_t)P + 1))) return r;
-  if ((r = store_put(ctx, st.vimages, vimages, (size_t)VE))) return r;
-  if ((r = store_put(ctx, st.vgrids, vgrids, (size_t)2 * VE))) return r;
-  if ((r = store_put(ctx, st.timages, timages, (size_t)P))) return r;
-  if ((r = store_put(ctx, st.cell_base, base.data(), base.size()))) return r;
-  if ((r = store_put(ctx, st.gw, gw.data(), gw.size()))) return r;
-  if ((r = store_put(ctx, st.gh, gh.data(), gh.size()))) return r;
-  if ((r = store_put(ctx, st.cell_off, cell_off.data(), cell_off.size()))) return r;
-  if ((r = store_put(ctx, st.cell_patch, cell_patch.data(), cell_patch.size()))) return r;
-  {
-    const unsigned long long* dpc = nullptr;
-    if ((r = store_put<unsigned long long>(ctx, dpc, nullptr, 0, (size_t)(cells ? cells : 1)))) return r;
-    st.dp = const_cast<unsigned long long*>(dpc);
-  }
   st.depth_flag = ctx->depth_flag;
   st.ncc_threshold = ctx->ncc_threshold;
   const double c120 = std::cos(120.0 * M_PI / 180.0);   // findMatch.cpp:126
@@ -1282,8 +1335,64 @@ int pmvsb_store_upload(pmvsb_ctx* ctx, int P, const float* coords, const float* 
   if ((double)cf < c120) cf = std::nextafterf(cf, INFINITY);
   st.cos120_f = cf;
   ctx->store_entries = E; ctx->store_ventries = VE; ctx->store_cells = cells;
-  CK(cudaStreamSynchronize(ctx->stream));   // host vectors above go out of scope
+  store_view(ctx);
+  if (P > 0) {
+    k_entry_owner<<<(P + 255) / 256, 256, 0, ctx->stream>>>(0, P, b.img_off.p, b.entry_patch.p);
+    k_entry_owner<<<(P + 255) / 256, 256, 0, ctx->stream>>>(0, P, b.vimg_off.p, b.ventry_patch.p);
+    ctx->launches += 2;
+  }
+  if ((r = build_cell_lists(ctx, false))) return r;
+  if ((r = build_cell_lists(ctx, true))) return r;
+  CK(cudaStreamSynchronize(ctx->stream));   // the caller's host buffers are free again
   ctx->store_set = true;
+  return PMVSB_OK;
+}
+
+static int need_store(pmvsb_ctx* ctx, bool depth);
+
+int pmvsb_store_append(pmvsb_ctx* ctx, int n, const float* coords, const float* normals, const float* ncc, const float* dscale,
+                       const int32_t* img_off, const int32_t* images, const int32_t* grids, const int32_t* vimg_off,
+                       const int32_t* vimages, const int32_t* vgrids, const int32_t* timages) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  if (n < 0 || (n > 0 && (!coords || !normals || !ncc || !dscale || !img_off || !vimg_off || !timages))) return fail(ctx, PMVSB_EINVAL, "store_append: bad argument");
+  if (n == 0) return PMVSB_OK;
+  const int dE = img_off[n] - img_off[0], dVE = vimg_off[n] - vimg_off[0];
+  if ((dE > 0 && (!images || !grids)) || (dVE > 0 && (!vimages || !vgrids))) return fail(ctx, PMVSB_EINVAL, "store_append: null list");
+  if ((r = check_lists(ctx, "store_append", n, img_off, images, grids, false))) return r;
+  if ((r = check_lists(ctx, "store_append", n, vimg_off, vimages, vgrids, true))) return r;
+  StoreBufs& b = ctx->sb;
+  const int P = ctx->store.P, E = ctx->store_entries, VE = ctx->store_ventries;
+  std::vector<int32_t> off(n), voff(n);
+  for (int i = 0; i < n; ++i) { off[i] = E + img_off[i + 1] - img_off[0]; voff[i] = VE + vimg_off[i + 1] - vimg_off[0]; }
+  if ((r = dvec_put(ctx, b.coords, (size_t)4 * P, coords, (size_t)4 * n))) return r;
+  if ((r = dvec_put(ctx, b.normals, (size_t)4 * P, normals, (size_t)4 * n))) return r;
+  if ((r = dvec_put(ctx, b.ncc, (size_t)P, ncc, (size_t)n))) return r;
+  if ((r = dvec_put(ctx, b.dscale, (size_t)P, dscale, (size_t)n))) return r;
+  if ((r = dvec_put(ctx, b.timages, (size_t)P, timages, (size_t)n))) return r;
+  if ((r = dvec_put(ctx, b.img_off, (size_t)P + 1, off.data(), (size_t)n))) return r;
+  if ((r = dvec_put(ctx, b.images, (size_t)E, images, (size_t)dE))) return r;
+  if ((r = dvec_put(ctx, b.grids, (size_t)2 * E, grids, (size_t)2 * dE))) return r;
+  if ((r = dvec_put(ctx, b.vimg_off, (size_t)P + 1, voff.data(), (size_t)n))) return r;
+  if ((r = dvec_put(ctx, b.vimages, (size_t)VE, vimages, (size_t)dVE))) return r;
+  if ((r = dvec_put(ctx, b.vgrids, (size_t)2 * VE, vgrids, (size_t)2 * dVE))) return r;
+  if ((r = dvec_reserve(ctx, b.entry_patch, (size_t)E + dE, (size_t)E))) return r;
+  if ((r = dvec_reserve(ctx, b.ventry_patch, (size_t)std::max(VE + dVE, 1), (size_t)VE))) return r;
+  store_view(ctx);
+  k_entry_owner<<<(n + 255) / 256, 256, 0, ctx->stream>>>(P, n, b.img_off.p, b.entry_patch.p);
+  k_entry_owner<<<(n + 255) / 256, 256, 0, ctx->stream>>>(P, n, b.vimg_off.p, b.ventry_patch.p);
+  ctx->launches += 2;
+  ctx->store_entries = E + dE; ctx->store_ventries = VE + dVE;
+  if ((r = build_cell_lists(ctx, false))) return r;
+  if ((r = build_cell_lists(ctx, true))) return r;
+  if (ctx->depth_built) {   // CPatchOrganizerS::updateDepthMaps (patchOrganizerS.cpp:351-381)
+    const long long t = (long long)n * ctx->tnum;
+    k_depth_maps<<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(ctx->scene, ctx->store, P, n);
+    ++ctx->launches;
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->store.P = P + n;
   return PMVSB_OK;
 }
 
@@ -1292,7 +1401,7 @@ static int need_store(pmvsb_ctx* ctx, bool depth) {
   if (r) return r;
   if (!ctx->store_set) return fail(ctx, PMVSB_ESTATE, "no patch table: call pmvsb_store_upload first");
   if (depth && ctx->depth_flag != 0 && !ctx->depth_built) return fail(ctx, PMVSB_ESTATE, "depth maps not built: call pmvsb_build_depth_maps first");
-  if (!depth && ctx->store_appended) return fail(ctx, PMVSB_ESTATE, "table was extended by pmvsb_depth_maps_add: upload it again before gains / filterExact");
+  if (!depth && ctx->store_appended) return fail(ctx, PMVSB_ESTATE, "table was extended by pmvsb_depth_maps_add (coordinates only): upload it again first");
   ctx->store.depth_flag = ctx->depth_flag;
   ctx->store.ncc_threshold = ctx->ncc_threshold;
   return PMVSB_OK;
@@ -1319,9 +1428,8 @@ int pmvsb_depth_maps_add(pmvsb_ctx* ctx, int n, const float* coords) {
   if (n < 0 || (n > 0 && !coords)) return fail(ctx, PMVSB_EINVAL, "depth_maps_add: bad argument");
   if (!ctx->depth_built) return fail(ctx, PMVSB_ESTATE, "depth maps not built: call pmvsb_build_depth_maps first");
   if (n == 0) return PMVSB_OK;
-  if (ctx->store.P + n > ctx->coords_cap) return fail(ctx, PMVSB_ENOMEM, "depth_maps_add: table capacity exhausted, upload the table again");
-  float* dst = const_cast<float*>(ctx->store.coords) + (size_t)4 * ctx->store.P;
-  CK(cudaMemcpyAsync(dst, coords, sizeof(float) * 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  if ((r = dvec_put(ctx, ctx->sb.coords, (size_t)4 * ctx->store.P, coords, (size_t)4 * n))) return r;
+  store_view(ctx);
   const long long t = (long long)n * ctx->tnum;
   k_depth_maps<<<(unsigned)((t + 255) / 256), 256, 0, ctx->stream>>>(ctx->scene, ctx->store, ctx->store.P, n);
   ++ctx->launches;
@@ -1396,6 +1504,115 @@ int pmvsb_compute_gains_store(pmvsb_ctx* ctx, float* gains) {
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(gains, dg.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_store_update_vimages(pmvsb_ctx* ctx, int additive, int32_t* total) {
+  int r = need_store(ctx, true);
+  if (r) return r;
+  if (ctx->store_appended) return fail(ctx, PMVSB_ESTATE, "table was extended by pmvsb_depth_maps_add (coordinates only): upload it again first");
+  StoreBufs& b = ctx->sb;
+  const int P = ctx->store.P;
+  if (total) *total = 0;
+  if (P == 0) return PMVSB_OK;
+  if ((r = dvec_reserve(ctx, b.alt_voff, (size_t)P + 1))) return r;
+  CK(cudaMemsetAsync(b.alt_voff.p + P, 0, sizeof(int32_t), ctx->stream));
+  k_store_vimages<false><<<(P + 3) / 4, 128, 0, ctx->stream>>>(ctx->scene, ctx->store, additive, b.alt_voff.p, nullptr, nullptr, nullptr);
+  ++ctx->launches;
+  if ((r = device_scan(ctx, b.alt_voff.p, P + 1))) return r;
+  int32_t VE = 0;
+  CK(cudaMemcpyAsync(&VE, b.alt_voff.p + P, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if ((r = dvec_reserve(ctx, b.alt_vimages, (size_t)std::max(VE, 1)))) return r;
+  if ((r = dvec_reserve(ctx, b.alt_vgrids, (size_t)2 * std::max(VE, 1)))) return r;
+  k_store_vimages<true><<<(P + 3) / 4, 128, 0, ctx->stream>>>(ctx->scene, ctx->store, additive, nullptr, b.alt_voff.p, b.alt_vimages.p, b.alt_vgrids.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  std::swap(b.vimg_off, b.alt_voff); std::swap(b.vimages, b.alt_vimages); std::swap(b.vgrids, b.alt_vgrids);
+  ctx->store_ventries = VE;
+  if ((r = dvec_reserve(ctx, b.ventry_patch, (size_t)std::max(VE, 1)))) return r;
+  store_view(ctx);
+  k_entry_owner<<<(P + 255) / 256, 256, 0, ctx->stream>>>(0, P, b.vimg_off.p, b.ventry_patch.p);
+  ++ctx->launches;
+  if ((r = build_cell_lists(ctx, true))) return r;
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (total) *total = VE;
+  return PMVSB_OK;
+}
+
+int pmvsb_store_download_vimages(pmvsb_ctx* ctx, int32_t* vimg_off, int32_t* vimages, int32_t* vgrids) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  if (!vimg_off || ((!vimages || !vgrids) && ctx->store_ventries > 0)) return fail(ctx, PMVSB_EINVAL, "store_download_vimages: null pointer");
+  const int P = ctx->store.P, VE = ctx->store_ventries;
+  CK(cudaMemcpyAsync(vimg_off, ctx->sb.vimg_off.p, sizeof(int32_t) * ((size_t)P + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  if (VE > 0) {
+    CK(cudaMemcpyAsync(vimages, ctx->sb.vimages.p, sizeof(int32_t) * (size_t)VE, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(vgrids, ctx->sb.vgrids.p, sizeof(int32_t) * (size_t)2 * VE, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_download_cell_lists(pmvsb_ctx* ctx, int visible, int32_t* cell_off, int32_t* cell_patch) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  if (!cell_off) return fail(ctx, PMVSB_EINVAL, "download_cell_lists: null pointer");
+  const int cells = ctx->store_cells;
+  const DVec<int32_t>& off = visible ? ctx->sb.vcell_off : ctx->sb.cell_off;
+  const DVec<int32_t>& lst = visible ? ctx->sb.vcell_patch : ctx->sb.cell_patch;
+  CK(cudaMemcpyAsync(cell_off, off.p, sizeof(int32_t) * ((size_t)cells + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (cell_patch && cell_off[cells] > 0) {
+    CK(cudaMemcpyAsync(cell_patch, lst.p, sizeof(int32_t) * (size_t)cell_off[cells], cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return PMVSB_OK;
+}
+
+int pmvsb_find_empty_blocks_store(pmvsb_ctx* ctx, int n, const int32_t* ids, uint8_t* mask, float* radius) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  if (n < 0 || (n > 0 && (!ids || !mask || !radius))) return fail(ctx, PMVSB_EINVAL, "find_empty_blocks_store: bad argument");
+  if (n == 0) return PMVSB_OK;
+  for (int i = 0; i < n; ++i)
+    if (ids[i] < 0 || ids[i] >= ctx->store.P) return fail(ctx, PMVSB_EINVAL, "find_empty_blocks_store: patch index out of range");
+  DevBuf<int32_t> di;
+  DevBuf<uint8_t> dm;
+  DevBuf<float> dr;
+  CK(di.alloc(n)); CK(dm.alloc(n)); CK(dr.alloc(n));
+  CK(cudaMemcpyAsync(di.p, ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  k_find_empty_blocks<<<(n + 3) / 4, 128, 0, ctx->stream>>>(ctx->scene, ctx->store, n, di.p, dm.p, dr.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(mask, dm.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(radius, dr.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_filter_neighbor_store(pmvsb_ctx* ctx, float quad, uint8_t* reject, float* residual, int32_t* ncount, int32_t* overflow) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  if (!reject) return fail(ctx, PMVSB_EINVAL, "filter_neighbor_store: null pointer");
+  if (overflow) *overflow = 0;
+  const int P = ctx->store.P;
+  if (P == 0) return PMVSB_OK;
+  DevBuf<uint8_t> dj;
+  DevBuf<float> dres;
+  DevBuf<int32_t> dn, dov;
+  CK(dj.alloc(P)); CK(dres.alloc(P)); CK(dn.alloc(P)); CK(dov.alloc(1));
+  CK(cudaMemsetAsync(dov.p, 0, sizeof(int32_t), ctx->stream));
+  k_filter_neighbor<<<(P + kNbWarps - 1) / kNbWarps, kNbWarps * 32, 0, ctx->stream>>>(ctx->scene, ctx->store, quad, ctx->tau, dj.p, dres.p, dn.p, dov.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(reject, dj.p, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+  if (residual) CK(cudaMemcpyAsync(residual, dres.p, sizeof(float) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ncount) CK(cudaMemcpyAsync(ncount, dn.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+  int32_t ov = 0;
+  CK(cudaMemcpyAsync(&ov, dov.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (overflow) *overflow = ov;
   return PMVSB_OK;
 }
 

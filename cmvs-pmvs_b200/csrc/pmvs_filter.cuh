@@ -29,6 +29,8 @@ struct StoreDev {               // the patch table (CPatch fields the filter sta
   const int32_t* gh;
   const int32_t* cell_off;      // _pgrids as CSR over flattened cells
   const int32_t* cell_patch;
+  const int32_t* vcell_off;     // _vpgrids likewise (patches that only SEE the cell, patchOrganizerS.cpp:333-346)
+  const int32_t* vcell_patch;
   unsigned long long* dp;       // depth map: (orderable depth << 32 | patch id) per flattened cell, ~0 = empty
   int depth_flag;               // CFindMatch::_depth
   float ncc_threshold;

@@ -124,6 +124,13 @@ int pmvsb_grid_dims(pmvsb_ctx* ctx, int image, int* gwidth, int* gheight);   /* 
 int pmvsb_store_upload(pmvsb_ctx* ctx, int P, const float* coords, const float* normals, const float* ncc, const float* dscale,
                        const int32_t* img_off, const int32_t* images, const int32_t* grids,
                        const int32_t* vimg_off, const int32_t* vimages, const int32_t* vgrids, const int32_t* timages);
+/* CPatchOrganizerS::addPatch for n patches committed since the last upload (patchOrganizerS.cpp:312-349): full
+ * records are appended (table ids P, P+1, ...; offsets relative to img_off[0] / vimg_off[0]), the cell lists are
+ * rebuilt on the device and, once depth maps exist, the new patches are merged into them (updateDepthMaps,
+ * patchOrganizerS.cpp:351-381).  Every store call stays valid on the extended table. */
+int pmvsb_store_append(pmvsb_ctx* ctx, int n, const float* coords, const float* normals, const float* ncc, const float* dscale,
+                       const int32_t* img_off, const int32_t* images, const int32_t* grids,
+                       const int32_t* vimg_off, const int32_t* vimages, const int32_t* vgrids, const int32_t* timages);
 /* CFilter::setDepthMaps (source/pmvs/filter.cpp:667-732): nearest patch per cell of every target image */
 int pmvsb_build_depth_maps(pmvsb_ctx* ctx);
 int pmvsb_download_depth_map(pmvsb_ctx* ctx, int image, int32_t* patch_id);   /* gw*gh ids, -1 = empty */
@@ -135,6 +142,25 @@ int pmvsb_depth_maps_add(pmvsb_ctx* ctx, int n, const float* coords);
 /* CPatchOrganizerS::setVImagesVGrids (patchOrganizerS.cpp:420-450) for every table patch, from an empty _vimages:
  * vimages int32[vcap*P], vgrids int32[2*vcap*P], nv int32[P] */
 int pmvsb_set_vimages_store(pmvsb_ctx* ctx, int vcap, int32_t* vimages, int32_t* vgrids, int32_t* nv);
+/* CFilter::setDepthMapsVGridsVPGridsAddPatchV (filter.cpp:734-783): setVImagesVGrids for every table patch written
+ * into the table's own _vimages/_vgrids (additive = 0: from empty lists, 1: keep and append), _vpgrids rebuilt.
+ * total = number of (patch, visible image) entries afterwards; pmvsb_store_download_vimages returns them as CSR
+ * (vimg_off int32[P+1], vimages int32[total], vgrids int32[2*total]). */
+int pmvsb_store_update_vimages(pmvsb_ctx* ctx, int additive, int32_t* total);
+int pmvsb_store_download_vimages(pmvsb_ctx* ctx, int32_t* vimg_off, int32_t* vimages, int32_t* vgrids);
+/* _pgrids (visible = 0) / _vpgrids (1) of the table as the device built them: cell_off int32[cells+1] over the
+ * flattened cells of the target images in image order, cell_patch int32[cell_off[cells]] (may be NULL) -- parity hook */
+int pmvsb_download_cell_lists(pmvsb_ctx* ctx, int visible, int32_t* cell_off, int32_t* cell_patch);
+/* CExpand::findEmptyBlocks (source/pmvs/expand.cpp:108-180) for n table patches: bit i of mask[k] is set when
+ * direction i (angle 2 pi i / 6 in the ortho(normal) frame) already has a neighbour from
+ * findNeighbors(patch, scale 4, margin 1) at in-plane distance in [r/6, 2.5 r]; radius[k] = r = computeRadius
+ * (expand.cpp:182-198).  The caller places candidates in the clear directions. */
+int pmvsb_find_empty_blocks_store(pmvsb_ctx* ctx, int n, const int32_t* ids, uint8_t* mask, float* radius);
+/* CFilter::filterNeighborThread + filterQuad (filter.cpp:357-462) for every table patch: reject[k] = 1 when the
+ * patch has fewer than 6 neighbours (findNeighbors scale 4, margin 2, skipvis 1) or its quadric-fit residual is
+ * >= quad.  Optional outputs: residual float[P] (-1 = too few neighbours), ncount int32[P] unique neighbours,
+ * overflow = patches whose neighbour set did not fit on chip (kept, never silently rejected). */
+int pmvsb_filter_neighbor_store(pmvsb_ctx* ctx, float quad, uint8_t* reject, float* residual, int32_t* ncount, int32_t* overflow);
 /* CFilter::filterExactThread's visibility re-test (filter.cpp:315-343): safe uint8[E], one flag per image entry */
 int pmvsb_filter_exact_store(pmvsb_ctx* ctx, uint8_t* safe);
 /* CFilter::filterOutsideThread / computeGain (filter.cpp:88-201): gains float[P] */

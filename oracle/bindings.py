@@ -272,6 +272,25 @@ class OracleLib(_Common):
         f = self.lib.pmvso_compute_gain; f.restype = C.c_float
         return np.float32(f(self.ctx, int(k)))
 
+    def compute_radius(self, k):
+        f = self.lib.pmvso_compute_radius; f.restype = C.c_float
+        return np.float32(f(self.ctx, int(k)))
+
+    def find_neighbors(self, k, scale, margin, skipvis, cap=4096):
+        out = np.zeros(cap, np.int32)
+        n = self.lib.pmvso_find_neighbors(self.ctx, int(k), C.c_float(scale), int(margin), int(skipvis), out.ctypes.data_as(C.c_void_p), cap)
+        return out[:min(n, cap)].copy()
+
+    def find_empty_blocks(self, k):
+        r = C.c_float()
+        m = self.lib.pmvso_find_empty_blocks(self.ctx, int(k), C.byref(r))
+        return int(m), np.float32(r.value)
+
+    def filter_neighbor(self, k, quad=2.5):
+        res = C.c_float(); cnt = C.c_int()
+        rej = self.lib.pmvso_filter_neighbor(self.ctx, int(k), C.c_float(quad), C.byref(res), C.byref(cnt))
+        return int(rej), np.float32(res.value), cnt.value
+
     def close(self):
         if self.ctx:
             self.lib.pmvso_destroy(self.ctx)
@@ -389,6 +408,23 @@ class RefLib(_Common):
     def compute_gain(self, k):
         f = self.lib.ref_compute_gain; f.restype = C.c_float
         return np.float32(f(int(k)))
+
+    def compute_radius(self, k):
+        f = self.lib.ref_compute_radius; f.restype = C.c_float
+        return np.float32(f(int(k)))
+
+    def find_neighbors(self, k, scale, margin, skipvis, cap=4096):
+        out = np.zeros(cap, np.int32)
+        n = self.lib.ref_find_neighbors(int(k), C.c_float(scale), int(margin), int(skipvis), out.ctypes.data_as(C.c_void_p), cap)
+        return out[:min(n, cap)].copy()
+
+    def find_empty_blocks(self, k):
+        return int(self.lib.ref_find_empty_blocks(int(k)))
+
+    def filter_neighbor(self, k, quad=2.5):
+        cnt = C.c_int()
+        rej = self.lib.ref_filter_neighbor(int(k), C.c_float(quad), C.byref(cnt))
+        return int(rej), cnt.value
 
     def depth_flag(self):
         return self.lib.ref_get_depth_flag()

@@ -48,6 +48,8 @@ struct pmvso_ctx {
   int* cell_off;   /* pgrids as CSR over (image, cell): cell_base[image] + cell */
   int* cell_base;
   int* cell_patch;
+  int* vcell_off;   /* _vpgrids as CSR (patchOrganizerS.cpp:333-346) */
+  int* vcell_patch;
 };
 
 /* ---------------------------------------------------------------- small vector helpers (f32, source order) */
@@ -932,6 +934,7 @@ void pmvso_store_set(pmvso_ctx* c, int P, const float* coords, const float* norm
                      const int* vimg_off, const int* vimages, const int* vgrids, const int* timages) {
   free(c->s_coords); free(c->s_normals); free(c->s_ncc); free(c->s_dscale); free(c->s_img_off); free(c->s_images); free(c->s_grids);
   free(c->s_vimg_off); free(c->s_vimages); free(c->s_vgrids); free(c->s_timages); free(c->cell_off); free(c->cell_base); free(c->cell_patch);
+  free(c->vcell_off); free(c->vcell_patch);
   c->P = P;
   c->s_coords = dup_mem(coords, sizeof(float) * 4 * P); c->s_normals = dup_mem(normals, sizeof(float) * 4 * P);
   c->s_ncc = dup_mem(ncc, sizeof(float) * P); c->s_dscale = dup_mem(dscale, sizeof(float) * P);
@@ -963,6 +966,24 @@ void pmvso_store_set(pmvso_ctx* c, int P, const float* coords, const float* norm
       int gw, gh; pmvso_grid_dims(c, im, &gw, &gh);
       const int cell = c->cell_base[im] + grids[2 * e + 1] * gw + grids[2 * e];
       c->cell_patch[c->cell_off[cell] + fill[cell]++] = p;
+    }
+  /* _vpgrids the same way, from _vimages / _vgrids */
+  c->vcell_off = (int*)calloc(total + 1, sizeof(int));
+  for (int p = 0; p < P; ++p)
+    for (int e = vimg_off[p]; e < vimg_off[p + 1]; ++e) {
+      const int im = vimages[e];
+      int gw, gh; pmvso_grid_dims(c, im, &gw, &gh);
+      c->vcell_off[c->cell_base[im] + vgrids[2 * e + 1] * gw + vgrids[2 * e] + 1]++;
+    }
+  for (int i = 0; i < total; ++i) c->vcell_off[i + 1] += c->vcell_off[i];
+  c->vcell_patch = (int*)malloc(sizeof(int) * (c->vcell_off[total] ? c->vcell_off[total] : 1));
+  memset(fill, 0, sizeof(int) * total);
+  for (int p = 0; p < P; ++p)
+    for (int e = vimg_off[p]; e < vimg_off[p + 1]; ++e) {
+      const int im = vimages[e];
+      int gw, gh; pmvso_grid_dims(c, im, &gw, &gh);
+      const int cell = c->cell_base[im] + vgrids[2 * e + 1] * gw + vgrids[2 * e];
+      c->vcell_patch[c->vcell_off[cell] + fill[cell]++] = p;
     }
   free(fill);
 }
@@ -1106,4 +1127,209 @@ float pmvso_compute_gain(const pmvso_ctx* c, int k) {
     gain -= maxpressure;
   }
   return gain;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * neighbour searches over the table: findNeighbors, findEmptyBlocks, filterNeighbor / filterQuad
+ * --------------------------------------------------------------------------------------------------------------- */
+/* Vec4f ortho (include/numeric/vec4.hpp:303-322) */
+static void ortho4(const float* z, float* x, float* y) {
+  x[0] = x[1] = x[2] = x[3] = 0.0f;
+  if (fabsf(z[0]) > 0.5f) { x[0] = z[1]; x[1] = -z[0]; x[2] = 0.0f; }
+  else if (fabsf(z[1]) > 0.5f) { x[1] = z[2]; x[2] = -z[1]; x[0] = 0.0f; }
+  else { x[2] = z[0]; x[0] = -z[2]; x[1] = 0.0f; }
+  unitize4(x);
+  y[0] = z[1] * x[2] - z[2] * x[1];
+  y[1] = z[2] * x[0] - z[0] * x[2];
+  y[2] = z[0] * x[1] - z[1] * x[0];
+  y[3] = 0.0f;
+}
+
+/* CExpand::computeRadius (expand.cpp:182-198) over COptim::computeUnits (optim.cpp:446-471) */
+float pmvso_compute_radius(const pmvso_ctx* c, int k) {
+  const float* X = c->s_coords + 4 * k; const float* N = c->s_normals + 4 * k;
+  float min1 = INFINITY, min2 = INFINITY;   /* nth_element(.., begin + 1, ..): the second smallest value */
+  const int n = c->s_img_off[k + 1] - c->s_img_off[k];
+  for (int e = c->s_img_off[k]; e < c->s_img_off[k + 1]; ++e) {
+    const int im = c->s_images[e];
+    float u = get_unit(c, im, X);
+    float ray[4];
+    for (int j = 0; j < 4; ++j) ray[j] = c->cams[im].centre[j] - X[j];
+    unitize4(ray);
+    const float denom = dot4(ray, N);
+    if (0.0 < denom) u /= denom; else u = (float)(INT_MAX / 2);
+    if (u < min1) { min2 = min1; min1 = u; } else if (u < min2) min2 = u;
+  }
+  if (n >= 2) return min2 * c->csize;
+  return n == 1 ? min1 * c->csize : 0.0f;
+}
+
+/* CFindMatch::isNeighborRadius (findMatch.cpp:151-185) */
+static int is_neighbor_radius(const pmvso_ctx* c, int a, int b, float hunit, float thr, float radius) {
+  const float* Xa = c->s_coords + 4 * a; const float* Xb = c->s_coords + 4 * b;
+  const float* Na = c->s_normals + 4 * a; const float* Nb = c->s_normals + 4 * b;
+  if (dot4(Na, Nb) < cos(120.0 * M_PI / 180.0)) return 0;
+  const float diff[4] = {Xb[0] - Xa[0], Xb[1] - Xa[1], Xb[2] - Xa[2], Xb[3] - Xa[3]};
+  const float vunit = c->s_dscale[a] + c->s_dscale[b];
+  const float f0 = dot4(Na, diff);
+  const float f1 = dot4(Nb, diff);
+  float ftmp = (float)((fabsf(f0) + fabsf(f1)) / 2.0);
+  ftmp /= vunit;
+  float t[4];
+  for (int k = 0; k < 4; ++k) t[k] = diff[k] * 2 - Na[k] * f0 - Nb[k] * f1;
+  const float hsize = (float)(norm4(t) / 2.0 / hunit);
+  if (radius / hunit < hsize) return 0;
+  if (1.0 < hsize) ftmp /= fminf_(2.0f, hsize);
+  return ftmp < thr ? 1 : 0;
+}
+
+static int cmp_int(const void* a, const void* b) { const int x = *(const int*)a, y = *(const int*)b; return (x > y) - (x < y); }
+
+/* CPatchOrganizerS::findNeighbors (patchOrganizerS.cpp:528-651): unique table ids, ascending (the reference sorts
+ * by address).  Returns the count; at most cap ids are written. */
+int pmvso_find_neighbors(const pmvso_ctx* c, int k, float scale, int margin, int skipvis, int* out, int cap) {
+  const float* X = c->s_coords + 4 * k;
+  const float radius = (float)(1.5 * margin * pmvso_compute_radius(c, k));
+  float unit = 0.0f;
+  const int n = c->s_img_off[k + 1] - c->s_img_off[k];
+  for (int e = c->s_img_off[k]; e < c->s_img_off[k + 1]; ++e) unit += get_unit(c, c->s_images[e], X);
+  unit /= n;
+  unit *= c->csize;
+  const float thr = 0.5f * scale;   /* _neighborThreshold (findMatch.cpp:96) x scale */
+  int cnt = 0, room = 256;
+  int* buf = (int*)malloc(sizeof(int) * room);
+  for (int pass = 0; pass < (skipvis ? 1 : 2); ++pass) {
+    const int e0 = pass ? c->s_vimg_off[k] : c->s_img_off[k], e1 = pass ? c->s_vimg_off[k + 1] : c->s_img_off[k + 1];
+    for (int e = e0; e < e1; ++e) {
+      const int image = pass ? c->s_vimages[e] : c->s_images[e];
+      if (c->tnum <= image) continue;
+      const int ix = pass ? c->s_vgrids[2 * e] : c->s_grids[2 * e], iy = pass ? c->s_vgrids[2 * e + 1] : c->s_grids[2 * e + 1];
+      int gw, gh; pmvso_grid_dims(c, image, &gw, &gh);
+      for (int j = -margin; j <= margin; ++j) {
+        const int y = iy + j;
+        if (y < 0 || gh <= y) continue;
+        for (int i = -margin; i <= margin; ++i) {
+          const int x = ix + i;
+          if (x < 0 || gw <= x) continue;
+          const int cell = c->cell_base[image] + y * gw + x;
+          for (int list = 0; list < 2; ++list) {
+            const int* off = list ? c->vcell_off : c->cell_off;
+            const int* lst = list ? c->vcell_patch : c->cell_patch;
+            for (int q = off[cell]; q < off[cell + 1]; ++q)
+              if (is_neighbor_radius(c, k, lst[q], unit, thr, radius)) {
+                if (cnt == room) { room *= 2; buf = (int*)realloc(buf, sizeof(int) * room); }
+                buf[cnt++] = lst[q];
+              }
+          }
+        }
+      }
+    }
+  }
+  qsort(buf, cnt, sizeof(int), cmp_int);
+  int u = 0;
+  for (int i = 0; i < cnt; ++i) if (i == 0 || buf[i] != buf[i - 1]) buf[u++] = buf[i];
+  for (int i = 0; i < u && i < cap; ++i) out[i] = buf[i];
+  free(buf);
+  return u;
+}
+
+/* CExpand::findEmptyBlocks (expand.cpp:108-180): bit i = direction i already filled (fill[i] > 0); *radius = computeRadius */
+int pmvso_find_empty_blocks(const pmvso_ctx* c, int k, float* radius_out) {
+  const float* X = c->s_coords + 4 * k; const float* N = c->s_normals + 4 * k;
+  const int dnum = 6;
+  float xdir[4], ydir[4];
+  ortho4(N, xdir, ydir);
+  float fill[6] = {0, 0, 0, 0, 0, 0};
+  const float radius = pmvso_compute_radius(c, k);
+  const float radiuslow = radius / 6.0f, radiushigh = radius * 2.5f;
+  int cap = c->P > 0 ? c->P : 1;
+  int* nb = (int*)malloc(sizeof(int) * cap);
+  const int n = pmvso_find_neighbors(c, k, 4.0f, 1, 0, nb, cap);
+  for (int i = 0; i < n; ++i) {
+    const float* Xq = c->s_coords + 4 * nb[i];
+    const float diff[4] = {Xq[0] - X[0], Xq[1] - X[1], Xq[2] - X[2], Xq[3] - X[3]};
+    float f2[2] = {dot4(diff, xdir), dot4(diff, ydir)};
+    const float len = sqrtf(f2[0] * f2[0] + f2[1] * f2[1]);
+    if (len < radiuslow || radiushigh < len) continue;
+    f2[0] /= len; f2[1] /= len;
+    float angle = atan2f(f2[1], f2[0]);
+    if (angle < 0.0) angle = (float)(angle + 2 * M_PI);
+    const float findex = (float)(angle / (2 * M_PI / dnum));
+    const int lindex = (int)floor(findex);
+    const int hindex = lindex + 1;
+    fill[lindex % dnum] += hindex - findex;
+    fill[hindex % dnum] += findex - lindex;
+  }
+  free(nb);
+  int mask = 0;
+  for (int i = 0; i < dnum; ++i) if (0.0f < fill[i]) mask |= 1 << i;
+  if (radius_out) *radius_out = radius;
+  return mask;
+}
+
+/* CFilter::filterNeighborThread + filterQuad (filter.cpp:357-462).  The least-squares solve (Cmylapack::lls ->
+ * Eigen jacobiSvd in the reference, absent: PARITY UNPINNED) is the 5x5 normal equations in double with partial
+ * pivoting.  Returns 1 = reject; *residual_out = -1 when there are fewer than 6 neighbours. */
+int pmvso_filter_neighbor(const pmvso_ctx* c, int k, float quad, float* residual_out, int* ncount_out) {
+  const float* X = c->s_coords + 4 * k; const float* N = c->s_normals + 4 * k;
+  int cap = c->P > 0 ? c->P : 1;
+  int* nb = (int*)malloc(sizeof(int) * cap);
+  const int n = pmvso_find_neighbors(c, k, 4.0f, 2, 1, nb, cap);
+  if (ncount_out) *ncount_out = n;
+  if (n < 6) { free(nb); if (residual_out) *residual_out = -1.0f; return 1; }
+  float xdir[4], ydir[4];
+  ortho4(N, xdir, ydir);
+  float h = 0.0f;
+  for (int i = 0; i < n; ++i) {
+    const float* Xq = c->s_coords + 4 * nb[i];
+    const float d[4] = {Xq[0] - X[0], Xq[1] - X[1], Xq[2] - X[2], Xq[3] - X[3]};
+    h += norm4(d);
+  }
+  h /= n;
+  float* fx = (float*)malloc(sizeof(float) * n); float* fy = (float*)malloc(sizeof(float) * n); float* fz = (float*)malloc(sizeof(float) * n);
+  double ATA[5][5] = {{0}}, ATb[5] = {0};
+  for (int i = 0; i < n; ++i) {
+    const float* Xq = c->s_coords + 4 * nb[i];
+    const float d[4] = {Xq[0] - X[0], Xq[1] - X[1], Xq[2] - X[2], Xq[3] - X[3]};
+    fx[i] = dot4(d, xdir) / h; fy[i] = dot4(d, ydir) / h; fz[i] = dot4(d, N);
+    const double row[5] = {(double)(fx[i] * fx[i]), (double)(fy[i] * fy[i]), (double)(fx[i] * fy[i]), (double)fx[i], (double)fy[i]};
+    for (int a = 0; a < 5; ++a) {
+      for (int b = 0; b < 5; ++b) ATA[a][b] += row[a] * row[b];
+      ATb[a] += row[a] * (double)fz[i];
+    }
+  }
+  double M[5][6], x[5] = {0, 0, 0, 0, 0};
+  for (int a = 0; a < 5; ++a) { for (int b = 0; b < 5; ++b) M[a][b] = ATA[a][b]; M[a][5] = ATb[a]; }
+  int singular = 0;
+  for (int col = 0; col < 5 && !singular; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < 5; ++r) if (fabs(M[r][col]) > fabs(M[piv][col])) piv = r;
+    if (fabs(M[piv][col]) < 1e-300) { singular = 1; break; }
+    if (piv != col) for (int j = 0; j < 6; ++j) { const double t = M[col][j]; M[col][j] = M[piv][j]; M[piv][j] = t; }
+    for (int r = col + 1; r < 5; ++r) {
+      const double f = M[r][col] / M[col][col];
+      for (int j = col; j < 6; ++j) M[r][j] -= f * M[col][j];
+    }
+  }
+  if (!singular)
+    for (int r = 4; r >= 0; --r) {
+      double acc = M[r][5];
+      for (int j = r + 1; j < 5; ++j) acc -= M[r][j] * x[j];
+      x[r] = acc / M[r][r];
+    }
+  const float xs[5] = {(float)x[0], (float)x[1], (float)x[2], (float)x[3], (float)x[4]};
+  const int nimg = c->s_img_off[k + 1] - c->s_img_off[k];
+  const int inum = c->tau < nimg ? c->tau : nimg;
+  float unit = 0.0f;
+  for (int i = 0; i < inum; ++i) unit += get_unit(c, c->s_images[c->s_img_off[k] + i], X);
+  unit /= inum;
+  float residual = 0.0f;
+  for (int i = 0; i < n; ++i) {
+    const float res = xs[0] * (fx[i] * fx[i]) + xs[1] * (fy[i] * fy[i]) + xs[2] * (fx[i] * fy[i]) + xs[3] * fx[i] + xs[4] * fy[i] - fz[i];
+    residual += fabsf(res) / unit;
+  }
+  residual /= (n - 5);
+  free(fx); free(fy); free(fz); free(nb);
+  if (residual_out) *residual_out = residual;
+  return residual < quad ? 0 : 1;
 }

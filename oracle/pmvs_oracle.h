@@ -81,7 +81,13 @@ int pmvso_set_vimages(const pmvso_ctx* c, int k, int* vimages, int* vgrids, int 
 /* CFilter::filterExactThread's test (filter.cpp:315-343) for store patch k in (image, ix, iy): 1 = keep */
 int pmvso_filter_exact_safe(const pmvso_ctx* c, int k, int image, int ix, int iy);
 int pmvso_is_neighbor(const pmvso_ctx* c, int a, int b, float thr);  /* CFindMatch::isNeighbor, findMatch.cpp:120-149 */
-float pmvso_compute_gain(const pmvso_ctx* c, int k);                 /* CFilter::computeGain, filter.cpp:88-146 */
+float pmvso_compute_gain(const pmvso_ctx* c, int k);
+/* CExpand::computeRadius (expand.cpp:182-198), CPatchOrganizerS::findNeighbors (patchOrganizerS.cpp:528-651),
+ * CExpand::findEmptyBlocks (expand.cpp:108-180), CFilter::filterNeighborThread + filterQuad (filter.cpp:357-462) */
+float pmvso_compute_radius(const pmvso_ctx* c, int k);
+int pmvso_find_neighbors(const pmvso_ctx* c, int k, float scale, int margin, int skipvis, int* out, int cap);
+int pmvso_find_empty_blocks(const pmvso_ctx* c, int k, float* radius_out);
+int pmvso_filter_neighbor(const pmvso_ctx* c, int k, float quad, float* residual_out, int* ncount_out);                 /* CFilter::computeGain, filter.cpp:88-146 */
 
 #ifdef __cplusplus
 }

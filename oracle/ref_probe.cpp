@@ -350,6 +350,36 @@ int ref_get_cell(int image, int cell, int* out, int cap) {
   for (int i = 0; i < n; ++i) out[i] = v[i]->_id;
   return (int)v.size();
 }
+// CPatchOrganizerS::findNeighbors of table patch k: unique neighbours as table ids, ascending
+int ref_find_neighbors(int k, float scale, int margin, int skipvis, int* out, int cap) {
+  std::vector<Patch::PPatch> nb;
+  g_fm->_pos.findNeighbors(*g_fm->_pos._ppatches[k], nb, 0, scale, margin, skipvis);
+  std::vector<int> ids;
+  for (const auto& q : nb) ids.push_back(q->_id);
+  std::sort(ids.begin(), ids.end());
+  for (int i = 0; i < (int)ids.size() && i < cap; ++i) out[i] = ids[i];
+  return (int)ids.size();
+}
+float ref_compute_radius(int k) { return g_fm->_expand.computeRadius(*g_fm->_pos._ppatches[k]); }
+// CExpand::findEmptyBlocks on a copy of patch k with _dflag cleared: bit i = direction i is NOT offered, i.e. fill[i] > 0
+int ref_find_empty_blocks(int k) {
+  Patch::PPatch pp(new Patch::CPatch(*g_fm->_pos._ppatches[k]));
+  pp->_dflag = 0;
+  std::vector<std::vector<Vec4f> > can;
+  g_fm->_expand.findEmptyBlocks(pp, can);
+  int mask = 0;
+  for (int i = 0; i < (int)can.size(); ++i) if (can[i].empty()) mask |= 1 << i;
+  return mask;
+}
+// CFilter::filterNeighborThread's test for table patch k (filter.cpp:375-388): 1 = reject
+int ref_filter_neighbor(int k, float quad, int* ncount) {
+  g_fm->_quadThreshold = quad;   // option `quad` (source/pmvs/option.cpp), default 2.5
+  std::vector<Patch::PPatch> nb;
+  g_fm->_pos.findNeighbors(*g_fm->_pos._ppatches[k], nb, 0, 4, 2, 1);
+  if (ncount) *ncount = (int)nb.size();
+  if ((int)nb.size() < 6) return 1;
+  return g_fm->_filter.filterQuad(*g_fm->_pos._ppatches[k], nb);
+}
 int ref_get_depth_flag(void) { return g_fm->_depth; }
 float ref_neighbor_threshold(int which) { return which == 0 ? g_fm->_neighborThreshold : (which == 1 ? g_fm->_neighborThreshold1 : g_fm->_neighborThreshold2); }
 

@@ -56,10 +56,26 @@ def main():
         pairs.append((a, b, ref.is_neighbor(a, b, 1.0), ref.is_neighbor(a, b, 0.5)))
     out["nb_pairs"] = np.array(pairs, np.int32)
     out["gains"] = np.array([ref.compute_gain(k) for k in range(P)], np.float32)
+    # neighbour searches on the same table: findNeighbors (both call patterns), computeRadius, findEmptyBlocks' fill
+    # mask, filterNeighbor's verdict -- for every patch (small scene)
+    nb_off1, nb1, nb_off2, nb2 = [0], [], [0], []
+    for k in range(P):
+        a = ref.find_neighbors(k, 4.0, 1, 0); b = ref.find_neighbors(k, 4.0, 2, 1)
+        nb1.append(a); nb_off1.append(nb_off1[-1] + len(a)); nb2.append(b); nb_off2.append(nb_off2[-1] + len(b))
+    out["fn_m1_off"] = np.array(nb_off1, np.int32); out["fn_m1"] = np.concatenate(nb1).astype(np.int32)
+    out["fn_m2_off"] = np.array(nb_off2, np.int32); out["fn_m2"] = np.concatenate(nb2).astype(np.int32)
+    out["radius"] = np.array([ref.compute_radius(k) for k in range(P)], np.float32)
+    out["empty_mask"] = np.array([ref.find_empty_blocks(k) for k in range(P)], np.uint8)
+    fnb = [ref.filter_neighbor(k) for k in range(P)]
+    out["fnb_reject"] = np.array([r for r, _ in fnb], np.uint8); out["fnb_count"] = np.array([c for _, c in fnb], np.int32)
+    # the final table has already been through the filter at quad 2.5; tighter thresholds exercise filterQuad's fit
+    out["fnb_quads"] = np.array([0.03, 0.1, 0.5], np.float32)
+    out["fnb_reject_q"] = np.array([[ref.filter_neighbor(k, float(q))[0] for k in range(P)] for q in out["fnb_quads"]], np.uint8)
     path = os.path.join(HERE, "pmvs_state.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes; patches", P, "visible", np.bincount(out["vis_answer"]), "neighbours",
-          out["nb_pairs"][:, 2].mean(), "gain<0", (out["gains"] < 0).mean())
+          out["nb_pairs"][:, 2].mean(), "gain<0", (out["gains"] < 0).mean(), "filterNeighbor rejects", out["fnb_reject"].mean(),
+          "mean neighbours", out["fnb_count"].mean(), "rejects at tighter quad", out["fnb_reject_q"].mean(axis=1))
 
 
 if __name__ == "__main__":

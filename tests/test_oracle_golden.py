@@ -175,3 +175,21 @@ def test_is_neighbor_and_gain(oracle_state, S):
         assert oracle_state.is_neighbor(a, b, 1.0) == n1 and oracle_state.is_neighbor(a, b, 0.5) == n05, (a, b)
     gains = np.array([oracle_state.compute_gain(k) for k in range(len(S["gains"]))], np.float32)
     assert np.array_equal(gains, S["gains"])
+
+
+def test_find_neighbors_empty_blocks_filter_neighbor(oracle_state, S):
+    """findNeighbors (both call patterns), computeRadius, findEmptyBlocks' fill mask and filterNeighbor's verdict
+    (at the option's quad and at three tighter ones) for EVERY patch of the reference's final table"""
+    o = oracle_state
+    P = len(S["st_ncc"])
+    for k in range(P):
+        assert np.array_equal(o.find_neighbors(k, 4.0, 1, 0), S["fn_m1"][S["fn_m1_off"][k]:S["fn_m1_off"][k + 1]]), k
+        assert np.array_equal(o.find_neighbors(k, 4.0, 2, 1), S["fn_m2"][S["fn_m2_off"][k]:S["fn_m2_off"][k + 1]]), k
+        assert o.compute_radius(k) == S["radius"][k], k
+        assert o.find_empty_blocks(k)[0] == S["empty_mask"][k], k
+        rej, res, cnt = o.filter_neighbor(k)
+        assert rej == S["fnb_reject"][k] and cnt == S["fnb_count"][k], k
+    for qi, q in enumerate(S["fnb_quads"]):
+        mine = np.array([o.filter_neighbor(k, float(q))[0] for k in range(0, P, 3)], np.uint8)
+        assert np.array_equal(mine, S["fnb_reject_q"][qi][::3]), q
+    assert 0.2 < S["fnb_reject_q"][0].mean() < 0.8 and S["empty_mask"].min() < 63
