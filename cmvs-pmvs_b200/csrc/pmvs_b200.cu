@@ -798,7 +798,7 @@ static T* arena_take(pmvsb_ctx* ctx, size_t n) {
 template <typename T>
 static int dvec_reserve(pmvsb_ctx* ctx, DVec<T>& v, size_t n, size_t keep = 0) {
   if (n <= v.cap && v.p) return PMVSB_OK;
-  const size_t want = n + n / 2 + 4096;
+  const size_t want = 2 * n + 4096;
   T* np = nullptr;
   CK(cudaMalloc((void**)&np, sizeof(T) * want));
   if (keep && v.p) CK(cudaMemcpyAsync(np, v.p, sizeof(T) * keep, cudaMemcpyDeviceToDevice, ctx->stream));

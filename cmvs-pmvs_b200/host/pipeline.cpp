@@ -20,6 +20,7 @@
 #include <numeric>
 #include <queue>
 #include <random>
+#include <sstream>
 
 #include "pmvs_host.hpp"
 
@@ -251,83 +252,110 @@ void Pipeline::remove_patch(int id) {   // patchOrganizerS.cpp:452-477
 }
 
 std::vector<int> Pipeline::collect_patches() const {   // patchOrganizerS.cpp:207-236: first appearance in (image, cell) order
+  std::vector<std::vector<int>> per_image(tnum_);
+  parallel_for(tnum_, threads_, [&](int im) {
+    std::vector<int>& v = per_image[im];
+    for (const auto& cell : grids_[im].pg) v.insert(v.end(), cell.begin(), cell.end());
+  }, 1);
   std::vector<int> ids;
   std::vector<char> seen(patches_.size(), 0);
-  for (int im = 0; im < tnum_; ++im)
-    for (const auto& cell : grids_[im].pg)
-      for (int q : cell)
-        if (!seen[q]) { seen[q] = 1; ids.push_back(q); }
+  for (const auto& v : per_image)
+    for (int q : v)
+      if (!seen[q]) { seen[q] = 1; ids.push_back(q); }
   return ids;
+}
+
+// CPatch fields of a list of patches as the arrays pmvsb_store_upload / pmvsb_store_append take
+struct Pipeline::TableArrays {
+  std::vector<float> coords, normals, ncc, dsc;
+  std::vector<int32_t> ioff, voff, images, grids, vimages, vgrids, timages;
+};
+
+void Pipeline::marshal(const std::vector<int>& ids, TableArrays& t) const {
+  const int P = (int)ids.size();
+  t.coords.resize((size_t)4 * P); t.normals.resize((size_t)4 * P); t.ncc.resize(P); t.dsc.resize(P); t.timages.resize(P);
+  t.ioff.assign(P + 1, 0); t.voff.assign(P + 1, 0);
+  for (int k = 0; k < P; ++k) {
+    t.ioff[k + 1] = t.ioff[k] + (int32_t)patches_[ids[k]].images.size();
+    t.voff[k + 1] = t.voff[k] + (int32_t)patches_[ids[k]].vimages.size();
+  }
+  t.images.resize(std::max(1, t.ioff[P])); t.grids.resize((size_t)2 * std::max(1, t.ioff[P]));
+  t.vimages.resize(std::max(1, t.voff[P])); t.vgrids.resize((size_t)2 * std::max(1, t.voff[P]));
+  parallel_for(P, threads_, [&](int k) {
+    const Patch& p = patches_[ids[k]];
+    for (int c = 0; c < 4; ++c) { t.coords[4 * k + c] = p.coord[c]; t.normals[4 * k + c] = p.normal[c]; }
+    t.ncc[k] = p.ncc; t.dsc[k] = p.dscale; t.timages[k] = p.timages;
+    int e = t.ioff[k];
+    for (size_t i = 0; i < p.images.size(); ++i, ++e) { t.images[e] = p.images[i]; t.grids[2 * e] = p.grids[i][0]; t.grids[2 * e + 1] = p.grids[i][1]; }
+    e = t.voff[k];
+    for (size_t i = 0; i < p.vimages.size(); ++i, ++e) { t.vimages[e] = p.vimages[i]; t.vgrids[2 * e] = p.vgrids[i][0]; t.vgrids[2 * e + 1] = p.vgrids[i][1]; }
+  }, 1024);
 }
 
 void Pipeline::upload_table(const std::vector<int>& ids) {
   Tick tk(this, "gpu.upload_table+depth_maps");
   table_ids_ = ids;
-  const int P = (int)ids.size();
-  std::vector<float> coords((size_t)4 * P), normals((size_t)4 * P), ncc(P), dsc(P);
-  std::vector<int32_t> ioff(P + 1, 0), voff(P + 1, 0), images, grids, vimages, vgrids, timages(P);
-  for (int k = 0; k < P; ++k) {
-    const Patch& p = patches_[ids[k]];
-    for (int c = 0; c < 4; ++c) { coords[4 * k + c] = p.coord[c]; normals[4 * k + c] = p.normal[c]; }
-    ncc[k] = p.ncc; dsc[k] = p.dscale; timages[k] = p.timages;
-    for (size_t i = 0; i < p.images.size(); ++i) { images.push_back(p.images[i]); grids.push_back(p.grids[i][0]); grids.push_back(p.grids[i][1]); }
-    for (size_t i = 0; i < p.vimages.size(); ++i) { vimages.push_back(p.vimages[i]); vgrids.push_back(p.vgrids[i][0]); vgrids.push_back(p.vgrids[i][1]); }
-    ioff[k + 1] = (int32_t)images.size(); voff[k + 1] = (int32_t)vimages.size();
-  }
-  if (images.empty()) { images.push_back(0); grids.push_back(0); grids.push_back(0); }
-  if (vimages.empty()) { vimages.push_back(0); vgrids.push_back(0); vgrids.push_back(0); }
+  table_index_.assign(patches_.size(), -1);
+  for (size_t k = 0; k < ids.size(); ++k) table_index_[ids[k]] = (int)k;
+  TableArrays t;
+  marshal(ids, t);
   if (pmvsb_set_thresholds(gpu_, ncc_threshold_, ncc_threshold_before_)) die("set_thresholds");
   if (pmvsb_set_depth(gpu_, depth_)) die("set_depth");
-  if (pmvsb_store_upload(gpu_, P, coords.data(), normals.data(), ncc.data(), dsc.data(), ioff.data(), images.data(), grids.data(), voff.data(),
-                         vimages.data(), vgrids.data(), timages.data())) die("store_upload");
+  if (pmvsb_store_upload(gpu_, (int)ids.size(), t.coords.data(), t.normals.data(), t.ncc.data(), t.dsc.data(), t.ioff.data(), t.images.data(),
+                         t.grids.data(), t.voff.data(), t.vimages.data(), t.vgrids.data(), t.timages.data())) die("store_upload");
   if (pmvsb_build_depth_maps(gpu_)) die("build_depth_maps");
 }
 
-// CFilter::setDepthMapsVGridsVPGridsAddPatchV (filter.cpp:734-783)
+// CPatchOrganizerS::addPatch + updateDepthMaps for patches committed since the table was uploaded
+void Pipeline::append_table(const std::vector<int>& ids) {
+  if (ids.empty()) return;
+  Tick tk(this, "gpu.append_table");
+  table_index_.resize(patches_.size(), -1);
+  for (int id : ids) { table_index_[id] = (int)table_ids_.size(); table_ids_.push_back(id); }
+  TableArrays t;
+  marshal(ids, t);
+  if (pmvsb_store_append(gpu_, (int)ids.size(), t.coords.data(), t.normals.data(), t.ncc.data(), t.dsc.data(), t.ioff.data(), t.images.data(),
+                         t.grids.data(), t.voff.data(), t.vimages.data(), t.vgrids.data(), t.timages.data())) die("store_append");
+}
+
+// CFilter::setDepthMapsVGridsVPGridsAddPatchV (filter.cpp:734-783): table -> GPU, depth maps, _vimages/_vgrids of every
+// patch recomputed on the device inside the table, then mirrored into the host patches and _vpgrids
 void Pipeline::rebuild_depth_and_vis(bool additive) {
   Tick tk(this, "filter.rebuild_depth_and_vis");
   const std::vector<int> ids = collect_patches();
-  for (int im = 0; im < tnum_; ++im)
-    for (auto& cell : grids_[im].vpg) cell.clear();
   if (!additive)
-    for (int id : ids) { patches_[id].vimages.clear(); patches_[id].vgrids.clear(); }
+    parallel_for((int)ids.size(), threads_, [&](int k) { patches_[ids[k]].vimages.clear(); patches_[ids[k]].vgrids.clear(); }, 1024);
   upload_table(ids);
   const int P = (int)ids.size();
+  parallel_for(tnum_, threads_, [&](int im) { for (auto& cell : grids_[im].vpg) cell.clear(); }, 1);
   if (P == 0) return;
-  const int vs = tnum_;
-  int stride = 1;
-  for (int id : ids) stride = std::max(stride, (int)patches_[id].images.size());
-  std::vector<float> coords((size_t)4 * P), normals((size_t)4 * P);
-  std::vector<int32_t> images((size_t)stride * P, 0), nimages(P), vim((size_t)vs * P, 0), nv(P, 0), vgr((size_t)2 * vs * P, 0);
-  for (int k = 0; k < P; ++k) {
-    const Patch& p = patches_[ids[k]];
-    for (int c = 0; c < 4; ++c) { coords[4 * k + c] = p.coord[c]; normals[4 * k + c] = p.normal[c]; }
-    nimages[k] = (int)p.images.size();
-    for (size_t i = 0; i < p.images.size(); ++i) images[(size_t)k * stride + i] = p.images[i];
-    nv[k] = (int)p.vimages.size();
-    for (size_t i = 0; i < p.vimages.size(); ++i) { vim[(size_t)k * vs + i] = p.vimages[i]; vgr[((size_t)k * vs + i) * 2] = p.vgrids[i][0]; vgr[((size_t)k * vs + i) * 2 + 1] = p.vgrids[i][1]; }
-  }
-  if (pmvsb_set_vimages_batch(gpu_, P, stride, coords.data(), normals.data(), images.data(), nimages.data(), vs, vim.data(), nv.data(), vgr.data())) die("set_vimages_batch");
-  for (int k = 0; k < P; ++k) {
+  int32_t total = 0;
+  if (pmvsb_store_update_vimages(gpu_, additive ? 1 : 0, &total)) die("store_update_vimages");
+  std::vector<int32_t> voff(P + 1), vim(std::max(1, total)), vgr((size_t)2 * std::max(1, total));
+  if (pmvsb_store_download_vimages(gpu_, voff.data(), vim.data(), vgr.data())) die("store_download_vimages");
+  parallel_for(P, threads_, [&](int k) {
     Patch& p = patches_[ids[k]];
-    p.vimages.clear(); p.vgrids.clear();
-    for (int i = 0; i < nv[k]; ++i) {
-      p.vimages.push_back(vim[(size_t)k * vs + i]);
-      p.vgrids.push_back({vgr[((size_t)k * vs + i) * 2], vgr[((size_t)k * vs + i) * 2 + 1]});
+    const int n = voff[k + 1] - voff[k];
+    p.vimages.resize(n); p.vgrids.resize(n);
+    for (int i = 0; i < n; ++i) {
+      p.vimages[i] = vim[voff[k] + i];
+      p.vgrids[i] = {vgr[(size_t)2 * (voff[k] + i)], vgr[(size_t)2 * (voff[k] + i) + 1]};
     }
-  }
-  // addPatchV: per image, patches in table order
-  for (int id : ids) {
-    const Patch& p = patches_[id];
-    for (size_t i = 0; i < p.vimages.size(); ++i)
-      grids_[p.vimages[i]].vpg[(size_t)p.vgrids[i][1] * grids_[p.vimages[i]].gw + p.vgrids[i][0]].push_back(id);
-  }
-  // the vimages changed: give the GPU table the new lists (gains read them)
-  upload_table(ids);
+  }, 1024);
+  // addPatchV: per image, patches in table order (one thread owns one image's cells)
+  parallel_for(tnum_, threads_, [&](int im) {
+    ImageGrid& g = grids_[im];
+    for (int k = 0; k < P; ++k) {
+      const Patch& p = patches_[ids[k]];
+      for (size_t i = 0; i < p.vimages.size(); ++i)
+        if (p.vimages[i] == im) g.vpg[(size_t)p.vgrids[i][1] * g.gw + p.vgrids[i][0]].push_back(ids[k]);
+    }
+  }, 1);
 }
 
 // ---------------------------------------------------------------------------------------------- evaluate a wave
 void Pipeline::evaluate(std::vector<Candidate>& cands, std::vector<int>& verdict) {
+  Tick tk_all(this, "evaluate.total");
   const int P = (int)cands.size();
   verdict.assign(P, 1);
   if (P == 0) return;
@@ -477,7 +505,10 @@ void Pipeline::seed_round() {
     // ---- enumerate the wave: every (cell, feature, candidate) of this image from the current snapshot
     std::vector<Candidate> wave;
     const ImageGrid& g = grids_[index];
-    for (int y = 0; y < g.gh; ++y)
+    std::vector<std::vector<Candidate>> per_row(g.gh);   // rows are enumerated by the CPU threads, concatenated in row order
+    { Tick tk2(this, "host.seed.candidates");
+    parallel_for(g.gh, threads_, [&](int y) {
+      std::vector<Candidate>& wave = per_row[y];
       for (int x = 0; x < g.gw; ++x) {
         const int cell = y * g.gw + x;
         if (bins[index][cell].empty() || !can_add(index, x, y)) continue;
@@ -569,6 +600,10 @@ void Pipeline::seed_round() {
           }
         }
       }
+    }, 1);
+    }
+    for (auto& v : per_row) for (auto& c : v) wave.push_back(std::move(c));
+    per_row.clear();
     std::vector<int> verdict;
     evaluate(wave, verdict);
     // ---- commit: replay the reference's sequential rule per cell (seed.cpp:151-199)
@@ -658,43 +693,36 @@ void Pipeline::expand_round() {
   std::cerr << "Expanding patches..." << std::flush;
   const double two_pi = 2 * M_PI;
   int wave_no = 0;
-  if (depth_ != 0) upload_table(collect_patches());   // depth maps for setVImagesVGrids of the candidates
+  upload_table(collect_patches());   // resident table: neighbour searches, depth maps for setVImagesVGrids of the candidates
   size_t last_table_size = patches_.size();
   while (!frontier.empty()) {
     std::stable_sort(frontier.begin(), frontier.end(), [&](int a, int b) { return patches_[a].tmp > patches_[b].tmp; });
     std::vector<Candidate> wave;
-    std::vector<std::vector<Candidate>> per_parent(frontier.size());
+    // findEmptyBlocks (expand.cpp:108-180): the neighbour search of every frontier patch is one kernel over the resident
+    // table; it returns the directions that already have a neighbour and computeRadius
+    frontier.erase(std::remove_if(frontier.begin(), frontier.end(), [&](int id) { return !patches_[id].alive; }), frontier.end());
+    const int F = (int)frontier.size();
+    std::vector<int32_t> fidx(F);
+    std::vector<uint8_t> fmask(F);
+    std::vector<float> fradius(F);
+    for (int fi = 0; fi < F; ++fi) {
+      fidx[fi] = table_index_[frontier[fi]];
+      if (fidx[fi] < 0) { std::cerr << "expand: frontier patch is not in the GPU table" << std::endl; std::exit(1); }
+    }
+    { Tick tk2(this, "gpu.find_empty_blocks");
+    if (pmvsb_find_empty_blocks_store(gpu_, F, fidx.data(), fmask.data(), fradius.data())) die("find_empty_blocks_store"); }
+    std::vector<std::vector<Candidate>> per_parent(F);
     { Tick tk2(this, "host.expand.candidates");
-    parallel_for((int)frontier.size(), threads_, [&](int fi) {
+    parallel_for(F, threads_, [&](int fi) {
       const int id = frontier[fi];
-      std::vector<Candidate>& wave = per_parent[fi];   // this parent's candidates; concatenated in frontier order below
+      std::vector<Candidate>& mine = per_parent[fi];   // this parent's candidates; concatenated in frontier order below
       const Patch& pp = patches_[id];
-      if (!pp.alive) return;
-      // findEmptyBlocks (expand.cpp:108-180)
       float xdir[4], ydir[4];
       ortho(pp.normal, xdir, ydir);
       const int dnum = 6;
-      float fill[6] = {0, 0, 0, 0, 0, 0};
-      const float radius = compute_radius(pp);
-      const float rlow = radius / 6.0f, rhigh = radius * 2.5f;
-      std::vector<int> nb;
-      find_neighbors(pp, nb, 4.0f, 1, false);
-      for (int q : nb) {
-        float diff[4];
-        for (int k = 0; k < 4; ++k) diff[k] = patches_[q].coord[k] - pp.coord[k];
-        float f2[2] = {dot4(diff, xdir), dot4(diff, ydir)};
-        const float len = std::sqrt(f2[0] * f2[0] + f2[1] * f2[1]);
-        if (len < rlow || rhigh < len) continue;
-        f2[0] /= len; f2[1] /= len;
-        float angle = std::atan2(f2[1], f2[0]);
-        if (angle < 0.0) angle += (float)two_pi;
-        const float findex = (float)(angle / (two_pi / dnum));
-        const int lindex = (int)std::floor(findex), hindex = lindex + 1;
-        fill[lindex % dnum] += hindex - findex;
-        fill[hindex % dnum] += findex - lindex;
-      }
+      const float radius = fradius[fi];
       for (int i = 0; i < dnum; ++i) {
-        if (0.0f < fill[i]) continue;
+        if (fmask[fi] & (1 << i)) continue;
         if (pp.dflag & (1 << i)) continue;
         const float angle = (float)(two_pi * i / dnum);
         Candidate c;
@@ -711,9 +739,9 @@ void Pipeline::expand_round() {
         }
         if (c.patch.images.empty()) { patches_[id].dflag |= (unsigned char)(1 << i); continue; }
         if (check_counts(c.patch)) { patches_[id].dflag |= (unsigned char)(1 << i); continue; }
-        wave.push_back(c);
+        mine.push_back(c);
       }
-    }, 16);
+    }, 256);
     }
     for (auto& v : per_parent) for (auto& c : v) wave.push_back(std::move(c));
     per_parent.clear();
@@ -721,6 +749,7 @@ void Pipeline::expand_round() {
     evaluate(wave, verdict);
     // commit in parent-priority order; cells may have been taken by an earlier commit of this wave
     std::vector<int> next;
+    { Tick tk_commit(this, "host.expand.commit");
     for (size_t k = 0; k < wave.size(); ++k) {
       Candidate& c = wave[k];
       ++st.trial;
@@ -730,8 +759,7 @@ void Pipeline::expand_round() {
       else {
         Patch& p = c.patch;
         // the cell rules are re-checked against the grids as they are NOW (what a sequential run would have seen)
-        Patch probe = p;
-        if (check_counts(probe)) { ++st.fail0; fail = true; }
+        if (check_counts(p)) { ++st.fail0; fail = true; }
         if (!fail && depth_ >= 2) {   // COptim::check (optim.cpp:363-383)
           const float gain = compute_gain(p);
           p.tmp = gain;
@@ -753,17 +781,12 @@ void Pipeline::expand_round() {
       }
       if (fail) patches_[c.parent].dflag |= (unsigned char)(1 << c.dir);
     }
-    // CPatchOrganizerS::updateDepthMaps for the patches committed by this wave (patchOrganizerS.cpp:351-381)
-    if (depth_ != 0) {
+    }
+    // CPatchOrganizerS::addPatch + updateDepthMaps for the patches committed by this wave: extend the resident table
+    {
       std::vector<int> fresh;
       for (size_t id = last_table_size; id < patches_.size(); ++id) fresh.push_back((int)id);
-      if (!fresh.empty()) {
-        Tick tk3(this, "gpu.depth_maps_add");
-        std::vector<float> cc((size_t)4 * fresh.size());
-        for (size_t k = 0; k < fresh.size(); ++k)
-          for (int c4 = 0; c4 < 4; ++c4) cc[4 * k + c4] = patches_[fresh[k]].coord[c4];
-        if (pmvsb_depth_maps_add(gpu_, (int)fresh.size(), cc.data()) != 0) upload_table(collect_patches());   // capacity: full upload
-      }
+      append_table(fresh);
       last_table_size = patches_.size();
     }
     frontier.swap(next);
@@ -775,6 +798,7 @@ void Pipeline::expand_round() {
 
 // ---------------------------------------------------------------------------------------------- filters
 void Pipeline::filter_outside() {   // filter.cpp:29-86
+  Tick tk(this, "filter.outside");
   std::cerr << "FilterOutside" << std::endl;
   const std::vector<int> ids = table_ids_;   // table uploaded by the preceding rebuild
   const int P = (int)ids.size();
@@ -793,94 +817,86 @@ void Pipeline::filter_outside() {   // filter.cpp:29-86
 }
 
 void Pipeline::filter_exact() {   // filter.cpp:203-355
+  Tick tk(this, "filter.exact");
   std::cerr << "Filter Exact: " << std::flush;
   const std::vector<int> ids = table_ids_;
   const int P = (int)ids.size();
   if (P == 0) return;
-  size_t E = 0;
-  for (int id : ids) E += patches_[id].images.size();
-  std::vector<uint8_t> safe(std::max<size_t>(E, 1));
-  if (pmvsb_filter_exact_store(gpu_, safe.data())) die("filter_exact_store");
+  std::vector<int32_t> eoff(P + 1, 0);
+  for (int k = 0; k < P; ++k) eoff[k + 1] = eoff[k] + (int32_t)patches_[ids[k]].images.size();
+  std::vector<uint8_t> safe(std::max<size_t>(eoff[P], 1));
+  { Tick tk2(this, "gpu.filter_exact");
+  if (pmvsb_filter_exact_store(gpu_, safe.data())) die("filter_exact_store"); }
   // per patch: surviving target images in ascending image order (the reference visits image by image), then the
-  // non-target images in their old order
+  // non-target images in their old order (filter.cpp:262-272); the cells of the dropped images lose the patch (240-252)
   struct Entry { int image, gx, gy; };
-  const int stride = std::min(num_, 64);
-  std::vector<float> coords, normals;
-  std::vector<int32_t> images, nimages;
-  std::vector<int> todo;
-  size_t e = 0;
-  int count = 0;
-  for (int k = 0; k < P; ++k) {
+  std::vector<std::vector<Entry>> dropped(P);
+  parallel_for(P, threads_, [&](int k) {
     Patch& p = patches_[ids[k]];
     std::vector<Entry> keep, other;
-    for (size_t i = 0; i < p.images.size(); ++i, ++e) {
+    for (size_t i = 0; i < p.images.size(); ++i) {
       const int im = p.images[i];
-      if (tnum_ <= im) { other.push_back({im, p.grids[i][0], p.grids[i][1]}); continue; }
-      if (safe[e]) keep.push_back({im, p.grids[i][0], p.grids[i][1]});
-      else {
-        auto& cell = grids_[im].pg[(size_t)p.grids[i][1] * grids_[im].gw + p.grids[i][0]];
-        cell.erase(std::remove(cell.begin(), cell.end(), ids[k]), cell.end());
-      }
+      const Entry en{im, p.grids[i][0], p.grids[i][1]};
+      if (tnum_ <= im) other.push_back(en);
+      else if (safe[eoff[k] + i]) keep.push_back(en);
+      else dropped[k].push_back(en);
     }
     std::stable_sort(keep.begin(), keep.end(), [](const Entry& a, const Entry& b) { return a.image < b.image; });
     p.timages = (int)keep.size();
     keep.insert(keep.end(), other.begin(), other.end());
-    // the cell lists keep the patch where it stays; rebuild the patch's own lists
-    p.images.clear(); p.grids.clear();
-    for (const Entry& en : keep) { p.images.push_back(en.image); p.grids.push_back({en.gx, en.gy}); }
-    if ((int)p.images.size() < opt_.minImageNum) { remove_patch(ids[k]); ++count; continue; }
+    p.images.resize(keep.size()); p.grids.resize(keep.size());
+    for (size_t i = 0; i < keep.size(); ++i) { p.images[i] = keep[i].image; p.grids[i] = {keep[i].gx, keep[i].gy}; }
+  }, 1024);
+  std::vector<int> todo;
+  int count = 0;
+  for (int k = 0; k < P; ++k) {
+    for (const Entry& en : dropped[k]) {
+      auto& cell = grids_[en.image].pg[(size_t)en.gy * grids_[en.image].gw + en.gx];
+      cell.erase(std::remove(cell.begin(), cell.end(), ids[k]), cell.end());
+    }
+    if ((int)patches_[ids[k]].images.size() < opt_.minImageNum) { remove_patch(ids[k]); ++count; continue; }
     todo.push_back(ids[k]);
   }
-  // setRefImage + setGrids for the survivors (filter.cpp:277-280)
+  // setRefImage + setGrids for the survivors (filter.cpp:277-280).  The cells of a kept image are a function of the
+  // patch centre, which has not moved: the patch stays where it is in _pgrids, as in the reference.
   const int T = (int)todo.size();
   if (T > 0) {
-    coords.resize((size_t)4 * T); normals.resize((size_t)4 * T);
-    images.assign((size_t)stride * T, 0); nimages.resize(T);
-    std::vector<int32_t> grids((size_t)2 * stride * T);
-    for (int j = 0; j < T; ++j) {
+    int stride = 1;
+    for (int id : todo) stride = std::max(stride, (int)patches_[id].images.size());
+    stride = std::min(stride, 64);
+    std::vector<float> coords((size_t)4 * T), normals((size_t)4 * T);
+    std::vector<int32_t> images((size_t)stride * T, 0), nimages(T), grids((size_t)2 * stride * T);
+    parallel_for(T, threads_, [&](int j) {
       const Patch& p = patches_[todo[j]];
       for (int c = 0; c < 4; ++c) { coords[4 * j + c] = p.coord[c]; normals[4 * j + c] = p.normal[c]; }
       nimages[j] = std::min((int)p.images.size(), stride);
       for (int i = 0; i < nimages[j]; ++i) images[(size_t)j * stride + i] = p.images[i];
-    }
-    if (pmvsb_set_ref_image_batch(gpu_, T, stride, coords.data(), normals.data(), images.data(), nimages.data(), grids.data())) die("set_ref_image_batch");
-    for (int j = 0; j < T; ++j) {
+    }, 1024);
+    { Tick tk2(this, "gpu.set_ref_image");
+    if (pmvsb_set_ref_image_batch(gpu_, T, stride, coords.data(), normals.data(), images.data(), nimages.data(), grids.data())) die("set_ref_image_batch"); }
+    parallel_for(T, threads_, [&](int j) {
+      if (nimages[j] == 0) return;
       Patch& p = patches_[todo[j]];
-      // the patch moves with its recomputed cells: take it out of the old cells, put it into the new ones
-      for (size_t i = 0; i < p.images.size(); ++i)
-        if (p.images[i] < tnum_) {
-          auto& cell = grids_[p.images[i]].pg[(size_t)p.grids[i][1] * grids_[p.images[i]].gw + p.grids[i][0]];
-          cell.erase(std::remove(cell.begin(), cell.end(), todo[j]), cell.end());
-        }
-      if (nimages[j] == 0) { remove_patch(todo[j]); ++count; continue; }
       p.images.assign(images.begin() + (size_t)j * stride, images.begin() + (size_t)j * stride + nimages[j]);
-      p.grids.clear();
-      for (int i = 0; i < nimages[j]; ++i) p.grids.push_back({grids[((size_t)j * stride + i) * 2], grids[((size_t)j * stride + i) * 2 + 1]});
-      for (size_t i = 0; i < p.images.size(); ++i)
-        if (p.images[i] < tnum_) {
-          const ImageGrid& g = grids_[p.images[i]];
-          if (p.grids[i][0] >= 0 && p.grids[i][0] < g.gw && p.grids[i][1] >= 0 && p.grids[i][1] < g.gh)
-            grids_[p.images[i]].pg[(size_t)p.grids[i][1] * g.gw + p.grids[i][0]].push_back(todo[j]);
-        }
-    }
+      p.grids.resize(nimages[j]);
+      for (int i = 0; i < nimages[j]; ++i) p.grids[i] = {grids[((size_t)j * stride + i) * 2], grids[((size_t)j * stride + i) * 2 + 1]};
+    }, 1024);
+    for (int j = 0; j < T; ++j)
+      if (nimages[j] == 0) { remove_patch(todo[j]); ++count; }
   }
   std::cerr << std::endl << P << " -> " << P - count << " (" << 100.0f * (P - count) / P << "%)" << std::endl;
 }
 
-void Pipeline::filter_neighbor() {   // filter.cpp:357-392, 464-519 (times = 1)
-  Tick tk(this, "host.filter_neighbor");
+void Pipeline::filter_neighbor() {   // filter.cpp:357-392, 464-519 (times = 1): one kernel over the table of the preceding rebuild
+  Tick tk(this, "gpu.filter_neighbor");
   std::cerr << "FilterNeighbor:\t" << std::flush;
-  const std::vector<int> ids = collect_patches();
+  const std::vector<int> ids = table_ids_;
   const int P = (int)ids.size();
   if (P == 0) return;
-  std::vector<char> reject(P, 0);
-  parallel_for(P, threads_, [&](int k) {
-    const Patch& p = patches_[ids[k]];
-    std::vector<int> nb;
-    find_neighbors(p, nb, 4.0f, 2, true);
-    if ((int)nb.size() < 6) reject[k] = 1;
-    else if (filter_quad(p, nb)) reject[k] = 1;
-  });
+  std::vector<uint8_t> reject(P, 0);
+  int32_t overflow = 0;
+  if (pmvsb_filter_neighbor_store(gpu_, opt_.quad, reject.data(), nullptr, nullptr, &overflow)) die("filter_neighbor_store");
+  if (overflow) std::cerr << "(" << overflow << " patches with more neighbours than the kernel keeps: not fitted) ";
   int count = 0;
   for (int k = 0; k < P; ++k) if (reject[k]) { remove_patch(ids[k]); ++count; }
   std::cerr << P << " -> " << P - count << " (" << 100.0f * (P - count) / P << "%)" << std::endl;
@@ -961,6 +977,26 @@ void Pipeline::run() {   // findMatch.cpp:187-220
 }
 
 // ---------------------------------------------------------------------------------------------- writers
+namespace {
+// formats records [0, P) on the CPU threads (one text block per slice, same iostream formatting as a single stream)
+// and writes the blocks in order
+template <typename F>
+void write_records(const std::string& path, const std::string& header, int P, int threads, int precision, F record) {
+  const int slices = std::max(1, std::min(threads * 4, (P + 4095) / 4096));
+  std::vector<std::string> text(slices);
+  pmvs::parallel_for(slices, threads, [&](int sidx) {
+    const int b = (int)((long long)P * sidx / slices), e = (int)((long long)P * (sidx + 1) / slices);
+    std::ostringstream o;
+    if (precision > 0) o << std::setprecision(precision);
+    for (int k = b; k < e; ++k) record(o, k);
+    text[sidx] = o.str();
+  }, 1);
+  std::ofstream o(path.c_str(), std::ios::binary);
+  o << header;
+  for (const std::string& t : text) o.write(t.data(), (std::streamsize)t.size());
+}
+}  // namespace
+
 void Pipeline::write(const std::string& base, bool ply, bool patch, bool pset) {   // patchOrganizerS.cpp:89-132, 687-779
   {
   Tick tk(this, "write.total");
@@ -981,22 +1017,20 @@ void Pipeline::write(const std::string& base, bool ply, bool patch, bool pset) {
       }
       if (pmvsb_patch_colors_batch(gpu_, P, stride, coords.data(), images.data(), nimages.data(), rgb.data())) die("patch_colors_batch");
     }
-    std::ofstream o((base + ".ply").c_str());
-    o << std::setprecision(std::numeric_limits<double>::max_digits10);
-    o << "ply\nformat ascii 1.0\nelement vertex " << P << "\nproperty float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\n"
+    std::ostringstream h;
+    h << "ply\nformat ascii 1.0\nelement vertex " << P << "\nproperty float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\n"
       << "property float nz\nproperty uchar diffuse_red\nproperty uchar diffuse_green\nproperty uchar diffuse_blue\nproperty float quality\nend_header\n";
-    for (int k = 0; k < P; ++k) {
+    write_records(base + ".ply", h.str(), P, threads_, std::numeric_limits<double>::max_digits10, [&](std::ostream& o, int k) {
       const Patch& p = patches_[ids[k]];
       o << p.coord[0] << ' ' << p.coord[1] << ' ' << p.coord[2] << ' ' << p.normal[0] << ' ' << p.normal[1] << ' ' << p.normal[2] << ' '
         << (int)rgb[3 * k] << ' ' << (int)rgb[3 * k + 1] << ' ' << (int)rgb[3 * k + 2] << ' ' << p.ncc << '\n';
-    }
+    });
   }
   if (patch) {
     // same text as the reference's `ofstr << patch` (source/pmvs/patch.cpp:30-48); newlines instead of std::endl flushes
-    std::ofstream o((base + ".patch").c_str());
-    o << std::setprecision(std::numeric_limits<double>::max_digits10);
-    o << "PATCHES" << '\n' << P << '\n';
-    for (int k = 0; k < P; ++k) {
+    std::ostringstream h;
+    h << "PATCHES" << '\n' << P << '\n';
+    write_records(base + ".patch", h.str(), P, threads_, std::numeric_limits<double>::max_digits10, [&](std::ostream& o, int k) {
       const Patch& p = patches_[ids[k]];
       o << "PATCHS" << '\n'
         << p.coord[0] << ' ' << p.coord[1] << ' ' << p.coord[2] << ' ' << p.coord[3] << '\n'
@@ -1007,15 +1041,13 @@ void Pipeline::write(const std::string& base, bool ply, bool patch, bool pset) {
       o << '\n' << (int)p.vimages.size() << '\n';
       for (int im : p.vimages) o << image_ids_[im] << ' ';
       o << '\n' << "\n";
-    }
+    });
   }
-  if (pset) {
-    std::ofstream o((base + ".pset").c_str());
-    for (int k = 0; k < P; ++k) {
+  if (pset)
+    write_records(base + ".pset", "", P, threads_, 0, [&](std::ostream& o, int k) {
       const Patch& p = patches_[ids[k]];
       o << p.coord[0] << ' ' << p.coord[1] << ' ' << p.coord[2] << ' ' << p.normal[0] << ' ' << p.normal[1] << ' ' << p.normal[2] << "\n";
-    }
-  }
+    });
   std::cerr << "wrote " << P << " patches to " << base << ".*" << std::endl;
   }
   for (const auto& kv : seconds_) std::cerr << "time " << kv.first << ' ' << kv.second << " s" << std::endl;

@@ -108,7 +108,10 @@ class Pipeline {
   void remove_patch(int id);                // CPatchOrganizerS::removePatch
   std::vector<int> collect_patches() const; // ids of live patches in the reference's collectPatches order
   void rebuild_depth_and_vis(bool additive);
+  struct TableArrays;
+  void marshal(const std::vector<int>& ids, TableArrays& t) const;
   void upload_table(const std::vector<int>& ids);
+  void append_table(const std::vector<int>& ids);
   // ---- rounds
   void seed_round();
   void expand_round();
@@ -139,7 +142,8 @@ class Pipeline {
   std::vector<std::vector<Feature>> features_;
   std::vector<ImageGrid> grids_;
   std::vector<Patch> patches_;
-  std::vector<int> table_ids_;              // ids in the table last uploaded to the GPU
+  std::vector<int> table_ids_;              // table index -> patch id, for the table resident on the GPU
+  std::vector<int> table_index_;            // patch id -> table index (-1: not in the table)
   std::map<std::string, double> seconds_;   // wall time per phase (printed by write())
  public:
   struct Tick {

@@ -218,34 +218,46 @@ Pipeline::~Pipeline() {
 void Pipeline::load() {
   Tick tk(this, "load.total");
   if (num_ == 0 || tnum_ == 0) fatal("No target images");
-  if (pmvsb_create(&gpu_, 0, num_, tnum_, opt_.level, opt_.csize, opt_.wsize, opt_.minImageNum, opt_.threshold, opt_.maxAngleDeg) != 0)
+  // the files are read by the CPU threads while this thread brings the CUDA context up
+  struct Loaded { float P[12]; std::vector<unsigned char> rgb; int w = 0, h = 0; std::string error; };
+  std::vector<Loaded> loaded(num_);
+  std::thread reader([&]() {
+    parallel_for(num_, threads_, [&](int i) {
+      Loaded& L = loaded[i];
+      char name[1024];
+      std::snprintf(name, sizeof(name), "%stxt/%08d.txt", opt_.prefix.c_str(), image_ids_[i]);
+      if (!read_camera(name, L.P)) {
+        std::snprintf(name, sizeof(name), "%stxt/%04d.txt", opt_.prefix.c_str(), image_ids_[i]);
+        if (!read_camera(name, L.P)) { L.error = std::string("Cannot read camera: ") + name; return; }
+      }
+      std::snprintf(name, sizeof(name), "%svisualize/%08d.ppm", opt_.prefix.c_str(), image_ids_[i]);
+      if (!read_ppm(name, L.rgb, L.w, L.h)) {
+        std::snprintf(name, sizeof(name), "%svisualize/%04d.ppm", opt_.prefix.c_str(), image_ids_[i]);
+        if (!read_ppm(name, L.rgb, L.w, L.h)) {
+          std::snprintf(name, sizeof(name), "%svisualize/%08d.jpg", opt_.prefix.c_str(), image_ids_[i]);
+          if (std::ifstream(name)) L.error = std::string("JPEG input is not supported by pmvs-b200 (convert to binary PPM): ") + name;
+          else L.error = "Unsupported iamge format found. Stop allocation: " + std::string(name);
+        }
+      }
+    }, 1);
+  });
+  int created;
+  { Tick tk2(this, "load.create_gpu_context");
+    created = pmvsb_create(&gpu_, 0, num_, tnum_, opt_.level, opt_.csize, opt_.wsize, opt_.minImageNum, opt_.threshold, opt_.maxAngleDeg); }
+  { Tick tk2(this, "load.wait_for_files"); reader.join(); }
+  if (created != 0)
     fatal("pmvs-b200: cannot create a GPU context (CUDA device required; there is no CPU fallback) or bad options");
   cams_.resize(num_);
   lw_.resize(num_); lh_.resize(num_);
   level_rgb_.resize(num_);
   std::cerr << "Reading images: " << std::flush;
   for (int i = 0; i < num_; ++i) {
-    char name[1024];
-    float P[12];
-    std::snprintf(name, sizeof(name), "%stxt/%08d.txt", opt_.prefix.c_str(), image_ids_[i]);
-    if (!read_camera(name, P)) {
-      std::snprintf(name, sizeof(name), "%stxt/%04d.txt", opt_.prefix.c_str(), image_ids_[i]);
-      if (!read_camera(name, P)) fatal(std::string("Cannot read camera: ") + name);
-    }
-    if (pmvsb_upload_camera(gpu_, i, P)) die("upload_camera");
-    std::vector<unsigned char> rgb;
-    int w = 0, h = 0;
-    std::snprintf(name, sizeof(name), "%svisualize/%08d.ppm", opt_.prefix.c_str(), image_ids_[i]);
-    if (!read_ppm(name, rgb, w, h)) {
-      std::snprintf(name, sizeof(name), "%svisualize/%04d.ppm", opt_.prefix.c_str(), image_ids_[i]);
-      if (!read_ppm(name, rgb, w, h)) {
-        std::snprintf(name, sizeof(name), "%svisualize/%08d.jpg", opt_.prefix.c_str(), image_ids_[i]);
-        if (std::ifstream(name)) fatal(std::string("JPEG input is not supported by pmvs-b200 (convert to binary PPM): ") + name);
-        fatal("Unsupported iamge format found. Stop allocation: " + std::string(name));
-      }
-    }
-    if (pmvsb_upload_image(gpu_, i, w, h, rgb.data())) die("upload_image");
+    Loaded& L = loaded[i];
+    if (!L.error.empty()) fatal(L.error);
+    if (pmvsb_upload_camera(gpu_, i, L.P)) die("upload_camera");
+    if (pmvsb_upload_image(gpu_, i, L.w, L.h, L.rgb.data())) die("upload_image");
     if (pmvsb_set_visdata2(gpu_, i, opt_.visdata2[i].data(), (int)opt_.visdata2[i].size())) die("set_visdata2");
+    std::vector<unsigned char>().swap(L.rgb);
     std::cerr << '*' << std::flush;
   }
   std::cerr << std::endl;
