@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--height", type=int, default=1200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline budget")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the end-to-end pmvs2 wall-time measurement")
     return ap.parse_args()
 
 
@@ -168,6 +169,48 @@ def make_seed_patches(scene, gpu_lib, n, seed, device):
 
 
 # --------------------------------------------------------------------------------------------------------
+# second half of BASELINE.json's metric: wall time of the whole pmvs2 run on the workload's scene
+# --------------------------------------------------------------------------------------------------------
+def pipeline_wall_time(scene, impl):
+    """Runs the drop-in binary (impl 'b200') or the reference binary built from the reference's own sources (impl
+    'reference', all host threads) on the scene written to disk as PPM + txt + option file; returns a dict."""
+    import subprocess
+    cores = os.cpu_count() or 1
+    prefix = write_scene_for_reference(scene, cores)
+    exe = os.path.join(ROOT, "cmvs-pmvs_b200", "bin", "pmvs2") if impl == "b200" else os.path.join(ROOT, "oracle", "_ref", "pmvs3_ref")
+    if not os.path.exists(exe):
+        return {"scene": scene.name, "unavailable": os.path.relpath(exe, ROOT) + " not built"}
+    t0 = time.perf_counter()
+    p = subprocess.run([exe, prefix, "option.txt", "PSET"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    secs = time.perf_counter() - t0
+    out = {"scene": "%s %d views %dx%d level %d csize %d" % (scene.name, scene.num, scene.width, scene.height, scene.option["level"], scene.option["csize"]),
+           "binary": os.path.relpath(exe, ROOT), "wall_seconds": secs, "host_threads": cores, "returncode": p.returncode}
+    try:
+        with open(prefix + "models/option.txt.pset") as f:
+            out["patches"] = sum(1 for _ in f)
+    except OSError:
+        out["patches"] = None
+    refined = [int(l.split()[-1]) for l in p.stderr.splitlines() if l.startswith("Total pass fail0 fail1 refinepatch:") and "." not in l.split()[-1]]
+    if refined:
+        out["refined_patches"] = int(sum(refined))                      # the reference's own "refinepatch" counter (SURVEY 8d)
+        out["refined_patches_per_sec_whole_run"] = out["refined_patches"] / secs
+    import shutil
+    shutil.rmtree(prefix, ignore_errors=True)
+    return out
+
+
+def measured_traffic(patches):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_refine launch from the committed `ncu --set full` capture
+    (profiles/r1_k_refine_dram.json); only valid for the launch size it was captured on."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_k_refine_dram.json")) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_per_launch"]) if int(d["patches_per_launch"]) == int(patches) else None
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU code (oracle/_ref), bounded sample per step
 # --------------------------------------------------------------------------------------------------------
 def write_scene_for_reference(scene, cpu_threads):
@@ -250,6 +293,8 @@ def main():
                                  "evals_per_patch": r["evals_per_patch"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
+        if not args.no_pipeline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "pmvs3_ref")):
+            line["pipeline"] = pipeline_wall_time(scene, "reference")
         print(json.dumps(line))
         return
 
@@ -359,7 +404,7 @@ def main():
     k_ms = float(np.mean(kernel_ms))
     achieved = alg_bytes / (k_ms / 1000.0) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_refine<7>", "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth",
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "kernel_ms": k_ms,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(P), "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "evals_per_patch": evals_sum / P,
                 "note": "algorithmic bytes = 588 B x views x (evaluations + 1) per patch (SURVEY.md 8d); most gathers hit L1/L2, "
                         "so HBM traffic is far below this figure and the kernel is FP32/issue bound"}
@@ -376,9 +421,11 @@ def main():
         r = reference_rate(scene, (coords[:n], normals[:n], images[:n], dsc[:n]), seconds=args.cpu_seconds)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                                 "evals_per_patch": r["evals_per_patch"]}
+    lib.close()
+    if rank == 0 and world == 1 and not args.no_pipeline:
+        line["pipeline"] = pipeline_wall_time(scene, "b200")
     if rank == 0:
         print(json.dumps(line))
-    lib.close()
     if world > 1:
         dist.destroy_process_group()
 
