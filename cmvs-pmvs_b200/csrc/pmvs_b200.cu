@@ -5,6 +5,8 @@
 #include "../../include/pmvs_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -21,7 +23,7 @@
 #include "pmvs_cells.cuh"
 
 #ifndef PMVS_MINBLOCKS
-#define PMVS_MINBLOCKS 6
+#define PMVS_MINBLOCKS 8
 #endif
 
 using namespace pmvsb;
@@ -546,6 +548,10 @@ struct pmvsb_ctx {
   int32_t* d_vis_idx = nullptr;
   SelectParams select;
   bool finalized = false;
+  ncclComm_t comm = nullptr;        // wave exchange across GPUs (one process per GPU)
+  int comm_rank = 0, comm_world = 1;
+  char* comm_buf = nullptr;
+  size_t comm_cap = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -794,6 +800,34 @@ static T* arena_take(pmvsb_ctx* ctx, size_t n) {
   return reinterpret_cast<T*>(ctx->arena + off);
 }
 
+// ---- NCCL, bound at run time: a single-GPU run never needs the library, and inside a Python process the copy that
+// torch already loaded (same soname) is the one that gets used
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  const char* (*GetErrorString)(ncclResult_t);
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static int state = 0;   // 0 untried, 1 ok, -1 unavailable
+  if (state == 0) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    state = -1;
+    if (h) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+      api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+      if (api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString) state = 1;
+    }
+  }
+  return state == 1 ? &api : nullptr;
+}
+
 // ---- resident patch table: grow-only arrays, cell lists built on the device -----------------------------------
 template <typename T>
 static int dvec_reserve(pmvsb_ctx* ctx, DVec<T>& v, size_t n, size_t keep = 0) {
@@ -945,6 +979,8 @@ int pmvsb_destroy(pmvsb_ctx* ctx) {
   cudaFree(ctx->d_cams); cudaFree(ctx->d_levels); cudaFree(ctx->d_counter); cudaFree(ctx->d_vis_off); cudaFree(ctx->d_vis_idx);
   cudaFree(ctx->arena);
   store_free(ctx);
+  if (ctx->comm && nccl_api()) nccl_api()->CommDestroy(ctx->comm);
+  cudaFree(ctx->comm_buf);
   for (auto& b : ctx->pool) cudaFree(b.second);
   g_current = nullptr;
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1814,6 +1850,57 @@ int pmvsb_refine_batch(pmvsb_ctx* ctx, int P, int stride, float* coords, float* 
   CK(cudaMemcpyAsync(ok, d_ok, sizeof(uint8_t) * nP, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (flags[1]) return fail(ctx, PMVSB_EINVAL, "image index out of range in patch batch (those patches were skipped, ok = 0)");
+  return PMVSB_OK;
+}
+
+// ---- multi-GPU: one process (and one context) per GPU; the only exchange of the path is the all-gather of a wave's results
+int pmvsb_comm_unique_id(pmvsb_ctx* ctx, uint8_t* id128) {
+  if (!ctx || !id128) return fail(ctx, PMVSB_EINVAL, "comm_unique_id: null pointer");
+  NcclApi* api = nccl_api();
+  if (!api) return fail(ctx, PMVSB_ESTATE, "comm_unique_id: libnccl.so.2 could not be loaded");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  const ncclResult_t r = api->GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(ctx, PMVSB_ECUDA, std::string("ncclGetUniqueId: ") + api->GetErrorString(r));
+  std::memcpy(id128, &id, 128);
+  return PMVSB_OK;
+}
+
+int pmvsb_comm_init(pmvsb_ctx* ctx, int rank, int world, const uint8_t* id128) {
+  if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return fail(ctx, PMVSB_EINVAL, "comm_init: bad argument");
+  if (ctx->comm) return fail(ctx, PMVSB_ESTATE, "comm_init: communicator already initialised");
+  NcclApi* api = nccl_api();
+  if (!api) return fail(ctx, PMVSB_ESTATE, "comm_init: libnccl.so.2 could not be loaded");
+  CK(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  const ncclResult_t r = api->CommInitRank(&ctx->comm, world, id, rank);
+  if (r != ncclSuccess) { ctx->comm = nullptr; return fail(ctx, PMVSB_ECUDA, std::string("ncclCommInitRank: ") + api->GetErrorString(r)); }
+  ctx->comm_rank = rank; ctx->comm_world = world;
+  return PMVSB_OK;
+}
+
+int pmvsb_allgather(pmvsb_ctx* ctx, const void* send, size_t bytes, void* recv) {
+  if (!ctx || (bytes > 0 && (!send || !recv))) return fail(ctx, PMVSB_EINVAL, "allgather: null pointer");
+  if (bytes == 0) return PMVSB_OK;
+  if (ctx->comm_world == 1) { std::memcpy(recv, send, bytes); return PMVSB_OK; }
+  if (!ctx->comm) return fail(ctx, PMVSB_ESTATE, "allgather: call pmvsb_comm_init first");
+  NcclApi* api = nccl_api();
+  CK(cudaSetDevice(ctx->device));
+  const size_t need = bytes * ((size_t)ctx->comm_world + 1);
+  if (need > ctx->comm_cap) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->comm_buf); ctx->comm_buf = nullptr; ctx->comm_cap = 0;
+    CK(cudaMalloc((void**)&ctx->comm_buf, need + need / 2));
+    ctx->comm_cap = need + need / 2;
+  }
+  char* d_send = ctx->comm_buf;
+  char* d_recv = ctx->comm_buf + bytes;
+  CK(cudaMemcpyAsync(d_send, send, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const ncclResult_t r = api->AllGather(d_send, d_recv, bytes, ncclChar, ctx->comm, ctx->stream);
+  if (r != ncclSuccess) return fail(ctx, PMVSB_ECUDA, std::string("ncclAllGather: ") + api->GetErrorString(r));
+  CK(cudaMemcpyAsync(recv, d_recv, bytes * (size_t)ctx->comm_world, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return PMVSB_OK;
 }
 

@@ -10,7 +10,7 @@
 // 3 steps (ncu evidence: profiles/).
 //
 // Arithmetic policy is unchanged for everything that decides an integer (angle gate, level pick,
-// grabSafe, sample positions: reference f32 operation order, IEEE div/sqrt, no FMA).  The texture
+// grabSafe, window origin and steps: reference f32 operation order, IEEE div/sqrt, no FMA).  The texture
 // statistics are evaluated as   NCC = sum_c sum_k (a_k - mean_a)(b_k - mean_b) / (147 sd_a sd_b)
 // with two-pass means, i.e. without the reference's per-element division (optim.cpp:1061-1066); that
 // differs from the reference by rounding only (~1e-7, bar 1e-4).
@@ -20,6 +20,21 @@
 namespace pmvsb {
 
 constexpr int kGroup = 8;  // lanes per patch
+
+// Instruction-count switches of the scoring loop, all ON by default (measured on B200, 262 144 patches x 5 views:
+// 76.0 ms with all off, 68.9 ms with FAST_POS + FMA_INTERP, 65.2 ms with FOLD_PIVOT and 8 resident blocks per SM).
+// They change roundings inside the texture statistics only (positions by a few ulp, colours by <= 2 ulp), never a
+// texel choice by more than the continuous bilinear hand-over, and no integer decision: my_f / computeINCC stay
+// within ~1e-6 of the reference (bar 1e-4).  The bit-exact texture path is k_grab_tex (pmvs_device.cuh).
+#ifndef PMVS_FAST_POS
+#define PMVS_FAST_POS 1
+#endif
+#ifndef PMVS_FMA_INTERP
+#define PMVS_FMA_INTERP 1
+#endif
+#ifndef PMVS_FOLD_PIVOT
+#define PMVS_FOLD_PIVOT 1
+#endif
 
 __device__ __forceinline__ float group_sum(float v) {
   v += __shfl_xor_sync(kFull, v, 4);
@@ -35,7 +50,8 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, uint32_t magic, ui
 }
 
 // CImage::getColor (include/image/image.hpp:435-476) on RGBA8 words; same operation order as get_color().
-__device__ __forceinline__ void get_color_fast(const uint32_t* __restrict__ pix, int w, uint32_t magic, float x, float y, float* rgb) {
+__device__ __forceinline__ void get_color_fast(const uint32_t* __restrict__ pix, int w, uint32_t magic, float x, float y, float* rgb,
+                                               float pv0 = 0.0f, float pv1 = 0.0f, float pv2 = 0.0f) {
   const int lx = (int)x;
   const int ly = (int)y;
   const float dx1 = x - (float)lx, dx0 = 1.0f - dx1;
@@ -43,6 +59,21 @@ __device__ __forceinline__ void get_color_fast(const uint32_t* __restrict__ pix,
   const float f00 = dx0 * dy0, f01 = dx0 * dy1, f10 = dx1 * dy0, f11 = dx1 * dy1;
   const uint32_t* p = pix + (ly * w + lx);  // < 2^31 texels per level
   const uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + w), d = __ldg(p + w + 1);
+#if PMVS_FMA_INTERP
+  // contracted: 1 FMUL + 3 FFMA per channel instead of 4 FMUL + 3 FADD; differs from the reference's sum by rounding
+  // only (<= 2 ulp of a value in [0, 255]), the texel choice is unchanged
+  // (pv = minus the pivot the caller subtracts from every sample: folded into the chain's first FFMA)
+  const float pv[3] = {pv0, pv1, pv2};
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const uint32_t sel = 0x7540u + ch;
+    float v = fmaf(byte_to_float(d, magic, sel), f11, pv[ch]);
+    v = fmaf(byte_to_float(b, magic, sel), f10, v);
+    v = fmaf(byte_to_float(c, magic, sel), f01, v);
+    rgb[ch] = fmaf(byte_to_float(a, magic, sel), f00, v);
+  }
+  return;
+#endif
   rgb[0] = (byte_to_float(a, magic, 0x7540) * f00 + byte_to_float(c, magic, 0x7540) * f01) + (byte_to_float(b, magic, 0x7540) * f10 + byte_to_float(d, magic, 0x7540) * f11);
   rgb[1] = (byte_to_float(a, magic, 0x7541) * f00 + byte_to_float(c, magic, 0x7541) * f01) + (byte_to_float(b, magic, 0x7541) * f10 + byte_to_float(d, magic, 0x7541) * f11);
   rgb[2] = (byte_to_float(a, magic, 0x7542) * f00 + byte_to_float(c, magic, 0x7542) * f01) + (byte_to_float(b, magic, 0x7542) * f10 + byte_to_float(d, magic, 0x7542) * f11);
@@ -142,8 +173,12 @@ template <int WSIZE>
 struct ColSteps {
   float sx[WSIZE - 1], sy[WSIZE - 1];
   __device__ __forceinline__ void set(const ViewWin& w, int gl) {
+#if PMVS_FAST_POS
+    sx[0] = w.dxx; sx[1] = w.dxy; sy[0] = (float)gl;   // step vector and this lane's column
+#else
 #pragma unroll
     for (int i = 0; i < WSIZE - 1; ++i) { sx[i] = i < gl ? w.dxx : 0.0f; sy[i] = i < gl ? w.dxy : 0.0f; }
+#endif
   }
 };
 
@@ -151,17 +186,17 @@ struct ColSteps {
 // `left`).  Idle lanes pass pix = SceneDev::dummy_pix and sample texel (0,0) of it: no branch in the row loop.
 template <int WSIZE>
 __device__ __forceinline__ void sample_row(const uint32_t* __restrict__ pix, int w, uint32_t magic, const ColSteps<WSIZE>& cs,
-                                           float bx, float by, float* rgb) {
+                                           float bx, float by, float* rgb, float pv0 = 0.0f, float pv1 = 0.0f, float pv2 = 0.0f) {
 #if PMVS_FAST_POS
-  float x = bx, y = by;
-#pragma unroll
-  for (int i = 0; i < WSIZE - 1; ++i) { x += cs.sx[i]; y += cs.sy[i]; }
+  // closed form bx + gl * dx (one FFMA per coordinate) instead of replaying the reference's running sum: the position
+  // differs by a few ulp, bilinear interpolation is continuous across texel borders, so the colour moves by ~1e-6
+  const float x = fmaf(cs.sx[0], cs.sy[0], bx), y = fmaf(cs.sx[1], cs.sy[0], by);
 #else
   float x = bx, y = by;
 #pragma unroll
   for (int i = 0; i < WSIZE - 1; ++i) { x += cs.sx[i]; y += cs.sy[i]; }
 #endif
-  get_color_fast(pix, w, magic, x, y, rgb);
+  get_color_fast(pix, w, magic, x, y, rgb, pv0, pv1, pv2);
 }
 
 // per-group patch context; every lane of the group holds the same values except my_image / my_weight
@@ -205,9 +240,6 @@ __device__ __forceinline__ void group_ctx_init(const SceneDev& s, GroupCtx& gc, 
 
 #ifndef PMVS_CUSTOM_SINCOS
 #define PMVS_CUSTOM_SINCOS 0
-#endif
-#ifndef PMVS_FAST_POS
-#define PMVS_FAST_POS 0
 #endif
 #ifndef PMVS_ROW_UNROLL
 #define PMVS_ROW_UNROLL 1
@@ -344,10 +376,17 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
     PMVS_UNROLL_ROWS
     for (int row = 0; row < WSIZE; ++row) {
       float rgb[3];
+#if PMVS_FMA_INTERP && PMVS_FOLD_PIVOT
+      sample_row<WSIZE>(pix, lw, s.f32_2p23, cs, bx, by, rgb, -ra0, -ra1, -ra2);   // rgb = sample - reference mean (ra = 0 for the reference view)
+      const float4 d = reftex[row * rstride];
+      if (is_ref) reftex[row * rstride] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+      const float b0 = rgb[0], b1 = rgb[1], b2 = rgb[2];
+#else
       sample_row<WSIZE>(pix, lw, s.f32_2p23, cs, bx, by, rgb);
       const float4 d = reftex[row * rstride];
       if (is_ref) reftex[row * rstride] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
       const float b0 = rgb[0] - ra0, b1 = rgb[1] - ra1, b2 = rgb[2] - ra2;
+#endif
       s0 += b0; s1 += b1; s2 += b2;
       q = fmaf(b0, b0, q); q = fmaf(b1, b1, q); q = fmaf(b2, b2, q);
       cr = fmaf(d.x, b0, cr); cr = fmaf(d.y, b1, cr); cr = fmaf(d.z, b2, cr);

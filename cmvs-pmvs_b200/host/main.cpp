@@ -3,6 +3,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <iostream>
 #include <string>
 
@@ -32,7 +33,10 @@ int main(int argc, char* argv[]) {
   for (int i = 0; i < argc; ++i) std::cout << std::endl << argv[i];
   std::cout << std::endl;
   const pmvs::Options opt = pmvs::parse_options(argv[1], argv[2]);
-  pmvs::Pipeline pipe(opt);
+  const pmvs::Dist dist = pmvs::Dist::from_env();   // WORLD_SIZE > 1: one process per GPU (distributed.cpp)
+  static std::ofstream quiet;
+  if (dist.rank != 0) { quiet.open("/dev/null"); std::cerr.rdbuf(quiet.rdbuf()); std::cout.rdbuf(quiet.rdbuf()); }   // rank 0 reports
+  pmvs::Pipeline pipe(opt, dist);
   pipe.load();
   pipe.run();
   bool patch = false, pset = false;
@@ -41,7 +45,7 @@ int main(int argc, char* argv[]) {
     if (a == "PATCH") patch = true;
     if (a == "PSET") pset = true;
   }
-  pipe.write(std::string(argv[1]) + "models/" + argv[2], true, patch, pset);
+  pipe.write(std::string(argv[1]) + "models/" + argv[2], true, patch, pset);   // rank 0 writes
   std::cerr << "time main.total " << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() << " s" << std::endl;
   return 0;
 }

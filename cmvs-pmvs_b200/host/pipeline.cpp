@@ -354,11 +354,11 @@ void Pipeline::rebuild_depth_and_vis(bool additive) {
 }
 
 // ---------------------------------------------------------------------------------------------- evaluate a wave
-void Pipeline::evaluate(std::vector<Candidate>& cands, std::vector<int>& verdict) {
-  Tick tk_all(this, "evaluate.total");
-  const int P = (int)cands.size();
-  verdict.assign(P, 1);
-  if (P == 0) return;
+void Pipeline::evaluate_range(std::vector<Candidate>& all, std::vector<int>& all_verdict, int lo, int hi) {
+  const int P = hi - lo;
+  if (P <= 0) return;
+  Candidate* cands = all.data() + lo;      // this rank's shard of the wave
+  int* verdict = all_verdict.data() + lo;
   const int stride = std::min(num_, 64);
   std::vector<float> coords((size_t)4 * P), normals((size_t)4 * P), dsc(P), asc(P), ncc(P, -1.0f), tmp(P);
   std::vector<int32_t> images((size_t)stride * P, 0), nimages(P), v0(P), evals(P), grids((size_t)2 * stride * P), timages(P), v1(P);
@@ -427,6 +427,70 @@ void Pipeline::evaluate(std::vector<Candidate>& cands, std::vector<int>& verdict
       p.vimages.push_back(avim[(size_t)j * vs + i]);
       p.vgrids.push_back({avgr[((size_t)j * vs + i) * 2], avgr[((size_t)j * vs + i) * 2 + 1]});
     }
+  }
+}
+
+// pre -> refine -> post (+ vimages at depth >= 1) for a wave.  With several GPUs every rank evaluates a contiguous shard
+// and the results are all-gathered, so that all ranks commit the same wave.
+void Pipeline::evaluate(std::vector<Candidate>& cands, std::vector<int>& verdict) {
+  Tick tk_all(this, "evaluate.total");
+  const int P = (int)cands.size();
+  verdict.assign(P, 1);
+  if (P == 0) return;
+  int lo = 0, hi = P;
+  Dist::shard(P, dist_.world, dist_.rank, lo, hi);
+  evaluate_range(cands, verdict, lo, hi);
+  if (dist_.world > 1) exchange_results(cands, verdict);
+}
+
+// Fixed-size record per candidate: verdict, the CPatch fields post-processing produced, its visible-image lists.
+void Pipeline::exchange_results(std::vector<Candidate>& cands, std::vector<int>& verdict) {
+  Tick tk(this, "gpu.allgather_wave");
+  const int P = (int)cands.size(), W = dist_.world;
+  const int stride = std::min(num_, 64), vs = tnum_;
+  const int words = 4 + 12 + 3 * stride + 3 * vs;            // int32 / float32 words per record
+  const int per_rank = (P + W - 1) / W + 1;                   // every shard fits (shards differ by at most one)
+  std::vector<int32_t> send((size_t)per_rank * words, 0), recv((size_t)per_rank * words * W, 0);
+  int lo = 0, hi = 0;
+  Dist::shard(P, W, dist_.rank, lo, hi);
+  parallel_for(hi - lo, threads_, [&](int j) {
+    const Patch& p = cands[lo + j].patch;
+    int32_t* r = send.data() + (size_t)j * words;
+    float* f = reinterpret_cast<float*>(r + 4);
+    r[0] = verdict[lo + j];
+    if (r[0] != 0) return;
+    r[1] = (int32_t)std::min<size_t>(p.images.size(), stride); r[2] = (int32_t)std::min<size_t>(p.vimages.size(), vs); r[3] = p.timages;
+    for (int c = 0; c < 4; ++c) { f[c] = p.coord[c]; f[4 + c] = p.normal[c]; }
+    f[8] = p.ncc; f[9] = p.dscale; f[10] = p.ascale; f[11] = p.tmp;
+    int32_t* q = r + 16;
+    for (int i = 0; i < r[1]; ++i) { q[i] = p.images[i]; q[stride + 2 * i] = p.grids[i][0]; q[stride + 2 * i + 1] = p.grids[i][1]; }
+    q += 3 * stride;
+    for (int i = 0; i < r[2]; ++i) { q[i] = p.vimages[i]; q[vs + 2 * i] = p.vgrids[i][0]; q[vs + 2 * i + 1] = p.vgrids[i][1]; }
+  }, 256);
+  if (pmvsb_allgather(gpu_, send.data(), send.size() * sizeof(int32_t), recv.data())) die("allgather");
+  for (int rk = 0; rk < W; ++rk) {
+    if (rk == dist_.rank) continue;
+    int rlo = 0, rhi = 0;
+    Dist::shard(P, W, rk, rlo, rhi);
+    const int32_t* base = recv.data() + (size_t)rk * per_rank * words;
+    parallel_for(rhi - rlo, threads_, [&](int j) {
+      const int32_t* r = base + (size_t)j * words;
+      const float* f = reinterpret_cast<const float*>(r + 4);
+      verdict[rlo + j] = r[0];
+      if (r[0] != 0) return;
+      Patch& p = cands[rlo + j].patch;
+      for (int c = 0; c < 4; ++c) { p.coord[c] = f[c]; p.normal[c] = f[4 + c]; }
+      p.ncc = f[8]; p.dscale = f[9]; p.ascale = f[10]; p.tmp = f[11];
+      p.timages = r[3];
+      const int32_t* q = r + 16;
+      p.images.assign(q, q + r[1]);
+      p.grids.resize(r[1]);
+      for (int i = 0; i < r[1]; ++i) p.grids[i] = {q[stride + 2 * i], q[stride + 2 * i + 1]};
+      q += 3 * stride;
+      p.vimages.assign(q, q + r[2]);
+      p.vgrids.resize(r[2]);
+      for (int i = 0; i < r[2]; ++i) p.vgrids[i] = {q[vs + 2 * i], q[vs + 2 * i + 1]};
+    }, 256);
   }
 }
 
@@ -998,6 +1062,7 @@ void write_records(const std::string& path, const std::string& header, int P, in
 }  // namespace
 
 void Pipeline::write(const std::string& base, bool ply, bool patch, bool pset) {   // patchOrganizerS.cpp:89-132, 687-779
+  if (!is_root()) return;   // every rank holds the same patches; one of them writes
   {
   Tick tk(this, "write.total");
   const std::vector<int> ids = collect_patches();

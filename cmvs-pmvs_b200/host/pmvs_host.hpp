@@ -55,6 +55,16 @@ struct Options {   // source/pmvs/option.cpp:10-28, 47-109
 };
 Options parse_options(const std::string& prefix, const std::string& option);
 
+// one process per GPU (distributed.cpp); world = 1 is the ordinary single-GPU run
+struct Dist {
+  int rank = 0, world = 1, local_rank = 0, port = 0;
+  std::string master_addr;
+  static Dist from_env();
+  void broadcast_from_root(void* buf, size_t n) const;
+  // contiguous balanced shard of n items for rank r
+  static void shard(int n, int world, int r, int& lo, int& hi) { lo = (int)((long long)n * r / world); hi = (int)((long long)n * (r + 1) / world); }
+};
+
 struct Camera {
   float P[3][4];       // at the working level
   float centre[4], oaxis[4], xaxis[3], yaxis[3], zaxis[3], ipscale;
@@ -85,7 +95,8 @@ struct Stats { long trial = 0, pass = 0, fail0 = 0, fail1 = 0; };
 
 class Pipeline {
  public:
-  explicit Pipeline(const Options& o);
+  explicit Pipeline(const Options& o, const Dist& dist = Dist());
+  bool is_root() const { return dist_.rank == 0; }
   ~Pipeline();
   void load();                 // images + cameras -> GPU context, features
   void run();                  // seed, 3 x (expand, filter)
@@ -125,9 +136,12 @@ class Pipeline {
   struct Candidate { Patch patch; int parent = -1; int dir = -1; int cell = -1; int feature = -1; int order = 0; };
   // pre -> refine -> post (+ vimages at depth >= 1) for a batch; verdict[i] = 0 accepted, 1 failed in preProcess, 2 in postProcess
   void evaluate(std::vector<Candidate>& cands, std::vector<int>& verdict);
+  void evaluate_range(std::vector<Candidate>& cands, std::vector<int>& verdict, int lo, int hi);
+  void exchange_results(std::vector<Candidate>& cands, std::vector<int>& verdict);
   void die(const std::string& where) const;
 
   Options opt_;
+  Dist dist_;
   pmvsb_ctx* gpu_ = nullptr;
   int num_ = 0, tnum_ = 0, tau_ = 0, depth_ = 0, threads_ = 1;
   float ncc_threshold_ = 0.7f, ncc_threshold_before_ = 0.4f;

@@ -200,7 +200,7 @@ void Pipeline::die(const std::string& where) const {
   std::exit(1);
 }
 
-Pipeline::Pipeline(const Options& o) : opt_(o) {
+Pipeline::Pipeline(const Options& o, const Dist& dist) : opt_(o), dist_(dist) {
   image_ids_ = o.timages;
   image_ids_.insert(image_ids_.end(), o.oimages.begin(), o.oimages.end());
   tnum_ = (int)o.timages.size();
@@ -208,7 +208,7 @@ Pipeline::Pipeline(const Options& o) : opt_(o) {
   tau_ = std::min(o.minImageNum * 2, num_);                 // findMatch.cpp:56
   ncc_threshold_ = o.threshold;
   ncc_threshold_before_ = o.threshold - 0.3f;               // findMatch.cpp:104
-  threads_ = std::max(1, std::min(o.CPU, (int)std::thread::hardware_concurrency()));
+  threads_ = std::max(1, std::min(o.CPU, (int)std::thread::hardware_concurrency() / std::max(1, dist.world)));   // the ranks share the host cores
 }
 
 Pipeline::~Pipeline() {
@@ -243,10 +243,17 @@ void Pipeline::load() {
   });
   int created;
   { Tick tk2(this, "load.create_gpu_context");
-    created = pmvsb_create(&gpu_, 0, num_, tnum_, opt_.level, opt_.csize, opt_.wsize, opt_.minImageNum, opt_.threshold, opt_.maxAngleDeg); }
+    created = pmvsb_create(&gpu_, dist_.local_rank, num_, tnum_, opt_.level, opt_.csize, opt_.wsize, opt_.minImageNum, opt_.threshold, opt_.maxAngleDeg); }
   { Tick tk2(this, "load.wait_for_files"); reader.join(); }
   if (created != 0)
     fatal("pmvs-b200: cannot create a GPU context (CUDA device required; there is no CPU fallback) or bad options");
+  if (dist_.world > 1) {   // NCCL communicator over the GPUs of this run
+    Tick tk2(this, "load.nccl_init");
+    uint8_t id[128] = {0};
+    if (dist_.rank == 0 && pmvsb_comm_unique_id(gpu_, id)) die("comm_unique_id");
+    dist_.broadcast_from_root(id, sizeof(id));
+    if (pmvsb_comm_init(gpu_, dist_.rank, dist_.world, id)) die("comm_init");
+  }
   cams_.resize(num_);
   lw_.resize(num_); lh_.resize(num_);
   level_rgb_.resize(num_);

@@ -27,6 +27,7 @@
 #ifndef PMVS_B200_H
 #define PMVS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -196,6 +197,18 @@ int pmvsb_refine_batch(pmvsb_ctx* ctx, int P, int stride, float* coords, float* 
 int pmvsb_refine_batch_dev(pmvsb_ctx* ctx, int P, int stride, float* d_coords, float* d_normals,
                            const int32_t* d_images, const int32_t* d_nimages, const float* d_dscales,
                            float* d_ncc, int32_t* d_evals, uint8_t* d_ok);
+/* ---- multi-GPU -------------------------------------------------------------------------------------
+ * One process and one context per GPU, images and cameras replicated (the reference shares one CPhotoSetS between its
+ * worker threads, findMatch.hpp).  The candidates of a wave are independent given the grid snapshot, so each rank
+ * evaluates a contiguous shard and the ONLY exchange is the all-gather of the per-candidate result records, after
+ * which every rank applies the same deterministic commit (the role of the per-image locks around _pgrids in
+ * source/pmvs/expand.cpp:225-237).  NCCL is loaded at run time (libnccl.so.2).
+ * rank 0 creates the 128-byte id, the caller hands it to the other ranks (any channel), everybody calls comm_init. */
+int pmvsb_comm_unique_id(pmvsb_ctx* ctx, uint8_t* id128);
+int pmvsb_comm_init(pmvsb_ctx* ctx, int rank, int world, const uint8_t* id128);
+/* host buffers: send = bytes, recv = world * bytes in rank order; identity copy when no communicator (world = 1) */
+int pmvsb_allgather(pmvsb_ctx* ctx, const void* send, size_t bytes, void* recv);
+
 int pmvsb_sync(pmvsb_ctx* ctx);
 /* the CUDA stream (cudaStream_t) the context launches on, for event timing by the caller */
 void* pmvsb_stream(pmvsb_ctx* ctx);

@@ -91,3 +91,24 @@ def test_bad_input_exits_1(tmp_path):
     assert p.returncode == 1 and "option" in p.stderr.lower()
     p = subprocess.run([PMVS2], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert p.returncode == 1 and "Usage" in (p.stderr + p.stdout)
+
+
+def test_two_gpus_write_the_same_models(run, pkg, scene, tmp_path_factory):
+    """One process per GPU (WORLD_SIZE 2): wave shards + NCCL all-gather of the results.  Every candidate is evaluated
+    by exactly one rank with the same kernels, every rank commits the same wave: the models are byte-identical."""
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    G, prefix1, _ = run
+    scene.option["CPU"] = os.cpu_count() or 4
+    prefix2 = pkg.synth.write_scene(scene, str(tmp_path_factory.mktemp("pmvs2_scene_2gpu")))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", "--no-python", PMVS2, prefix2, "option.txt", "PATCH", "PSET"]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-3000:]
+    for ext in (".patch", ".pset", ".ply"):
+        a = open(prefix1 + "models/option.txt" + ext, "rb").read()
+        b = open(prefix2 + "models/option.txt" + ext, "rb").read()
+        assert a == b, ext
+    assert "gpu.allgather_wave" in p.stderr
