@@ -24,7 +24,7 @@ SYMBOLS = [
     "pmvsb_download_depth_map", "pmvsb_depth_maps_add", "pmvsb_store_append", "pmvsb_store_update_vimages",
     "pmvsb_store_download_vimages", "pmvsb_download_cell_lists", "pmvsb_find_empty_blocks_store", "pmvsb_filter_neighbor_store", "pmvsb_set_vimages_store", "pmvsb_filter_exact_store", "pmvsb_compute_gains_store", "pmvsb_set_vimages_batch", "pmvsb_set_ref_image_batch",
     "pmvsb_patch_colors_batch", "pmvsb_refine_batch",
-    "pmvsb_refine_batch_dev", "pmvsb_comm_unique_id", "pmvsb_comm_init", "pmvsb_allgather", "pmvsb_sync", "pmvsb_stream", "pmvsb_set_stream", "pmvsb_launch_count", "pmvsb_last_refine_ms",
+    "pmvsb_refine_batch_dev", "pmvsb_detect_features", "pmvsb_comm_unique_id", "pmvsb_comm_init", "pmvsb_allgather", "pmvsb_sync", "pmvsb_stream", "pmvsb_set_stream", "pmvsb_launch_count", "pmvsb_last_refine_ms",
 ]
 
 
@@ -304,6 +304,13 @@ class PmvsB200:
         p = lambda v: C.c_void_p(int(v)) if v else None
         self._ck(self.lib.pmvsb_refine_batch_dev(self.ctx, int(P), int(stride), p(d_coords), p(d_normals), p(d_images), p(d_nimages),
                                                  p(d_dscales), p(d_ncc), p(d_evals), p(d_ok)))
+
+    def detect_features(self, index, gspeedup=16, cap=65536):
+        xy = np.zeros((cap, 2), np.float32); resp = np.zeros(cap, np.float32); types = np.zeros(cap, np.int32)
+        n = C.c_int32()
+        self._ck(self.lib.pmvsb_detect_features(self.ctx, int(index), int(gspeedup), cap, _vp(xy), _vp(resp), _vp(types), C.byref(n)))
+        k = min(n.value, cap)
+        return xy[:k].copy(), resp[:k].copy(), types[:k].copy()
 
     def comm_unique_id(self):
         buf = (C.c_uint8 * 128)()

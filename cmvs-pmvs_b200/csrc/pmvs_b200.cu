@@ -21,6 +21,7 @@
 #include "pmvs_select.cuh"
 #include "pmvs_filter.cuh"
 #include "pmvs_cells.cuh"
+#include "pmvs_features.cuh"
 
 #ifndef PMVS_MINBLOCKS
 #define PMVS_MINBLOCKS 8
@@ -1850,6 +1851,137 @@ int pmvsb_refine_batch(pmvsb_ctx* ctx, int P, int stride, float* coords, float* 
   CK(cudaMemcpyAsync(ok, d_ok, sizeof(uint8_t) * nP, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (flags[1]) return fail(ctx, PMVSB_EINVAL, "image index out of range in patch batch (those patches were skipped, ok = 0)");
+  return PMVSB_OK;
+}
+
+// ---- feature detection -------------------------------------------------------------------------------------------
+namespace {
+// CDetector::setGaussI (source/pmvs/detector.cpp:31-49); exp is the double libm entry point in the reference's object
+std::vector<float> gauss_taps(float sigma) {
+  const int margin = (int)std::ceil(2 * sigma);
+  std::vector<float> g(2 * margin + 1);
+  float denom = 0.0f;
+  for (int x = 0; x < (int)g.size(); ++x) {
+    const int xt = x - margin;
+    const float d = (float)std::exp((double)(-(xt * xt) / (2 * sigma * sigma)));
+    g[x] = d;
+    denom += d;
+  }
+  for (float& v : g) v /= denom;
+  return g;
+}
+struct FeatPoint { float r; int x, y; long seq; };
+}  // namespace
+
+int pmvsb_detect_features(pmvsb_ctx* ctx, int index, int gspeedup, int cap, float* xy, float* response, int32_t* type, int32_t* count) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (index < 0 || index >= ctx->num || gspeedup < 1 || cap < 0 || !count || (cap > 0 && (!xy || !response || !type)))
+    return fail(ctx, PMVSB_EINVAL, "detect_features: bad argument");
+  const HostImage& hi = ctx->images[index];
+  const int w = hi.w[ctx->level], h = hi.h[ctx->level];
+  const int n = w * h;
+  LevelDev lv;
+  lv.pix = hi.levels[ctx->level]; lv.w = w; lv.h = h;
+  const int factor = 2, gridsize = gspeedup * factor;
+  const int gw = (w + gridsize - 1) / gridsize, gh = (h + gridsize - 1) / gridsize, nb = gw * gh;
+  // filters: derivative, box, Gaussians (Harris sigma 4; DoG 1 * sqrt(2)^k)
+  const float first = 1.0f, last = 3.0f;
+  const float scalestep = (float)std::pow((double)2.0f, (double)(1 / 2.0f));
+  int steps = (int)std::ceil(std::log((double)(last / first)) / std::log((double)scalestep));
+  steps = std::max(4, steps);
+  const int nres = steps + 1;
+  std::vector<std::vector<float>> filters;
+  filters.push_back({-0.5f, 0.0f, 0.5f});
+  filters.push_back({(float)(1.0 / 3.0), (float)(1.0 / 3.0), (float)(1.0 / 3.0)});
+  filters.push_back(gauss_taps(4.0f));
+  std::vector<float> sigmas(nres);
+  for (int k = 0; k < nres; ++k) {
+    if (k == 0) sigmas[k] = first; else if (k == 1) sigmas[k] = first * scalestep; else if (k == 2) sigmas[k] = first * scalestep * scalestep;
+    else sigmas[k] = (float)((double)first * std::pow((double)scalestep, (double)k));   // _firstScale * pow(scalestep, i + 1)
+    filters.push_back(gauss_taps(sigmas[k]));
+  }
+  std::vector<float> flat;
+  std::vector<int> foff;
+  for (const auto& f : filters) { foff.push_back((int)flat.size()); flat.insert(flat.end(), f.begin(), f.end()); }
+  DevBuf<float> d_taps, img, ta, tb, tc, resb, dogb, outr;
+  DevBuf<int32_t> outxy, outn;
+  DevBuf<unsigned char> seen;
+  CK(d_taps.alloc(flat.size())); CK(img.alloc((size_t)3 * n)); CK(ta.alloc((size_t)3 * n)); CK(tb.alloc((size_t)3 * n)); CK(tc.alloc((size_t)3 * n));
+  CK(resb.alloc((size_t)nres * n)); CK(dogb.alloc((size_t)(nres - 1) * n)); CK(outr.alloc((size_t)nb * 4)); CK(outxy.alloc((size_t)nb * 8));
+  CK(outn.alloc(nb)); CK(seen.alloc(n));
+  CK(cudaMemcpyAsync(d_taps.p, flat.data(), sizeof(float) * flat.size(), cudaMemcpyHostToDevice, ctx->stream));
+  const dim3 cb(128), cg3((w + 127) / 128, h, 3), cg1((w + 127) / 128, h, 1);
+  const int tb1 = 256, gb1 = (n + 255) / 256;
+  auto conv = [&](bool vertical, const float* src, float* dst, int filt, dim3 grid) {
+    const int nt = (int)filters[filt].size();
+    if (vertical) k_feat_conv<true><<<grid, cb, 0, ctx->stream>>>(src, dst, w, h, d_taps.p + foff[filt], nt);
+    else k_feat_conv<false><<<grid, cb, 0, ctx->stream>>>(src, dst, w, h, d_taps.p + foff[filt], nt);
+    ++ctx->launches;
+  };
+  std::vector<FeatPoint> feats;
+  std::vector<float> h_r((size_t)nb * 4);
+  std::vector<int32_t> h_xy((size_t)nb * 8), h_n(nb);
+  int total = 0;
+  auto collect = [&](int ftype) -> int {   // reverse iteration of the result multiset: strongest first, later insertion first among equals
+    if (cudaMemcpyAsync(h_r.data(), outr.p, sizeof(float) * h_r.size(), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(h_xy.data(), outxy.p, sizeof(int32_t) * h_xy.size(), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(h_n.data(), outn.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    feats.clear();
+    long seq = 0;
+    for (int b = 0; b < nb; ++b)
+      for (int k = 0; k < h_n[b]; ++k) feats.push_back({h_r[(size_t)b * 4 + k], h_xy[((size_t)b * 4 + k) * 2], h_xy[((size_t)b * 4 + k) * 2 + 1], seq++});
+    std::sort(feats.begin(), feats.end(), [](const FeatPoint& a, const FeatPoint& b) { return a.r != b.r ? a.r > b.r : a.seq > b.seq; });
+    for (const FeatPoint& f : feats) {
+      if (total < cap) { xy[2 * total] = (float)f.x; xy[2 * total + 1] = (float)f.y; response[total] = f.r; type[total] = ftype; }
+      ++total;
+    }
+    return 0;
+  };
+  k_feat_planes<<<gb1, tb1, 0, ctx->stream>>>(lv, img.p);
+  ++ctx->launches;
+  // ---- Harris (harris.cpp:112-137, 60-110, 139-172)
+  conv(false, img.p, ta.p, 0, cg3); conv(true, ta.p, tb.p, 1, cg3);    // tb = dI/dx
+  conv(false, img.p, ta.p, 1, cg3); conv(true, ta.p, tc.p, 0, cg3);    // tc = dI/dy
+  k_feat_products<<<gb1, tb1, 0, ctx->stream>>>(tb.p, tc.p, n, ta.p);   // ta = (xx, yy, xy)
+  ++ctx->launches;
+  conv(false, ta.p, tb.p, 2, cg3); conv(true, tb.p, ta.p, 2, cg3);
+  k_feat_harris_response<<<gb1, tb1, 0, ctx->stream>>>(ta.p, n, tb.p);
+  k_feat_nms<<<cg1, cb, 0, ctx->stream>>>(tb.p, w, h, tc.p);
+  {
+    const int margin = (2 * (int)std::ceil(2 * 4.0f) + 1) / 2;   // _gaussD.size() / 2
+    k_feat_select<0><<<(nb + 3) / 4, 128, 0, ctx->stream>>>(tc.p, nullptr, nullptr, nullptr, w, h, gridsize, gw, gh, margin, margin, nullptr,
+                                                            outr.p, outxy.p, outn.p);
+  }
+  ctx->launches += 3;
+  CK(cudaGetLastError());
+  if (collect(0)) return fail(ctx, PMVSB_ECUDA, "detect_features: copy failed");
+  // ---- difference of Gaussians (dog.cpp:122-183)
+  for (int k = 0; k < nres; ++k) {
+    conv(false, img.p, ta.p, 3 + k, cg3); conv(true, ta.p, tb.p, 3 + k, cg3);
+    k_feat_norm<<<gb1, tb1, 0, ctx->stream>>>(tb.p, n, resb.p + (size_t)k * n);
+    ++ctx->launches;
+  }
+  for (int k = 0; k + 1 < nres; ++k) {
+    k_feat_sub<<<gb1, tb1, 0, ctx->stream>>>(resb.p + (size_t)(k + 1) * n, resb.p + (size_t)k * n, n, dogb.p + (size_t)k * n);
+    ++ctx->launches;
+  }
+  CK(cudaMemsetAsync(seen.p, 0, n, ctx->stream));
+  CK(cudaMemsetAsync(outn.p, 0, sizeof(int32_t) * nb, ctx->stream));
+  // the reference walks i = 2 .. steps-1 with (pdog, cdog, ndog) = dog[i-2 .. i]; the select kernel takes two scales per
+  // launch and keeps the block's multiset in registers, so steps == 4 (scales 1 .. 3, the only values pmvs uses) is one launch
+  if (steps != 4) return fail(ctx, PMVSB_EINVAL, "detect_features: unsupported scale range");
+  {
+    const int ma = (int)std::ceil(2 * (float)((double)first * std::pow((double)scalestep, 3.0)));
+    const int mb = (int)std::ceil(2 * (float)((double)first * std::pow((double)scalestep, 4.0)));
+    k_feat_select<1><<<(nb + 3) / 4, 128, 0, ctx->stream>>>(dogb.p, dogb.p + (size_t)n, dogb.p + (size_t)2 * n, dogb.p + (size_t)3 * n, w, h, gridsize,
+                                                            gw, gh, ma, mb, seen.p, outr.p, outxy.p, outn.p);
+    ++ctx->launches;
+  }
+  CK(cudaGetLastError());
+  if (collect(1)) return fail(ctx, PMVSB_ECUDA, "detect_features: copy failed");
+  *count = total;
   return PMVSB_OK;
 }
 

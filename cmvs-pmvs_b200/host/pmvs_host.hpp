@@ -150,7 +150,6 @@ class Pipeline {
   std::vector<int> image_ids_;              // file numbers, targets first
   std::vector<Camera> cams_;
   std::vector<int> lw_, lh_;                // image size at the working level
-  std::vector<std::vector<unsigned char>> level_rgb_;   // image bytes at the working level (feature detection)
   std::vector<std::vector<double>> P0_;     // level-`level` projection in double for the epipolar search
   std::vector<std::vector<float>> distances_;
   std::vector<std::vector<Feature>> features_;

@@ -256,7 +256,6 @@ void Pipeline::load() {
   }
   cams_.resize(num_);
   lw_.resize(num_); lh_.resize(num_);
-  level_rgb_.resize(num_);
   std::cerr << "Reading images: " << std::flush;
   for (int i = 0; i < num_; ++i) {
     Loaded& L = loaded[i];
@@ -278,8 +277,6 @@ void Pipeline::load() {
     P0_[i].resize(12);
     for (int k = 0; k < 12; ++k) { c.P[k / 4][k % 4] = P[k]; P0_[i][k] = P[k]; }
     if (pmvsb_image_dims(gpu_, i, opt_.level, &lw_[i], &lh_[i])) die("image_dims");
-    level_rgb_[i].resize((size_t)lw_[i] * lh_[i] * 3);
-    if (pmvsb_download_image(gpu_, i, opt_.level, level_rgb_[i].data())) die("download_image");
     ImageGrid& g = grids_[i];
     if (pmvsb_grid_dims(gpu_, i, &g.gw, &g.gh)) die("grid_dims");
     if (i < tnum_) {
@@ -317,205 +314,24 @@ void Pipeline::load() {
 }
 
 // ---------------------------------------------------------------------------------------------- features
-namespace {
-using Plane = std::vector<float>;   // row-major w*h
-
-struct Img3 {
-  int w = 0, h = 0;
-  Plane c[3];
-};
-
-void gauss_kernel(float sigma, std::vector<float>& g) {   // CDetector::setGaussI (detector.cpp)
-  const int margin = (int)std::ceil(2 * sigma);
-  g.resize(2 * margin + 1);
-  float denom = 0.0f;
-  for (int x = 0; x < (int)g.size(); ++x) {
-    const int t = x - margin;
-    const float v = std::exp(-(t * t) / (2 * sigma * sigma));
-    g[x] = v;
-    denom += v;
-  }
-  for (float& v : g) v /= denom;
-}
-
-// the reference's unmasked-path convolutions clamp the coordinate for the Vec3f image (mask.empty() branch of the
-// masked overload, detector.hpp: edges replicate)
-void convolve_x(Plane& img, int w, int h, const std::vector<float>& f, Plane& buf) {
-  const int margin = (int)f.size() / 2;
-  for (int y = 0; y < h; ++y)
-    for (int x = 0; x < w; ++x) {
-      float acc = 0.0f;
-      for (int j = 0; j < (int)f.size(); ++j) {
-        int xt = x + j - margin;
-        xt = xt < 0 ? 0 : (xt >= w ? w - 1 : xt);
-        acc += f[j] * img[(size_t)y * w + xt];
-      }
-      buf[(size_t)y * w + x] = acc;
-    }
-  buf.swap(img);
-}
-void convolve_y(Plane& img, int w, int h, const std::vector<float>& f, Plane& buf) {
-  const int margin = (int)f.size() / 2;
-  for (int y = 0; y < h; ++y)
-    for (int x = 0; x < w; ++x) {
-      float acc = 0.0f;
-      for (int j = 0; j < (int)f.size(); ++j) {
-        int yt = y + j - margin;
-        yt = yt < 0 ? 0 : (yt >= h ? h - 1 : yt);
-        acc += f[j] * img[(size_t)yt * w + x];
-      }
-      buf[(size_t)y * w + x] = acc;
-    }
-  buf.swap(img);
-}
-
-struct BlockTop {   // keeps the 4 strongest responses of a block (the reference's multiset per result grid)
-  std::multiset<std::pair<float, std::pair<int, int>>> s;
-  void offer(float r, int x, int y, int cap, bool strict_gate) {
-    if ((int)s.size() < cap || !strict_gate || s.begin()->first < r) {
-      s.insert({r, {x, y}});
-      if ((int)s.size() > cap) s.erase(s.begin());
-    }
-  }
-};
-
-void harris(const Img3& im, int gspeedup, float sigma, std::vector<Feature>& out) {
-  const int w = im.w, h = im.h;
-  std::vector<float> gaussI;
-  gauss_kernel(sigma, gaussI);
-  const std::vector<float> dfilter = {-0.5f, 0.0f, 0.5f};
-  const std::vector<float> ifilter = {(float)(1.0 / 3.0), (float)(1.0 / 3.0), (float)(1.0 / 3.0)};
-  Plane buf((size_t)w * h), xx((size_t)w * h, 0.0f), yy((size_t)w * h, 0.0f), xy((size_t)w * h, 0.0f);
-  for (int k = 0; k < 3; ++k) {
-    Plane dx = im.c[k], dy = im.c[k];
-    convolve_x(dx, w, h, dfilter, buf); convolve_y(dx, w, h, ifilter, buf);
-    convolve_x(dy, w, h, ifilter, buf); convolve_y(dy, w, h, dfilter, buf);
-    for (size_t i = 0; i < xx.size(); ++i) { xx[i] += dx[i] * dx[i]; yy[i] += dy[i] * dy[i]; xy[i] += dx[i] * dy[i]; }
-  }
-  convolve_x(xx, w, h, gaussI, buf); convolve_y(xx, w, h, gaussI, buf);
-  convolve_x(yy, w, h, gaussI, buf); convolve_y(yy, w, h, gaussI, buf);
-  convolve_x(xy, w, h, gaussI, buf); convolve_y(xy, w, h, gaussI, buf);
-  Plane resp((size_t)w * h);
-  for (size_t i = 0; i < resp.size(); ++i) {
-    const float D = xx[i] * yy[i] - xy[i] * xy[i];
-    const float tr = xx[i] + yy[i];
-    resp[i] = (float)(D - 0.06 * tr * tr);
-  }
-  Plane nms = resp;
-  for (int y = 1; y < h - 1; ++y)
-    for (int x = 1; x < w - 1; ++x) {
-      const float v = resp[(size_t)y * w + x];
-      if (v < resp[(size_t)y * w + x + 1] || v < resp[(size_t)y * w + x - 1] || v < resp[(size_t)(y + 1) * w + x] || v < resp[(size_t)(y - 1) * w + x])
-        nms[(size_t)y * w + x] = 0.0f;
-    }
-  const int factor = 2, cap = factor * factor, gridsize = gspeedup * factor;
-  const int gw = (w + gridsize - 1) / gridsize, gh = (h + gridsize - 1) / gridsize;
-  std::vector<BlockTop> blocks((size_t)gw * gh);
-  // setGaussD(sigma) has the same support as setGaussI(sigma): margin = ceil(2 sigma)
-  const int margin = (int)std::ceil(2 * sigma);
-  for (int y = margin; y < h - margin; ++y)
-    for (int x = margin; x < w - margin; ++x) {
-      const float v = nms[(size_t)y * w + x];
-      if (v == 0.0f) continue;
-      blocks[(size_t)std::min(y / gridsize, gh - 1) * gw + std::min(x / gridsize, gw - 1)].offer(v, x, y, cap, true);
-    }
-  // CDetectFeatures pushes the points strongest first (detectFeatures.cpp:95-99)
-  std::multiset<std::pair<float, std::pair<int, int>>> all;
-  for (const BlockTop& b : blocks) all.insert(b.s.begin(), b.s.end());
-  for (auto it = all.rbegin(); it != all.rend(); ++it) out.push_back({(float)it->second.first, (float)it->second.second, it->first, 0});
-}
-
-void smooth_norm(const Img3& im, float sigma, Plane& res) {   // CDifferenceOfGaussians::setRes
-  std::vector<float> g;
-  gauss_kernel(sigma, g);
-  Plane buf((size_t)im.w * im.h), ch[3];
-  for (int k = 0; k < 3; ++k) {
-    ch[k] = im.c[k];
-    convolve_x(ch[k], im.w, im.h, g, buf);
-    convolve_y(ch[k], im.w, im.h, g, buf);
-  }
-  res.resize((size_t)im.w * im.h);
-  for (size_t i = 0; i < res.size(); ++i) res[i] = std::sqrt(ch[0][i] * ch[0][i] + ch[1][i] * ch[1][i] + ch[2][i] * ch[2][i]);
-}
-
-void dog(const Img3& im, int gspeedup, float first, float last, std::vector<Feature>& out) {
-  const int w = im.w, h = im.h;
-  const int factor = 2, cap = factor * factor, gridsize = gspeedup * factor;
-  const int gw = (w + gridsize - 1) / gridsize, gh = (h + gridsize - 1) / gridsize;
-  std::vector<BlockTop> blocks((size_t)gw * gh);
-  const float step = std::pow(2.0f, 1 / 2.0f);
-  const int steps = std::max(4, (int)std::ceil(std::log(last / first) / std::log(step)));
-  Plane pdog, cdog, ndog, cres, nres;
-  auto diff = [&](const Plane& a, const Plane& b, Plane& d) { d = b; for (size_t i = 0; i < d.size(); ++i) d[i] -= a[i]; };
-  smooth_norm(im, first, cres);
-  smooth_norm(im, first * step, nres);
-  diff(cres, nres, cdog);
-  cres.swap(nres);
-  smooth_norm(im, first * step * step, nres);
-  diff(cres, nres, ndog);
-  std::vector<unsigned char> seen((size_t)w * h, 0);
-  auto at = [&](const Plane& p, int x, int y) { return p[(size_t)y * w + x]; };
-  for (int i = 2; i <= steps - 1; ++i) {
-    const float cscale = first * std::pow(step, i + 1);
-    cres.swap(nres);
-    smooth_norm(im, cscale, nres);
-    pdog.swap(cdog);
-    cdog.swap(ndog);
-    diff(cres, nres, ndog);
-    const int margin = (int)std::ceil(2 * cscale);
-    for (int y = margin; y < h - margin; ++y)
-      for (int x = margin; x < w - margin; ++x) {
-        const float v = at(cdog, x, y);
-        if (seen[(size_t)y * w + x] || v == 0.0f) continue;
-        bool ext;
-        if (0.0f < v) {
-          ext = at(cdog, x - 1, y - 1) < v && at(cdog, x - 1, y) < v && at(cdog, x - 1, y + 1) < v && at(cdog, x, y - 1) < v &&
-                at(cdog, x, y + 1) < v && at(cdog, x + 1, y - 1) < v && at(cdog, x + 1, y) < v && at(cdog, x + 1, y + 1) < v &&
-                at(pdog, x, y) < v && at(ndog, x, y) < v;
-        } else {
-          ext = at(cdog, x - 1, y - 1) > v && at(cdog, x - 1, y) > v && at(cdog, x - 1, y + 1) > v && at(cdog, x, y - 1) > v &&
-                at(cdog, x, y + 1) > v && at(cdog, x + 1, y - 1) > v && at(cdog, x + 1, y) > v && at(cdog, x + 1, y + 1) > v &&
-                v < at(pdog, x, y) && v < at(ndog, x, y);
-        }
-        if (!ext) continue;
-        seen[(size_t)y * w + x] = 1;
-        blocks[(size_t)std::min(y / gridsize, gh - 1) * gw + std::min(x / gridsize, gw - 1)].offer(std::fabs(v), x, y, cap, false);
-      }
-  }
-  std::multiset<std::pair<float, std::pair<int, int>>> all;
-  for (const BlockTop& b : blocks) all.insert(b.s.begin(), b.s.end());
-  for (auto it = all.rbegin(); it != all.rend(); ++it) out.push_back({(float)it->second.first, (float)it->second.second, it->first, 1});
-}
-}  // namespace
-
+// CDetectFeatures::run (source/pmvs/detectFeatures.cpp:13-125): Harris + DoG per image, on the device pyramid
 void Pipeline::detect_features() {
-  Tick tk(this, "host.detect_features");
+  Tick tk(this, "gpu.detect_features");
   features_.assign(num_, {});
   const int fcsize = 16;   // findMatch.cpp:81
-  std::vector<std::thread> th;
-  std::vector<int> next(1, 0);
-  std::mutex* mu = new std::mutex();
-  auto work = [&]() {
-    for (;;) {
-      int i;
-      { std::lock_guard<std::mutex> lk(*mu); i = next[0]++; }
-      if (i >= num_) break;
-      Img3 im;
-      im.w = lw_[i]; im.h = lh_[i];
-      for (int k = 0; k < 3; ++k) im.c[k].resize((size_t)im.w * im.h);
-      for (size_t p = 0; p < (size_t)im.w * im.h; ++p)
-        for (int k = 0; k < 3; ++k) im.c[k][p] = ((int)level_rgb_[i][3 * p + k]) / 255.0f;
-      harris(im, fcsize, 4.0f, features_[i]);
-      dog(im, fcsize, 1.0f, 3.0f, features_[i]);
-    }
-  };
-  const int nth = std::max(1, std::min(opt_.CPU, (int)std::thread::hardware_concurrency()));
-  for (int t = 1; t < nth; ++t) th.emplace_back(work);
-  work();
-  for (auto& t : th) t.join();
-  delete mu;
   size_t total = 0;
-  for (const auto& f : features_) total += f.size();
+  std::vector<float> xy, resp;
+  std::vector<int32_t> type;
+  for (int i = 0; i < num_; ++i) {
+    const int blocks = ((lw_[i] + 2 * fcsize - 1) / (2 * fcsize)) * ((lh_[i] + 2 * fcsize - 1) / (2 * fcsize));
+    const int cap = 8 * blocks;   // at most 4 points per block and detector
+    xy.resize((size_t)2 * cap); resp.resize(cap); type.resize(cap);
+    int32_t n = 0;
+    if (pmvsb_detect_features(gpu_, i, fcsize, cap, xy.data(), resp.data(), type.data(), &n)) die("detect_features");
+    features_[i].resize(n);
+    for (int k = 0; k < n; ++k) features_[i][k] = {xy[2 * k], xy[2 * k + 1], resp[k], type[k]};
+    total += (size_t)n;
+  }
   std::cerr << "features: " << total << " in " << num_ << " images" << std::endl;
 }
 

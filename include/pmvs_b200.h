@@ -197,6 +197,14 @@ int pmvsb_refine_batch(pmvsb_ctx* ctx, int P, int stride, float* coords, float* 
 int pmvsb_refine_batch_dev(pmvsb_ctx* ctx, int P, int stride, float* d_coords, float* d_normals,
                            const int32_t* d_images, const int32_t* d_nimages, const float* d_dscales,
                            float* d_ncc, int32_t* d_evals, uint8_t* d_ok);
+/* ---- feature detection ---------------------------------------------------------------------
+ * CDetectFeatures::runThread for one image (source/pmvs/detectFeatures.cpp:77-118): CHarris::run (sigma 4,
+ * source/pmvs/harris.cpp:174-240) then CDifferenceOfGaussians::run (scales 1..3, source/pmvs/dog.cpp:96-198) on the
+ * working-level image of the device pyramid, at most 4 points per (2*gspeedup)^2-pixel block and detector.  Output in the
+ * reference's order (Harris strongest first, then DoG strongest first): xy float[2*cap] pixel coordinates, response
+ * float[cap], type int32[cap] (0 Harris, 1 DoG); *count = number of features found (may exceed cap). */
+int pmvsb_detect_features(pmvsb_ctx* ctx, int index, int gspeedup, int cap, float* xy, float* response, int32_t* type, int32_t* count);
+
 /* ---- multi-GPU -------------------------------------------------------------------------------------
  * One process and one context per GPU, images and cameras replicated (the reference shares one CPhotoSetS between its
  * worker threads, findMatch.hpp).  The candidates of a wave are independent given the grid snapshot, so each rank

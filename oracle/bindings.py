@@ -272,6 +272,13 @@ class OracleLib(_Common):
         f = self.lib.pmvso_compute_gain; f.restype = C.c_float
         return np.float32(f(self.ctx, int(k)))
 
+    def detect_features(self, index, gspeedup=16, cap=65536):
+        """(x, y), response, type per feature: Harris first, then DoG, strongest first"""
+        xy = np.zeros((cap, 2), np.float32); resp = np.zeros(cap, np.float32); types = np.zeros(cap, np.int32)
+        n = self.lib.pmvso_detect_features(self.ctx, int(index), int(gspeedup), xy.ctypes.data_as(C.c_void_p), resp.ctypes.data_as(C.c_void_p),
+                                           types.ctypes.data_as(C.c_void_p), cap)
+        return xy[:n].copy(), resp[:n].copy(), types[:n].copy()
+
     def compute_radius(self, k):
         f = self.lib.pmvso_compute_radius; f.restype = C.c_float
         return np.float32(f(self.ctx, int(k)))
@@ -408,6 +415,12 @@ class RefLib(_Common):
     def compute_gain(self, k):
         f = self.lib.ref_compute_gain; f.restype = C.c_float
         return np.float32(f(int(k)))
+
+    def detect_features(self, index, gspeedup=16, cap=65536):
+        xy = np.zeros((cap, 2), np.float32); resp = np.zeros(cap, np.float32); types = np.zeros(cap, np.int32)
+        n = self.lib.ref_detect_features(int(index), int(gspeedup), xy.ctypes.data_as(C.c_void_p), resp.ctypes.data_as(C.c_void_p),
+                                         types.ctypes.data_as(C.c_void_p), cap)
+        return xy[:n].copy(), resp[:n].copy(), types[:n].copy()
 
     def compute_radius(self, k):
         f = self.lib.ref_compute_radius; f.restype = C.c_float

@@ -1333,3 +1333,218 @@ int pmvso_filter_neighbor(const pmvso_ctx* c, int k, float quad, float* residual
   if (residual_out) *residual_out = residual;
   return residual < quad ? 0 : 1;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * feature detection: CHarris::run (harris.cpp:174-240) and CDifferenceOfGaussians::run
+ * (dog.cpp:96-198) on the working-level image, unmasked images (mask and edge empty, detector.hpp:23-94 take the
+ * clamping branch).  Same f32 operation order; exp / pow / log are the double libm entry points (nm -u detector.o).
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct { float r; int x, y; long seq; } fpoint_t;
+
+static void gauss_i(float sigma, float* g, int* ntaps) {   /* CDetector::setGaussI (detector.cpp:31-49) */
+  const int margin = (int)ceil(2 * sigma);
+  const int size = 2 * margin + 1;
+  float denom = 0.0f;
+  for (int x = 0; x < size; ++x) {
+    const int xt = x - margin;
+    const float d = (float)exp(-(xt * xt) / (2 * sigma * sigma));
+    g[x] = d;
+    denom += d;
+  }
+  for (int x = 0; x < size; ++x) g[x] /= denom;
+  *ntaps = size;
+}
+
+/* masked overload with an empty mask: coordinates clamp to the image (detector.hpp:26-94) */
+static void conv_x(float* img, int w, int h, const float* f, int n, float* buf) {
+  const int margin = n / 2;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      float acc = 0.0f;
+      for (int j = 0; j < n; ++j) {
+        int xt = x + j - margin;
+        if (xt < 0) xt = 0; else if (w <= xt) xt = w - 1;
+        acc += f[j] * img[(size_t)y * w + xt];
+      }
+      buf[(size_t)y * w + x] = acc;
+    }
+  memcpy(img, buf, sizeof(float) * (size_t)w * h);
+}
+static void conv_y(float* img, int w, int h, const float* f, int n, float* buf) {
+  const int margin = n / 2;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      float acc = 0.0f;
+      for (int j = 0; j < n; ++j) {
+        int yt = y + j - margin;
+        if (yt < 0) yt = 0; else if (h <= yt) yt = h - 1;
+        acc += f[j] * img[(size_t)yt * w + x];
+      }
+      buf[(size_t)y * w + x] = acc;
+    }
+  memcpy(img, buf, sizeof(float) * (size_t)w * h);
+}
+
+/* the per-block multiset<CPoint> (ordered by response; equal keys keep insertion order, begin() = smallest, oldest) */
+typedef struct { fpoint_t p[5]; int n; } block_t;
+static void block_insert(block_t* b, fpoint_t q) {   /* insert after the elements that are <= q, then drop begin() beyond 4 */
+  int pos = b->n;
+  while (pos > 0 && q.r < b->p[pos - 1].r) { b->p[pos] = b->p[pos - 1]; --pos; }
+  b->p[pos] = q;
+  b->n++;
+  if (b->n > 4) { for (int i = 1; i < b->n; ++i) b->p[i - 1] = b->p[i]; b->n--; }
+}
+static int cmp_fpoint_desc(const void* a, const void* b) {   /* reverse iteration of the result multiset */
+  const fpoint_t* p = (const fpoint_t*)a; const fpoint_t* q = (const fpoint_t*)b;
+  if (p->r != q->r) return p->r < q->r ? 1 : -1;
+  return p->seq < q->seq ? 1 : (p->seq > q->seq ? -1 : 0);
+}
+static int emit_blocks(block_t* blocks, int nb, int type, float* xy, float* resp, int* types, int cap, int have) {
+  int total = 0;
+  for (int i = 0; i < nb; ++i) total += blocks[i].n;
+  fpoint_t* all = (fpoint_t*)malloc(sizeof(fpoint_t) * (total ? total : 1));
+  long seq = 0;
+  int k = 0;
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j < blocks[i].n; ++j) { all[k] = blocks[i].p[j]; all[k].seq = seq++; ++k; }
+  qsort(all, total, sizeof(fpoint_t), cmp_fpoint_desc);
+  for (int i = 0; i < total && have + i < cap; ++i) {
+    xy[2 * (have + i)] = (float)all[i].x; xy[2 * (have + i) + 1] = (float)all[i].y;
+    resp[have + i] = all[i].r; types[have + i] = type;
+  }
+  free(all);
+  return total;
+}
+
+/* features of image `index` at the working level, Harris points first then DoG, each strongest first
+ * (detectFeatures.cpp:77-118).  Returns the total count; at most cap are written. */
+int pmvso_detect_features(const pmvso_ctx* c, int index, int gspeedup, float* xy, float* resp, int* types, int cap) {
+  const int w = c->w[index * c->nlevels + c->level], h = c->h[index * c->nlevels + c->level];
+  const unsigned char* pix = c->pix[index * c->nlevels + c->level];
+  const size_t n = (size_t)w * h;
+  float* im[3];
+  for (int k = 0; k < 3; ++k) {
+    im[k] = (float*)malloc(sizeof(float) * n);
+    for (size_t i = 0; i < n; ++i) im[k][i] = ((int)pix[3 * i + k]) / 255.0f;
+  }
+  float* buf = (float*)malloc(sizeof(float) * n);
+  const int factor = 2, gridsize = gspeedup * factor;
+  const int gw = (w + gridsize - 1) / gridsize, gh = (h + gridsize - 1) / gridsize;
+  int have = 0;
+  /* ---- Harris, sigma 4 */
+  {
+    const float sigma = 4.0f;
+    float gI[64]; int nI;
+    gauss_i(sigma, gI, &nI);
+    const float dfilter[3] = {-0.5f, 0.0f, 0.5f};
+    const float ifilter[3] = {(float)(1.0 / 3.0), (float)(1.0 / 3.0), (float)(1.0 / 3.0)};
+    float* xx = (float*)calloc(n, sizeof(float)); float* yy = (float*)calloc(n, sizeof(float)); float* xyp = (float*)calloc(n, sizeof(float));
+    float* dx = (float*)malloc(sizeof(float) * n); float* dy = (float*)malloc(sizeof(float) * n);
+    float* sx = (float*)calloc(n, sizeof(float)); float* sy = (float*)calloc(n, sizeof(float)); float* sxy = (float*)calloc(n, sizeof(float));
+    /* Vec3f * Vec3f = x x' + y y' + z z' summed left to right (vec3.hpp); accumulate the three channel products in that order */
+    for (int k = 0; k < 3; ++k) {
+      memcpy(dx, im[k], sizeof(float) * n); memcpy(dy, im[k], sizeof(float) * n);
+      conv_x(dx, w, h, dfilter, 3, buf); conv_y(dx, w, h, ifilter, 3, buf);
+      conv_x(dy, w, h, ifilter, 3, buf); conv_y(dy, w, h, dfilter, 3, buf);
+      for (size_t i = 0; i < n; ++i) {
+        if (k == 0) { sx[i] = dx[i] * dx[i]; sy[i] = dy[i] * dy[i]; sxy[i] = dx[i] * dy[i]; }
+        else { sx[i] = sx[i] + dx[i] * dx[i]; sy[i] = sy[i] + dy[i] * dy[i]; sxy[i] = sxy[i] + dx[i] * dy[i]; }
+      }
+    }
+    for (size_t i = 0; i < n; ++i) { xx[i] += sx[i]; yy[i] += sy[i]; xyp[i] += sxy[i]; }   /* harris.cpp:76-78 */
+    conv_x(xx, w, h, gI, nI, buf); conv_y(xx, w, h, gI, nI, buf);
+    conv_x(yy, w, h, gI, nI, buf); conv_y(yy, w, h, gI, nI, buf);
+    conv_x(xyp, w, h, gI, nI, buf); conv_y(xyp, w, h, gI, nI, buf);
+    float* response = dx;   /* reuse */
+    for (size_t i = 0; i < n; ++i) {
+      const float D = xx[i] * yy[i] - xyp[i] * xyp[i];
+      const float tr = xx[i] + yy[i];
+      response[i] = (float)(D - 0.06 * tr * tr);
+    }
+    float* nms = dy;
+    memcpy(nms, response, sizeof(float) * n);
+    for (int y = 1; y < h - 1; ++y)
+      for (int x = 1; x < w - 1; ++x) {
+        const float v = response[(size_t)y * w + x];
+        if (v < response[(size_t)y * w + x + 1] || v < response[(size_t)y * w + x - 1] || v < response[(size_t)(y + 1) * w + x] ||
+            v < response[(size_t)(y - 1) * w + x]) nms[(size_t)y * w + x] = 0.0f;
+      }
+    block_t* blocks = (block_t*)calloc((size_t)gw * gh, sizeof(block_t));
+    const int margin = (2 * (int)ceil(2 * sigma) + 1) / 2;   /* _gaussD.size() / 2 (detector.cpp:10-12) */
+    for (int y = margin; y < h - margin; ++y)
+      for (int x = margin; x < w - margin; ++x) {
+        const float v = nms[(size_t)y * w + x];
+        if (v == 0.0) continue;
+        const int x0 = x / gridsize < gw - 1 ? x / gridsize : gw - 1, y0 = y / gridsize < gh - 1 ? y / gridsize : gh - 1;
+        block_t* b = &blocks[(size_t)y0 * gw + x0];
+        if (b->n < 4 || b->p[0].r < v) { fpoint_t q = {v, x, y, 0}; block_insert(b, q); }
+      }
+    have += emit_blocks(blocks, gw * gh, 0, xy, resp, types, cap, have);
+    free(blocks); free(xx); free(yy); free(xyp); free(dx); free(dy); free(sx); free(sy); free(sxy);
+  }
+  /* ---- difference of Gaussians, scales 1 .. 3 */
+  {
+    const float first = 1.0f, last = 3.0f;
+    const float scalestep = (float)pow(2.0f, 1 / 2.0f);
+    int steps = (int)ceil(log(last / first) / log(scalestep));
+    if (steps < 4) steps = 4;
+    const int nres = steps + 1;                      /* res[k] at sigma first * step^k (the reference keeps a window of two) */
+    float** res = (float**)malloc(sizeof(float*) * nres);
+    float* ch = (float*)malloc(sizeof(float) * n);
+    for (int k = 0; k < nres; ++k) {
+      float sigma;
+      if (k == 0) sigma = first; else if (k == 1) sigma = first * scalestep; else if (k == 2) sigma = first * scalestep * scalestep;
+      else sigma = (float)(first * pow(scalestep, k));   /* cscale = _firstScale * pow(scalestep, i + 1), k = i + 1 */
+      float g[128]; int ng;
+      gauss_i(sigma, g, &ng);
+      res[k] = (float*)calloc(n, sizeof(float));
+      float* acc0 = res[k];
+      /* norm(Vec3f) = sqrt(x x + y y + z z) (vec3.hpp:210-214) */
+      float* c0 = (float*)malloc(sizeof(float) * n); float* c1 = (float*)malloc(sizeof(float) * n);
+      memcpy(c0, im[0], sizeof(float) * n); conv_x(c0, w, h, g, ng, buf); conv_y(c0, w, h, g, ng, buf);
+      memcpy(c1, im[1], sizeof(float) * n); conv_x(c1, w, h, g, ng, buf); conv_y(c1, w, h, g, ng, buf);
+      memcpy(ch, im[2], sizeof(float) * n); conv_x(ch, w, h, g, ng, buf); conv_y(ch, w, h, g, ng, buf);
+      for (size_t i = 0; i < n; ++i) acc0[i] = sqrtf(c0[i] * c0[i] + c1[i] * c1[i] + ch[i] * ch[i]);
+      free(c0); free(c1);
+    }
+    float** dog = (float**)malloc(sizeof(float*) * (nres - 1));
+    for (int k = 0; k + 1 < nres; ++k) {
+      dog[k] = (float*)malloc(sizeof(float) * n);
+      for (size_t i = 0; i < n; ++i) dog[k][i] = res[k + 1][i] - res[k][i];
+    }
+    unsigned char* seen = (unsigned char*)calloc(n, 1);
+    block_t* blocks = (block_t*)calloc((size_t)gw * gh, sizeof(block_t));
+    for (int i = 2; i <= steps - 1; ++i) {
+      const float cscale = (float)(first * pow(scalestep, i + 1));
+      const float* pd = dog[i - 2]; const float* cd = dog[i - 1]; const float* nd = dog[i];
+      const int margin = (int)ceil(2 * cscale);
+      for (int y = margin; y < h - margin; ++y)
+        for (int x = margin; x < w - margin; ++x) {
+          const size_t o = (size_t)y * w + x;
+          const float v = cd[o];
+          if (seen[o] || v == 0.0) continue;
+          int ext;
+          if (0.0 < v)
+            ext = cd[o - w - 1] < v && cd[o - 1] < v && cd[o + w - 1] < v && cd[o - w] < v && cd[o + w] < v && cd[o - w + 1] < v && cd[o + 1] < v &&
+                  cd[o + w + 1] < v && pd[o] < v && nd[o] < v;
+          else
+            ext = cd[o - w - 1] > v && cd[o - 1] > v && cd[o + w - 1] > v && cd[o - w] > v && cd[o + w] > v && cd[o - w + 1] > v && cd[o + 1] > v &&
+                  cd[o + w + 1] > v && v < pd[o] && v < nd[o];
+          if (!ext) continue;
+          seen[o] = 1;
+          const int x0 = x / gridsize < gw - 1 ? x / gridsize : gw - 1, y0 = y / gridsize < gh - 1 ? y / gridsize : gh - 1;
+          fpoint_t q = {fabsf(v), x, y, 0};
+          block_insert(&blocks[(size_t)y0 * gw + x0], q);
+        }
+    }
+    const int got = emit_blocks(blocks, gw * gh, 1, xy, resp, types, cap, have);
+    have += got;
+    free(blocks); free(seen); free(ch);
+    for (int k = 0; k < nres; ++k) free(res[k]);
+    for (int k = 0; k + 1 < nres; ++k) free(dog[k]);
+    free(res); free(dog);
+  }
+  free(buf);
+  for (int k = 0; k < 3; ++k) free(im[k]);
+  return have;
+}

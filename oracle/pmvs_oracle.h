@@ -84,6 +84,9 @@ int pmvso_is_neighbor(const pmvso_ctx* c, int a, int b, float thr);  /* CFindMat
 float pmvso_compute_gain(const pmvso_ctx* c, int k);
 /* CExpand::computeRadius (expand.cpp:182-198), CPatchOrganizerS::findNeighbors (patchOrganizerS.cpp:528-651),
  * CExpand::findEmptyBlocks (expand.cpp:108-180), CFilter::filterNeighborThread + filterQuad (filter.cpp:357-462) */
+/* CDetectFeatures (detectFeatures.cpp:50-125): CHarris::run + CDifferenceOfGaussians::run on the working-level image;
+ * xy float[2*cap], resp float[cap], types int[cap] (0 Harris, 1 DoG); returns the number of features */
+int pmvso_detect_features(const pmvso_ctx* c, int index, int gspeedup, float* xy, float* resp, int* types, int cap);
 float pmvso_compute_radius(const pmvso_ctx* c, int k);
 int pmvso_find_neighbors(const pmvso_ctx* c, int k, float scale, int margin, int skipvis, int* out, int cap);
 int pmvso_find_empty_blocks(const pmvso_ctx* c, int k, float* radius_out);

@@ -34,6 +34,9 @@
 #define private public
 #include "pmvs/findMatch.hpp"
 #include "pmvs/option.hpp"
+#include "pmvs/harris.hpp"
+#include "pmvs/dog.hpp"
+#include "pmvs/point.hpp"
 #undef protected
 #undef private
 
@@ -379,6 +382,34 @@ int ref_filter_neighbor(int k, float quad, int* ncount) {
   if (ncount) *ncount = (int)nb.size();
   if ((int)nb.size() < 6) return 1;
   return g_fm->_filter.filterQuad(*g_fm->_pos._ppatches[k], nb);
+}
+// CDetectFeatures::runThread's body for one image (detectFeatures.cpp:77-118): CHarris then CDifferenceOfGaussians on the
+// working-level image, each result multiset read in reverse (strongest first)
+int ref_detect_features(int index, int gspeedup, float* xy, float* resp, int* types, int cap) {
+  Image::CPhotoSetS& pss = g_fm->_pss;
+  const int level = g_fm->_level;
+  int n = 0;
+  auto emit = [&](std::multiset<CPoint>& result) {
+    for (auto it = result.rbegin(); it != result.rend(); ++it) {
+      if (n < cap) { xy[2 * n] = it->_icoord[0]; xy[2 * n + 1] = it->_icoord[1]; resp[n] = it->_response; types[n] = it->_type; }
+      ++n;
+    }
+  };
+  {
+    CHarris harris;
+    std::multiset<CPoint> result;
+    harris.run(pss._photos[index].getImage(level), pss._photos[index].CImage::getMask(level), pss._photos[index].CImage::getEdge(level),
+               pss._photos[index].getWidth(level), pss._photos[index].getHeight(level), gspeedup, 4.0f, result);
+    emit(result);
+  }
+  {
+    CDifferenceOfGaussians dog;
+    std::multiset<CPoint> result;
+    dog.run(pss._photos[index].getImage(level), pss._photos[index].CImage::getMask(level), pss._photos[index].CImage::getEdge(level),
+            pss._photos[index].getWidth(level), pss._photos[index].getHeight(level), gspeedup, 1.0f, 3.0f, result);
+    emit(result);
+  }
+  return n;
 }
 int ref_get_depth_flag(void) { return g_fm->_depth; }
 float ref_neighbor_threshold(int which) { return which == 0 ? g_fm->_neighborThreshold : (which == 1 ? g_fm->_neighborThreshold1 : g_fm->_neighborThreshold2); }

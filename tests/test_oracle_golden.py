@@ -193,3 +193,15 @@ def test_find_neighbors_empty_blocks_filter_neighbor(oracle_state, S):
         mine = np.array([o.filter_neighbor(k, float(q))[0] for k in range(0, P, 3)], np.uint8)
         assert np.array_equal(mine, S["fnb_reject_q"][qi][::3]), q
     assert 0.2 < S["fnb_reject_q"][0].mean() < 0.8 and S["empty_mask"].min() < 63
+
+
+def test_detect_features(oracle, scene_checked):
+    """Harris + DoG features of every image: positions, responses (bit for bit), types and order equal the reference's"""
+    F = np.load(os.path.join(HERE, "golden", "pmvs_features.npz"))
+    assert scene_checked.sha256() == bytes(F["scene_sha256"]).hex()
+    for i in range(scene_checked.num):
+        xy, resp, typ = oracle.detect_features(i, 16)
+        lo, hi = F["off"][i], F["off"][i + 1]
+        assert np.array_equal(xy, F["xy"][lo:hi].astype(np.float32)), i
+        assert np.array_equal(resp, F["resp"][lo:hi]) and np.array_equal(typ, F["type"][lo:hi].astype(np.int32)), i
+    assert (F["type"] == 0).sum() > 100 and (F["type"] == 1).sum() > 100

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("scene", nargs="?", default="sphere16")
     ap.add_argument("--cpu", type=int, default=1, help="CPU option for the reference run (1 = deterministic)")
     ap.add_argument("--skip-ref", action="store_true")
+    ap.add_argument("--ranks", type=int, default=1, help="pmvs2 processes (one per GPU, launched with torch.distributed.run --no-python)")
     a = ap.parse_args()
     import torch
     synth = g.load_package().synth
@@ -58,12 +59,16 @@ def main():
     scene.option["CPU"] = os.cpu_count() or 4
     pg = synth.write_scene(scene, "/tmp/cmp_gpu_%s" % a.scene)
     t = time.time()
-    p = subprocess.run([os.path.join(ROOT, "cmvs-pmvs_b200/bin/pmvs2"), pg, "option.txt", "PATCH", "PSET"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    cmd = [os.path.join(ROOT, "cmvs-pmvs_b200/bin/pmvs2"), pg, "option.txt", "PATCH", "PSET"]
+    if a.ranks > 1:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.ranks), "--master-addr", "127.0.0.1",
+               "--master-port", "29741", "--no-python"] + cmd
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     if p.returncode != 0:
         print(p.stderr[-3000:])
         raise SystemExit("pmvs2 failed with %d" % p.returncode)
     runs["pmvs_b200"] = (time.time() - t, np.loadtxt(pg + "models/option.txt.pset", dtype=np.float32).reshape(-1, 6))
-    open(os.path.join(ROOT, "gpurun_out", "pmvs2_%s.log" % a.scene), "w").write(p.stderr) if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
+    open(os.path.join(ROOT, "gpurun_out", "pmvs2_%s%s.log" % (a.scene, "" if a.ranks == 1 else "_x%d" % a.ranks)), "w").write(p.stderr) if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
     for k, (secs, pts) in runs.items():
         r = {"seconds": secs, "patches": int(len(pts))}
         if scene.kind == "sphere" and len(pts):
