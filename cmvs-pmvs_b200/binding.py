@@ -22,7 +22,7 @@ SYMBOLS = [
     "pmvsb_compute_incc_batch", "pmvsb_set_inccs_batch", "pmvsb_set_scales_batch", "pmvsb_pre_process_batch",
     "pmvsb_post_process_batch", "pmvsb_set_depth", "pmvsb_grid_dims", "pmvsb_store_upload", "pmvsb_build_depth_maps",
     "pmvsb_download_depth_map", "pmvsb_depth_maps_add", "pmvsb_store_append", "pmvsb_store_update_vimages",
-    "pmvsb_store_download_vimages", "pmvsb_download_cell_lists", "pmvsb_find_empty_blocks_store", "pmvsb_filter_neighbor_store", "pmvsb_set_vimages_store", "pmvsb_filter_exact_store", "pmvsb_compute_gains_store", "pmvsb_set_vimages_batch", "pmvsb_set_ref_image_batch",
+    "pmvsb_store_download_vimages", "pmvsb_download_cell_lists", "pmvsb_find_empty_blocks_store", "pmvsb_filter_neighbor_store", "pmvsb_check_batch", "pmvsb_set_vimages_store", "pmvsb_filter_exact_store", "pmvsb_compute_gains_store", "pmvsb_set_vimages_batch", "pmvsb_set_ref_image_batch",
     "pmvsb_patch_colors_batch", "pmvsb_refine_batch",
     "pmvsb_refine_batch_dev", "pmvsb_detect_features", "pmvsb_comm_unique_id", "pmvsb_comm_init", "pmvsb_allgather", "pmvsb_sync", "pmvsb_stream", "pmvsb_set_stream", "pmvsb_launch_count", "pmvsb_last_refine_ms",
 ]
@@ -259,6 +259,17 @@ class PmvsB200:
         ov = C.c_int32()
         self._ck(self.lib.pmvsb_filter_neighbor_store(self.ctx, C.c_float(quad), _vp(rej), _vp(res), _vp(cnt), C.byref(ov)))
         return rej, res, cnt, ov.value
+
+    def check_batch(self, coords, normals, ncc, dscale, timages, images, nimages, grids, vimages, nv, vgrids, quad=2.5):
+        """COptim::check for candidates outside the table; images (P, stride), grids (P, stride, 2), vimages (P, vstride), vgrids (P, vstride, 2)"""
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        coords = _f32(coords).reshape(-1, 4); P = coords.shape[0]
+        images = i32(images).reshape(P, -1); vimages = i32(vimages).reshape(P, -1)
+        gain = np.zeros(P, np.float32); rej = np.zeros(P, np.uint8); ov = C.c_int32()
+        self._ck(self.lib.pmvsb_check_batch(self.ctx, P, images.shape[1], _vp(coords), _vp(_f32(normals)), _vp(_f32(ncc)), _vp(_f32(dscale)),
+                                            _vp(i32(timages)), _vp(images), _vp(i32(nimages)), _vp(i32(grids)), vimages.shape[1], _vp(vimages),
+                                            _vp(i32(nv)), _vp(i32(vgrids)), C.c_float(quad), _vp(gain), _vp(rej), C.byref(ov)))
+        return gain, rej, ov.value
 
     def build_depth_maps(self):
         self._ck(self.lib.pmvsb_build_depth_maps(self.ctx))

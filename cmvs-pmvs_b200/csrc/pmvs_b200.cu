@@ -1653,6 +1653,49 @@ int pmvsb_filter_neighbor_store(pmvsb_ctx* ctx, float quad, uint8_t* reject, flo
   return PMVSB_OK;
 }
 
+int pmvsb_check_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals, const float* ncc, const float* dscale,
+                      const int32_t* timages, const int32_t* images, const int32_t* nimages, const int32_t* grids, int vstride,
+                      const int32_t* vimages, const int32_t* nv, const int32_t* vgrids, float quad, float* gain, uint8_t* reject, int32_t* overflow) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  if (P < 0 || stride < 1 || vstride < 1 || (P > 0 && (!coords || !normals || !ncc || !dscale || !timages || !images || !nimages || !grids ||
+                                                      !vimages || !nv || !vgrids || !gain || !reject)))
+    return fail(ctx, PMVSB_EINVAL, "check_batch: bad argument");
+  if (overflow) *overflow = 0;
+  if (P == 0) return PMVSB_OK;
+  for (int p = 0; p < P; ++p) {   // the kernel trusts image indexes; cells are range-checked on the device
+    for (int i = 0; i < std::min(nimages[p], stride); ++i)
+      if (images[(size_t)p * stride + i] < 0 || images[(size_t)p * stride + i] >= ctx->num) return fail(ctx, PMVSB_EINVAL, "check_batch: image index out of range");
+    for (int i = 0; i < std::min(nv[p], vstride); ++i)
+      if (vimages[(size_t)p * vstride + i] < 0 || vimages[(size_t)p * vstride + i] >= ctx->tnum) return fail(ctx, PMVSB_EINVAL, "check_batch: vimage index out of range");
+  }
+  DevBuf<float> dc, dn, dncc, dds, dgain;
+  DevBuf<int32_t> dti, dim, dni, dgr, dvi, dnv, dvg, dov;
+  DevBuf<uint8_t> drej;
+  CK(dc.alloc((size_t)4 * P)); CK(dn.alloc((size_t)4 * P)); CK(dncc.alloc(P)); CK(dds.alloc(P)); CK(dgain.alloc(P)); CK(dti.alloc(P));
+  CK(dim.alloc((size_t)stride * P)); CK(dni.alloc(P)); CK(dgr.alloc((size_t)2 * stride * P)); CK(dvi.alloc((size_t)vstride * P)); CK(dnv.alloc(P));
+  CK(dvg.alloc((size_t)2 * vstride * P)); CK(dov.alloc(1)); CK(drej.alloc(P));
+  auto up = [&](void* d, const void* h, size_t bytes) { return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream); };
+  CK(up(dc.p, coords, sizeof(float) * 4 * (size_t)P)); CK(up(dn.p, normals, sizeof(float) * 4 * (size_t)P));
+  CK(up(dncc.p, ncc, sizeof(float) * (size_t)P)); CK(up(dds.p, dscale, sizeof(float) * (size_t)P)); CK(up(dti.p, timages, sizeof(int32_t) * (size_t)P));
+  CK(up(dim.p, images, sizeof(int32_t) * (size_t)stride * P)); CK(up(dni.p, nimages, sizeof(int32_t) * (size_t)P));
+  CK(up(dgr.p, grids, sizeof(int32_t) * 2 * (size_t)stride * P)); CK(up(dvi.p, vimages, sizeof(int32_t) * (size_t)vstride * P));
+  CK(up(dnv.p, nv, sizeof(int32_t) * (size_t)P)); CK(up(dvg.p, vgrids, sizeof(int32_t) * 2 * (size_t)vstride * P));
+  CK(cudaMemsetAsync(dov.p, 0, sizeof(int32_t), ctx->stream));
+  k_check_batch<<<(P + kNbWarps - 1) / kNbWarps, kNbWarps * 32, 0, ctx->stream>>>(ctx->scene, ctx->store, P, stride, vstride, dc.p, dn.p, dncc.p, dds.p,
+                                                                                 dti.p, dim.p, dni.p, dgr.p, dvi.p, dnv.p, dvg.p, quad, ctx->tau, dgain.p,
+                                                                                 drej.p, dov.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(gain, dgain.p, sizeof(float) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(reject, drej.p, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+  int32_t ov = 0;
+  CK(cudaMemcpyAsync(&ov, dov.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (overflow) *overflow = ov;
+  return PMVSB_OK;
+}
+
 int pmvsb_set_vimages_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals, const int32_t* images,
                             const int32_t* nimages, int vstride, int32_t* vimages, int32_t* nv, int32_t* vgrids) {
   int r = need_store(ctx, true);

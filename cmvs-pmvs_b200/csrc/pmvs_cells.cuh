@@ -189,6 +189,18 @@ __global__ void k_store_vimages(SceneDev s, StoreDev st, int additive, int32_t* 
 // ---------------------------------------------------------------------------------------------------
 // neighbour search
 // ---------------------------------------------------------------------------------------------------
+struct PatchLists {      // _images/_grids and _vimages/_vgrids of the query patch: a table patch or a candidate outside the table
+  const int32_t* images; const int32_t* grids; int nimg;
+  const int32_t* vimages; const int32_t* vgrids; int nv;
+};
+__device__ __forceinline__ PatchLists table_lists(const StoreDev& st, int p) {
+  PatchLists l;
+  const int e0 = st.img_off[p], v0 = st.vimg_off[p];
+  l.images = st.images + e0; l.grids = st.grids + 2 * e0; l.nimg = st.img_off[p + 1] - e0;
+  l.vimages = st.vimages + v0; l.vgrids = st.vgrids + 2 * v0; l.nv = st.vimg_off[p + 1] - v0;
+  return l;
+}
+
 struct NeighborQuery {   // what findNeighbors derives from the patch before it looks at any cell
   float X[4], N[4];
   float unit;     // mean getUnit over the patch's images x csize
@@ -199,20 +211,19 @@ struct NeighborQuery {   // what findNeighbors derives from the patch before it 
 };
 
 // getUnit summed in list order and COptim::computeUnits' second-smallest value (optim.cpp:446-471), lanes over images
-__device__ __forceinline__ void neighbor_query(const SceneDev& s, const StoreDev& st, int p, int margin, int lane, NeighborQuery& q) {
-  const float4 c4 = __ldg(reinterpret_cast<const float4*>(st.coords) + p);
-  const float4 n4 = __ldg(reinterpret_cast<const float4*>(st.normals) + p);
+__device__ __forceinline__ void neighbor_query(const SceneDev& s, const PatchLists& pl, float4 c4, float4 n4, float dscale, int margin, int lane,
+                                               NeighborQuery& q) {
   q.X[0] = c4.x; q.X[1] = c4.y; q.X[2] = c4.z; q.X[3] = c4.w;
   q.N[0] = n4.x; q.N[1] = n4.y; q.N[2] = n4.z; q.N[3] = n4.w;
-  q.dscale = st.dscale[p];
-  const int e0 = st.img_off[p], e1 = st.img_off[p + 1];
+  q.dscale = dscale;
+  const int e0 = 0, e1 = pl.nimg;
   q.nimg = e1 - e0;
   float usum = 0.0f, min1 = INFINITY, min2 = INFINITY;
   for (int base = e0; base < e1; base += 32) {
     float u = 0.0f, uu = 0.0f;
     if (base + lane < e1) {
       CamDev cam;
-      load_cam(s, st.images[base + lane], cam);
+      load_cam(s, pl.images[base + lane], cam);
       u = get_unit(cam, s.level, q.X);
       float ray[4] = {cam.centre[0] - q.X[0], cam.centre[1] - q.X[1], cam.centre[2] - q.X[2], cam.centre[3] - q.X[3]};
       unitize4(ray);
@@ -229,6 +240,10 @@ __device__ __forceinline__ void neighbor_query(const SceneDev& s, const StoreDev
   q.unit = q.nimg > 0 ? fdiv(usum, (float)q.nimg) * (float)s.csize : 0.0f;
   q.base_radius = q.nimg >= 2 ? min2 * (float)s.csize : (q.nimg == 1 ? min1 * (float)s.csize : 0.0f);
   q.radius = 1.5f * (float)margin * q.base_radius;
+}
+__device__ __forceinline__ void neighbor_query(const SceneDev& s, const StoreDev& st, int p, int margin, int lane, NeighborQuery& q) {
+  neighbor_query(s, table_lists(st, p), __ldg(reinterpret_cast<const float4*>(st.coords) + p), __ldg(reinterpret_cast<const float4*>(st.normals) + p),
+                 st.dscale[p], margin, lane, q);
 }
 
 // CFindMatch::isNeighborRadius (findMatch.cpp:151-185)
@@ -257,17 +272,16 @@ __device__ __forceinline__ bool is_neighbor_radius(const StoreDev& st, const Nei
 // visible-only images), hands every patch found in _pgrids / _vpgrids that passes isNeighborRadius to `hit`.
 // A neighbour seen through several images is reported several times, as in the reference before its sort + unique.
 template <typename Hit>
-__device__ __forceinline__ void for_each_neighbor(const SceneDev& s, const StoreDev& st, int p, const NeighborQuery& q, int margin,
+__device__ __forceinline__ void for_each_neighbor(const SceneDev& s, const StoreDev& st, const PatchLists& pl, const NeighborQuery& q, int margin,
                                                   bool skipvis, float thr, int lane, Hit hit) {
-  const int e0 = st.img_off[p], e1 = st.img_off[p + 1];
-  const int v0 = st.vimg_off[p], v1 = skipvis ? v0 : st.vimg_off[p + 1];
+  const int ni = pl.nimg, nv = skipvis ? 0 : pl.nv;
   const int side = 2 * margin + 1, win = side * side;
-  const int items = ((e1 - e0) + (v1 - v0)) * win;
+  const int items = (ni + nv) * win;
   for (int it = lane; it < items; it += 32) {
     const int le = it / win, w = it - le * win;
     int image, ix, iy;
-    if (le < e1 - e0) { image = st.images[e0 + le]; ix = st.grids[2 * (e0 + le)]; iy = st.grids[2 * (e0 + le) + 1]; }
-    else { const int v = v0 + le - (e1 - e0); image = st.vimages[v]; ix = st.vgrids[2 * v]; iy = st.vgrids[2 * v + 1]; }
+    if (le < ni) { image = pl.images[le]; ix = pl.grids[2 * le]; iy = pl.grids[2 * le + 1]; }
+    else { const int v = le - ni; image = pl.vimages[v]; ix = pl.vgrids[2 * v]; iy = pl.vgrids[2 * v + 1]; }
     if (image >= s.tnum) continue;
     const int x = ix + (w % side) - margin, y = iy + (w / side) - margin;
     const int gw = st.gw[image], gh = st.gh[image];
@@ -312,7 +326,7 @@ __global__ void k_find_empty_blocks(SceneDev s, StoreDev st, int n, const int32_
   ortho4(q.N, xdir, ydir);
   const float rlow = fdiv(q.base_radius, 6.0f), rhigh = q.base_radius * 2.5f;
   unsigned bits = 0;
-  for_each_neighbor(s, st, p, q, 1, false, 0.5f * 4.0f, lane, [&](int, const float* Xb) {
+  for_each_neighbor(s, st, table_lists(st, p), q, 1, false, 0.5f * 4.0f, lane, [&](int, const float* Xb) {
     const float diff[4] = {Xb[0] - q.X[0], Xb[1] - q.X[1], Xb[2] - q.X[2], Xb[3] - q.X[3]};
     float fx = dot4(diff, xdir), fy = dot4(diff, ydir);
     const float len = fsqrt(fx * fx + fy * fy);
@@ -337,29 +351,28 @@ constexpr int kNbSlots = 1024;        // hash slots per warp; the search window 
 constexpr int kNbMax = 512;           // unique neighbours kept (beyond that the patch is accepted unfitted and counted)
 constexpr int kNbWarps = 4;
 
-__global__ void __launch_bounds__(kNbWarps * 32)
-k_filter_neighbor(SceneDev s, StoreDev st, float quad, int tau, uint8_t* __restrict__ reject, float* __restrict__ residual_out,
-                  int32_t* __restrict__ ncount, int32_t* __restrict__ overflow) {
-  __shared__ int32_t slots[kNbWarps][kNbSlots];
-  __shared__ int32_t list[kNbWarps][kNbMax];
-  __shared__ int32_t list_n[kNbWarps];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = blockIdx.x * kNbWarps + wib;
-  if (p >= st.P) return;
-  int32_t* tab = slots[wib];
-  int32_t* lst = list[wib];
+struct NeighborSetSmem {              // per block: one hash set + one list per warp
+  int32_t slots[kNbWarps][kNbSlots];
+  int32_t list[kNbWarps][kNbMax];
+  int32_t list_n[kNbWarps];
+};
+
+// findNeighbors(scale 4, `margin`, skipvis) of one patch into the warp's shared list, unique and in table order.
+// Returns the number of unique neighbours (may exceed kNbMax: then *lost is set and the list is truncated).
+__device__ __forceinline__ int collect_neighbors(const SceneDev& s, const StoreDev& st, const PatchLists& pl, const NeighborQuery& q, int margin,
+                                                 bool skipvis, NeighborSetSmem& sm, int wib, int lane, bool* lost_out) {
+  int32_t* tab = sm.slots[wib];
+  int32_t* lst = sm.list[wib];
   for (int i = lane; i < kNbSlots; i += 32) tab[i] = -1;
-  if (lane == 0) list_n[wib] = 0;
+  if (lane == 0) sm.list_n[wib] = 0;
   __syncwarp();
-  NeighborQuery q;
-  neighbor_query(s, st, p, 2, lane, q);
   bool lost = false;
-  for_each_neighbor(s, st, p, q, 2, true, 0.5f * 4.0f, lane, [&](int b, const float*) {
+  for_each_neighbor(s, st, pl, q, margin, skipvis, 0.5f * 4.0f, lane, [&](int b, const float*) {
     unsigned h = ((unsigned)b * 2654435761u) >> 22;   // 10 bits
     for (int probe = 0; probe < kNbSlots; ++probe) {
       const int old = atomicCAS(tab + h, -1, b);
       if (old == -1) {
-        const int pos = atomicAdd(&list_n[wib], 1);
+        const int pos = atomicAdd(&sm.list_n[wib], 1);
         if (pos < kNbMax) lst[pos] = b; else lost = true;
         return;
       }
@@ -369,18 +382,10 @@ k_filter_neighbor(SceneDev s, StoreDev st, float quad, int tau, uint8_t* __restr
     lost = true;
   });
   __syncwarp();
-  lost = __any_sync(kFull, lost);
-  const int n = min(list_n[wib], kNbMax);
-  if (lane == 0) ncount[p] = list_n[wib];
-  if (lost) {
-    if (lane == 0) { atomicAdd(overflow, 1); reject[p] = 0; residual_out[p] = -2.0f; }
-    return;
-  }
-  if (n < 6) {
-    if (lane == 0) { reject[p] = 1; residual_out[p] = -1.0f; }
-    return;
-  }
-  // table order (the reference sorts by address; any fixed order will do, this one is reproducible)
+  *lost_out = __any_sync(kFull, lost);
+  const int total = sm.list_n[wib];
+  const int n = min(total, kNbMax);
+  // table order (the reference sorts by address; any fixed order will do, this one is reproducible): bitonic sort
   int m = 1;
   while (m < n) m <<= 1;
   for (int i = n + lane; i < m; i += 32) lst[i] = INT32_MAX;
@@ -397,9 +402,18 @@ k_filter_neighbor(SceneDev s, StoreDev st, float quad, int tau, uint8_t* __restr
       }
       __syncwarp();
     }
+  return total;
+}
+
+// CFilter::filterQuad (filter.cpp:394-462) over the n neighbours in lst: residual of the quadric
+// z = a x^2 + b y^2 + c xy + d x + e y fitted in the patch's tangent frame, in units of the patch's mean getUnit over
+// its first tau images.  The 5x5 normal equations are accumulated in double over the lanes and solved by lane 0 (the
+// reference calls Eigen's jacobiSvd on the same system -- not available, parity unpinned); h and the residual are
+// summed in list order like the reference's float loops.
+__device__ __forceinline__ float quad_residual(const SceneDev& s, const StoreDev& st, const PatchLists& pl, const NeighborQuery& q,
+                                               const int32_t* lst, int n, int tau, int lane) {
   float xdir[4], ydir[4];
   ortho4(q.N, xdir, ydir);
-  // h = mean distance to the neighbours, summed in list order
   float hsum = 0.0f;
   for (int base = 0; base < n; base += 32) {
     float d = 0.0f;
@@ -412,8 +426,7 @@ k_filter_neighbor(SceneDev s, StoreDev st, float quad, int tau, uint8_t* __restr
     for (int i = 0; i < cnt; ++i) hsum += __shfl_sync(kFull, d, i);
   }
   const float h = fdiv(hsum, (float)n);
-  // normal equations: 15 distinct entries of A^T A and 5 of A^T b
-  double acc[20];
+  double acc[20];   // 15 distinct entries of A^T A and 5 of A^T b
 #pragma unroll
   for (int k = 0; k < 20; ++k) acc[k] = 0.0;
   for (int i = lane; i < n; i += 32) {
@@ -462,15 +475,13 @@ k_filter_neighbor(SceneDev s, StoreDev st, float quad, int tau, uint8_t* __restr
   }
 #pragma unroll
   for (int a = 0; a < 5; ++a) xs[a] = __shfl_sync(kFull, xs[a], 0);
-  // residual in units of the patch's mean getUnit over its first tau images (filter.cpp:436-443)
   const int inum = min(tau, q.nimg);
   float unit = 0.0f;
   {
-    const int e0 = st.img_off[p];
     float u = 0.0f;
     if (lane < inum) {
       CamDev cam;
-      load_cam(s, st.images[e0 + lane], cam);
+      load_cam(s, pl.images[lane], cam);
       u = get_unit(cam, s.level, q.X);
     }
     for (int i = 0; i < inum; ++i) unit += __shfl_sync(kFull, u, i);
@@ -489,8 +500,129 @@ k_filter_neighbor(SceneDev s, StoreDev st, float quad, int tau, uint8_t* __restr
     const int cnt = min(32, n - base);
     for (int i = 0; i < cnt; ++i) residual += __shfl_sync(kFull, term, i);
   }
-  residual = fdiv(residual, (float)(n - 5));
+  return fdiv(residual, (float)(n - 5));
+}
+
+// CFilter::filterNeighborThread (filter.cpp:357-392) for every table patch: fewer than 6 neighbours from
+// findNeighbors(scale 4, margin 2, skipvis 1), or a quadric residual >= quad, rejects the patch.
+__global__ void __launch_bounds__(kNbWarps * 32)
+k_filter_neighbor(SceneDev s, StoreDev st, float quad, int tau, uint8_t* __restrict__ reject, float* __restrict__ residual_out,
+                  int32_t* __restrict__ ncount, int32_t* __restrict__ overflow) {
+  __shared__ NeighborSetSmem sm;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * kNbWarps + wib;
+  if (p >= st.P) return;
+  const PatchLists pl = table_lists(st, p);
+  NeighborQuery q;
+  neighbor_query(s, st, p, 2, lane, q);
+  bool lost;
+  const int total = collect_neighbors(s, st, pl, q, 2, true, sm, wib, lane, &lost);
+  if (lane == 0) ncount[p] = total;
+  if (lost) {
+    if (lane == 0) { atomicAdd(overflow, 1); reject[p] = 0; residual_out[p] = -2.0f; }
+    return;
+  }
+  if (total < 6) {
+    if (lane == 0) { reject[p] = 1; residual_out[p] = -1.0f; }
+    return;
+  }
+  const float residual = quad_residual(s, st, pl, q, sm.list[wib], total, tau, lane);
   if (lane == 0) { reject[p] = residual < quad ? 0 : 1; residual_out[p] = residual; }
+}
+
+// CFindMatch::isNeighbor (findMatch.cpp:120-149) between a patch outside the table (a) and table patch b
+__device__ __forceinline__ int is_neighbor_ext(const SceneDev& s, const StoreDev& st, const float* Xa, const float* Na, float ua, float dscale_a,
+                                               int b, float thr) {
+  const float4 xb = __ldg(reinterpret_cast<const float4*>(st.coords) + b);
+  const float4 nb = __ldg(reinterpret_cast<const float4*>(st.normals) + b);
+  const float Xb[4] = {xb.x, xb.y, xb.z, xb.w}, Nb[4] = {nb.x, nb.y, nb.z, nb.w};
+  CamDev cam;
+  load_cam(s, st.images[st.img_off[b]], cam);
+  const float ub = get_unit(cam, s.level, Xb);
+  const float hunit = (float)((double)(ua + ub) / 2.0 * (double)s.csize);
+  if (dot4(Na, Nb) < st.cos120_f) return 0;
+  const float diff[4] = {Xb[0] - Xa[0], Xb[1] - Xa[1], Xb[2] - Xa[2], Xb[3] - Xa[3]};
+  const float vunit = dscale_a + st.dscale[b];
+  const float f0 = dot4(Na, diff);
+  const float f1 = dot4(Nb, diff);
+  float ftmp = (fabsf(f0) + fabsf(f1)) / 2.0f;
+  ftmp /= vunit;
+  float t[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t[k] = diff[k] * 2.0f - Na[k] * f0 - Nb[k] * f1;
+  const float hsize = (float)((double)sqrtf(dot4(t, t)) / 2.0 / (double)hunit);
+  if (1.0f < hsize) ftmp /= smin(2.0f, hsize);
+  return ftmp < thr ? 1 : 0;
+}
+
+// COptim::check (source/pmvs/optim.cpp:363-383) for a batch of candidates that are not in the table (postProcess calls
+// it at _depth >= 2): gain = computeGain (filter.cpp:88-146) against the table's cells; reject when gain < 0, or when
+// findNeighbors(scale 4, margin 2) finds more than 6 neighbours and the quadric residual is >= quad.
+// One warp per candidate; lanes take one image entry each for the gain, then share the neighbour search.
+__global__ void __launch_bounds__(kNbWarps * 32)
+k_check_batch(SceneDev s, StoreDev st, int A, int stride, int vstride, const float* __restrict__ coords, const float* __restrict__ normals,
+              const float* __restrict__ ncc, const float* __restrict__ dscale, const int32_t* __restrict__ timages,
+              const int32_t* __restrict__ images, const int32_t* __restrict__ nimages, const int32_t* __restrict__ grids,
+              const int32_t* __restrict__ vimages, const int32_t* __restrict__ nv, const int32_t* __restrict__ vgrids, float quad, int tau,
+              float* __restrict__ gain_out, uint8_t* __restrict__ reject, int32_t* __restrict__ overflow) {
+  __shared__ NeighborSetSmem sm;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kNbWarps + wib;
+  if (c >= A) return;
+  PatchLists pl;
+  pl.images = images + (size_t)c * stride; pl.grids = grids + (size_t)2 * c * stride; pl.nimg = min(nimages[c], stride);
+  pl.vimages = vimages + (size_t)c * vstride; pl.vgrids = vgrids + (size_t)2 * c * vstride; pl.nv = min(nv[c], vstride);
+  const float4 c4 = __ldg(reinterpret_cast<const float4*>(coords) + c);
+  const float4 n4 = __ldg(reinterpret_cast<const float4*>(normals) + c);
+  const float X[4] = {c4.x, c4.y, c4.z, c4.w}, N[4] = {n4.x, n4.y, n4.z, n4.w};
+  const float thr = st.ncc_threshold, ds = dscale[c];
+  // ---- gain
+  float gain = smax(0.0f, ncc[c] - thr) * (float)timages[c];   // score2
+  if (pl.nimg > 0) {
+    CamDev cam;
+    load_cam(s, pl.images[0], cam);
+    const float ua = get_unit(cam, s.level, X);
+    const int entries = pl.nimg + pl.nv;
+    for (int base = 0; base < entries; base += 32) {
+      const int e = base + lane;
+      float maxpressure = 0.0f;
+      if (e < entries) {
+        const bool vis = e >= pl.nimg;
+        const int index = vis ? pl.vimages[e - pl.nimg] : pl.images[e];
+        if (index < s.tnum) {
+          const int gx = vis ? pl.vgrids[2 * (e - pl.nimg)] : pl.grids[2 * e], gy = vis ? pl.vgrids[2 * (e - pl.nimg) + 1] : pl.grids[2 * e + 1];
+          const int gwd = st.gw[index], ghd = st.gh[index];
+          if (gx >= 0 && gx < gwd && gy >= 0 && gy < ghd) {
+            const int cell = st.cell_base[index] + gy * gwd + gx;
+            float pdepth = 0.0f;
+            if (vis) { load_cam(s, index, cam); pdepth = dot4(cam.oaxis, X); }
+            for (int j = st.cell_off[cell]; j < st.cell_off[cell + 1]; ++j) {
+              const int qd = st.cell_patch[j];
+              if (vis) {
+                const float4 xq = __ldg(reinterpret_cast<const float4*>(st.coords) + qd);
+                const float Xq[4] = {xq.x, xq.y, xq.z, xq.w};
+                if (!(pdepth < dot4(cam.oaxis, Xq))) continue;
+              }
+              if (!is_neighbor_ext(s, st, X, N, ua, ds, qd, 1.0f)) maxpressure = smax(maxpressure, st.ncc[qd] - thr);
+            }
+          }
+        }
+      }
+      const int cnt = min(32, entries - base);
+      for (int i = 0; i < cnt; ++i) gain -= __shfl_sync(kFull, maxpressure, i);   // list order: the reference's float sum
+    }
+  }
+  if (lane == 0) gain_out[c] = gain;
+  if (gain < 0.0f) { if (lane == 0) reject[c] = 1; return; }
+  // ---- neighbours and quadric fit
+  NeighborQuery q;
+  neighbor_query(s, pl, c4, n4, ds, 2, lane, q);
+  bool lost;
+  const int total = collect_neighbors(s, st, pl, q, 2, false, sm, wib, lane, &lost);
+  if (lost) { if (lane == 0) { atomicAdd(overflow, 1); reject[c] = 0; } return; }
+  int rej = 0;
+  if (6 < total) rej = quad_residual(s, st, pl, q, sm.list[wib], total, tau, lane) < quad ? 0 : 1;
+  if (lane == 0) reject[c] = (uint8_t)rej;
 }
 
 }  // namespace pmvsb

@@ -85,139 +85,6 @@ bool Pipeline::is_neighbor(const Patch& l, const Patch& r, float thr) const {   
   return is_neighbor(l, r, hunit, thr, -1.0f);
 }
 
-float Pipeline::compute_radius(const Patch& p) const {   // expand.cpp:182-198 with COptim::computeUnits (optim.cpp:446-471)
-  std::vector<float> units;
-  for (int im : p.images) {
-    float u = get_unit(im, p.coord);
-    const Camera& c = cams_[im];
-    float ray[4] = {c.centre[0] - p.coord[0], c.centre[1] - p.coord[1], c.centre[2] - p.coord[2], c.centre[3] - p.coord[3]};
-    unitize4(ray);
-    const float d = dot4(ray, p.normal);
-    u = 0.0f < d ? u / d : (float)(INT32_MAX / 2);
-    units.push_back(u);
-  }
-  if (units.size() < 2) return units.empty() ? 0.0f : units[0] * opt_.csize;
-  std::nth_element(units.begin(), units.begin() + 1, units.end());
-  return units[1] * opt_.csize;
-}
-
-void Pipeline::find_neighbors(const Patch& p, std::vector<int>& out, float scale, int margin, bool skipvis) const {   // patchOrganizerS.cpp:528-651
-  out.clear();
-  const float radius = 1.5f * margin * compute_radius(p);
-  float unit = 0.0f;
-  for (int im : p.images) unit += get_unit(im, p.coord);
-  unit /= (int)p.images.size();
-  unit *= opt_.csize;
-  auto scan = [&](int image, int ix, int iy) {
-    const ImageGrid& g = grids_[image];
-    for (int j = -margin; j <= margin; ++j) {
-      const int y = iy + j;
-      if (y < 0 || g.gh <= y) continue;
-      for (int i = -margin; i <= margin; ++i) {
-        const int x = ix + i;
-        if (x < 0 || g.gw <= x) continue;
-        const size_t cell = (size_t)y * g.gw + x;
-        for (int q : g.pg[cell])
-          if (is_neighbor(p, patches_[q], unit, neighbor_threshold_ * scale, radius)) out.push_back(q);
-        for (int q : g.vpg[cell])
-          if (is_neighbor(p, patches_[q], unit, neighbor_threshold_ * scale, radius)) out.push_back(q);
-      }
-    }
-  };
-  for (size_t i = 0; i < p.images.size(); ++i)
-    if (p.images[i] < tnum_) scan(p.images[i], p.grids[i][0], p.grids[i][1]);
-  if (!skipvis)
-    for (size_t i = 0; i < p.vimages.size(); ++i) scan(p.vimages[i], p.vgrids[i][0], p.vgrids[i][1]);
-  std::sort(out.begin(), out.end());
-  out.erase(std::unique(out.begin(), out.end()), out.end());
-}
-
-// CFilter::filterQuad (filter.cpp:394-462): fit z = a x^2 + b y^2 + c xy + d x + e y over the neighbours in the
-// patch's tangent frame (least squares in double, as Cmylapack::lls does through Eigen), residual in units.
-bool Pipeline::filter_quad(const Patch& p, const std::vector<int>& nb) const {
-  float xd[4], yd[4];
-  ortho(p.normal, xd, yd);
-  const int n = (int)nb.size();
-  float hsum = 0.0f;
-  for (int q : nb) {
-    float d[4];
-    for (int k = 0; k < 4; ++k) d[k] = patches_[q].coord[k] - p.coord[k];
-    hsum += norm4(d);
-  }
-  const float h = hsum / n;
-  std::vector<float> fx(n), fy(n), fz(n);
-  double ATA[5][5] = {{0}}, ATb[5] = {0};
-  for (int i = 0; i < n; ++i) {
-    float d[4];
-    for (int k = 0; k < 4; ++k) d[k] = patches_[nb[i]].coord[k] - p.coord[k];
-    fx[i] = dot4(d, xd) / h; fy[i] = dot4(d, yd) / h; fz[i] = dot4(d, p.normal);
-    const double row[5] = {(double)(fx[i] * fx[i]), (double)(fy[i] * fy[i]), (double)(fx[i] * fy[i]), (double)fx[i], (double)fy[i]};
-    for (int a = 0; a < 5; ++a) {
-      for (int b = 0; b < 5; ++b) ATA[a][b] += row[a] * row[b];
-      ATb[a] += row[a] * (double)fz[i];
-    }
-  }
-  // Gaussian elimination with partial pivoting on the 5x5 normal equations
-  double M[5][6];
-  for (int a = 0; a < 5; ++a) { for (int b = 0; b < 5; ++b) M[a][b] = ATA[a][b]; M[a][5] = ATb[a]; }
-  double x[5] = {0, 0, 0, 0, 0};
-  bool singular = false;
-  for (int c = 0; c < 5 && !singular; ++c) {
-    int piv = c;
-    for (int r = c + 1; r < 5; ++r) if (std::fabs(M[r][c]) > std::fabs(M[piv][c])) piv = r;
-    if (std::fabs(M[piv][c]) < 1e-300) { singular = true; break; }
-    if (piv != c) for (int k = 0; k < 6; ++k) std::swap(M[c][k], M[piv][k]);
-    for (int r = c + 1; r < 5; ++r) {
-      const double f = M[r][c] / M[c][c];
-      for (int k = c; k < 6; ++k) M[r][k] -= f * M[c][k];
-    }
-  }
-  if (!singular)
-    for (int r = 4; r >= 0; --r) {
-      double s = M[r][5];
-      for (int k = r + 1; k < 5; ++k) s -= M[r][k] * x[k];
-      x[r] = s / M[r][r];
-    }
-  const float xs[5] = {(float)x[0], (float)x[1], (float)x[2], (float)x[3], (float)x[4]};
-  const int inum = std::min(tau_, (int)p.images.size());
-  float unit = 0.0f;
-  for (int i = 0; i < inum; ++i) unit += get_unit(p.images[i], p.coord);
-  unit /= inum;
-  float residual = 0.0f;
-  for (int i = 0; i < n; ++i) {
-    const float res = xs[0] * (fx[i] * fx[i]) + xs[1] * (fy[i] * fy[i]) + xs[2] * (fx[i] * fy[i]) + xs[3] * fx[i] + xs[4] * fy[i] - fz[i];
-    residual += std::fabs(res) / unit;
-  }
-  residual /= (n - 5);
-  return !(residual < opt_.quad);
-}
-
-float Pipeline::compute_gain(const Patch& p) const {   // filter.cpp:88-146 (host copy for COptim::check, optim.cpp:363-383)
-  float gain = std::max(0.0f, p.ncc - ncc_threshold_) * p.timages;
-  for (size_t i = 0; i < p.images.size(); ++i) {
-    const int index = p.images[i];
-    if (tnum_ <= index) continue;
-    const ImageGrid& g = grids_[index];
-    float maxp = 0.0f;
-    for (int q : g.pg[(size_t)p.grids[i][1] * g.gw + p.grids[i][0]])
-      if (!is_neighbor(p, patches_[q], neighbor_threshold1_)) maxp = std::max(maxp, patches_[q].ncc - ncc_threshold_);
-    gain -= maxp;
-  }
-  for (size_t i = 0; i < p.vimages.size(); ++i) {
-    const int index = p.vimages[i];
-    if (tnum_ <= index) continue;
-    const ImageGrid& g = grids_[index];
-    const float pdepth = dot4(cams_[index].oaxis, p.coord);
-    float maxp = 0.0f;
-    for (int q : g.pg[(size_t)p.vgrids[i][1] * g.gw + p.vgrids[i][0]]) {
-      const float bdepth = dot4(cams_[index].oaxis, patches_[q].coord);
-      if (pdepth < bdepth && !is_neighbor(p, patches_[q], neighbor_threshold1_)) maxp = std::max(maxp, patches_[q].ncc - ncc_threshold_);
-    }
-    gain -= maxp;
-  }
-  return gain;
-}
-
 // ---------------------------------------------------------------------------------------------- bookkeeping
 int Pipeline::add_patch(const Patch& p) {   // patchOrganizerS.cpp:312-349
   const int id = (int)patches_.size();
@@ -427,6 +294,25 @@ void Pipeline::evaluate_range(std::vector<Candidate>& all, std::vector<int>& all
       p.vimages.push_back(avim[(size_t)j * vs + i]);
       p.vgrids.push_back({avgr[((size_t)j * vs + i) * 2], avgr[((size_t)j * vs + i) * 2 + 1]});
     }
+  }
+  if (depth_ < 2) return;
+  // COptim::check (optim.cpp:363-383), the last step of postProcess from the second round on: gain against the cells of
+  // the resident table, then the quadric fit over its neighbours
+  Tick tk(this, "gpu.check");
+  std::vector<float> ancc(A), adsc(A), again(A);
+  std::vector<int32_t> ati(A), agr((size_t)2 * stride * A, 0);
+  std::vector<uint8_t> arej(A);
+  for (int j = 0; j < A; ++j) {
+    const Patch& p = cands[acc[j]].patch;
+    ancc[j] = p.ncc; adsc[j] = p.dscale; ati[j] = p.timages;
+    for (size_t i = 0; i < p.grids.size(); ++i) { agr[((size_t)j * stride + i) * 2] = p.grids[i][0]; agr[((size_t)j * stride + i) * 2 + 1] = p.grids[i][1]; }
+  }
+  int32_t overflow = 0;
+  if (pmvsb_check_batch(gpu_, A, stride, ac.data(), an.data(), ancc.data(), adsc.data(), ati.data(), ai.data(), ani.data(), agr.data(), vs, avim.data(),
+                        anv.data(), avgr.data(), opt_.quad, again.data(), arej.data(), &overflow)) die("check_batch");
+  for (int j = 0; j < A; ++j) {
+    cands[acc[j]].patch.tmp = again[j];
+    if (arej[j]) verdict[acc[j]] = 2;
   }
 }
 
@@ -824,17 +710,6 @@ void Pipeline::expand_round() {
         Patch& p = c.patch;
         // the cell rules are re-checked against the grids as they are NOW (what a sequential run would have seen)
         if (check_counts(p)) { ++st.fail0; fail = true; }
-        if (!fail && depth_ >= 2) {   // COptim::check (optim.cpp:363-383)
-          const float gain = compute_gain(p);
-          p.tmp = gain;
-          if (gain < 0.0f) fail = true;
-          if (!fail) {
-            std::vector<int> nb;
-            find_neighbors(p, nb, 4.0f, 2, false);
-            if (6 < (int)nb.size() && filter_quad(p, nb)) fail = true;
-          }
-          if (fail) ++st.fail1;
-        }
         if (!fail) {
           ++st.pass;
           const bool requeue = update_counts(p);

@@ -1,9 +1,10 @@
 // cmvs-pmvs_b200/host/pmvs_host.hpp -- host side of the pmvs2 drop-in binary (C++17).
 //
-// What stays on the host (BASELINE.json north_star): option / camera / image file handling, feature detection,
-// seed candidate enumeration, the per-image cell bookkeeping (CPatchOrganizerS's role), the quadric and
-// small-group filters and the output writers.  Everything photometric (pre/postProcess, refinePatch, depth maps,
-// visibility, gains) is a batched call into libpmvs_b200.so (include/pmvs_b200.h).
+// What stays on the host (BASELINE.json north_star): option / camera / image file handling, seed candidate
+// enumeration, the per-image cell bookkeeping and commit rules (CPatchOrganizerS's role), the small-group filter and
+// the output writers.  Everything photometric or neighbour-searching (features, pre/postProcess incl. check,
+// refinePatch, depth maps, visibility, gains, findEmptyBlocks, filterNeighbor) is a batched call into
+// libpmvs_b200.so (include/pmvs_b200.h).
 //
 // The reference works patch by patch from worker threads; this driver works in WAVES: all candidates that can be
 // generated from the current grid snapshot are evaluated by one launch per stage and then committed in the
@@ -110,10 +111,6 @@ class Pipeline {
   float get_unit(int image, const float* X) const;
   bool is_neighbor(const Patch& l, const Patch& r, float hunit, float thr, float radius) const;   // radius < 0: no radius test
   bool is_neighbor(const Patch& l, const Patch& r, float thr) const;
-  float compute_radius(const Patch& p) const;
-  void find_neighbors(const Patch& p, std::vector<int>& out, float scale, int margin, bool skipvis) const;
-  bool filter_quad(const Patch& p, const std::vector<int>& neighbors) const;
-  float compute_gain(const Patch& p) const;
   // ---- bookkeeping
   int add_patch(const Patch& p);            // CPatchOrganizerS::addPatch
   void remove_patch(int id);                // CPatchOrganizerS::removePatch

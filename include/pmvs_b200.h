@@ -162,6 +162,13 @@ int pmvsb_find_empty_blocks_store(pmvsb_ctx* ctx, int n, const int32_t* ids, uin
  * >= quad.  Optional outputs: residual float[P] (-1 = too few neighbours), ncount int32[P] unique neighbours,
  * overflow = patches whose neighbour set did not fit on chip (kept, never silently rejected). */
 int pmvsb_filter_neighbor_store(pmvsb_ctx* ctx, float quad, uint8_t* reject, float* residual, int32_t* ncount, int32_t* overflow);
+/* COptim::check (source/pmvs/optim.cpp:363-383), the last step of postProcess at _depth >= 2, for a batch of candidates that
+ * are not in the table: gain[p] = CFilter::computeGain (filter.cpp:88-146, stored to CPatch::_tmp) against the table's
+ * cells; reject[p] = 1 when gain < 0, or when findNeighbors(scale 4, margin 2) has more than 6 neighbours and the
+ * quadric residual (filterQuad) is >= quad.  Lists as in pre/post-process (stride / vstride = capacity per patch). */
+int pmvsb_check_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals, const float* ncc, const float* dscale,
+                      const int32_t* timages, const int32_t* images, const int32_t* nimages, const int32_t* grids, int vstride,
+                      const int32_t* vimages, const int32_t* nv, const int32_t* vgrids, float quad, float* gain, uint8_t* reject, int32_t* overflow);
 /* CFilter::filterExactThread's visibility re-test (filter.cpp:315-343): safe uint8[E], one flag per image entry */
 int pmvsb_filter_exact_store(pmvsb_ctx* ctx, uint8_t* safe);
 /* CFilter::filterOutsideThread / computeGain (filter.cpp:88-201): gains float[P] */

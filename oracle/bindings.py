@@ -293,6 +293,11 @@ class OracleLib(_Common):
         m = self.lib.pmvso_find_empty_blocks(self.ctx, int(k), C.byref(r))
         return int(m), np.float32(r.value)
 
+    def check(self, k, quad=2.5):
+        gain = C.c_float()
+        rej = self.lib.pmvso_check(self.ctx, int(k), C.c_float(quad), C.byref(gain))
+        return int(rej), np.float32(gain.value)
+
     def filter_neighbor(self, k, quad=2.5):
         res = C.c_float(); cnt = C.c_int()
         rej = self.lib.pmvso_filter_neighbor(self.ctx, int(k), C.c_float(quad), C.byref(res), C.byref(cnt))
@@ -433,6 +438,11 @@ class RefLib(_Common):
 
     def find_empty_blocks(self, k):
         return int(self.lib.ref_find_empty_blocks(int(k)))
+
+    def check(self, k, quad=2.5):
+        gain = C.c_float()
+        rej = self.lib.ref_check(int(k), C.c_float(quad), C.byref(gain))
+        return int(rej), np.float32(gain.value)
 
     def filter_neighbor(self, k, quad=2.5):
         cnt = C.c_int()

@@ -1267,16 +1267,10 @@ int pmvso_find_empty_blocks(const pmvso_ctx* c, int k, float* radius_out) {
   return mask;
 }
 
-/* CFilter::filterNeighborThread + filterQuad (filter.cpp:357-462).  The least-squares solve (Cmylapack::lls ->
- * Eigen jacobiSvd in the reference, absent: PARITY UNPINNED) is the 5x5 normal equations in double with partial
- * pivoting.  Returns 1 = reject; *residual_out = -1 when there are fewer than 6 neighbours. */
-int pmvso_filter_neighbor(const pmvso_ctx* c, int k, float quad, float* residual_out, int* ncount_out) {
+/* CFilter::filterQuad (filter.cpp:394-462) over the neighbour list nb[0..n).  The least-squares solve (Cmylapack::lls ->
+ * Eigen jacobiSvd in the reference, absent: PARITY UNPINNED) is the 5x5 normal equations in double with partial pivoting. */
+static float quad_residual(const pmvso_ctx* c, int k, const int* nb, int n) {
   const float* X = c->s_coords + 4 * k; const float* N = c->s_normals + 4 * k;
-  int cap = c->P > 0 ? c->P : 1;
-  int* nb = (int*)malloc(sizeof(int) * cap);
-  const int n = pmvso_find_neighbors(c, k, 4.0f, 2, 1, nb, cap);
-  if (ncount_out) *ncount_out = n;
-  if (n < 6) { free(nb); if (residual_out) *residual_out = -1.0f; return 1; }
   float xdir[4], ydir[4];
   ortho4(N, xdir, ydir);
   float h = 0.0f;
@@ -1329,9 +1323,35 @@ int pmvso_filter_neighbor(const pmvso_ctx* c, int k, float quad, float* residual
     residual += fabsf(res) / unit;
   }
   residual /= (n - 5);
-  free(fx); free(fy); free(fz); free(nb);
+  free(fx); free(fy); free(fz);
+  return residual;
+}
+
+/* CFilter::filterNeighborThread (filter.cpp:357-392).  Returns 1 = reject; *residual_out = -1 when there are fewer than 6 neighbours. */
+int pmvso_filter_neighbor(const pmvso_ctx* c, int k, float quad, float* residual_out, int* ncount_out) {
+  int cap = c->P > 0 ? c->P : 1;
+  int* nb = (int*)malloc(sizeof(int) * cap);
+  const int n = pmvso_find_neighbors(c, k, 4.0f, 2, 1, nb, cap);
+  if (ncount_out) *ncount_out = n;
+  if (n < 6) { free(nb); if (residual_out) *residual_out = -1.0f; return 1; }
+  const float residual = quad_residual(c, k, nb, n);
+  free(nb);
   if (residual_out) *residual_out = residual;
   return residual < quad ? 0 : 1;
+}
+
+/* COptim::check (optim.cpp:363-383) on table patch k: 1 = reject; *gain_out = computeGain (what check stores in _tmp) */
+int pmvso_check(const pmvso_ctx* c, int k, float quad, float* gain_out) {
+  const float gain = pmvso_compute_gain(c, k);
+  if (gain_out) *gain_out = gain;
+  if (gain < 0.0) return 1;
+  int cap = c->P > 0 ? c->P : 1;
+  int* nb = (int*)malloc(sizeof(int) * cap);
+  const int n = pmvso_find_neighbors(c, k, 4.0f, 2, 0, nb, cap);
+  int rej = 0;
+  if (6 < n && !(quad_residual(c, k, nb, n) < quad)) rej = 1;
+  free(nb);
+  return rej;
 }
 
 /* ---------------------------------------------------------------------------------------------------------------

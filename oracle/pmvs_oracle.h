@@ -90,7 +90,8 @@ int pmvso_detect_features(const pmvso_ctx* c, int index, int gspeedup, float* xy
 float pmvso_compute_radius(const pmvso_ctx* c, int k);
 int pmvso_find_neighbors(const pmvso_ctx* c, int k, float scale, int margin, int skipvis, int* out, int cap);
 int pmvso_find_empty_blocks(const pmvso_ctx* c, int k, float* radius_out);
-int pmvso_filter_neighbor(const pmvso_ctx* c, int k, float quad, float* residual_out, int* ncount_out);                 /* CFilter::computeGain, filter.cpp:88-146 */
+int pmvso_filter_neighbor(const pmvso_ctx* c, int k, float quad, float* residual_out, int* ncount_out);
+int pmvso_check(const pmvso_ctx* c, int k, float quad, float* gain_out);   /* COptim::check, optim.cpp:363-383 */                 /* CFilter::computeGain, filter.cpp:88-146 */
 
 #ifdef __cplusplus
 }

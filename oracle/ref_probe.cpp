@@ -411,6 +411,14 @@ int ref_detect_features(int index, int gspeedup, float* xy, float* resp, int* ty
   }
   return n;
 }
+// COptim::check on a COPY of table patch k (check clears the image list of a rejected patch): 1 = reject, *gain = _tmp
+int ref_check(int k, float quad, float* gain) {
+  g_fm->_quadThreshold = quad;
+  Patch::CPatch p = *g_fm->_pos._ppatches[k];
+  const int r = g_fm->_optim.check(p);
+  *gain = p._tmp;
+  return r;
+}
 int ref_get_depth_flag(void) { return g_fm->_depth; }
 float ref_neighbor_threshold(int which) { return which == 0 ? g_fm->_neighborThreshold : (which == 1 ? g_fm->_neighborThreshold1 : g_fm->_neighborThreshold2); }
 

@@ -68,6 +68,10 @@ def main():
     out["empty_mask"] = np.array([ref.find_empty_blocks(k) for k in range(P)], np.uint8)
     fnb = [ref.filter_neighbor(k) for k in range(P)]
     out["fnb_reject"] = np.array([r for r, _ in fnb], np.uint8); out["fnb_count"] = np.array([c for _, c in fnb], np.int32)
+    # COptim::check (gain + quadric test of postProcess at depth >= 2) on every table patch, at the option's quad and a tight one
+    chk = [ref.check(k, 2.5) for k in range(P)]
+    out["check_reject"] = np.array([r for r, _ in chk], np.uint8); out["check_gain"] = np.array([g_ for _, g_ in chk], np.float32)
+    out["check_reject_q01"] = np.array([ref.check(k, 0.1)[0] for k in range(P)], np.uint8)
     # the final table has already been through the filter at quad 2.5; tighter thresholds exercise filterQuad's fit
     out["fnb_quads"] = np.array([0.03, 0.1, 0.5], np.float32)
     out["fnb_reject_q"] = np.array([[ref.filter_neighbor(k, float(q))[0] for k in range(P)] for q in out["fnb_quads"]], np.uint8)

@@ -63,3 +63,31 @@ def make_patches(scene, orc, n, seed, k=None, depth_sigma=0.004, normal_sigma=0.
         images[i] = pick_views(scene, coords[i], normals[i], k)
         dscales[i] = orc.set_scales(coords[i], images[i])[0]
     return dict(coords=coords, normals=normals, images=images, dscales=dscales)
+
+
+def option_variants():
+    """Option-file variants of small_scene() that exercise the rest of the option contract (source/pmvs/option.cpp)."""
+    return {
+        "oimages": {"timages": (-1, 0, 12), "oimages": (-1, 12, 16)},             # four non-target images
+        "visdata": {"useVisData": 1},                                              # vis.dat: +-3 neighbours on the ring
+        "sequence": {"sequence": 2},                                               # only images within 2 of the reference
+        "enumerated": {"timages": (8, 0, 2, 4, 6, 8, 10, 12, 14), "oimages": (4, 1, 5, 9, 13), "csize": 1, "level": 1},
+    }
+
+
+def write_variant(scene, name, prefix, cpu):
+    """small_scene() with the variant's option file (and vis.dat) under `prefix`; returns the prefix with trailing '/'."""
+    import copy
+    synth = _synth()
+    sc = copy.copy(scene)
+    sc.option = dict(scene.option)
+    sc.option.update(option_variants()[name])
+    sc.option["CPU"] = cpu
+    out = synth.write_scene(sc, prefix)
+    n = scene.num
+    with open(out + "vis.dat", "w") as f:
+        f.write("VISDATA\n%d\n" % n)
+        for i in range(n):
+            nb = sorted({(i + d) % n for d in (-3, -2, -1, 1, 2, 3)})
+            f.write("%d %d  %s\n" % (i, len(nb), " ".join(str(v) for v in nb)))
+    return out

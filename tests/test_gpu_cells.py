@@ -150,3 +150,30 @@ def test_append_rejects_bad_indexes(gpu, pkg, state):
     with pytest.raises(pkg.PmvsError):
         gpu.store_append(bad)
     gpu.store_upload(st); gpu.build_depth_maps()
+
+
+def test_check_batch_matches_reference(gpu, S, state):
+    """COptim::check for candidates handed over as arrays (here: the table's own patches, so the reference's answers on
+    its final table apply): gains bit-exact, verdicts equal at the option's quad and at a tight one"""
+    st, o = state
+    P = len(st["ncc"])
+    ni = np.diff(st["img_off"]); nv = np.diff(st["vimg_off"])
+    stride, vstride = int(ni.max()), max(int(nv.max()), 1)
+    images = np.zeros((P, stride), np.int32); grids = np.zeros((P, stride, 2), np.int32)
+    vimages = np.zeros((P, vstride), np.int32); vgrids = np.zeros((P, vstride, 2), np.int32)
+    for k in range(P):
+        a, b = st["img_off"][k], st["img_off"][k + 1]
+        images[k, :b - a] = st["images"][a:b]; grids[k, :b - a] = st["grids"].reshape(-1, 2)[a:b]
+        a, b = st["vimg_off"][k], st["vimg_off"][k + 1]
+        vimages[k, :b - a] = st["vimages"][a:b]; vgrids[k, :b - a] = st["vgrids"].reshape(-1, 2)[a:b]
+    gain, rej, ov = gpu.check_batch(st["coords"], st["normals"], st["ncc"], st["dscale"], st["timages"], images, ni, grids, vimages, nv, vgrids, 2.5)
+    assert ov == 0
+    assert np.array_equal(gain, S["check_gain"])
+    assert np.array_equal(rej, S["check_reject"])
+    _, rej2, _ = gpu.check_batch(st["coords"], st["normals"], st["ncc"], st["dscale"], st["timages"], images, ni, grids, vimages, nv, vgrids, 0.1)
+    assert (rej2 != S["check_reject_q01"]).mean() < 1e-3     # residuals on the threshold may round either way (lane-wise double sums)
+    sub = slice(100, 164)                                     # a small batch, wider strides than needed
+    g3, r3, _ = gpu.check_batch(st["coords"][sub], st["normals"][sub], st["ncc"][sub], st["dscale"][sub], st["timages"][sub],
+                                np.pad(images[sub], ((0, 0), (0, 5))), ni[sub], np.pad(grids[sub], ((0, 0), (0, 5), (0, 0))),
+                                np.pad(vimages[sub], ((0, 0), (0, 3))), nv[sub], np.pad(vgrids[sub], ((0, 0), (0, 3), (0, 0))), 2.5)
+    assert np.array_equal(g3, gain[sub]) and np.array_equal(r3, rej[sub])

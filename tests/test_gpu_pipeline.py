@@ -112,3 +112,25 @@ def test_two_gpus_write_the_same_models(run, pkg, scene, tmp_path_factory):
         b = open(prefix2 + "models/option.txt" + ext, "rb").read()
         assert a == b, ext
     assert "gpu.allgather_wave" in p.stderr
+
+
+@pytest.mark.parametrize("name", ["oimages", "visdata", "sequence", "enumerated"])
+def test_option_variants(name, scene, tmp_path):
+    """The rest of the option-file contract (source/pmvs/option.cpp): non-target images, vis.dat, sequence, enumerated
+    image lists with csize 1 -- same bars against the reference binary's cloud for the same option file."""
+    import torch
+    from scene_util import write_variant
+    G = np.load(os.path.join(HERE, "golden", "pmvs_pipeline.npz"))
+    prefix = write_variant(scene, name, str(tmp_path / name), cpu=os.cpu_count() or 4)
+    p = subprocess.run([PMVS2, prefix, "option.txt", "PSET"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    pts = np.loadtxt(prefix + "models/option.txt.pset", dtype=np.float32).reshape(-1, 6)
+    ref = G["variant_%s_pset" % name]
+    want = int(G["variant_%s_patches" % name])
+    R = torch.from_numpy(ref[:, :3]).cuda()
+    d = torch.cdist(R, R); d.fill_diagonal_(1e9)
+    spacing = float(d.min(dim=1).values.mean())
+    a, b = _nn(pts[:, :3], ref[:, :3]), _nn(ref[:, :3], pts[:, :3])
+    print("%s: patches %d vs reference %d; cloud distance %.5f / %.5f, reference spacing %.5f" % (name, len(pts), want, a, b, spacing))
+    assert abs(len(pts) - want) <= COUNT_TOL * want, (len(pts), want)
+    assert a < CLOUD_TOL * spacing and b < CLOUD_TOL * spacing, (a, b, spacing)

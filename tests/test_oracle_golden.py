@@ -205,3 +205,14 @@ def test_detect_features(oracle, scene_checked):
         assert np.array_equal(xy, F["xy"][lo:hi].astype(np.float32)), i
         assert np.array_equal(resp, F["resp"][lo:hi]) and np.array_equal(typ, F["type"][lo:hi].astype(np.int32)), i
     assert (F["type"] == 0).sum() > 100 and (F["type"] == 1).sum() > 100
+
+
+def test_check(oracle_state, S):
+    """COptim::check (gain + quadric test) on every table patch at the option's quad and at a tight one"""
+    o = oracle_state
+    P = len(S["st_ncc"])
+    got = [o.check(k, 2.5) for k in range(P)]
+    assert np.array_equal(np.array([r for r, _ in got], np.uint8), S["check_reject"])
+    assert np.array_equal(np.array([g for _, g in got], np.float32), S["check_gain"])
+    assert np.array_equal(np.array([o.check(k, 0.1)[0] for k in range(P)], np.uint8), S["check_reject_q01"])
+    assert 0.01 < S["check_reject_q01"].mean() < 0.5
