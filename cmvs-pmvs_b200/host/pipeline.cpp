@@ -95,11 +95,8 @@ int Pipeline::add_patch(const Patch& p) {   // patchOrganizerS.cpp:312-349
     if (tnum_ <= im) continue;
     grids_[im].pg[(size_t)p.grids[i][1] * grids_[im].gw + p.grids[i][0]].push_back(id);
   }
-  if (depth_ != 0)
-    for (size_t i = 0; i < p.vimages.size(); ++i) {
-      const int im = p.vimages[i];
-      grids_[im].vpg[(size_t)p.vgrids[i][1] * grids_[im].gw + p.vgrids[i][0]].push_back(id);
-    }
+  // _vpgrids live on the device (pmvsb_store_append / pmvsb_store_update_vimages); the one host consumer,
+  // filter_small_groups, builds its own copy from the patches' _vimages when it runs
   return id;
 }
 
@@ -110,10 +107,6 @@ void Pipeline::remove_patch(int id) {   // patchOrganizerS.cpp:452-477
     const int im = p.images[i];
     if (tnum_ <= im) continue;
     drop(grids_[im].pg[(size_t)p.grids[i][1] * grids_[im].gw + p.grids[i][0]]);
-  }
-  for (size_t i = 0; i < p.vimages.size(); ++i) {
-    const int im = p.vimages[i];
-    drop(grids_[im].vpg[(size_t)p.vgrids[i][1] * grids_[im].gw + p.vgrids[i][0]]);
   }
   p.alive = false;
 }
@@ -186,7 +179,7 @@ void Pipeline::append_table(const std::vector<int>& ids) {
 }
 
 // CFilter::setDepthMapsVGridsVPGridsAddPatchV (filter.cpp:734-783): table -> GPU, depth maps, _vimages/_vgrids of every
-// patch recomputed on the device inside the table, then mirrored into the host patches and _vpgrids
+// patch recomputed on the device inside the table (with _vpgrids), then mirrored into the host patches' lists
 void Pipeline::rebuild_depth_and_vis(bool additive) {
   Tick tk(this, "filter.rebuild_depth_and_vis");
   const std::vector<int> ids = collect_patches();
@@ -194,7 +187,6 @@ void Pipeline::rebuild_depth_and_vis(bool additive) {
     parallel_for((int)ids.size(), threads_, [&](int k) { patches_[ids[k]].vimages.clear(); patches_[ids[k]].vgrids.clear(); }, 1024);
   upload_table(ids);
   const int P = (int)ids.size();
-  parallel_for(tnum_, threads_, [&](int im) { for (auto& cell : grids_[im].vpg) cell.clear(); }, 1);
   if (P == 0) return;
   int32_t total = 0;
   if (pmvsb_store_update_vimages(gpu_, additive ? 1 : 0, &total)) die("store_update_vimages");
@@ -209,15 +201,6 @@ void Pipeline::rebuild_depth_and_vis(bool additive) {
       p.vgrids[i] = {vgr[(size_t)2 * (voff[k] + i)], vgr[(size_t)2 * (voff[k] + i) + 1]};
     }
   }, 1024);
-  // addPatchV: per image, patches in table order (one thread owns one image's cells)
-  parallel_for(tnum_, threads_, [&](int im) {
-    ImageGrid& g = grids_[im];
-    for (int k = 0; k < P; ++k) {
-      const Patch& p = patches_[ids[k]];
-      for (size_t i = 0; i < p.vimages.size(); ++i)
-        if (p.vimages[i] == im) g.vpg[(size_t)p.vgrids[i][1] * g.gw + p.vgrids[i][0]].push_back(ids[k]);
-    }
-  }, 1);
 }
 
 // ---------------------------------------------------------------------------------------------- evaluate a wave
@@ -230,12 +213,12 @@ void Pipeline::evaluate_range(std::vector<Candidate>& all, std::vector<int>& all
   std::vector<float> coords((size_t)4 * P), normals((size_t)4 * P), dsc(P), asc(P), ncc(P, -1.0f), tmp(P);
   std::vector<int32_t> images((size_t)stride * P, 0), nimages(P), v0(P), evals(P), grids((size_t)2 * stride * P), timages(P), v1(P);
   std::vector<uint8_t> ok(P);
-  for (int k = 0; k < P; ++k) {
+  parallel_for(P, threads_, [&](int k) {
     const Patch& p = cands[k].patch;
     for (int c = 0; c < 4; ++c) { coords[4 * k + c] = p.coord[c]; normals[4 * k + c] = p.normal[c]; }
     nimages[k] = std::min((int)p.images.size(), stride);
     for (int i = 0; i < nimages[k]; ++i) images[(size_t)k * stride + i] = p.images[i];
-  }
+  }, 512);
   if (pmvsb_set_thresholds(gpu_, ncc_threshold_, ncc_threshold_before_)) die("set_thresholds");
   { Tick tk(this, "gpu.pre_process");
   if (pmvsb_pre_process_batch(gpu_, P, stride, coords.data(), normals.data(), images.data(), nimages.data(), dsc.data(), asc.data(), v0.data())) die("pre_process_batch"); }
@@ -247,21 +230,21 @@ void Pipeline::evaluate_range(std::vector<Candidate>& all, std::vector<int>& all
   std::vector<float> lc((size_t)4 * L), ln((size_t)4 * L), ld(L), lncc(L), ltmp(L);
   std::vector<int32_t> li((size_t)stride * L), lni(L), lev(L), lgr((size_t)2 * stride * L), lti(L), lv(L);
   std::vector<uint8_t> lok(L);
-  for (int j = 0; j < L; ++j) {
+  parallel_for(L, threads_, [&](int j) {
     const int k = live[j];
     for (int c = 0; c < 4; ++c) { lc[4 * j + c] = coords[4 * k + c]; ln[4 * j + c] = normals[4 * k + c]; }
     ld[j] = dsc[k]; lni[j] = nimages[k];
     for (int i = 0; i < stride; ++i) li[(size_t)j * stride + i] = images[(size_t)k * stride + i];
-  }
+  }, 512);
   { Tick tk(this, "gpu.refine");
   if (pmvsb_refine_batch(gpu_, L, stride, lc.data(), ln.data(), li.data(), lni.data(), ld.data(), lncc.data(), lev.data(), lok.data())) die("refine_batch"); }
   // a failed optimiser leaves the patch untouched and the reference still runs postProcess on it (optim.cpp:496-502)
   { Tick tk(this, "gpu.post_process");
   if (pmvsb_post_process_batch(gpu_, L, stride, lc.data(), ln.data(), lncc.data(), li.data(), lni.data(), lgr.data(), lti.data(), ltmp.data(), lv.data())) die("post_process_batch"); }
-  for (int j = 0; j < L; ++j) {
+  parallel_for(L, threads_, [&](int j) {
     const int k = live[j];
     Patch& p = cands[k].patch;
-    if (lv[j] != 0) { verdict[k] = 2; continue; }
+    if (lv[j] != 0) { verdict[k] = 2; return; }
     verdict[k] = 0;
     for (int c = 0; c < 4; ++c) { p.coord[c] = lc[4 * j + c]; p.normal[c] = ln[4 * j + c]; }
     p.ncc = lok[j] ? lncc[j] : p.ncc;
@@ -271,7 +254,7 @@ void Pipeline::evaluate_range(std::vector<Candidate>& all, std::vector<int>& all
     p.grids.clear();
     for (int i = 0; i < lni[j]; ++i) p.grids.push_back({lgr[((size_t)j * stride + i) * 2], lgr[((size_t)j * stride + i) * 2 + 1]});
     p.vimages.clear(); p.vgrids.clear();
-  }
+  }, 512);
   if (depth_ == 0) return;
   // setVImagesVGrids for the accepted candidates (optim.cpp:184-186) against the current depth maps
   std::vector<int> acc;
@@ -847,6 +830,16 @@ void Pipeline::filter_small_groups() {   // filter.cpp:524-665
   const std::vector<int> ids = collect_patches();
   const int P = (int)ids.size();
   if (P == 0) return;
+  // _vpgrids of the current table (addPatchV, filter.cpp:773-781): per image, patches in table order
+  parallel_for(tnum_, threads_, [&](int im) {
+    ImageGrid& g = grids_[im];
+    for (auto& cell : g.vpg) cell.clear();
+    for (int k = 0; k < P; ++k) {
+      const Patch& p = patches_[ids[k]];
+      for (size_t i = 0; i < p.vimages.size(); ++i)
+        if (p.vimages[i] == im) g.vpg[(size_t)p.vgrids[i][1] * g.gw + p.vgrids[i][0]].push_back(ids[k]);
+    }
+  }, 1);
   std::vector<int> index_of(patches_.size(), -1);
   for (int k = 0; k < P; ++k) index_of[ids[k]] = k;
   std::vector<int> label(P, -1);
