@@ -176,7 +176,7 @@ def pipeline_wall_time(scene, impl):
     'reference', all host threads) on the scene written to disk as PPM + txt + option file; returns a dict."""
     import subprocess
     cores = os.cpu_count() or 1
-    prefix = write_scene_for_reference(scene, cores)
+    prefix = write_scene_for_reference(scene, cores, tag="pipeline")   # its own directory: RefLib leaves feature-cache stubs in models/
     exe = os.path.join(ROOT, "cmvs-pmvs_b200", "bin", "pmvs2") if impl == "b200" else os.path.join(ROOT, "oracle", "_ref", "pmvs3_ref")
     if not os.path.exists(exe):
         return {"scene": scene.name, "unavailable": os.path.relpath(exe, ROOT) + " not built"}
@@ -190,7 +190,12 @@ def pipeline_wall_time(scene, impl):
             out["patches"] = sum(1 for _ in f)
     except OSError:
         out["patches"] = None
-    refined = [int(l.split()[-1]) for l in p.stderr.splitlines() if l.startswith("Total pass fail0 fail1 refinepatch:") and "." not in l.split()[-1]]
+    refined = []   # the count lines are all-integer; the reference also prints a percentage line (floats, nan when a round is empty)
+    for l in p.stderr.splitlines():
+        if l.startswith("Total pass fail0 fail1 refinepatch:"):
+            tok = l.split(":")[1].split()
+            if len(tok) == 5 and all(t.isdigit() for t in tok) and not (tok[0] == "100" and int(tok[1]) + int(tok[2]) + int(tok[3]) != 100):
+                refined.append(int(tok[4]))
     if refined:
         out["refined_patches"] = int(sum(refined))                      # the reference's own "refinepatch" counter
         out["refined_patches_per_sec_whole_run"] = out["refined_patches"] / secs
@@ -213,10 +218,10 @@ def measured_traffic(patches):
 # --------------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU code (oracle/_ref), bounded sample per step
 # --------------------------------------------------------------------------------------------------------
-def write_scene_for_reference(scene, cpu_threads):
+def write_scene_for_reference(scene, cpu_threads, tag="scene"):
     import __graft_entry__ as g
     synth = g.load_package().synth
-    prefix = "/tmp/pmvs_b200_bench_scene_%d/" % os.getpid()
+    prefix = "/tmp/pmvs_b200_bench_%s_%d/" % (tag, os.getpid())
     scene.option = dict(scene.option)
     scene.option["CPU"] = cpu_threads
     synth.write_scene(scene, prefix)
