@@ -36,6 +36,93 @@ constexpr int kGroup = 8;  // lanes per patch
 #define PMVS_FOLD_PIVOT 1
 #endif
 
+// PMVS_FAST_DIV: inside the optimiser loop (get_paxes_c, view_window_c, the per-view statistics) IEEE f32 division and
+// square root (13- and 10-instruction expansions, 12 % of the kernel's issue slots in the round-1 ncu source view:
+// profiles/r1_k_refine_g_lines_v3.txt) become MUFU.RCP * x and MUFU.SQRT / MUFU.RSQ (<= 2 ulp), and the dot products of
+// project() are FMA chains.  The objective moves by ~1e-6 (bar 1e-4).  An integer decision of the loop (angle gate, level
+// pick, grabSafe) can only flip where its operand lies within 2 ulp of the threshold; pre/postProcess, grabTex and every
+// kernel with integer outputs keep the exact helpers of pmvs_device.cuh.
+#ifndef PMVS_FAST_DIV
+#define PMVS_FAST_DIV 1
+#endif
+#if PMVS_FAST_DIV
+// .ftz forms: bare MUFU without the denormal pre/post-scaling (no operand here is ever subnormal: distances, depths,
+// texture variances >= 1/147 or exactly 0)
+__device__ __forceinline__ float grcp(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float gdiv(float a, float b) { return a * grcp(b); }
+__device__ __forceinline__ float gsqrt(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float grsqrt(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float gdot4(const float* u, const float* v) { return fmaf(u[3], v[3], fmaf(u[2], v[2], fmaf(u[1], v[1], u[0] * v[0]))); }
+__device__ __forceinline__ float gdot3(const float* u, const float* v) { return fmaf(u[2], v[2], fmaf(u[1], v[1], u[0] * v[0])); }
+#else
+__device__ __forceinline__ float gdiv(float a, float b) { return fdiv(a, b); }
+__device__ __forceinline__ float gsqrt(float a) { return fsqrt(a); }
+__device__ __forceinline__ float gdot4(const float* u, const float* v) { return dot4(u, v); }
+__device__ __forceinline__ float gdot3(const float* u, const float* v) { return dot3(u, v); }
+#endif
+// unitize / project / getUnit of pmvs_device.cuh on the g-helpers (same control flow)
+__device__ __forceinline__ void gunitize3(float* v) {
+  const float l = gdot3(v, v);
+  if (l != 1.0f && l != 0.0f) {
+#if PMVS_FAST_DIV
+    const float r = grsqrt(l);
+    v[0] *= r; v[1] *= r; v[2] *= r;
+#else
+    const float s = fsqrt(l);
+    v[0] = fdiv(v[0], s); v[1] = fdiv(v[1], s); v[2] = fdiv(v[2], s);
+#endif
+  }
+}
+__device__ __forceinline__ void gunitize4(float* v) {
+  const float l = gdot4(v, v);
+  if (l != 1.0f && l != 0.0f) {
+#if PMVS_FAST_DIV
+    const float r = grsqrt(l);
+    v[0] *= r; v[1] *= r; v[2] *= r; v[3] *= r;
+#else
+    const float s = fsqrt(l);
+    v[0] = fdiv(v[0], s); v[1] = fdiv(v[1], s); v[2] = fdiv(v[2], s); v[3] = fdiv(v[3], s);
+#endif
+  }
+}
+__device__ __forceinline__ void gproject(const CamDev& cam, const float* X, float* o) {
+#if PMVS_FAST_DIV
+  o[0] = gdot4(cam.P[0], X);
+  o[1] = gdot4(cam.P[1], X);
+  o[2] = gdot4(cam.P[2], X);
+  if (o[2] <= 0.0f) {
+    o[0] = -65535.0f; o[1] = -65535.0f; o[2] = -1.0f;
+    return;
+  }
+  const float r = grcp(o[2]);
+  const float lim = 2147483648.0f;
+  o[0] = smax(-lim, smin(lim, o[0] * r));
+  o[1] = smax(-lim, smin(lim, o[1] * r));
+  o[2] = 1.0f;
+#else
+  project(cam, X, o);
+#endif
+}
+__device__ __forceinline__ float gget_unit(const CamDev& cam, int level, const float* X) {
+#if PMVS_FAST_DIV
+  const float d[4] = {X[0] - cam.centre[0], X[1] - cam.centre[1], X[2] - cam.centre[2], X[3] - cam.centre[3]};
+  const float fz = gsqrt(gdot4(d, d));
+  if (cam.ipscale == 0.0f) return 1.0f;
+  return gdiv(fz * (float)(2 << level), cam.ipscale);
+#else
+  return get_unit(cam, level, X);
+#endif
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z) {   // .w is never read: reuse z
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %3};" :: "r"(a), "f"(x), "f"(y), "f"(z) : "memory");
+}
+
 __device__ __forceinline__ float group_sum(float v) {
   v += __shfl_xor_sync(kFull, v, 4);
   v += __shfl_xor_sync(kFull, v, 2);
@@ -54,9 +141,16 @@ __device__ __forceinline__ void get_color_fast(const uint32_t* __restrict__ pix,
                                                float pv0 = 0.0f, float pv1 = 0.0f, float pv2 = 0.0f) {
   const int lx = (int)x;
   const int ly = (int)y;
+#if PMVS_FMA_INTERP
+  // the four weights from ONE product: f11 = dx1 dy1, f10 = dx1 - f11, f01 = dy1 - f11, f00 = (1 - dx1) - f01
+  // (1 FMUL + 4 FADD instead of 2 FADD + 4 FMUL; each weight within 1 ulp of 1 of the reference's product)
+  const float dx1 = x - (float)lx, dy1 = y - (float)ly;
+  const float f11 = dx1 * dy1, f10 = dx1 - f11, f01 = dy1 - f11, f00 = (1.0f - dx1) - f01;
+#else
   const float dx1 = x - (float)lx, dx0 = 1.0f - dx1;
   const float dy1 = y - (float)ly, dy0 = 1.0f - dy1;
   const float f00 = dx0 * dy0, f01 = dx0 * dy1, f10 = dx1 * dy0, f11 = dx1 * dy1;
+#endif
   const uint32_t* p = pix + (ly * w + lx);  // < 2^31 texels per level
   const uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + w), d = __ldg(p + w + 1);
 #if PMVS_FMA_INTERP
@@ -84,29 +178,35 @@ __device__ __forceinline__ void get_color_fast(const uint32_t* __restrict__ pix,
 // projections run as a 2-trip loop around ONE inlined copy of project().
 __device__ __forceinline__ void get_paxes_c(const CamDev& cam, int level, const float* coord, const float* normal,
                                             float* px, float* py) {
-  const float pscale = get_unit(cam, level, coord);
+  const float pscale = gget_unit(cam, level, coord);
   const float n3[3] = {normal[0], normal[1], normal[2]};
   float y3[3], x3[3];
   cross3(n3, cam.xaxis, y3);
-  unitize3(y3);
+  gunitize3(y3);
   cross3(y3, n3, x3);
   px[0] = x3[0] * pscale; px[1] = x3[1] * pscale; px[2] = x3[2] * pscale; px[3] = 0.0f * pscale;
   py[0] = y3[0] * pscale; py[1] = y3[1] * pscale; py[2] = y3[2] * pscale; py[3] = 0.0f * pscale;
   float c0[3];
-  project(cam, coord, c0);
+  gproject(cam, coord, c0);
   float dis0 = 1.0f, dis1 = 1.0f;
 #pragma unroll 1
   for (int a = 0; a < 2; ++a) {
     float t[4], c1[3];
 #pragma unroll
     for (int k = 0; k < 4; ++k) t[k] = coord[k] + (a == 0 ? px[k] : py[k]);
-    project(cam, t, c1);
+    gproject(cam, t, c1);
     const float d[3] = {c1[0] - c0[0], c1[1] - c0[1], c1[2] - c0[2]};
-    const float dis = fsqrt(dot3(d, d));
+    const float dis = gsqrt(gdot3(d, d));
     if (a == 0) dis0 = dis; else dis1 = dis;
   }
 #pragma unroll
+#if PMVS_FAST_DIV
+  const float r0 = grcp(dis0), r1 = grcp(dis1);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { px[k] *= r0; py[k] *= r1; }
+#else
   for (int k = 0; k < 4; ++k) { px[k] = fdiv(px[k], dis0); py[k] = fdiv(py[k], dis1); }
+#endif
 }
 
 template <int WSIZE>
@@ -116,21 +216,21 @@ __device__ __forceinline__ ViewWin view_window_c(const SceneDev& s, const CamDev
   w.newlevel = -1;
   w.lx = w.ly = w.dxx = w.dxy = w.dyx = w.dyy = 0.0f;
   float ray[4] = {cam.centre[0] - coord[0], cam.centre[1] - coord[1], cam.centre[2] - coord[2], cam.centre[3] - coord[3]};
-  unitize4(ray);
-  const float weight = smax(0.0f, dot4(ray, pz));
+  gunitize4(ray);
+  const float weight = smax(0.0f, gdot4(ray, pz));
   if (weight < s.cos_angle1) return w;  // optim.cpp:823
 
   float center[3], dx[3] = {0, 0, 0}, dy[3] = {0, 0, 0};
-  project(cam, coord, center);
+  gproject(cam, coord, center);
   float nrm = 0.0f;
 #pragma unroll 1
   for (int a = 0; a < 2; ++a) {
     float t[4], q[3];
 #pragma unroll
     for (int k = 0; k < 4; ++k) t[k] = coord[k] + (a == 0 ? px[k] : py[k]);
-    project(cam, t, q);
+    gproject(cam, t, q);
     const float d[3] = {q[0] - center[0], q[1] - center[1], q[2] - center[2]};
-    const float len = fsqrt(dot3(d, d));
+    const float len = gsqrt(gdot3(d, d));
     if (a == 0) { dx[0] = d[0]; dx[1] = d[1]; nrm = len; }
     else { dy[0] = d[0]; dy[1] = d[1]; nrm = nrm + len; }   // norm(dx) + norm(dy), optim.cpp:831
   }
@@ -140,9 +240,9 @@ __device__ __forceinline__ ViewWin view_window_c(const SceneDev& s, const CamDev
   for (int k = 0; k < s.n_level_thr; ++k)
     if (ratio >= s.level_thr[k]) ++leveldif;
   const int newlevel = s.level + leveldif;
-  const float scale = (leveldif >= 0) ? (float)(1 << leveldif) : 1.0f / (float)(1 << (-leveldif));  // MyPow2
-  // scale is a power of two: multiplying by its (exact) reciprocal gives the bits of the reference's division
-  const float iscale = (leveldif >= 0) ? 1.0f / (float)(1 << leveldif) : (float)(1 << (-leveldif));
+  // MyPow2(leveldif) is a power of two: multiplying by its exact reciprocal 2^-leveldif (built from the exponent field)
+  // gives the bits of the reference's division
+  const float iscale = __int_as_float((127 - leveldif) << 23);
   center[0] *= iscale; center[1] *= iscale;
   dx[0] *= iscale; dx[1] *= iscale;
   dy[0] *= iscale; dy[1] *= iscale;
@@ -373,13 +473,16 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
     const bool is_ref = v == 0;
     if (is_ref) { ra0 = ra1 = ra2 = 0.0f; }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, q = 0.f, cr = 0.f;
+    uint32_t rt = (uint32_t)__cvta_generic_to_shared(reftex);
     PMVS_UNROLL_ROWS
     for (int row = 0; row < WSIZE; ++row) {
       float rgb[3];
 #if PMVS_FMA_INTERP && PMVS_FOLD_PIVOT
       sample_row<WSIZE>(pix, lw, s.f32_2p23, cs, bx, by, rgb, -ra0, -ra1, -ra2);   // rgb = sample - reference mean (ra = 0 for the reference view)
-      const float4 d = reftex[row * rstride];
-      if (is_ref) reftex[row * rstride] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+      // explicit 32-bit shared addressing: one live register, no generic-to-shared rematerialisation in the loop
+      const float4 d = lds128(rt);
+      if (is_ref) sts128(rt, rgb[0], rgb[1], rgb[2]);
+      rt += rstride * 16;
       const float b0 = rgb[0], b1 = rgb[1], b2 = rgb[2];
 #else
       sample_row<WSIZE>(pix, lw, s.f32_2p23, cs, bx, by, rgb);
@@ -395,7 +498,11 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
     s0 = group_sum(smp ? s0 : 0.0f); s1 = group_sum(smp ? s1 : 0.0f); s2 = group_sum(smp ? s2 : 0.0f);
     if (is_ref) {
       // normalize's two passes (optim.cpp:1036-1053): channel means, then deviations and their squares
+#if PMVS_FAST_DIV
+      ra0 = s0 * (1.0f / N); ra1 = s1 * (1.0f / N); ra2 = s2 * (1.0f / N);
+#else
       ra0 = fdiv(s0, N); ra1 = fdiv(s1, N); ra2 = fdiv(s2, N);
+#endif
       float qq = 0.f, d0s = 0.f, d1s = 0.f, d2s = 0.f;
 #pragma unroll 1
       for (int row = 0; row < WSIZE; ++row) {
@@ -412,18 +519,29 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
     q = group_sum(smp ? q : 0.0f); cr = group_sum(smp ? cr : 0.0f);
     if (on) {
       // sd = sqrt(sum dev^2 / 147), 0 -> 1 (optim.cpp:1055-1059); dot = sum(t_ref t_cur) / 147 (optim.cpp:1069-1077)
+#if PMVS_FAST_DIV
+      // d = cross / (147 sd_a sd_b) with sd = sqrt(sq / 147), 0 -> 1, i.e. cross * rsqrt(A B) with A = sq or 147
+      const float sq_cur = fmaxf(fmaf(-(1.0f / N), fmaf(s2, s2, fmaf(s1, s1, s0 * s0)), q), 0.0f);
+      const float cross = fmaf(-(1.0f / N), fmaf(s2, rd2, fmaf(s1, rd1, s0 * rd0)), cr);
+      const float A = sq_ref == 0.0f ? N3 : sq_ref, B = sq_cur == 0.0f ? N3 : sq_cur;
+      const float d = cross * grsqrt(A * B);
+      const float r1 = 1.0f - d;
+      const float rob = gdiv(r1, fmaf(3.0f, r1, 1.0f));
+#else
       const float sq_cur = fmaxf(q - (s0 * s0 + s1 * s1 + s2 * s2) / N, 0.0f);
       const float cross = cr - (s0 * rd0 + s1 * rd1 + s2 * rd2) / N;
       float sda = fsqrt(fdiv(sq_ref, N3)), sdb = fsqrt(fdiv(sq_cur, N3));
       if (sda == 0.0f) sda = 1.0f;
       if (sdb == 0.0f) sdb = 1.0f;
       const float d = fdiv(fdiv(cross, sda * sdb), N3);
+      const float rob = robustincc(1.0f - d);
+#endif
       if (mode == 0) {
-        acc += (double)robustincc(1.0f - d);
+        acc += (double)rob;
         ++denom;
       } else if (mode == 1) {
         totalweight += wv;
-        acc += (double)(robustincc(1.0f - d) * wv);
+        acc += (double)(rob * wv);
       } else {
         totalweight += wv;
         acc += (1.0 - (double)d) * (double)wv;
