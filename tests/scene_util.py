@@ -91,3 +91,16 @@ def write_variant(scene, name, prefix, cpu):
             nb = sorted({(i + d) % n for d in (-3, -2, -1, 1, 2, 3)})
             f.write("%d %d  %s\n" % (i, len(nb), " ".join(str(v) for v in nb)))
     return out
+
+
+SKE_TWO_CLUSTERS = "SKE\n16 2\n8 2\n0 1 2 3 4 5 6 7 \n8 15 \n8 2\n8 9 10 11 12 13 14 15 \n0 7 \n"
+
+
+def write_clusters(scene, prefix, cpu):
+    """small_scene() laid out like a CMVS output directory: images, cameras, vis.dat (+-3 ring neighbours) and a ske.dat
+    with two clusters (the halves of the ring as target images, two images of the other half as `oimages`), in the format
+    CMVS::CBundle::writeGroups writes (source/cmvs/bundle.cpp:1462-1481).  genOption turns it into option-0000/0001."""
+    out = write_variant(scene, "visdata", prefix, cpu)
+    with open(out + "ske.dat", "w") as f:
+        f.write(SKE_TWO_CLUSTERS)
+    return out

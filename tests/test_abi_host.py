@@ -96,3 +96,24 @@ def test_allgather_world2_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert "rank %d ok" % r in o
+
+
+def test_genoption_matches_reference(tmp_path):
+    """bin/genOption writes, byte for byte, the option-%04d files and pmvs.sh that the reference's genOption wrote for the
+    same ske.dat (tests/golden/pmvs_clusters.npz, made by oracle/_ref/genOption_ref = source/genOption.cpp)."""
+    import subprocess
+    from scene_util import SKE_TWO_CLUSTERS
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pmvs_clusters.npz"))
+    exe = os.path.join(ROOT, "cmvs-pmvs_b200", "bin", "genOption")
+    assert os.path.exists(exe), "genOption not built: run __graft_entry__.build()"
+    prefix = str(tmp_path) + "/"
+    open(prefix + "ske.dat", "w").write(SKE_TWO_CLUSTERS)
+    subprocess.run([exe, prefix] + [str(a) for a in G["args"]], check=True)
+    for name in ("option-0000", "option-0001", "pmvs.sh"):
+        assert open(prefix + name, "rb").read() == bytes(G["file_" + name]), name
+    # defaults (level 1 csize 2 threshold 0.7 wsize 7 minImageNum 3 CPU 8) and the usage / missing-file exits
+    subprocess.run([exe, prefix], check=True)
+    txt = open(prefix + "option-0001").read()
+    assert "threshold 0.7\n" in txt and "CPU 8\n" in txt and "timages 8 8 9 10 11 12 13 14 15 \n" in txt and "oimages 2 0 7 \n" in txt
+    assert subprocess.run([exe], stderr=subprocess.PIPE).returncode == 1
+    assert subprocess.run([exe, prefix + "nowhere/"], stderr=subprocess.PIPE).returncode == 1

@@ -144,3 +144,44 @@ def test_option_variants(name, scene, tmp_path):
     assert abs(len(pts) - want) <= tol * want, (len(pts), want)
     assert a < CLOUD_TOL * spacing and b < CLOUD_TOL * spacing, (a, b, spacing)
     assert far < 1.5 * spacing
+
+
+def test_clusters_one_per_gpu_and_merge(scene, tmp_path):
+    """a CMVS-shaped directory (ske.dat + vis.dat) -> bin/genOption -> bin/pmvs2_clusters, which runs every
+    option-%04d on its own GPU slot and concatenates the cluster models.  Bars per cluster = the whole-run bars against the
+    cloud the reference binary wrote for the same option file (tests/golden/pmvs_clusters.npz)."""
+    import torch
+    from scene_util import write_clusters
+    G = np.load(os.path.join(HERE, "golden", "pmvs_clusters.npz"))
+    assert scene.sha256() == bytes(G["scene_sha256"]).hex()
+    BIN = os.path.dirname(PMVS2)
+    prefix = write_clusters(scene, str(tmp_path / "cmvs"), cpu=os.cpu_count() or 4)
+    args = [str(a) for a in G["args"]]
+    args[5] = str(os.cpu_count() or 4)
+    subprocess.run([os.path.join(BIN, "genOption"), prefix] + args, check=True)
+    gpus = max(1, min(2, torch.cuda.device_count()))
+    p = subprocess.run([os.path.join(BIN, "pmvs2_clusters"), prefix, "--gpus", str(gpus), "PATCH", "PSET"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    total = 0
+    for c in range(2):
+        pts = np.loadtxt(prefix + "models/option-%04d.pset" % c, dtype=np.float32).reshape(-1, 6)
+        ref = G["cluster_%d_pset" % c]
+        total += len(pts)
+        R = torch.from_numpy(ref[:, :3]).cuda()
+        d = torch.cdist(R, R); d.fill_diagonal_(1e9)
+        spacing = float(d.min(dim=1).values.mean())
+        a, b = _nn(pts[:, :3], ref[:, :3]), _nn(ref[:, :3], pts[:, :3])
+        print("cluster %d: patches %d vs reference %d; cloud distance %.5f / %.5f, reference spacing %.5f" % (c, len(pts), len(ref), a, b, spacing))
+        assert abs(len(pts) - len(ref)) <= COUNT_TOL * len(ref), (c, len(pts), len(ref))
+        assert a < CLOUD_TOL * spacing and b < CLOUD_TOL * spacing, (c, a, b, spacing)
+    # the merge: counts add up, bodies are the cluster bodies in cluster order
+    merged = np.loadtxt(prefix + "models/option-all.pset", dtype=np.float32).reshape(-1, 6)
+    assert len(merged) == total
+    ply = open(prefix + "models/option-all.ply").read().split("\n")
+    assert ply[2] == "element vertex %d" % total and len(ply) - 1 - (ply.index("end_header") + 1) == total
+    tok = open(prefix + "models/option-all.patch").read().split()
+    assert tok[0] == "PATCHES" and int(tok[1]) == total and tok.count("PATCHS") == total
+    first = np.loadtxt(prefix + "models/option-0000.pset", dtype=np.float32).reshape(-1, 6)
+    assert np.array_equal(merged[: len(first)], first)
+    assert "cluster 1 ->" in p.stderr and "merged %d patches of 2 clusters" % total in p.stderr
