@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(128) k_refine(SceneDev s, int P, int stride, f
 
 
 // ---- second-generation kernels: 8 lanes per patch, 4 patches per warp (pmvs_group.cuh) ---------------
-template <int WSIZE>
+template <int WSIZE, bool TEX>
 __global__ void __launch_bounds__(128) k_score_g(SceneDev s, int P, int stride, const float* __restrict__ coords,
                                                  const float* __restrict__ normals, const int32_t* __restrict__ images,
                                                  const int32_t* __restrict__ nimages, const float* __restrict__ dscales,
@@ -315,11 +315,11 @@ __global__ void __launch_bounds__(128) k_score_g(SceneDev s, int P, int stride, 
   double f;
   if (mode == 0) {
     float c2[4], n2[4];
-    f = group_objective<WSIZE>(s, gc, x, gl, g, 0, c2, n2, reftex, 128);
+    f = group_objective<WSIZE, TEX>(s, gc, x, gl, g, 0, c2, n2, reftex, 128);
   } else {
     CamDev refcam;
     load_cam(s, gc.size > 0 ? gc.ref : 0, refcam);
-    f = group_photo_score<WSIZE>(s, gc, refcam, coord, normal, gl, g, mode, reftex, 128);
+    f = group_photo_score<WSIZE, TEX>(s, gc, refcam, coord, normal, gl, g, mode, reftex, 128);
   }
   if (p < P && gl == 0) out[p] = f;
 }
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(128) k_score_g(SceneDev s, int P, int stride, 
 // K3 (v2): COptim::refinePatch for a whole frontier.  Each 8-lane group pulls patches from a global counter
 // and runs its own Nelder-Mead (state in shared memory, advanced by the group leader); the four groups of a
 // warp evaluate their objectives in lock step.
-template <int WSIZE>
+template <int WSIZE, bool TEX>
 __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, int P, int stride, float* __restrict__ coords, float* __restrict__ normals,
                                                      const int32_t* __restrict__ images, const int32_t* __restrict__ nimages,
                                                      const float* __restrict__ dscales, float* __restrict__ ncc_out,
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
     const int mode = (have && nm.state == NM_FINAL) ? 1 : 0;
     const double xt[3] = {nm.xt[0], nm.xt[1], nm.xt[2]};
     float rc[4], rn[4];
-    const double fx = group_objective<WSIZE>(s, gc, xt, gl, g, mode, rc, rn, reftex, 128);
+    const double fx = group_objective<WSIZE, TEX>(s, gc, xt, gl, g, mode, rc, rn, reftex, 128);
     __syncwarp();
     if (have && gl == 0) nm_advance(nm, fx, s.xtol);
     __syncwarp();
@@ -533,6 +533,10 @@ struct pmvsb_ctx {
   std::vector<std::vector<int32_t>> visdata2;
   CamDev* d_cams = nullptr;
   LevelDev* d_levels = nullptr;
+  cudaArray_t atlas_array = nullptr;        // every (image, level) in one block-linear RGBA8 array (texture gather)
+  cudaTextureObject_t atlas_tex = 0;
+  int atlas_w = 0, atlas_h = 0;
+  bool atlas_enabled = true;                // PMVSB_NO_ATLAS=1 in the environment: global-load gathers (A/B measurements)
   int* d_counter = nullptr;
   int32_t* d_vis_off = nullptr;
   // filter-stage patch table
@@ -713,6 +717,7 @@ void fill_scene(pmvsb_ctx* c) {
   s.xtol = c->xtol; s.step = c->step; s.maxeval = c->maxeval;
   s.f32_2p23 = 0x4B000000u;
   s.dummy_pix = c->images.empty() || c->images[0].levels.empty() ? nullptr : c->images[0].levels[0];
+  s.atlas = (unsigned long long)c->atlas_tex;
 }
 
 // Scratch device buffers of the host-pointer entry points come from a per-context pool: cudaMalloc / cudaFree cost
@@ -760,12 +765,16 @@ int check_ready(pmvsb_ctx* ctx) {
 }
 
 // group kernels (8 lanes per patch) cover wsize <= 8; wsize 9 falls back to the warp-per-patch kernels
+// (the group kernels gather through the texture atlas when the scene has one, else through global loads)
 #define DISPATCH_GROUP(ctx, KG, KW, gridg, gridw, block, ...)                                   \
   do {                                                                                          \
+    const bool tex_ = (ctx)->scene.atlas != 0;                                                  \
     switch ((ctx)->wsize) {                                                                     \
-      case 5: KG<5><<<gridg, block, 0, (ctx)->stream>>>(__VA_ARGS__); break;                    \
+      case 5: if (tex_) KG<5, true><<<gridg, block, 0, (ctx)->stream>>>(__VA_ARGS__);           \
+              else KG<5, false><<<gridg, block, 0, (ctx)->stream>>>(__VA_ARGS__); break;        \
       case 9: KW<9><<<gridw, block, 0, (ctx)->stream>>>(__VA_ARGS__); break;                    \
-      default: KG<7><<<gridg, block, 0, (ctx)->stream>>>(__VA_ARGS__); break;                   \
+      default: if (tex_) KG<7, true><<<gridg, block, 0, (ctx)->stream>>>(__VA_ARGS__);          \
+               else KG<7, false><<<gridg, block, 0, (ctx)->stream>>>(__VA_ARGS__); break;       \
     }                                                                                           \
     ++(ctx)->launches;                                                                          \
   } while (0)
@@ -940,6 +949,7 @@ int pmvsb_create(pmvsb_ctx** out, int device, int num_images, int num_target, in
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return PMVSB_ECUDA;
   pmvsb_ctx* ctx = new pmvsb_ctx();
+  if (const char* v = std::getenv("PMVSB_NO_ATLAS")) ctx->atlas_enabled = !(v[0] && v[0] != '0');
   ctx->device = device;
   ctx->num = num_images; ctx->tnum = num_target; ctx->level = level; ctx->csize = csize; ctx->wsize = wsize;
   ctx->min_image_num = min_image_num;
@@ -971,6 +981,8 @@ int pmvsb_create(pmvsb_ctx** out, int device, int num_images, int num_target, in
   return PMVSB_OK;
 }
 
+static void atlas_free(pmvsb_ctx* ctx);
+
 int pmvsb_destroy(pmvsb_ctx* ctx) {
   if (!ctx) return PMVSB_EINVAL;
   cudaSetDevice(ctx->device);
@@ -978,6 +990,7 @@ int pmvsb_destroy(pmvsb_ctx* ctx) {
   for (auto& im : ctx->images)
     for (auto* p : im.levels) cudaFree(p);
   cudaFree(ctx->d_cams); cudaFree(ctx->d_levels); cudaFree(ctx->d_counter); cudaFree(ctx->d_vis_off); cudaFree(ctx->d_vis_idx);
+  atlas_free(ctx);
   cudaFree(ctx->arena);
   store_free(ctx);
   if (ctx->comm && nccl_api()) nccl_api()->CommDestroy(ctx->comm);
@@ -1047,6 +1060,71 @@ int pmvsb_set_visdata2(pmvsb_ctx* ctx, int index, const int32_t* list, int n) {
   return PMVSB_OK;
 }
 
+// One block-linear RGBA8 CUDA array holding every (image, pyramid level), read by the group kernels with tex2Dgather.
+// A warp's four groups sample different images and levels in one instruction and the texture handle of TLD4 must be
+// warp-uniform, hence ONE texture for the whole scene (per-level handles would make the compiler serialise the gather
+// per distinct handle).  Shelf packing: level l occupies a block of rows, its images laid out left to right, top to
+// bottom in cells of that level's largest width x height.  Limits: cudaDeviceProp::maxTexture2DGather (32768 x 32768 on
+// B200); a scene that does not fit keeps atlas_tex = 0 and the kernels gather through global loads.
+static void atlas_free(pmvsb_ctx* ctx) {
+  if (ctx->atlas_tex) cudaDestroyTextureObject(ctx->atlas_tex);
+  if (ctx->atlas_array) cudaFreeArray(ctx->atlas_array);
+  ctx->atlas_tex = 0; ctx->atlas_array = nullptr; ctx->atlas_w = ctx->atlas_h = 0;
+}
+
+static int atlas_build(pmvsb_ctx* ctx, std::vector<LevelDev>& hl) {
+  for (LevelDev& d : hl) { d.ax1 = 1.0f; d.ay1 = 1.0f; d.pad0 = d.pad1 = 0; }
+  if (!ctx->atlas_enabled || ctx->num < 1) { atlas_free(ctx); return PMVSB_OK; }
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ctx->device));
+  const int max_w = prop.maxTexture2DGather[0], max_h = prop.maxTexture2DGather[1];
+  std::vector<int> cw(ctx->nlevels, 0), ch(ctx->nlevels, 0);   // cell size per level
+  for (int i = 0; i < ctx->num; ++i)
+    for (int l = 0; l < ctx->nlevels; ++l) { cw[l] = std::max(cw[l], ctx->images[i].w[l]); ch[l] = std::max(ch[l], ctx->images[i].h[l]); }
+  if (cw[0] < 1 || ch[0] < 1 || cw[0] > max_w) { atlas_free(ctx); return PMVSB_OK; }
+  // roughly square: columns of level 0 chosen so that width ~ height of the level-0 block
+  int cols0 = (int)std::ceil(std::sqrt((double)ctx->num * ch[0] / cw[0]));
+  cols0 = std::max(1, std::min(cols0, max_w / cw[0]));
+  const int W = cols0 * cw[0];
+  std::vector<int> cols(ctx->nlevels, 1), row0(ctx->nlevels, 0);
+  long long H = 0;
+  for (int l = 0; l < ctx->nlevels; ++l) {
+    if (cw[l] < 1 || ch[l] < 1) continue;
+    cols[l] = std::max(1, W / cw[l]);
+    row0[l] = (int)H;
+    H += (long long)((ctx->num + cols[l] - 1) / cols[l]) * ch[l];
+  }
+  if (H > max_h) { atlas_free(ctx); return PMVSB_OK; }
+  if (!ctx->atlas_array || ctx->atlas_w != W || ctx->atlas_h != (int)H) {
+    atlas_free(ctx);
+    const cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+    if (cudaMallocArray(&ctx->atlas_array, &cd, (size_t)W, (size_t)H, cudaArrayTextureGather) != cudaSuccess) {
+      cudaGetLastError();   // no memory for the second copy: stay on the global-load path
+      ctx->atlas_array = nullptr;
+      return PMVSB_OK;
+    }
+    ctx->atlas_w = W; ctx->atlas_h = (int)H;
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeArray; rd.res.array.array = ctx->atlas_array;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 0;
+    CK(cudaCreateTextureObject(&ctx->atlas_tex, &rd, &td, nullptr));
+  }
+  for (int i = 0; i < ctx->num; ++i)
+    for (int l = 0; l < ctx->nlevels; ++l) {
+      const int w = ctx->images[i].w[l], h = ctx->images[i].h[l];
+      if (w < 1 || h < 1) continue;
+      const int ox = (i % cols[l]) * cw[l], oy = row0[l] + (i / cols[l]) * ch[l];
+      CK(cudaMemcpy2DToArrayAsync(ctx->atlas_array, (size_t)ox * sizeof(uchar4), (size_t)oy, ctx->images[i].levels[l], (size_t)w * sizeof(uchar4),
+                                  (size_t)w * sizeof(uchar4), (size_t)h, cudaMemcpyDeviceToDevice, ctx->stream));
+      LevelDev& d = hl[(size_t)i * ctx->nlevels + l];
+      d.ax1 = (float)(ox + 1); d.ay1 = (float)(oy + 1);   // integers < 2^15 + texel index < 2^15: exact in f32
+    }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
 int pmvsb_finalize_scene(pmvsb_ctx* ctx) {
   if (!ctx) return PMVSB_EINVAL;
   for (int i = 0; i < ctx->num; ++i) {
@@ -1072,6 +1150,10 @@ int pmvsb_finalize_scene(pmvsb_ctx* ctx) {
       LevelDev& d = hl[(size_t)i * ctx->nlevels + l];
       d.pix = ctx->images[i].levels[l]; d.w = ctx->images[i].w[l]; d.h = ctx->images[i].h[l];
     }
+  }
+  {
+    const int r = atlas_build(ctx, hl);
+    if (r) return r;
   }
   cudaFree(ctx->d_cams); cudaFree(ctx->d_levels);
   ctx->d_cams = nullptr; ctx->d_levels = nullptr;
@@ -1832,9 +1914,9 @@ int pmvsb_refine_batch_dev(pmvsb_ctx* ctx, int P, int stride, float* d_coords, f
   if (ctx->refine_blocks_per_sm == 0) {
     int nb = 0;
     switch (ctx->wsize) {
-      case 5: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_refine_g<5>, 128, 0)); break;
+      case 5: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_refine_g<5, true>, 128, 0)); break;
       case 9: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_refine<9>, 128, 0)); break;
-      default: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_refine_g<7>, 128, 0)); break;
+      default: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_refine_g<7, true>, 128, 0)); break;
     }
     ctx->refine_blocks_per_sm = nb > 0 ? nb : 1;
   }

@@ -31,9 +31,12 @@ struct __align__(16) CamDev {  // one per image (Image::CCamera + COptim axes), 
   float pad[2];
 };
 
-struct LevelDev {          // one per (image, pyramid level)
+struct LevelDev {          // one per (image, pyramid level); 32 B
   const uchar4* pix;       // RGBA8, row-major, pitch = w pixels; alpha unused
   int w, h;
+  float ax1, ay1;          // this level's origin inside the gather atlas, plus one: texel (x, y)'s 2x2 footprint is centred at
+                           // (x + ax1, y + ay1) in atlas coordinates (SceneDev::atlas)
+  int pad0, pad1;
 };
 
 struct SceneDev {
@@ -48,6 +51,8 @@ struct SceneDev {
   int maxeval;
   uint32_t f32_2p23;       // 0x4B000000, passed as data so PRMT keeps its immediate slot for the byte selector
   const uchar4* dummy_pix; // any valid level (image 0, level 0): idle lanes sample texel (0,0) of it instead of branching
+  unsigned long long atlas; // cudaTextureObject_t over ONE block-linear RGBA8 array holding every (image, level): point filter,
+                            // normalized-float reads, unnormalized coordinates, gather enabled; 0 = not built (does not fit)
 };
 
 // IEEE f32 division / square root.  With PMVS_NOINLINE_DIV the ~13-instruction expansions (60 of them in the

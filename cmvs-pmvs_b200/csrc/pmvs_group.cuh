@@ -173,6 +173,28 @@ __device__ __forceinline__ void get_color_fast(const uint32_t* __restrict__ pix,
   rgb[2] = (byte_to_float(a, magic, 0x7542) * f00 + byte_to_float(c, magic, 0x7542) * f01) + (byte_to_float(b, magic, 0x7542) * f10 + byte_to_float(d, magic, 0x7542) * f11);
 }
 
+// The same bilinear sample through the texture unit: ONE tex2Dgather per channel returns the 2x2 footprint already as
+// floats (byte / 255, exact; NCC is scale-invariant), so the 4 LDG + 12 PRMT + 12 FADD of get_color_fast become 3 TLD4 and
+// the gathers leave the LSU data path.  The footprint is named by its integer centre (lxf + 1 + origin: exact in f32, no
+// dependence on the sampler's fixed-point rounding), the weights come from the level-local coordinates as before.
+// Component order on sm_100a (tools/probe/tex_gather_probe.cu): w = (x0,y0), z = (x1,y0), x = (x0,y1), y = (x1,y1).
+__device__ __forceinline__ void get_color_gather(unsigned long long atlas, float ax1, float ay1, float x, float y, float* rgb,
+                                                 float pv0, float pv1, float pv2) {
+  const float lxf = truncf(x), lyf = truncf(y);   // x, y >= 3 (grabSafe): trunc == floor
+  const float dx1 = x - lxf, dy1 = y - lyf;
+  const float f11 = dx1 * dy1, f10 = dx1 - f11, f01 = dy1 - f11, f00 = (1.0f - dx1) - f01;
+  const float gx = lxf + ax1, gy = lyf + ay1;
+  const float pv[3] = {pv0, pv1, pv2};
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float4 t = tex2Dgather<float4>((cudaTextureObject_t)atlas, gx, gy, ch);
+    float v = fmaf(t.y, f11, pv[ch]);
+    v = fmaf(t.z, f10, v);
+    v = fmaf(t.x, f01, v);
+    rgb[ch] = fmaf(t.w, f00, v);
+  }
+}
+
 // ---- compact (code-size conscious) variants: the refine loop must stay inside the instruction cache ----
 // Same operations in the same order as get_paxes() / view_window() of pmvs_device.cuh; the two axis
 // projections run as a 2-trip loop around ONE inlined copy of project().
@@ -298,6 +320,12 @@ __device__ __forceinline__ void sample_row(const uint32_t* __restrict__ pix, int
 #endif
   get_color_fast(pix, w, magic, x, y, rgb, pv0, pv1, pv2);
 }
+template <int WSIZE>
+__device__ __forceinline__ void sample_row_tex(unsigned long long atlas, float ax1, float ay1, const ColSteps<WSIZE>& cs, float bx, float by,
+                                               float* rgb, float pv0, float pv1, float pv2) {
+  const float x = fmaf(cs.sx[0], cs.sy[0], bx), y = fmaf(cs.sx[1], cs.sy[0], by);
+  get_color_gather(atlas, ax1, ay1, x, y, rgb, pv0, pv1, pv2);
+}
 
 // per-group patch context; every lane of the group holds the same values except my_image / my_weight
 struct GroupCtx {
@@ -417,7 +445,7 @@ __device__ __forceinline__ void group_decode(const SceneDev& s, const GroupCtx& 
 //                    same surface, so b' = b - mean_ref is almost centred and the raw-moment variance
 //                    sum b'^2 - (sum b')^2/N does not cancel), and sum d_ref * b' is the covariance.
 // `reftex` points at this thread's column of a [WSIZE][blockDim.x] float4 array in shared memory.
-template <int WSIZE>
+template <int WSIZE, bool TEX = false>
 __device__ __forceinline__ double group_photo_score(const SceneDev& s, const GroupCtx& gc, const CamDev& refcam, const float* coord,
                                                     const float* normal, int gl, int g, int mode, float4* reftex, int rstride) {
   const bool live = gc.size > 0;
@@ -456,18 +484,27 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
     const int index = __shfl_sync(kFull, gc.my_image, v, kGroup);
     const float wv = __shfl_sync(kFull, gc.my_weight, v, kGroup);
     const bool smp = on && col;
-    // lanes that do not sample (8th lane, rejected view, idle group) read texel (0,0) of a dummy level
+    // groups whose view is off (rejected view, idle group) read texel (0,0) of a dummy level.  The 8th lane of a live
+    // group re-samples column WSIZE-1 (same addresses as its neighbour: no extra L1 wavefront, ncu: the dummy texel cost
+    // one of 5.7 tag requests per gather) and is masked out of the sums by `smp`.
     const uint32_t* pix = reinterpret_cast<const uint32_t*>(s.dummy_pix);
     int lw = 0;
     float bx = 0.0f, by = 0.0f;
     ColSteps<WSIZE> cs;
     ViewWin wz = w;
-    if (!smp) { wz.dxx = wz.dxy = wz.dyx = wz.dyy = 0.0f; }
+    float ax1 = 1.0f, ay1 = 1.0f;   // TEX: off groups gather the footprint at the atlas origin
+    if (!on) { wz.dxx = wz.dxy = wz.dyx = wz.dyy = 0.0f; }
     if (on) {
-      const LevelDev lv = s.levels[index * s.nlevels + w.newlevel];
-      if (col) { pix = reinterpret_cast<const uint32_t*>(lv.pix); lw = lv.w; bx = w.lx; by = w.ly; }
+      if (TEX) {
+        const float2 o = *reinterpret_cast<const float2*>(&s.levels[index * s.nlevels + w.newlevel].ax1);
+        ax1 = o.x; ay1 = o.y;
+      } else {
+        const LevelDev lv = s.levels[index * s.nlevels + w.newlevel];
+        pix = reinterpret_cast<const uint32_t*>(lv.pix); lw = lv.w;
+      }
+      bx = w.lx; by = w.ly;
     }
-    cs.set(wz, gl);
+    cs.set(wz, gl < WSIZE ? gl : WSIZE - 1);
     // ONE sampling loop for every view (a second copy of the loop body costs instruction-cache misses):
     // the reference view (v == 0) runs it with ra = 0, i.e. b = raw sample, and additionally stores the row.
     const bool is_ref = v == 0;
@@ -478,7 +515,9 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
     for (int row = 0; row < WSIZE; ++row) {
       float rgb[3];
 #if PMVS_FMA_INTERP && PMVS_FOLD_PIVOT
-      sample_row<WSIZE>(pix, lw, s.f32_2p23, cs, bx, by, rgb, -ra0, -ra1, -ra2);   // rgb = sample - reference mean (ra = 0 for the reference view)
+      // rgb = sample - reference mean (ra = 0 for the reference view)
+      if (TEX) sample_row_tex<WSIZE>(s.atlas, ax1, ay1, cs, bx, by, rgb, -ra0, -ra1, -ra2);
+      else sample_row<WSIZE>(pix, lw, s.f32_2p23, cs, bx, by, rgb, -ra0, -ra1, -ra2);
       // explicit 32-bit shared addressing: one live register, no generic-to-shared rematerialisation in the loop
       const float4 d = lds128(rt);
       if (is_ref) sts128(rt, rgb[0], rgb[1], rgb[2]);
@@ -560,13 +599,13 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
 }
 
 // my_f(x) / computeINCC at decode(x); coord/normal receive the decoded patch.
-template <int WSIZE>
+template <int WSIZE, bool TEX = false>
 __device__ __forceinline__ double group_objective(const SceneDev& s, const GroupCtx& gc, const double* x, int gl, int g, int mode,
                                                   float* coord, float* normal, float4* reftex, int rstride) {
   CamDev refcam;
   load_cam(s, gc.size > 0 ? gc.ref : 0, refcam);  // 128 B, L1-resident; not kept in registers across the loop
   group_decode(s, gc, refcam.xaxis, refcam.yaxis, refcam.zaxis, x, gl, coord, normal);
-  return group_photo_score<WSIZE>(s, gc, refcam, coord, normal, gl, g, mode, reftex, rstride);
+  return group_photo_score<WSIZE, TEX>(s, gc, refcam, coord, normal, gl, g, mode, reftex, rstride);
 }
 
 // The Nelder-Mead state of one group, kept in SHARED memory (216 B per patch) and advanced by the group's
