@@ -267,7 +267,7 @@ def main():
                           "%d views %dx%d, level 1 csize 2 wsize 7 minImageNum 3; %d seed patches x %d views per GPU per step, "
                           "refinePatch + computeINCC" % (args.views, args.width, args.height, args.patches, VIEWS),
               "patches_per_gpu": args.patches, "views_per_patch": VIEWS, "optimizer": "in-kernel Nelder-Mead, xtol 1e-4, maxeval 1000",
-              "l2": "inputs larger than L2 (RGBA pyramids of 48 views = 0.49 GB + patch arrays); no explicit flush",
+              "l2": "inputs larger than L2 (RGBA pyramids of 48 views = 0.49 GB, read through a texture atlas of the same size, + patch arrays); no explicit flush",
               "parallelism": "patches sharded over %d GPU(s), images replicated, NCCL all-gather of refined records per step" % world}
 
     if args.impl == "reference":
@@ -408,11 +408,12 @@ def main():
     alg_bytes = BYTES_PER_VIEW_EVAL * VIEWS * (evals_sum + P)          # 588 * V * (E + 1) summed over the launch
     k_ms = float(np.mean(kernel_ms))
     achieved = alg_bytes / (k_ms / 1000.0) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_refine<7>", "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth",
+    roofline = {"bound": "hbm", "kernel": "k_refine_g<7, atlas>", "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth",
                 "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(P), "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "evals_per_patch": evals_sum / P,
                 "note": "algorithmic bytes = 588 B x views x (evaluations + 1) per patch (SURVEY.md 8d); most gathers hit L1/L2, "
-                        "so HBM traffic is far below this figure and the kernel is FP32/issue bound"}
+                        "so HBM traffic is far below this figure; the kernel is bound by instruction issue (71 %) and TLD4 latency/throughput "
+                        "(texture data pipe 68 %), profiles/r1_k_refine_g_atlas_full_ncu_metrics.csv"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -195,6 +195,27 @@ __device__ __forceinline__ void get_color_gather(unsigned long long atlas, float
   }
 }
 
+// Split form for software pipelining: issue the three gathers of a sample now, interpolate later (the kernel is bound by
+// TLD4 latency at 8 warps per scheduler, so the next row's gathers are put in flight before this row is consumed).
+struct Foot { float4 r, g, b; float dx1, dy1; };
+__device__ __forceinline__ void gather_issue(unsigned long long atlas, float ax1, float ay1, float x, float y, Foot& f) {
+  const float lxf = truncf(x), lyf = truncf(y);
+  f.dx1 = x - lxf; f.dy1 = y - lyf;
+  const float gx = lxf + ax1, gy = lyf + ay1;
+  f.r = tex2Dgather<float4>((cudaTextureObject_t)atlas, gx, gy, 0);
+  f.g = tex2Dgather<float4>((cudaTextureObject_t)atlas, gx, gy, 1);
+  f.b = tex2Dgather<float4>((cudaTextureObject_t)atlas, gx, gy, 2);
+}
+__device__ __forceinline__ void gather_finish(const Foot& f, float* rgb, float pv0, float pv1, float pv2) {
+  const float f11 = f.dx1 * f.dy1, f10 = f.dx1 - f11, f01 = f.dy1 - f11, f00 = (1.0f - f.dx1) - f01;
+  rgb[0] = fmaf(f.r.w, f00, fmaf(f.r.x, f01, fmaf(f.r.z, f10, fmaf(f.r.y, f11, pv0))));
+  rgb[1] = fmaf(f.g.w, f00, fmaf(f.g.x, f01, fmaf(f.g.z, f10, fmaf(f.g.y, f11, pv1))));
+  rgb[2] = fmaf(f.b.w, f00, fmaf(f.b.x, f01, fmaf(f.b.z, f10, fmaf(f.b.y, f11, pv2))));
+}
+#ifndef PMVS_TEX_PIPELINE
+#define PMVS_TEX_PIPELINE 1
+#endif
+
 // ---- compact (code-size conscious) variants: the refine loop must stay inside the instruction cache ----
 // Same operations in the same order as get_paxes() / view_window() of pmvs_device.cuh; the two axis
 // projections run as a 2-trip loop around ONE inlined copy of project().
@@ -511,6 +532,35 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
     if (is_ref) { ra0 = ra1 = ra2 = 0.0f; }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, q = 0.f, cr = 0.f;
     uint32_t rt = (uint32_t)__cvta_generic_to_shared(reftex);
+#if PMVS_TEX_PIPELINE && PMVS_FMA_INTERP && PMVS_FOLD_PIVOT && PMVS_FAST_POS
+    if (TEX) {
+      static_assert(WSIZE % 2 == 1, "the pipelined loop consumes rows in pairs plus one");
+      const float ox = cs.sx[0] * cs.sy[0], oy = cs.sx[1] * cs.sy[0];   // this lane's column offset along the row
+      float px = bx + ox, py = by + oy;
+      auto consume = [&](const Foot& f) {
+        float rgb[3];
+        gather_finish(f, rgb, -ra0, -ra1, -ra2);
+        const float4 d = lds128(rt);
+        if (is_ref) sts128(rt, rgb[0], rgb[1], rgb[2]);
+        rt += rstride * 16;
+        s0 += rgb[0]; s1 += rgb[1]; s2 += rgb[2];
+        q = fmaf(rgb[0], rgb[0], q); q = fmaf(rgb[1], rgb[1], q); q = fmaf(rgb[2], rgb[2], q);
+        cr = fmaf(d.x, rgb[0], cr); cr = fmaf(d.y, rgb[1], cr); cr = fmaf(d.z, rgb[2], cr);
+      };
+      Foot A, B;
+      gather_issue(s.atlas, ax1, ay1, px, py, A);
+#pragma unroll 1
+      for (int row = 0; row < WSIZE - 1; row += 2) {
+        px += wz.dyx; py += wz.dyy;
+        gather_issue(s.atlas, ax1, ay1, px, py, B);
+        consume(A);
+        px += wz.dyx; py += wz.dyy;
+        gather_issue(s.atlas, ax1, ay1, px, py, A);
+        consume(B);
+      }
+      consume(A);
+    } else
+#endif
     PMVS_UNROLL_ROWS
     for (int row = 0; row < WSIZE; ++row) {
       float rgb[3];
