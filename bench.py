@@ -300,7 +300,7 @@ def main():
                 "gpu_launches": 0}
         if not args.no_pipeline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "pmvs3_ref")):
             line["pipeline"] = pipeline_wall_time(scene, "reference")
-        print(json.dumps(line))
+        print_line(json.dumps(line))
         return
 
     import torch
@@ -431,10 +431,35 @@ def main():
     if rank == 0 and world == 1 and not args.no_pipeline:
         line["pipeline"] = pipeline_wall_time(scene, "b200")
     if rank == 0:
-        print(json.dumps(line))
+        print_line(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+class _StdoutToStderr:
+    """stdout carries exactly ONE JSON line: anything native libraries print on fd 1 meanwhile (NCCL's version banner when
+    NCCL_DEBUG is set) goes to stderr; print_line() writes the JSON line to the real stdout."""
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        global print_line
+
+        def print_line(text, _fd=self.real):
+            os.write(_fd, (text + "\n").encode())
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
+
+
+def print_line(text):
+    print(text, flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    with _StdoutToStderr():
+        main()
