@@ -471,17 +471,20 @@ __global__ void __launch_bounds__(32) k_post_process(SceneDev s, SelectParams sp
 
 
 // COptim::setRefImage + setGrids for a batch (filterExact's tail, filter.cpp:277-280)
-template <int WSIZE>
+// One launch per view-capacity class (MAXV = 16 / 32 / 64): a block serves its patch only if the list length falls in
+// (LO, MAXV]; the small classes hold 4x / 2x more resident warps per SM (the scratch is the occupancy limit).
+template <int WSIZE, int MAXV, int LO>
 __global__ void __launch_bounds__(32) k_set_ref_image(SceneDev s, SelectParams sp, int P, int stride, const float* __restrict__ coords,
                                                       const float* __restrict__ normals, int32_t* __restrict__ images,
                                                       int32_t* __restrict__ nimages, int32_t* __restrict__ grids) {
-  __shared__ SelScratch<WSIZE> sc;
+  __shared__ SelScratch<WSIZE, MAXV> sc;
   const int p = blockIdx.x, lane = threadIdx.x;
   if (p >= P) return;
-  float coord[4], normal[4];
-  load_patch(coords, normals, p, coord, normal);
   const int cap = min(stride, kSelMaxViews);
   int n = min(nimages[p], cap);
+  if (n > MAXV || (n <= LO && !(LO == 0 && n <= 0))) return;   // another class's patch (n <= 0 is handled by the first class)
+  float coord[4], normal[4];
+  load_patch(coords, normals, p, coord, normal);
   for (int i = lane; i < n; i += 32) sc.images[i] = images[(size_t)p * stride + i];
   __syncwarp();
   if (n > 0) n = sel_set_ref_image<WSIZE>(s, sc, n, lane, coord, normal);
@@ -1819,9 +1822,18 @@ int pmvsb_set_ref_image_batch(pmvsb_ctx* ctx, int P, int stride, const float* co
   DevBuf<int32_t> dg;
   CK(dg.alloc((size_t)2 * stride * P));
   CK(cudaMemsetAsync(dg.p, 0xff, sizeof(int32_t) * (size_t)2 * stride * P, ctx->stream));
-  if (ctx->wsize == 5) k_set_ref_image<5><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, dg.p);
-  else k_set_ref_image<7><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, dg.p);
-  ++ctx->launches;
+#define LAUNCH_SET_REF(W, MAXV, LO) \
+  k_set_ref_image<W, MAXV, LO><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, dg.p); ++ctx->launches
+  if (ctx->wsize == 5) {
+    LAUNCH_SET_REF(5, 16, 0);
+    if (stride > 16) { LAUNCH_SET_REF(5, 32, 16); }
+    if (stride > 32) { LAUNCH_SET_REF(5, 64, 32); }
+  } else {
+    LAUNCH_SET_REF(7, 16, 0);
+    if (stride > 16) { LAUNCH_SET_REF(7, 32, 16); }
+    if (stride > 32) { LAUNCH_SET_REF(7, 64, 32); }
+  }
+#undef LAUNCH_SET_REF
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(images, st.images.p, sizeof(int32_t) * (size_t)stride * P, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(nimages, st.nimages.p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));

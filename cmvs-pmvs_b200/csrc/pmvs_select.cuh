@@ -26,23 +26,25 @@ struct SelectParams {          // host-tabulated constants (same libm as the ref
 };
 
 // per-warp scratch in shared memory
-template <int WSIZE>
+// MAXV = view capacity: 37.6 KB at 64 views (6 resident warps per SM), 9.7 KB at 16 (23 warps); kernels whose list length is
+// known up front (setRefImage) are launched once per capacity class
+template <int WSIZE, int MAXV = kSelMaxViews>
 struct SelScratch {
   static constexpr int TS = 3 * WSIZE * WSIZE;
-  float tex[TS][kSelMaxViews];      // column v = texture of view v (bank-conflict free per lane, broadcast for v fixed)
-  int images[kSelMaxViews];
-  int tmp_images[kSelMaxViews];
-  int aux[kSelMaxViews];            // the full image list while `images` holds the target subset (setRefImage)
-  float val[kSelMaxViews];          // inccs / units
-  float rays[kSelMaxViews][4];
-  unsigned char valid[kSelMaxViews];
+  float tex[TS][MAXV];      // column v = texture of view v (bank-conflict free per lane, broadcast for v fixed)
+  int images[MAXV];
+  int tmp_images[MAXV];
+  int aux[MAXV];            // the full image list while `images` holds the target subset (setRefImage)
+  float val[MAXV];          // inccs / units
+  float rays[MAXV][4];
+  unsigned char valid[MAXV];
 };
 
 // grabTex (optim.cpp:815-863) by ONE lane, sequential, into column `slot`; then normalize (optim.cpp:1031-1067).
-template <int WSIZE>
-__device__ __forceinline__ bool lane_grab_normalize(const SceneDev& s, SelScratch<WSIZE>& sc, int slot, int index, const float* coord,
+template <int WSIZE, int MAXV>
+__device__ __forceinline__ bool lane_grab_normalize(const SceneDev& s, SelScratch<WSIZE, MAXV>& sc, int slot, int index, const float* coord,
                                                     const float* px, const float* py, const float* pz) {
-  constexpr int TS = SelScratch<WSIZE>::TS;
+  constexpr int TS = SelScratch<WSIZE, MAXV>::TS;
   CamDev cam;
   load_cam(s, index, cam);
   const ViewWin w = view_window<WSIZE>(s, cam, index, coord, px, py, pz);
@@ -81,9 +83,9 @@ __device__ __forceinline__ bool lane_grab_normalize(const SceneDev& s, SelScratc
 }
 
 // COptim::dot (optim.cpp:1069-1077), sequential
-template <int WSIZE>
-__device__ __forceinline__ float lane_dot(const SelScratch<WSIZE>& sc, int a, int b) {
-  constexpr int TS = SelScratch<WSIZE>::TS;
+template <int WSIZE, int MAXV>
+__device__ __forceinline__ float lane_dot(const SelScratch<WSIZE, MAXV>& sc, int a, int b) {
+  constexpr int TS = SelScratch<WSIZE, MAXV>::TS;
   float ans = 0.0f;
   for (int i = 0; i < TS; ++i) ans += sc.tex[i][a] * sc.tex[i][b];
   return ans / (float)TS;
@@ -148,8 +150,8 @@ __device__ __forceinline__ int sel_add_images(const SceneDev& s, const SelectPar
 }
 
 // textures + validity of views [0, n) with axes from images[0] (what both setINCCs forms do first, optim.cpp:709-722)
-template <int WSIZE>
-__device__ __forceinline__ void sel_grab_all(const SceneDev& s, SelScratch<WSIZE>& sc, int n, int lane, const float* coord, const float* normal) {
+template <int WSIZE, int MAXV>
+__device__ __forceinline__ void sel_grab_all(const SceneDev& s, SelScratch<WSIZE, MAXV>& sc, int n, int lane, const float* coord, const float* normal) {
   CamDev refcam;
   load_cam(s, sc.images[0], refcam);
   float px[4], py[4];
@@ -159,8 +161,8 @@ __device__ __forceinline__ void sel_grab_all(const SceneDev& s, SelScratch<WSIZE
 }
 
 // COptim::constraintImages (optim.cpp:192-206): keep image 0 and every i with 1 - NCC(0, i) < 1 - threshold
-template <int WSIZE>
-__device__ __forceinline__ int sel_constraint_images(const SceneDev& s, SelScratch<WSIZE>& sc, int n, int lane, const float* coord,
+template <int WSIZE, int MAXV>
+__device__ __forceinline__ int sel_constraint_images(const SceneDev& s, SelScratch<WSIZE, MAXV>& sc, int n, int lane, const float* coord,
                                                      const float* normal, float ncc_threshold) {
   sel_grab_all<WSIZE>(s, sc, n, lane, coord, normal);
   const bool ref_ok = sc.valid[0] != 0;
@@ -319,8 +321,8 @@ __device__ __forceinline__ int sel_filter_by_angle(const SceneDev& s, Scratch& s
 // COptim::setRefImage (optim.cpp:208-254): robust all-pairs matrix (setINCCs matrix form, optim.cpp:746-781) over
 // the TARGET images of the patch; the reference image becomes the one with the smallest row sum and is swapped
 // into slot 0.  Returns the list length (0 when the patch has no target image: the reference clears the list).
-template <int WSIZE>
-__device__ __forceinline__ int sel_set_ref_image(const SceneDev& s, SelScratch<WSIZE>& sc, int n, int lane, const float* coord,
+template <int WSIZE, int MAXV>
+__device__ __forceinline__ int sel_set_ref_image(const SceneDev& s, SelScratch<WSIZE, MAXV>& sc, int n, int lane, const float* coord,
                                                  const float* normal) {
   for (int i = lane; i < n; i += 32) sc.aux[i] = sc.images[i];
   __syncwarp();
@@ -376,8 +378,8 @@ __device__ __forceinline__ void sel_set_grids(const SceneDev& s, const Scratch& 
 }
 
 // COptim::preProcess (optim.cpp:95-122).  Returns the verdict (0 keep / 1 reject); n, dscale, ascale updated.
-template <int WSIZE>
-__device__ __forceinline__ int sel_pre_process(const SceneDev& s, const SelectParams& sp, SelScratch<WSIZE>& sc, int& n, int cap, int lane,
+template <int WSIZE, int MAXV>
+__device__ __forceinline__ int sel_pre_process(const SceneDev& s, const SelectParams& sp, SelScratch<WSIZE, MAXV>& sc, int& n, int cap, int lane,
                                                const float* coord, const float* normal, float& dscale, float& ascale) {
   dscale = 0.0f; ascale = 0.0f;
   n = sel_add_images(s, sp, sc, n, cap, lane, coord, normal);
@@ -390,8 +392,8 @@ __device__ __forceinline__ int sel_pre_process(const SceneDev& s, const SelectPa
 }
 
 // COptim::postProcess (optim.cpp:150-190) at _depth == 0: no masks / bounding images in scope (getMask == 1).
-template <int WSIZE>
-__device__ __forceinline__ int sel_post_process(const SceneDev& s, const SelectParams& sp, SelScratch<WSIZE>& sc, int& n, int cap, int lane,
+template <int WSIZE, int MAXV>
+__device__ __forceinline__ int sel_post_process(const SceneDev& s, const SelectParams& sp, SelScratch<WSIZE, MAXV>& sc, int& n, int cap, int lane,
                                                 const float* coord, const float* normal, float ncc, int32_t* grids, int& timages, float& tmp) {
   timages = 0; tmp = 0.0f;
   if (n < s.min_image_num) return 1;
