@@ -424,17 +424,17 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
 
 
 // ---- K4: visible-image-set selection (pmvs_select.cuh): one warp (= one CTA) per patch ----------------
-template <int WSIZE>
+template <int WSIZE, int MAXV>
 __global__ void __launch_bounds__(32) k_pre_process(SceneDev s, SelectParams sp, int P, int stride, const float* __restrict__ coords,
                                                     const float* __restrict__ normals, int32_t* __restrict__ images,
                                                     int32_t* __restrict__ nimages, float* __restrict__ dscale,
                                                     float* __restrict__ ascale, int32_t* __restrict__ verdict) {
-  __shared__ SelScratch<WSIZE> sc;
+  __shared__ SelScratch<WSIZE, MAXV> sc;   // MAXV >= stride: the scratch is the occupancy limit (dispatch by stride)
   const int p = blockIdx.x, lane = threadIdx.x;
   if (p >= P) return;
   float coord[4], normal[4];
   load_patch(coords, normals, p, coord, normal);
-  const int cap = min(stride, kSelMaxViews);
+  const int cap = min(stride, MAXV);
   int n = min(nimages[p], cap);
   for (int i = lane; i < n; i += 32) sc.images[i] = images[(size_t)p * stride + i];
   __syncwarp();
@@ -446,18 +446,18 @@ __global__ void __launch_bounds__(32) k_pre_process(SceneDev s, SelectParams sp,
   if (lane == 0) { nimages[p] = n; dscale[p] = ds; ascale[p] = as; verdict[p] = v; }
 }
 
-template <int WSIZE>
+template <int WSIZE, int MAXV>
 __global__ void __launch_bounds__(32) k_post_process(SceneDev s, SelectParams sp, int P, int stride, const float* __restrict__ coords,
                                                      const float* __restrict__ normals, const float* __restrict__ ncc,
                                                      int32_t* __restrict__ images, int32_t* __restrict__ nimages,
                                                      int32_t* __restrict__ grids, int32_t* __restrict__ timages,
                                                      float* __restrict__ tmp, int32_t* __restrict__ verdict) {
-  __shared__ SelScratch<WSIZE> sc;
+  __shared__ SelScratch<WSIZE, MAXV> sc;   // MAXV >= stride: the scratch is the occupancy limit (dispatch by stride)
   const int p = blockIdx.x, lane = threadIdx.x;
   if (p >= P) return;
   float coord[4], normal[4];
   load_patch(coords, normals, p, coord, normal);
-  const int cap = min(stride, kSelMaxViews);
+  const int cap = min(stride, MAXV);
   int n = min(nimages[p], cap);
   for (int i = lane; i < n; i += 32) sc.images[i] = images[(size_t)p * stride + i];
   __syncwarp();
@@ -780,6 +780,18 @@ int check_ready(pmvsb_ctx* ctx) {
                else KG<7, false><<<gridg, block, 0, (ctx)->stream>>>(__VA_ARGS__); break;       \
     }                                                                                           \
     ++(ctx)->launches;                                                                          \
+  } while (0)
+
+// selection kernels: scratch capacity = smallest of 16 / 32 / 48 / 64 views that holds `stride` (larger strides are capped at 64)
+#define DISPATCH_VIEWS(ctx, stride, LAUNCH)                                                     \
+  do {                                                                                          \
+    if ((ctx)->wsize == 5) {                                                                    \
+      if ((stride) <= 16) LAUNCH(5, 16); else if ((stride) <= 32) LAUNCH(5, 32);                \
+      else if ((stride) <= 48) LAUNCH(5, 48); else LAUNCH(5, 64);                               \
+    } else {                                                                                    \
+      if ((stride) <= 16) LAUNCH(7, 16); else if ((stride) <= 32) LAUNCH(7, 32);                \
+      else if ((stride) <= 48) LAUNCH(7, 48); else LAUNCH(7, 64);                               \
+    }                                                                                           \
   } while (0)
 
 #define DISPATCH_WSIZE(ctx, KERNEL, grid, block, ...)                                           \
@@ -1874,8 +1886,9 @@ int pmvsb_pre_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coor
   DevBuf<float> dd, da;
   DevBuf<int32_t> dv;
   CK(dd.alloc(P)); CK(da.alloc(P)); CK(dv.alloc(P));
-  if (ctx->wsize == 5) k_pre_process<5><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, dd.p, da.p, dv.p);
-  else k_pre_process<7><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, dd.p, da.p, dv.p);
+#define LAUNCH_PRE(W, MAXV) k_pre_process<W, MAXV><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, st.images.p, st.nimages.p, dd.p, da.p, dv.p)
+  DISPATCH_VIEWS(ctx, stride, LAUNCH_PRE);
+#undef LAUNCH_PRE
   ++ctx->launches;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(images, st.images.p, sizeof(int32_t) * (size_t)stride * P, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1902,8 +1915,9 @@ int pmvsb_post_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coo
   CK(dn.alloc(P)); CK(dt.alloc(P)); CK(dg.alloc((size_t)2 * stride * P)); CK(dti.alloc(P)); CK(dv.alloc(P));
   CK(cudaMemcpyAsync(dn.p, ncc, sizeof(float) * P, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(dg.p, 0xff, sizeof(int32_t) * (size_t)2 * stride * P, ctx->stream));
-  if (ctx->wsize == 5) k_post_process<5><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, dn.p, st.images.p, st.nimages.p, dg.p, dti.p, dt.p, dv.p);
-  else k_post_process<7><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, dn.p, st.images.p, st.nimages.p, dg.p, dti.p, dt.p, dv.p);
+#define LAUNCH_POST(W, MAXV) k_post_process<W, MAXV><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, st.coords.p, st.normals.p, dn.p, st.images.p, st.nimages.p, dg.p, dti.p, dt.p, dv.p)
+  DISPATCH_VIEWS(ctx, stride, LAUNCH_POST);
+#undef LAUNCH_POST
   ++ctx->launches;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(images, st.images.p, sizeof(int32_t) * (size_t)stride * P, cudaMemcpyDeviceToHost, ctx->stream));
