@@ -117,3 +117,63 @@ def test_genoption_matches_reference(tmp_path):
     assert "threshold 0.7\n" in txt and "CPU 8\n" in txt and "timages 8 8 9 10 11 12 13 14 15 \n" in txt and "oimages 2 0 7 \n" in txt
     assert subprocess.run([exe], stderr=subprocess.PIPE).returncode == 1
     assert subprocess.run([exe, prefix + "nowhere/"], stderr=subprocess.PIPE).returncode == 1
+
+
+def test_clusters_runner_schedules_and_merges(tmp_path):
+    """bin/pmvs2_clusters without a GPU: a stand-in `pmvs2` next to a copy of the runner records its CUDA_VISIBLE_DEVICES and
+    writes small models; the runner must start every option-%04d exactly once, never two clusters on one GPU slot at a time,
+    and concatenate the models (counts add up, bodies in cluster order).  The real thing runs in tests/test_gpu_pipeline.py."""
+    import shutil
+    import stat
+    import subprocess
+    src = os.path.join(ROOT, "cmvs-pmvs_b200", "bin", "pmvs2_clusters")
+    assert os.path.exists(src), "pmvs2_clusters not built: run __graft_entry__.build()"
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    shutil.copy2(src, bindir / "pmvs2_clusters")
+    fake = bindir / "pmvs2"
+    fake.write_text("""#!/bin/bash
+# stand-in for pmvs2: prefix option [PATCH] [PSET]
+prefix=$1; opt=$2; c=$((10#${opt#option-})); n=$((c + 2))
+echo "$opt $CUDA_VISIBLE_DEVICES start $(date +%s%N)" >> ${prefix}trace.txt
+sleep 0.3
+{ printf 'ply\\nformat ascii 1.0\\nelement vertex %d\\nproperty float x\\nend_header\\n' $n; for i in $(seq $n); do echo "$c $i 0 0 0 1 1 2 3 0.9"; done; } > ${prefix}models/$opt.ply
+{ printf 'PATCHES\\n%d\\n' $n; for i in $(seq $n); do printf 'PATCHS\\n%d %d 0 1\\n0 0 1 0\\n0.9 1 1\\n3\\n0 1 2 \\n0\\n\\n\\n' $c $i; done; } > ${prefix}models/$opt.patch
+for i in $(seq $n); do echo "$c $i 0 0 0 1"; done > ${prefix}models/$opt.pset
+echo "$opt $CUDA_VISIBLE_DEVICES end $(date +%s%N)" >> ${prefix}trace.txt
+[ "$opt" != "option-0099" ]
+""")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    prefix = str(tmp_path / "scene") + "/"
+    os.makedirs(prefix)
+    K = 5
+    for c in range(K):
+        open(prefix + "option-%04d" % c, "w").write("level 1\n")
+    env = dict(os.environ)
+    env.pop("CUDA_VISIBLE_DEVICES", None)
+    p = subprocess.run([str(bindir / "pmvs2_clusters"), prefix, "--gpus", "2", "PATCH", "PSET"], stderr=subprocess.PIPE, text=True, env=env, timeout=120)
+    assert p.returncode == 0, p.stderr
+    trace = [l.split() for l in open(prefix + "trace.txt")]
+    starts = {t[0]: (t[1], int(t[3])) for t in trace if t[2] == "start"}
+    ends = {t[0]: int(t[3]) for t in trace if t[2] == "end"}
+    assert sorted(starts) == ["option-%04d" % c for c in range(K)]
+    assert {d for d, _ in starts.values()} == {"0", "1"}
+    for a in starts:                       # two clusters on the same device never overlap in time
+        for b in starts:
+            if a < b and starts[a][0] == starts[b][0]:
+                assert ends[a] <= starts[b][1] or ends[b] <= starts[a][1], (a, b)
+    total = sum(c + 2 for c in range(K))
+    pset = open(prefix + "models/option-all.pset").read().split("\n")[:-1]
+    assert len(pset) == total and pset[0] == "0 1 0 0 0 1" and pset[-1] == "%d %d 0 0 0 1" % (K - 1, K + 1)
+    ply = open(prefix + "models/option-all.ply").read().split("\n")
+    assert ply[2] == "element vertex %d" % total and "property float quality" in ply and len(ply) - 1 - (ply.index("end_header") + 1) == total
+    patch = open(prefix + "models/option-all.patch").read()
+    assert patch.startswith("PATCHES\n%d\n" % total) and patch.count("PATCHS") == total
+    # error paths: unknown argument, no option files, a failing cluster
+    assert subprocess.run([str(bindir / "pmvs2_clusters"), prefix, "--bogus"], stderr=subprocess.PIPE).returncode == 1
+    assert subprocess.run([str(bindir / "pmvs2_clusters"), str(tmp_path) + "/empty/", "--gpus", "1"], stderr=subprocess.PIPE).returncode == 1
+    shutil.rmtree(prefix + "models")
+    for c in range(K, 100):
+        open(prefix + "option-%04d" % c, "w").write("level 1\n")
+    q = subprocess.run([str(bindir / "pmvs2_clusters"), prefix, "--gpus", "16", "--no-merge"], stderr=subprocess.PIPE, text=True, env=env, timeout=300)
+    assert q.returncode == 1 and "cluster 99 FAILED" in q.stderr
