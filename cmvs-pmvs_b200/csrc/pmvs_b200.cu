@@ -313,13 +313,14 @@ __global__ void __launch_bounds__(128) k_score_g(SceneDev s, int P, int stride, 
   __shared__ float4 reftex_s[WSIZE * 128];
   float4* reftex = reftex_s + threadIdx.x;
   double f;
+  float ra_state[3] = {kPivot0, kPivot0, kPivot0};
   if (mode == 0) {
     float c2[4], n2[4];
-    f = group_objective<WSIZE, TEX>(s, gc, x, gl, g, 0, c2, n2, reftex, 128);
+    f = group_objective<WSIZE, TEX>(s, gc, x, gl, g, 0, c2, n2, reftex, 128, ra_state);
   } else {
     CamDev refcam;
     load_cam(s, gc.size > 0 ? gc.ref : 0, refcam);
-    f = group_photo_score<WSIZE, TEX>(s, gc, refcam, coord, normal, gl, g, mode, reftex, 128);
+    f = group_photo_score<WSIZE, TEX>(s, gc, refcam, coord, normal, gl, g, mode, reftex, 128, ra_state);
   }
   if (p < P && gl == 0) out[p] = f;
 }
@@ -350,6 +351,7 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
   }
   int p = -1;
   bool have = false, exhausted = false;
+  float ra_state[3] = {kPivot0, kPivot0, kPivot0};   // reference-view pivot carried from one evaluation of a patch to the next
   for (;;) {
     if (!have && !exhausted) {  // this group needs a patch (divergent between groups; shuffles name the group only)
       int q = 0;
@@ -383,6 +385,7 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
             nm_start(nm, x, s.step);  // clamps the start into the box as optim.cpp:629-634 does
           }
           have = true;
+          ra_state[0] = ra_state[1] = ra_state[2] = kPivot0;   // results must not depend on the group's previous patch
         }
       }
     }
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
     const int mode = (have && nm.state == NM_FINAL) ? 1 : 0;
     const double xt[3] = {nm.xt[0], nm.xt[1], nm.xt[2]};
     float rc[4], rn[4];
-    const double fx = group_objective<WSIZE, TEX>(s, gc, xt, gl, g, mode, rc, rn, reftex, 128);
+    const double fx = group_objective<WSIZE, TEX>(s, gc, xt, gl, g, mode, rc, rn, reftex, 128, ra_state);
     __syncwarp();
     if (have && gl == 0) nm_advance(nm, fx, s.xtol);
     __syncwarp();

@@ -20,6 +20,8 @@
 namespace pmvsb {
 
 constexpr int kGroup = 8;  // lanes per patch
+// first pivot of a patch's reference view: mid-grey in the units of the sampling path (the atlas path reads byte / 255)
+#define kPivot0 (TEX ? 0.5f : 127.5f)
 
 // Instruction-count switches of the scoring loop, all ON by default (measured on B200, 262 144 patches x 5 views:
 // 76.0 ms with all off, 68.9 ms with FAST_POS + FMA_INTERP, 65.2 ms with FOLD_PIVOT and 8 resident blocks per SM).
@@ -116,7 +118,7 @@ __device__ __forceinline__ float gget_unit(const CamDev& cam, int level, const f
 
 __device__ __forceinline__ float4 lds128(uint32_t a) {
   float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");   // ordered against the plain C++ stores of pass 2
   return v;
 }
 __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z) {   // .w is never read: reuse z
@@ -459,16 +461,16 @@ __device__ __forceinline__ void group_decode(const SceneDev& s, const GroupCtx& 
 //
 // Texture statistics are STREAMED so that no texture lives in registers and the row loop can stay rolled
 // (code size: the refine loop has to fit the instruction cache; registers: occupancy):
-//   reference view : pass 1 samples the 7 rows, stores them in shared memory and sums them; pass 2 turns the
-//                    stored values into deviations from the channel means (normalize's two passes,
-//                    optim.cpp:1036-1053) and accumulates sum d^2;
-//   other views    : one pass; each sample b is pivoted by the REFERENCE view's channel mean (all views see the
+//   reference view : one pass: samples the 7 rows pivoted by the previous evaluation's reference means (`ra_state`),
+//                    stores a' in shared memory, accumulates sum a' and sum a'^2;
+//   other views    : one pass; each sample b is pivoted by THIS evaluation's reference means (all views see the
 //                    same surface, so b' = b - mean_ref is almost centred and the raw-moment variance
-//                    sum b'^2 - (sum b')^2/N does not cancel), and sum d_ref * b' is the covariance.
+//                    sum b'^2 - (sum b')^2/N does not cancel); sum a' b' - (sum a')(sum b')/N is the covariance.
 // `reftex` points at this thread's column of a [WSIZE][blockDim.x] float4 array in shared memory.
 template <int WSIZE, bool TEX = false>
 __device__ __forceinline__ double group_photo_score(const SceneDev& s, const GroupCtx& gc, const CamDev& refcam, const float* coord,
-                                                    const float* normal, int gl, int g, int mode, float4* reftex, int rstride) {
+                                                    const float* normal, int gl, int g, int mode, float4* reftex, int rstride,
+                                                    float* ra_state) {
   const bool live = gc.size > 0;
   float px[4], py[4];
   get_paxes_c(refcam, s.level, coord, normal, px, py);
@@ -485,8 +487,12 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
 
   constexpr float N = (float)(WSIZE * WSIZE);
   constexpr float N3 = (float)(3 * WSIZE * WSIZE);
-  float ra0 = 0.f, ra1 = 0.f, ra2 = 0.f;   // reference channel means
-  float rd0 = 0.f, rd1 = 0.f, rd2 = 0.f;   // sum of reference deviations per channel (rounding residue, ~0)
+  // The reference view is pivoted by the reference means of the group's PREVIOUS evaluation (ra_state; the window moves
+  // by a fraction of a pixel between evaluations, so the stored values a' = a - pivot are centred to ~1 %) and every
+  // statistic is a raw moment of pivoted data: sum a'^2 - (sum a')^2 / N for the variance, sum a' b' - (sum a')(sum b') / N
+  // for the covariance.  That is normalize()'s two passes (optim.cpp:1036-1053) without the second pass over the rows.
+  float ra0 = ra_state[0], ra1 = ra_state[1], ra2 = ra_state[2];   // pivot, then this evaluation's reference means
+  float rd0 = 0.f, rd1 = 0.f, rd2 = 0.f;   // sum of the stored (pivoted) reference values per channel
   float sq_ref = 1.0f;
   double acc = 0.0;
   float totalweight = 0.0f;
@@ -529,7 +535,6 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
     // ONE sampling loop for every view (a second copy of the loop body costs instruction-cache misses):
     // the reference view (v == 0) runs it with ra = 0, i.e. b = raw sample, and additionally stores the row.
     const bool is_ref = v == 0;
-    if (is_ref) { ra0 = ra1 = ra2 = 0.0f; }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, q = 0.f, cr = 0.f;
     uint32_t rt = (uint32_t)__cvta_generic_to_shared(reftex);
 #if PMVS_TEX_PIPELINE && PMVS_FMA_INTERP && PMVS_FOLD_PIVOT && PMVS_FAST_POS
@@ -576,8 +581,8 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
 #else
       sample_row<WSIZE>(pix, lw, s.f32_2p23, cs, bx, by, rgb);
       const float4 d = reftex[row * rstride];
-      if (is_ref) reftex[row * rstride] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
       const float b0 = rgb[0] - ra0, b1 = rgb[1] - ra1, b2 = rgb[2] - ra2;
+      if (is_ref) reftex[row * rstride] = make_float4(b0, b1, b2, 0.0f);
 #endif
       s0 += b0; s1 += b1; s2 += b2;
       q = fmaf(b0, b0, q); q = fmaf(b1, b1, q); q = fmaf(b2, b2, q);
@@ -586,23 +591,11 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
     }
     s0 = group_sum(smp ? s0 : 0.0f); s1 = group_sum(smp ? s1 : 0.0f); s2 = group_sum(smp ? s2 : 0.0f);
     if (is_ref) {
-      // normalize's two passes (optim.cpp:1036-1053): channel means, then deviations and their squares
-#if PMVS_FAST_DIV
-      ra0 = s0 * (1.0f / N); ra1 = s1 * (1.0f / N); ra2 = s2 * (1.0f / N);
-#else
-      ra0 = fdiv(s0, N); ra1 = fdiv(s1, N); ra2 = fdiv(s2, N);
-#endif
-      float qq = 0.f, d0s = 0.f, d1s = 0.f, d2s = 0.f;
-#pragma unroll 1
-      for (int row = 0; row < WSIZE; ++row) {
-        const float4 t = reftex[row * rstride];
-        const float d0 = t.x - ra0, d1 = t.y - ra1, d2 = t.z - ra2;
-        reftex[row * rstride] = make_float4(d0, d1, d2, 0.0f);   // a non-sampling lane's column is read by itself only
-        qq = fmaf(d0, d0, qq); qq = fmaf(d1, d1, qq); qq = fmaf(d2, d2, qq);
-        d0s += d0; d1s += d1; d2s += d2;
-      }
-      sq_ref = group_sum(smp ? qq : 0.0f);
-      rd0 = group_sum(smp ? d0s : 0.0f); rd1 = group_sum(smp ? d1s : 0.0f); rd2 = group_sum(smp ? d2s : 0.0f);
+      q = group_sum(smp ? q : 0.0f);
+      rd0 = s0; rd1 = s1; rd2 = s2;
+      sq_ref = fmaxf(fmaf(-(1.0f / N), fmaf(s2, s2, fmaf(s1, s1, s0 * s0)), q), 0.0f);
+      if (sq_ref <= 1.0e-6f * q) sq_ref = 0.0f;   // constant texture up to the rounding of the raw moments: sd = 0 -> 1 (optim.cpp:1058)
+      ra0 = fmaf(s0, 1.0f / N, ra0); ra1 = fmaf(s1, 1.0f / N, ra1); ra2 = fmaf(s2, 1.0f / N, ra2);   // the true channel means
       continue;
     }
     q = group_sum(smp ? q : 0.0f); cr = group_sum(smp ? cr : 0.0f);
@@ -610,7 +603,8 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
       // sd = sqrt(sum dev^2 / 147), 0 -> 1 (optim.cpp:1055-1059); dot = sum(t_ref t_cur) / 147 (optim.cpp:1069-1077)
 #if PMVS_FAST_DIV
       // d = cross / (147 sd_a sd_b) with sd = sqrt(sq / 147), 0 -> 1, i.e. cross * rsqrt(A B) with A = sq or 147
-      const float sq_cur = fmaxf(fmaf(-(1.0f / N), fmaf(s2, s2, fmaf(s1, s1, s0 * s0)), q), 0.0f);
+      float sq_cur = fmaxf(fmaf(-(1.0f / N), fmaf(s2, s2, fmaf(s1, s1, s0 * s0)), q), 0.0f);
+      if (sq_cur <= 1.0e-6f * q) sq_cur = 0.0f;
       const float cross = fmaf(-(1.0f / N), fmaf(s2, rd2, fmaf(s1, rd1, s0 * rd0)), cr);
       const float A = sq_ref == 0.0f ? N3 : sq_ref, B = sq_cur == 0.0f ? N3 : sq_cur;
       const float d = cross * grsqrt(A * B);
@@ -637,6 +631,7 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
       }
     }
   }
+  if (have_ref) { ra_state[0] = ra0; ra_state[1] = ra1; ra_state[2] = ra2; }
   if (!have_ref) return 2.0;
   if (mode == 0) {
     const int mininum = s.min_image_num < gc.size ? s.min_image_num : gc.size;
@@ -651,11 +646,11 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
 // my_f(x) / computeINCC at decode(x); coord/normal receive the decoded patch.
 template <int WSIZE, bool TEX = false>
 __device__ __forceinline__ double group_objective(const SceneDev& s, const GroupCtx& gc, const double* x, int gl, int g, int mode,
-                                                  float* coord, float* normal, float4* reftex, int rstride) {
+                                                  float* coord, float* normal, float4* reftex, int rstride, float* ra_state) {
   CamDev refcam;
   load_cam(s, gc.size > 0 ? gc.ref : 0, refcam);  // 128 B, L1-resident; not kept in registers across the loop
   group_decode(s, gc, refcam.xaxis, refcam.yaxis, refcam.zaxis, x, gl, coord, normal);
-  return group_photo_score<WSIZE, TEX>(s, gc, refcam, coord, normal, gl, g, mode, reftex, rstride);
+  return group_photo_score<WSIZE, TEX>(s, gc, refcam, coord, normal, gl, g, mode, reftex, rstride, ra_state);
 }
 
 // The Nelder-Mead state of one group, kept in SHARED memory (216 B per patch) and advanced by the group's
