@@ -400,7 +400,11 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
     float rc[4], rn[4];
     const double fx = group_objective<WSIZE, TEX>(s, gc, xt, gl, g, mode, rc, rn, reftex, 128, ra_state);
     __syncwarp();
+#if PMVS_NM_LANES
+    if (have && gl < 3) nm_advance_lanes(nm, fx, s.xtol, gl, 0x7u << (g * kGroup), g * kGroup);
+#else
     if (have && gl == 0) nm_advance(nm, fx, s.xtol);
+#endif
     __syncwarp();
     if (have) {
       const int st = nm.state;

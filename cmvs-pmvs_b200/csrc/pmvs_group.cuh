@@ -116,6 +116,15 @@ __device__ __forceinline__ float gget_unit(const CamDev& cam, int level, const f
 #endif
 }
 
+// a / b for a small integer-valued b with y = RN(1 / b): q = RN(a y), r = a - b q (exact in one FMA), q' = RN(q + r y) is the
+// correctly rounded quotient (Markstein's final division step; holds for every finite a without over/underflow), i.e. the
+// same bits as the IEEE division of oracle/nm3.h in 3 instructions instead of ~30
+__device__ __forceinline__ double div_small(double a, double b, double y) {
+  const double q = a * y;
+  const double r = fma(-b, q, a);
+  return fma(r, y, q);
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");   // ordered against the plain C++ stores of pass 2
@@ -256,8 +265,9 @@ __device__ __forceinline__ void get_paxes_c(const CamDev& cam, int level, const 
 
 template <int WSIZE>
 __device__ __forceinline__ ViewWin view_window_c(const SceneDev& s, const CamDev& cam, int index, const float* coord,
-                                                 const float* px, const float* py, const float* pz) {
+                                                 const float* px, const float* py, const float* pz, float2* atlas_origin) {
   ViewWin w;
+  *atlas_origin = make_float2(1.0f, 1.0f);
   w.newlevel = -1;
   w.lx = w.ly = w.dxx = w.dxy = w.dyx = w.dyy = 0.0f;
   float ray[4] = {cam.centre[0] - coord[0], cam.centre[1] - coord[1], cam.centre[2] - coord[2], cam.centre[3] - coord[3]};
@@ -302,6 +312,7 @@ __device__ __forceinline__ ViewWin view_window_c(const SceneDev& s, const CamDev
     hi[k] = smax(tl, smax(tr, smax(bl, br)));
   }
   const LevelDev lv = s.levels[index * s.nlevels + newlevel];
+  *atlas_origin = make_float2(lv.ax1, lv.ay1);   // travels with the window: no level-table load in the per-view loop
   const bool safe = (lo[0] >= 3.0f) && (hi[0] < (float)(lv.w - 1 - 3)) && (lo[1] >= 3.0f) && (hi[1] < (float)(lv.h - 1 - 3));
   if (!safe) return w;
   w.lx = center[0] - dx[0] * m - dy[0] * m;
@@ -477,10 +488,11 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
   ViewWin mine;
   mine.newlevel = -1;
   mine.lx = mine.ly = mine.dxx = mine.dxy = mine.dyx = mine.dyy = 0.0f;
+  float2 mine_origin = make_float2(1.0f, 1.0f);
   if (gl < gc.size) {
     CamDev cam;
     load_cam(s, gc.my_image, cam);
-    mine = view_window_c<WSIZE>(s, cam, gc.my_image, coord, px, py, normal);
+    mine = view_window_c<WSIZE>(s, cam, gc.my_image, coord, px, py, normal, &mine_origin);
   }
   const unsigned validmask = (__ballot_sync(kFull, mine.newlevel >= 0) >> (g * kGroup)) & 0xffu;
   const bool have_ref = live && (validmask & 1u);
@@ -507,8 +519,15 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
     w.lx = __shfl_sync(kFull, mine.lx, v, kGroup);   w.ly = __shfl_sync(kFull, mine.ly, v, kGroup);
     w.dxx = __shfl_sync(kFull, mine.dxx, v, kGroup); w.dxy = __shfl_sync(kFull, mine.dxy, v, kGroup);
     w.dyx = __shfl_sync(kFull, mine.dyx, v, kGroup); w.dyy = __shfl_sync(kFull, mine.dyy, v, kGroup);
-    w.newlevel = __shfl_sync(kFull, mine.newlevel, v, kGroup);
-    const int index = __shfl_sync(kFull, gc.my_image, v, kGroup);
+    float ax1 = 1.0f, ay1 = 1.0f;   // TEX: off groups gather the footprint at the atlas origin
+    int index = 0;
+    if (TEX) {
+      ax1 = __shfl_sync(kFull, mine_origin.x, v, kGroup); ay1 = __shfl_sync(kFull, mine_origin.y, v, kGroup);
+      w.newlevel = 0;
+    } else {
+      w.newlevel = __shfl_sync(kFull, mine.newlevel, v, kGroup);
+      index = __shfl_sync(kFull, gc.my_image, v, kGroup);
+    }
     const float wv = __shfl_sync(kFull, gc.my_weight, v, kGroup);
     const bool smp = on && col;
     // groups whose view is off (rejected view, idle group) read texel (0,0) of a dummy level.  The 8th lane of a live
@@ -519,13 +538,11 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
     float bx = 0.0f, by = 0.0f;
     ColSteps<WSIZE> cs;
     ViewWin wz = w;
-    float ax1 = 1.0f, ay1 = 1.0f;   // TEX: off groups gather the footprint at the atlas origin
-    if (!on) { wz.dxx = wz.dxy = wz.dyx = wz.dyy = 0.0f; }
+    // (clamped texture addressing makes any coordinate safe: only the global-load path has to pin idle lanes to the dummy texel;
+    //  an invalid view's window is all zeros anyway)
+    if (!TEX && !on) { wz.dxx = wz.dxy = wz.dyx = wz.dyy = 0.0f; }
     if (on) {
-      if (TEX) {
-        const float2 o = *reinterpret_cast<const float2*>(&s.levels[index * s.nlevels + w.newlevel].ax1);
-        ax1 = o.x; ay1 = o.y;
-      } else {
+      if (!TEX) {
         const LevelDev lv = s.levels[index * s.nlevels + w.newlevel];
         pix = reinterpret_cast<const uint32_t*>(lv.pix); lw = lv.w;
       }
@@ -636,6 +653,10 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
   if (mode == 0) {
     const int mininum = s.min_image_num < gc.size ? s.min_image_num : gc.size;
     if (denom < mininum - 1) return 2.0;
+    if (denom >= 1 && denom <= 7) {   // tau - 1 views at most in practice: same bits as the division, without its expansion
+      const double y = denom == 1 ? 1.0 : denom == 2 ? 0.5 : denom == 3 ? 1.0 / 3.0 : denom == 4 ? 0.25 : denom == 5 ? 0.2 : denom == 6 ? 1.0 / 6.0 : 1.0 / 7.0;
+      return div_small(acc, (double)denom, y);
+    }
     return acc / (double)denom;
   }
   if (gc.nimages < 2) return 2.0;
@@ -758,13 +779,122 @@ __device__ __forceinline__ void nm_advance(NMShared& n, double fx, double xtol) 
       n.state = NM_FINAL;
       for (int j = 0; j < 3; ++j) n.xt[j] = n.p[0][j];
     } else {
-      for (int j = 0; j < 3; ++j) n.c[j] = ((n.p[0][j] + n.p[1][j]) + n.p[2][j]) / 3.0;
+      for (int j = 0; j < 3; ++j) n.c[j] = div_small((n.p[0][j] + n.p[1][j]) + n.p[2][j], 3.0, 1.0 / 3.0);   // == sum / 3.0
       n.xr[0] = n.c[0] + (n.c[0] - n.p[3][0]);
       n.xr[1] = clampd(n.c[1] + (n.c[1] - n.p[3][1]), lb1, ub1);
       n.xr[2] = clampd(n.c[2] + (n.c[2] - n.p[3][2]), lb1, ub1);
       for (int j = 0; j < 3; ++j) n.xt[j] = n.xr[j];
       n.state = NM_REFLECT;
     }
+  }
+}
+
+// nm_advance spread over lanes 0..2 of the group: lane j owns coordinate j of every vertex (its column of p, xt, c, xr), all
+// three hold the scalars (f values, state) in registers and take identical decisions, so the per-coordinate loops of
+// nm_advance become one operation and the only exchange is the simplex extent (max over the three columns).  Same steps,
+// same tie rules, same bits as nm_advance / oracle/nm3.h (checked bit for bit against the leader-only form on the GPU).
+// The stable insertion runs as a fixed compare-exchange network on registers: vertex k in [ins_lo, ins_hi] moves down
+// while it is strictly better than its predecessor.
+// Measured on B200 (262 144 patches): 41.0 ms against 40.7 ms for the leader-only form, results bit-identical -- the three
+// lanes' loads / stores of the state and the always-executed network cost what the shorter paths save.  Kept off.
+#ifndef PMVS_NM_LANES
+#define PMVS_NM_LANES 0
+#endif
+__device__ __forceinline__ void cswapd(bool sw, double& a, double& b) {
+  const double t = sw ? b : a;
+  b = sw ? a : b;
+  a = t;
+}
+__device__ __forceinline__ void nm_advance_lanes(NMShared& n, double fx, double xtol, int j, unsigned mask3, int lane_base) {
+  const double lb1 = -23.99999, ub1 = 23.99999;
+  const bool boxed = j > 0;   // depth is unbounded, the two angles are boxed (optim.cpp:601-602)
+  int state = n.state;
+  if (state == NM_FINAL) {
+    if (j == 0) { n.fr = fx; n.state = NM_DONE_OK; }
+    return;
+  }
+  int idx = n.idx;
+  const int cnt = n.cnt + 1;
+  double f[4] = {n.f[0], n.f[1], n.f[2], n.f[3]};
+  double p[4] = {n.p[0][j], n.p[1][j], n.p[2][j], n.p[3][j]};
+  double fr = n.fr, fref = n.fref;
+  double xt = n.xt[j], c = n.c[j], xr = n.xr[j];
+  int ins_lo = 1, ins_hi = 0;   // empty range
+  bool new_iter = false;
+  if (state == NM_INIT || state == NM_SHRINK) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = idx == k ? fx : f[k];
+    if (state == NM_INIT) ins_lo = ins_hi = idx;
+    ++idx;
+    if (idx <= 3) xt = idx == 1 ? p[1] : (idx == 2 ? p[2] : p[3]);
+    else { new_iter = true; if (state == NM_SHRINK) { ins_lo = 1; ins_hi = 3; } }
+  } else if (state == NM_REFLECT) {
+    fr = fx;
+    if (fx < f[0]) {
+      const double e = c + 2.0 * (c - p[3]);
+      xt = boxed ? clampd(e, lb1, ub1) : e;
+      state = NM_EXPAND;
+    } else if (fx < f[2]) {
+      p[3] = xr; f[3] = fx;
+      ins_lo = ins_hi = 3;
+      new_iter = true;
+    } else {
+      const bool outside = fx < f[3];
+      xt = c + 0.5 * ((outside ? xr : p[3]) - c);
+      fref = outside ? fx : f[3];
+      state = NM_CONTRACT;
+    }
+  } else {  // NM_EXPAND or NM_CONTRACT
+    const bool take_xt = state == NM_EXPAND ? (fx < fr) : (fx < fref);
+    if (take_xt || state == NM_EXPAND) {
+      p[3] = take_xt ? xt : xr;
+      f[3] = take_xt ? fx : fr;
+      ins_lo = ins_hi = 3;
+      new_iter = true;
+    } else {  // failed contraction: shrink towards the best vertex, re-evaluate vertices 1..3 in order
+#pragma unroll
+      for (int i = 1; i <= 3; ++i) p[i] = p[0] + 0.5 * (p[i] - p[0]);
+      state = NM_SHRINK;
+      idx = 1;
+      xt = p[1];
+    }
+  }
+#pragma unroll
+  for (int k = 1; k <= 3; ++k) {
+    bool moving = ins_lo <= k && k <= ins_hi;
+#pragma unroll
+    for (int q = k; q >= 1; --q) {
+      const bool sw = moving && f[q] < f[q - 1];
+      cswapd(sw, f[q], f[q - 1]);
+      cswapd(sw, p[q], p[q - 1]);
+      moving = sw;
+    }
+  }
+  if (new_iter) {
+    double mine = fabs(p[1] - p[0]);
+    mine = fmax(mine, fabs(p[2] - p[0]));
+    mine = fmax(mine, fabs(p[3] - p[0]));
+    const double s0 = __shfl_sync(mask3, mine, lane_base), s1 = __shfl_sync(mask3, mine, lane_base + 1), s2 = __shfl_sync(mask3, mine, lane_base + 2);
+    const double size = fmax(s0, fmax(s1, s2));
+    if (size <= xtol) {
+      state = NM_FINAL;
+      xt = p[0];
+    } else {
+      c = div_small((p[0] + p[1]) + p[2], 3.0, 1.0 / 3.0);   // == sum / 3.0
+      const double r = c + (c - p[3]);
+      xr = boxed ? clampd(r, lb1, ub1) : r;
+      xt = xr;
+      state = NM_REFLECT;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) n.p[i][j] = p[i];
+  n.xt[j] = xt; n.c[j] = c; n.xr[j] = xr;
+  if (j == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) n.f[i] = f[i];
+    n.fr = fr; n.fref = fref;
+    n.state = state; n.idx = idx; n.cnt = cnt;
   }
 }
 

@@ -47,11 +47,14 @@ def main():
             if r > 0:
                 ms.append(lib.last_refine_ms())
         ncc = d_ncc.cpu().numpy()
+        cur = (ncc, d_ev.cpu().numpy(), d_c.cpu().numpy(), d_n.cpu().numpy())
         if ref is None:
-            ref = ncc
-        print("%-22s kernel ms %s  -> %.3f M patches/s  evals %.1f  ok %.4f  max|dncc vs first| %.2e" % (
+            ref = cur
+        same = all(np.array_equal(a, b) for a, b in zip(cur, ref))
+        print("%-22s kernel ms %s  -> %.3f M patches/s  evals %.1f  ok %.4f  max|dncc vs first| %.2e  identical evals %.4f  %s" % (
             name, ["%.1f" % m for m in ms], P / (min(ms) / 1e3) / 1e6, float(d_ev.float().mean()), float(d_ok.float().mean()),
-            float(np.abs(ncc - ref).max())), flush=True)
+            float(np.abs(ncc - ref[0]).max()), float((cur[1] == ref[1]).mean()),
+            "BIT-IDENTICAL to first (ncc, evals, coords, normals)" if same else "differs from first"), flush=True)
         lib.close()
 
 
