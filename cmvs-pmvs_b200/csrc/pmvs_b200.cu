@@ -310,17 +310,16 @@ __global__ void __launch_bounds__(128) k_score_g(SceneDev s, int P, int stride, 
     if (mode == 0) { x[0] = xs[3 * p]; x[1] = xs[3 * p + 1]; x[2] = xs[3 * p + 2]; }
   }
   __syncwarp();
-  __shared__ float4 reftex_s[WSIZE * 128];
-  float4* reftex = reftex_s + threadIdx.x;
+  __shared__ __align__(16) float reftex[RefTex<WSIZE>::kFloats];
   double f;
   float ra_state[3] = {kPivot0, kPivot0, kPivot0};
   if (mode == 0) {
     float c2[4], n2[4];
-    f = group_objective<WSIZE, TEX>(s, gc, x, gl, g, 0, c2, n2, reftex, 128, ra_state);
+    f = group_objective<WSIZE, TEX>(s, gc, x, gl, g, 0, c2, n2, reftex, ra_state);
   } else {
     CamDev refcam;
     load_cam(s, gc.size > 0 ? gc.ref : 0, refcam);
-    f = group_photo_score<WSIZE, TEX>(s, gc, refcam, coord, normal, gl, g, mode, reftex, 128, ra_state);
+    f = group_photo_score<WSIZE, TEX>(s, gc, refcam, coord, normal, gl, g, mode, reftex, ra_state);
   }
   if (p < P && gl == 0) out[p] = f;
 }
@@ -336,8 +335,7 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
                                                      int* __restrict__ counter) {
   // counter[0] = next patch to hand out, counter[1] = set to 1 when a patch names an image outside [0, num)
   __shared__ NMShared nms[4][4];  // [warp in CTA][group in warp]
-  __shared__ float4 reftex_s[WSIZE * 128];  // reference-view deviations, [row][thread]
-  float4* reftex = reftex_s + threadIdx.x;
+  __shared__ __align__(16) float reftex[RefTex<WSIZE>::kFloats];  // pivoted reference-view samples (pmvs_group.cuh: RefTex)
   const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
   const unsigned gmask = 0xffu << (g * kGroup);
   NMShared& nm = nms[threadIdx.x >> 5][g];
@@ -398,7 +396,7 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
     const int mode = (have && nm.state == NM_FINAL) ? 1 : 0;
     const double xt[3] = {nm.xt[0], nm.xt[1], nm.xt[2]};
     float rc[4], rn[4];
-    const double fx = group_objective<WSIZE, TEX>(s, gc, xt, gl, g, mode, rc, rn, reftex, 128, ra_state);
+    const double fx = group_objective<WSIZE, TEX>(s, gc, xt, gl, g, mode, rc, rn, reftex, ra_state);
     __syncwarp();
 #if PMVS_NM_LANES
     if (have && gl < 3) nm_advance_lanes(nm, fx, s.xtol, gl, 0x7u << (g * kGroup), g * kGroup);

@@ -125,14 +125,53 @@ __device__ __forceinline__ double div_small(double a, double b, double y) {
   return fma(r, y, q);
 }
 
-__device__ __forceinline__ float4 lds128(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");   // ordered against the plain C++ stores of pass 2
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z) {   // .w is never read: reuse z
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %3};" :: "r"(a), "f"(x), "f"(y), "f"(z) : "memory");
-}
+// Reference-view scratch of the group kernels, one column per thread of a 128-thread CTA.
+// PMVS_REFTEX_SOA = 1: three float planes [channel][row][thread] (12 B per sample, 3 LDS.32 / STS.32 with immediate plane
+// offsets) instead of one float4 per sample (16 B, LDS.128): 10.5 KB instead of 14 KB per CTA, which lets 8 CTAs fit the
+// 132 KB shared-memory carve-out and leaves ~32 KB more of the SM's 256 KB to the texture cache.
+#ifndef PMVS_REFTEX_SOA
+#define PMVS_REFTEX_SOA 1
+#endif
+#if PMVS_REFTEX_SOA && !(PMVS_FMA_INTERP && PMVS_FOLD_PIVOT)
+#error "PMVS_REFTEX_SOA needs the default sampling path (PMVS_FMA_INTERP and PMVS_FOLD_PIVOT)"
+#endif
+template <int WSIZE>
+struct RefTex {
+#if PMVS_REFTEX_SOA
+  static constexpr int kFloats = 3 * WSIZE * 128;
+  static constexpr uint32_t kRowBytes = 128 * 4, kPlaneBytes = WSIZE * 128 * 4;
+#else
+  static constexpr int kFloats = 4 * WSIZE * 128;
+  static constexpr uint32_t kRowBytes = 128 * 16, kPlaneBytes = 0;
+#endif
+  // shared-window address of this thread's column in row 0
+  static __device__ __forceinline__ uint32_t column(const float* base) {
+#if PMVS_REFTEX_SOA
+    return (uint32_t)__cvta_generic_to_shared(base) + threadIdx.x * 4;
+#else
+    return (uint32_t)__cvta_generic_to_shared(base) + threadIdx.x * 16;
+#endif
+  }
+  static __device__ __forceinline__ float4 load(uint32_t a) {
+    float4 v;
+#if PMVS_REFTEX_SOA
+    asm volatile("ld.shared.f32 %0, [%3];\n\tld.shared.f32 %1, [%3+%4];\n\tld.shared.f32 %2, [%3+%5];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z) : "r"(a), "n"(kPlaneBytes), "n"(2 * kPlaneBytes) : "memory");
+    v.w = 0.0f;
+#else
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+#endif
+    return v;
+  }
+  static __device__ __forceinline__ void store(uint32_t a, float x, float y, float z) {
+#if PMVS_REFTEX_SOA
+    asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+%4], %2;\n\tst.shared.f32 [%0+%5], %3;"
+                 :: "r"(a), "f"(x), "f"(y), "f"(z), "n"(kPlaneBytes), "n"(2 * kPlaneBytes) : "memory");
+#else
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %3};" :: "r"(a), "f"(x), "f"(y), "f"(z) : "memory");
+#endif
+  }
+};
 
 __device__ __forceinline__ float group_sum(float v) {
   v += __shfl_xor_sync(kFull, v, 4);
@@ -477,10 +516,10 @@ __device__ __forceinline__ void group_decode(const SceneDev& s, const GroupCtx& 
 //   other views    : one pass; each sample b is pivoted by THIS evaluation's reference means (all views see the
 //                    same surface, so b' = b - mean_ref is almost centred and the raw-moment variance
 //                    sum b'^2 - (sum b')^2/N does not cancel); sum a' b' - (sum a')(sum b')/N is the covariance.
-// `reftex` points at this thread's column of a [WSIZE][blockDim.x] float4 array in shared memory.
+// `reftex` is the CTA's RefTex<WSIZE> scratch in shared memory (kFloats floats; blockDim.x = 128).
 template <int WSIZE, bool TEX = false>
 __device__ __forceinline__ double group_photo_score(const SceneDev& s, const GroupCtx& gc, const CamDev& refcam, const float* coord,
-                                                    const float* normal, int gl, int g, int mode, float4* reftex, int rstride,
+                                                    const float* normal, int gl, int g, int mode, float* reftex,
                                                     float* ra_state) {
   const bool live = gc.size > 0;
   float px[4], py[4];
@@ -553,7 +592,7 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
     // the reference view (v == 0) runs it with ra = 0, i.e. b = raw sample, and additionally stores the row.
     const bool is_ref = v == 0;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, q = 0.f, cr = 0.f;
-    uint32_t rt = (uint32_t)__cvta_generic_to_shared(reftex);
+    uint32_t rt = RefTex<WSIZE>::column(reftex);
 #if PMVS_TEX_PIPELINE && PMVS_FMA_INTERP && PMVS_FOLD_PIVOT && PMVS_FAST_POS
     if (TEX) {
       static_assert(WSIZE % 2 == 1, "the pipelined loop consumes rows in pairs plus one");
@@ -562,9 +601,9 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
       auto consume = [&](const Foot& f) {
         float rgb[3];
         gather_finish(f, rgb, -ra0, -ra1, -ra2);
-        const float4 d = lds128(rt);
-        if (is_ref) sts128(rt, rgb[0], rgb[1], rgb[2]);
-        rt += rstride * 16;
+        const float4 d = RefTex<WSIZE>::load(rt);
+        if (is_ref) RefTex<WSIZE>::store(rt, rgb[0], rgb[1], rgb[2]);
+        rt += RefTex<WSIZE>::kRowBytes;
         s0 += rgb[0]; s1 += rgb[1]; s2 += rgb[2];
         q = fmaf(rgb[0], rgb[0], q); q = fmaf(rgb[1], rgb[1], q); q = fmaf(rgb[2], rgb[2], q);
         cr = fmaf(d.x, rgb[0], cr); cr = fmaf(d.y, rgb[1], cr); cr = fmaf(d.z, rgb[2], cr);
@@ -591,15 +630,16 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
       if (TEX) sample_row_tex<WSIZE>(s.atlas, ax1, ay1, cs, bx, by, rgb, -ra0, -ra1, -ra2);
       else sample_row<WSIZE>(pix, lw, s.f32_2p23, cs, bx, by, rgb, -ra0, -ra1, -ra2);
       // explicit 32-bit shared addressing: one live register, no generic-to-shared rematerialisation in the loop
-      const float4 d = lds128(rt);
-      if (is_ref) sts128(rt, rgb[0], rgb[1], rgb[2]);
-      rt += rstride * 16;
+      const float4 d = RefTex<WSIZE>::load(rt);
+      if (is_ref) RefTex<WSIZE>::store(rt, rgb[0], rgb[1], rgb[2]);
+      rt += RefTex<WSIZE>::kRowBytes;
       const float b0 = rgb[0], b1 = rgb[1], b2 = rgb[2];
 #else
       sample_row<WSIZE>(pix, lw, s.f32_2p23, cs, bx, by, rgb);
-      const float4 d = reftex[row * rstride];
+      float4* col = reinterpret_cast<float4*>(reftex) + threadIdx.x;   // (PMVS_REFTEX_SOA == 0 here)
+      const float4 d = col[row * 128];
       const float b0 = rgb[0] - ra0, b1 = rgb[1] - ra1, b2 = rgb[2] - ra2;
-      if (is_ref) reftex[row * rstride] = make_float4(b0, b1, b2, 0.0f);
+      if (is_ref) col[row * 128] = make_float4(b0, b1, b2, 0.0f);
 #endif
       s0 += b0; s1 += b1; s2 += b2;
       q = fmaf(b0, b0, q); q = fmaf(b1, b1, q); q = fmaf(b2, b2, q);
@@ -667,11 +707,11 @@ __device__ __forceinline__ double group_photo_score(const SceneDev& s, const Gro
 // my_f(x) / computeINCC at decode(x); coord/normal receive the decoded patch.
 template <int WSIZE, bool TEX = false>
 __device__ __forceinline__ double group_objective(const SceneDev& s, const GroupCtx& gc, const double* x, int gl, int g, int mode,
-                                                  float* coord, float* normal, float4* reftex, int rstride, float* ra_state) {
+                                                  float* coord, float* normal, float* reftex, float* ra_state) {
   CamDev refcam;
   load_cam(s, gc.size > 0 ? gc.ref : 0, refcam);  // 128 B, L1-resident; not kept in registers across the loop
   group_decode(s, gc, refcam.xaxis, refcam.yaxis, refcam.zaxis, x, gl, coord, normal);
-  return group_photo_score<WSIZE, TEX>(s, gc, refcam, coord, normal, gl, g, mode, reftex, rstride, ra_state);
+  return group_photo_score<WSIZE, TEX>(s, gc, refcam, coord, normal, gl, g, mode, reftex, ra_state);
 }
 
 // The Nelder-Mead state of one group, kept in SHARED memory (216 B per patch) and advanced by the group's
