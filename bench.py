@@ -412,8 +412,8 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(P), "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "evals_per_patch": evals_sum / P,
                 "note": "algorithmic bytes = 588 B x views x (evaluations + 1) per patch (SURVEY.md 8d); most gathers hit L1/L2, "
-                        "so HBM traffic is far below this figure; the kernel is bound by instruction issue (71 %) and TLD4 latency/throughput "
-                        "(texture data pipe 68 %), profiles/r1_k_refine_g_atlas_full_ncu_metrics.csv"}
+                        "so HBM traffic is far below this figure; the kernel is bound by instruction issue (76 %) and TLD4 latency/throughput "
+                        "(texture data pipe 75 %), profiles/r1_k_refine_g_v8_full_ncu_metrics.csv"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
