@@ -228,7 +228,7 @@ def write_scene_for_reference(scene, cpu_threads, tag="scene"):
     return prefix
 
 
-def reference_rate(scene, patches, seconds, steps=1, warmup=0):
+def reference_rate(scene, patches, seconds, steps=1, warmup=0, full=None):
     """Times COptim::refinePatch of the reference build over a bounded sample on all host cores.
     Returns dict(value, cores, kind, sample, ms_per_step, evals_per_patch)."""
     from oracle import bindings as ob
@@ -253,7 +253,7 @@ def reference_rate(scene, patches, seconds, steps=1, warmup=0):
             times.append(r["seconds"]); evals.append(float(r["evals"].mean()))
     total = float(sum(times))
     return dict(value=per_step * len(times) / total, cores=cores, kind=kind,
-                sample="%d of the %d bench patches per step x %d steps, COptim::refinePatch on %d host threads" % (per_step, len(coords), len(times), cores),
+                sample="%d-patch sample of the %d-patch step (same generator, seed 4) per step x %d steps, COptim::refinePatch on %d host threads" % (per_step, full or len(coords), len(times), cores),
                 ms_per_step=1000.0 * total / len(times), evals_per_patch=float(np.mean(evals)), unit=UNIT)
 
 
@@ -290,7 +290,7 @@ def main():
                     d = np.array([orc.set_scales(c[i], im[i])[0] for i in range(len(c))], np.float32)
                     return d, d
             patches = make_seed_patches(scene, _S(), n, seed=4, device=dev)
-        r = reference_rate(scene, patches, seconds=max(20.0, 8.0 * (args.steps + args.warmup)), steps=args.steps, warmup=args.warmup)
+        r = reference_rate(scene, patches, seconds=max(20.0, 8.0 * (args.steps + args.warmup)), steps=args.steps, warmup=args.warmup, full=args.patches)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -424,7 +424,7 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = min(P, 1 << 16)
-        r = reference_rate(scene, (coords[:n], normals[:n], images[:n], dsc[:n]), seconds=args.cpu_seconds)
+        r = reference_rate(scene, (coords[:n], normals[:n], images[:n], dsc[:n]), seconds=args.cpu_seconds, full=P)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                                 "evals_per_patch": r["evals_per_patch"]}
     lib.close()
