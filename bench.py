@@ -196,6 +196,16 @@ def pipeline_wall_time(scene, impl):
             tok = l.split(":")[1].split()
             if len(tok) == 5 and all(t.isdigit() for t in tok) and not (tok[0] == "100" and int(tok[1]) + int(tok[2]) + int(tok[3]) != 100):
                 refined.append(int(tok[4]))
+    phases = {}   # pmvs2's own per-phase clocks ("time <name> <seconds> s" on stderr)
+    for l in p.stderr.splitlines():
+        tok = l.split()
+        if len(tok) == 4 and tok[0] == "time" and tok[3] == "s":
+            try:
+                phases[tok[1]] = round(float(tok[2]), 4)
+            except ValueError:
+                pass
+    if phases:
+        out["phases_seconds"] = phases
     if refined:
         out["refined_patches"] = int(sum(refined))                      # the reference's own "refinepatch" counter
         out["refined_patches_per_sec_whole_run"] = out["refined_patches"] / secs
