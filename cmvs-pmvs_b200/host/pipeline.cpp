@@ -157,7 +157,7 @@ void Pipeline::upload_table(const std::vector<int>& ids) {
   table_ids_ = ids;
   table_index_.assign(patches_.size(), -1);
   for (size_t k = 0; k < ids.size(); ++k) table_index_[ids[k]] = (int)k;
-  TableArrays t;
+  static TableArrays t;   // reused by the ~18 uploads of a run: no fresh 60 MB of zero-filled pages per call (marshal writes every slot it sizes)
   marshal(ids, t);
   if (pmvsb_set_thresholds(gpu_, ncc_threshold_, ncc_threshold_before_)) die("set_thresholds");
   if (pmvsb_set_depth(gpu_, depth_)) die("set_depth");
@@ -190,7 +190,8 @@ void Pipeline::rebuild_depth_and_vis(bool additive) {
   if (P == 0) return;
   int32_t total = 0;
   if (pmvsb_store_update_vimages(gpu_, additive ? 1 : 0, &total)) die("store_update_vimages");
-  std::vector<int32_t> voff(P + 1), vim(std::max(1, total)), vgr((size_t)2 * std::max(1, total));
+  static std::vector<int32_t> voff, vim, vgr;   // reused across the rebuilds (the download overwrites every slot it sizes)
+  voff.resize(P + 1); vim.resize(std::max(1, total)); vgr.resize((size_t)2 * std::max(1, total));
   if (pmvsb_store_download_vimages(gpu_, voff.data(), vim.data(), vgr.data())) die("store_download_vimages");
   parallel_for(P, threads_, [&](int k) {
     Patch& p = patches_[ids[k]];
