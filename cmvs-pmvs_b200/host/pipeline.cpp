@@ -65,7 +65,8 @@ float Pipeline::get_unit(int image, const float* X) const {          // optim.cp
 }
 
 bool Pipeline::is_neighbor(const Patch& l, const Patch& r, float hunit, float thr, float radius) const {   // findMatch.cpp:125-185
-  if (dot4(l.normal, r.normal) < std::cos(120.0 * M_PI / 180.0)) return false;
+  static const double cos120 = std::cos(120.0 * M_PI / 180.0);   // same double as the reference's per-call expression
+  if (dot4(l.normal, r.normal) < cos120) return false;
   float diff[4];
   for (int k = 0; k < 4; ++k) diff[k] = r.coord[k] - l.coord[k];
   const float vunit = l.dscale + r.dscale;
@@ -86,9 +87,10 @@ bool Pipeline::is_neighbor(const Patch& l, const Patch& r, float thr) const {   
 }
 
 // ---------------------------------------------------------------------------------------------- bookkeeping
-int Pipeline::add_patch(const Patch& p) {   // patchOrganizerS.cpp:312-349
+int Pipeline::add_patch(Patch&& moved) {   // patchOrganizerS.cpp:312-349
   const int id = (int)patches_.size();
-  patches_.push_back(p);
+  patches_.push_back(std::move(moved));   // the four lists change owner instead of being copied
+  const Patch& p = patches_.back();
   patches_.back().alive = true;
   for (size_t i = 0; i < p.images.size(); ++i) {
     const int im = p.images[i];
@@ -570,7 +572,7 @@ void Pipeline::seed_round() {
           if (count_threshold0_ <= count) break;
         }
         if (count != 0 && best) {
-          add_patch(*best);
+          add_patch(Patch(*best));
           ++total;
           placed = true;
         }
@@ -698,7 +700,7 @@ void Pipeline::expand_round() {
           ++st.pass;
           const bool requeue = update_counts(p);
           p.flag = 1;
-          const int nid = add_patch(p);
+          const int nid = add_patch(std::move(p));   // the wave's copy is not read again (only c.parent / c.dir)
           if (requeue) next.push_back(nid);
         }
       }
@@ -843,6 +845,9 @@ void Pipeline::filter_small_groups() {   // filter.cpp:524-665
   }, 1);
   std::vector<int> index_of(patches_.size(), -1);
   for (int k = 0; k < P; ++k) index_of[ids[k]] = k;
+  // getUnit of every table patch once (is_neighbor's hunit needs it for both patches of each of the ~1e7 tests)
+  std::vector<float> unit(P);
+  parallel_for(P, threads_, [&](int k) { const Patch& p = patches_[ids[k]]; unit[k] = get_unit(p.images[0], p.coord); }, 4096);
   std::vector<int> label(P, -1);
   int id = -1;
   for (int start = 0; start < P; ++start) {
@@ -867,7 +872,8 @@ void Pipeline::filter_small_groups() {   // filter.cpp:524-665
             for (int q : *lst) {
               const int kq = index_of[q];
               if (kq < 0 || label[kq] != -1) continue;
-              if (is_neighbor(p, patches_[q], neighbor_threshold2_)) { label[kq] = id; work.push_back(kq); }
+              const float hunit = (float)((unit[k] + unit[kq]) / 2.0 * opt_.csize);   // findMatch.cpp:120-123
+              if (is_neighbor(p, patches_[q], hunit, neighbor_threshold2_, -1.0f)) { label[kq] = id; work.push_back(kq); }
             }
         }
       }

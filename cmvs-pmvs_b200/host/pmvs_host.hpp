@@ -112,7 +112,7 @@ class Pipeline {
   bool is_neighbor(const Patch& l, const Patch& r, float hunit, float thr, float radius) const;   // radius < 0: no radius test
   bool is_neighbor(const Patch& l, const Patch& r, float thr) const;
   // ---- bookkeeping
-  int add_patch(const Patch& p);            // CPatchOrganizerS::addPatch
+  int add_patch(Patch&& p);                 // CPatchOrganizerS::addPatch (takes the lists over)
   void remove_patch(int id);                // CPatchOrganizerS::removePatch
   std::vector<int> collect_patches() const; // ids of live patches in the reference's collectPatches order
   void rebuild_depth_and_vis(bool additive);
