@@ -177,3 +177,27 @@ echo "$opt $CUDA_VISIBLE_DEVICES end $(date +%s%N)" >> ${prefix}trace.txt
         open(prefix + "option-%04d" % c, "w").write("level 1\n")
     q = subprocess.run([str(bindir / "pmvs2_clusters"), prefix, "--gpus", "16", "--no-merge"], stderr=subprocess.PIPE, text=True, env=env, timeout=300)
     assert q.returncode == 1 and "cluster 99 FAILED" in q.stderr
+
+
+def test_reference_arm_line_contract():
+    """`bench.py --impl reference` (the arm the driver times beside ours): rank 0 prints ONE JSON line with the metric,
+    config and unit of our arm, `impl`, a `cpu_baseline` describing the run and an `e2e` without copies; any other rank
+    exits 0 without output.  Tiny scene so that it runs on the CPU suite's budget."""
+    import json
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--patches", "512", "--steps", "2", "--warmup", "1",
+           "--no-pipeline", "--views", "8", "--width", "320", "--height", "240"]
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "refined_patches_per_sec" and d["unit"] == "patches/s"
+    assert d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] and "sample" in d["cpu_baseline"]
+    assert d["e2e"] == {"value": d["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=600)
+    assert p.returncode == 0 and p.stdout.strip() == ""
