@@ -425,6 +425,19 @@ def main():
                         "so HBM traffic is far below this figure; the kernel is bound by instruction issue (76 %) and TLD4 latency/throughput "
                         "(texture data pipe 75 %), profiles/r1_k_refine_g_v8_full_ncu_metrics.csv"}
 
+    # the limit the kernel actually runs against: its texture pipe.  One evaluation of a warp's four patches
+    # issues views x wsize rows x 3 one-channel TLD4, each ~8.3 clk of the SM's pipe whatever its active lanes
+    # (profiles/r1_tex_lane_probe.txt: 24.9 clk per warp-row of three gathers on B200)
+    try:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        clk_hz = 1.0e6 * float(clocks.get("sm_mhz") or 1965.0)
+        warp_evals = (evals_sum + P) / 4.0                               # optimiser evaluations + the final computeINCC, 4 patches per warp
+        floor_ms = 1000.0 * warp_evals * VIEWS * 7 * 24.9 / (sms * clk_hz)
+        roofline["texture_pipe_floor"] = {"floor_ms": floor_ms, "frac": floor_ms / k_ms, "clk_per_warp_row": 24.9, "sms": int(sms),
+                                          "source": "profiles/r1_tex_lane_probe.txt"}
+    except Exception as e:  # an annotation only: never fail the bench line over it
+        roofline["texture_pipe_floor"] = {"unavailable": str(e)[:120]}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config, "clocks": clocks,
