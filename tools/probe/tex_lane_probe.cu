@@ -8,10 +8,12 @@
 #include <cuda_runtime.h>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s failed: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
 
-enum { ALL32, SKIP_LANE7, SKIP_QUAD7, HALF_WARP, FOOTPRINT16, HW_BILINEAR, MIX_TLD4_LDG, LDG_ONLY, NMODES };
+enum { ALL32, SKIP_LANE7, SKIP_QUAD7, HALF_WARP, FOOTPRINT16, HW_BILINEAR, MIX_TLD4_LDG, LDG_ONLY, ONE_WINDOW, LANE_WINDOWS, NEAR4, NEAR8, NEAR16, NEAR32, NMODES };
 static const char* kNames[NMODES] = {
     "TLD4 x3, 32 lanes            ", "TLD4 x3, lanes 7/15/23/31 off", "TLD4 x3, lanes 28..31 off    ", "TLD4 x3, lanes 16..31 off    ",
-    "1 point fetch of a 16 B texel", "1 hardware-bilinear fetch    ", "rows 0-3 TLD4 x3, 4-6 LDG x4 ", "LDG x4                       "};
+    "1 point fetch of a 16 B texel", "1 hardware-bilinear fetch    ", "rows 0-3 TLD4 x3, 4-6 LDG x4 ", "LDG x4                       ",
+    "TLD4 x3, ONE window per warp ", "TLD4 x3, a window per LANE   ",
+    "TLD4 x3, 4 windows 4 px apart", "TLD4 x3, 4 windows 8 px apart", "TLD4 x3, 4 windows 16 px apart", "TLD4 x3, 4 windows 32 px apart"};
 
 template <int MODE>
 __global__ void __launch_bounds__(128, 8) k(cudaTextureObject_t gather, cudaTextureObject_t foot, cudaTextureObject_t lin, const uint32_t* pix,
@@ -20,14 +22,25 @@ __global__ void __launch_bounds__(128, 8) k(cudaTextureObject_t gather, cudaText
   // SKIP_QUAD7 packs four 7-lane groups into lanes 0..27; every other mode uses 8-lane groups
   const int g = MODE == SKIP_QUAD7 ? lane / 7 : lane >> 3, gl = MODE == SKIP_QUAD7 ? lane % 7 : lane & 7;
   const bool active = MODE == SKIP_LANE7 ? gl != 7 : MODE == SKIP_QUAD7 ? lane < 28 : MODE == HALF_WARP ? lane < 16 : true;
-  unsigned seed = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 4 + (g & 3);
+  // locality of a warp's 32 footprints: four windows (the kernel's layout), ONE window (4 rows x 8 columns of it at a time), or 32
+  unsigned seed = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 4 + (MODE == ONE_WINDOW ? 0 : (g & 3));
+  if (MODE == LANE_WINDOWS) seed = seed * 32 + lane;
+  // NEARd: the warp's four windows sit on a 2 x 2 grid d pixels apart (what a warp-local, locality-ordered hand-out would give)
+  constexpr bool kNear = MODE == NEAR4 || MODE == NEAR8 || MODE == NEAR16 || MODE == NEAR32;
+  constexpr float kD = MODE == NEAR4 ? 4.f : MODE == NEAR8 ? 8.f : MODE == NEAR16 ? 16.f : 32.f;
+  if (kNear) seed = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 4;
   float acc = 0.f;
   for (int it = 0; it < iters; ++it) {
     if (it % 150 == 0) seed = seed * 1664525u + 1013904223u;   // a window is re-sampled ~150 times (one Nelder-Mead run)
-    const float bx = 8.0f + (float)((seed >> 8) % (W - 32)), by = 8.0f + (float)((seed >> 20) % (H - 32));
+    float bx = 8.0f + (float)((seed >> 8) % (W - 96)), by = 8.0f + (float)((seed >> 20) % (H - 96));
+    if (kNear) { bx += (float)(g & 1) * kD; by += (float)(g >> 1) * kD; }
     for (int row = 0; row < 7; ++row) {
       const float jit = (float)(it & 7) * 0.05f;
-      const float x = bx + gl * 0.93f + row * 0.11f + jit, y = by + row * 0.97f + gl * 0.07f + jit;
+      // ONE_WINDOW: the warp's four groups take four rows of one window.  The sub-pixel term keeps the seven iterations' coordinates
+      // distinct: without it (first run, profiles/r1_tex_lane_probe.txt: 7.4 clk) rows 0/2/4/6 and 1/3/5 were identical requests and the
+      // compiler merged them, so that figure is 2/7 of the four-window cost and says nothing about the hardware
+      const float ry = MODE == ONE_WINDOW ? (float)((row & 1) * 4 + g) + (float)(row >> 1) * 0.13f : (float)row;
+      const float x = bx + gl * 0.93f + ry * 0.11f + jit, y = by + ry * 0.97f + gl * 0.07f + jit;
       const float lxf = truncf(x), lyf = truncf(y);
       if (!active) continue;
       if (MODE == FOOTPRINT16) {
@@ -64,7 +77,7 @@ void run(cudaTextureObject_t gather, cudaTextureObject_t foot, cudaTextureObject
   printf("%s: %7.2f ms, %5.1f clk per warp-row per SM (1.965 GHz)\n", kNames[MODE], ms, ms * 1e-3 * 1.965e9 / warp_rows);
 }
 
-int main() {
+int main(int argc, char**) {
   const int W = 6400, H = 4800;   // atlas-sized
   std::vector<uchar4> img((size_t)W * H);
   for (size_t i = 0; i < img.size(); ++i) img[i] = make_uchar4(i * 7, i * 13, i * 3, 0);
@@ -97,6 +110,14 @@ int main() {
   cudaTextureObject_t foot; CK(cudaCreateTextureObject(&foot, &frd, &ftd, nullptr));
   float* d; CK(cudaMalloc(&d, 4));
   const int iters = 2000;
+  if (argc > 1) {   // "near": only the locality sweep
+    run<ALL32>(gather, foot, lin, pix, W, H, d, iters);
+    run<NEAR4>(gather, foot, lin, pix, W, H, d, iters); run<NEAR8>(gather, foot, lin, pix, W, H, d, iters);
+    run<NEAR16>(gather, foot, lin, pix, W, H, d, iters); run<NEAR32>(gather, foot, lin, pix, W, H, d, iters);
+    run<ONE_WINDOW>(gather, foot, lin, pix, W, H, d, iters);
+    CK(cudaDeviceSynchronize());
+    return 0;
+  }
   run<ALL32>(gather, foot, lin, pix, W, H, d, iters);
   run<SKIP_LANE7>(gather, foot, lin, pix, W, H, d, iters);
   run<SKIP_QUAD7>(gather, foot, lin, pix, W, H, d, iters);
@@ -105,6 +126,8 @@ int main() {
   run<HW_BILINEAR>(gather, foot, lin, pix, W, H, d, iters);
   run<MIX_TLD4_LDG>(gather, foot, lin, pix, W, H, d, iters);
   run<LDG_ONLY>(gather, foot, lin, pix, W, H, d, iters);
+  run<ONE_WINDOW>(gather, foot, lin, pix, W, H, d, iters);
+  run<LANE_WINDOWS>(gather, foot, lin, pix, W, H, d, iters);
   CK(cudaDeviceSynchronize());
   return 0;
 }
