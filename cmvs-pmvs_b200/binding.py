@@ -17,7 +17,8 @@ LIB_PATH = os.environ.get("PMVS_B200_LIB") or os.path.join(HERE, "lib", "libpmvs
 # every symbol include/pmvs_b200.h declares
 SYMBOLS = [
     "pmvsb_create", "pmvsb_destroy", "pmvsb_last_error", "pmvsb_version", "pmvsb_upload_camera", "pmvsb_upload_image",
-    "pmvsb_set_visdata2", "pmvsb_finalize_scene", "pmvsb_set_thresholds", "pmvsb_set_optimizer", "pmvsb_image_dims",
+    "pmvsb_upload_mask", "pmvsb_set_edge", "pmvsb_set_bimages", "pmvsb_download_mask", "pmvsb_mask_gate_batch",
+    "pmvsb_remove_images_edge_batch", "pmvsb_set_visdata2", "pmvsb_finalize_scene", "pmvsb_set_thresholds", "pmvsb_set_optimizer", "pmvsb_image_dims",
     "pmvsb_download_image", "pmvsb_get_camera", "pmvsb_project_batch", "pmvsb_grab_tex_batch", "pmvsb_eval_objective_batch",
     "pmvsb_compute_incc_batch", "pmvsb_set_inccs_batch", "pmvsb_set_scales_batch", "pmvsb_pre_process_batch",
     "pmvsb_post_process_batch", "pmvsb_set_depth", "pmvsb_grid_dims", "pmvsb_store_upload", "pmvsb_build_depth_maps",
@@ -121,6 +122,42 @@ class PmvsB200:
 
     def finalize_scene(self):
         self._ck(self.lib.pmvsb_finalize_scene(self.ctx))
+
+    def upload_mask(self, index, gray, which=0):
+        """which = 0: masks/%08d.pgm (inside when 127 < v); 1: edges/%08d.pgm (inside when 1 < v); before finalize_scene."""
+        gray = np.ascontiguousarray(gray, dtype=np.uint8)
+        self._ck(self.lib.pmvsb_upload_mask(self.ctx, int(index), int(which), gray.shape[1], gray.shape[0], _vp(gray)))
+
+    def set_edge(self, threshold):
+        self._ck(self.lib.pmvsb_set_edge(self.ctx, C.c_float(threshold)))
+
+    def set_bimages(self, indexes):
+        a = np.ascontiguousarray(indexes, dtype=np.int32).reshape(-1)
+        self._ck(self.lib.pmvsb_set_bimages(self.ctx, _vp(a), len(a)))
+
+    def set_visdata2(self, index, lst):
+        a = np.ascontiguousarray(lst, dtype=np.int32).reshape(-1)
+        self._ck(self.lib.pmvsb_set_visdata2(self.ctx, int(index), _vp(a), len(a)))
+
+    def mask_map(self, index, which=0):
+        """working-level mask (0) / edge map (1) of an image as (h, w) uint8, or None when it has none"""
+        w, h = C.c_int(), C.c_int()
+        self._ck(self.lib.pmvsb_image_dims(self.ctx, int(index), self.level, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), np.uint8); present = C.c_int()
+        self._ck(self.lib.pmvsb_download_mask(self.ctx, int(index), int(which), _vp(out), C.byref(present)))
+        return out if present.value else None
+
+    def mask_gate_batch(self, coords):
+        coords = _f32(coords).reshape(-1, 4)
+        out = np.zeros(coords.shape[0], np.uint8)
+        self._ck(self.lib.pmvsb_mask_gate_batch(self.ctx, coords.shape[0], _vp(coords), _vp(out)))
+        return out
+
+    def remove_images_edge_batch(self, coords, images, nimages):
+        P, stride, coords, _, images, nimages, _ = _patch_arrays(coords, None, images, nimages)
+        im = images.copy(); n = nimages.copy()
+        self._ck(self.lib.pmvsb_remove_images_edge_batch(self.ctx, P, stride, _vp(coords), _vp(im), _vp(n)))
+        return im, n
 
     def set_thresholds(self, ncc, ncc_before):
         self._ck(self.lib.pmvsb_set_thresholds(self.ctx, C.c_float(ncc), C.c_float(ncc_before)))

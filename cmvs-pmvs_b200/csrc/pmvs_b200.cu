@@ -460,6 +460,82 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
 }
 
 
+// ---- masks / edges (CImage::_masks, _edges) -------------------------------------------------------------
+// CImage::alloc's binarisation (source/image/image.cpp:146-176): masks keep 127 < v, edge files keep 1 < v
+__global__ void k_map_binarise(const uint8_t* __restrict__ in, size_t n, int above, uint8_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = above < (int)in[i] ? 255 : 0;
+}
+// CImage::buildMask / buildEdge (image.cpp:326-393): a pixel is "in" when any of its (clamped) 2x2 parents is
+__global__ void k_map_down(const uint8_t* __restrict__ src, int sw, int sh, uint8_t* __restrict__ dst, int dw, int dh) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= dw || y >= dh) return;
+  const int y0 = 2 * y, y1 = min(sh - 1, 2 * y + 1), x0 = 2 * x, x1 = min(sw - 1, 2 * x + 1);
+  const int in = (src[(size_t)y0 * sw + x0] != 0) + (src[(size_t)y0 * sw + x1] != 0) + (src[(size_t)y1 * sw + x0] != 0) + (src[(size_t)y1 * sw + x1] != 0);
+  dst[(size_t)y * dw + x] = 0 < in ? 255 : 0;
+}
+// CImage::setEdge (image.cpp:407-471): squared central differences summed over the channels (integers, exact in f32) ...
+__global__ void k_edge_grad(const uchar4* __restrict__ pix, int w, int h, float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  float v = 0.0f;
+  if (1 <= y && y < h - 1 && 1 <= x && x < w - 1) {
+    const uchar4 r = pix[(size_t)y * w + x + 1], l = pix[(size_t)y * w + x - 1], t = pix[(size_t)(y - 1) * w + x], b = pix[(size_t)(y + 1) * w + x];
+    const int d[6] = {abs((int)r.x - (int)l.x), abs((int)b.x - (int)t.x), abs((int)r.y - (int)l.y), abs((int)b.y - (int)t.y),
+                      abs((int)r.z - (int)l.z), abs((int)b.z - (int)t.z)};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v += (float)(d[k] * d[k]);
+  }
+  out[(size_t)y * w + x] = v;
+}
+// ... smoothed by CImage::filterG (image.cpp:1013-1060): taps outside the image skipped, sum divided by the weights used;
+// sequential f32 multiply-add in tap order (-fmad=false)
+template <bool VERTICAL>
+__global__ void k_edge_smooth(const float* __restrict__ src, float* __restrict__ dst, int w, int h, const float* __restrict__ taps, int margin) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  float acc = 0.0f, denom = 0.0f;
+  for (int j = -margin; j <= margin; ++j) {
+    const int xt = VERTICAL ? x : x + j, yt = VERTICAL ? y + j : y;
+    if (xt < 0 || w <= xt || yt < 0 || h <= yt) continue;
+    const float f = __ldg(taps + j + margin);
+    acc += f * src[(size_t)yt * w + xt];
+    denom += f;
+  }
+  dst[(size_t)y * w + x] = fdiv(acc, denom);
+}
+__global__ void k_edge_threshold(const float* __restrict__ v, size_t n, float thr, uint8_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = thr < v[i] ? 255 : 0;
+}
+// the gate of postProcess / expandSub / collectCandidates for a batch of points: one warp per point
+__global__ void k_mask_gate(SceneDev s, int n, const float* __restrict__ coords, uint8_t* __restrict__ inside) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const float4 c4 = __ldg(reinterpret_cast<const float4*>(coords) + warp);
+  const float X[4] = {c4.x, c4.y, c4.z, c4.w};
+  const bool ok = mask_gate_warp(s, X, lane);
+  if (lane == 0) inside[warp] = ok ? 1 : 0;
+}
+// COptim::removeImagesEdge (source/pmvs/optim.cpp:385-396): one thread per patch, list kept in order
+__global__ void k_remove_images_edge(SceneDev s, int P, int stride, const float* __restrict__ coords, int32_t* __restrict__ images,
+                                     int32_t* __restrict__ nimages) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float4 c4 = __ldg(reinterpret_cast<const float4*>(coords) + p);
+  const float X[4] = {c4.x, c4.y, c4.z, c4.w};
+  int32_t* im = images + (size_t)p * stride;
+  const int n = min(nimages[p], stride);
+  int out = 0;
+  for (int i = 0; i < n; ++i) {
+    const int image = im[i];
+    CamDev cam;
+    load_cam(s, image, cam);
+    if (get_edge_img(s, cam, image, X)) im[out++] = image;
+  }
+  nimages[p] = out;
+}
+
 // ---- K4: visible-image-set selection (pmvs_select.cuh): one warp (= one CTA) per patch ----------------
 template <int WSIZE, int MAXV>
 __global__ void __launch_bounds__(32) k_pre_process(SceneDev s, SelectParams sp, int P, int stride, const float* __restrict__ coords,
@@ -544,6 +620,7 @@ struct HostCam {
 struct HostImage {
   std::vector<uchar4*> levels;
   std::vector<int> w, h;
+  uint8_t* maps[2] = {nullptr, nullptr};   // working-level mask / edge map (CImage::_masks[level], _edges[level]), null = none
   bool set = false;
 };
 
@@ -581,6 +658,9 @@ struct pmvsb_ctx {
   DVec<int32_t> order_bin, order_counts, order_idx;   // processing order of a refine batch (k_order_*), grow-only
   bool order_enabled = true;                // PMVSB_NO_ORDER=1: hand patches out in index order (A/B measurements)
   int32_t* d_vis_off = nullptr;
+  const unsigned char** d_map_tab[2] = {nullptr, nullptr};   // per-image pointers to the working-level masks / edges
+  std::vector<int32_t> bimages;
+  int32_t* d_bimages = nullptr;
   // filter-stage patch table
   StoreDev store;
   StoreBufs sb;                     // grow-only device arrays behind `store`
@@ -723,6 +803,7 @@ float angle_of(float d) { return (float)std::acos((double)d); }
 void fill_select(pmvsb_ctx* c) {
   SelectParams& sp = c->select;
   sp.vis_off = c->d_vis_off; sp.vis_idx = c->d_vis_idx;
+  sp.overflow = c->d_counter + 2;
   sp.cos_angle0_f = (float)std::cos((double)c->angle_threshold0);          // optim.cpp:416
   sp.sort_threshold = (float)(1.0f - std::cos(10.0 * M_PI / 180.0));      // optim.cpp:287
   sp.ncc_threshold = c->ncc_threshold; sp.ncc_threshold_before = c->ncc_threshold_before;
@@ -760,6 +841,8 @@ void fill_scene(pmvsb_ctx* c) {
   s.f32_2p23 = 0x4B000000u;
   s.dummy_pix = c->images.empty() || c->images[0].levels.empty() ? nullptr : c->images[0].levels[0];
   s.atlas = (unsigned long long)c->atlas_tex;
+  s.mask_lv = c->d_map_tab[0]; s.edge_lv = c->d_map_tab[1];
+  s.bimages = c->d_bimages; s.n_bimages = c->d_bimages ? (int)c->bimages.size() : 0;
 }
 
 // Scratch device buffers of the host-pointer entry points come from a per-context pool: cudaMalloc / cudaFree cost
@@ -1029,7 +1112,8 @@ int pmvsb_create(pmvsb_ctx** out, int device, int num_images, int num_target, in
   ctx->stream = ctx->own_stream;
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_counter, 2 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_counter, 4 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(ctx->d_counter, 0, 4 * sizeof(int));
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) { delete ctx; return PMVSB_ECUDA; }
   *out = ctx;
@@ -1042,8 +1126,11 @@ int pmvsb_destroy(pmvsb_ctx* ctx) {
   if (!ctx) return PMVSB_EINVAL;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  for (auto& im : ctx->images)
+  for (auto& im : ctx->images) {
     for (auto* p : im.levels) cudaFree(p);
+    cudaFree(im.maps[0]); cudaFree(im.maps[1]);
+  }
+  cudaFree(ctx->d_map_tab[0]); cudaFree(ctx->d_map_tab[1]); cudaFree(ctx->d_bimages);
   cudaFree(ctx->d_cams); cudaFree(ctx->d_levels); cudaFree(ctx->d_counter); cudaFree(ctx->d_vis_off); cudaFree(ctx->d_vis_idx);
   atlas_free(ctx);
   cudaFree(ctx->order_bin.p); cudaFree(ctx->order_counts.p); cudaFree(ctx->order_idx.p);
@@ -1077,6 +1164,8 @@ int pmvsb_upload_image(pmvsb_ctx* ctx, int index, int width, int height, const u
   CK(cudaSetDevice(ctx->device));
   HostImage& im = ctx->images[index];
   for (auto* p : im.levels) cudaFree(p);
+  cudaFree(im.maps[0]); cudaFree(im.maps[1]);
+  im.maps[0] = im.maps[1] = nullptr;
   im.levels.assign(ctx->nlevels, nullptr);
   im.w.assign(ctx->nlevels, 0);
   im.h.assign(ctx->nlevels, 0);
@@ -1104,6 +1193,101 @@ int pmvsb_upload_image(pmvsb_ctx* ctx, int index, int width, int height, const u
   CK(cudaStreamSynchronize(ctx->stream));
   im.set = true;
   ctx->finalized = false;
+  return PMVSB_OK;
+}
+
+// level-0 map (already 255 / 0) -> the working level through the 2x2 "any parent in" pyramid; replaces im.maps[which]
+static int map_to_working_level(pmvsb_ctx* ctx, HostImage& im, int which, uint8_t* d_level0) {
+  uint8_t* cur = d_level0;
+  for (int l = 1; l <= ctx->level; ++l) {
+    uint8_t* next = nullptr;
+    const size_t nl = (size_t)std::max(im.w[l], 1) * std::max(im.h[l], 1);
+    CK(cudaMalloc((void**)&next, nl));
+    if (im.w[l] > 0 && im.h[l] > 0) {
+      k_map_down<<<dim3((im.w[l] + 127) / 128, im.h[l]), 128, 0, ctx->stream>>>(cur, im.w[l - 1], im.h[l - 1], next, im.w[l], im.h[l]);
+      ++ctx->launches;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(cur);
+    cur = next;
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(im.maps[which]);
+  im.maps[which] = cur;
+  ctx->finalized = false;
+  return PMVSB_OK;
+}
+
+int pmvsb_upload_mask(pmvsb_ctx* ctx, int index, int which, int width, int height, const uint8_t* gray) {
+  if (!ctx || !gray || index < 0 || index >= ctx->num || (which != 0 && which != 1)) return fail(ctx, PMVSB_EINVAL, "upload_mask: bad argument");
+  g_current = ctx;
+  CK(cudaSetDevice(ctx->device));
+  HostImage& im = ctx->images[index];
+  if (!im.set) return fail(ctx, PMVSB_ESTATE, "upload_mask: upload the image first");
+  if (width != im.w[0] || height != im.h[0]) return fail(ctx, PMVSB_EINVAL, "upload_mask: the map must have the size of its image");
+  const size_t n0 = (size_t)width * height;
+  DevBuf<uint8_t> staging;
+  CK(staging.alloc(n0));
+  CK(cudaMemcpyAsync(staging.p, gray, n0, cudaMemcpyHostToDevice, ctx->stream));
+  uint8_t* level0 = nullptr;
+  CK(cudaMalloc((void**)&level0, n0));
+  k_map_binarise<<<(unsigned)((n0 + 255) / 256), 256, 0, ctx->stream>>>(staging.p, n0, which == 0 ? 127 : 1, level0);
+  ++ctx->launches;
+  return map_to_working_level(ctx, im, which, level0);
+}
+
+int pmvsb_set_edge(pmvsb_ctx* ctx, float threshold) {
+  if (!ctx) return PMVSB_EINVAL;
+  g_current = ctx;
+  CK(cudaSetDevice(ctx->device));
+  const float sigma = 3.f, sigma2 = 2.f * sigma * sigma;
+  const int margin = (int)std::floor(2 * sigma);
+  std::vector<float> taps(2 * margin + 1);
+  for (int i = -margin; i <= margin; ++i) taps[i + margin] = expf(-i * i / sigma2);   // image.cpp:446-452 (the object imports expf)
+  const float new_threshold = threshold * threshold * (2 * margin + 1) * (2 * margin + 1) / 3.0f;
+  DevBuf<float> d_taps;
+  CK(d_taps.alloc(taps.size()));
+  CK(cudaMemcpyAsync(d_taps.p, taps.data(), sizeof(float) * taps.size(), cudaMemcpyHostToDevice, ctx->stream));
+  for (int index = 0; index < ctx->num; ++index) {
+    HostImage& im = ctx->images[index];
+    if (!im.set) return fail(ctx, PMVSB_ESTATE, "set_edge: upload every image first");
+    const int w = im.w[0], h = im.h[0];
+    const size_t n0 = (size_t)w * h;
+    DevBuf<float> a, b;
+    CK(a.alloc(n0)); CK(b.alloc(n0));
+    const dim3 grid((w + 127) / 128, h);
+    k_edge_grad<<<grid, 128, 0, ctx->stream>>>(im.levels[0], w, h, a.p);
+    k_edge_smooth<true><<<grid, 128, 0, ctx->stream>>>(a.p, b.p, w, h, d_taps.p, margin);
+    k_edge_smooth<false><<<grid, 128, 0, ctx->stream>>>(b.p, a.p, w, h, d_taps.p, margin);
+    uint8_t* level0 = nullptr;
+    CK(cudaMalloc((void**)&level0, n0));
+    k_edge_threshold<<<(unsigned)((n0 + 255) / 256), 256, 0, ctx->stream>>>(a.p, n0, new_threshold, level0);
+    ctx->launches += 4;
+    const int r = map_to_working_level(ctx, im, 1, level0);
+    if (r) return r;
+  }
+  return PMVSB_OK;
+}
+
+int pmvsb_set_bimages(pmvsb_ctx* ctx, const int32_t* list, int n) {
+  if (!ctx || n < 0 || (n > 0 && !list)) return fail(ctx, PMVSB_EINVAL, "set_bimages: bad argument");
+  for (int i = 0; i < n; ++i)
+    if (list[i] < 0 || list[i] >= ctx->num) return fail(ctx, PMVSB_EINVAL, "set_bimages: image index out of range");
+  ctx->bimages.assign(list, list + n);
+  ctx->finalized = false;
+  return PMVSB_OK;
+}
+
+int pmvsb_download_mask(pmvsb_ctx* ctx, int index, int which, uint8_t* out, int* present) {
+  if (!ctx || index < 0 || index >= ctx->num || (which != 0 && which != 1) || !present) return fail(ctx, PMVSB_EINVAL, "download_mask: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const HostImage& im = ctx->images[index];
+  *present = im.maps[which] ? 1 : 0;
+  if (im.maps[which] && out) {
+    CK(cudaMemcpyAsync(out, im.maps[which], (size_t)im.w[ctx->level] * im.h[ctx->level], cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   return PMVSB_OK;
 }
 
@@ -1229,6 +1413,22 @@ int pmvsb_finalize_scene(pmvsb_ctx* ctx) {
     CK(cudaMalloc((void**)&ctx->d_vis_idx, sizeof(int32_t) * (idx.size() ? idx.size() : 1)));
     CK(cudaMemcpy(ctx->d_vis_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice));
     if (!idx.empty()) CK(cudaMemcpy(ctx->d_vis_idx, idx.data(), sizeof(int32_t) * idx.size(), cudaMemcpyHostToDevice));
+  }
+  for (int which = 0; which < 2; ++which) {
+    cudaFree(ctx->d_map_tab[which]);
+    ctx->d_map_tab[which] = nullptr;
+    std::vector<const unsigned char*> tab(ctx->num, nullptr);
+    bool any = false;
+    for (int i = 0; i < ctx->num; ++i) { tab[i] = ctx->images[i].maps[which]; any |= tab[i] != nullptr; }
+    if (!any) continue;
+    CK(cudaMalloc((void**)&ctx->d_map_tab[which], sizeof(void*) * tab.size()));
+    CK(cudaMemcpy(ctx->d_map_tab[which], tab.data(), sizeof(void*) * tab.size(), cudaMemcpyHostToDevice));
+  }
+  cudaFree(ctx->d_bimages);
+  ctx->d_bimages = nullptr;
+  if (!ctx->bimages.empty()) {
+    CK(cudaMalloc((void**)&ctx->d_bimages, sizeof(int32_t) * ctx->bimages.size()));
+    CK(cudaMemcpy(ctx->d_bimages, ctx->bimages.data(), sizeof(int32_t) * ctx->bimages.size(), cudaMemcpyHostToDevice));
   }
   fill_scene(ctx);
   fill_select(ctx);
@@ -1923,6 +2123,54 @@ int pmvsb_patch_colors_batch(pmvsb_ctx* ctx, int P, int stride, const float* coo
   return PMVSB_OK;
 }
 
+// addImages keeps at most min(stride, PMVSB_MAX_VIEWS) images per patch while the reference keeps all: a list that
+// would have grown past the capacity is an ERROR, not a truncation (call after the stream has been synchronised)
+static int check_view_overflow(pmvsb_ctx* ctx, const char* who, int stride) {
+  int flag = 0;
+  CK(cudaMemcpy(&flag, ctx->d_counter + 2, sizeof(int), cudaMemcpyDeviceToHost));
+  if (!flag) return PMVSB_OK;
+  CK(cudaMemset(ctx->d_counter + 2, 0, sizeof(int)));
+  return fail(ctx, PMVSB_ERANGE, std::string(who) + ": a patch is visible in more images than the list capacity (" +
+                                     std::to_string(std::min(stride, PMVSB_MAX_VIEWS)) + "); pass stride = number of images, at most " +
+                                     std::to_string(PMVSB_MAX_VIEWS) + " (cluster larger scenes)");
+}
+
+int pmvsb_mask_gate_batch(pmvsb_ctx* ctx, int n, const float* coords, uint8_t* inside) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (n < 0 || (n > 0 && (!coords || !inside))) return fail(ctx, PMVSB_EINVAL, "mask_gate_batch: bad argument");
+  if (n == 0) return PMVSB_OK;
+  if (!ctx->scene.mask_lv && ctx->scene.n_bimages == 0) { std::memset(inside, 1, (size_t)n); return PMVSB_OK; }   // no map, no bounding image: nothing to launch
+  DevBuf<float> dc;
+  DevBuf<uint8_t> di;
+  CK(dc.alloc((size_t)4 * n)); CK(di.alloc(n));
+  CK(cudaMemcpyAsync(dc.p, coords, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+  k_mask_gate<<<(n + 3) / 4, 128, 0, ctx->stream>>>(ctx->scene, n, dc.p, di.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(inside, di.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_remove_images_edge_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, int32_t* images, int32_t* nimages) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (!nimages) return fail(ctx, PMVSB_EINVAL, "remove_images_edge_batch: null pointer");
+  if (P == 0) return PMVSB_OK;
+  PatchStage st;
+  r = stage_patches(ctx, st, P, stride, coords, nullptr, images, nimages, nullptr);
+  if (r) return r;
+  if (!ctx->scene.edge_lv) return PMVSB_OK;   // getEdge == 1 everywhere: the lists stay as they are
+  k_remove_images_edge<<<(P + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, P, stride, st.coords.p, st.images.p, st.nimages.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(images, st.images.p, sizeof(int32_t) * (size_t)stride * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(nimages, st.nimages.p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
 int pmvsb_pre_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals, int32_t* images,
                             int32_t* nimages, float* dscale, float* ascale, int32_t* verdict) {
   int r = check_ready(ctx);
@@ -1947,7 +2195,7 @@ int pmvsb_pre_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coor
   CK(cudaMemcpyAsync(ascale, da.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(verdict, dv.p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  return PMVSB_OK;
+  return check_view_overflow(ctx, "pre/post_process_batch", stride);
 }
 
 int pmvsb_post_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals, const float* ncc,
@@ -1977,7 +2225,7 @@ int pmvsb_post_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coo
   CK(cudaMemcpyAsync(tmp, dt.p, sizeof(float) * P, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(verdict, dv.p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  return PMVSB_OK;
+  return check_view_overflow(ctx, "pre/post_process_batch", stride);
 }
 
 int pmvsb_refine_batch_dev(pmvsb_ctx* ctx, int P, int stride, float* d_coords, float* d_normals, const int32_t* d_images,
@@ -2131,10 +2379,19 @@ int pmvsb_detect_features(pmvsb_ctx* ctx, int index, int gspeedup, int cap, floa
   CK(cudaMemcpyAsync(d_taps.p, flat.data(), sizeof(float) * flat.size(), cudaMemcpyHostToDevice, ctx->stream));
   const dim3 cb(128), cg3((w + 127) / 128, h, 3), cg1((w + 127) / 128, h, 1);
   const int tb1 = 256, gb1 = (n + 255) / 256;
+  // the detectors' _mask: the image's mask and / or edge map at the working level (detectFeatures.cpp:88-92)
+  DevBuf<unsigned char> maskbuf;
+  const unsigned char* fmask = nullptr;
+  if (hi.maps[0] || hi.maps[1]) {
+    CK(maskbuf.alloc(n));
+    k_feat_mask<<<gb1, tb1, 0, ctx->stream>>>(hi.maps[0], hi.maps[1], n, maskbuf.p);
+    ++ctx->launches;
+    fmask = maskbuf.p;
+  }
   auto conv = [&](bool vertical, const float* src, float* dst, int filt, dim3 grid) {
     const int nt = (int)filters[filt].size();
-    if (vertical) k_feat_conv<true><<<grid, cb, 0, ctx->stream>>>(src, dst, w, h, d_taps.p + foff[filt], nt);
-    else k_feat_conv<false><<<grid, cb, 0, ctx->stream>>>(src, dst, w, h, d_taps.p + foff[filt], nt);
+    if (vertical) k_feat_conv<true><<<grid, cb, 0, ctx->stream>>>(src, dst, w, h, d_taps.p + foff[filt], nt, fmask);
+    else k_feat_conv<false><<<grid, cb, 0, ctx->stream>>>(src, dst, w, h, d_taps.p + foff[filt], nt, fmask);
     ++ctx->launches;
   };
   std::vector<FeatPoint> feats;
@@ -2162,10 +2419,10 @@ int pmvsb_detect_features(pmvsb_ctx* ctx, int index, int gspeedup, int cap, floa
   // ---- Harris (harris.cpp:112-137, 60-110, 139-172)
   conv(false, img.p, ta.p, 0, cg3); conv(true, ta.p, tb.p, 1, cg3);    // tb = dI/dx
   conv(false, img.p, ta.p, 1, cg3); conv(true, ta.p, tc.p, 0, cg3);    // tc = dI/dy
-  k_feat_products<<<gb1, tb1, 0, ctx->stream>>>(tb.p, tc.p, n, ta.p);   // ta = (xx, yy, xy)
+  k_feat_products<<<gb1, tb1, 0, ctx->stream>>>(tb.p, tc.p, n, ta.p, fmask);   // ta = (xx, yy, xy)
   ++ctx->launches;
   conv(false, ta.p, tb.p, 2, cg3); conv(true, tb.p, ta.p, 2, cg3);
-  k_feat_harris_response<<<gb1, tb1, 0, ctx->stream>>>(ta.p, n, tb.p);
+  k_feat_harris_response<<<gb1, tb1, 0, ctx->stream>>>(ta.p, n, tb.p, fmask);
   k_feat_nms<<<cg1, cb, 0, ctx->stream>>>(tb.p, w, h, tc.p);
   {
     const int margin = (2 * (int)std::ceil(2 * 4.0f) + 1) / 2;   // _gaussD.size() / 2

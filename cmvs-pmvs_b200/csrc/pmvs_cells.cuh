@@ -171,7 +171,7 @@ __global__ void k_store_vimages(SceneDev s, StoreDev st, int additive, int32_t* 
         project(cam, X, ic);
         ix = ((int)floorf(ic[0] + 0.5f)) / s.csize;
         iy = ((int)floorf(ic[1] + 0.5f)) / s.csize;
-        ok = is_visible(s, st, cam, X, N, image, ix, iy, 0.5f) != 0;
+        ok = is_visible(s, st, cam, X, N, image, ix, iy, 0.5f) != 0 && get_edge_img(s, cam, image, X) != 0;   // patchOrganizerS.cpp:444-445
       }
     }
     const unsigned m = __ballot_sync(kFull, ok);
@@ -332,7 +332,10 @@ __global__ void k_find_empty_blocks(SceneDev s, StoreDev st, int n, const int32_
     const float len = fsqrt(fx * fx + fy * fy);
     if (len < rlow || rhigh < len) return;
     fx = fdiv(fx, len); fy = fdiv(fy, len);
-    float angle = atan2f(fy, fx);
+    // the reference's unqualified atan2 binds to the DOUBLE libm entry (nm -u expand.o: atan2), rounded to float on
+    // assignment; a child that refinement left where findEmptyBlocks put it sits exactly on a sector boundary of its
+    // parent, so the last ulp decides the sector.  CUDA's double atan2 (<= 2 ulp in double) rounds to the same float.
+    float angle = (float)atan2((double)fy, (double)fx);
     if (angle < 0.0f) angle = (float)((double)angle + 2.0 * 3.14159265358979323846);
     const float findex = (float)((double)angle / (2.0 * 3.14159265358979323846 / 6.0));
     const int lindex = (int)floorf(findex), hindex = lindex + 1;

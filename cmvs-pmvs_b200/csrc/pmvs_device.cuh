@@ -53,6 +53,12 @@ struct SceneDev {
   const uchar4* dummy_pix; // any valid level (image 0, level 0): idle lanes sample texel (0,0) of it instead of branching
   unsigned long long atlas; // cudaTextureObject_t over ONE block-linear RGBA8 array holding every (image, level): point filter,
                             // normalized-float reads, unnormalized coordinates, gather enabled; 0 = not built (does not fit)
+  // CImage::_masks / _edges at the working level (255 in, 0 out), one pointer per image; an image without a map has a
+  // null entry, a scene without any has a null table (the common case: every gate below is then a uniform early-out)
+  const unsigned char* const* mask_lv;
+  const unsigned char* const* edge_lv;
+  const int32_t* bimages;   // SOption::_bindexes (bounding images, option useBound)
+  int n_bimages;
 };
 
 // IEEE f32 division / square root.  With PMVS_NOINLINE_DIV the ~13-instruction expansions (60 of them in the
@@ -121,6 +127,52 @@ __device__ __forceinline__ void project(const CamDev& cam, const float* X, float
   const float lim = 2147483648.0f;  // (float)(INT_MAX - 3.0f) and -(float)(INT_MIN + 3.0f)
   o[0] = smax(-lim, smin(lim, o[0]));
   o[1] = smax(-lim, smin(lim, o[1]));
+}
+
+// CPhoto::getMask(coord, level) (include/image/photo.hpp:44-49 -> image.hpp:540-565): 1 without a map, 1 outside the image
+__device__ __forceinline__ int get_mask_img(const SceneDev& s, int image, const float* X) {
+  const unsigned char* m = s.mask_lv ? s.mask_lv[image] : nullptr;
+  if (!m) return 1;
+  CamDev cam;
+  load_cam(s, image, cam);
+  float ic[3];
+  project(cam, X, ic);
+  const LevelDev lv = s.levels[image * s.nlevels + s.level];
+  const int ix = (int)floorf(ic[0] + 0.5f), iy = (int)floorf(ic[1] + 0.5f);
+  if (ix < 0 || lv.w <= ix || iy < 0 || lv.h <= iy) return 1;
+  return m[(size_t)iy * lv.w + ix];
+}
+// CPhoto::getEdge(coord, level) (photo.hpp:51-59 -> image.hpp:567-592): 1 without a map, 0 outside [0, w-1) x [0, h-1)
+__device__ __forceinline__ int get_edge_img(const SceneDev& s, const CamDev& cam, int image, const float* X) {
+  const unsigned char* m = s.edge_lv ? s.edge_lv[image] : nullptr;
+  if (!m) return 1;
+  float ic[3];
+  project(cam, X, ic);
+  const LevelDev lv = s.levels[image * s.nlevels + s.level];
+  if (ic[0] < 0.0f || (float)(lv.w - 1) <= ic[0] || ic[1] < 0.0f || (float)(lv.h - 1) <= ic[1]) return 0;
+  const int ix = (int)floorf(ic[0] + 0.5f), iy = (int)floorf(ic[1] + 0.5f);
+  if (ix < 0 || lv.w <= ix || iy < 0 || lv.h <= iy) return 1;
+  return m[(size_t)iy * lv.w + ix];
+}
+// one term of CFindMatch::insideBimages (source/pmvs/findMatch.cpp:109-118)
+__device__ __forceinline__ int inside_bimage(const SceneDev& s, int image, const float* X) {
+  CamDev cam;
+  load_cam(s, image, cam);
+  float ic[3];
+  project(cam, X, ic);
+  const LevelDev lv = s.levels[image * s.nlevels + s.level];
+  return !(ic[0] < 0.0f || (float)(lv.w - 1) < ic[0] || ic[1] < 0.0f || (float)(lv.h - 1) < ic[1]);
+}
+// `getMask(coord, level) == 0 || insideBimages(coord) == 0` of postProcess / expandSub / collectCandidates
+// (optim.cpp:153, expand.cpp:212, seed.cpp:314): CPhotoSetS::getMask walks EVERY image (photoSetS.hpp:109-116).
+// Warp-collective; true = the point passes.
+__device__ __forceinline__ bool mask_gate_warp(const SceneDev& s, const float* X, int lane) {
+  if (!s.mask_lv && s.n_bimages == 0) return true;
+  bool bad = false;
+  if (s.mask_lv)
+    for (int i = lane; i < s.num; i += 32) bad |= get_mask_img(s, i, X) == 0;
+  for (int i = lane; i < s.n_bimages; i += 32) bad |= inside_bimage(s, s.bimages[i], X) == 0;
+  return !__any_sync(kFull, bad);
 }
 
 // COptim::getUnit (optim.cpp:1116-1124): 2.0 * |X - C| * 2^level / ipscale, evaluated in double

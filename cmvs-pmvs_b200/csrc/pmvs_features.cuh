@@ -22,28 +22,41 @@ __global__ void k_feat_planes(LevelDev lv, float* __restrict__ planes) {
   planes[2 * n + i] = fdiv((float)(int)p.z, 255.0f);
 }
 
-// CDetector::convolveX / convolveY with an empty mask (detector.hpp:26-94); blockIdx.z selects the plane
+// CDetector::convolveX / convolveY, the overloads that take a mask (detector.hpp:26-94: coordinates clamp to the image;
+// a masked-out pixel yields 0 and masked-out taps are skipped); mask = null for an image without mask and edge map.
+// blockIdx.z selects the plane.
 template <bool VERTICAL>
-__global__ void k_feat_conv(const float* __restrict__ src, float* __restrict__ dst, int w, int h, const float* __restrict__ taps, int ntaps) {
+__global__ void k_feat_conv(const float* __restrict__ src, float* __restrict__ dst, int w, int h, const float* __restrict__ taps, int ntaps,
+                            const unsigned char* __restrict__ mask) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= w) return;
   const size_t plane = (size_t)blockIdx.z * w * h;
   const float* s = src + plane;
   const int margin = ntaps / 2;
   float acc = 0.0f;
-  for (int j = 0; j < ntaps; ++j) {
-    int xt = x, yt = y;
-    if (VERTICAL) { yt = y + j - margin; yt = yt < 0 ? 0 : (h <= yt ? h - 1 : yt); }
-    else { xt = x + j - margin; xt = xt < 0 ? 0 : (w <= xt ? w - 1 : xt); }
-    acc += __ldg(taps + j) * __ldg(s + (size_t)yt * w + xt);
-  }
+  if (!mask || mask[(size_t)y * w + x] != 0)
+    for (int j = 0; j < ntaps; ++j) {
+      int xt = x, yt = y;
+      if (VERTICAL) { yt = y + j - margin; yt = yt < 0 ? 0 : (h <= yt ? h - 1 : yt); }
+      else { xt = x + j - margin; xt = xt < 0 ? 0 : (w <= xt ? w - 1 : xt); }
+      if (mask && mask[(size_t)yt * w + xt] == 0) continue;
+      acc += __ldg(taps + j) * __ldg(s + (size_t)yt * w + xt);
+    }
   dst[plane + (size_t)y * w + x] = acc;
+}
+// CHarris::init / CDifferenceOfGaussians::init (harris.cpp:22-43, dog.cpp:240-261): mask AND edge where both exist
+__global__ void k_feat_mask(const unsigned char* __restrict__ a, const unsigned char* __restrict__ b, int n, unsigned char* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = !a ? b[i] : (!b ? a[i] : ((a[i] && b[i]) ? 255 : 0));
 }
 
 // CHarris::preprocess2's products (harris.cpp:60-79): Vec3f * Vec3f summed over the channels left to right
-__global__ void k_feat_products(const float* __restrict__ dx, const float* __restrict__ dy, int n, float* __restrict__ out) {
+__global__ void k_feat_products(const float* __restrict__ dx, const float* __restrict__ dy, int n, float* __restrict__ out,
+                                const unsigned char* __restrict__ mask) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (mask && mask[i] == 0) { out[i] = 0.0f; out[n + i] = 0.0f; out[2 * n + i] = 0.0f; return; }   // harris.cpp:74
   const float a0 = dx[i], a1 = dx[n + i], a2 = dx[2 * n + i];
   const float b0 = dy[i], b1 = dy[n + i], b2 = dy[2 * n + i];
   out[i] = 0.0f + ((a0 * a0 + a1 * a1) + a2 * a2);
@@ -52,9 +65,10 @@ __global__ void k_feat_products(const float* __restrict__ dx, const float* __res
 }
 
 // CHarris::setResponse (harris.cpp:139-172): D - 0.06 tr^2 in double, then the 4-neighbour non-maximum suppression
-__global__ void k_feat_harris_response(const float* __restrict__ m, int n, float* __restrict__ resp) {
+__global__ void k_feat_harris_response(const float* __restrict__ m, int n, float* __restrict__ resp, const unsigned char* __restrict__ mask) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (mask && mask[i] == 0) { resp[i] = 0.0f; return; }   // harris.cpp:147
   const float xx = m[i], yy = m[n + i], xy = m[2 * n + i];
   const float D = xx * yy - xy * xy;
   const float tr = xx + yy;

@@ -118,7 +118,7 @@ __global__ void k_set_vimages(SceneDev s, StoreDev st, int vcap, int32_t* __rest
         project(cam, X, ic);
         ix = ((int)floorf(ic[0] + 0.5f)) / s.csize;
         iy = ((int)floorf(ic[1] + 0.5f)) / s.csize;
-        ok = is_visible(s, st, cam, X, N, image, ix, iy, 0.5f) != 0;
+        ok = is_visible(s, st, cam, X, N, image, ix, iy, 0.5f) != 0 && get_edge_img(s, cam, image, X) != 0;   // patchOrganizerS.cpp:444-445
       }
     }
     const unsigned m = __ballot_sync(kFull, ok);
@@ -163,7 +163,7 @@ __global__ void k_set_vimages_batch(SceneDev s, StoreDev st, int P, int stride, 
         project(cam, X, ic);
         ix = ((int)floorf(ic[0] + 0.5f)) / s.csize;
         iy = ((int)floorf(ic[1] + 0.5f)) / s.csize;
-        ok = is_visible(s, st, cam, X, N, image, ix, iy, 0.5f) != 0;
+        ok = is_visible(s, st, cam, X, N, image, ix, iy, 0.5f) != 0 && get_edge_img(s, cam, image, X) != 0;   // patchOrganizerS.cpp:444-445
       }
     }
     const unsigned m = __ballot_sync(kFull, ok);

@@ -23,6 +23,7 @@ struct SelectParams {          // host-tabulated constants (same libm as the ref
   float sort_threshold;        // (float)(1.0f - cos(10 deg)) (optim.cpp:287)
   float angle_dot_lo, angle_dot_hi;  // checkAngles: minAngle < (float)acos(d) < maxAngle  <=>  lo <= d <= hi
   float ncc_threshold, ncc_threshold_before;
+  int* overflow;               // set when addImages found more images than the list capacity holds (reported, never silent)
 };
 
 // per-warp scratch in shared memory
@@ -110,7 +111,7 @@ __device__ __forceinline__ int warp_compact(Scratch& sc, int n, int lane, Pred k
   return out;
 }
 
-// COptim::addImages (optim.cpp:398-444); no edge images in scope (getEdge == 1 when no edge map exists)
+// COptim::addImages (optim.cpp:398-444)
 template <class Scratch>
 __device__ __forceinline__ int sel_add_images(const SceneDev& s, const SelectParams& sp, Scratch& sc, int n, int cap, int lane,
                                               const float* coord, const float* normal) {
@@ -131,7 +132,7 @@ __device__ __forceinline__ int sel_add_images(const SceneDev& s, const SelectPar
         project(cam, coord, ic);
         const LevelDev lv = s.levels[im * s.nlevels + s.level];
         const bool outside = ic[0] < 0.0f || (float)(lv.w - 1) <= ic[0] || ic[1] < 0.0f || (float)(lv.h - 1) <= ic[1];
-        if (!outside) {
+        if (!outside && get_edge_img(s, cam, im, coord)) {
           float ray[4] = {cam.centre[0] - coord[0], cam.centre[1] - coord[1], cam.centre[2] - coord[2], cam.centre[3] - coord[3]};
           unitize4(ray);
           ok = sp.cos_angle0_f <= dot4(ray, normal);
@@ -143,6 +144,7 @@ __device__ __forceinline__ int sel_add_images(const SceneDev& s, const SelectPar
     const unsigned m = __ballot_sync(kFull, ok);
     const int pos = n + __popc(m & ((1u << lane) - 1u));
     if (ok && pos < cap) sc.images[pos] = im;
+    if (ok && pos >= cap) *sp.overflow = 1;   // the reference has no cap (optim.cpp:439): the entry point turns this into an error
     n = min(cap, n + __popc(m));
     __syncwarp();
   }
@@ -391,12 +393,13 @@ __device__ __forceinline__ int sel_pre_process(const SceneDev& s, const SelectPa
   return 0;
 }
 
-// COptim::postProcess (optim.cpp:150-190) at _depth == 0: no masks / bounding images in scope (getMask == 1).
+// COptim::postProcess (optim.cpp:150-190) up to _tmp = score2 (setVImagesVGrids and check are separate calls).
 template <int WSIZE, int MAXV>
 __device__ __forceinline__ int sel_post_process(const SceneDev& s, const SelectParams& sp, SelScratch<WSIZE, MAXV>& sc, int& n, int cap, int lane,
                                                 const float* coord, const float* normal, float ncc, int32_t* grids, int& timages, float& tmp) {
   timages = 0; tmp = 0.0f;
   if (n < s.min_image_num) return 1;
+  if (!mask_gate_warp(s, coord, lane)) return 1;   // optim.cpp:153
   n = sel_add_images(s, sp, sc, n, cap, lane, coord, normal);
   n = sel_constraint_images<WSIZE>(s, sc, n, lane, coord, normal, sp.ncc_threshold);
   n = sel_filter_by_angle(s, sc, n, lane, coord, normal);

@@ -9,6 +9,7 @@
 // Differences by construction: candidates of one wave are generated from one snapshot of the grids and are
 // evaluated together; they are committed in priority order with the cell rules re-checked at commit time.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -54,6 +55,8 @@ void Pipeline::project(int image, const float* X, float* o) const {   // include
   if (o[2] <= 0.0f) { o[0] = -65535.0f; o[1] = -65535.0f; o[2] = -1.0f; return; }
   const float z = o[2];
   o[0] /= z; o[1] /= z; o[2] /= z;
+  o[0] = std::max((float)(INT_MIN + 3.0f), std::min((float)(INT_MAX - 3.0f), o[0]));
+  o[1] = std::max((float)(INT_MIN + 3.0f), std::min((float)(INT_MAX - 3.0f), o[1]));
 }
 
 float Pipeline::get_unit(int image, const float* X) const {          // optim.cpp:1116-1124
@@ -62,6 +65,45 @@ float Pipeline::get_unit(int image, const float* X) const {          // optim.cp
   const float fz = norm4(d);
   if (c.ipscale == 0.0f) return 1.0f;
   return (float)(2.0 * fz * (1 << opt_.level) / c.ipscale);
+}
+
+int Pipeline::get_mask(int image, int ix, int iy) const {   // include/image/image.hpp:553-565
+  const std::vector<unsigned char>& m = masks_[image];
+  if (m.empty()) return 1;
+  if (ix < 0 || lw_[image] <= ix || iy < 0 || lh_[image] <= iy) return 1;
+  return m[(size_t)iy * lw_[image] + ix];
+}
+
+int Pipeline::get_mask(int image, const float* X) const {   // include/image/photo.hpp:44-49, image.hpp:540-551
+  if (masks_[image].empty()) return 1;
+  float ic[3];
+  project(image, X, ic);
+  return get_mask(image, (int)std::floor(ic[0] + 0.5f), (int)std::floor(ic[1] + 0.5f));
+}
+
+int Pipeline::get_edge(int image, const float* X) const {   // photo.hpp:51-59, image.hpp:567-592
+  const std::vector<unsigned char>& m = edges_[image];
+  if (m.empty()) return 1;
+  float ic[3];
+  project(image, X, ic);
+  if (ic[0] < 0 || lw_[image] - 1 <= ic[0] || ic[1] < 0 || lh_[image] - 1 <= ic[1]) return 0;
+  const int ix = (int)std::floor(ic[0] + 0.5f), iy = (int)std::floor(ic[1] + 0.5f);
+  if (ix < 0 || lw_[image] <= ix || iy < 0 || lh_[image] <= iy) return 1;
+  return m[(size_t)iy * lw_[image] + ix];
+}
+
+// `_pss.getMask(coord, _level) == 0 || insideBimages(coord) == 0` (expand.cpp:212, seed.cpp:314; include/image/photoSetS.hpp:109-116,
+// findMatch.cpp:109-118): true = the point passes
+bool Pipeline::mask_gate(const float* X) const {
+  if (any_mask_)
+    for (int i = 0; i < num_; ++i)
+      if (get_mask(i, X) == 0) return false;
+  for (int index : opt_.bindexes) {
+    float ic[3];
+    project(index, X, ic);
+    if (ic[0] < 0.0 || lw_[index] - 1 < ic[0] || ic[1] < 0.0 || lh_[index] - 1 < ic[1]) return false;
+  }
+  return true;
 }
 
 bool Pipeline::is_neighbor(const Patch& l, const Patch& r, float hunit, float thr, float radius) const {   // findMatch.cpp:125-185
@@ -413,6 +455,7 @@ void Pipeline::seed_round() {
     }
   }
   auto can_add = [&](int image, int x, int y) {   // seed.cpp:325-338
+    if (!get_mask(image, opt_.csize * x, opt_.csize * y)) return false;
     if (tnum_ <= image) return true;
     const size_t c = (size_t)y * grids_[image].gw + x;
     if (!grids_[image].pg[c].empty()) return false;
@@ -512,6 +555,7 @@ void Pipeline::seed_round() {
                 for (int i3 = 0; i3 < 3; ++i3) h.coord[i3] = (float)(inv[i3][0] * v[0] + inv[i3][1] * v[1] + inv[i3][2] * v[2]);
                 h.coord[3] = 1.0f;
                 if (dot4(cams_[index].P[2], h.coord) <= 0.0f) continue;
+                if (!mask_gate(h.coord)) continue;   // seed.cpp:314
                 float d0[4], d1[4];
                 for (int c4 = 0; c4 < 4; ++c4) { d0[c4] = h.coord[c4] - cams_[index].centre[c4]; d1[c4] = h.coord[c4] - cams_[other].centre[c4]; }
                 h.resp = std::fabs(norm4(d0) - norm4(d1));
@@ -674,7 +718,15 @@ void Pipeline::expand_round() {
           if (0 <= ix && ix < grids_[im].gw && 0 <= iy && iy < grids_[im].gh) { c.patch.images.push_back(im); c.patch.grids.push_back({ix, iy}); }
         }
         if (c.patch.images.empty()) { patches_[id].dflag |= (unsigned char)(1 << i); continue; }
+        if (!mask_gate(c.patch.coord)) { patches_[id].dflag |= (unsigned char)(1 << i); continue; }   // expand.cpp:212
         if (check_counts(c.patch)) { patches_[id].dflag |= (unsigned char)(1 << i); continue; }
+        if (any_edge_) {   // COptim::removeImagesEdge (optim.cpp:385-396, expand.cpp:219)
+          size_t out = 0;
+          for (size_t k = 0; k < c.patch.images.size(); ++k)
+            if (get_edge(c.patch.images[k], c.patch.coord)) { c.patch.images[out] = c.patch.images[k]; c.patch.grids[out] = c.patch.grids[k]; ++out; }
+          c.patch.images.resize(out); c.patch.grids.resize(out);
+          if (out == 0) { patches_[id].dflag |= (unsigned char)(1 << i); continue; }
+        }
         mine.push_back(c);
       }
     }, 256);

@@ -111,6 +111,11 @@ class Pipeline {
   float get_unit(int image, const float* X) const;
   bool is_neighbor(const Patch& l, const Patch& r, float hunit, float thr, float radius) const;   // radius < 0: no radius test
   bool is_neighbor(const Patch& l, const Patch& r, float thr) const;
+  // masks / edges / bounding images (CImage::getMask, CPhoto::getMask / getEdge, CFindMatch::insideBimages)
+  int get_mask(int image, int ix, int iy) const;          // include/image/image.hpp:553-565 at the working level
+  int get_mask(int image, const float* X) const;          // include/image/photo.hpp:44-49
+  int get_edge(int image, const float* X) const;          // photo.hpp:51-59
+  bool mask_gate(const float* X) const;                   // getMask(coord, level) != 0 && insideBimages(coord) != 0
   // ---- bookkeeping
   int add_patch(Patch&& p);                 // CPatchOrganizerS::addPatch (takes the lists over)
   void remove_patch(int id);                // CPatchOrganizerS::removePatch
@@ -147,6 +152,8 @@ class Pipeline {
   std::vector<int> image_ids_;              // file numbers, targets first
   std::vector<Camera> cams_;
   std::vector<int> lw_, lh_;                // image size at the working level
+  std::vector<std::vector<unsigned char>> masks_, edges_;   // working-level maps as the GPU built them (empty = none)
+  bool any_mask_ = false, any_edge_ = false;
   std::vector<std::vector<double>> P0_;     // level-`level` projection in double for the epipolar search
   std::vector<std::vector<float>> distances_;
   std::vector<std::vector<Feature>> features_;

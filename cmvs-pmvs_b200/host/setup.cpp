@@ -195,6 +195,41 @@ static bool read_ppm(const std::string& path, std::vector<unsigned char>& rgb, i
   return got == rgb.size();
 }
 
+// masks/%08d.{pgm,pbm}, edges/%08d.{pgm,pbm} (CImage::completeName + readPGMImage / readPBMImage,
+// source/image/image.cpp:38-75, 507-567, 619-668): binary P5, or binary P4 read as ONE continuous bit stream (the reference does
+// not skip the row padding) with a set bit = outside (0) and a clear bit = inside (255).
+static bool read_gray_map(const std::string& base, std::vector<unsigned char>& out, int& w, int& h) {
+  for (const char* ext : {".pgm", ".pbm"}) {
+    std::ifstream in((base + ext).c_str(), std::ios::binary);
+    if (!in.is_open()) continue;
+    const bool pgm = ext[2] == 'g';
+    std::string header;
+    in >> header;
+    in.get();
+    if (header != (pgm ? "P5" : "P4")) { std::cerr << "Only accept binary " << (pgm ? "pgm" : "pbm") << " format: " << base << ext << std::endl; return false; }
+    while (in.peek() == '#') { std::string line; std::getline(in, line); }
+    int maxv = 255;
+    in >> w >> h;
+    if (pgm) in >> maxv;
+    in.get();
+    if (in.fail() || w < 1 || h < 1) return false;
+    out.assign((size_t)w * h, 0);
+    if (pgm) {
+      in.read(reinterpret_cast<char*>(out.data()), (std::streamsize)out.size());
+      if ((size_t)in.gcount() != out.size()) fatal("Truncated map file: " + base + ext);
+    } else {
+      size_t count = 0;
+      unsigned char byte = 0;
+      while (count < out.size()) {
+        if (!in.read(reinterpret_cast<char*>(&byte), 1)) fatal("Truncated map file: " + base + ext);
+        for (int j = 0; j < 8 && count < out.size(); ++j, byte = (unsigned char)(byte << 1)) out[count++] = (byte >> 7) ? 0 : 255;
+      }
+    }
+    return true;
+  }
+  return false;
+}
+
 void Pipeline::die(const std::string& where) const {
   std::cerr << where << ": " << (gpu_ ? pmvsb_last_error(gpu_) : "no GPU context") << std::endl;
   std::exit(1);
@@ -218,8 +253,14 @@ Pipeline::~Pipeline() {
 void Pipeline::load() {
   Tick tk(this, "load.total");
   if (num_ == 0 || tnum_ == 0) fatal("No target images");
+  if (num_ > PMVSB_MAX_VIEWS)
+    std::cerr << "pmvs-b200: " << num_ << " images in one option file; a patch may list at most " << PMVSB_MAX_VIEWS
+              << " visible images (the run stops with an error if one needs more -- cluster the scene with CMVS / genOption)" << std::endl;
   // the files are read by the CPU threads while this thread brings the CUDA context up
-  struct Loaded { float P[12]; std::vector<unsigned char> rgb; int w = 0, h = 0; std::string error; };
+  struct Loaded {
+    float P[12]; std::vector<unsigned char> rgb; int w = 0, h = 0; std::string error;
+    std::vector<unsigned char> map[2]; int mw[2] = {0, 0}, mh[2] = {0, 0};   // masks/ and edges/ files, when present
+  };
   std::vector<Loaded> loaded(num_);
   std::thread reader([&]() {
     parallel_for(num_, threads_, [&](int i) {
@@ -230,6 +271,7 @@ void Pipeline::load() {
         std::snprintf(name, sizeof(name), "%stxt/%04d.txt", opt_.prefix.c_str(), image_ids_[i]);
         if (!read_camera(name, L.P)) { L.error = std::string("Cannot read camera: ") + name; return; }
       }
+      bool four_digits = false;
       std::snprintf(name, sizeof(name), "%svisualize/%08d.ppm", opt_.prefix.c_str(), image_ids_[i]);
       if (!read_ppm(name, L.rgb, L.w, L.h)) {
         std::snprintf(name, sizeof(name), "%svisualize/%04d.ppm", opt_.prefix.c_str(), image_ids_[i]);
@@ -237,7 +279,14 @@ void Pipeline::load() {
           std::snprintf(name, sizeof(name), "%svisualize/%08d.jpg", opt_.prefix.c_str(), image_ids_[i]);
           if (std::ifstream(name)) L.error = std::string("JPEG input is not supported by pmvs-b200 (convert to binary PPM): ") + name;
           else L.error = "Unsupported iamge format found. Stop allocation: " + std::string(name);
+          return;
         }
+        four_digits = true;
+      }
+      for (int which = 0; which < 2; ++which) {   // photoSetS.cpp:43-49, 60-62: same digit count as the image name
+        std::snprintf(name, sizeof(name), four_digits ? "%s%s/%04d" : "%s%s/%08d", opt_.prefix.c_str(), which == 0 ? "masks" : "edges", image_ids_[i]);
+        if (read_gray_map(name, L.map[which], L.mw[which], L.mh[which]) && (L.mw[which] != L.w || L.mh[which] != L.h))
+          L.error = std::string(which == 0 ? "Mask" : "Edge map") + " and image differ in size: " + name;
       }
     }, 1);
   });
@@ -262,12 +311,32 @@ void Pipeline::load() {
     if (!L.error.empty()) fatal(L.error);
     if (pmvsb_upload_camera(gpu_, i, L.P)) die("upload_camera");
     if (pmvsb_upload_image(gpu_, i, L.w, L.h, L.rgb.data())) die("upload_image");
+    for (int which = 0; which < 2; ++which)
+      if (!L.map[which].empty()) {
+        std::cerr << (which == 0 ? "Read mask: " : "Read edge: ") << image_ids_[i] << std::endl;
+        if (pmvsb_upload_mask(gpu_, i, which, L.mw[which], L.mh[which], L.map[which].data())) die("upload_mask");
+        std::vector<unsigned char>().swap(L.map[which]);
+      }
     if (pmvsb_set_visdata2(gpu_, i, opt_.visdata2[i].data(), (int)opt_.visdata2[i].size())) die("set_visdata2");
     std::vector<unsigned char>().swap(L.rgb);
     std::cerr << '*' << std::flush;
   }
   std::cerr << std::endl;
+  if (opt_.setEdge != 0.0f && pmvsb_set_edge(gpu_, opt_.setEdge)) die("set_edge");   // findMatch.cpp:74-76
+  if (!opt_.bindexes.empty() && pmvsb_set_bimages(gpu_, opt_.bindexes.data(), (int)opt_.bindexes.size())) die("set_bimages");
   if (pmvsb_finalize_scene(gpu_)) die("finalize_scene");
+  masks_.assign(num_, {}); edges_.assign(num_, {});
+  for (int i = 0; i < num_; ++i)
+    for (int which = 0; which < 2; ++which) {
+      int present = 0, w = 0, h = 0;
+      if (pmvsb_download_mask(gpu_, i, which, nullptr, &present)) die("download_mask");
+      if (!present) continue;
+      if (pmvsb_image_dims(gpu_, i, opt_.level, &w, &h)) die("image_dims");
+      std::vector<unsigned char>& m = which == 0 ? masks_[i] : edges_[i];
+      m.resize((size_t)w * h);
+      if (pmvsb_download_mask(gpu_, i, which, m.data(), &present)) die("download_mask");
+      (which == 0 ? any_mask_ : any_edge_) = true;
+    }
   grids_.resize(num_);
   P0_.resize(num_);
   for (int i = 0; i < num_; ++i) {

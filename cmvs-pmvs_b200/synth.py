@@ -330,6 +330,9 @@ def option_text(opt: dict) -> str:
     lines = []
     for k in ("level", "csize", "threshold", "wsize", "minImageNum", "CPU", "useVisData", "sequence"):
         lines.append("%s %s" % (k, opt[k]))
+    for k in ("setEdge", "useBound", "quad", "maxAngle"):   # optional keys (source/pmvs/option.cpp:59-62, 102-106)
+        if k in opt:
+            lines.append("%s %s" % (k, opt[k]))
     lines.append("timages " + " ".join(str(v) for v in opt["timages"]))
     lines.append("oimages " + " ".join(str(v) for v in opt["oimages"]))
     return "\n".join(lines) + "\n"

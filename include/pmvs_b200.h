@@ -39,6 +39,7 @@ extern "C" {
 #define PMVSB_ECUDA (-2)    /* CUDA runtime error */
 #define PMVSB_ESTATE (-3)   /* call out of order (e.g. scene not finalised) */
 #define PMVSB_ENOMEM (-4)
+#define PMVSB_ERANGE (-5)   /* a patch's image list outgrew its capacity (PMVSB_MAX_VIEWS): results would differ from the reference's */
 
 #define PMVSB_MAX_TAU 8     /* views used by refinePatch / computeINCC (tau = min(2*minImageNum, num)) */
 #define PMVSB_MAX_VIEWS 64  /* views per patch accepted by set_inccs / pre- and post-process kernels */
@@ -62,6 +63,22 @@ int pmvsb_upload_camera(pmvsb_ctx* ctx, int index, const float* P);
 /* Image::CImage::alloc + buildImage (source/image/image.cpp:113-180,228-325): rgb = interleaved
  * uint8 w*h*3 (what readAnyImage produces); the level+3 pyramid is built on the device. */
 int pmvsb_upload_image(pmvsb_ctx* ctx, int index, int width, int height, const uint8_t* rgb);
+/* Masks and edge maps (optional).  CImage::alloc reads <prefix>masks/%08d.{pgm,pbm} and <prefix>edges/%08d.{pgm,pbm}
+ * (source/image/image.cpp:146-176; file names source/image/photoSetS.cpp:43-49): gray = uint8[width*height] as stored in the
+ * file, at the size of the image, uploaded AFTER its image.  which = 0: mask, a pixel is inside when 127 < v;
+ * which = 1: edge map, inside when 1 < v.  The "any of the 2x2 parents" pyramid of buildMask / buildEdge
+ * (image.cpp:326-393) is built on the device down to the working level, the only level the path reads
+ * (getMask / getEdge are always called with CFindMatch::_level). */
+int pmvsb_upload_mask(pmvsb_ctx* ctx, int index, int which, int width, int height, const uint8_t* gray);
+/* Option `setEdge` (CPhotoSetS::setEdge, source/image/photoSetS.cpp:91-95 -> CImage::setEdge, image.cpp:407-471): the edge map
+ * of EVERY image recomputed from its level-0 colour gradients (replaces uploaded edge files, as in findMatch.cpp:74-76). */
+int pmvsb_set_edge(pmvsb_ctx* ctx, float threshold);
+/* Option `useBound`: SOption::_bindexes (source/pmvs/option.cpp:301-325), image indexes whose frames bound the reconstruction
+ * (CFindMatch::insideBimages, source/pmvs/findMatch.cpp:109-118). */
+int pmvsb_set_bimages(pmvsb_ctx* ctx, const int32_t* list, int n);
+/* parity hook: the working-level map of an image (CImage::getMask(level) / getEdge(level), 255 in / 0 out);
+ * *present = 0 when the image has none (out untouched; out may be NULL to query) */
+int pmvsb_download_mask(pmvsb_ctx* ctx, int index, int which, uint8_t* out, int* present);
 /* SOption::_visdata2 (source/pmvs/option.cpp:202-299): candidate images for addImages. Default: all. */
 int pmvsb_set_visdata2(pmvsb_ctx* ctx, int index, const int32_t* list, int n);
 /* After all cameras and images are uploaded: builds the device tables.  Required before any batch call. */
@@ -102,10 +119,20 @@ int pmvsb_set_inccs_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords
 int pmvsb_set_scales_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const int32_t* images,
                            const int32_t* nimages, float* dscale, float* ascale);
 
+/* `_pss.getMask(coord, _level) == 0 || insideBimages(coord) == 0` as expandSub, collectCandidates and postProcess test it
+ * (source/pmvs/expand.cpp:212, seed.cpp:314, optim.cpp:153) for n points (coords float[4n]): inside[k] = 1 when the point passes
+ * (CPhotoSetS::getMask walks every image of the scene, include/image/photoSetS.hpp:109-116). */
+int pmvsb_mask_gate_batch(pmvsb_ctx* ctx, int n, const float* coords, uint8_t* inside);
+/* COptim::removeImagesEdge (source/pmvs/optim.cpp:385-396), called by expandSub before preProcess (expand.cpp:219): images whose
+ * edge map rejects the patch centre leave the list (order kept); images / nimages updated in place. */
+int pmvsb_remove_images_edge_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, int32_t* images, int32_t* nimages);
+
 /* ---- visible-image-set selection around the hot call (integer results: bit-exact) -----------------------
  * COptim::preProcess (optim.cpp:95-122) for a batch of candidates: addImages -> constraintImages(nccThresholdBefore)
  * -> sortImages -> setScales -> minImageNum check -> checkAngles.  images/nimages are updated in place
- * (stride = capacity per patch, at most 64 views are kept); verdict 0 = keep, 1 = reject (as the reference returns). */
+ * (stride = capacity per patch, at most PMVSB_MAX_VIEWS); verdict 0 = keep, 1 = reject (as the reference returns).
+ * The reference's lists are unbounded: when addImages finds more images than the capacity holds, the call fails with
+ * PMVSB_ERANGE instead of truncating. */
 int pmvsb_pre_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coords, const float* normals,
                             int32_t* images, int32_t* nimages, float* dscale, float* ascale, int32_t* verdict);
 /* COptim::postProcess (optim.cpp:150-190) at CFindMatch::_depth == 0 (seed round): addImages ->

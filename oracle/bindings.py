@@ -358,6 +358,30 @@ class RefLib(_Common):
     def run(self):
         self.lib.ref_run()
 
+    # -- masks / edges / bounding images ---------------------------------------------------------------
+    def map_bytes(self, index, which, level=None):
+        """CImage::getMask(level) / getEdge(level) as (h, w) uint8, or None when the image has no such map"""
+        level = self.level if level is None else level
+        w, h = C.c_int(), C.c_int()
+        self.lib.ref_image_dims(int(index), level, C.byref(w), C.byref(h))
+        n = self.lib.ref_map_bytes(int(index), int(which), level, None)
+        if n == 0:
+            return None
+        out = np.zeros(n, np.uint8)
+        self.lib.ref_map_bytes(int(index), int(which), level, out.ctypes.data_as(C.c_void_p))
+        return out[: w.value * h.value].reshape(h.value, w.value)
+
+    def mask_gate(self, coord):
+        return self.lib.ref_mask_gate(_f4(coord).ctypes.data_as(C.c_void_p))
+
+    def get_edge(self, coord, index):
+        return self.lib.ref_get_edge(_f4(coord).ctypes.data_as(C.c_void_p), int(index))
+
+    def remove_images_edge(self, coord, images):
+        im = _imgs(images).copy()
+        n = self.lib.ref_remove_images_edge(_f4(coord).ctypes.data_as(C.c_void_p), im.ctypes.data_as(C.c_void_p), len(im))
+        return im[:n].copy()
+
     def patches(self, cap=256):
         n = self.lib.ref_num_patches()
         coords = np.zeros((n, 4), np.float32); normals = np.zeros((n, 4), np.float32); nda = np.zeros((n, 3), np.float32)

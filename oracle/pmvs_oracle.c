@@ -1252,7 +1252,7 @@ int pmvso_find_empty_blocks(const pmvso_ctx* c, int k, float* radius_out) {
     const float len = sqrtf(f2[0] * f2[0] + f2[1] * f2[1]);
     if (len < radiuslow || radiushigh < len) continue;
     f2[0] /= len; f2[1] /= len;
-    float angle = atan2f(f2[1], f2[0]);
+    float angle = (float)atan2((double)f2[1], (double)f2[0]);   /* the reference object imports the double atan2 (nm -u) */
     if (angle < 0.0) angle = (float)(angle + 2 * M_PI);
     const float findex = (float)(angle / (2 * M_PI / dnum));
     const int lindex = (int)floor(findex);

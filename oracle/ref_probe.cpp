@@ -292,6 +292,31 @@ int ref_post_process(const float* coord, const float* normal, float ncc, int* im
   return r;
 }
 
+// ---- masks / edges / bounding images --------------------------------------------------------------------------
+// CImage::getMask(level) (which = 0) / getEdge(level) (1) bytes of one image; returns the byte count (0 = no map)
+int ref_map_bytes(int index, int which, int level, unsigned char* out) {
+  const Image::CPhoto& ph = g_fm->_pss._photos[index];
+  const std::vector<unsigned char>& m = which == 0 ? ph.CImage::getMask(level) : ph.CImage::getEdge(level);
+  if (out && !m.empty()) std::memcpy(out, m.data(), m.size());
+  return (int)m.size();
+}
+// the gate of expandSub / collectCandidates / postProcess (expand.cpp:212, seed.cpp:314, optim.cpp:153): 1 = passes
+int ref_mask_gate(const float* coord) {
+  return !(g_fm->_pss.getMask(v4(coord), g_fm->_level) == 0 || g_fm->insideBimages(v4(coord)) == 0);
+}
+int ref_get_mask_image(const float* coord, int index) { return g_fm->_pss.getMask(v4(coord), index, g_fm->_level); }
+int ref_get_edge(const float* coord, int index) { return g_fm->_pss.getEdge(v4(coord), index, g_fm->_level); }
+int ref_num_bimages(void) { return (int)g_fm->_bindexes.size(); }
+// COptim::removeImagesEdge; returns the new length
+int ref_remove_images_edge(const float* coord, int* images, int n) {
+  Patch::CPatch patch;
+  float nrm[4] = {0, 0, 0, 0};
+  fill_patch(patch, coord, nrm, images, n);
+  g_fm->_optim.removeImagesEdge(patch);
+  for (int i = 0; i < (int)patch._images.size(); ++i) images[i] = patch._images[i];
+  return (int)patch._images.size();
+}
+
 // Whole reference run (seed + 3 x expand/filter), CFindMatch::run.
 void ref_run(void) { g_fm->run(); }
 int ref_num_patches(void) { g_fm->_pos.collectPatches(1); return (int)g_fm->_pos._ppatches.size(); }

@@ -93,6 +93,77 @@ def write_variant(scene, name, prefix, cpu):
     return out
 
 
+def mask_maps(scene, which):
+    """Deterministic per-image maps for the mask / edge contract (source/image/image.cpp:146-176): which = 0 masks (the top of
+    every frame is outside, stored with gray values on both sides of the 127 threshold), 1 edge files (a band
+    pattern with values around the `1 <` threshold).  Images 3, 7, 11, 15 have no mask file; odd images with a mask get a
+    binary PBM (the reference reads it as one continuous bit stream), the others a PGM.  Returns {index: (kind, array)}."""
+    h, w = scene.height, scene.width
+    yy, xx = np.mgrid[0:h, 0:w]
+    out = {}
+    for i in range(scene.num):
+        if which == 0:
+            if i % 4 == 3:
+                continue
+            # a silhouette-style mask must keep everything any OTHER camera sees (the gate rejects a point that falls outside
+            # the mask of ANY image it projects into): cut the top cap of the sphere and a small off-object corner
+            inside = (yy >= h * (0.18 + 0.03 * np.cos(i))) & ~((xx < 0.1 * w) & (yy > 0.9 * h))
+            if i % 2 == 1:
+                out[i] = ("pbm", inside)
+            else:
+                out[i] = ("pgm", np.where(inside, 128 + (xx + yy + i) % 100, (xx * 3 + yy) % 128).astype(np.uint8))
+        else:
+            if i % 3 == 2:
+                continue
+            inside = ((xx + 2 * yy + 7 * i) % 23) < 19
+            out[i] = ("pgm", np.where(inside, 2 + (xx + i) % 200, (xx + yy) % 2).astype(np.uint8))
+    return out
+
+
+def write_map_files(prefix, folder, maps):
+    os.makedirs(prefix + folder, exist_ok=True)
+    for i, (kind, a) in maps.items():
+        h, w = a.shape
+        if kind == "pgm":
+            with open(prefix + "%s/%08d.pgm" % (folder, i), "wb") as f:
+                f.write(b"P5\n# written by tests/scene_util.py\n%d %d\n255\n" % (w, h))
+                f.write(np.ascontiguousarray(a, dtype=np.uint8).tobytes())
+        else:   # P4 as CImage::writePBMImage lays it out: one bit stream without row padding, set bit = outside
+            bits = np.packbits((~a.astype(bool)).ravel())
+            with open(prefix + "%s/%08d.pbm" % (folder, i), "wb") as f:
+                f.write(b"P4\n%d %d\n" % (w, h))
+                f.write(bits.tobytes())
+
+
+def mask_variants():
+    """Scene variants for the masks / edges / bimages.dat part of the option contract: name -> (option updates, files)."""
+    return {
+        "masked": ({"useBound": 1}, ("masks", "bimages")),     # masks/ + useBound with bimages.dat = images 0 and 8
+        "edgefiles": ({}, ("edges",)),                          # edges/%08d.pgm
+        "setedge": ({"setEdge": 2.5}, ()),                       # edge maps computed from the images (CImage::setEdge)
+        "allmaps": ({"useBound": 1, "setEdge": 0.0}, ("masks", "edges", "bimages")),
+    }
+
+
+def write_mask_variant(scene, name, prefix, cpu):
+    import copy
+    synth = _synth()
+    upd, files = mask_variants()[name]
+    sc = copy.copy(scene)
+    sc.option = dict(scene.option)
+    sc.option.update(upd)
+    sc.option["CPU"] = cpu
+    out = synth.write_scene(sc, prefix)
+    if "masks" in files:
+        write_map_files(out, "masks", mask_maps(scene, 0))
+    if "edges" in files:
+        write_map_files(out, "edges", mask_maps(scene, 1))
+    if "bimages" in files:
+        with open(out + "bimages.dat", "w") as f:
+            f.write("3\n0 8 99\n")    # 99 is not a target image: ignored (option.cpp:318-321)
+    return out
+
+
 SKE_TWO_CLUSTERS = "SKE\n16 2\n8 2\n0 1 2 3 4 5 6 7 \n8 15 \n8 2\n8 9 10 11 12 13 14 15 \n0 7 \n"
 
 

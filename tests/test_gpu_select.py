@@ -68,12 +68,18 @@ def test_post_process_bit_exact(gpu, oracle, scene, candidates):
     assert verdicts[0] > 0.5 * P
 
 
-def test_pre_process_ragged_and_empty(gpu, scene, candidates):
+def test_pre_process_ragged_and_empty(gpu, pkg, scene, candidates):
     pb, n0 = candidates
-    # zero images -> rejected, untouched; capacity smaller than the scene -> list is capped, no overflow
+    # zero images -> rejected, untouched
     P = 8
-    images = np.zeros((P, 4), np.int32); images[:, :3] = pb["images"][:P, :3]
+    images = np.zeros((P, scene.num), np.int32); images[:, :3] = pb["images"][:P, :3]
     n = np.array([0, 1, 2, 3, 3, 3, 2, 0], np.int32)
     out = gpu.pre_process_batch(pb["coords"][:P], pb["normals"][:P], images, n)
     assert out["verdict"][0] == 1 and out["nimages"][0] == 0
-    assert (out["nimages"] <= 4).all()
+    # a capacity smaller than what addImages finds is an ERROR (the reference's lists are unbounded), never a silent cap
+    small = np.zeros((P, 4), np.int32); small[:, :3] = pb["images"][:P, :3]
+    with pytest.raises(pkg.PmvsError, match="more images than the list capacity"):
+        gpu.pre_process_batch(pb["coords"][:P], pb["normals"][:P], small, n)
+    # the context stays usable and the flag is cleared
+    again = gpu.pre_process_batch(pb["coords"][:P], pb["normals"][:P], images, n)
+    assert np.array_equal(again["images"], out["images"]) and np.array_equal(again["verdict"], out["verdict"])
