@@ -18,7 +18,8 @@ LIB_PATH = os.environ.get("PMVS_B200_LIB") or os.path.join(HERE, "lib", "libpmvs
 SYMBOLS = [
     "pmvsb_create", "pmvsb_destroy", "pmvsb_last_error", "pmvsb_version", "pmvsb_upload_camera", "pmvsb_upload_image",
     "pmvsb_upload_mask", "pmvsb_set_edge", "pmvsb_set_bimages", "pmvsb_download_mask", "pmvsb_mask_gate_batch",
-    "pmvsb_remove_images_edge_batch", "pmvsb_set_visdata2", "pmvsb_finalize_scene", "pmvsb_set_thresholds", "pmvsb_set_optimizer", "pmvsb_image_dims",
+    "pmvsb_remove_images_edge_batch", "pmvsb_store_set_seq", "pmvsb_store_counts", "pmvsb_store_rebuild", "pmvsb_filter_exact_apply_store",
+    "pmvsb_small_group_edges_store", "pmvsb_filter_small_groups_store", "pmvsb_store_download_lists", "pmvsb_set_visdata2", "pmvsb_finalize_scene", "pmvsb_set_thresholds", "pmvsb_set_optimizer", "pmvsb_image_dims",
     "pmvsb_download_image", "pmvsb_get_camera", "pmvsb_project_batch", "pmvsb_grab_tex_batch", "pmvsb_eval_objective_batch",
     "pmvsb_compute_incc_batch", "pmvsb_set_inccs_batch", "pmvsb_set_scales_batch", "pmvsb_pre_process_batch",
     "pmvsb_post_process_batch", "pmvsb_set_depth", "pmvsb_grid_dims", "pmvsb_store_upload", "pmvsb_build_depth_maps",
@@ -275,6 +276,53 @@ class PmvsB200:
         off = np.zeros(self._store_P + 1, np.int32); vim = np.zeros(max(total.value, 1), np.int32); vgr = np.zeros((max(total.value, 1), 2), np.int32)
         self._ck(self.lib.pmvsb_store_download_vimages(self.ctx, _vp(off), _vp(vim), _vp(vgr)))
         return off, vim[:total.value], vgr[:total.value]
+
+    # -- the table reorganised on the device ------------------------------------------------------------
+    def store_counts(self):
+        P, E, VE = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self.lib.pmvsb_store_counts(self.ctx, C.byref(P), C.byref(E), C.byref(VE)))
+        return P.value, E.value, VE.value
+
+    def store_set_seq(self, seq, first=0):
+        seq = np.ascontiguousarray(seq, dtype=np.int32)
+        self._ck(self.lib.pmvsb_store_set_seq(self.ctx, int(first), len(seq), _vp(seq)))
+
+    def store_rebuild(self, keep=None, additive=1):
+        """-> perm (old table index of every patch of the new table)"""
+        P = self.store_counts()[0]
+        k = None if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
+        n = C.c_int32(); perm = np.zeros(max(P, 1), np.int32)
+        self._ck(self.lib.pmvsb_store_rebuild(self.ctx, _vp(k), int(additive), C.byref(n), _vp(perm)))
+        self._store_P = n.value; self._store_E = self.store_counts()[1]
+        return perm[: n.value].copy()
+
+    def store_download(self):
+        """the table's lists as the device holds them: dict(seq, timages, img_off, images, grids, vimg_off, vimages, vgrids)"""
+        P, E, VE = self.store_counts()
+        seq = np.zeros(P, np.int32); ti = np.zeros(P, np.int32); off = np.zeros(P + 1, np.int32)
+        im = np.zeros(max(E, 1), np.int32); gr = np.zeros((max(E, 1), 2), np.int32)
+        self._ck(self.lib.pmvsb_store_download_lists(self.ctx, _vp(seq), _vp(ti), _vp(off), _vp(im), _vp(gr)))
+        voff = np.zeros(P + 1, np.int32); vim = np.zeros(max(VE, 1), np.int32); vgr = np.zeros((max(VE, 1), 2), np.int32)
+        self._ck(self.lib.pmvsb_store_download_vimages(self.ctx, _vp(voff), _vp(vim), _vp(vgr)))
+        return dict(seq=seq, timages=ti, img_off=off, images=im[:E], grids=gr[:E], vimg_off=voff, vimages=vim[:VE], vgrids=vgr[:VE])
+
+    def filter_exact_apply_store(self):
+        keep = np.zeros(self.store_counts()[0], np.uint8)
+        self._ck(self.lib.pmvsb_filter_exact_apply_store(self.ctx, _vp(keep)))
+        return keep
+
+    def small_group_edges_store(self, thr=1.0):
+        P = self.store_counts()[0]
+        off = np.zeros(P + 1, np.int32); total = C.c_int32()
+        self._ck(self.lib.pmvsb_small_group_edges_store(self.ctx, C.c_float(thr), _vp(off), None, 0, C.byref(total)))
+        adj = np.zeros(max(total.value, 1), np.int32)
+        self._ck(self.lib.pmvsb_small_group_edges_store(self.ctx, C.c_float(thr), _vp(off), _vp(adj), total.value, C.byref(total)))
+        return off, adj[: total.value]
+
+    def filter_small_groups_store(self, thr=1.0):
+        keep = np.zeros(self.store_counts()[0], np.uint8); t = C.c_int32()
+        self._ck(self.lib.pmvsb_filter_small_groups_store(self.ctx, C.c_float(thr), _vp(keep), C.byref(t)))
+        return keep, t.value
 
     def cell_lists(self, visible):
         cells = sum(self.grid_dims(i)[0] * self.grid_dims(i)[1] for i in range(self.num_target))

@@ -21,6 +21,7 @@
 #include "pmvs_select.cuh"
 #include "pmvs_filter.cuh"
 #include "pmvs_cells.cuh"
+#include "pmvs_table.cuh"
 #include "pmvs_features.cuh"
 
 #ifndef PMVS_MINBLOCKS
@@ -460,6 +461,11 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
 }
 
 
+__global__ void k_iota(int32_t* __restrict__ out, int first, int n, int value0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[first + i] = value0 + i;
+}
+
 // ---- masks / edges (CImage::_masks, _edges) -------------------------------------------------------------
 // CImage::alloc's binarisation (source/image/image.cpp:146-176): masks keep 127 < v, edge files keep 1 < v
 __global__ void k_map_binarise(const uint8_t* __restrict__ in, size_t n, int above, uint8_t* __restrict__ out) {
@@ -636,6 +642,9 @@ struct StoreBufs {
   DVec<int32_t> alt_voff, alt_vimages, alt_vgrids;                  // double buffers of pmvsb_store_update_vimages
   DVec<int32_t> cell_base, gw, gh, cell_off, cell_patch, vcell_off, vcell_patch, cursor, tile_sums, counts;
   DVec<unsigned long long> dp;
+  // device-side reorganisation (pmvs_table.cuh): creation sequence numbers, second copies of every field, sort scratch
+  DVec<int32_t> seq, alt_seq, alt_timages, alt_img_off, alt_images, alt_grids, first_cell, perm, bucket_off, rows, rows_n, row_cells;
+  DVec<float> alt_coords, alt_normals, alt_ncc, alt_dscale;
 };
 
 struct pmvsb_ctx {
@@ -669,6 +678,7 @@ struct pmvsb_ctx {
   std::vector<int32_t> h_gw, h_gh, h_base;
   int depth_flag = 0;
   bool store_set = false, depth_built = false;
+  int seq_next = 0;                 // next creation sequence number handed out by pmvsb_store_append
   std::vector<std::pair<size_t, void*>> pool;   // idle scratch blocks (size, pointer)
   char* arena = nullptr;          // grow-only device staging for the host-pointer entry points
   size_t arena_cap = 0, arena_used = 0;
@@ -997,7 +1007,9 @@ static int dvec_put(pmvsb_ctx* ctx, DVec<T>& v, size_t at, const T* src, size_t 
 }
 static void store_free(pmvsb_ctx* ctx) {
   StoreBufs& b = ctx->sb;
-  for (DVec<float>* v : {&b.coords, &b.normals, &b.ncc, &b.dscale}) { cudaFree(v->p); v->p = nullptr; v->cap = 0; }
+  for (DVec<float>* v : {&b.coords, &b.normals, &b.ncc, &b.dscale, &b.alt_coords, &b.alt_normals, &b.alt_ncc, &b.alt_dscale}) { cudaFree(v->p); v->p = nullptr; v->cap = 0; }
+  for (DVec<int32_t>* v : {&b.seq, &b.alt_seq, &b.alt_timages, &b.alt_img_off, &b.alt_images, &b.alt_grids, &b.first_cell, &b.perm, &b.bucket_off, &b.rows,
+                           &b.rows_n, &b.row_cells}) { cudaFree(v->p); v->p = nullptr; v->cap = 0; }
   for (DVec<int32_t>* v : {&b.timages, &b.img_off, &b.images, &b.grids, &b.entry_patch, &b.vimg_off, &b.vimages, &b.vgrids, &b.ventry_patch,
                            &b.alt_voff, &b.alt_vimages, &b.alt_vgrids, &b.cell_base, &b.gw, &b.gh, &b.cell_off, &b.cell_patch, &b.vcell_off,
                            &b.vcell_patch, &b.cursor, &b.tile_sums, &b.counts}) { cudaFree(v->p); v->p = nullptr; v->cap = 0; }
@@ -1710,6 +1722,8 @@ int pmvsb_store_upload(pmvsb_ctx* ctx, int P, const float* coords, const float* 
   if ((r = dvec_put(ctx, b.vgrids, 0, vgrids, (size_t)2 * VE))) return r;
   if ((r = dvec_reserve(ctx, b.entry_patch, (size_t)std::max(E, 1)))) return r;
   if ((r = dvec_reserve(ctx, b.ventry_patch, (size_t)std::max(VE, 1)))) return r;
+  if ((r = dvec_reserve(ctx, b.seq, (size_t)std::max(P, 1)))) return r;
+  if (P > 0) { k_iota<<<(P + 255) / 256, 256, 0, ctx->stream>>>(b.seq.p, 0, P, 0); ++ctx->launches; }   // default creation order = table order
   StoreDev& st = ctx->store;
   st.P = P;
   st.depth_flag = ctx->depth_flag;
@@ -1729,6 +1743,7 @@ int pmvsb_store_upload(pmvsb_ctx* ctx, int P, const float* coords, const float* 
   if ((r = build_cell_lists(ctx, true))) return r;
   CK(cudaStreamSynchronize(ctx->stream));   // the caller's host buffers are free again
   ctx->store_set = true;
+  ctx->seq_next = P;
   return PMVSB_OK;
 }
 
@@ -1762,6 +1777,10 @@ int pmvsb_store_append(pmvsb_ctx* ctx, int n, const float* coords, const float* 
   if ((r = dvec_put(ctx, b.vgrids, (size_t)2 * VE, vgrids, (size_t)2 * dVE))) return r;
   if ((r = dvec_reserve(ctx, b.entry_patch, (size_t)E + dE, (size_t)E))) return r;
   if ((r = dvec_reserve(ctx, b.ventry_patch, (size_t)std::max(VE + dVE, 1), (size_t)VE))) return r;
+  if ((r = dvec_reserve(ctx, b.seq, (size_t)P + n, (size_t)P))) return r;
+  k_iota<<<(n + 255) / 256, 256, 0, ctx->stream>>>(b.seq.p, P, n, ctx->seq_next);   // appended patches are the youngest
+  ++ctx->launches;
+  ctx->seq_next += n;
   store_view(ctx);
   k_entry_owner<<<(n + 255) / 256, 256, 0, ctx->stream>>>(P, n, b.img_off.p, b.entry_patch.p);
   k_entry_owner<<<(n + 255) / 256, 256, 0, ctx->stream>>>(P, n, b.vimg_off.p, b.ventry_patch.p);
@@ -1891,9 +1910,16 @@ int pmvsb_compute_gains_store(pmvsb_ctx* ctx, float* gains) {
   return PMVSB_OK;
 }
 
+static int store_update_vimages_impl(pmvsb_ctx* ctx, int additive, int32_t* total);
+
 int pmvsb_store_update_vimages(pmvsb_ctx* ctx, int additive, int32_t* total) {
   int r = need_store(ctx, true);
   if (r) return r;
+  return store_update_vimages_impl(ctx, additive, total);
+}
+
+static int store_update_vimages_impl(pmvsb_ctx* ctx, int additive, int32_t* total) {
+  int r = 0;
   if (ctx->store_appended) return fail(ctx, PMVSB_ESTATE, "table was extended by pmvsb_depth_maps_add (coordinates only): upload it again first");
   StoreBufs& b = ctx->sb;
   const int P = ctx->store.P;
@@ -1934,6 +1960,274 @@ int pmvsb_store_download_vimages(pmvsb_ctx* ctx, int32_t* vimg_off, int32_t* vim
     CK(cudaMemcpyAsync(vimages, ctx->sb.vimages.p, sizeof(int32_t) * (size_t)VE, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(vgrids, ctx->sb.vgrids.p, sizeof(int32_t) * (size_t)2 * VE, cudaMemcpyDeviceToHost, ctx->stream));
   }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+
+// ---- the table reorganised on the device (pmvs_table.cuh) -------------------------------------------------------
+int pmvsb_store_set_seq(pmvsb_ctx* ctx, int first, int n, const int32_t* seq) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  if (first < 0 || n < 0 || first + n > ctx->store.P || (n > 0 && !seq)) return fail(ctx, PMVSB_EINVAL, "store_set_seq: bad range");
+  if (n == 0) return PMVSB_OK;
+  CK(cudaMemcpyAsync(ctx->sb.seq.p + first, seq, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; ++i) ctx->seq_next = std::max(ctx->seq_next, seq[i] + 1);
+  return PMVSB_OK;
+}
+
+int pmvsb_store_counts(pmvsb_ctx* ctx, int32_t* P, int32_t* entries, int32_t* ventries) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  if (P) *P = ctx->store.P;
+  if (entries) *entries = ctx->store_entries;
+  if (ventries) *ventries = ctx->store_ventries;
+  return PMVSB_OK;
+}
+
+static int store_update_vimages_impl(pmvsb_ctx* ctx, int additive, int32_t* total);
+
+int pmvsb_store_rebuild(pmvsb_ctx* ctx, const uint8_t* keep, int additive, int32_t* new_count, int32_t* perm_out) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  StoreBufs& b = ctx->sb;
+  const int P = ctx->store.P, cells = ctx->store_cells;
+  if (new_count) *new_count = 0;
+  DevBuf<uint8_t> dkeep;
+  if (keep && P > 0) {
+    CK(dkeep.alloc(P));
+    CK(cudaMemcpyAsync(dkeep.p, keep, (size_t)P, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if ((r = dvec_reserve(ctx, b.first_cell, (size_t)std::max(P, 1)))) return r;
+  if ((r = dvec_reserve(ctx, b.perm, (size_t)std::max(P, 1)))) return r;
+  if ((r = dvec_reserve(ctx, b.bucket_off, (size_t)cells + 1))) return r;
+  if ((r = dvec_reserve(ctx, b.cursor, (size_t)cells + 1))) return r;
+  CK(cudaMemsetAsync(b.bucket_off.p, 0, sizeof(int32_t) * ((size_t)cells + 1), ctx->stream));
+  CK(cudaMemsetAsync(b.cursor.p, 0, sizeof(int32_t) * ((size_t)cells + 1), ctx->stream));
+  int32_t newP = 0;
+  if (P > 0) {
+    k_tab_first_cell<<<(P + 255) / 256, 256, 0, ctx->stream>>>(ctx->store, ctx->tnum, keep ? dkeep.p : nullptr, b.first_cell.p, b.bucket_off.p);
+    ++ctx->launches;
+    if ((r = device_scan(ctx, b.bucket_off.p, cells + 1))) return r;
+    k_tab_bucket_fill<<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, b.first_cell.p, b.bucket_off.p, b.cursor.p, b.perm.p);
+    k_tab_bucket_sort<<<(cells + 255) / 256, 256, 0, ctx->stream>>>(cells, b.bucket_off.p, b.perm.p, b.seq.p);
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(&newP, b.bucket_off.p + cells, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  // scalar fields and the image lists through the permutation, into the second set of buffers
+  const size_t n1 = (size_t)std::max(newP, 1);
+  if ((r = dvec_reserve(ctx, b.alt_coords, 4 * n1)) || (r = dvec_reserve(ctx, b.alt_normals, 4 * n1)) || (r = dvec_reserve(ctx, b.alt_ncc, n1)) ||
+      (r = dvec_reserve(ctx, b.alt_dscale, n1)) || (r = dvec_reserve(ctx, b.alt_timages, n1)) || (r = dvec_reserve(ctx, b.alt_seq, n1)) ||
+      (r = dvec_reserve(ctx, b.alt_img_off, n1 + 1)) || (r = dvec_reserve(ctx, b.alt_voff, n1 + 1)))
+    return r;
+  int32_t E = 0, VE = 0;
+  if (newP > 0) {
+    k_tab_gather_fields<<<(newP + 255) / 256, 256, 0, ctx->stream>>>(newP, b.perm.p, reinterpret_cast<const float4*>(b.coords.p),
+        reinterpret_cast<const float4*>(b.normals.p), b.ncc.p, b.dscale.p, b.timages.p, b.seq.p, reinterpret_cast<float4*>(b.alt_coords.p),
+        reinterpret_cast<float4*>(b.alt_normals.p), b.alt_ncc.p, b.alt_dscale.p, b.alt_timages.p, b.alt_seq.p);
+    k_tab_gather_len<<<(newP + 256) / 256, 256, 0, ctx->stream>>>(newP, b.perm.p, b.img_off.p, b.alt_img_off.p);
+    ctx->launches += 2;
+    if ((r = device_scan(ctx, b.alt_img_off.p, newP + 1))) return r;
+    CK(cudaMemcpyAsync(&E, b.alt_img_off.p + newP, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (additive) {
+      k_tab_gather_len<<<(newP + 256) / 256, 256, 0, ctx->stream>>>(newP, b.perm.p, b.vimg_off.p, b.alt_voff.p);
+      ++ctx->launches;
+      if ((r = device_scan(ctx, b.alt_voff.p, newP + 1))) return r;
+      CK(cudaMemcpyAsync(&VE, b.alt_voff.p + newP, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      CK(cudaMemsetAsync(b.alt_voff.p, 0, sizeof(int32_t) * ((size_t)newP + 1), ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if ((r = dvec_reserve(ctx, b.alt_images, (size_t)std::max(E, 1))) || (r = dvec_reserve(ctx, b.alt_grids, (size_t)2 * std::max(E, 1))) ||
+        (r = dvec_reserve(ctx, b.alt_vimages, (size_t)std::max(VE, 1))) || (r = dvec_reserve(ctx, b.alt_vgrids, (size_t)2 * std::max(VE, 1))))
+      return r;
+    const int gl = (int)(((size_t)newP * 32 + 255) / 256);
+    k_tab_gather_lists<<<gl, 256, 0, ctx->stream>>>(newP, b.perm.p, b.img_off.p, b.images.p, b.grids.p, b.alt_img_off.p, b.alt_images.p, b.alt_grids.p);
+    ++ctx->launches;
+    if (additive && VE > 0) {
+      k_tab_gather_lists<<<gl, 256, 0, ctx->stream>>>(newP, b.perm.p, b.vimg_off.p, b.vimages.p, b.vgrids.p, b.alt_voff.p, b.alt_vimages.p, b.alt_vgrids.p);
+      ++ctx->launches;
+    }
+  } else {
+    CK(cudaMemsetAsync(b.alt_img_off.p, 0, sizeof(int32_t), ctx->stream));
+    CK(cudaMemsetAsync(b.alt_voff.p, 0, sizeof(int32_t), ctx->stream));
+  }
+  CK(cudaGetLastError());
+  if (perm_out && newP > 0) CK(cudaMemcpyAsync(perm_out, b.perm.p, sizeof(int32_t) * (size_t)newP, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::swap(b.coords, b.alt_coords); std::swap(b.normals, b.alt_normals); std::swap(b.ncc, b.alt_ncc); std::swap(b.dscale, b.alt_dscale);
+  std::swap(b.timages, b.alt_timages); std::swap(b.seq, b.alt_seq); std::swap(b.img_off, b.alt_img_off); std::swap(b.images, b.alt_images);
+  std::swap(b.grids, b.alt_grids); std::swap(b.vimg_off, b.alt_voff); std::swap(b.vimages, b.alt_vimages); std::swap(b.vgrids, b.alt_vgrids);
+  ctx->store.P = newP;
+  ctx->store_entries = E; ctx->store_ventries = VE;
+  ctx->store_appended = false;
+  if ((r = dvec_reserve(ctx, b.entry_patch, (size_t)std::max(E, 1)))) return r;
+  if ((r = dvec_reserve(ctx, b.ventry_patch, (size_t)std::max(VE, 1)))) return r;
+  store_view(ctx);
+  if (newP > 0) {
+    k_entry_owner<<<(newP + 255) / 256, 256, 0, ctx->stream>>>(0, newP, b.img_off.p, b.entry_patch.p);
+    ++ctx->launches;
+  }
+  if ((r = build_cell_lists(ctx, false))) return r;
+  // CFilter::setDepthMaps, then setVImagesVGrids for every patch and _vpgrids (filter.cpp:734-783)
+  CK(cudaMemsetAsync(ctx->store.dp, 0xff, sizeof(unsigned long long) * (cells ? cells : 1), ctx->stream));
+  const long long nt = (long long)newP * ctx->tnum;
+  if (nt > 0) {
+    k_depth_maps<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->scene, ctx->store, 0, newP);
+    ++ctx->launches;
+  }
+  CK(cudaGetLastError());
+  ctx->depth_built = true;
+  if (newP > 0 && additive != 2) {
+    if ((r = store_update_vimages_impl(ctx, additive, nullptr))) return r;
+  } else {
+    if (newP > 0) {
+      k_entry_owner<<<(newP + 255) / 256, 256, 0, ctx->stream>>>(0, newP, b.vimg_off.p, b.ventry_patch.p);
+      ++ctx->launches;
+    }
+    if ((r = build_cell_lists(ctx, true))) return r;
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (new_count) *new_count = newP;
+  return PMVSB_OK;
+}
+
+int pmvsb_filter_exact_apply_store(pmvsb_ctx* ctx, uint8_t* keep) {
+  int r = need_store(ctx, true);
+  if (r) return r;
+  if (!keep) return fail(ctx, PMVSB_EINVAL, "filter_exact_apply_store: null pointer");
+  if (ctx->wsize == 9) return fail(ctx, PMVSB_EINVAL, "filter_exact_apply_store: wsize 9 is not supported by the selection kernels");
+  StoreBufs& b = ctx->sb;
+  const int P = ctx->store.P, E = ctx->store_entries;
+  if (P == 0) return PMVSB_OK;
+  const int stride = std::min(ctx->num, PMVSB_MAX_VIEWS);
+  DevBuf<uint8_t> safe, dkeep;
+  CK(safe.alloc((size_t)std::max(E, 1))); CK(dkeep.alloc(P));
+  if ((r = dvec_reserve(ctx, b.rows, (size_t)stride * P)) || (r = dvec_reserve(ctx, b.rows_n, (size_t)P + 1)) ||
+      (r = dvec_reserve(ctx, b.row_cells, (size_t)2 * stride * P)) || (r = dvec_reserve(ctx, b.alt_img_off, (size_t)P + 1)))
+    return r;
+  if (E > 0) {
+    k_filter_exact<<<(E + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, ctx->store, E, safe.p);
+    ++ctx->launches;
+  }
+  k_tab_prune<<<(P + 127) / 128, 128, 0, ctx->stream>>>(ctx->store, ctx->tnum, ctx->min_image_num, safe.p, stride, b.rows.p, b.rows_n.p, b.timages.p);
+  ++ctx->launches;
+  // setRefImage + setGrids for the survivors (filter.cpp:277-280), one launch per view-capacity class
+#define LAUNCH_SET_REF(W, MAXV, LO) \
+  k_set_ref_image<W, MAXV, LO><<<P, 32, 0, ctx->stream>>>(ctx->scene, ctx->select, P, stride, b.coords.p, b.normals.p, b.rows.p, b.rows_n.p, b.row_cells.p); ++ctx->launches
+  if (ctx->wsize == 5) {
+    LAUNCH_SET_REF(5, 16, 0);
+    if (stride > 16) { LAUNCH_SET_REF(5, 32, 16); }
+    if (stride > 32) { LAUNCH_SET_REF(5, 64, 32); }
+  } else {
+    LAUNCH_SET_REF(7, 16, 0);
+    if (stride > 16) { LAUNCH_SET_REF(7, 32, 16); }
+    if (stride > 32) { LAUNCH_SET_REF(7, 64, 32); }
+  }
+#undef LAUNCH_SET_REF
+  k_tab_flags_from_len<<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, b.rows_n.p, dkeep.p);
+  CK(cudaMemcpyAsync(b.alt_img_off.p, b.rows_n.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemsetAsync(b.alt_img_off.p + P, 0, sizeof(int32_t), ctx->stream));
+  ++ctx->launches;
+  if ((r = device_scan(ctx, b.alt_img_off.p, P + 1))) return r;
+  int32_t newE = 0;
+  CK(cudaMemcpyAsync(&newE, b.alt_img_off.p + P, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(keep, dkeep.p, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if ((r = dvec_reserve(ctx, b.alt_images, (size_t)std::max(newE, 1))) || (r = dvec_reserve(ctx, b.alt_grids, (size_t)2 * std::max(newE, 1)))) return r;
+  k_tab_rows_to_lists<<<(P + 127) / 128, 128, 0, ctx->stream>>>(P, stride, b.rows.p, b.row_cells.p, b.alt_img_off.p, b.alt_images.p, b.alt_grids.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::swap(b.img_off, b.alt_img_off); std::swap(b.images, b.alt_images); std::swap(b.grids, b.alt_grids);
+  ctx->store_entries = newE;
+  if ((r = dvec_reserve(ctx, b.entry_patch, (size_t)std::max(newE, 1)))) return r;
+  store_view(ctx);
+  k_entry_owner<<<(P + 255) / 256, 256, 0, ctx->stream>>>(0, P, b.img_off.p, b.entry_patch.p);
+  ++ctx->launches;
+  if ((r = build_cell_lists(ctx, false))) return r;   // the cells of the dropped images lose the patch (filter.cpp:240-252)
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_small_group_edges_store(pmvsb_ctx* ctx, float neighbor_threshold, int32_t* adj_off, int32_t* adj, int cap, int32_t* total) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  if (!adj_off || !total || cap < 0 || (cap > 0 && !adj)) return fail(ctx, PMVSB_EINVAL, "small_group_edges_store: bad argument");
+  const int P = ctx->store.P;
+  *total = 0;
+  adj_off[0] = 0;
+  if (P == 0) return PMVSB_OK;
+  DevBuf<int32_t> doff, dadj;
+  CK(doff.alloc((size_t)P + 1));
+  k_tab_group_edges<false><<<(P + 128) / 128, 128, 0, ctx->stream>>>(ctx->scene, ctx->store, neighbor_threshold, doff.p, nullptr, nullptr);
+  ++ctx->launches;
+  if ((r = device_scan(ctx, doff.p, P + 1))) return r;
+  CK(cudaMemcpyAsync(adj_off, doff.p, sizeof(int32_t) * ((size_t)P + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *total = adj_off[P];
+  if (*total > cap) return PMVSB_OK;   // the caller sizes adj from *total and calls again
+  if (*total == 0) return PMVSB_OK;
+  CK(dadj.alloc((size_t)*total));
+  k_tab_group_edges<true><<<(P + 128) / 128, 128, 0, ctx->stream>>>(ctx->scene, ctx->store, neighbor_threshold, nullptr, doff.p, dadj.p);
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(adj, dadj.p, sizeof(int32_t) * (size_t)*total, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
+
+int pmvsb_filter_small_groups_store(pmvsb_ctx* ctx, float neighbor_threshold, uint8_t* keep, int32_t* group_threshold) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  if (!keep) return fail(ctx, PMVSB_EINVAL, "filter_small_groups_store: null pointer");
+  const int P = ctx->store.P;
+  if (group_threshold) *group_threshold = std::max(20, P / 10000);
+  if (P == 0) return PMVSB_OK;
+  std::vector<int32_t> off((size_t)P + 1), adj;
+  int32_t total = 0;
+  if ((r = pmvsb_small_group_edges_store(ctx, neighbor_threshold, off.data(), nullptr, 0, &total))) return r;
+  adj.resize((size_t)std::max(total, 1));
+  if ((r = pmvsb_small_group_edges_store(ctx, neighbor_threshold, off.data(), adj.data(), total, &total))) return r;
+  // the labelling walk of filterSmallGroups (filter.cpp:541-563): sequential by definition (a patch takes the label of the
+  // first walk that reaches it), integer work over the adjacency the device built
+  std::vector<int32_t> label((size_t)P, -1), queue;
+  queue.reserve(P);
+  int id = -1;
+  for (int start = 0; start < P; ++start) {
+    if (label[start] != -1) continue;
+    label[start] = ++id;
+    queue.clear();
+    queue.push_back(start);
+    for (size_t head = 0; head < queue.size(); ++head) {
+      const int k = queue[head];
+      for (int j = off[k]; j < off[k + 1]; ++j) {
+        const int q = adj[j];
+        if (label[q] != -1) continue;
+        label[q] = id;
+        queue.push_back(q);
+      }
+    }
+  }
+  std::vector<int32_t> size((size_t)id + 1, 0);
+  for (int p = 0; p < P; ++p) ++size[label[p]];
+  const int threshold = std::max(20, P / 10000);
+  for (int p = 0; p < P; ++p) keep[p] = size[label[p]] < threshold ? 0 : 1;
+  return PMVSB_OK;
+}
+
+int pmvsb_store_download_lists(pmvsb_ctx* ctx, int32_t* seq, int32_t* timages, int32_t* img_off, int32_t* images, int32_t* grids) {
+  int r = need_store(ctx, false);
+  if (r) return r;
+  const int P = ctx->store.P, E = ctx->store_entries;
+  const StoreBufs& b = ctx->sb;
+  if (seq && P > 0) CK(cudaMemcpyAsync(seq, b.seq.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+  if (timages && P > 0) CK(cudaMemcpyAsync(timages, b.timages.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+  if (img_off) CK(cudaMemcpyAsync(img_off, b.img_off.p, sizeof(int32_t) * ((size_t)P + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  if (images && E > 0) CK(cudaMemcpyAsync(images, b.images.p, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToHost, ctx->stream));
+  if (grids && E > 0) CK(cudaMemcpyAsync(grids, b.grids.p, sizeof(int32_t) * (size_t)2 * E, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return PMVSB_OK;
 }

@@ -134,38 +134,21 @@ int Pipeline::add_patch(Patch&& moved) {   // patchOrganizerS.cpp:312-349
   patches_.push_back(std::move(moved));   // the four lists change owner instead of being copied
   const Patch& p = patches_.back();
   patches_.back().alive = true;
+  // the host keeps the OCCUPANCY of _pgrids (what the cell rules read); the lists themselves (_pgrids, _vpgrids) live
+  // on the device (pmvsb_store_append / pmvsb_store_rebuild)
   for (size_t i = 0; i < p.images.size(); ++i) {
     const int im = p.images[i];
     if (tnum_ <= im) continue;
-    grids_[im].pg[(size_t)p.grids[i][1] * grids_[im].gw + p.grids[i][0]].push_back(id);
+    ++grids_[im].occ[(size_t)p.grids[i][1] * grids_[im].gw + p.grids[i][0]];
   }
-  // _vpgrids live on the device (pmvsb_store_append / pmvsb_store_update_vimages); the one host consumer,
-  // filter_small_groups, builds its own copy from the patches' _vimages when it runs
   return id;
 }
 
-void Pipeline::remove_patch(int id) {   // patchOrganizerS.cpp:452-477
-  Patch& p = patches_[id];
-  auto drop = [&](std::vector<int>& v) { v.erase(std::remove(v.begin(), v.end(), id), v.end()); };
-  for (size_t i = 0; i < p.images.size(); ++i) {
-    const int im = p.images[i];
-    if (tnum_ <= im) continue;
-    drop(grids_[im].pg[(size_t)p.grids[i][1] * grids_[im].gw + p.grids[i][0]]);
-  }
-  p.alive = false;
-}
-
-std::vector<int> Pipeline::collect_patches() const {   // patchOrganizerS.cpp:207-236: first appearance in (image, cell) order
-  std::vector<std::vector<int>> per_image(tnum_);
-  parallel_for(tnum_, threads_, [&](int im) {
-    std::vector<int>& v = per_image[im];
-    for (const auto& cell : grids_[im].pg) v.insert(v.end(), cell.begin(), cell.end());
-  }, 1);
+// ids of the live patches in creation order
+std::vector<int> Pipeline::live_patches() const {
   std::vector<int> ids;
-  std::vector<char> seen(patches_.size(), 0);
-  for (const auto& v : per_image)
-    for (int q : v)
-      if (!seen[q]) { seen[q] = 1; ids.push_back(q); }
+  for (int id = 0; id < (int)patches_.size(); ++id)
+    if (patches_[id].alive) ids.push_back(id);
   return ids;
 }
 
@@ -196,18 +179,66 @@ void Pipeline::marshal(const std::vector<int>& ids, TableArrays& t) const {
   }, 1024);
 }
 
+// The live patches go to the GPU once (after the seed round); from then on the table lives there: expansion appends to it
+// (append_table), the filter rounds reorganise it in place (device_rebuild) and the host mirrors what it needs (sync_table).
 void Pipeline::upload_table(const std::vector<int>& ids) {
   Tick tk(this, "gpu.upload_table+depth_maps");
-  table_ids_ = ids;
-  table_index_.assign(patches_.size(), -1);
-  for (size_t k = 0; k < ids.size(); ++k) table_index_[ids[k]] = (int)k;
-  static TableArrays t;   // reused by the ~18 uploads of a run: no fresh 60 MB of zero-filled pages per call (marshal writes every slot it sizes)
+  TableArrays t;
   marshal(ids, t);
   if (pmvsb_set_thresholds(gpu_, ncc_threshold_, ncc_threshold_before_)) die("set_thresholds");
   if (pmvsb_set_depth(gpu_, depth_)) die("set_depth");
   if (pmvsb_store_upload(gpu_, (int)ids.size(), t.coords.data(), t.normals.data(), t.ncc.data(), t.dsc.data(), t.ioff.data(), t.images.data(),
                          t.grids.data(), t.voff.data(), t.vimages.data(), t.vgrids.data(), t.timages.data())) die("store_upload");
-  if (pmvsb_build_depth_maps(gpu_)) die("build_depth_maps");
+  if (pmvsb_store_set_seq(gpu_, 0, (int)ids.size(), ids.data())) die("store_set_seq");   // creation order = patch id
+  table_ids_ = ids;
+  device_rebuild(2, nullptr);   // collectPatches numbering + depth maps; _vimages as they are
+}
+
+// CPatchOrganizerS::removePatch for the table patches with keep == 0 (null: none), collectPatches renumbering and
+// CFilter::setDepthMapsVGridsVPGridsAddPatchV(additive) (filter.cpp:734-783), all on the device; mode 2 = renumbering and
+// depth maps only.  The host follows with the permutation.
+void Pipeline::device_rebuild(int mode, const std::vector<uint8_t>* keep) {
+  Tick tk(this, "gpu.table_rebuild");
+  if (pmvsb_set_thresholds(gpu_, ncc_threshold_, ncc_threshold_before_)) die("set_thresholds");
+  if (pmvsb_set_depth(gpu_, depth_)) die("set_depth");
+  std::vector<int32_t> perm(std::max<size_t>(table_ids_.size(), 1));
+  int32_t n = 0;
+  if (pmvsb_store_rebuild(gpu_, keep ? keep->data() : nullptr, mode, &n, perm.data())) die("store_rebuild");
+  std::vector<int> ids(n);
+  for (int k = 0; k < n; ++k) ids[k] = table_ids_[perm[k]];
+  table_ids_.swap(ids);
+  table_index_.assign(patches_.size(), -1);
+  for (int k = 0; k < n; ++k) table_index_[table_ids_[k]] = k;
+}
+
+// the table's lists back into the host patches (what the next expansion round and the writers read), the patches that left
+// the table marked dead, the occupancy of _pgrids recounted
+void Pipeline::sync_table() {
+  Tick tk(this, "host.sync_table");
+  int32_t P = 0, E = 0, VE = 0;
+  if (pmvsb_store_counts(gpu_, &P, &E, &VE)) die("store_counts");
+  if (P != (int)table_ids_.size()) { std::cerr << "sync_table: table size mismatch" << std::endl; std::exit(1); }
+  std::vector<int32_t> seq(std::max(P, 1)), ti(std::max(P, 1)), off(P + 1), im(std::max(E, 1)), gr((size_t)2 * std::max(E, 1)), voff(P + 1),
+      vim(std::max(VE, 1)), vgr((size_t)2 * std::max(VE, 1));
+  if (pmvsb_store_download_lists(gpu_, seq.data(), ti.data(), off.data(), im.data(), gr.data())) die("store_download_lists");
+  if (pmvsb_store_download_vimages(gpu_, voff.data(), vim.data(), vgr.data())) die("store_download_vimages");
+  for (Patch& p : patches_) p.alive = false;
+  parallel_for(P, threads_, [&](int k) {
+    if (seq[k] != table_ids_[k]) { std::cerr << "sync_table: the device and host numberings disagree" << std::endl; std::exit(1); }
+    Patch& p = patches_[table_ids_[k]];
+    p.alive = true;
+    p.timages = ti[k];
+    const int n = off[k + 1] - off[k], nv = voff[k + 1] - voff[k];
+    p.images.assign(im.begin() + off[k], im.begin() + off[k + 1]);
+    p.grids.resize(n);
+    for (int i = 0; i < n; ++i) p.grids[i] = {gr[(size_t)2 * (off[k] + i)], gr[(size_t)2 * (off[k] + i) + 1]};
+    p.vimages.assign(vim.begin() + voff[k], vim.begin() + voff[k + 1]);
+    p.vgrids.resize(nv);
+    for (int i = 0; i < nv; ++i) p.vgrids[i] = {vgr[(size_t)2 * (voff[k] + i)], vgr[(size_t)2 * (voff[k] + i) + 1]};
+  }, 1024);
+  parallel_for(tnum_, threads_, [&](int t) { std::fill(grids_[t].occ.begin(), grids_[t].occ.end(), 0); }, 1);
+  for (int e = 0; e < E; ++e)
+    if (im[e] < tnum_) ++grids_[im[e]].occ[(size_t)gr[(size_t)2 * e + 1] * grids_[im[e]].gw + gr[(size_t)2 * e]];
 }
 
 // CPatchOrganizerS::addPatch + updateDepthMaps for patches committed since the table was uploaded
@@ -215,37 +246,13 @@ void Pipeline::append_table(const std::vector<int>& ids) {
   if (ids.empty()) return;
   Tick tk(this, "gpu.append_table");
   table_index_.resize(patches_.size(), -1);
+  const int first = (int)table_ids_.size();
   for (int id : ids) { table_index_[id] = (int)table_ids_.size(); table_ids_.push_back(id); }
   TableArrays t;
   marshal(ids, t);
   if (pmvsb_store_append(gpu_, (int)ids.size(), t.coords.data(), t.normals.data(), t.ncc.data(), t.dsc.data(), t.ioff.data(), t.images.data(),
                          t.grids.data(), t.voff.data(), t.vimages.data(), t.vgrids.data(), t.timages.data())) die("store_append");
-}
-
-// CFilter::setDepthMapsVGridsVPGridsAddPatchV (filter.cpp:734-783): table -> GPU, depth maps, _vimages/_vgrids of every
-// patch recomputed on the device inside the table (with _vpgrids), then mirrored into the host patches' lists
-void Pipeline::rebuild_depth_and_vis(bool additive) {
-  Tick tk(this, "filter.rebuild_depth_and_vis");
-  const std::vector<int> ids = collect_patches();
-  if (!additive)
-    parallel_for((int)ids.size(), threads_, [&](int k) { patches_[ids[k]].vimages.clear(); patches_[ids[k]].vgrids.clear(); }, 1024);
-  upload_table(ids);
-  const int P = (int)ids.size();
-  if (P == 0) return;
-  int32_t total = 0;
-  if (pmvsb_store_update_vimages(gpu_, additive ? 1 : 0, &total)) die("store_update_vimages");
-  static std::vector<int32_t> voff, vim, vgr;   // reused across the rebuilds (the download overwrites every slot it sizes)
-  voff.resize(P + 1); vim.resize(std::max(1, total)); vgr.resize((size_t)2 * std::max(1, total));
-  if (pmvsb_store_download_vimages(gpu_, voff.data(), vim.data(), vgr.data())) die("store_download_vimages");
-  parallel_for(P, threads_, [&](int k) {
-    Patch& p = patches_[ids[k]];
-    const int n = voff[k + 1] - voff[k];
-    p.vimages.resize(n); p.vgrids.resize(n);
-    for (int i = 0; i < n; ++i) {
-      p.vimages[i] = vim[voff[k] + i];
-      p.vgrids[i] = {vgr[(size_t)2 * (voff[k] + i)], vgr[(size_t)2 * (voff[k] + i) + 1]};
-    }
-  }, 1024);
+  if (pmvsb_store_set_seq(gpu_, first, (int)ids.size(), ids.data())) die("store_set_seq");
 }
 
 // ---------------------------------------------------------------------------------------------- evaluate a wave
@@ -443,8 +450,8 @@ void Pipeline::seed_round() {
   std::cerr << "adding seeds " << std::endl;
   for (auto& g : grids_) std::fill(g.counts.begin(), g.counts.end(), 0);
   for (int im = 0; im < tnum_; ++im)
-    for (size_t c = 0; c < grids_[im].pg.size(); ++c)
-      if (!grids_[im].pg[c].empty()) grids_[im].counts[c] = (unsigned char)count_threshold2_;
+    for (size_t c = 0; c < grids_[im].occ.size(); ++c)
+      if (grids_[im].occ[c] != 0) grids_[im].counts[c] = (unsigned char)count_threshold2_;
   // features binned by cell (seed.cpp:25-36)
   std::vector<std::vector<std::vector<int>>> bins(num_);
   for (int i = 0; i < num_; ++i) {
@@ -458,7 +465,7 @@ void Pipeline::seed_round() {
     if (!get_mask(image, opt_.csize * x, opt_.csize * y)) return false;
     if (tnum_ <= image) return true;
     const size_t c = (size_t)y * grids_[image].gw + x;
-    if (!grids_[image].pg[c].empty()) return false;
+    if (grids_[image].occ[c] != 0) return false;
     return !(count_threshold2_ <= grids_[image].counts[c]);
   };
   const double cos_a0 = std::cos(60.0f * M_PI / 180.0f);
@@ -640,7 +647,7 @@ bool Pipeline::check_counts(const Patch& p) const {   // expand.cpp:258-323; tru
     const int ix = p.grids[i][0], iy = p.grids[i][1];
     if (ix < 0 || g.gw <= ix || iy < 0 || g.gh <= iy) continue;
     const size_t c = (size_t)iy * g.gw + ix;
-    if (!g.pg[c].empty()) { ++full; continue; }
+    if (g.occ[c] != 0) { ++full; continue; }
     if (count_threshold1_ <= g.counts[c]) ++full; else ++empty;
   }
   if (depth_ <= 1) return empty < opt_.minImageNum && full != 0;
@@ -668,12 +675,14 @@ void Pipeline::expand_round() {
   for (auto& g : grids_) std::fill(g.counts.begin(), g.counts.end(), 0);
   for (Patch& p : patches_) p.flag = 0;
   // the queue is ordered by _tmp (patchOrganizerS.hpp:10-15); a wave takes the whole frontier, best first
-  std::vector<int> frontier = collect_patches();
+  // the table is on the device in collectPatches order (uploaded after the seed round, reorganised by the filter rounds)
+  if (!table_ready_) { upload_table(live_patches()); table_ready_ = true; }
+  else device_rebuild(2, nullptr);   // CExpand::run starts from collectPatches + fresh depth maps (expand.cpp:42-47)
+  std::vector<int> frontier = table_ids_;
   for (int id : frontier) patches_[id].flag = 1;
   std::cerr << "Expanding patches..." << std::flush;
   const double two_pi = 2 * M_PI;
   int wave_no = 0;
-  upload_table(collect_patches());   // resident table: neighbour searches, depth maps for setVImagesVGrids of the candidates
   size_t last_table_size = patches_.size();
   while (!frontier.empty()) {
     std::stable_sort(frontier.begin(), frontier.end(), [&](int a, int b) { return patches_[a].tmp > patches_[b].tmp; });
@@ -774,184 +783,80 @@ void Pipeline::expand_round() {
 }
 
 // ---------------------------------------------------------------------------------------------- filters
+// CFilter::run (filter.cpp:13-27).  The table stays on the device for the whole round: every filter is a kernel over it that
+// answers with one keep flag per patch, removal + renumbering + depth maps + _vimages/_vpgrids are pmvsb_store_rebuild, and the
+// host reads the lists back once, at the end of the round (sync_table).
+void Pipeline::apply_keep(const char* name, const std::vector<uint8_t>& keep) {
+  const int P = (int)keep.size();
+  int count = 0;
+  for (int k = 0; k < P; ++k) count += keep[k] ? 0 : 1;
+  std::cerr << P << " -> " << P - count << " (" << 100.0f * (P - count) / std::max(P, 1) << "%)" << std::endl;
+  (void)name;
+  device_rebuild(1, &keep);   // setDepthMapsVGridsVPGridsAddPatchV(1) after every filter
+}
+
 void Pipeline::filter_outside() {   // filter.cpp:29-86
   Tick tk(this, "filter.outside");
   std::cerr << "FilterOutside" << std::endl;
-  const std::vector<int> ids = table_ids_;   // table uploaded by the preceding rebuild
-  const int P = (int)ids.size();
+  const int P = (int)table_ids_.size();
   if (P == 0) return;
   std::vector<float> gains(P);
   if (pmvsb_compute_gains_store(gpu_, gains.data())) die("compute_gains_store");
-  int count = 0;
+  std::vector<uint8_t> keep(P);
   double ave = 0.0, ave2 = 0.0;
   for (int k = 0; k < P; ++k) {
     ave += gains[k]; ave2 += (double)gains[k] * gains[k];
-    if (gains[k] < 0.0f) { remove_patch(ids[k]); ++count; }
+    keep[k] = gains[k] < 0.0f ? 0 : 1;
   }
   ave /= P; ave2 /= P;
   std::cerr << "Gain (ave/var): " << ave << ' ' << std::sqrt(std::max(0.0, ave2 - ave * ave)) << std::endl;
-  std::cerr << P << " -> " << P - count << " (" << 100.0f * (P - count) / P << "%)" << std::endl;
+  apply_keep("outside", keep);
 }
 
 void Pipeline::filter_exact() {   // filter.cpp:203-355
   Tick tk(this, "filter.exact");
   std::cerr << "Filter Exact: " << std::flush;
-  const std::vector<int> ids = table_ids_;
-  const int P = (int)ids.size();
+  const int P = (int)table_ids_.size();
   if (P == 0) return;
-  std::vector<int32_t> eoff(P + 1, 0);
-  for (int k = 0; k < P; ++k) eoff[k + 1] = eoff[k] + (int32_t)patches_[ids[k]].images.size();
-  std::vector<uint8_t> safe(std::max<size_t>(eoff[P], 1));
-  { Tick tk2(this, "gpu.filter_exact");
-  if (pmvsb_filter_exact_store(gpu_, safe.data())) die("filter_exact_store"); }
-  // per patch: surviving target images in ascending image order (the reference visits image by image), then the
-  // non-target images in their old order (filter.cpp:262-272); the cells of the dropped images lose the patch (240-252)
-  struct Entry { int image, gx, gy; };
-  std::vector<std::vector<Entry>> dropped(P);
-  parallel_for(P, threads_, [&](int k) {
-    Patch& p = patches_[ids[k]];
-    std::vector<Entry> keep, other;
-    for (size_t i = 0; i < p.images.size(); ++i) {
-      const int im = p.images[i];
-      const Entry en{im, p.grids[i][0], p.grids[i][1]};
-      if (tnum_ <= im) other.push_back(en);
-      else if (safe[eoff[k] + i]) keep.push_back(en);
-      else dropped[k].push_back(en);
-    }
-    std::stable_sort(keep.begin(), keep.end(), [](const Entry& a, const Entry& b) { return a.image < b.image; });
-    p.timages = (int)keep.size();
-    keep.insert(keep.end(), other.begin(), other.end());
-    p.images.resize(keep.size()); p.grids.resize(keep.size());
-    for (size_t i = 0; i < keep.size(); ++i) { p.images[i] = keep[i].image; p.grids[i] = {keep[i].gx, keep[i].gy}; }
-  }, 1024);
-  std::vector<int> todo;
-  int count = 0;
-  for (int k = 0; k < P; ++k) {
-    for (const Entry& en : dropped[k]) {
-      auto& cell = grids_[en.image].pg[(size_t)en.gy * grids_[en.image].gw + en.gx];
-      cell.erase(std::remove(cell.begin(), cell.end(), ids[k]), cell.end());
-    }
-    if ((int)patches_[ids[k]].images.size() < opt_.minImageNum) { remove_patch(ids[k]); ++count; continue; }
-    todo.push_back(ids[k]);
-  }
-  // setRefImage + setGrids for the survivors (filter.cpp:277-280).  The cells of a kept image are a function of the
-  // patch centre, which has not moved: the patch stays where it is in _pgrids, as in the reference.
-  const int T = (int)todo.size();
-  if (T > 0) {
-    int stride = 1;
-    for (int id : todo) stride = std::max(stride, (int)patches_[id].images.size());
-    stride = std::min(stride, 64);
-    std::vector<float> coords((size_t)4 * T), normals((size_t)4 * T);
-    std::vector<int32_t> images((size_t)stride * T, 0), nimages(T), grids((size_t)2 * stride * T);
-    parallel_for(T, threads_, [&](int j) {
-      const Patch& p = patches_[todo[j]];
-      for (int c = 0; c < 4; ++c) { coords[4 * j + c] = p.coord[c]; normals[4 * j + c] = p.normal[c]; }
-      nimages[j] = std::min((int)p.images.size(), stride);
-      for (int i = 0; i < nimages[j]; ++i) images[(size_t)j * stride + i] = p.images[i];
-    }, 1024);
-    { Tick tk2(this, "gpu.set_ref_image");
-    if (pmvsb_set_ref_image_batch(gpu_, T, stride, coords.data(), normals.data(), images.data(), nimages.data(), grids.data())) die("set_ref_image_batch"); }
-    parallel_for(T, threads_, [&](int j) {
-      if (nimages[j] == 0) return;
-      Patch& p = patches_[todo[j]];
-      p.images.assign(images.begin() + (size_t)j * stride, images.begin() + (size_t)j * stride + nimages[j]);
-      p.grids.resize(nimages[j]);
-      for (int i = 0; i < nimages[j]; ++i) p.grids[i] = {grids[((size_t)j * stride + i) * 2], grids[((size_t)j * stride + i) * 2 + 1]};
-    }, 1024);
-    for (int j = 0; j < T; ++j)
-      if (nimages[j] == 0) { remove_patch(todo[j]); ++count; }
-  }
-  std::cerr << std::endl << P << " -> " << P - count << " (" << 100.0f * (P - count) / P << "%)" << std::endl;
+  std::vector<uint8_t> keep(P);
+  if (pmvsb_filter_exact_apply_store(gpu_, keep.data())) die("filter_exact_apply_store");
+  std::cerr << std::endl;
+  apply_keep("exact", keep);
 }
 
-void Pipeline::filter_neighbor() {   // filter.cpp:357-392, 464-519 (times = 1): one kernel over the table of the preceding rebuild
-  Tick tk(this, "gpu.filter_neighbor");
+void Pipeline::filter_neighbor() {   // filter.cpp:357-392, 464-519 (times = 1)
+  Tick tk(this, "filter.neighbor");
   std::cerr << "FilterNeighbor:\t" << std::flush;
-  const std::vector<int> ids = table_ids_;
-  const int P = (int)ids.size();
+  const int P = (int)table_ids_.size();
   if (P == 0) return;
-  std::vector<uint8_t> reject(P, 0);
+  std::vector<uint8_t> keep(P, 0);
   int32_t overflow = 0;
-  if (pmvsb_filter_neighbor_store(gpu_, opt_.quad, reject.data(), nullptr, nullptr, &overflow)) die("filter_neighbor_store");
+  if (pmvsb_filter_neighbor_store(gpu_, opt_.quad, keep.data(), nullptr, nullptr, &overflow)) die("filter_neighbor_store");
   if (overflow) std::cerr << "(" << overflow << " patches with more neighbours than the kernel keeps: not fitted) ";
-  int count = 0;
-  for (int k = 0; k < P; ++k) if (reject[k]) { remove_patch(ids[k]); ++count; }
-  std::cerr << P << " -> " << P - count << " (" << 100.0f * (P - count) / P << "%)" << std::endl;
+  for (int k = 0; k < P; ++k) keep[k] = keep[k] ? 0 : 1;   // the kernel answers with reject flags
+  apply_keep("neighbor", keep);
 }
 
 void Pipeline::filter_small_groups() {   // filter.cpp:524-665
-  Tick tk(this, "host.filter_small_groups");
+  Tick tk(this, "filter.small_groups");
   std::cerr << "FilterGroups:\t" << std::flush;
-  const std::vector<int> ids = collect_patches();
-  const int P = (int)ids.size();
+  const int P = (int)table_ids_.size();
   if (P == 0) return;
-  // _vpgrids of the current table (addPatchV, filter.cpp:773-781): per image, patches in table order
-  parallel_for(tnum_, threads_, [&](int im) {
-    ImageGrid& g = grids_[im];
-    for (auto& cell : g.vpg) cell.clear();
-    for (int k = 0; k < P; ++k) {
-      const Patch& p = patches_[ids[k]];
-      for (size_t i = 0; i < p.vimages.size(); ++i)
-        if (p.vimages[i] == im) g.vpg[(size_t)p.vgrids[i][1] * g.gw + p.vgrids[i][0]].push_back(ids[k]);
-    }
-  }, 1);
-  std::vector<int> index_of(patches_.size(), -1);
-  for (int k = 0; k < P; ++k) index_of[ids[k]] = k;
-  // getUnit of every table patch once (is_neighbor's hunit needs it for both patches of each of the ~1e7 tests)
-  std::vector<float> unit(P);
-  parallel_for(P, threads_, [&](int k) { const Patch& p = patches_[ids[k]]; unit[k] = get_unit(p.images[0], p.coord); }, 4096);
-  std::vector<int> label(P, -1);
-  int id = -1;
-  for (int start = 0; start < P; ++start) {
-    if (label[start] != -1) continue;
-    label[start] = ++id;
-    std::list<int> work{start};
-    while (!work.empty()) {
-      const int k = work.front();
-      work.pop_front();
-      const Patch& p = patches_[ids[k]];
-      const int im = p.images[0], ix = p.grids[0][0], iy = p.grids[0][1];
-      const ImageGrid& g = grids_[im];
-      if (im >= tnum_) continue;
-      for (int y = -1; y <= 1; ++y) {
-        const int yy = iy + y;
-        if (yy < 0 || g.gh <= yy) continue;
-        for (int x = -1; x <= 1; ++x) {
-          const int xx = ix + x;
-          if (xx < 0 || g.gw <= xx) continue;
-          const size_t cell = (size_t)yy * g.gw + xx;
-          for (const std::vector<int>* lst : {&g.pg[cell], &g.vpg[cell]})
-            for (int q : *lst) {
-              const int kq = index_of[q];
-              if (kq < 0 || label[kq] != -1) continue;
-              const float hunit = (float)((unit[k] + unit[kq]) / 2.0 * opt_.csize);   // findMatch.cpp:120-123
-              if (is_neighbor(p, patches_[q], hunit, neighbor_threshold2_, -1.0f)) { label[kq] = id; work.push_back(kq); }
-            }
-        }
-      }
-    }
-  }
-  std::vector<int> size(id + 1, 0);
-  for (int l : label) ++size[l];
-  const int threshold = std::max(20, P / 10000);
+  std::vector<uint8_t> keep(P);
+  int32_t threshold = 0;
+  if (pmvsb_filter_small_groups_store(gpu_, neighbor_threshold2_, keep.data(), &threshold)) die("filter_small_groups_store");
   std::cerr << threshold << std::endl;
-  int count = 0;
-  for (int k = 0; k < P; ++k)
-    if (size[label[k]] < threshold) { remove_patch(ids[k]); ++count; }
-  std::cerr << P << " -> " << P - count << " (" << 100.0f * (P - count) / P << "%)" << std::endl;
+  apply_keep("groups", keep);
 }
 
 void Pipeline::filter_round() {   // filter.cpp:13-27
   Tick tk(this, "round.filter");
-  rebuild_depth_and_vis(false);
+  device_rebuild(0, nullptr);
   filter_outside();
-  rebuild_depth_and_vis(true);
   filter_exact();
-  rebuild_depth_and_vis(true);
   filter_neighbor();
-  rebuild_depth_and_vis(true);
   filter_small_groups();
-  rebuild_depth_and_vis(true);
+  sync_table();
 }
 
 void Pipeline::run() {   // findMatch.cpp:187-220
@@ -992,7 +897,7 @@ void Pipeline::write(const std::string& base, bool ply, bool patch, bool pset) {
   if (!is_root()) return;   // every rank holds the same patches; one of them writes
   {
   Tick tk(this, "write.total");
-  const std::vector<int> ids = collect_patches();
+  const std::vector<int> ids = table_ready_ ? table_ids_ : live_patches();
   const int P = (int)ids.size();
   if (ply) {
     std::vector<uint8_t> rgb((size_t)3 * std::max(P, 1), 0);

@@ -88,7 +88,7 @@ struct Patch {         // Patch::CPatch
 
 struct ImageGrid {     // per image: CPatchOrganizerS::_pgrids / _vpgrids / _counts / _dpgrids of that image
   int gw = 0, gh = 0;
-  std::vector<std::vector<int>> pg, vpg;   // patch ids per cell (target images only)
+  std::vector<int> occ;                    // number of patches in each cell of _pgrids (target images only); the lists are on the device
   std::vector<unsigned char> counts;
 };
 
@@ -118,9 +118,10 @@ class Pipeline {
   bool mask_gate(const float* X) const;                   // getMask(coord, level) != 0 && insideBimages(coord) != 0
   // ---- bookkeeping
   int add_patch(Patch&& p);                 // CPatchOrganizerS::addPatch (takes the lists over)
-  void remove_patch(int id);                // CPatchOrganizerS::removePatch
-  std::vector<int> collect_patches() const; // ids of live patches in the reference's collectPatches order
-  void rebuild_depth_and_vis(bool additive);
+  std::vector<int> live_patches() const;    // ids of the live patches in creation order
+  void device_rebuild(int mode, const std::vector<uint8_t>* keep);
+  void apply_keep(const char* name, const std::vector<uint8_t>& keep);
+  void sync_table();
   struct TableArrays;
   void marshal(const std::vector<int>& ids, TableArrays& t) const;
   void upload_table(const std::vector<int>& ids);
@@ -161,6 +162,7 @@ class Pipeline {
   std::vector<Patch> patches_;
   std::vector<int> table_ids_;              // table index -> patch id, for the table resident on the GPU
   std::vector<int> table_index_;            // patch id -> table index (-1: not in the table)
+  bool table_ready_ = false;                // the table has been uploaded (after the seed round)
   std::map<std::string, double> seconds_;   // wall time per phase (printed by write())
  public:
   struct Tick {

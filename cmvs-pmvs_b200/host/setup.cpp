@@ -349,8 +349,7 @@ void Pipeline::load() {
     ImageGrid& g = grids_[i];
     if (pmvsb_grid_dims(gpu_, i, &g.gw, &g.gh)) die("grid_dims");
     if (i < tnum_) {
-      g.pg.assign((size_t)g.gw * g.gh, {});
-      g.vpg.assign((size_t)g.gw * g.gh, {});
+      g.occ.assign((size_t)g.gw * g.gh, 0);
       g.counts.assign((size_t)g.gw * g.gh, 0);
     }
   }

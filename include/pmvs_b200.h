@@ -176,6 +176,36 @@ int pmvsb_set_vimages_store(pmvsb_ctx* ctx, int vcap, int32_t* vimages, int32_t*
  * (vimg_off int32[P+1], vimages int32[total], vgrids int32[2*total]). */
 int pmvsb_store_update_vimages(pmvsb_ctx* ctx, int additive, int32_t* total);
 int pmvsb_store_download_vimages(pmvsb_ctx* ctx, int32_t* vimg_off, int32_t* vimages, int32_t* vgrids);
+/* ---- the table reorganised on the device: a filter round without marshalling patches through the host ----------------------
+ * Creation sequence numbers of table patches [first, first + n): the order of a cell's patch vector in the reference (addPatch
+ * appends, patchOrganizerS.cpp:312-349).  Default after pmvsb_store_upload: the table order; appended patches are younger than
+ * every patch before them. */
+int pmvsb_store_set_seq(pmvsb_ctx* ctx, int first, int n, const int32_t* seq);
+int pmvsb_store_counts(pmvsb_ctx* ctx, int32_t* P, int32_t* entries, int32_t* ventries);
+/* CPatchOrganizerS::removePatch for the patches with keep[k] == 0 (keep = NULL: none), then
+ * CFilter::setDepthMapsVGridsVPGridsAddPatchV(additive) (source/pmvs/filter.cpp:734-783): the survivors renumbered in
+ * collectPatches order (patchOrganizerS.cpp:207-236: first appearance in (image, cell) order, creation order inside a cell),
+ * _pgrids rebuilt, depth maps (setDepthMaps), setVImagesVGrids for every patch (additive = 0 from empty _vimages), _vpgrids.
+ * additive = 2: renumbering and depth maps only, _vimages kept as they are (collectPatches + setDepthMaps, what the table needs
+ * when an expansion round starts, expand.cpp:42-47).
+ * new_count = patches left; perm (optional, int32[new_count]) = the OLD table index of each patch of the new table. */
+int pmvsb_store_rebuild(pmvsb_ctx* ctx, const uint8_t* keep, int additive, int32_t* new_count, int32_t* perm);
+/* CFilter::filterExact on the table (filter.cpp:203-355): the visibility re-test of every image entry (filterExactThread), the
+ * lists pruned (surviving target images in ascending image order, then the non-target ones), _timages, then setRefImage +
+ * setGrids for the survivors; keep[k] = 0 for a patch left with fewer than minImageNum images or without a target image
+ * (its lists are emptied; pmvsb_store_rebuild removes it).  _pgrids is rebuilt; depth maps and _vimages are untouched. */
+int pmvsb_filter_exact_apply_store(pmvsb_ctx* ctx, uint8_t* keep);
+/* The neighbour tests of CFilter::filterSmallGroupsSub (filter.cpp:602-665) for every table patch p: the patches q listed in
+ * _pgrids / _vpgrids of the 3x3 cells around p's cell in its reference image with isNeighbor(p, q, neighbor_threshold), as CSR
+ * adjacency (adj_off int32[P+1]; adj int32[*total], written when *total <= cap: call once with cap = 0 to size it). */
+int pmvsb_small_group_edges_store(pmvsb_ctx* ctx, float neighbor_threshold, int32_t* adj_off, int32_t* adj, int cap, int32_t* total);
+/* CFilter::filterSmallGroups (filter.cpp:524-600): keep[k] = 0 for the patches of a connected group smaller than
+ * *group_threshold = max(20, P / 10000).  The neighbour tests run on the device (above); the labelling walk is sequential by
+ * definition (a patch takes the label of the first walk that reaches it) and runs over that adjacency on the calling thread. */
+int pmvsb_filter_small_groups_store(pmvsb_ctx* ctx, float neighbor_threshold, uint8_t* keep, int32_t* group_threshold);
+/* table lists back to the host (any pointer may be NULL): seq, timages int32[P]; img_off int32[P+1]; images int32[E];
+ * grids int32[2E] (P, E from pmvsb_store_counts); _vimages through pmvsb_store_download_vimages */
+int pmvsb_store_download_lists(pmvsb_ctx* ctx, int32_t* seq, int32_t* timages, int32_t* img_off, int32_t* images, int32_t* grids);
 /* _pgrids (visible = 0) / _vpgrids (1) of the table as the device built them: cell_off int32[cells+1] over the
  * flattened cells of the target images in image order, cell_patch int32[cell_off[cells]] (may be NULL) -- parity hook */
 int pmvsb_download_cell_lists(pmvsb_ctx* ctx, int visible, int32_t* cell_off, int32_t* cell_patch);

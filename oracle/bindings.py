@@ -473,6 +473,23 @@ class RefLib(_Common):
         rej = self.lib.ref_filter_neighbor(int(k), C.c_float(quad), C.byref(cnt))
         return int(rej), cnt.value
 
+    def remove_and_rebuild(self, keep, additive=1):
+        """removePatch where keep == 0, then setDepthMapsVGridsVPGridsAddPatchV(additive) -> former table index of each new table patch"""
+        keep = np.ascontiguousarray(keep, dtype=np.uint8)
+        out = np.zeros(len(keep), np.int32)
+        n = self.lib.ref_remove_and_rebuild(keep.ctypes.data_as(C.c_void_p), int(additive), out.ctypes.data_as(C.c_void_p), len(out))
+        return out[:n].copy()
+
+    def filter_small_groups(self, cap):
+        out = np.zeros(cap, np.int32)
+        n = self.lib.ref_filter_small_groups(out.ctypes.data_as(C.c_void_p), cap)
+        return out[:n].copy()
+
+    def filter_exact(self, cap):
+        out = np.zeros(cap, np.int32)
+        n = self.lib.ref_filter_exact(out.ctypes.data_as(C.c_void_p), cap)
+        return out[:n].copy()
+
     def depth_flag(self):
         return self.lib.ref_get_depth_flag()
 

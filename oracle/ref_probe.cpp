@@ -444,6 +444,36 @@ int ref_check(int k, float quad, float* gain) {
   *gain = p._tmp;
   return r;
 }
+// ---- filter-round stages on the reference's own state --------------------------------------------------------------
+// removePatch for the table patches (numbering of ref_collect_patches) with keep[k] == 0, then
+// CFilter::setDepthMapsVGridsVPGridsAddPatchV(additive); old_index[i] = former table index of new table patch i.
+static std::map<const Patch::CPatch*, int> g_old_index;
+static int report_old_indexes(int* old_index, int cap) {
+  g_fm->_pos.collectPatches(0);
+  const int n = (int)g_fm->_pos._ppatches.size();
+  for (int i = 0; i < n && i < cap; ++i) old_index[i] = g_old_index[g_fm->_pos._ppatches[i].get()];
+  return n;
+}
+int ref_remove_and_rebuild(const unsigned char* keep, int additive, int* old_index, int cap) {
+  g_fm->_pos.collectPatches(0);
+  const std::vector<Patch::PPatch> pp = g_fm->_pos._ppatches;
+  g_old_index.clear();
+  for (int k = 0; k < (int)pp.size(); ++k) g_old_index[pp[k].get()] = k;
+  for (int k = 0; k < (int)pp.size(); ++k)
+    if (!keep[k]) g_fm->_pos.removePatch(pp[k]);
+  g_fm->_filter.setDepthMapsVGridsVPGridsAddPatchV(additive);
+  return report_old_indexes(old_index, cap);
+}
+// CFilter::filterSmallGroups on the current state; survivors as former table indexes (numbering of the last ref_remove_and_rebuild)
+int ref_filter_small_groups(int* old_index, int cap) {
+  g_fm->_filter.filterSmallGroups();
+  return report_old_indexes(old_index, cap);
+}
+// CFilter::filterExact on the current state (depth maps of the last rebuild); survivors as former table indexes
+int ref_filter_exact(int* old_index, int cap) {
+  g_fm->_filter.filterExact();
+  return report_old_indexes(old_index, cap);
+}
 int ref_get_depth_flag(void) { return g_fm->_depth; }
 float ref_neighbor_threshold(int which) { return which == 0 ? g_fm->_neighborThreshold : (which == 1 ? g_fm->_neighborThreshold1 : g_fm->_neighborThreshold2); }
 

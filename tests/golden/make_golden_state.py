@@ -75,6 +75,27 @@ def main():
     # the final table has already been through the filter at quad 2.5; tighter thresholds exercise filterQuad's fit
     out["fnb_quads"] = np.array([0.03, 0.1, 0.5], np.float32)
     out["fnb_reject_q"] = np.array([[ref.filter_neighbor(k, float(q))[0] for k in range(P)] for q in out["fnb_quads"]], np.uint8)
+    # ---- filter-round stages that change the table (run last: they mutate the reference's state) -------------------------
+    # (1) a fragmented table: 55 % of the patches removed in blobs, setDepthMapsVGridsVPGridsAddPatchV(1), then filterSmallGroups
+    cell = np.floor(st["coords"][:, :3] * 4.0).astype(np.int64)
+    blob = (cell[:, 0] * 73856093 ^ cell[:, 1] * 19349663 ^ cell[:, 2] * 83492791) % 100
+    keep0 = ((blob >= 55) | (rng.random(P) < 0.03)).astype(np.uint8)
+    out["frag_keep"] = keep0
+    out["frag_perm"] = ref.remove_and_rebuild(keep0, additive=1)
+    frag = ref.state()
+    out["frag_vimg_off"] = frag["vimg_off"]; out["frag_vimages"] = frag["vimages"]; out["frag_vgrids"] = frag["vgrids"]
+    out["frag_groups_survivors"] = ref.filter_small_groups(P)
+    # (2) on what is left: everything rebuilt from empty _vimages (additive 0), then filterExact
+    left = ref.state()
+    out["exact_perm"] = ref.remove_and_rebuild(np.ones(len(left["ncc"]), np.uint8), additive=0)
+    before = ref.state()
+    out["exact_vimg_off"] = before["vimg_off"]; out["exact_vimages"] = before["vimages"]
+    out["exact_survivors"] = ref.filter_exact(len(before["ncc"]))
+    after = ref.state()
+    out["exact_img_off"] = after["img_off"]; out["exact_images"] = after["images"]; out["exact_grids"] = after["grids"]
+    out["exact_timages"] = after["timages"]
+    print("fragmented table:", int(keep0.sum()), "kept ->", len(out["frag_perm"]), "-> small groups leave", len(out["frag_groups_survivors"]),
+          "-> filterExact leaves", len(out["exact_survivors"]), "image entries", int(before["img_off"][-1]), "->", int(after["img_off"][-1]))
     path = os.path.join(HERE, "pmvs_state.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes; patches", P, "visible", np.bincount(out["vis_answer"]), "neighbours",

@@ -77,9 +77,10 @@ def test_pre_process_ragged_and_empty(gpu, pkg, scene, candidates):
     out = gpu.pre_process_batch(pb["coords"][:P], pb["normals"][:P], images, n)
     assert out["verdict"][0] == 1 and out["nimages"][0] == 0
     # a capacity smaller than what addImages finds is an ERROR (the reference's lists are unbounded), never a silent cap
-    small = np.zeros((P, 4), np.int32); small[:, :3] = pb["images"][:P, :3]
+    # (on this ring of cameras a surface point has ~3 cameras inside the 60-degree cone: one listed + two found > capacity 2)
+    small = np.zeros((P, 2), np.int32); small[:, :1] = pb["images"][:P, :1]
     with pytest.raises(pkg.PmvsError, match="more images than the list capacity"):
-        gpu.pre_process_batch(pb["coords"][:P], pb["normals"][:P], small, n)
+        gpu.pre_process_batch(pb["coords"][:P], pb["normals"][:P], small, np.ones(P, np.int32))
     # the context stays usable and the flag is cleared
     again = gpu.pre_process_batch(pb["coords"][:P], pb["normals"][:P], images, n)
     assert np.array_equal(again["images"], out["images"]) and np.array_equal(again["verdict"], out["verdict"])
