@@ -238,9 +238,10 @@ def write_scene_for_reference(scene, cpu_threads, tag="scene"):
     return prefix
 
 
-def reference_rate(scene, patches, seconds, steps=1, warmup=0, full=None):
+def reference_rate(scene, patches, seconds, steps=1, warmup=0, full=None, ref_xtol_seconds=0.0):
     """Times COptim::refinePatch of the reference build over a bounded sample on all host cores.
-    Returns dict(value, cores, kind, sample, ms_per_step, evals_per_patch)."""
+    Returns dict(value, cores, kind, sample, ms_per_step, evals_per_patch).  ref_xtol_seconds > 0 adds `at_reference_xtol`:
+    the same loop with the stand-in optimiser's tolerance floor removed, i.e. at the reference's own xtol_rel 1e-7."""
     from oracle import bindings as ob
     cores = os.cpu_count() or 1
     coords, normals, images, dsc = patches
@@ -262,7 +263,17 @@ def reference_rate(scene, patches, seconds, steps=1, warmup=0, full=None):
         if it >= warmup:
             times.append(r["seconds"]); evals.append(float(r["evals"].mean()))
     total = float(sum(times))
-    return dict(value=per_step * len(times) / total, cores=cores, kind=kind,
+    extra = {}
+    if ref_xtol_seconds > 0 and kind == "reference":
+        lib.set_xtol_floor(0.0)
+        m = int(max(256, min(len(coords), rate * ref_xtol_seconds / 1.6)))
+        r2 = lib.refine_batch(coords[:m], normals[:m], images[:m], dsc[:m], threads=cores)
+        lib.set_xtol_floor(1.0e-4)
+        extra["at_reference_xtol"] = {"value": m / max(r2["seconds"], 1e-9), "unit": UNIT, "xtol": 1.0e-7, "evals_per_patch": float(r2["evals"].mean()),
+                                      "ok_fraction": float(r2["ok"].mean()), "sample": "%d patches" % m,
+                                      "note": "Nelder-Mead stand-in run down to the reference's xtol_rel 1e-7 (floor 0): the f32 objective is flat below ~1e-5, "
+                                              "the extra evaluations walk a plateau"}
+    return dict(extra, value=per_step * len(times) / total, cores=cores, kind=kind,
                 sample="%d-patch sample of the %d-patch step (same generator, seed 4) per step x %d steps, COptim::refinePatch on %d host threads" % (per_step, full or len(coords), len(times), cores),
                 ms_per_step=1000.0 * total / len(times), evals_per_patch=float(np.mean(evals)), unit=UNIT)
 
@@ -287,25 +298,24 @@ def main():
         dev = "cuda:0" if torch.cuda.is_available() else "cpu"
         pkg, scene = build_scene(args, dev)
         n = min(args.patches, 1 << 16)
-        if torch.cuda.is_available():
-            lib = pkg.PmvsB200.from_scene(scene)
-            patches = make_seed_patches(scene, lib, n, seed=4, device=dev)
-            lib.close()
-        else:
-            from oracle import bindings as ob
-            orc = ob.OracleLib.from_scene(scene)
+        # the seed patches of this arm never touch libpmvs_b200.so: setScales comes from the CPU oracle (bit-exact with the
+        # kernel's, tests/test_gpu_parity.py), so the only native code this process loads is oracle/
+        from oracle import bindings as ob
+        orc = ob.OracleLib.from_scene(scene)
 
-            class _S:  # set_scales through the oracle when no GPU exists (CPU-only debugging)
-                def set_scales_batch(self, c, im):
-                    d = np.array([orc.set_scales(c[i], im[i])[0] for i in range(len(c))], np.float32)
-                    return d, d
-            patches = make_seed_patches(scene, _S(), n, seed=4, device=dev)
-        r = reference_rate(scene, patches, seconds=max(20.0, 8.0 * (args.steps + args.warmup)), steps=args.steps, warmup=args.warmup, full=args.patches)
+        class _S:
+            def set_scales_batch(self, c, im):
+                d = np.array([orc.set_scales(c[i], im[i])[0] for i in range(len(c))], np.float32)
+                return d, d
+        patches = make_seed_patches(scene, _S(), n, seed=4, device=dev)
+        r = reference_rate(scene, patches, seconds=max(20.0, 8.0 * (args.steps + args.warmup)), steps=args.steps, warmup=args.warmup, full=args.patches,
+                           ref_xtol_seconds=6.0)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
-                                 "evals_per_patch": r["evals_per_patch"]},
+                                 "evals_per_patch": r["evals_per_patch"], "optimizer": "reference objective (COptim::my_f) + nm3 Nelder-Mead stand-in for nlopt BOBYQA, xtol 1e-4",
+                                 "at_reference_xtol": r.get("at_reference_xtol")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         if not args.no_pipeline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "pmvs3_ref")):
@@ -398,7 +408,7 @@ def main():
         if r != 0:
             raise RuntimeError(lib.lib.pmvsb_last_error(lib.ctx).decode())
 
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, args.steps)      # the same number of timed steps as `value`
     step_e2e()
     barrier()
     t0 = time.perf_counter()
@@ -414,29 +424,32 @@ def main():
     d2h = P * (16 + 16 + 4 + 4 + 1)
 
     # ---- roofline of the dominant kernel (k_refine) ----------------------------------------------------
+    # PRIMARY bound: the SM's texture pipe.  The kernel's gathers are TLD4 through L1TEX (hit rates 89 % L1 / 99.7 % L2, 143 MB of
+    # DRAM per launch), so HBM is not what limits it; one warp-wide TLD4 occupies the pipe of its SM for clk_per_tld4 cycles
+    # whatever its active lanes (tools/probe/tex_lane_probe.cu on B200: 24.9 clk per warp-row of three one-channel gathers).
+    # achieved = TLD4 issued per second by this launch, peak = what 148 pipes can retire; frac = achieved / peak.
+    # SECONDARY (`hbm_formula`): SURVEY.md 8d's algorithmic bytes (588 B x views x (evaluations + 1) per patch) over the measured
+    # copy bandwidth, kept for continuity with round 1.
     peak, peak_kind = peaks()
     alg_bytes = BYTES_PER_VIEW_EVAL * VIEWS * (evals_sum + P)          # 588 * V * (E + 1) summed over the launch
     k_ms = float(np.mean(kernel_ms))
     achieved = alg_bytes / (k_ms / 1000.0) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_refine_g<7, atlas>", "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth",
-                "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(P), "kernel_ms": k_ms,
-                "algorithmic_bytes_per_launch": alg_bytes, "evals_per_patch": evals_sum / P,
-                "note": "algorithmic bytes = 588 B x views x (evaluations + 1) per patch (SURVEY.md 8d); most gathers hit L1/L2, "
-                        "so HBM traffic is far below this figure; the kernel is bound by instruction issue (76 %) and TLD4 latency/throughput "
-                        "(texture data pipe 75 %), profiles/r1_k_refine_g_v8_full_ncu_metrics.csv"}
-
-    # the limit the kernel actually runs against: its texture pipe.  One evaluation of a warp's four patches
-    # issues views x wsize rows x 3 one-channel TLD4, each ~8.3 clk of the SM's pipe whatever its active lanes
-    # (profiles/r1_tex_lane_probe.txt: 24.9 clk per warp-row of three gathers on B200)
-    try:
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        clk_hz = 1.0e6 * float(clocks.get("sm_mhz") or 1965.0)
-        warp_evals = (evals_sum + P) / 4.0                               # optimiser evaluations + the final computeINCC, 4 patches per warp
-        floor_ms = 1000.0 * warp_evals * VIEWS * 7 * 24.9 / (sms * clk_hz)
-        roofline["texture_pipe_floor"] = {"floor_ms": floor_ms, "frac": floor_ms / k_ms, "clk_per_warp_row": 24.9, "sms": int(sms),
-                                          "source": "profiles/r1_tex_lane_probe.txt"}
-    except Exception as e:  # an annotation only: never fail the bench line over it
-        roofline["texture_pipe_floor"] = {"unavailable": str(e)[:120]}
+    hbm_formula = {"achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth", "unit": "GB/s", "frac": achieved / peak,
+                   "algorithmic_bytes_per_launch": alg_bytes, "traffic": measured_traffic(P)}
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    clk_hz = 1.0e6 * float(clocks.get("sm_mhz") or 1965.0)
+    clk_per_tld4 = 24.9 / 3.0
+    warp_evals = (evals_sum + P) / 4.0                                   # optimiser evaluations + the final computeINCC, 4 patches per warp
+    tld4 = warp_evals * VIEWS * 7 * 3                                    # views x wsize rows x three one-channel gathers
+    tld4_rate = tld4 / (k_ms / 1000.0) / 1e9
+    tld4_peak = sms * clk_hz / clk_per_tld4 / 1e9
+    roofline = {"bound": "texture_pipe", "kernel": "k_refine_g<7, atlas>", "achieved": tld4_rate, "peak": tld4_peak, "unit": "G warp-TLD4/s",
+                "frac": tld4_rate / tld4_peak, "peak_kind": "measured pipe occupancy per TLD4 (%.2f clk, profiles/r1_tex_lane_probe.txt) x %d SMs x %.0f MHz" % (clk_per_tld4, sms, clk_hz / 1e6),
+                "traffic": measured_traffic(P), "kernel_ms": k_ms, "evals_per_patch": evals_sum / P, "tld4_per_launch": tld4,
+                "hbm_formula": hbm_formula,
+                "note": "texel gathers are served by L1TEX / L2 (DRAM traffic per launch = `traffic` bytes, 0.03 % of the algorithmic bytes), so the "
+                        "binding unit is the texture pipe (ncu: 75 % busy) next to instruction issue (76 %), profiles/r1_k_refine_g_v8_full_ncu_metrics.csv; "
+                        "hbm_formula is SURVEY.md 8d's algorithmic-bytes fraction of the measured HBM copy bandwidth"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -447,9 +460,10 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = min(P, 1 << 16)
-        r = reference_rate(scene, (coords[:n], normals[:n], images[:n], dsc[:n]), seconds=args.cpu_seconds, full=P)
+        r = reference_rate(scene, (coords[:n], normals[:n], images[:n], dsc[:n]), seconds=args.cpu_seconds, full=P, ref_xtol_seconds=5.0)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
-                                "evals_per_patch": r["evals_per_patch"]}
+                                "evals_per_patch": r["evals_per_patch"], "optimizer": "reference objective (COptim::my_f) + nm3 Nelder-Mead stand-in for nlopt BOBYQA, xtol 1e-4",
+                                "at_reference_xtol": r.get("at_reference_xtol")}
     lib.close()
     if rank == 0 and world == 1 and not args.no_pipeline:
         line["pipeline"] = pipeline_wall_time(scene, "b200")

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("PMVS_B200_LIB") or os.path.join(HERE, "lib", "libpmvs
 
 # every symbol include/pmvs_b200.h declares
 SYMBOLS = [
-    "pmvsb_create", "pmvsb_destroy", "pmvsb_last_error", "pmvsb_version", "pmvsb_upload_camera", "pmvsb_upload_image",
+    "pmvsb_create", "pmvsb_destroy", "pmvsb_last_error", "pmvsb_version", "pmvsb_device_count", "pmvsb_upload_camera", "pmvsb_upload_image",
     "pmvsb_upload_mask", "pmvsb_set_edge", "pmvsb_set_bimages", "pmvsb_download_mask", "pmvsb_mask_gate_batch",
     "pmvsb_remove_images_edge_batch", "pmvsb_store_set_seq", "pmvsb_store_counts", "pmvsb_store_rebuild", "pmvsb_filter_exact_apply_store",
     "pmvsb_small_group_edges_store", "pmvsb_filter_small_groups_store", "pmvsb_store_download_lists", "pmvsb_set_visdata2", "pmvsb_finalize_scene", "pmvsb_set_thresholds", "pmvsb_set_optimizer", "pmvsb_image_dims",

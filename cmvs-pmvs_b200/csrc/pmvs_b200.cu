@@ -920,6 +920,8 @@ int check_ready(pmvsb_ctx* ctx) {
     if ((ctx)->wsize == 5) {                                                                    \
       if ((stride) <= 16) LAUNCH(5, 16); else if ((stride) <= 32) LAUNCH(5, 32);                \
       else if ((stride) <= 48) LAUNCH(5, 48); else LAUNCH(5, 64);                               \
+    } else if ((ctx)->wsize == 9) {   /* 243 floats per view: 32 views fill the 48 KB of static shared memory */ \
+      if ((stride) <= 16) LAUNCH(9, 16); else LAUNCH(9, 32);                                    \
     } else {                                                                                    \
       if ((stride) <= 16) LAUNCH(7, 16); else if ((stride) <= 32) LAUNCH(7, 32);                \
       else if ((stride) <= 48) LAUNCH(7, 48); else LAUNCH(7, 64);                               \
@@ -1084,7 +1086,12 @@ static int check_lists(pmvsb_ctx* ctx, const char* who, int count, const int32_t
 
 extern "C" {
 
-const char* pmvsb_version(void) { return "pmvs-b200 0.1 (sm_100a)"; }
+const char* pmvsb_version(void) { return "pmvs-b200 0.2 (sm_100a)"; }
+
+int pmvsb_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 
 const char* pmvsb_last_error(const pmvsb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
@@ -2098,7 +2105,7 @@ int pmvsb_filter_exact_apply_store(pmvsb_ctx* ctx, uint8_t* keep) {
   int r = need_store(ctx, true);
   if (r) return r;
   if (!keep) return fail(ctx, PMVSB_EINVAL, "filter_exact_apply_store: null pointer");
-  if (ctx->wsize == 9) return fail(ctx, PMVSB_EINVAL, "filter_exact_apply_store: wsize 9 is not supported by the selection kernels");
+  if (ctx->wsize == 9 && ctx->num > 32) return fail(ctx, PMVSB_EINVAL, "filter_exact_apply_store: wsize 9 keeps at most 32 images per patch in the selection kernels");
   StoreBufs& b = ctx->sb;
   const int P = ctx->store.P, E = ctx->store_entries;
   if (P == 0) return PMVSB_OK;
@@ -2121,6 +2128,9 @@ int pmvsb_filter_exact_apply_store(pmvsb_ctx* ctx, uint8_t* keep) {
     LAUNCH_SET_REF(5, 16, 0);
     if (stride > 16) { LAUNCH_SET_REF(5, 32, 16); }
     if (stride > 32) { LAUNCH_SET_REF(5, 64, 32); }
+  } else if (ctx->wsize == 9) {
+    LAUNCH_SET_REF(9, 16, 0);
+    if (stride > 16) { LAUNCH_SET_REF(9, 32, 16); }
   } else {
     LAUNCH_SET_REF(7, 16, 0);
     if (stride > 16) { LAUNCH_SET_REF(7, 32, 16); }
@@ -2370,7 +2380,7 @@ int pmvsb_set_ref_image_batch(pmvsb_ctx* ctx, int P, int stride, const float* co
   int r = check_ready(ctx);
   if (r) return r;
   if (!normals || !nimages || !grids) return fail(ctx, PMVSB_EINVAL, "set_ref_image_batch: null pointer");
-  if (ctx->wsize == 9) return fail(ctx, PMVSB_EINVAL, "set_ref_image_batch: wsize 9 is not supported by the selection kernels");
+  if (ctx->wsize == 9 && std::min(stride, ctx->num) > 32) return fail(ctx, PMVSB_EINVAL, "set_ref_image_batch: wsize 9 keeps at most 32 images per patch in the selection kernels");
   if (P == 0) return PMVSB_OK;
   PatchStage st;
   r = stage_patches(ctx, st, P, stride, coords, normals, images, nimages, nullptr);
@@ -2384,6 +2394,9 @@ int pmvsb_set_ref_image_batch(pmvsb_ctx* ctx, int P, int stride, const float* co
     LAUNCH_SET_REF(5, 16, 0);
     if (stride > 16) { LAUNCH_SET_REF(5, 32, 16); }
     if (stride > 32) { LAUNCH_SET_REF(5, 64, 32); }
+  } else if (ctx->wsize == 9) {
+    LAUNCH_SET_REF(9, 16, 0);
+    if (stride > 16) { LAUNCH_SET_REF(9, 32, 16); }
   } else {
     LAUNCH_SET_REF(7, 16, 0);
     if (stride > 16) { LAUNCH_SET_REF(7, 32, 16); }
@@ -2470,7 +2483,7 @@ int pmvsb_pre_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coor
   int r = check_ready(ctx);
   if (r) return r;
   if (!normals || !nimages || !dscale || !ascale || !verdict) return fail(ctx, PMVSB_EINVAL, "pre_process_batch: null pointer");
-  if (ctx->wsize == 9) return fail(ctx, PMVSB_EINVAL, "pre_process_batch: wsize 9 is not supported by the selection kernels");
+  if (ctx->wsize == 9 && std::min(stride, ctx->num) > 32) return fail(ctx, PMVSB_EINVAL, "pre_process_batch: wsize 9 keeps at most 32 images per patch in the selection kernels");
   if (P == 0) return PMVSB_OK;
   PatchStage st;
   r = stage_patches(ctx, st, P, stride, coords, normals, images, nimages, nullptr);
@@ -2497,7 +2510,7 @@ int pmvsb_post_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coo
   int r = check_ready(ctx);
   if (r) return r;
   if (!normals || !ncc || !nimages || !grids || !timages || !tmp || !verdict) return fail(ctx, PMVSB_EINVAL, "post_process_batch: null pointer");
-  if (ctx->wsize == 9) return fail(ctx, PMVSB_EINVAL, "post_process_batch: wsize 9 is not supported by the selection kernels");
+  if (ctx->wsize == 9 && std::min(stride, ctx->num) > 32) return fail(ctx, PMVSB_EINVAL, "post_process_batch: wsize 9 keeps at most 32 images per patch in the selection kernels");
   if (P == 0) return PMVSB_OK;
   PatchStage st;
   r = stage_patches(ctx, st, P, stride, coords, normals, images, nimages, nullptr);

@@ -33,9 +33,11 @@ int main(int argc, char* argv[]) {
   for (int i = 0; i < argc; ++i) std::cout << std::endl << argv[i];
   std::cout << std::endl;
   const pmvs::Options opt = pmvs::parse_options(argv[1], argv[2]);
-  const pmvs::Dist dist = pmvs::Dist::from_env();   // WORLD_SIZE > 1: one process per GPU (distributed.cpp)
-  static std::ofstream quiet;
-  if (dist.rank != 0) { quiet.open("/dev/null"); std::cerr.rdbuf(quiet.rdbuf()); std::cout.rdbuf(quiet.rdbuf()); }   // rank 0 reports
+  pmvs::Dist dist = pmvs::Dist::from_env();   // WORLD_SIZE > 1: one process per GPU (distributed.cpp)
+  // rank 0 reports; the other ranks' streams go to a sink that is never destroyed (the iostream library flushes cerr / cout
+  // at exit, after function-local statics are gone)
+  if (dist.rank != 0) { std::ofstream* quiet = new std::ofstream("/dev/null"); std::cerr.rdbuf(quiet->rdbuf()); std::cout.rdbuf(quiet->rdbuf()); }
+  dist.connect();
   pmvs::Pipeline pipe(opt, dist);
   pipe.load();
   pipe.run();

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -364,54 +365,62 @@ void Pipeline::evaluate(std::vector<Candidate>& cands, std::vector<int>& verdict
   if (dist_.world > 1) exchange_results(cands, verdict);
 }
 
-// Fixed-size record per candidate: verdict, the CPatch fields post-processing produced, its visible-image lists.
+// One message per rank and wave: the verdicts of its shard, then ONLY the accepted candidates' records (header, the
+// CPatch scalars post-processing produced, image and visible-image lists at their real lengths).  The sizes travel over
+// the rendezvous sockets first (that is also where a rank that died is noticed); the messages, padded to the longest, go
+// through one NCCL all-gather (or the sockets with PMVSB_EXCHANGE=tcp).
 void Pipeline::exchange_results(std::vector<Candidate>& cands, std::vector<int>& verdict) {
   Tick tk(this, "gpu.allgather_wave");
   const int P = (int)cands.size(), W = dist_.world;
-  const int stride = std::min(num_, 64), vs = tnum_;
-  const int words = 4 + 12 + 3 * stride + 3 * vs;            // int32 / float32 words per record
-  const int per_rank = (P + W - 1) / W + 1;                   // every shard fits (shards differ by at most one)
-  std::vector<int32_t> send((size_t)per_rank * words, 0), recv((size_t)per_rank * words * W, 0);
   int lo = 0, hi = 0;
   Dist::shard(P, W, dist_.rank, lo, hi);
-  parallel_for(hi - lo, threads_, [&](int j) {
-    const Patch& p = cands[lo + j].patch;
-    int32_t* r = send.data() + (size_t)j * words;
-    float* f = reinterpret_cast<float*>(r + 4);
-    r[0] = verdict[lo + j];
-    if (r[0] != 0) return;
-    r[1] = (int32_t)std::min<size_t>(p.images.size(), stride); r[2] = (int32_t)std::min<size_t>(p.vimages.size(), vs); r[3] = p.timages;
-    for (int c = 0; c < 4; ++c) { f[c] = p.coord[c]; f[4 + c] = p.normal[c]; }
-    f[8] = p.ncc; f[9] = p.dscale; f[10] = p.ascale; f[11] = p.tmp;
-    int32_t* q = r + 16;
-    for (int i = 0; i < r[1]; ++i) { q[i] = p.images[i]; q[stride + 2 * i] = p.grids[i][0]; q[stride + 2 * i + 1] = p.grids[i][1]; }
-    q += 3 * stride;
-    for (int i = 0; i < r[2]; ++i) { q[i] = p.vimages[i]; q[vs + 2 * i] = p.vgrids[i][0]; q[vs + 2 * i + 1] = p.vgrids[i][1]; }
-  }, 256);
-  if (pmvsb_allgather(gpu_, send.data(), send.size() * sizeof(int32_t), recv.data())) die("allgather");
+  std::vector<int32_t> msg;
+  msg.reserve((size_t)(hi - lo) * 64);
+  for (int k = lo; k < hi; ++k) msg.push_back(verdict[k]);
+  for (int k = lo; k < hi; ++k) {
+    if (verdict[k] != 0) continue;
+    const Patch& p = cands[k].patch;
+    const int32_t ni = (int32_t)p.images.size(), nv = (int32_t)p.vimages.size();
+    msg.push_back(ni); msg.push_back(nv); msg.push_back(p.timages);
+    const float f[12] = {p.coord[0], p.coord[1], p.coord[2], p.coord[3], p.normal[0], p.normal[1], p.normal[2], p.normal[3], p.ncc, p.dscale, p.ascale, p.tmp};
+    const size_t at = msg.size();
+    msg.resize(at + 12);
+    std::memcpy(msg.data() + at, f, sizeof(f));
+    for (int i = 0; i < ni; ++i) { msg.push_back(p.images[i]); msg.push_back(p.grids[i][0]); msg.push_back(p.grids[i][1]); }
+    for (int i = 0; i < nv; ++i) { msg.push_back(p.vimages[i]); msg.push_back(p.vgrids[i][0]); msg.push_back(p.vgrids[i][1]); }
+  }
+  std::vector<int64_t> sizes(W, 0);
+  const int64_t mine = (int64_t)msg.size();
+  dist_.allgather(&mine, sizeof(mine), sizes.data());
+  const size_t longest = (size_t)*std::max_element(sizes.begin(), sizes.end());
+  if (longest == 0) return;
+  msg.resize(longest, 0);
+  std::vector<int32_t> all(longest * W);
+  if (dist_.tcp_exchange) dist_.allgather(msg.data(), longest * sizeof(int32_t), all.data());
+  else if (pmvsb_allgather(gpu_, msg.data(), longest * sizeof(int32_t), all.data())) die("allgather");
+  exchanged_bytes_ += (double)longest * sizeof(int32_t) * W;
   for (int rk = 0; rk < W; ++rk) {
     if (rk == dist_.rank) continue;
     int rlo = 0, rhi = 0;
     Dist::shard(P, W, rk, rlo, rhi);
-    const int32_t* base = recv.data() + (size_t)rk * per_rank * words;
-    parallel_for(rhi - rlo, threads_, [&](int j) {
-      const int32_t* r = base + (size_t)j * words;
-      const float* f = reinterpret_cast<const float*>(r + 4);
-      verdict[rlo + j] = r[0];
-      if (r[0] != 0) return;
-      Patch& p = cands[rlo + j].patch;
+    const int32_t* r = all.data() + (size_t)rk * longest;
+    const int32_t* q = r + (rhi - rlo);
+    for (int k = rlo; k < rhi; ++k) {
+      verdict[k] = r[k - rlo];
+      if (verdict[k] != 0) continue;
+      Patch& p = cands[k].patch;
+      const int ni = q[0], nv = q[1];
+      p.timages = q[2];
+      float f[12];
+      std::memcpy(f, q + 3, sizeof(f));
       for (int c = 0; c < 4; ++c) { p.coord[c] = f[c]; p.normal[c] = f[4 + c]; }
       p.ncc = f[8]; p.dscale = f[9]; p.ascale = f[10]; p.tmp = f[11];
-      p.timages = r[3];
-      const int32_t* q = r + 16;
-      p.images.assign(q, q + r[1]);
-      p.grids.resize(r[1]);
-      for (int i = 0; i < r[1]; ++i) p.grids[i] = {q[stride + 2 * i], q[stride + 2 * i + 1]};
-      q += 3 * stride;
-      p.vimages.assign(q, q + r[2]);
-      p.vgrids.resize(r[2]);
-      for (int i = 0; i < r[2]; ++i) p.vgrids[i] = {q[vs + 2 * i], q[vs + 2 * i + 1]};
-    }, 256);
+      q += 15;
+      p.images.resize(ni); p.grids.resize(ni);
+      for (int i = 0; i < ni; ++i, q += 3) { p.images[i] = q[0]; p.grids[i] = {q[1], q[2]}; }
+      p.vimages.resize(nv); p.vgrids.resize(nv);
+      for (int i = 0; i < nv; ++i, q += 3) { p.vimages[i] = q[0]; p.vgrids[i] = {q[1], q[2]}; }
+    }
   }
 }
 
@@ -948,6 +957,7 @@ void Pipeline::write(const std::string& base, bool ply, bool patch, bool pset) {
   std::cerr << "wrote " << P << " patches to " << base << ".*" << std::endl;
   }
   for (const auto& kv : seconds_) std::cerr << "time " << kv.first << ' ' << kv.second << " s" << std::endl;
+  if (dist_.world > 1) std::cerr << "exchange " << dist_.world << " ranks, " << exchanged_bytes_ / 1.0e6 << " MB all-gathered over " << (dist_.tcp_exchange ? "tcp" : "nccl") << std::endl;
 }
 
 }  // namespace pmvs

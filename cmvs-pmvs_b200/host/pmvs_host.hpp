@@ -59,9 +59,13 @@ Options parse_options(const std::string& prefix, const std::string& option);
 // one process per GPU (distributed.cpp); world = 1 is the ordinary single-GPU run
 struct Dist {
   int rank = 0, world = 1, local_rank = 0, port = 0;
+  bool tcp_exchange = false;      // PMVSB_EXCHANGE=tcp: wave exchange over the sockets below instead of NCCL
   std::string master_addr;
+  std::vector<int> fds;           // rank 0: one socket per peer (index = rank); peers: fds[0] = the socket to rank 0
   static Dist from_env();
+  void connect();                 // persistent star through rank 0 (no-op when world == 1)
   void broadcast_from_root(void* buf, size_t n) const;
+  void allgather(const void* send, size_t n, void* recv) const;   // n bytes per rank, rank order
   // contiguous balanced shard of n items for rank r
   static void shard(int n, int world, int r, int& lo, int& hi) { lo = (int)((long long)n * r / world); hi = (int)((long long)n * (r + 1) / world); }
 };
@@ -162,6 +166,7 @@ class Pipeline {
   std::vector<Patch> patches_;
   std::vector<int> table_ids_;              // table index -> patch id, for the table resident on the GPU
   std::vector<int> table_index_;            // patch id -> table index (-1: not in the table)
+  double exchanged_bytes_ = 0.0;            // wave results received over the all-gather (multi-GPU runs)
   bool table_ready_ = false;                // the table has been uploaded (after the seed round)
   std::map<std::string, double> seconds_;   // wall time per phase (printed by write())
  public:

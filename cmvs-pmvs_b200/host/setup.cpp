@@ -292,11 +292,12 @@ void Pipeline::load() {
   });
   int created;
   { Tick tk2(this, "load.create_gpu_context");
-    created = pmvsb_create(&gpu_, dist_.local_rank, num_, tnum_, opt_.level, opt_.csize, opt_.wsize, opt_.minImageNum, opt_.threshold, opt_.maxAngleDeg); }
+    int ndev = pmvsb_device_count();
+    created = pmvsb_create(&gpu_, ndev > 0 ? dist_.local_rank % ndev : dist_.local_rank, num_, tnum_, opt_.level, opt_.csize, opt_.wsize, opt_.minImageNum, opt_.threshold, opt_.maxAngleDeg); }
   { Tick tk2(this, "load.wait_for_files"); reader.join(); }
   if (created != 0)
     fatal("pmvs-b200: cannot create a GPU context (CUDA device required; there is no CPU fallback) or bad options");
-  if (dist_.world > 1) {   // NCCL communicator over the GPUs of this run
+  if (dist_.world > 1 && !dist_.tcp_exchange) {   // NCCL communicator over the GPUs of this run
     Tick tk2(this, "load.nccl_init");
     uint8_t id[128] = {0};
     if (dist_.rank == 0 && pmvsb_comm_unique_id(gpu_, id)) die("comm_unique_id");

@@ -56,6 +56,7 @@ int pmvsb_create(pmvsb_ctx** out, int device, int num_images, int num_target, in
 int pmvsb_destroy(pmvsb_ctx* ctx);
 const char* pmvsb_last_error(const pmvsb_ctx* ctx);
 const char* pmvsb_version(void);
+int pmvsb_device_count(void);   /* CUDA devices visible to this process (0 when there is none) */
 
 /* Image::CCamera::init + updateCamera (source/image/camera.cpp:13-54,109-136) and
  * COptim::setAxesScales (source/pmvs/optim.cpp:43-64): P = 3x4 row-major float32 of txt/%08d.txt. */

@@ -490,6 +490,10 @@ class RefLib(_Common):
         n = self.lib.ref_filter_exact(out.ctypes.data_as(C.c_void_p), cap)
         return out[:n].copy()
 
+    def set_xtol_floor(self, v):
+        """x-tolerance floor of the nm3 stand-in behind the reference's nlopt call (0 = the reference's own 1e-7)"""
+        self.lib.ref_set_xtol_floor(C.c_double(v))
+
     def depth_flag(self):
         return self.lib.ref_get_depth_flag()
 

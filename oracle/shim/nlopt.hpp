@@ -37,6 +37,9 @@ inline void srand(unsigned long) {}
 inline unsigned long long& total_evals() { static unsigned long long v = 0; return v; }
 inline unsigned long long& total_calls() { static unsigned long long v = 0; return v; }
 inline int& last_evals() { static thread_local int v = 0; return v; }
+// The x-tolerance floor at run time (default PMVS_NM_XTOL_FLOOR; 0 = exactly the reference's xtol_rel * step = 1e-7):
+// the optimiser-tolerance studies and bench.py's second CPU figure set it through oracle/ref_probe.cpp.
+inline double& xtol_floor() { static double v = PMVS_NM_XTOL_FLOOR; return v; }
 
 class opt {
  public:
@@ -55,7 +58,7 @@ class opt {
     for (unsigned i = 0; i < _n; ++i)
       if (x[i] < _lb[i] || x[i] > _ub[i]) throw std::invalid_argument("nm3 shim: x out of bounds");
     const double step = PMVS_NM_STEP;
-    const double xtol = std::fmax(_xtol_rel * step, PMVS_NM_XTOL_FLOOR);
+    const double xtol = std::fmax(_xtol_rel * step, xtol_floor());
     int nev = 0;
     const int maxeval = _maxeval > 0 ? _maxeval : 1000000;
     int r = nm3_minimize(_n, &opt::thunk, this, _lb.data(), _ub.data(), x.data(), &minf, step,

@@ -115,6 +115,27 @@ def test_two_gpus_write_the_same_models(run, pkg, scene, tmp_path_factory):
     assert "gpu.allgather_wave" in p.stderr
 
 
+def test_two_ranks_on_one_gpu_write_the_same_models(run, pkg, scene, tmp_path_factory):
+    """The multi-rank path on ANY box: two pmvs2 processes share GPU 0 (each with its own context and table), every wave is cut
+    into two shards, the accepted candidates' records are exchanged (PMVSB_EXCHANGE=tcp: NCCL refuses two ranks on one device;
+    the message format and everything after it are the NCCL path's), both ranks commit the same wave.  The models must be
+    byte-identical to the single-process run."""
+    import sys
+    G, prefix1, _ = run
+    scene.option["CPU"] = max(1, (os.cpu_count() or 4) // 2)
+    prefix2 = pkg.synth.write_scene(scene, str(tmp_path_factory.mktemp("pmvs2_scene_2ranks")))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29753", "--no-python", PMVS2, prefix2, "option.txt", "PATCH", "PSET"]
+    env = dict(os.environ, PMVSB_EXCHANGE="tcp", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900, env=env)
+    assert p.returncode == 0, p.stderr[-3000:]
+    for ext in (".patch", ".pset", ".ply"):
+        a = open(prefix1 + "models/option.txt" + ext, "rb").read()
+        b = open(prefix2 + "models/option.txt" + ext, "rb").read()
+        assert a == b, ext
+    assert "exchange 2 ranks" in p.stderr and "over tcp" in p.stderr
+
+
 @pytest.mark.parametrize("name", ["oimages", "visdata", "sequence", "enumerated"])
 def test_option_variants(name, scene, tmp_path):
     """The rest of the option-file contract (source/pmvs/option.cpp): non-target images, vis.dat, sequence, enumerated
