@@ -19,7 +19,7 @@ SYMBOLS = [
     "pmvsb_create", "pmvsb_destroy", "pmvsb_last_error", "pmvsb_version", "pmvsb_device_count", "pmvsb_upload_camera", "pmvsb_upload_image",
     "pmvsb_upload_mask", "pmvsb_set_edge", "pmvsb_set_bimages", "pmvsb_download_mask", "pmvsb_mask_gate_batch",
     "pmvsb_remove_images_edge_batch", "pmvsb_store_set_seq", "pmvsb_store_counts", "pmvsb_store_rebuild", "pmvsb_filter_exact_apply_store",
-    "pmvsb_small_group_edges_store", "pmvsb_filter_small_groups_store", "pmvsb_store_download_lists", "pmvsb_set_visdata2", "pmvsb_finalize_scene", "pmvsb_set_thresholds", "pmvsb_set_optimizer", "pmvsb_image_dims",
+    "pmvsb_set_features", "pmvsb_seed_candidates", "pmvsb_small_group_edges_store", "pmvsb_filter_small_groups_store", "pmvsb_store_download_lists", "pmvsb_set_visdata2", "pmvsb_finalize_scene", "pmvsb_set_thresholds", "pmvsb_set_optimizer", "pmvsb_image_dims",
     "pmvsb_download_image", "pmvsb_get_camera", "pmvsb_project_batch", "pmvsb_grab_tex_batch", "pmvsb_eval_objective_batch",
     "pmvsb_compute_incc_batch", "pmvsb_set_inccs_batch", "pmvsb_set_scales_batch", "pmvsb_pre_process_batch",
     "pmvsb_post_process_batch", "pmvsb_set_depth", "pmvsb_grid_dims", "pmvsb_store_upload", "pmvsb_build_depth_maps",
@@ -407,6 +407,28 @@ class PmvsB200:
         self._ck(self.lib.pmvsb_detect_features(self.ctx, int(index), int(gspeedup), cap, _vp(xy), _vp(resp), _vp(types), C.byref(n)))
         k = min(n.value, cap)
         return xy[:k].copy(), resp[:k].copy(), types[:k].copy()
+
+    def set_features(self, index, xy, types):
+        xy = _f32(xy).reshape(-1, 2); types = np.ascontiguousarray(types, dtype=np.int32).reshape(-1)
+        self._ck(self.lib.pmvsb_set_features(self.ctx, int(index), len(types), _vp(xy), _vp(types)))
+
+    def seed_candidates(self, index, views, blocked):
+        """-> dict(ref_feature, ref_cell, ref_start, ref_count, coords (n,4), other_image, other_feature, resp)"""
+        views = np.ascontiguousarray(views, dtype=np.int32).reshape(-1)
+        blocked = np.ascontiguousarray(blocked, dtype=np.uint8).reshape(-1)
+        nref, total = C.c_int32(), C.c_int32()
+        call = lambda cr, rf, rc, rs, rn, cap, co, oi, of, rp: self._ck(self.lib.pmvsb_seed_candidates(
+            self.ctx, int(index), len(views), _vp(views), _vp(blocked), cr, C.byref(nref), _vp(rf), _vp(rc), _vp(rs), _vp(rn), cap, C.byref(total),
+            _vp(co), _vp(oi), _vp(of), _vp(rp)))
+        call(0, None, None, None, None, 0, None, None, None, None)
+        R = nref.value
+        rf = np.zeros(max(R, 1), np.int32); rc = np.zeros(max(R, 1), np.int32); rs = np.zeros(max(R, 1), np.int32); rn = np.zeros(max(R, 1), np.int32)
+        call(R, rf, rc, rs, rn, 0, None, None, None, None)
+        n = total.value
+        co = np.zeros((max(n, 1), 4), np.float32); oi = np.zeros(max(n, 1), np.int32); of = np.zeros(max(n, 1), np.int32); rp = np.zeros(max(n, 1), np.float32)
+        if n:
+            call(R, rf, rc, rs, rn, n, co, oi, of, rp)
+        return dict(ref_feature=rf[:R], ref_cell=rc[:R], ref_start=rs[:R], ref_count=rn[:R], coords=co[:n], other_image=oi[:n], other_feature=of[:n], resp=rp[:n])
 
     def comm_unique_id(self):
         buf = (C.c_uint8 * 128)()

@@ -22,6 +22,7 @@
 #include "pmvs_filter.cuh"
 #include "pmvs_cells.cuh"
 #include "pmvs_table.cuh"
+#include "pmvs_seed.cuh"
 #include "pmvs_features.cuh"
 
 #ifndef PMVS_MINBLOCKS
@@ -668,6 +669,15 @@ struct pmvsb_ctx {
   bool order_enabled = true;                // PMVSB_NO_ORDER=1: hand patches out in index order (A/B measurements)
   int32_t* d_vis_off = nullptr;
   const unsigned char** d_map_tab[2] = {nullptr, nullptr};   // per-image pointers to the working-level masks / edges
+  // features of every image binned by cell (CSeed::_ppoints), for the seed candidate kernel
+  std::vector<std::vector<float>> feat_xy;
+  std::vector<std::vector<int32_t>> feat_type;
+  bool feat_dirty = true;
+  std::vector<int32_t> h_feat_base, h_fcell_base, h_fcell_off, h_flist;
+  DVec<float> d_fxy;
+  DVec<int32_t> d_ftype, d_fcell_base, d_fcell_off, d_flist, d_fgw, d_fgh;
+  DVec<uint8_t> d_blocked;
+  DVec<SeedHit> d_seed_out;
   std::vector<int32_t> bimages;
   int32_t* d_bimages = nullptr;
   // filter-stage patch table
@@ -860,6 +870,17 @@ void fill_scene(pmvsb_ctx* c) {
 // before returning, so a block released by one call is idle when the next call takes it.
 thread_local pmvsb_ctx* g_current = nullptr;   // context of the entry point running on this thread
 
+// Device memory comes from the device's stream-ordered pool with an unlimited release threshold (set in pmvsb_create): once
+// the pool has grown, cudaMallocAsync / cudaFreeAsync are sub-microsecond list operations, while cudaMalloc / cudaFree go to the
+// driver every time (tens of microseconds alone, milliseconds each when another process holds a context on the same GPU) and
+// cudaFree synchronises the device.  A pipeline run makes thousands of scratch allocations.
+cudaError_t dev_malloc(pmvsb_ctx* ctx, void** p, size_t bytes) {
+  return cudaMallocAsync(p, bytes ? bytes : 1, ctx ? ctx->stream : (cudaStream_t)0);
+}
+void dev_free(pmvsb_ctx* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx ? ctx->stream : (cudaStream_t)0);
+}
+
 void* pool_take(pmvsb_ctx* ctx, size_t bytes, size_t& granted) {
   size_t want = 256;
   while (want < bytes) want <<= 1;
@@ -869,7 +890,7 @@ void* pool_take(pmvsb_ctx* ctx, size_t bytes, size_t& granted) {
       if (ctx->pool[i].first == want) { void* p = ctx->pool[i].second; ctx->pool.erase(ctx->pool.begin() + i); return p; }
   }
   void* p = nullptr;
-  if (cudaMalloc(&p, want) != cudaSuccess) return nullptr;
+  if (dev_malloc(ctx, &p, want) != cudaSuccess) return nullptr;
   return p;
 }
 
@@ -880,7 +901,7 @@ struct DevBuf {
   pmvsb_ctx* owner = nullptr;
   ~DevBuf() {
     if (!p) return;
-    if (owner && owner->pool.size() < 64) owner->pool.push_back({bytes, (void*)p}); else cudaFree(p);
+    if (owner && owner->pool.size() < 64) owner->pool.push_back({bytes, (void*)p}); else dev_free(owner, p);
   }
   cudaError_t alloc(size_t n) {
     owner = g_current;
@@ -948,7 +969,7 @@ static int arena_reserve(pmvsb_ctx* ctx, size_t bytes) {
   cudaFree(ctx->arena);
   ctx->arena = nullptr; ctx->arena_cap = 0;
   const size_t want = bytes + bytes / 4 + (1u << 20);
-  CK(cudaMalloc((void**)&ctx->arena, want));
+  CK(dev_malloc(ctx, (void**)&ctx->arena, want));
   ctx->arena_cap = want;
   return PMVSB_OK;
 }
@@ -993,10 +1014,9 @@ static int dvec_reserve(pmvsb_ctx* ctx, DVec<T>& v, size_t n, size_t keep = 0) {
   if (n <= v.cap && v.p) return PMVSB_OK;
   const size_t want = 2 * n + 4096;
   T* np = nullptr;
-  CK(cudaMalloc((void**)&np, sizeof(T) * want));
+  CK(dev_malloc(ctx, (void**)&np, sizeof(T) * want));
   if (keep && v.p) CK(cudaMemcpyAsync(np, v.p, sizeof(T) * keep, cudaMemcpyDeviceToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(v.p);
+  dev_free(ctx, v.p);   // stream-ordered: after the copy above
   v.p = np; v.cap = want;
   return PMVSB_OK;
 }
@@ -1129,6 +1149,12 @@ int pmvsb_create(pmvsb_ctx** out, int device, int num_images, int num_target, in
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
   ctx->stream = ctx->own_stream;
+  if (e == cudaSuccess) {   // keep freed blocks in the device's stream-ordered pool (see dev_malloc)
+    cudaMemPool_t mp = nullptr;
+    uint64_t keep_all = UINT64_MAX;
+    if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep_all);
+    cudaGetLastError();
+  }
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_counter, 4 * sizeof(int));
@@ -1154,6 +1180,8 @@ int pmvsb_destroy(pmvsb_ctx* ctx) {
   atlas_free(ctx);
   cudaFree(ctx->order_bin.p); cudaFree(ctx->order_counts.p); cudaFree(ctx->order_idx.p);
   cudaFree(ctx->arena);
+  cudaFree(ctx->d_fxy.p); cudaFree(ctx->d_ftype.p); cudaFree(ctx->d_fcell_base.p); cudaFree(ctx->d_fcell_off.p); cudaFree(ctx->d_flist.p);
+  cudaFree(ctx->d_fgw.p); cudaFree(ctx->d_fgh.p); cudaFree(ctx->d_blocked.p); cudaFree(ctx->d_seed_out.p);
   store_free(ctx);
   if (ctx->comm && nccl_api()) nccl_api()->CommDestroy(ctx->comm);
   cudaFree(ctx->comm_buf);
@@ -1193,7 +1221,7 @@ int pmvsb_upload_image(pmvsb_ctx* ctx, int index, int width, int height, const u
   CK(staging.alloc(n0 * 3));
   CK(cudaMemcpyAsync(staging.p, rgb, n0 * 3, cudaMemcpyHostToDevice, ctx->stream));
   im.w[0] = width; im.h[0] = height;
-  CK(cudaMalloc((void**)&im.levels[0], n0 * sizeof(uchar4)));
+  CK(dev_malloc(ctx, (void**)&im.levels[0], n0 * sizeof(uchar4)));
   const int blocks = (int)std::min<size_t>((n0 + 255) / 256, (size_t)ctx->sm_count * 16);
   k_rgb_to_rgba<<<blocks, 256, 0, ctx->stream>>>(staging.p, im.levels[0], n0);
   ++ctx->launches;
@@ -1201,7 +1229,7 @@ int pmvsb_upload_image(pmvsb_ctx* ctx, int index, int width, int height, const u
     im.w[l] = im.w[l - 1] / 2;  // image.cpp:136-139
     im.h[l] = im.h[l - 1] / 2;
     const size_t nl = (size_t)std::max(im.w[l], 1) * std::max(im.h[l], 1);
-    CK(cudaMalloc((void**)&im.levels[l], nl * sizeof(uchar4)));
+    CK(dev_malloc(ctx, (void**)&im.levels[l], nl * sizeof(uchar4)));
     if (im.w[l] > 0 && im.h[l] > 0) {
       dim3 block(32, 8), grid((im.w[l] + 31) / 32, (im.h[l] + 7) / 8);
       k_pyr_down<<<grid, block, 0, ctx->stream>>>(im.levels[l - 1], im.w[l - 1], im.h[l - 1], im.levels[l], im.w[l], im.h[l]);
@@ -1221,7 +1249,7 @@ static int map_to_working_level(pmvsb_ctx* ctx, HostImage& im, int which, uint8_
   for (int l = 1; l <= ctx->level; ++l) {
     uint8_t* next = nullptr;
     const size_t nl = (size_t)std::max(im.w[l], 1) * std::max(im.h[l], 1);
-    CK(cudaMalloc((void**)&next, nl));
+    CK(dev_malloc(ctx, (void**)&next, nl));
     if (im.w[l] > 0 && im.h[l] > 0) {
       k_map_down<<<dim3((im.w[l] + 127) / 128, im.h[l]), 128, 0, ctx->stream>>>(cur, im.w[l - 1], im.h[l - 1], next, im.w[l], im.h[l]);
       ++ctx->launches;
@@ -1250,7 +1278,7 @@ int pmvsb_upload_mask(pmvsb_ctx* ctx, int index, int which, int width, int heigh
   CK(staging.alloc(n0));
   CK(cudaMemcpyAsync(staging.p, gray, n0, cudaMemcpyHostToDevice, ctx->stream));
   uint8_t* level0 = nullptr;
-  CK(cudaMalloc((void**)&level0, n0));
+  CK(dev_malloc(ctx, (void**)&level0, n0));
   k_map_binarise<<<(unsigned)((n0 + 255) / 256), 256, 0, ctx->stream>>>(staging.p, n0, which == 0 ? 127 : 1, level0);
   ++ctx->launches;
   return map_to_working_level(ctx, im, which, level0);
@@ -1280,7 +1308,7 @@ int pmvsb_set_edge(pmvsb_ctx* ctx, float threshold) {
     k_edge_smooth<true><<<grid, 128, 0, ctx->stream>>>(a.p, b.p, w, h, d_taps.p, margin);
     k_edge_smooth<false><<<grid, 128, 0, ctx->stream>>>(b.p, a.p, w, h, d_taps.p, margin);
     uint8_t* level0 = nullptr;
-    CK(cudaMalloc((void**)&level0, n0));
+    CK(dev_malloc(ctx, (void**)&level0, n0));
     k_edge_threshold<<<(unsigned)((n0 + 255) / 256), 256, 0, ctx->stream>>>(a.p, n0, new_threshold, level0);
     ctx->launches += 4;
     const int r = map_to_working_level(ctx, im, 1, level0);
@@ -1689,6 +1717,8 @@ int pmvsb_grid_dims(pmvsb_ctx* ctx, int image, int* gwidth, int* gheight) {
   return PMVSB_OK;
 }
 
+static void grid_geometry(pmvsb_ctx* ctx);
+
 int pmvsb_store_upload(pmvsb_ctx* ctx, int P, const float* coords, const float* normals, const float* ncc, const float* dscale,
                        const int32_t* img_off, const int32_t* images, const int32_t* grids, const int32_t* vimg_off,
                        const int32_t* vimages, const int32_t* vgrids, const int32_t* timages) {
@@ -1701,13 +1731,8 @@ int pmvsb_store_upload(pmvsb_ctx* ctx, int P, const float* coords, const float* 
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->store_set = false; ctx->depth_built = false; ctx->store_appended = false;
   StoreBufs& b = ctx->sb;
-  if (ctx->h_gw.empty()) {   // grid geometry (patchOrganizerS.cpp:72-77), once per scene
-    ctx->h_gw.resize(ctx->num); ctx->h_gh.resize(ctx->num); ctx->h_base.assign(ctx->tnum + 1, 0);
-    for (int i = 0; i < ctx->num; ++i) {
-      ctx->h_gw[i] = (ctx->images[i].w[ctx->level] + ctx->csize - 1) / ctx->csize;
-      ctx->h_gh[i] = (ctx->images[i].h[ctx->level] + ctx->csize - 1) / ctx->csize;
-    }
-    for (int i = 0; i < ctx->tnum; ++i) ctx->h_base[i + 1] = ctx->h_base[i] + ctx->h_gw[i] * ctx->h_gh[i];
+  if (!b.cell_base.p) {   // grid geometry (patchOrganizerS.cpp:72-77), once per scene
+    grid_geometry(ctx);
     if ((r = dvec_put(ctx, b.cell_base, 0, ctx->h_base.data(), ctx->h_base.size()))) return r;
     if ((r = dvec_put(ctx, b.gw, 0, ctx->h_gw.data(), ctx->h_gw.size()))) return r;
     if ((r = dvec_put(ctx, b.gh, 0, ctx->h_gh.data(), ctx->h_gh.size()))) return r;
@@ -1971,6 +1996,167 @@ int pmvsb_store_download_vimages(pmvsb_ctx* ctx, int32_t* vimg_off, int32_t* vim
   return PMVSB_OK;
 }
 
+
+
+// ---- seed candidate enumeration (pmvs_seed.cuh) ------------------------------------------------------------------
+int pmvsb_set_features(pmvsb_ctx* ctx, int index, int n, const float* xy, const int32_t* type) {
+  if (!ctx || index < 0 || index >= ctx->num || n < 0 || (n > 0 && (!xy || !type))) return fail(ctx, PMVSB_EINVAL, "set_features: bad argument");
+  if (ctx->feat_xy.empty()) { ctx->feat_xy.resize(ctx->num); ctx->feat_type.resize(ctx->num); }
+  ctx->feat_xy[index].assign(xy, xy + (size_t)2 * n);
+  ctx->feat_type[index].assign(type, type + n);
+  ctx->feat_dirty = true;
+  return PMVSB_OK;
+}
+
+static void grid_geometry(pmvsb_ctx* ctx) {   // patchOrganizerS.cpp:72-77
+  if (!ctx->h_gw.empty()) return;
+  ctx->h_gw.resize(ctx->num); ctx->h_gh.resize(ctx->num); ctx->h_base.assign(ctx->tnum + 1, 0);
+  for (int i = 0; i < ctx->num; ++i) {
+    ctx->h_gw[i] = (ctx->images[i].w[ctx->level] + ctx->csize - 1) / ctx->csize;
+    ctx->h_gh[i] = (ctx->images[i].h[ctx->level] + ctx->csize - 1) / ctx->csize;
+  }
+  for (int i = 0; i < ctx->tnum; ++i) ctx->h_base[i + 1] = ctx->h_base[i] + ctx->h_gw[i] * ctx->h_gh[i];
+}
+
+// CSeed::readPoints (seed.cpp:23-36): features binned by cell, in the order they were handed over
+static int upload_feature_bins(pmvsb_ctx* ctx) {
+  if (!ctx->feat_dirty) return PMVSB_OK;
+  grid_geometry(ctx);
+  if (ctx->feat_xy.empty()) { ctx->feat_xy.resize(ctx->num); ctx->feat_type.resize(ctx->num); }
+  const int num = ctx->num;
+  ctx->h_feat_base.assign(num + 1, 0); ctx->h_fcell_base.assign(num + 1, 0);
+  for (int i = 0; i < num; ++i) {
+    ctx->h_feat_base[i + 1] = ctx->h_feat_base[i] + (int)ctx->feat_type[i].size();
+    ctx->h_fcell_base[i + 1] = ctx->h_fcell_base[i] + ctx->h_gw[i] * ctx->h_gh[i];
+  }
+  const int nf = ctx->h_feat_base[num], cells = ctx->h_fcell_base[num];
+  std::vector<float> xy((size_t)2 * std::max(nf, 1));
+  std::vector<int32_t> type(std::max(nf, 1)), cell_of(std::max(nf, 1), -1);
+  ctx->h_fcell_off.assign((size_t)cells + 1, 0);
+  ctx->h_flist.assign(std::max(nf, 1), 0);
+  for (int i = 0; i < num; ++i)
+    for (int k = 0; k < (int)ctx->feat_type[i].size(); ++k) {
+      const int f = ctx->h_feat_base[i] + k;
+      const float x = ctx->feat_xy[i][2 * k], y = ctx->feat_xy[i][2 * k + 1];
+      xy[2 * f] = x; xy[2 * f + 1] = y; type[f] = ctx->feat_type[i][k];
+      const int ix = ((int)std::floor(x + 0.5f)) / ctx->csize, iy = ((int)std::floor(y + 0.5f)) / ctx->csize;
+      if (ix < 0 || ix >= ctx->h_gw[i] || iy < 0 || iy >= ctx->h_gh[i]) continue;   // cannot happen for detector output
+      cell_of[f] = ctx->h_fcell_base[i] + iy * ctx->h_gw[i] + ix;
+      ++ctx->h_fcell_off[cell_of[f] + 1];
+    }
+  for (int c = 0; c < cells; ++c) ctx->h_fcell_off[c + 1] += ctx->h_fcell_off[c];
+  std::vector<int32_t> cur(ctx->h_fcell_off.begin(), ctx->h_fcell_off.end() - 1);
+  for (int f = 0; f < nf; ++f)
+    if (cell_of[f] >= 0) ctx->h_flist[cur[cell_of[f]]++] = f;
+  int r;
+  if ((r = dvec_put(ctx, ctx->d_fxy, 0, xy.data(), xy.size())) || (r = dvec_put(ctx, ctx->d_ftype, 0, type.data(), type.size())) ||
+      (r = dvec_put(ctx, ctx->d_fcell_base, 0, ctx->h_fcell_base.data(), ctx->h_fcell_base.size())) ||
+      (r = dvec_put(ctx, ctx->d_fcell_off, 0, ctx->h_fcell_off.data(), ctx->h_fcell_off.size())) ||
+      (r = dvec_put(ctx, ctx->d_flist, 0, ctx->h_flist.data(), ctx->h_flist.size())) ||
+      (r = dvec_put(ctx, ctx->d_fgw, 0, ctx->h_gw.data(), ctx->h_gw.size())) || (r = dvec_put(ctx, ctx->d_fgh, 0, ctx->h_gh.data(), ctx->h_gh.size())))
+    return r;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->feat_dirty = false;
+  return PMVSB_OK;
+}
+
+// Image::setF (include/image/camera.hpp:129-151) at the working level: double copies of the float projection rows, 4x4
+// determinants through the triple cross product of numeric/vec4.hpp:216-231 (the reference's operation order)
+static double det4_rows(const double* a, const double* b, const double* c, const double* d) {
+  const double d1 = (c[2] * d[3]) - (c[3] * d[2]), d2 = (c[1] * d[3]) - (c[3] * d[1]), d3 = (c[1] * d[2]) - (c[2] * d[1]);
+  const double d4 = (c[0] * d[3]) - (c[3] * d[0]), d5 = (c[0] * d[2]) - (c[2] * d[0]), d6 = (c[0] * d[1]) - (c[1] * d[0]);
+  const double x0 = -b[1] * d1 + b[2] * d2 - b[3] * d3, x1 = b[0] * d1 - b[2] * d4 + b[3] * d5;
+  const double x2 = -b[0] * d2 + b[1] * d4 - b[3] * d6, x3 = b[0] * d3 - b[1] * d5 + b[2] * d6;
+  return a[0] * x0 + a[1] * x1 + a[2] * x2 + a[3] * x3;
+}
+static void level_projection(const pmvsb_ctx* ctx, int image, double P[3][4]) {
+  const float sc = 1.0f / (float)(1 << ctx->level);
+  for (int k = 0; k < 4; ++k) {
+    P[0][k] = (double)(ctx->cams[image].P0[0][k] * sc);
+    P[1][k] = (double)(ctx->cams[image].P0[1][k] * sc);
+    P[2][k] = (double)ctx->cams[image].P0[2][k];
+  }
+}
+static void set_F(const pmvsb_ctx* ctx, int lhs, int rhs, double* F) {
+  double a[3][4], b[3][4];
+  level_projection(ctx, lhs, a);
+  level_projection(ctx, rhs, b);
+  F[0] = det4_rows(a[1], a[2], b[1], b[2]); F[1] = det4_rows(a[1], a[2], b[2], b[0]); F[2] = det4_rows(a[1], a[2], b[0], b[1]);
+  F[3] = det4_rows(a[2], a[0], b[1], b[2]); F[4] = det4_rows(a[2], a[0], b[2], b[0]); F[5] = det4_rows(a[2], a[0], b[0], b[1]);
+  F[6] = det4_rows(a[0], a[1], b[1], b[2]); F[7] = det4_rows(a[0], a[1], b[2], b[0]); F[8] = det4_rows(a[0], a[1], b[0], b[1]);
+}
+
+int pmvsb_seed_candidates(pmvsb_ctx* ctx, int index, int nviews, const int32_t* views, const uint8_t* blocked, int cap_ref, int32_t* nref,
+                          int32_t* ref_feature, int32_t* ref_cell, int32_t* ref_start, int32_t* ref_count, int cap, int32_t* total, float* coords,
+                          int32_t* other_image, int32_t* other_feature, float* resp) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (index < 0 || index >= ctx->num || nviews < 0 || nviews > kMaxTau || (nviews > 0 && !views) || !blocked || !nref || !total || cap_ref < 0 || cap < 0)
+    return fail(ctx, PMVSB_EINVAL, "seed_candidates: bad argument");
+  for (int k = 0; k < nviews; ++k)
+    if (views[k] < 0 || views[k] >= ctx->num || views[k] == index) return fail(ctx, PMVSB_EINVAL, "seed_candidates: bad view list");
+  if ((r = upload_feature_bins(ctx))) return r;
+  // the reference features: cells of `index` in row-major order that may take a patch, their features in bin order (seed.cpp:143-151)
+  std::vector<int32_t> feats, cells;
+  const int gw = ctx->h_gw[index], gh = ctx->h_gh[index], cb = ctx->h_fcell_base[index];
+  for (int c = 0; c < gw * gh; ++c) {
+    if (blocked[cb + c]) continue;
+    for (int j = ctx->h_fcell_off[cb + c]; j < ctx->h_fcell_off[cb + c + 1]; ++j) { feats.push_back(ctx->h_flist[j]); cells.push_back(c); }
+  }
+  const int R = (int)feats.size();
+  *nref = R; *total = 0;
+  if (R == 0 || nviews == 0) { *nref = nviews == 0 ? 0 : R; return PMVSB_OK; }
+  if (R > cap_ref) return PMVSB_OK;   // the caller sizes its arrays from *nref and calls again
+  if (!ref_feature || !ref_cell || !ref_start || !ref_count) return fail(ctx, PMVSB_EINVAL, "seed_candidates: null output");
+  SeedParams sp;
+  std::memset(&sp, 0, sizeof(sp));
+  sp.index = index; sp.nviews = nviews; sp.ep_threshold = 2.0f;   // findMatch.cpp:106
+  for (int k = 0; k < nviews; ++k) { sp.view[k].image = views[k]; set_F(ctx, index, views[k], sp.view[k].F); }
+  SeedDev sd;
+  sd.fxy = ctx->d_fxy.p; sd.ftype = ctx->d_ftype.p; sd.fcell_base = ctx->d_fcell_base.p; sd.fcell_off = ctx->d_fcell_off.p; sd.flist = ctx->d_flist.p;
+  sd.gw = ctx->d_fgw.p; sd.gh = ctx->d_fgh.p;
+  const int allcells = ctx->h_fcell_base[ctx->num];
+  if ((r = dvec_put(ctx, ctx->d_blocked, 0, blocked, (size_t)allcells))) return r;
+  DevBuf<int32_t> dfeat, dcount, dstart, dmisc;
+  CK(dfeat.alloc(R)); CK(dcount.alloc(R)); CK(dstart.alloc(R)); CK(dmisc.alloc(4));
+  CK(cudaMemcpyAsync(dfeat.p, feats.data(), sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice, ctx->stream));
+  size_t capacity = std::max<size_t>(ctx->d_seed_out.cap, (size_t)1 << 18);
+  int32_t misc[4] = {0, 0, 0, 0};   // cursor, features over kSeedCap, features that did not fit the buffer, -
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if ((r = dvec_reserve(ctx, ctx->d_seed_out, capacity))) return r;
+    capacity = ctx->d_seed_out.cap;
+    CK(cudaMemsetAsync(dmisc.p, 0, sizeof(int32_t) * 4, ctx->stream));
+    k_seed_candidates<<<(R + kSeedWarps - 1) / kSeedWarps, kSeedWarps * 32, 0, ctx->stream>>>(ctx->scene, sd, sp, ctx->d_blocked.p, R, dfeat.p, dcount.p, dstart.p,
+                                                                                              dmisc.p, (int)std::min<size_t>(capacity, 0x7fffffff), ctx->d_seed_out.p,
+                                                                                              dmisc.p + 1);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(misc, dmisc.p, sizeof(misc), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (misc[2] == 0) break;
+    capacity = (size_t)misc[0] + 1024;   // the cursor counted every hit: the second pass fits
+  }
+  if (misc[1] != 0) return fail(ctx, PMVSB_ERANGE, "seed_candidates: a feature has more than " + std::to_string(kSeedCap) + " epipolar candidates");
+  if (misc[2] != 0) return fail(ctx, PMVSB_ENOMEM, "seed_candidates: candidate buffer too small");
+  *total = misc[0];
+  CK(cudaMemcpyAsync(ref_count, dcount.p, sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ref_start, dstart.p, sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
+  for (int k = 0; k < R; ++k) { ref_feature[k] = feats[k] - ctx->h_feat_base[index]; ref_cell[k] = cells[k]; }
+  if (misc[0] > cap) { CK(cudaStreamSynchronize(ctx->stream)); return PMVSB_OK; }   // sizes known now: call again with room for *total
+  if (misc[0] > 0) {
+    if (!coords || !other_image || !other_feature || !resp) return fail(ctx, PMVSB_EINVAL, "seed_candidates: null output");
+    std::vector<SeedHit> hits((size_t)misc[0]);
+    CK(cudaMemcpyAsync(hits.data(), ctx->d_seed_out.p, sizeof(SeedHit) * hits.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < hits.size(); ++i) {
+      const SeedHit& h = hits[i];
+      coords[4 * i] = h.x; coords[4 * i + 1] = h.y; coords[4 * i + 2] = h.z; coords[4 * i + 3] = 1.0f;
+      other_image[i] = h.other_image; other_feature[i] = h.other_feature - ctx->h_feat_base[h.other_image]; resp[i] = h.resp;
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return PMVSB_OK;
+}
 
 // ---- the table reorganised on the device (pmvs_table.cuh) -------------------------------------------------------
 int pmvsb_store_set_seq(pmvsb_ctx* ctx, int first, int n, const int32_t* seq) {

@@ -461,15 +461,6 @@ void Pipeline::seed_round() {
   for (int im = 0; im < tnum_; ++im)
     for (size_t c = 0; c < grids_[im].occ.size(); ++c)
       if (grids_[im].occ[c] != 0) grids_[im].counts[c] = (unsigned char)count_threshold2_;
-  // features binned by cell (seed.cpp:25-36)
-  std::vector<std::vector<std::vector<int>>> bins(num_);
-  for (int i = 0; i < num_; ++i) {
-    bins[i].assign((size_t)grids_[i].gw * grids_[i].gh, {});
-    for (int f = 0; f < (int)features_[i].size(); ++f) {
-      const int ix = ((int)std::floor(features_[i][f].x + 0.5f)) / opt_.csize, iy = ((int)std::floor(features_[i][f].y + 0.5f)) / opt_.csize;
-      if (ix >= 0 && ix < grids_[i].gw && iy >= 0 && iy < grids_[i].gh) bins[i][(size_t)iy * grids_[i].gw + ix].push_back(f);
-    }
-  }
   auto can_add = [&](int image, int x, int y) {   // seed.cpp:325-338
     if (!get_mask(image, opt_.csize * x, opt_.csize * y)) return false;
     if (tnum_ <= image) return true;
@@ -477,6 +468,17 @@ void Pipeline::seed_round() {
     if (grids_[image].occ[c] != 0) return false;
     return !(count_threshold2_ <= grids_[image].counts[c]);
   };
+  // CSeed::canAdd of every cell of every image, kept current as the round commits (the candidate kernel reads it)
+  std::vector<int> cell_base(num_ + 1, 0);
+  for (int i = 0; i < num_; ++i) cell_base[i + 1] = cell_base[i] + grids_[i].gw * grids_[i].gh;
+  std::vector<uint8_t> blocked((size_t)cell_base[num_]);
+  parallel_for(num_, threads_, [&](int i) {
+    for (int y = 0; y < grids_[i].gh; ++y)
+      for (int x = 0; x < grids_[i].gw; ++x) blocked[(size_t)cell_base[i] + (size_t)y * grids_[i].gw + x] = can_add(i, x, y) ? 0 : 1;
+  }, 1);
+  auto refresh = [&](int image, int cell) { blocked[(size_t)cell_base[image] + cell] = can_add(image, cell % grids_[image].gw, cell / grids_[image].gw) ? 0 : 1; };
+  std::vector<int32_t> sc_ref, sc_other(1 << 18), sc_other_feat(1 << 18);
+  std::vector<float> sc_coord((size_t)4 << 18), sc_resp(1 << 18);
   const double cos_a0 = std::cos(60.0f * M_PI / 180.0f);
   for (int index : order) {
     // COptim::collectImages (optim.cpp:66-93)
@@ -491,136 +493,77 @@ void Pipeline::seed_round() {
     std::vector<int> indexes;
     for (int i = 0; i < std::min(tau_, (int)cand_im.size()); ++i) indexes.push_back(cand_im[i].second);
     if (indexes.empty()) continue;
-    std::vector<std::array<double, 9>> Fs(indexes.size());
-    for (size_t k = 0; k < indexes.size(); ++k) {
-      double F[3][3];
-      fundamental(P0_[index], P0_[indexes[k]], F);
-      for (int a = 0; a < 9; ++a) Fs[k][a] = F[a / 3][a % 3];
-    }
-    // ---- enumerate the wave: every (cell, feature, candidate) of this image from the current snapshot
+    // ---- enumerate the wave on the GPU: every (cell, feature, epipolar candidate) of this image from the current snapshot
+    // (CSeed::collectCells / collectCandidates / unproject, seed.cpp:207-384: pmvsb_seed_candidates)
     std::vector<Candidate> wave;
     const ImageGrid& g = grids_[index];
-    std::vector<std::vector<Candidate>> per_row(g.gh);   // rows are enumerated by the CPU threads, concatenated in row order
-    { Tick tk2(this, "host.seed.candidates");
-    parallel_for(g.gh, threads_, [&](int y) {
-      std::vector<Candidate>& wave = per_row[y];
-      for (int x = 0; x < g.gw; ++x) {
-        const int cell = y * g.gw + x;
-        if (bins[index][cell].empty() || !can_add(index, x, y)) continue;
-        for (int fi = 0; fi < (int)bins[index][cell].size(); ++fi) {
-          const Feature& p0 = features_[index][bins[index][cell][fi]];
-          struct Hit { float resp; int image, feat; float coord[4]; };
-          std::vector<Hit> hits;
-          for (size_t k = 0; k < indexes.size(); ++k) {
-            const int other = indexes[k];
-            const double* F = Fs[k].data();
-            // epipolar line of p0 in `other`: transpose(F) * p0 (seed.cpp:207-268)
-            const double line[3] = {F[0] * p0.x + F[3] * p0.y + F[6], F[1] * p0.x + F[4] * p0.y + F[7], F[2] * p0.x + F[5] * p0.y + F[8]};
-            if (line[0] == 0.0 && line[1] == 0.0) continue;
-            const ImageGrid& og = grids_[other];
-            std::vector<std::array<int, 2>> cells;
-            if (std::fabs(line[0]) > std::fabs(line[1])) {
-              for (int cy = 0; cy < og.gh; ++cy) {
-                const float fy = (float)((cy + 0.5) * opt_.csize - 0.5f);
-                float fx = (float)((-line[1] * fy - line[2]) / line[0]);
-                fx = std::max(-2147483648.0f, std::min(2147483648.0f, fx));
-                const int ix = ((int)std::floor(fx + 0.5f)) / opt_.csize;
-                for (int d : {0, -1, 1}) if (0 <= ix + d && ix + d < og.gw) cells.push_back({ix + d, cy});
-              }
-            } else {
-              for (int cx = 0; cx < og.gw; ++cx) {
-                const float fx = (float)((cx + 0.5) * opt_.csize - 0.5f);
-                float fy = (float)((-line[0] * fx - line[2]) / line[1]);
-                fy = std::max(-2147483648.0f, std::min(2147483648.0f, fy));
-                const int iy = ((int)std::floor(fy + 0.5f)) / opt_.csize;
-                for (int d : {0, -1, 1}) if (0 <= iy + d && iy + d < og.gh) cells.push_back({cx, iy + d});
-              }
-            }
-            for (const auto& c : cells) {
-              if (!can_add(other, c[0], c[1])) continue;
-              for (int f1 : bins[other][(size_t)c[1] * og.gw + c[0]]) {
-                const Feature& p1 = features_[other][f1];
-                if (p1.type != p0.type) continue;
-                // distance of p0 to the epipolar line of p1 (computeEPD, camera.hpp:118-127)
-                double l[3] = {F[0] * p1.x + F[1] * p1.y + F[2], F[3] * p1.x + F[4] * p1.y + F[5], F[6] * p1.x + F[7] * p1.y + F[8]};
-                const double nn = std::sqrt(l[0] * l[0] + l[1] * l[1]);
-                float epd = 0.0f;
-                if (nn != 0.0) epd = (float)std::fabs((l[0] * p0.x + l[1] * p0.y + l[2]) / nn);
-                if (2.0f <= epd) continue;   // _epThreshold (findMatch.cpp:106)
-                // triangulate (seed.cpp:340-384): normal equations of the 4 x 3 system in double
-                const std::vector<double>& Pa = P0_[index];
-                const std::vector<double>& Pb = P0_[other];
-                double A[4][3], b[4];
-                for (int c3 = 0; c3 < 3; ++c3) {
-                  A[0][c3] = Pa[c3] - p0.x * Pa[8 + c3]; A[1][c3] = Pa[4 + c3] - p0.y * Pa[8 + c3];
-                  A[2][c3] = Pb[c3] - p1.x * Pb[8 + c3]; A[3][c3] = Pb[4 + c3] - p1.y * Pb[8 + c3];
-                }
-                b[0] = p0.x * Pa[11] - Pa[3]; b[1] = p0.y * Pa[11] - Pa[7];
-                b[2] = p1.x * Pb[11] - Pb[3]; b[3] = p1.y * Pb[11] - Pb[7];
-                double M[3][3] = {{0}}, v[3] = {0, 0, 0};
-                for (int r = 0; r < 4; ++r)
-                  for (int i3 = 0; i3 < 3; ++i3) { v[i3] += A[r][i3] * b[r]; for (int j3 = 0; j3 < 3; ++j3) M[i3][j3] += A[r][i3] * A[r][j3]; }
-                const double det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
-                                   M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
-                if (det == 0.0) continue;
-                double inv[3][3];
-                inv[0][0] = (M[1][1] * M[2][2] - M[1][2] * M[2][1]) / det; inv[0][1] = (M[0][2] * M[2][1] - M[0][1] * M[2][2]) / det; inv[0][2] = (M[0][1] * M[1][2] - M[0][2] * M[1][1]) / det;
-                inv[1][0] = (M[1][2] * M[2][0] - M[1][0] * M[2][2]) / det; inv[1][1] = (M[0][0] * M[2][2] - M[0][2] * M[2][0]) / det; inv[1][2] = (M[0][2] * M[1][0] - M[0][0] * M[1][2]) / det;
-                inv[2][0] = (M[1][0] * M[2][1] - M[1][1] * M[2][0]) / det; inv[2][1] = (M[0][1] * M[2][0] - M[0][0] * M[2][1]) / det; inv[2][2] = (M[0][0] * M[1][1] - M[0][1] * M[1][0]) / det;
-                Hit h;
-                for (int i3 = 0; i3 < 3; ++i3) h.coord[i3] = (float)(inv[i3][0] * v[0] + inv[i3][1] * v[1] + inv[i3][2] * v[2]);
-                h.coord[3] = 1.0f;
-                if (dot4(cams_[index].P[2], h.coord) <= 0.0f) continue;
-                if (!mask_gate(h.coord)) continue;   // seed.cpp:314
-                float d0[4], d1[4];
-                for (int c4 = 0; c4 < 4; ++c4) { d0[c4] = h.coord[c4] - cams_[index].centre[c4]; d1[c4] = h.coord[c4] - cams_[other].centre[c4]; }
-                h.resp = std::fabs(norm4(d0) - norm4(d1));
-                h.image = other; h.feat = f1;
-                hits.push_back(h);
-              }
-            }
-          }
-          std::stable_sort(hits.begin(), hits.end(), [](const Hit& a, const Hit& b) { return a.resp < b.resp; });
-          int ord = 0;
-          for (const Hit& h : hits) {
-            Candidate c;
-            for (int k4 = 0; k4 < 4; ++k4) { c.patch.coord[k4] = h.coord[k4]; c.patch.normal[k4] = cams_[index].centre[k4] - h.coord[k4]; }
-            unitize4(c.patch.normal);
-            c.patch.normal[3] = 0.0f;
-            c.patch.images = {index, h.image};
-            c.cell = cell; c.feature = fi; c.order = ord++;
-            c.parent = h.image;   // other image (for the counters)
-            const Feature& p1 = features_[h.image][h.feat];
-            c.dir = (((int)std::floor(p1.y + 0.5f)) / opt_.csize) * grids_[h.image].gw + ((int)std::floor(p1.x + 0.5f)) / opt_.csize;
-            wave.push_back(c);
-          }
-        }
+    { Tick tk2(this, "gpu.seed.candidates");
+      int32_t nref = 0, total = 0;
+      if ((int)sc_ref.size() < 4 * 65536) sc_ref.resize(4 * 65536);
+      for (int attempt = 0; attempt < 3; ++attempt) {
+        const int cap_ref = (int)sc_ref.size() / 4, cap = (int)sc_other.size();
+        if (pmvsb_seed_candidates(gpu_, index, (int)indexes.size(), indexes.data(), blocked.data(), cap_ref, &nref, sc_ref.data(), sc_ref.data() + cap_ref,
+                                  sc_ref.data() + 2 * cap_ref, sc_ref.data() + 3 * cap_ref, cap, &total, sc_coord.data(), sc_other.data(),
+                                  sc_other_feat.data(), sc_resp.data())) die("seed_candidates");
+        if (nref <= cap_ref && total <= cap) break;
+        if (nref > cap_ref) sc_ref.resize((size_t)4 * nref);
+        if (total > cap) { sc_coord.resize((size_t)4 * total); sc_other.resize(total); sc_other_feat.resize(total); sc_resp.resize(total); }
       }
-    }, 1);
+      const int cap_ref = (int)sc_ref.size() / 4;
+      const int32_t *rfeat = sc_ref.data(), *rcell = rfeat + cap_ref, *rstart = rcell + cap_ref, *rcount = rstart + cap_ref;
+      size_t n = 0;
+      for (int r = 0; r < nref; ++r) n += (size_t)rcount[r];
+      wave.resize(n);
+      std::vector<size_t> at((size_t)nref + 1, 0);
+      for (int r = 0; r < nref; ++r) at[r + 1] = at[r] + (size_t)rcount[r];
+      parallel_for(nref, threads_, [&](int r) {
+        for (int j = 0; j < rcount[r]; ++j) {
+          const int h = rstart[r] + j;
+          Candidate& c = wave[at[r] + j];
+          const int other = sc_other[h];
+          for (int k4 = 0; k4 < 4; ++k4) { c.patch.coord[k4] = sc_coord[(size_t)4 * h + k4]; c.patch.normal[k4] = cams_[index].centre[k4] - c.patch.coord[k4]; }
+          unitize4(c.patch.normal);
+          c.patch.normal[3] = 0.0f;
+          c.patch.images = {index, other};
+          c.cell = rcell[r]; c.feature = rfeat[r]; c.order = j;
+          c.parent = other;   // other image (for the counters)
+          const Feature& p1 = features_[other][sc_other_feat[h]];
+          c.dir = (((int)std::floor(p1.y + 0.5f)) / opt_.csize) * grids_[other].gw + ((int)std::floor(p1.x + 0.5f)) / opt_.csize;
+        }
+      }, 16);
     }
-    for (auto& v : per_row) for (auto& c : v) wave.push_back(std::move(c));
-    per_row.clear();
     std::vector<int> verdict;
     evaluate(wave, verdict);
-    // ---- commit: replay the reference's sequential rule per cell (seed.cpp:151-199)
+    // ---- commit: replay the reference's sequential walk (seed.cpp:140-199) over the evaluated wave.  The cells are visited
+    // in the reference's order and canAdd is asked again on the LIVE grids -- for the reference cell before its features are
+    // tried, for the other image's cell before a candidate counts as a trial -- because a patch committed earlier in this wave
+    // may have taken the cell since the snapshot; such cells / candidates are skipped exactly as the sequential walk would
+    // (no trial counted).  The trial counters are unsigned chars that wrap, as in the reference.
     int total = 0;
     size_t k = 0;
+    std::vector<char> open_now;
     while (k < wave.size()) {
       const int cell = wave[k].cell;
       size_t cell_end = k;
       while (cell_end < wave.size() && wave[cell_end].cell == cell) ++cell_end;
       bool placed = false;
       size_t f0 = k;
+      if (!can_add(index, cell % g.gw, cell / g.gw)) f0 = cell_end;
       while (f0 < cell_end && !placed) {
         size_t f1 = f0;
         while (f1 < cell_end && wave[f1].feature == wave[f0].feature) ++f1;
         int count = 0;
         const Patch* best = nullptr;
         float best_score = 0.0f;
+        // collectCandidates asks canAdd for the whole list BEFORE the first trial of this feature (seed.cpp:153 -> 287)
+        open_now.resize(f1 - f0);
+        for (size_t c = f0; c < f1; ++c) open_now[c - f0] = can_add(wave[c].parent, wave[c].dir % grids_[wave[c].parent].gw, wave[c].dir / grids_[wave[c].parent].gw);
         for (size_t c = f0; c < f1; ++c) {
+          const int other = wave[c].parent, ocell = wave[c].dir;
+          if (!open_now[c - f0]) continue;
           // trial counters of both cells (seed.cpp:175-181)
-          if (grids_[index].counts[cell] < 255) ++grids_[index].counts[cell];
-          if (wave[c].parent < tnum_ && grids_[wave[c].parent].counts[wave[c].dir] < 255) ++grids_[wave[c].parent].counts[wave[c].dir];
+          ++grids_[index].counts[cell];
+          if (other < tnum_) { ++grids_[other].counts[ocell]; refresh(other, ocell); }
           ++st.trial;
           if (verdict[c] == 1) { ++st.fail0; continue; }
           if (verdict[c] == 2) { ++st.fail1; continue; }
@@ -632,12 +575,15 @@ void Pipeline::seed_round() {
           if (count_threshold0_ <= count) break;
         }
         if (count != 0 && best) {
-          add_patch(Patch(*best));
+          const int id = add_patch(Patch(*best));
+          for (size_t i = 0; i < patches_[id].images.size(); ++i)
+            if (patches_[id].images[i] < tnum_) refresh(patches_[id].images[i], patches_[id].grids[i][1] * grids_[patches_[id].images[i]].gw + patches_[id].grids[i][0]);
           ++total;
           placed = true;
         }
         f0 = f1;
       }
+      refresh(index, cell);
       k = cell_end;
     }
     std::cerr << '(' << index << ',' << total << ')' << std::flush;

@@ -399,6 +399,7 @@ void Pipeline::detect_features() {
     if (pmvsb_detect_features(gpu_, i, fcsize, cap, xy.data(), resp.data(), type.data(), &n)) die("detect_features");
     features_[i].resize(n);
     for (int k = 0; k < n; ++k) features_[i][k] = {xy[2 * k], xy[2 * k + 1], resp[k], type[k]};
+    if (pmvsb_set_features(gpu_, i, n, xy.data(), type.data())) die("set_features");   // CSeed::readPoints: binned on the device side
     total += (size_t)n;
   }
   std::cerr << "features: " << total << " in " << num_ << " images" << std::endl;

@@ -270,6 +270,24 @@ int pmvsb_refine_batch_dev(pmvsb_ctx* ctx, int P, int stride, float* d_coords, f
  * float[cap], type int32[cap] (0 Harris, 1 DoG); *count = number of features found (may exceed cap). */
 int pmvsb_detect_features(pmvsb_ctx* ctx, int index, int gspeedup, int cap, float* xy, float* response, int32_t* type, int32_t* count);
 
+/* ---- seed candidate enumeration ------------------------------------------------------------------
+ * CSeed::readPoints (source/pmvs/seed.cpp:23-36): the features of image `index` (what pmvsb_detect_features returned, or the
+ * caller's own), binned by cell on upload in the order given. */
+int pmvsb_set_features(pmvsb_ctx* ctx, int index, int n, const float* xy, const int32_t* type);
+/* CSeed::collectCells + collectCandidates + unproject (seed.cpp:207-384) for EVERY feature of reference image `index` that sits in
+ * a cell open for a patch, in one launch.  views[nviews] = COptim::collectImages' list (optim.cpp:66-93; nviews <= PMVSB_MAX_TAU);
+ * blocked = uint8 per cell of every image's grid, images back to back (targets and others; cell = y * gwidth + x of
+ * pmvsb_grid_dims), non-zero where CSeed::canAdd(image, x, y) is 0 (seed.cpp:325-338: mask, occupied, trial count reached).
+ * Outputs, per reference feature r < *nref in (cell, feature-in-cell) order: ref_feature[r] (index into the image's feature
+ * list), ref_cell[r], and its candidates [ref_start[r], ref_start[r] + ref_count[r]) in coords float[4 * ..] (the triangulated
+ * point, w = 1), other_image, other_feature (index into that image's list), resp = |dist to camera `index` - dist to the other
+ * camera|; a feature's candidates are in ascending resp order, ties in the reference's enumeration order.  The candidate set and
+ * all values equal the reference's; see pmvs_seed.cuh on the order.  Sizing: when *nref > cap_ref or *total > cap nothing (or
+ * only the per-feature arrays) is written -- call again with room. */
+int pmvsb_seed_candidates(pmvsb_ctx* ctx, int index, int nviews, const int32_t* views, const uint8_t* blocked, int cap_ref, int32_t* nref,
+                          int32_t* ref_feature, int32_t* ref_cell, int32_t* ref_start, int32_t* ref_count, int cap, int32_t* total,
+                          float* coords, int32_t* other_image, int32_t* other_feature, float* resp);
+
 /* ---- multi-GPU -------------------------------------------------------------------------------------
  * One process and one context per GPU, images and cameras replicated (the reference shares one CPhotoSetS between its
  * worker threads, findMatch.hpp).  The candidates of a wave are independent given the grid snapshot, so each rank

@@ -444,6 +444,47 @@ int ref_check(int k, float quad, float* gain) {
   *gain = p._tmp;
   return r;
 }
+// ---- seed stage (before ref_run: CFindMatch::run frees CSeed::_ppoints when the seeds are done) ----------------------
+// features of image `index` as CSeed holds them (cells row-major, a cell's features in detection order)
+int ref_features(int index, float* xy, int* type, int cap) {
+  int n = 0;
+  for (const auto& cell : g_fm->_seed._ppoints[index])
+    for (const auto& pp : cell) {
+      if (n < cap) { xy[2 * n] = pp->_icoord[0]; xy[2 * n + 1] = pp->_icoord[1]; type[n] = pp->_type; }
+      ++n;
+    }
+  return n;
+}
+int ref_collect_images(int index, int* out, int cap) {
+  std::vector<int> indexes;
+  g_fm->_optim.collectImages(index, indexes);
+  if (g_fm->_tau < (int)indexes.size()) indexes.resize(g_fm->_tau);   // seed.cpp:124-126
+  for (int i = 0; i < (int)indexes.size() && i < cap; ++i) out[i] = indexes[i];
+  return (int)indexes.size();
+}
+// CPatchOrganizerS::_counts of one target image (what CSeed::canAdd reads beside _pgrids)
+void ref_set_counts(int image, const unsigned char* counts) {
+  std::vector<unsigned char>& c = g_fm->_pos._counts[image];
+  std::memcpy(c.data(), counts, c.size());
+}
+int ref_can_add(int image, int x, int y) { return g_fm->_seed.canAdd(image, x, y); }
+// CSeed::collectCandidates for feature p of cell `cell` of image `index`: per candidate the other image, the other
+// feature's pixel, the triangulated point and _response.  (The order is the reference's sort of shared_ptr values.)
+int ref_collect_candidates(int index, int cell, int p, int* other_image, float* other_xy, float* coords, float* resp, int cap) {
+  std::vector<int> indexes;
+  g_fm->_optim.collectImages(index, indexes);
+  if (g_fm->_tau < (int)indexes.size()) indexes.resize(g_fm->_tau);
+  std::vector<PPoint> vcp;
+  g_fm->_seed.collectCandidates(index, indexes, *g_fm->_seed._ppoints[index][cell][p], vcp);
+  for (int i = 0; i < (int)vcp.size() && i < cap; ++i) {
+    other_image[i] = vcp[i]->_itmp;
+    other_xy[2 * i] = vcp[i]->_icoord[0]; other_xy[2 * i + 1] = vcp[i]->_icoord[1];
+    out4(vcp[i]->_coord, coords + 4 * i);
+    resp[i] = vcp[i]->_response;
+  }
+  return (int)vcp.size();
+}
+
 // ---- filter-round stages on the reference's own state --------------------------------------------------------------
 // removePatch for the table patches (numbering of ref_collect_patches) with keep[k] == 0, then
 // CFilter::setDepthMapsVGridsVPGridsAddPatchV(additive); old_index[i] = former table index of new table patch i.
