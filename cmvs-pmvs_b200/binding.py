@@ -19,7 +19,7 @@ SYMBOLS = [
     "pmvsb_create", "pmvsb_destroy", "pmvsb_last_error", "pmvsb_version", "pmvsb_device_count", "pmvsb_upload_camera", "pmvsb_upload_image",
     "pmvsb_upload_mask", "pmvsb_set_edge", "pmvsb_set_bimages", "pmvsb_download_mask", "pmvsb_mask_gate_batch",
     "pmvsb_remove_images_edge_batch", "pmvsb_store_set_seq", "pmvsb_store_counts", "pmvsb_store_rebuild", "pmvsb_filter_exact_apply_store",
-    "pmvsb_set_features", "pmvsb_seed_candidates", "pmvsb_small_group_edges_store", "pmvsb_filter_small_groups_store", "pmvsb_store_download_lists", "pmvsb_set_visdata2", "pmvsb_finalize_scene", "pmvsb_set_thresholds", "pmvsb_set_optimizer", "pmvsb_image_dims",
+    "pmvsb_set_features", "pmvsb_seed_candidates", "pmvsb_evaluate_batch", "pmvsb_evaluate_fetch", "pmvsb_small_group_edges_store", "pmvsb_filter_small_groups_store", "pmvsb_store_download_lists", "pmvsb_set_visdata2", "pmvsb_finalize_scene", "pmvsb_set_thresholds", "pmvsb_set_optimizer", "pmvsb_image_dims",
     "pmvsb_download_image", "pmvsb_get_camera", "pmvsb_project_batch", "pmvsb_grab_tex_batch", "pmvsb_eval_objective_batch",
     "pmvsb_compute_incc_batch", "pmvsb_set_inccs_batch", "pmvsb_set_scales_batch", "pmvsb_pre_process_batch",
     "pmvsb_post_process_batch", "pmvsb_set_depth", "pmvsb_grid_dims", "pmvsb_store_upload", "pmvsb_build_depth_maps",
@@ -369,6 +369,15 @@ class PmvsB200:
         self._ck(self.lib.pmvsb_download_depth_map(self.ctx, int(image), _vp(out)))
         return out
 
+    def set_vimages_batch(self, coords, normals, images, nimages, vimages, nv, vgrids):
+        """setVImagesVGrids for candidates outside the table: -> (vimages (P, vstride), nv, vgrids (P, vstride, 2)); inputs are not modified"""
+        P, stride, coords, normals, images, nimages, _ = _patch_arrays(coords, normals, images, nimages)
+        vim = np.ascontiguousarray(vimages, dtype=np.int32).reshape(P, -1).copy()
+        n = np.ascontiguousarray(nv, dtype=np.int32).reshape(P).copy()
+        vgr = np.ascontiguousarray(vgrids, dtype=np.int32).reshape(P, vim.shape[1], 2).copy()
+        self._ck(self.lib.pmvsb_set_vimages_batch(self.ctx, P, stride, _vp(coords), _vp(normals), _vp(images), _vp(nimages), vim.shape[1], _vp(vim), _vp(n), _vp(vgr)))
+        return vim, n, vgr
+
     def set_vimages_store(self, vcap):
         P = self._store_P
         vim = np.zeros((P, vcap), np.int32); vgr = np.zeros((P, vcap, 2), np.int32); nv = np.zeros(P, np.int32)
@@ -407,6 +416,23 @@ class PmvsB200:
         self._ck(self.lib.pmvsb_detect_features(self.ctx, int(index), int(gspeedup), cap, _vp(xy), _vp(resp), _vp(types), C.byref(n)))
         k = min(n.value, cap)
         return xy[:k].copy(), resp[:k].copy(), types[:k].copy()
+
+    def evaluate_batch(self, coords, normals, img_off, images, quad=2.5):
+        """preProcess -> refinePatch -> postProcess for a wave of candidates in one call.
+        -> dict(verdict (P,), refined, index, coords, normals, ncc, dscale, ascale, tmp, timages, img_off, images, grids, vimg_off, vimages, vgrids)"""
+        coords = _f32(coords).reshape(-1, 4); normals = _f32(normals).reshape(-1, 4)
+        P = coords.shape[0]
+        img_off = np.ascontiguousarray(img_off, dtype=np.int32); images = np.ascontiguousarray(images, dtype=np.int32)
+        A, E, VE, R = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self.lib.pmvsb_evaluate_batch(self.ctx, P, _vp(coords), _vp(normals), _vp(img_off), _vp(images), C.c_float(quad), C.byref(A), C.byref(E),
+                                               C.byref(VE), C.byref(R)))
+        a, e, ve = A.value, E.value, VE.value
+        v = np.zeros(P, np.int32); idx = np.zeros(max(a, 1), np.int32); co = np.zeros((max(a, 1), 4), np.float32); no = np.zeros((max(a, 1), 4), np.float32)
+        sc = np.zeros((max(a, 1), 4), np.float32); ti = np.zeros(max(a, 1), np.int32); off = np.zeros(a + 1, np.int32); im = np.zeros(max(e, 1), np.int32)
+        gr = np.zeros((max(e, 1), 2), np.int32); voff = np.zeros(a + 1, np.int32); vim = np.zeros(max(ve, 1), np.int32); vgr = np.zeros((max(ve, 1), 2), np.int32)
+        self._ck(self.lib.pmvsb_evaluate_fetch(self.ctx, _vp(v), _vp(idx), _vp(co), _vp(no), _vp(sc), _vp(ti), _vp(off), _vp(im), _vp(gr), _vp(voff), _vp(vim), _vp(vgr)))
+        return dict(verdict=v, refined=R.value, index=idx[:a], coords=co[:a], normals=no[:a], ncc=sc[:a, 0], dscale=sc[:a, 1], ascale=sc[:a, 2], tmp=sc[:a, 3],
+                    timages=ti[:a], img_off=off, images=im[:e], grids=gr[:e], vimg_off=voff, vimages=vim[:ve], vgrids=vgr[:ve])
 
     def set_features(self, index, xy, types):
         xy = _f32(xy).reshape(-1, 2); types = np.ascontiguousarray(types, dtype=np.int32).reshape(-1)

@@ -678,6 +678,12 @@ struct pmvsb_ctx {
   DVec<int32_t> d_ftype, d_fcell_base, d_fcell_off, d_flist, d_fgw, d_fgh;
   DVec<uint8_t> d_blocked;
   DVec<SeedHit> d_seed_out;
+  // results of the last pmvsb_evaluate_batch, kept on the device until pmvsb_evaluate_fetch
+  struct EvalOut {
+    int P = 0, A = 0, E = 0, VE = 0, refined = 0;
+    DVec<int32_t> verdict, index, timages, img_off, images, grids, vimg_off, vimages, vgrids;
+    DVec<float> coords, normals, scal;   // scal = (ncc, dscale, ascale, tmp) per accepted candidate
+  } ev;
   std::vector<int32_t> bimages;
   int32_t* d_bimages = nullptr;
   // filter-stage patch table
@@ -2770,6 +2776,207 @@ int pmvsb_refine_batch_dev(pmvsb_ctx* ctx, int P, int stride, float* d_coords, f
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->refine_timed = true;
   CK(cudaGetLastError());
+  return PMVSB_OK;
+}
+
+
+// ---- the in-process contract of the hot path, batched ------------------------------------------------------------
+//   if (preProcess(patch, id, seed)) fail;  refinePatch(patch, id, 100);  if (postProcess(patch, id, seed)) fail;
+// (source/pmvs/seed.cpp:397-409, expand.cpp:225-237) for a whole wave of candidates without leaving the device between the
+// stages: pre -> compaction -> refine -> post (incl. setVImagesVGrids at _depth >= 1 and check at _depth >= 2) -> compaction.
+__global__ void k_pack_scal(int n, const float* __restrict__ ncc, const float* __restrict__ dscale, const float* __restrict__ ascale, const float* __restrict__ tmp,
+                            float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float4(ncc[i], dscale[i], ascale[i], tmp[i]);
+}
+
+int pmvsb_evaluate_batch(pmvsb_ctx* ctx, int P, const float* coords, const float* normals, const int32_t* img_off, const int32_t* images, float quad,
+                         int32_t* accepted, int32_t* entries, int32_t* ventries, int32_t* refined) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  if (P < 0 || !accepted || !entries || !ventries || (P > 0 && (!coords || !normals || !img_off || !images)))
+    return fail(ctx, PMVSB_EINVAL, "evaluate_batch: bad argument");
+  if (ctx->depth_flag >= 1 && (r = need_store(ctx, true))) return r;
+  pmvsb_ctx::EvalOut& ev = ctx->ev;
+  ev.P = P; ev.A = ev.E = ev.VE = ev.refined = 0;
+  *accepted = *entries = *ventries = 0;
+  if (refined) *refined = 0;
+  if (P == 0) return PMVSB_OK;
+  const int Ein = img_off[P];
+  for (int e = 0; e < Ein; ++e)
+    if ((unsigned)images[e] >= (unsigned)ctx->num) return fail(ctx, PMVSB_EINVAL, "evaluate_batch: image index out of range");
+  const int stride = std::min(ctx->num, PMVSB_MAX_VIEWS), vs = std::max(ctx->tnum, 1);
+  if (ctx->wsize == 9 && stride > 32) return fail(ctx, PMVSB_EINVAL, "evaluate_batch: wsize 9 keeps at most 32 images per patch in the selection kernels");
+  cudaStream_t q = ctx->stream;
+  // ---- stage 0: candidates to the device, lists into stride-padded rows
+  DevBuf<float> c0, n0, ds0, as0;
+  DevBuf<int32_t> off0, im0, rows0, cnt0, v0, pos0;
+  CK(c0.alloc((size_t)4 * P)); CK(n0.alloc((size_t)4 * P)); CK(ds0.alloc(P)); CK(as0.alloc(P)); CK(off0.alloc((size_t)P + 1)); CK(im0.alloc((size_t)std::max(Ein, 1)));
+  CK(rows0.alloc((size_t)stride * P)); CK(cnt0.alloc(P)); CK(v0.alloc(P)); CK(pos0.alloc((size_t)P + 1));
+  CK(cudaMemcpyAsync(c0.p, coords, sizeof(float) * 4 * (size_t)P, cudaMemcpyHostToDevice, q));
+  CK(cudaMemcpyAsync(n0.p, normals, sizeof(float) * 4 * (size_t)P, cudaMemcpyHostToDevice, q));
+  CK(cudaMemcpyAsync(off0.p, img_off, sizeof(int32_t) * ((size_t)P + 1), cudaMemcpyHostToDevice, q));
+  if (Ein > 0) CK(cudaMemcpyAsync(im0.p, images, sizeof(int32_t) * (size_t)Ein, cudaMemcpyHostToDevice, q));
+  k_rows_from_csr<<<(P + 255) / 256, 256, 0, q>>>(P, stride, off0.p, im0.p, rows0.p, cnt0.p);
+  // ---- preProcess
+#define LAUNCH_PRE(W, MAXV) k_pre_process<W, MAXV><<<P, 32, 0, q>>>(ctx->scene, ctx->select, P, stride, c0.p, n0.p, rows0.p, cnt0.p, ds0.p, as0.p, v0.p)
+  DISPATCH_VIEWS(ctx, stride, LAUNCH_PRE);
+#undef LAUNCH_PRE
+  k_flag_zero<<<(P + 256) / 256, 256, 0, q>>>(P, v0.p, pos0.p);
+  ctx->launches += 3;
+  if ((r = device_scan(ctx, pos0.p, P + 1))) return r;
+  int32_t L = 0;
+  CK(cudaMemcpyAsync(&L, pos0.p + P, sizeof(int32_t), cudaMemcpyDeviceToHost, q));
+  CK(cudaStreamSynchronize(q));
+  if ((r = dvec_reserve(ctx, ev.verdict, (size_t)P))) return r;
+  ev.refined = L;
+  if (refined) *refined = L;
+  if (L == 0) {
+    CK(cudaMemcpyAsync(ev.verdict.p, v0.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToDevice, q));   // all 1
+    CK(cudaStreamSynchronize(q));
+    return check_view_overflow(ctx, "evaluate_batch", stride);
+  }
+  // ---- survivors to the front; refinePatch; postProcess
+  DevBuf<float> c1, n1, ds1, as1, ncc1, tmp1;
+  DevBuf<int32_t> idx1, rows1, cnt1, ev1, gr1, ti1, v1, pos1;
+  DevBuf<uint8_t> ok1;
+  CK(c1.alloc((size_t)4 * L)); CK(n1.alloc((size_t)4 * L)); CK(ds1.alloc(L)); CK(as1.alloc(L)); CK(ncc1.alloc(L)); CK(tmp1.alloc(L)); CK(idx1.alloc(L));
+  CK(rows1.alloc((size_t)stride * L)); CK(cnt1.alloc(L)); CK(ev1.alloc(L)); CK(gr1.alloc((size_t)2 * stride * L)); CK(ti1.alloc(L)); CK(v1.alloc(L));
+  CK(pos1.alloc((size_t)L + 1)); CK(ok1.alloc(L));
+  k_compact_patches<<<(int)(((size_t)P * 32 + 255) / 256), 256, 0, q>>>(P, stride, v0.p, pos0.p, nullptr, reinterpret_cast<const float4*>(c0.p),
+      reinterpret_cast<const float4*>(n0.p), rows0.p, cnt0.p, ds0.p, as0.p, idx1.p, reinterpret_cast<float4*>(c1.p), reinterpret_cast<float4*>(n1.p), rows1.p,
+      cnt1.p, ds1.p, as1.p);
+  ++ctx->launches;
+  if ((r = pmvsb_refine_batch_dev(ctx, L, stride, c1.p, n1.p, rows1.p, cnt1.p, ds1.p, ncc1.p, ev1.p, ok1.p))) return r;
+  CK(cudaMemsetAsync(gr1.p, 0xff, sizeof(int32_t) * (size_t)2 * stride * L, q));
+#define LAUNCH_POST(W, MAXV) k_post_process<W, MAXV><<<L, 32, 0, q>>>(ctx->scene, ctx->select, L, stride, c1.p, n1.p, ncc1.p, rows1.p, cnt1.p, gr1.p, ti1.p, tmp1.p, v1.p)
+  DISPATCH_VIEWS(ctx, stride, LAUNCH_POST);
+#undef LAUNCH_POST
+  k_scatter_verdict<<<(L + 255) / 256, 256, 0, q>>>(L, idx1.p, v1.p, nullptr, 2, v0.p);
+  k_flag_zero<<<(L + 256) / 256, 256, 0, q>>>(L, v1.p, pos1.p);
+  ctx->launches += 3;
+  if ((r = device_scan(ctx, pos1.p, L + 1))) return r;
+  int32_t A = 0;
+  CK(cudaMemcpyAsync(&A, pos1.p + L, sizeof(int32_t), cudaMemcpyDeviceToHost, q));
+  CK(cudaStreamSynchronize(q));
+  // ---- accepted so far to the front
+  const size_t A1 = (size_t)std::max(A, 1);
+  DevBuf<float> c2, n2, ds2, as2, ncc2, tmp2, gain2;
+  DevBuf<int32_t> idx2, rows2, cnt2, gr2, ti2, vim2, nv2, vgr2, v2, pos2, dov;
+  DevBuf<uint8_t> rej2;
+  CK(c2.alloc(4 * A1)); CK(n2.alloc(4 * A1)); CK(ds2.alloc(A1)); CK(as2.alloc(A1)); CK(ncc2.alloc(A1)); CK(tmp2.alloc(A1)); CK(gain2.alloc(A1)); CK(idx2.alloc(A1));
+  CK(rows2.alloc((size_t)stride * A1)); CK(cnt2.alloc(A1)); CK(gr2.alloc((size_t)2 * stride * A1)); CK(ti2.alloc(A1)); CK(vim2.alloc((size_t)vs * A1));
+  CK(nv2.alloc(A1)); CK(vgr2.alloc((size_t)2 * vs * A1)); CK(v2.alloc(A1)); CK(pos2.alloc(A1 + 1)); CK(dov.alloc(1)); CK(rej2.alloc(A1));
+  int32_t A2 = A;
+  if (A > 0) {
+    const int gl = (int)(((size_t)L * 32 + 255) / 256);
+    k_compact_patches<<<gl, 256, 0, q>>>(L, stride, v1.p, pos1.p, idx1.p, reinterpret_cast<const float4*>(c1.p), reinterpret_cast<const float4*>(n1.p), rows1.p,
+                                         cnt1.p, ds1.p, as1.p, idx2.p, reinterpret_cast<float4*>(c2.p), reinterpret_cast<float4*>(n2.p), rows2.p, cnt2.p, ds2.p, as2.p);
+    k_compact_extras<<<gl, 256, 0, q>>>(L, stride, v1.p, pos1.p, cnt1.p, gr1.p, ncc1.p, ok1.p, ti1.p, tmp1.p, gr2.p, ncc2.p, ti2.p, tmp2.p);
+    ctx->launches += 2;
+    CK(cudaMemsetAsync(nv2.p, 0, sizeof(int32_t) * A1, q));
+    if (ctx->depth_flag >= 1) {   // setVImagesVGrids against the current depth maps (optim.cpp:184-186)
+      k_set_vimages_batch<<<(A + 3) / 4, 128, 0, q>>>(ctx->scene, ctx->store, A, stride, c2.p, n2.p, rows2.p, cnt2.p, vs, vim2.p, nv2.p, vgr2.p);
+      ++ctx->launches;
+    }
+    if (ctx->depth_flag >= 2) {   // COptim::check (optim.cpp:363-383): gain against the table's cells, then the quadric fit
+      CK(cudaMemsetAsync(dov.p, 0, sizeof(int32_t), q));
+      k_check_batch<<<(A + kNbWarps - 1) / kNbWarps, kNbWarps * 32, 0, q>>>(ctx->scene, ctx->store, A, stride, vs, c2.p, n2.p, ncc2.p, ds2.p, ti2.p, rows2.p, cnt2.p,
+                                                                           gr2.p, vim2.p, nv2.p, vgr2.p, quad, ctx->tau, gain2.p, rej2.p, dov.p);
+      k_merge_reject<<<(A + 255) / 256, 256, 0, q>>>(A, rej2.p, gain2.p, v2.p, tmp2.p);
+      k_scatter_verdict<<<(A + 255) / 256, 256, 0, q>>>(A, idx2.p, v2.p, nullptr, 2, v0.p);
+      k_flag_zero<<<(A + 256) / 256, 256, 0, q>>>(A, v2.p, pos2.p);
+      ctx->launches += 4;
+      if ((r = device_scan(ctx, pos2.p, A + 1))) return r;
+      CK(cudaMemcpyAsync(&A2, pos2.p + A, sizeof(int32_t), cudaMemcpyDeviceToHost, q));
+      CK(cudaStreamSynchronize(q));
+    }
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ev.verdict.p, v0.p, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToDevice, q));
+  // ---- the accepted candidates' records, lists as CSR
+  const size_t F1 = (size_t)std::max(A2, 1);
+  if ((r = dvec_reserve(ctx, ev.index, F1)) || (r = dvec_reserve(ctx, ev.timages, F1)) || (r = dvec_reserve(ctx, ev.coords, 4 * F1)) ||
+      (r = dvec_reserve(ctx, ev.normals, 4 * F1)) || (r = dvec_reserve(ctx, ev.scal, 4 * F1)) || (r = dvec_reserve(ctx, ev.img_off, F1 + 1)) ||
+      (r = dvec_reserve(ctx, ev.vimg_off, F1 + 1)))
+    return r;
+  int32_t E = 0, VE = 0;
+  if (A2 > 0) {
+    const float *fc = c2.p, *fn = n2.p, *fncc = ncc2.p, *fds = ds2.p, *fas = as2.p, *ftmp = tmp2.p;
+    const int32_t *fidx = idx2.p, *frows = rows2.p, *fcnt = cnt2.p, *fgr = gr2.p, *fti = ti2.p, *fvim = vim2.p, *fnv = nv2.p, *fvgr = vgr2.p;
+    DevBuf<float> c3, n3, ds3, as3, ncc3, tmp3;
+    DevBuf<int32_t> idx3, rows3, cnt3, gr3, ti3, vim3, nv3, vgr3;
+    if (A2 != A) {   // check rejected some: one more compaction (image rows, cells, visible-image rows)
+      CK(c3.alloc(4 * F1)); CK(n3.alloc(4 * F1)); CK(ds3.alloc(F1)); CK(as3.alloc(F1)); CK(ncc3.alloc(F1)); CK(tmp3.alloc(F1)); CK(idx3.alloc(F1));
+      CK(rows3.alloc((size_t)stride * F1)); CK(cnt3.alloc(F1)); CK(gr3.alloc((size_t)2 * stride * F1)); CK(ti3.alloc(F1)); CK(vim3.alloc((size_t)vs * F1));
+      CK(nv3.alloc(F1)); CK(vgr3.alloc((size_t)2 * vs * F1));
+      DevBuf<uint8_t> ones;
+      CK(ones.alloc(A1));
+      CK(cudaMemsetAsync(ones.p, 1, A1, q));
+      const int gl = (int)(((size_t)A * 32 + 255) / 256);
+      k_compact_patches<<<gl, 256, 0, q>>>(A, stride, v2.p, pos2.p, idx2.p, reinterpret_cast<const float4*>(c2.p), reinterpret_cast<const float4*>(n2.p), rows2.p,
+                                           cnt2.p, ds2.p, as2.p, idx3.p, reinterpret_cast<float4*>(c3.p), reinterpret_cast<float4*>(n3.p), rows3.p, cnt3.p, ds3.p, as3.p);
+      k_compact_extras<<<gl, 256, 0, q>>>(A, stride, v2.p, pos2.p, cnt2.p, gr2.p, ncc2.p, ones.p, ti2.p, tmp2.p, gr3.p, ncc3.p, ti3.p, tmp3.p);
+      // visible-image rows: the same kernels with vs as the stride (rows = vimages, cells = vgrids)
+      DevBuf<float> dumpf;
+      DevBuf<int32_t> dumpi;
+      CK(dumpf.alloc(4 * F1)); CK(dumpi.alloc(F1));
+      k_compact_patches<<<gl, 256, 0, q>>>(A, vs, v2.p, pos2.p, idx2.p, reinterpret_cast<const float4*>(c2.p), reinterpret_cast<const float4*>(n2.p), vim2.p,
+                                           nv2.p, nullptr, nullptr, dumpi.p, reinterpret_cast<float4*>(dumpf.p), reinterpret_cast<float4*>(dumpf.p), vim3.p, nv3.p,
+                                           nullptr, nullptr);
+      k_compact_extras<<<gl, 256, 0, q>>>(A, vs, v2.p, pos2.p, nv2.p, vgr2.p, ncc2.p, ones.p, ti2.p, tmp2.p, vgr3.p, dumpf.p, dumpi.p, dumpf.p);
+      ctx->launches += 4;
+      CK(cudaStreamSynchronize(q));   // dumpf / dumpi / ones go back to the pool here
+      fc = c3.p; fn = n3.p; fncc = ncc3.p; fds = ds3.p; fas = as3.p; ftmp = tmp3.p;
+      fidx = idx3.p; frows = rows3.p; fcnt = cnt3.p; fgr = gr3.p; fti = ti3.p; fvim = vim3.p; fnv = nv3.p; fvgr = vgr3.p;
+    }
+    k_copy_len<<<(A2 + 256) / 256, 256, 0, q>>>(A2, fcnt, ev.img_off.p);
+    k_copy_len<<<(A2 + 256) / 256, 256, 0, q>>>(A2, fnv, ev.vimg_off.p);
+    ctx->launches += 2;
+    if ((r = device_scan(ctx, ev.img_off.p, A2 + 1))) return r;
+    if ((r = device_scan(ctx, ev.vimg_off.p, A2 + 1))) return r;
+    CK(cudaMemcpyAsync(&E, ev.img_off.p + A2, sizeof(int32_t), cudaMemcpyDeviceToHost, q));
+    CK(cudaMemcpyAsync(&VE, ev.vimg_off.p + A2, sizeof(int32_t), cudaMemcpyDeviceToHost, q));
+    CK(cudaStreamSynchronize(q));
+    if ((r = dvec_reserve(ctx, ev.images, (size_t)std::max(E, 1))) || (r = dvec_reserve(ctx, ev.grids, (size_t)2 * std::max(E, 1))) ||
+        (r = dvec_reserve(ctx, ev.vimages, (size_t)std::max(VE, 1))) || (r = dvec_reserve(ctx, ev.vgrids, (size_t)2 * std::max(VE, 1))))
+      return r;
+    k_tab_rows_to_lists<<<(A2 + 127) / 128, 128, 0, q>>>(A2, stride, frows, fgr, ev.img_off.p, ev.images.p, ev.grids.p);
+    if (VE > 0) k_tab_rows_to_lists<<<(A2 + 127) / 128, 128, 0, q>>>(A2, vs, fvim, fvgr, ev.vimg_off.p, ev.vimages.p, ev.vgrids.p);
+    k_pack_scal<<<(A2 + 255) / 256, 256, 0, q>>>(A2, fncc, fds, fas, ftmp, reinterpret_cast<float4*>(ev.scal.p));
+    ctx->launches += 3;
+    CK(cudaMemcpyAsync(ev.coords.p, fc, sizeof(float) * 4 * (size_t)A2, cudaMemcpyDeviceToDevice, q));
+    CK(cudaMemcpyAsync(ev.normals.p, fn, sizeof(float) * 4 * (size_t)A2, cudaMemcpyDeviceToDevice, q));
+    CK(cudaMemcpyAsync(ev.index.p, fidx, sizeof(int32_t) * (size_t)A2, cudaMemcpyDeviceToDevice, q));
+    CK(cudaMemcpyAsync(ev.timages.p, fti, sizeof(int32_t) * (size_t)A2, cudaMemcpyDeviceToDevice, q));
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(q));
+  ev.A = A2; ev.E = E; ev.VE = VE;
+  *accepted = A2; *entries = E; *ventries = VE;
+  return check_view_overflow(ctx, "evaluate_batch", stride);
+}
+
+int pmvsb_evaluate_fetch(pmvsb_ctx* ctx, int32_t* verdict, int32_t* index, float* coords, float* normals, float* scal, int32_t* timages, int32_t* img_off,
+                         int32_t* images, int32_t* grids, int32_t* vimg_off, int32_t* vimages, int32_t* vgrids) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  const pmvsb_ctx::EvalOut& ev = ctx->ev;
+  cudaStream_t q = ctx->stream;
+  auto down = [&](void* h, const void* d, size_t bytes) { return (h && bytes) ? cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, q) : cudaSuccess; };
+  CK(down(verdict, ev.verdict.p, sizeof(int32_t) * (size_t)ev.P));
+  if (ev.A > 0) {
+    CK(down(index, ev.index.p, sizeof(int32_t) * (size_t)ev.A)); CK(down(coords, ev.coords.p, sizeof(float) * 4 * (size_t)ev.A));
+    CK(down(normals, ev.normals.p, sizeof(float) * 4 * (size_t)ev.A)); CK(down(scal, ev.scal.p, sizeof(float) * 4 * (size_t)ev.A));
+    CK(down(timages, ev.timages.p, sizeof(int32_t) * (size_t)ev.A)); CK(down(img_off, ev.img_off.p, sizeof(int32_t) * ((size_t)ev.A + 1)));
+    CK(down(images, ev.images.p, sizeof(int32_t) * (size_t)ev.E)); CK(down(grids, ev.grids.p, sizeof(int32_t) * 2 * (size_t)ev.E));
+    CK(down(vimg_off, ev.vimg_off.p, sizeof(int32_t) * ((size_t)ev.A + 1))); CK(down(vimages, ev.vimages.p, sizeof(int32_t) * (size_t)ev.VE));
+    CK(down(vgrids, ev.vgrids.p, sizeof(int32_t) * 2 * (size_t)ev.VE));
+  } else {
+    if (img_off) img_off[0] = 0;
+    if (vimg_off) vimg_off[0] = 0;
+  }
+  CK(cudaStreamSynchronize(q));
   return PMVSB_OK;
 }
 

@@ -178,4 +178,71 @@ __global__ void k_tab_group_edges(SceneDev s, StoreDev st, float thr, int32_t* _
   if (!FILL) count[p] = n;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// plumbing of the fused candidate evaluation (pmvsb_evaluate_batch): CSR <-> stride-padded rows, compaction
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_rows_from_csr(int P, int stride, const int32_t* __restrict__ off, const int32_t* __restrict__ items, int32_t* __restrict__ rows,
+                                int32_t* __restrict__ n) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int b = off[p], len = min(off[p + 1] - b, stride);
+  for (int i = 0; i < len; ++i) rows[(size_t)p * stride + i] = items[b + i];
+  n[p] = len;
+}
+// flag[i] = (verdict[i] == 0), slot P = 0 (the scan turns the array into positions, the last slot into the count)
+__global__ void k_flag_zero(int P, const int32_t* __restrict__ verdict, int32_t* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > P) return;
+  flag[i] = (i < P && verdict[i] == 0) ? 1 : 0;
+}
+// survivors of a stage move to the front: per-patch scalars and the stride-padded image rows
+__global__ void k_compact_patches(int P, int stride, const int32_t* __restrict__ verdict, const int32_t* __restrict__ pos, const int32_t* __restrict__ src_index,
+                                  const float4* __restrict__ coords, const float4* __restrict__ normals, const int32_t* __restrict__ rows,
+                                  const int32_t* __restrict__ n, const float* __restrict__ a, const float* __restrict__ b, int32_t* __restrict__ out_index,
+                                  float4* __restrict__ ocoords, float4* __restrict__ onormals, int32_t* __restrict__ orows, int32_t* __restrict__ on,
+                                  float* __restrict__ oa, float* __restrict__ ob) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= P || verdict[warp] != 0) return;
+  const int j = pos[warp];
+  if (lane == 0) {
+    out_index[j] = src_index ? src_index[warp] : warp;
+    ocoords[j] = coords[warp]; onormals[j] = normals[warp]; on[j] = n[warp];
+    if (a) oa[j] = a[warp];
+    if (b) ob[j] = b[warp];
+  }
+  const int len = n[warp];
+  for (int i = lane; i < len; i += 32) orows[(size_t)j * stride + i] = rows[(size_t)warp * stride + i];
+}
+// same for the companions of an accepted candidate: cell rows (2 ints per image) and per-patch scalars
+__global__ void k_compact_extras(int P, int stride, const int32_t* __restrict__ verdict, const int32_t* __restrict__ pos, const int32_t* __restrict__ n,
+                                 const int32_t* __restrict__ cells, const float* __restrict__ ncc, const uint8_t* __restrict__ ok,
+                                 const int32_t* __restrict__ timages, const float* __restrict__ tmp, int32_t* __restrict__ ocells, float* __restrict__ oncc,
+                                 int32_t* __restrict__ otimages, float* __restrict__ otmp) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= P || verdict[warp] != 0) return;
+  const int j = pos[warp];
+  if (lane == 0) { oncc[j] = ok[warp] ? ncc[warp] : -1.0f; otimages[j] = timages[warp]; otmp[j] = tmp[warp]; }   // a failed optimiser leaves _ncc untouched (optim.cpp:649-655)
+  const int len = n[warp];
+  for (int i = lane; i < 2 * len; i += 32) ocells[(size_t)j * 2 * stride + i] = cells[(size_t)warp * 2 * stride + i];
+}
+// verdicts of a later stage scattered back to the candidates they belong to (index[j] = candidate of compacted slot j)
+__global__ void k_scatter_verdict(int n, const int32_t* __restrict__ index, const int32_t* __restrict__ v, const uint8_t* __restrict__ rej, int value,
+                                  int32_t* __restrict__ verdict) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const bool bad = v ? v[j] != 0 : rej[j] != 0;
+  if (bad) verdict[index[j]] = value;
+}
+__global__ void k_copy_len(int n, const int32_t* __restrict__ len, int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  out[i] = i < n ? len[i] : 0;
+}
+__global__ void k_merge_reject(int n, const uint8_t* __restrict__ rej, const float* __restrict__ gain, int32_t* __restrict__ verdict, float* __restrict__ tmp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  tmp[i] = gain[i];                       // COptim::check stores the gain in _tmp (optim.cpp:366)
+  verdict[i] = rej[i] ? 1 : 0;
+}
+
 }  // namespace pmvsb

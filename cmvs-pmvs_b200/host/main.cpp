@@ -7,6 +7,8 @@
 #include <iostream>
 #include <string>
 
+#include <unistd.h>
+
 #include "pmvs_host.hpp"
 
 int main(int argc, char* argv[]) {
@@ -49,5 +51,11 @@ int main(int argc, char* argv[]) {
   }
   pipe.write(std::string(argv[1]) + "models/" + argv[2], true, patch, pset);   // rank 0 writes
   std::cerr << "time main.total " << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() << " s" << std::endl;
-  return 0;
+  // The models are on disk and every stream is flushed.  Leave without unwinding: freeing a few thousand device allocations one
+  // by one and tearing the CUDA context down from user space costs ~0.5 s of a ~3 s run, and the driver releases everything
+  // when the process goes away anyway.
+  std::cout.flush();
+  std::cerr.flush();
+  std::fflush(nullptr);
+  _exit(0);
 }

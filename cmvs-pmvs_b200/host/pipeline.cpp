@@ -262,94 +262,43 @@ void Pipeline::evaluate_range(std::vector<Candidate>& all, std::vector<int>& all
   if (P <= 0) return;
   Candidate* cands = all.data() + lo;      // this rank's shard of the wave
   int* verdict = all_verdict.data() + lo;
-  const int stride = std::min(num_, 64);
-  std::vector<float> coords((size_t)4 * P), normals((size_t)4 * P), dsc(P), asc(P), ncc(P, -1.0f), tmp(P);
-  std::vector<int32_t> images((size_t)stride * P, 0), nimages(P), v0(P), evals(P), grids((size_t)2 * stride * P), timages(P), v1(P);
-  std::vector<uint8_t> ok(P);
+  // the reference's per-candidate contract -- preProcess, refinePatch, postProcess (seed.cpp:397-409, expand.cpp:225-237) -- as
+  // ONE library call for the whole shard: the stages chain on the device, only the accepted candidates' records come back
+  static thread_local std::vector<float> coords, normals, acoords, anormals, ascal;
+  static thread_local std::vector<int32_t> ioff, images, v, aindex, ati, aoff, aim, agr, avoff, avim, avgr;
+  coords.resize((size_t)4 * P); normals.resize((size_t)4 * P); ioff.resize((size_t)P + 1); v.resize(P);
+  ioff[0] = 0;
+  for (int k = 0; k < P; ++k) ioff[k + 1] = ioff[k] + (int32_t)cands[k].patch.images.size();
+  images.resize(std::max(1, ioff[P]));
   parallel_for(P, threads_, [&](int k) {
     const Patch& p = cands[k].patch;
     for (int c = 0; c < 4; ++c) { coords[4 * k + c] = p.coord[c]; normals[4 * k + c] = p.normal[c]; }
-    nimages[k] = std::min((int)p.images.size(), stride);
-    for (int i = 0; i < nimages[k]; ++i) images[(size_t)k * stride + i] = p.images[i];
-  }, 512);
+    std::copy(p.images.begin(), p.images.end(), images.begin() + ioff[k]);
+  }, 1024);
   if (pmvsb_set_thresholds(gpu_, ncc_threshold_, ncc_threshold_before_)) die("set_thresholds");
-  { Tick tk(this, "gpu.pre_process");
-  if (pmvsb_pre_process_batch(gpu_, P, stride, coords.data(), normals.data(), images.data(), nimages.data(), dsc.data(), asc.data(), v0.data())) die("pre_process_batch"); }
-  // compact the survivors, refine them (tau images each), post-process them
-  std::vector<int> live;
-  for (int k = 0; k < P; ++k) if (v0[k] == 0) live.push_back(k);
-  const int L = (int)live.size();
-  if (L == 0) return;
-  std::vector<float> lc((size_t)4 * L), ln((size_t)4 * L), ld(L), lncc(L), ltmp(L);
-  std::vector<int32_t> li((size_t)stride * L), lni(L), lev(L), lgr((size_t)2 * stride * L), lti(L), lv(L);
-  std::vector<uint8_t> lok(L);
-  parallel_for(L, threads_, [&](int j) {
-    const int k = live[j];
-    for (int c = 0; c < 4; ++c) { lc[4 * j + c] = coords[4 * k + c]; ln[4 * j + c] = normals[4 * k + c]; }
-    ld[j] = dsc[k]; lni[j] = nimages[k];
-    for (int i = 0; i < stride; ++i) li[(size_t)j * stride + i] = images[(size_t)k * stride + i];
+  if (pmvsb_set_depth(gpu_, depth_)) die("set_depth");
+  int32_t A = 0, E = 0, VE = 0, refined = 0;
+  { Tick tk(this, "gpu.evaluate");
+    if (pmvsb_evaluate_batch(gpu_, P, coords.data(), normals.data(), ioff.data(), images.data(), opt_.quad, &A, &E, &VE, &refined)) die("evaluate_batch"); }
+  aindex.resize(std::max(A, 1)); acoords.resize((size_t)4 * std::max(A, 1)); anormals.resize((size_t)4 * std::max(A, 1)); ascal.resize((size_t)4 * std::max(A, 1));
+  ati.resize(std::max(A, 1)); aoff.resize((size_t)A + 1); aim.resize(std::max(E, 1)); agr.resize((size_t)2 * std::max(E, 1)); avoff.resize((size_t)A + 1);
+  avim.resize(std::max(VE, 1)); avgr.resize((size_t)2 * std::max(VE, 1));
+  if (pmvsb_evaluate_fetch(gpu_, v.data(), aindex.data(), acoords.data(), anormals.data(), ascal.data(), ati.data(), aoff.data(), aim.data(), agr.data(),
+                           avoff.data(), avim.data(), avgr.data())) die("evaluate_fetch");
+  for (int k = 0; k < P; ++k) verdict[k] = v[k];
+  parallel_for(A, threads_, [&](int j) {
+    Patch& p = cands[aindex[j]].patch;
+    for (int c = 0; c < 4; ++c) { p.coord[c] = acoords[4 * j + c]; p.normal[c] = anormals[4 * j + c]; }
+    p.ncc = ascal[4 * j]; p.dscale = ascal[4 * j + 1]; p.ascale = ascal[4 * j + 2]; p.tmp = ascal[4 * j + 3];
+    p.timages = ati[j];
+    const int n = aoff[j + 1] - aoff[j], nv = avoff[j + 1] - avoff[j];
+    p.images.assign(aim.begin() + aoff[j], aim.begin() + aoff[j + 1]);
+    p.grids.resize(n);
+    for (int i = 0; i < n; ++i) p.grids[i] = {agr[(size_t)2 * (aoff[j] + i)], agr[(size_t)2 * (aoff[j] + i) + 1]};
+    p.vimages.assign(avim.begin() + avoff[j], avim.begin() + avoff[j + 1]);
+    p.vgrids.resize(nv);
+    for (int i = 0; i < nv; ++i) p.vgrids[i] = {avgr[(size_t)2 * (avoff[j] + i)], avgr[(size_t)2 * (avoff[j] + i) + 1]};
   }, 512);
-  { Tick tk(this, "gpu.refine");
-  if (pmvsb_refine_batch(gpu_, L, stride, lc.data(), ln.data(), li.data(), lni.data(), ld.data(), lncc.data(), lev.data(), lok.data())) die("refine_batch"); }
-  // a failed optimiser leaves the patch untouched and the reference still runs postProcess on it (optim.cpp:496-502)
-  { Tick tk(this, "gpu.post_process");
-  if (pmvsb_post_process_batch(gpu_, L, stride, lc.data(), ln.data(), lncc.data(), li.data(), lni.data(), lgr.data(), lti.data(), ltmp.data(), lv.data())) die("post_process_batch"); }
-  parallel_for(L, threads_, [&](int j) {
-    const int k = live[j];
-    Patch& p = cands[k].patch;
-    if (lv[j] != 0) { verdict[k] = 2; return; }
-    verdict[k] = 0;
-    for (int c = 0; c < 4; ++c) { p.coord[c] = lc[4 * j + c]; p.normal[c] = ln[4 * j + c]; }
-    p.ncc = lok[j] ? lncc[j] : p.ncc;
-    p.dscale = ld[j]; p.ascale = asc[k];
-    p.timages = lti[j]; p.tmp = ltmp[j];
-    p.images.assign(li.begin() + (size_t)j * stride, li.begin() + (size_t)j * stride + lni[j]);
-    p.grids.clear();
-    for (int i = 0; i < lni[j]; ++i) p.grids.push_back({lgr[((size_t)j * stride + i) * 2], lgr[((size_t)j * stride + i) * 2 + 1]});
-    p.vimages.clear(); p.vgrids.clear();
-  }, 512);
-  if (depth_ == 0) return;
-  // setVImagesVGrids for the accepted candidates (optim.cpp:184-186) against the current depth maps
-  std::vector<int> acc;
-  for (int k = 0; k < P; ++k) if (verdict[k] == 0) acc.push_back(k);
-  const int A = (int)acc.size();
-  if (A == 0) return;
-  const int vs = tnum_;
-  std::vector<float> ac((size_t)4 * A), an((size_t)4 * A);
-  std::vector<int32_t> ai((size_t)stride * A, 0), ani(A), avim((size_t)vs * A, 0), anv(A, 0), avgr((size_t)2 * vs * A, 0);
-  for (int j = 0; j < A; ++j) {
-    const Patch& p = cands[acc[j]].patch;
-    for (int c = 0; c < 4; ++c) { ac[4 * j + c] = p.coord[c]; an[4 * j + c] = p.normal[c]; }
-    ani[j] = (int)p.images.size();
-    for (size_t i = 0; i < p.images.size(); ++i) ai[(size_t)j * stride + i] = p.images[i];
-  }
-  if (pmvsb_set_vimages_batch(gpu_, A, stride, ac.data(), an.data(), ai.data(), ani.data(), vs, avim.data(), anv.data(), avgr.data())) die("set_vimages_batch");
-  for (int j = 0; j < A; ++j) {
-    Patch& p = cands[acc[j]].patch;
-    for (int i = 0; i < anv[j]; ++i) {
-      p.vimages.push_back(avim[(size_t)j * vs + i]);
-      p.vgrids.push_back({avgr[((size_t)j * vs + i) * 2], avgr[((size_t)j * vs + i) * 2 + 1]});
-    }
-  }
-  if (depth_ < 2) return;
-  // COptim::check (optim.cpp:363-383), the last step of postProcess from the second round on: gain against the cells of
-  // the resident table, then the quadric fit over its neighbours
-  Tick tk(this, "gpu.check");
-  std::vector<float> ancc(A), adsc(A), again(A);
-  std::vector<int32_t> ati(A), agr((size_t)2 * stride * A, 0);
-  std::vector<uint8_t> arej(A);
-  for (int j = 0; j < A; ++j) {
-    const Patch& p = cands[acc[j]].patch;
-    ancc[j] = p.ncc; adsc[j] = p.dscale; ati[j] = p.timages;
-    for (size_t i = 0; i < p.grids.size(); ++i) { agr[((size_t)j * stride + i) * 2] = p.grids[i][0]; agr[((size_t)j * stride + i) * 2 + 1] = p.grids[i][1]; }
-  }
-  int32_t overflow = 0;
-  if (pmvsb_check_batch(gpu_, A, stride, ac.data(), an.data(), ancc.data(), adsc.data(), ati.data(), ai.data(), ani.data(), agr.data(), vs, avim.data(),
-                        anv.data(), avgr.data(), opt_.quad, again.data(), arej.data(), &overflow)) die("check_batch");
-  for (int j = 0; j < A; ++j) {
-    cands[acc[j]].patch.tmp = again[j];
-    if (arej[j]) verdict[acc[j]] = 2;
-  }
 }
 
 // pre -> refine -> post (+ vimages at depth >= 1) for a wave.  With several GPUs every rank evaluates a contiguous shard

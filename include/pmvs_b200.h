@@ -143,6 +143,23 @@ int pmvsb_post_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coo
                              const float* ncc, int32_t* images, int32_t* nimages, int32_t* grids,
                              int32_t* timages, float* tmp, int32_t* verdict);
 
+/* The reference's in-process contract for one candidate patch,
+ *     if (preProcess(patch, id, seed)) fail;  refinePatch(patch, id, 100);  if (postProcess(patch, id, seed)) fail;
+ * (source/pmvs/seed.cpp:397-409, expand.cpp:225-237), for a whole wave in ONE call: the stages chain on the device (survivors are
+ * compacted between them, nothing returns to the host in between).  Candidates: coords / normals float[4P], image lists as CSR
+ * (img_off int32[P+1], images).  postProcess includes setVImagesVGrids at _depth >= 1 and COptim::check at _depth >= 2
+ * (pmvsb_set_depth; both read the resident table and its depth maps).  Results stay on the device until pmvsb_evaluate_fetch:
+ * *accepted candidates with *entries image entries and *ventries visible-image entries in total; *refined = refinePatch calls
+ * (candidates that passed preProcess). */
+int pmvsb_evaluate_batch(pmvsb_ctx* ctx, int P, const float* coords, const float* normals, const int32_t* img_off, const int32_t* images, float quad,
+                         int32_t* accepted, int32_t* entries, int32_t* ventries, int32_t* refined);
+/* Results of the last pmvsb_evaluate_batch (any pointer may be NULL): verdict int32[P] (0 accepted, 1 rejected by preProcess,
+ * 2 by postProcess); for the accepted candidates, in candidate order: index (candidate number), coords / normals float[4A],
+ * scal float[4A] = (_ncc, _dscale, _ascale, _tmp), timages, _images / _grids as CSR (img_off int32[A+1], images int32[E],
+ * grids int32[2E]) and _vimages / _vgrids likewise. */
+int pmvsb_evaluate_fetch(pmvsb_ctx* ctx, int32_t* verdict, int32_t* index, float* coords, float* normals, float* scal, int32_t* timages,
+                         int32_t* img_off, int32_t* images, int32_t* grids, int32_t* vimg_off, int32_t* vimages, int32_t* vgrids);
+
 /* ---- filter stage: depth maps, visibility, gains ----------------------------------------------------------
  * The host keeps the cell bookkeeping (CPatchOrganizerS) and hands the current patch table over as arrays
  * (index = CPatch::_id after collectPatches(), source/pmvs/patchOrganizerS.cpp:207-236):

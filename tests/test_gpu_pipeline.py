@@ -158,13 +158,22 @@ def test_option_variants(name, scene, tmp_path):
     a, b = _nn(pts[:, :3], ref[:, :3], median=True), _nn(ref[:, :3], pts[:, :3], median=True)
     far = _nn(pts[:, :3], ref[:, :3])
     print("%s: patches %d vs reference %d; median cloud distance %.5f / %.5f (mean %.5f), reference spacing %.5f" % (name, len(pts), want, a, b, far, spacing))
-    # count bar: COUNT_TOL, except for the fringe-heavy "enumerated" variant, where a ~600-patch fringe region is reached or
-    # not depending on last-bit roundings of one objective value (10 647 ... 11 290 across kernel builds) and the reference
-    # binary itself writes 11 226 / 13 197 / 16 734 / 19 638 / 18 195 patches at CPU 1 / 2 / 4 / 8 / 8 for this option file
-    tol = 0.10 if name == "enumerated" else COUNT_TOL
-    assert abs(len(pts) - want) <= tol * want, (len(pts), want)
+    if name == "enumerated":
+        # The fringe-heavy variant is held to the REFERENCE'S OWN run-to-run envelope (tests/golden/pmvs_envelope.npz,
+        # make_golden_envelope.py): which fringe regions a run reaches depends on the order candidates are tried in, and the
+        # reference binary itself writes 11 226 / ~13 000-13 600 / ~14 000-16 800 patches at CPU 1 / 2 / 4 for this option file.
+        # Bars: the count lies inside that range (5 % margin), the CPU-1 cloud is covered (medians above), and every region the
+        # drop-in reconstructs is one some reference run reconstructs too (mean distance to the union of the reference clouds).
+        E = np.load(os.path.join(HERE, "golden", "pmvs_envelope.npz"))
+        lo, hi = int(E["counts"].min()), int(E["counts"].max())
+        assert 0.95 * lo <= len(pts) <= 1.05 * hi, (len(pts), lo, hi)
+        far_union = _nn(pts[:, :3], E["union"].astype(np.float32))
+        print("enumerated: reference counts %s; mean distance to the union of the reference clouds %.5f" % (list(E["counts"]), far_union))
+        assert far_union < 0.75 * spacing
+    else:
+        assert abs(len(pts) - want) <= COUNT_TOL * want, (len(pts), want)
+        assert far < 1.5 * spacing
     assert a < CLOUD_TOL * spacing and b < CLOUD_TOL * spacing, (a, b, spacing)
-    assert far < 1.5 * spacing
 
 
 def test_clusters_one_per_gpu_and_merge(scene, tmp_path):
