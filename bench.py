@@ -171,8 +171,9 @@ def make_seed_patches(scene, gpu_lib, n, seed, device):
 # --------------------------------------------------------------------------------------------------------
 # second half of BASELINE.json's metric: wall time of the whole pmvs2 run on the workload's scene
 # --------------------------------------------------------------------------------------------------------
-def pipeline_wall_time(scene, impl):
-    """Runs the drop-in binary (impl 'b200') or the reference binary built from the reference's own sources (impl
+def pipeline_wall_time(scene, impl, ranks=1):
+    """Runs the drop-in binary (impl 'b200'; ranks > 1: one pmvs2 process per GPU under torch.distributed.run, frontier shards +
+    NCCL all-gather of the accepted candidates per wave) or the reference binary built from the reference's own sources (impl
     'reference', all host threads) on the scene written to disk as PPM + txt + option file; returns a dict."""
     import subprocess
     cores = os.cpu_count() or 1
@@ -180,11 +181,24 @@ def pipeline_wall_time(scene, impl):
     exe = os.path.join(ROOT, "cmvs-pmvs_b200", "bin", "pmvs2") if impl == "b200" else os.path.join(ROOT, "oracle", "_ref", "pmvs3_ref")
     if not os.path.exists(exe):
         return {"scene": scene.name, "unavailable": os.path.relpath(exe, ROOT) + " not built"}
+    cmd = [exe, prefix, "option.txt", "PSET"]
+    env = dict(os.environ)
+    if ranks > 1:
+        port = int(os.environ.get("MASTER_PORT", "29500")) + 211
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ranks), "--master-addr", "127.0.0.1", "--master-port", str(port),
+               "--no-python"] + cmd
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID", "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "ROLE_WORLD_SIZE"):
+            env.pop(k, None)
     t0 = time.perf_counter()
-    p = subprocess.run([exe, prefix, "option.txt", "PSET"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    p = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env)
     secs = time.perf_counter() - t0
     out = {"scene": "%s %d views %dx%d level %d csize %d" % (scene.name, scene.num, scene.width, scene.height, scene.option["level"], scene.option["csize"]),
-           "binary": os.path.relpath(exe, ROOT), "wall_seconds": secs, "host_threads": cores, "returncode": p.returncode}
+           "binary": os.path.relpath(exe, ROOT), "ranks": ranks, "wall_seconds": secs, "host_threads": cores, "returncode": p.returncode}
+    if ranks > 1:
+        out["note"] = "wall_seconds includes the launcher (torch.distributed.run start-up, ~1-2 s) and the NCCL bring-up; phases_seconds.main.total is pmvs2's own clock on rank 0"
+        for l in p.stderr.splitlines():
+            if "exchange " in l and " ranks" in l:
+                out["exchange"] = l[l.index("exchange "):].strip()
     try:
         with open(prefix + "models/option.txt.pset") as f:
             out["patches"] = sum(1 for _ in f)
@@ -465,12 +479,15 @@ def main():
                                 "evals_per_patch": r["evals_per_patch"], "optimizer": "reference objective (COptim::my_f) + nm3 Nelder-Mead stand-in for nlopt BOBYQA, xtol 1e-4",
                                 "at_reference_xtol": r.get("at_reference_xtol")}
     lib.close()
-    if rank == 0 and world == 1 and not args.no_pipeline:
-        line["pipeline"] = pipeline_wall_time(scene, "b200")
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0 and not args.no_pipeline:
+        if world > 1:
+            time.sleep(1.0)     # the other ranks leave their GPUs
+        line["pipeline"] = pipeline_wall_time(scene, "b200", ranks=world)
     if rank == 0:
         print_line(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 class _StdoutToStderr:

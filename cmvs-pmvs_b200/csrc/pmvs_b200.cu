@@ -9,6 +9,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -1128,8 +1129,15 @@ int pmvsb_create(pmvsb_ctx** out, int device, int num_images, int num_target, in
   if (num_images < 1 || num_target < 1 || num_target > num_images || level < 0 || level > 5 || csize < 1 ||
       min_image_num < 2 || (wsize != 5 && wsize != 7 && wsize != 9))
     return PMVSB_EINVAL;
+  // PMVSB_TRACE_INIT=1: milliseconds spent in each CUDA start-up step (the first runtime call brings the driver and the device up)
+  const bool trace = std::getenv("PMVSB_TRACE_INIT") != nullptr;
+  const auto t_init = std::chrono::steady_clock::now();
+  auto stamp = [&](const char* what) {
+    if (trace) std::fprintf(stderr, "init %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_init).count());
+  };
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return PMVSB_ECUDA;
+  stamp("cudaGetDeviceCount");
   pmvsb_ctx* ctx = new pmvsb_ctx();
   if (const char* v = std::getenv("PMVSB_NO_ATLAS")) ctx->atlas_enabled = !(v[0] && v[0] != '0');
   if (const char* v = std::getenv("PMVSB_NO_ORDER")) ctx->order_enabled = !(v[0] && v[0] != '0');
@@ -1153,6 +1161,9 @@ int pmvsb_create(pmvsb_ctx** out, int device, int num_images, int num_target, in
     for (int j = 0; j < num_images; ++j)
       if (j != i) ctx->visdata2[i].push_back(j);
   cudaError_t e = cudaSetDevice(device);
+  stamp("cudaSetDevice");
+  if (e == cudaSuccess) e = cudaFree(nullptr);   // forces the primary context into existence here
+  stamp("primary context");
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
   ctx->stream = ctx->own_stream;
   if (e == cudaSuccess) {   // keep freed blocks in the device's stream-ordered pool (see dev_malloc)
@@ -1166,6 +1177,7 @@ int pmvsb_create(pmvsb_ctx** out, int device, int num_images, int num_target, in
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_counter, 4 * sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(ctx->d_counter, 0, 4 * sizeof(int));
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  stamp("stream, events, counters");
   if (e != cudaSuccess) { delete ctx; return PMVSB_ECUDA; }
   *out = ctx;
   return PMVSB_OK;

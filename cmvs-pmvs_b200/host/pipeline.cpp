@@ -264,8 +264,9 @@ void Pipeline::evaluate_range(std::vector<Candidate>& all, std::vector<int>& all
   int* verdict = all_verdict.data() + lo;
   // the reference's per-candidate contract -- preProcess, refinePatch, postProcess (seed.cpp:397-409, expand.cpp:225-237) -- as
   // ONE library call for the whole shard: the stages chain on the device, only the accepted candidates' records come back
-  static thread_local std::vector<float> coords, normals, acoords, anormals, ascal;
-  static thread_local std::vector<int32_t> ioff, images, v, aindex, ati, aoff, aim, agr, avoff, avim, avgr;
+  // scratch reused across waves (the pipeline thread is the only caller; the worker threads of parallel_for see the same objects)
+  static std::vector<float> coords, normals, acoords, anormals, ascal;
+  static std::vector<int32_t> ioff, images, v, aindex, ati, aoff, aim, agr, avoff, avim, avgr;
   coords.resize((size_t)4 * P); normals.resize((size_t)4 * P); ioff.resize((size_t)P + 1); v.resize(P);
   ioff[0] = 0;
   for (int k = 0; k < P; ++k) ioff[k + 1] = ioff[k] + (int32_t)cands[k].patch.images.size();
@@ -542,35 +543,14 @@ void Pipeline::seed_round() {
 }
 
 // ---------------------------------------------------------------------------------------------- expansion
-bool Pipeline::check_counts(const Patch& p) const {   // expand.cpp:258-323; true = reject
-  int full = 0, empty = 0;
-  for (size_t i = 0; i < p.images.size(); ++i) {
-    const int im = p.images[i];
-    if (tnum_ <= im) continue;
-    const ImageGrid& g = grids_[im];
-    const int ix = p.grids[i][0], iy = p.grids[i][1];
-    if (ix < 0 || g.gw <= ix || iy < 0 || g.gh <= iy) continue;
-    const size_t c = (size_t)iy * g.gw + ix;
-    if (g.occ[c] != 0) { ++full; continue; }
-    if (count_threshold1_ <= g.counts[c]) ++full; else ++empty;
-  }
-  if (depth_ <= 1) return empty < opt_.minImageNum && full != 0;
-  return empty < opt_.minImageNum - 1 && full != 0;
+bool Pipeline::check_counts(const Patch& p) const {   // expand.cpp:258-323; true = reject (host/cell_rules.hpp)
+  return pmvs::check_counts(p.images.data(), p.grids.empty() ? nullptr : &p.grids[0][0], (int)p.images.size(), tnum_, cell_views_.data(), count_threshold1_,
+                            opt_.minImageNum, depth_);
 }
 
 bool Pipeline::update_counts(const Patch& p) {   // expand.cpp:325-406; true = the new patch joins the queue
-  int empty = 0;
-  auto visit = [&](int im, int ix, int iy) {
-    ImageGrid& g = grids_[im];
-    if (ix < 0 || g.gw <= ix || iy < 0 || g.gh <= iy) return;
-    const size_t c = (size_t)iy * g.gw + ix;
-    if (!(count_threshold1_ <= g.counts[c])) ++empty;
-    ++g.counts[c];   // unsigned char, wraps like the reference's
-  };
-  for (size_t i = 0; i < p.images.size(); ++i)
-    if (p.images[i] < tnum_) visit(p.images[i], p.grids[i][0], p.grids[i][1]);
-  for (size_t i = 0; i < p.vimages.size(); ++i) visit(p.vimages[i], p.vgrids[i][0], p.vgrids[i][1]);
-  return empty != 0;
+  return pmvs::update_counts(p.images.data(), p.grids.empty() ? nullptr : &p.grids[0][0], (int)p.images.size(), p.vimages.data(),
+                             p.vgrids.empty() ? nullptr : &p.vgrids[0][0], (int)p.vimages.size(), tnum_, cell_views_.data(), count_threshold1_);
 }
 
 void Pipeline::expand_round() {

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../include/pmvs_b200.h"
+#include "cell_rules.hpp"
 
 namespace pmvs {
 
@@ -163,6 +164,7 @@ class Pipeline {
   std::vector<std::vector<float>> distances_;
   std::vector<std::vector<Feature>> features_;
   std::vector<ImageGrid> grids_;
+  std::vector<CellGridView> cell_views_;   // grids_ as the cell rules take them (host/cell_rules.hpp)
   std::vector<Patch> patches_;
   std::vector<int> table_ids_;              // table index -> patch id, for the table resident on the GPU
   std::vector<int> table_index_;            // patch id -> table index (-1: not in the table)

@@ -354,6 +354,8 @@ void Pipeline::load() {
       g.counts.assign((size_t)g.gw * g.gh, 0);
     }
   }
+  cell_views_.resize(tnum_);
+  for (int i = 0; i < tnum_; ++i) cell_views_[i] = {grids_[i].gw, grids_[i].gh, grids_[i].occ.data(), grids_[i].counts.data()};
   // CPhotoSetS::setDistances (source/image/photoSetS.cpp:195-235): baseline / mean baseline + axis divergence beyond 10 degrees
   distances_.assign(num_, std::vector<float>(num_, 0.0f));
   float avedis = 0.0f;

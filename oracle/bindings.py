@@ -485,6 +485,10 @@ class RefLib(_Common):
         n = self.lib.ref_filter_small_groups(out.ctypes.data_as(C.c_void_p), cap)
         return out[:n].copy()
 
+    def shift_patches(self, flags, t):
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        self.lib.ref_shift_patches(flags.ctypes.data_as(C.c_void_p), C.c_float(t))
+
     def filter_exact(self, cap):
         out = np.zeros(cap, np.int32)
         n = self.lib.ref_filter_exact(out.ctypes.data_as(C.c_void_p), cap)

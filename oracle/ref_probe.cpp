@@ -485,6 +485,34 @@ int ref_collect_candidates(int index, int cell, int p, int* other_image, float* 
   return (int)vcp.size();
 }
 
+// ---- expansion cell rules on the reference's own grids ----------------------------------------------------------------
+void ref_get_occupancy(int image, int* out) {
+  const auto& g = g_fm->_pos._pgrids[image];
+  for (size_t c = 0; c < g.size(); ++c) out[c] = (int)g[c].size();
+}
+void ref_get_counts(int image, unsigned char* out) {
+  const std::vector<unsigned char>& c = g_fm->_pos._counts[image];
+  std::memcpy(out, c.data(), c.size());
+}
+void ref_set_count_threshold1(int v) { g_fm->_countThreshold1 = v; }
+static void raw_patch(Patch::CPatch& p, const int* images, const int* grids, int n, const int* vimages, const int* vgrids, int nv) {
+  p._images.assign(images, images + n);
+  for (int i = 0; i < n; ++i) p._grids.push_back(TVec2<int>(grids[2 * i], grids[2 * i + 1]));
+  p._vimages.assign(vimages, vimages + nv);
+  for (int i = 0; i < nv; ++i) p._vgrids.push_back(TVec2<int>(vgrids[2 * i], vgrids[2 * i + 1]));
+}
+// CExpand::checkCounts / updateCounts on a patch made of the given lists
+int ref_check_counts_raw(const int* images, const int* grids, int n) {
+  Patch::CPatch p;
+  raw_patch(p, images, grids, n, nullptr, nullptr, 0);
+  return g_fm->_expand.checkCounts(p);
+}
+int ref_update_counts_raw(const int* images, const int* grids, int n, const int* vimages, const int* vgrids, int nv) {
+  Patch::CPatch p;
+  raw_patch(p, images, grids, n, vimages, vgrids, nv);
+  return g_fm->_expand.updateCounts(p);
+}
+
 // ---- filter-round stages on the reference's own state --------------------------------------------------------------
 // removePatch for the table patches (numbering of ref_collect_patches) with keep[k] == 0, then
 // CFilter::setDepthMapsVGridsVPGridsAddPatchV(additive); old_index[i] = former table index of new table patch i.
@@ -509,6 +537,21 @@ int ref_remove_and_rebuild(const unsigned char* keep, int additive, int* old_ind
 int ref_filter_small_groups(int* old_index, int cap) {
   g_fm->_filter.filterSmallGroups();
   return report_old_indexes(old_index, cap);
+}
+// Moves the flagged table patches a fraction t of the way towards the camera of their reference image (removePatch, shift,
+// setGrids, addPatch): they now hide what lies behind them, which gives CFilter::filterExact something to prune.
+void ref_shift_patches(const unsigned char* flags, float t) {
+  g_fm->_pos.collectPatches(0);
+  std::vector<Patch::PPatch> pp = g_fm->_pos._ppatches;
+  for (int k = 0; k < (int)pp.size(); ++k) {
+    if (!flags[k]) continue;
+    g_fm->_pos.removePatch(pp[k]);
+    const Vec4f c = g_fm->_pss._photos[pp[k]->_images[0]].OpticalCenter();
+    pp[k]->_coord = pp[k]->_coord + t * (c - pp[k]->_coord);
+    pp[k]->_coord[3] = 1.0f;
+    g_fm->_pos.setGrids(*pp[k]);
+    g_fm->_pos.addPatch(pp[k]);
+  }
 }
 // CFilter::filterExact on the current state (depth maps of the last rebuild); survivors as former table indexes
 int ref_filter_exact(int* old_index, int cap) {

@@ -75,6 +75,45 @@ def main():
     # the final table has already been through the filter at quad 2.5; tighter thresholds exercise filterQuad's fit
     out["fnb_quads"] = np.array([0.03, 0.1, 0.5], np.float32)
     out["fnb_reject_q"] = np.array([[ref.filter_neighbor(k, float(q))[0] for k in range(P)] for q in out["fnb_quads"]], np.uint8)
+    # ---- expansion cell rules (CExpand::checkCounts / updateCounts) on the reference's own _pgrids, with pseudo-random trial
+    # counters: candidates = real patches' lists with their cells jittered (so that empty, counted-out and occupied cells all occur)
+    import ctypes as C
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    tn = scene.num
+    dims = [ref.grid_dims(i) for i in range(tn)]
+    occ, cnt0 = [], []
+    for i in range(tn):
+        o_ = np.zeros(dims[i][0] * dims[i][1], np.int32); ref.lib.ref_get_occupancy(i, vp(o_)); occ.append(o_)
+        c_ = rng.integers(0, 6, dims[i][0] * dims[i][1]).astype(np.uint8); c_[rng.random(len(c_)) < 0.002] = 255; cnt0.append(c_)
+        ref.lib.ref_set_counts(i, vp(c_))
+    out["cr_occ"] = np.concatenate(occ); out["cr_counts0"] = np.concatenate(cnt0)
+    NC = 3000
+    coff, cim, cgr, cvoff, cvim, cvgr = [0], [], [], [0], [], []
+    for k in rng.integers(0, P, NC):
+        a, b = st["img_off"][k], st["img_off"][k + 1]
+        keep = rng.random(b - a) < 0.8
+        im = st["images"][a:b][keep]; gr = st["grids"][a:b][keep] + rng.integers(-2, 3, (int(keep.sum()), 2))
+        cim.append(im); cgr.append(gr); coff.append(coff[-1] + len(im))
+        a, b = st["vimg_off"][k], st["vimg_off"][k + 1]
+        cvim.append(st["vimages"][a:b]); cvgr.append(st["vgrids"][a:b] + rng.integers(-1, 2, (b - a, 2))); cvoff.append(cvoff[-1] + b - a)
+    out["cr_off"] = np.array(coff, np.int32); out["cr_images"] = np.concatenate(cim).astype(np.int32); out["cr_grids"] = np.concatenate(cgr).astype(np.int32)
+    out["cr_voff"] = np.array(cvoff, np.int32); out["cr_vimages"] = np.concatenate(cvim).astype(np.int32); out["cr_vgrids"] = np.concatenate(cvgr).astype(np.int32)
+    for depth, thr1 in ((1, 4), (2, 2)):
+        ref.set_depth(depth); ref.lib.ref_set_count_threshold1(thr1)
+        v = [ref.lib.ref_check_counts_raw(vp(np.ascontiguousarray(out["cr_images"][coff[k]:coff[k + 1]])), vp(np.ascontiguousarray(out["cr_grids"][coff[k]:coff[k + 1]])),
+                                          int(coff[k + 1] - coff[k])) for k in range(NC)]
+        out["cr_check_d%d" % depth] = np.array(v, np.uint8)
+    rq = [ref.lib.ref_update_counts_raw(vp(np.ascontiguousarray(out["cr_images"][coff[k]:coff[k + 1]])), vp(np.ascontiguousarray(out["cr_grids"][coff[k]:coff[k + 1]])),
+                                        int(coff[k + 1] - coff[k]), vp(np.ascontiguousarray(out["cr_vimages"][cvoff[k]:cvoff[k + 1]])),
+                                        vp(np.ascontiguousarray(out["cr_vgrids"][cvoff[k]:cvoff[k + 1]])), int(cvoff[k + 1] - cvoff[k])) for k in range(NC)]
+    out["cr_requeue"] = np.array(rq, np.uint8)
+    cnt1 = []
+    for i in range(tn):
+        c_ = np.zeros(dims[i][0] * dims[i][1], np.uint8); ref.lib.ref_get_counts(i, vp(c_)); cnt1.append(c_)
+    out["cr_counts1"] = np.concatenate(cnt1)
+    print("cell rules: checkCounts rejects", out["cr_check_d1"].mean(), out["cr_check_d2"].mean(), "updateCounts requeues", out["cr_requeue"].mean(),
+          "counters changed", int((out["cr_counts1"] != out["cr_counts0"]).sum()))
+    ref.set_depth(int(out["depth_flag"]))
     # ---- filter-round stages that change the table (run last: they mutate the reference's state) -------------------------
     # (1) a fragmented table: 55 % of the patches removed in blobs, setDepthMapsVGridsVPGridsAddPatchV(1), then filterSmallGroups
     cell = np.floor(st["coords"][:, :3] * 4.0).astype(np.int64)
@@ -85,11 +124,15 @@ def main():
     frag = ref.state()
     out["frag_vimg_off"] = frag["vimg_off"]; out["frag_vimages"] = frag["vimages"]; out["frag_vgrids"] = frag["vgrids"]
     out["frag_groups_survivors"] = ref.filter_small_groups(P)
-    # (2) on what is left: everything rebuilt from empty _vimages (additive 0), then filterExact
+    # (2) on what is left: a sixth of the patches moved 3 % towards their reference camera (they now occlude their neighbours in the
+    # other images), everything rebuilt from empty _vimages (additive 0), then filterExact.  The GPU side starts from the state saved here.
     left = ref.state()
-    out["exact_perm"] = ref.remove_and_rebuild(np.ones(len(left["ncc"]), np.uint8), additive=0)
+    nl = len(left["ncc"])
+    ref.shift_patches((np.arange(nl) % 6 == 0).astype(np.uint8), 0.03)
+    ref.remove_and_rebuild(np.ones(nl, np.uint8), additive=0)
     before = ref.state()
-    out["exact_vimg_off"] = before["vimg_off"]; out["exact_vimages"] = before["vimages"]
+    for k_ in ("coords", "normals", "ncc", "dscale", "img_off", "images", "grids", "vimg_off", "vimages", "vgrids", "timages"):
+        out["exact_st_" + k_] = before[k_]
     out["exact_survivors"] = ref.filter_exact(len(before["ncc"]))
     after = ref.state()
     out["exact_img_off"] = after["img_off"]; out["exact_images"] = after["images"]; out["exact_grids"] = after["grids"]

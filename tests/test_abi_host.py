@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def test_header_symbols_exported(pkg):
@@ -201,3 +202,39 @@ def test_reference_arm_line_contract():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=600)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_cell_rules_match_the_reference():
+    """CExpand::checkCounts / updateCounts: the code pmvs2 runs (cmvs-pmvs_b200/host/cell_rules.hpp, through lib/libpmvs_host.so)
+    against the reference's own answers on its own _pgrids with pseudo-random trial counters (tests/golden/pmvs_state.npz):
+    3 000 candidates, both depth regimes, then updateCounts applied in order -- return values and every counter equal."""
+    import ctypes as C
+    import __graft_entry__ as g
+    g.build()
+    lib = C.CDLL(os.path.join(ROOT, "cmvs-pmvs_b200", "lib", "libpmvs_host.so"))
+    S = np.load(os.path.join(HERE, "golden", "pmvs_state.npz"))
+    from scene_util import small_scene
+    scene = small_scene()
+    assert scene.sha256() == bytes(S["scene_sha256"]).hex()
+    tn = scene.num
+    lvl, cs = scene.option["level"], scene.option["csize"]
+    w, h = scene.width >> lvl, scene.height >> lvl
+    gw = np.full(tn, (w + cs - 1) // cs, np.int32); gh = np.full(tn, (h + cs - 1) // cs, np.int32)
+    base = np.concatenate([[0], np.cumsum(gw * gh)]).astype(np.int32)
+    assert base[-1] == len(S["cr_occ"])
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    occ = np.ascontiguousarray(S["cr_occ"], np.int32)
+    off = np.ascontiguousarray(S["cr_off"], np.int32); im = np.ascontiguousarray(S["cr_images"], np.int32); gr = np.ascontiguousarray(S["cr_grids"], np.int32)
+    voff = np.ascontiguousarray(S["cr_voff"], np.int32); vim = np.ascontiguousarray(S["cr_vimages"], np.int32); vgr = np.ascontiguousarray(S["cr_vgrids"], np.int32)
+    P = len(off) - 1
+    for depth, thr1 in ((1, 4), (2, 2)):
+        counts = np.ascontiguousarray(S["cr_counts0"], np.uint8).copy()
+        v = np.zeros(P, np.uint8)
+        lib.pmvsh_check_counts_batch(tn, vp(gw), vp(gh), vp(base), vp(occ), vp(counts), P, vp(off), vp(im), vp(gr), thr1, 3, depth, vp(v))
+        assert np.array_equal(v, S["cr_check_d%d" % depth]), depth
+        assert 0.01 < v.mean() < 0.99      # both verdicts occur
+    counts = np.ascontiguousarray(S["cr_counts0"], np.uint8).copy()
+    rq = np.zeros(P, np.uint8)
+    lib.pmvsh_update_counts_batch(tn, vp(gw), vp(gh), vp(base), vp(occ), vp(counts), P, vp(off), vp(im), vp(gr), vp(voff), vp(vim), vp(vgr), 2, vp(rq))
+    assert np.array_equal(rq, S["cr_requeue"])
+    assert np.array_equal(counts, S["cr_counts1"]) and (counts != S["cr_counts0"]).sum() > 1000

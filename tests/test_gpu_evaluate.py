@@ -76,7 +76,7 @@ def test_depth0_equals_the_stages_called_one_by_one(gpu, scene, wave):
     off, images = _csr(pb, n0)
     out = gpu.evaluate_batch(pb["coords"], pb["normals"], off, images)
     _compare(out, verdict, refined, rec)
-    assert (verdict == 0).sum() > 50 and (verdict == 1).sum() > 20 and (verdict == 2).sum() > 5
+    assert (verdict == 0).sum() > 50 and (verdict == 1).sum() > 20 and (verdict == 2).sum() >= 1   # all three outcomes occur
     assert len(out["vimages"]) == 0
     # an empty wave is a no-op
     e = gpu.evaluate_batch(np.zeros((0, 4), np.float32), np.zeros((0, 4), np.float32), np.zeros(1, np.int32), np.zeros(0, np.int32))

@@ -215,3 +215,19 @@ def test_clusters_one_per_gpu_and_merge(scene, tmp_path):
     first = np.loadtxt(prefix + "models/option-0000.pset", dtype=np.float32).reshape(-1, 6)
     assert np.array_equal(merged[: len(first)], first)
     assert "cluster 1 ->" in p.stderr and "merged %d patches of 2 clusters" % total in p.stderr
+
+
+def test_large256_tool_at_reduced_size(tmp_path):
+    """tools/large256.py (BASELINE configs[3]: disjoint groups -> ske.dat -> genOption -> one pmvs2 per cluster per GPU -> merged
+    models) end to end at a size that fits the test budget: 3 clusters x 8 views of 400x300."""
+    import json
+    import sys
+    out = str(tmp_path / "large.json")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "large256.py"), "--clusters", "3", "--views", "8", "--width", "400", "--height", "300",
+                        "--gpus", "1", "--prefix", str(tmp_path / "scene"), "--out", out], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    r = json.load(open(out))
+    run = r["runs"][0]
+    counts = [run["patches_per_cluster"][str(c)] for c in range(3)]
+    assert all(c > 500 for c in counts), counts
+    assert run["merged"] == sum(counts)

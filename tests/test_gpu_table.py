@@ -63,17 +63,24 @@ def test_removal_rebuild_small_groups_and_exact_follow_the_reference(gpu, S, sta
     assert np.array_equal(perm[keep == 1], S["frag_groups_survivors"])
     assert 0 < (keep == 0).sum() < len(keep)
     perm2 = gpu.store_rebuild(keep, additive=1)
-    # (3) everything from empty _vimages, then filterExact
-    perm3 = gpu.store_rebuild(None, additive=0)
-    assert np.array_equal(perm3, S["exact_perm"])
-    d = gpu.store_download()
-    assert _csr_equal(d["vimg_off"], d["vimages"], S["exact_vimg_off"], S["exact_vimages"])
+    _upload(gpu, st)
+
+
+def test_filter_exact_follows_the_reference(gpu, S, state):
+    """CFilter::filterExact on a table with occluders (a sixth of the patches moved towards their cameras by the golden generator):
+    the visibility re-test prunes image lists, patches left with too few images go, setRefImage + setGrids for the rest."""
+    st, o = state
+    ex = {k: S["exact_st_" + k] for k in STORE_KEYS}
+    gpu.store_upload(ex)
+    gpu.build_depth_maps()
     keep = gpu.filter_exact_apply_store()
-    assert np.array_equal(np.where(keep == 1)[0], S["exact_survivors"])
-    gpu.store_rebuild(keep, additive=1)
+    assert 0 < (keep == 0).sum() < len(keep)
+    perm = gpu.store_rebuild(keep, additive=2)          # renumbering only (collectPatches), as ref.state() does
+    assert np.array_equal(perm, S["exact_survivors"])
     d = gpu.store_download()
     assert _csr_equal(d["img_off"], d["images"], S["exact_img_off"], S["exact_images"]) and np.array_equal(d["grids"], S["exact_grids"])
     assert np.array_equal(d["timages"], S["exact_timages"])
+    assert d["img_off"][-1] < ex["img_off"][-1]          # entries were really pruned
     _upload(gpu, st)
 
 
