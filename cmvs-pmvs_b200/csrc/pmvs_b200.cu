@@ -684,7 +684,8 @@ struct pmvsb_ctx {
     int P = 0, A = 0, E = 0, VE = 0, refined = 0;
     DVec<int32_t> verdict, index, timages, img_off, images, grids, vimg_off, vimages, vgrids;
     DVec<float> coords, normals, scal;   // scal = (ncc, dscale, ascale, tmp) per accepted candidate
-  } ev;
+  } ev, ev_all;                           // ev_all: the second set pmvsb_evaluate_allgather unpacks the whole wave into
+  double exchanged_bytes = 0.0;
   std::vector<int32_t> bimages;
   int32_t* d_bimages = nullptr;
   // filter-stage patch table
@@ -3222,6 +3223,121 @@ int pmvsb_allgather(pmvsb_ctx* ctx, const void* send, size_t bytes, void* recv) 
   CK(cudaStreamSynchronize(ctx->stream));
   return PMVSB_OK;
 }
+
+
+// ---- the wave exchange of a multi-GPU run, device to device ----------------------------------------------------
+// Each rank has evaluated a contiguous shard of the wave (pmvsb_evaluate_batch); its results are still on the device.  One packed
+// message per rank -- verdicts of the shard, then the ACCEPTED candidates' records with their lists at their real lengths --
+// goes through ONE ncclAllGather straight from device memory (NVLink / NVSwitch between the GPUs, no host staging), and is
+// unpacked into the result arrays of the whole wave, in rank order = candidate order.  pmvsb_evaluate_fetch then returns the
+// wave as if this rank had evaluated all of it.
+__global__ void k_offsets_to_len(int n, const int32_t* __restrict__ off, int32_t* __restrict__ len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) len[i] = off[i + 1] - off[i];
+}
+__global__ void k_add_scalar(int n, int32_t* __restrict__ a, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += v;
+}
+
+int pmvsb_evaluate_allgather(pmvsb_ctx* ctx, int shard_lo, int total_candidates) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  pmvsb_ctx::EvalOut& ev = ctx->ev;
+  if (shard_lo < 0 || total_candidates < shard_lo + ev.P) return fail(ctx, PMVSB_EINVAL, "evaluate_allgather: shard outside the wave");
+  if (ctx->comm_world == 1) return PMVSB_OK;
+  if (!ctx->comm) return fail(ctx, PMVSB_ESTATE, "evaluate_allgather: call pmvsb_comm_init first");
+  NcclApi* api = nccl_api();
+  cudaStream_t q = ctx->stream;
+  const int W = ctx->comm_world;
+  // sizes of every rank's message
+  DevBuf<int32_t> dmeta;
+  CK(dmeta.alloc((size_t)4 * (W + 1)));
+  const int32_t mine[4] = {ev.P, ev.A, ev.E, ev.VE};
+  CK(cudaMemcpyAsync(dmeta.p, mine, sizeof(mine), cudaMemcpyHostToDevice, q));
+  ncclResult_t nr = api->AllGather(dmeta.p, dmeta.p + 4, 4, ncclInt32, ctx->comm, q);
+  if (nr != ncclSuccess) return fail(ctx, PMVSB_ECUDA, std::string("ncclAllGather: ") + api->GetErrorString(nr));
+  std::vector<int32_t> meta((size_t)4 * W);
+  CK(cudaMemcpyAsync(meta.data(), dmeta.p + 4, sizeof(int32_t) * meta.size(), cudaMemcpyDeviceToHost, q));
+  CK(cudaStreamSynchronize(q));
+  auto words = [](int P, int A, int E, int VE) { return (size_t)P + (size_t)4 * A + (size_t)12 * A + (size_t)3 * E + (size_t)3 * VE; };
+  size_t longest = 0;
+  long long tP = 0, tA = 0, tE = 0, tVE = 0;
+  for (int k = 0; k < W; ++k) {
+    longest = std::max(longest, words(meta[4 * k], meta[4 * k + 1], meta[4 * k + 2], meta[4 * k + 3]));
+    tP += meta[4 * k]; tA += meta[4 * k + 1]; tE += meta[4 * k + 2]; tVE += meta[4 * k + 3];
+  }
+  if (tP != total_candidates) return fail(ctx, PMVSB_EINVAL, "evaluate_allgather: the shards do not add up to the wave");
+  longest = (longest + 3) & ~(size_t)3;
+  const size_t need = sizeof(int32_t) * longest * ((size_t)W + 1);
+  if (need > ctx->comm_cap) {
+    CK(cudaStreamSynchronize(q));
+    cudaFree(ctx->comm_buf); ctx->comm_buf = nullptr; ctx->comm_cap = 0;
+    CK(cudaMalloc((void**)&ctx->comm_buf, need + need / 2));
+    ctx->comm_cap = need + need / 2;
+  }
+  int32_t* send = reinterpret_cast<int32_t*>(ctx->comm_buf);
+  int32_t* recv = send + longest;
+  // ---- pack: [verdict P][index A][timages A][ilen A][vlen A][coords 4A][normals 4A][scal 4A][images E][grids 2E][vimages VE][vgrids 2VE]
+  {
+    const int P = ev.P, A = ev.A, E = ev.E, VE = ev.VE;
+    int32_t* w = send;
+    auto put = [&](const void* src, size_t n) { cudaError_t e = n ? cudaMemcpyAsync(w, src, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, q) : cudaSuccess; w += n; return e; };
+    CK(put(ev.verdict.p, (size_t)P));
+    if (A > 0) {
+      k_add_scalar<<<(A + 255) / 256, 256, 0, q>>>(A, ev.index.p, shard_lo);
+      CK(put(ev.index.p, (size_t)A)); CK(put(ev.timages.p, (size_t)A));
+      k_offsets_to_len<<<(A + 255) / 256, 256, 0, q>>>(A, ev.img_off.p, w);
+      k_offsets_to_len<<<(A + 255) / 256, 256, 0, q>>>(A, ev.vimg_off.p, w + A);
+      ctx->launches += 3;
+      w += 2 * (size_t)A;
+      CK(put(ev.coords.p, (size_t)4 * A)); CK(put(ev.normals.p, (size_t)4 * A)); CK(put(ev.scal.p, (size_t)4 * A));
+      CK(put(ev.images.p, (size_t)E)); CK(put(ev.grids.p, (size_t)2 * E)); CK(put(ev.vimages.p, (size_t)VE)); CK(put(ev.vgrids.p, (size_t)2 * VE));
+    }
+  }
+  nr = api->AllGather(send, recv, longest, ncclInt32, ctx->comm, q);
+  if (nr != ncclSuccess) return fail(ctx, PMVSB_ECUDA, std::string("ncclAllGather: ") + api->GetErrorString(nr));
+  // ---- unpack into the arrays of the whole wave
+  const size_t A1 = (size_t)std::max<long long>(tA, 1), E1 = (size_t)std::max<long long>(tE, 1), V1 = (size_t)std::max<long long>(tVE, 1);
+  pmvsb_ctx::EvalOut& o = ctx->ev_all;
+  if ((r = dvec_reserve(ctx, o.verdict, (size_t)std::max<long long>(tP, 1))) || (r = dvec_reserve(ctx, o.index, A1)) || (r = dvec_reserve(ctx, o.timages, A1)) ||
+      (r = dvec_reserve(ctx, o.img_off, A1 + 1)) || (r = dvec_reserve(ctx, o.vimg_off, A1 + 1)) || (r = dvec_reserve(ctx, o.coords, 4 * A1)) ||
+      (r = dvec_reserve(ctx, o.normals, 4 * A1)) || (r = dvec_reserve(ctx, o.scal, 4 * A1)) || (r = dvec_reserve(ctx, o.images, E1)) ||
+      (r = dvec_reserve(ctx, o.grids, 2 * E1)) || (r = dvec_reserve(ctx, o.vimages, V1)) || (r = dvec_reserve(ctx, o.vgrids, 2 * V1)))
+    return r;
+  size_t aP = 0, aA = 0, aE = 0, aV = 0;
+  for (int k = 0; k < W; ++k) {
+    const int P = meta[4 * k], A = meta[4 * k + 1], E = meta[4 * k + 2], VE = meta[4 * k + 3];
+    const int32_t* w = recv + (size_t)k * longest;
+    auto get = [&](void* dst, size_t n) { cudaError_t e = n ? cudaMemcpyAsync(dst, w, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, q) : cudaSuccess; w += n; return e; };
+    CK(get(o.verdict.p + aP, (size_t)P));
+    CK(get(o.index.p + aA, (size_t)A)); CK(get(o.timages.p + aA, (size_t)A));
+    CK(get(o.img_off.p + aA, (size_t)A)); CK(get(o.vimg_off.p + aA, (size_t)A));     // lengths for now
+    CK(get(o.coords.p + 4 * aA, (size_t)4 * A)); CK(get(o.normals.p + 4 * aA, (size_t)4 * A)); CK(get(o.scal.p + 4 * aA, (size_t)4 * A));
+    CK(get(o.images.p + aE, (size_t)E)); CK(get(o.grids.p + 2 * aE, (size_t)2 * E)); CK(get(o.vimages.p + aV, (size_t)VE)); CK(get(o.vgrids.p + 2 * aV, (size_t)2 * VE));
+    aP += P; aA += A; aE += E; aV += VE;
+  }
+  CK(cudaMemsetAsync(o.img_off.p + tA, 0, sizeof(int32_t), q));
+  CK(cudaMemsetAsync(o.vimg_off.p + tA, 0, sizeof(int32_t), q));
+  if ((r = device_scan(ctx, o.img_off.p, (int)tA + 1))) return r;
+  if ((r = device_scan(ctx, o.vimg_off.p, (int)tA + 1))) return r;
+  CK(cudaStreamSynchronize(q));
+  o.P = (int)tP; o.A = (int)tA; o.E = (int)tE; o.VE = (int)tVE; o.refined = ev.refined;
+  std::swap(ctx->ev, ctx->ev_all);
+  ctx->exchanged_bytes += (double)sizeof(int32_t) * longest * W;
+  return PMVSB_OK;
+}
+
+int pmvsb_evaluate_counts(pmvsb_ctx* ctx, int32_t* candidates, int32_t* accepted, int32_t* entries, int32_t* ventries) {
+  if (!ctx) return PMVSB_EINVAL;
+  if (candidates) *candidates = ctx->ev.P;
+  if (accepted) *accepted = ctx->ev.A;
+  if (entries) *entries = ctx->ev.E;
+  if (ventries) *ventries = ctx->ev.VE;
+  return PMVSB_OK;
+}
+
+double pmvsb_exchanged_bytes(const pmvsb_ctx* ctx) { return ctx ? ctx->exchanged_bytes : 0.0; }
 
 int pmvsb_sync(pmvsb_ctx* ctx) {
   if (!ctx) return PMVSB_EINVAL;

@@ -257,9 +257,9 @@ void Pipeline::append_table(const std::vector<int>& ids) {
 }
 
 // ---------------------------------------------------------------------------------------------- evaluate a wave
-void Pipeline::evaluate_range(std::vector<Candidate>& all, std::vector<int>& all_verdict, int lo, int hi) {
+void Pipeline::evaluate_range(std::vector<Candidate>& all, std::vector<int>& all_verdict, int lo, int hi, bool gather) {
   const int P = hi - lo;
-  if (P <= 0) return;
+  if (P <= 0 && !gather) return;
   Candidate* cands = all.data() + lo;      // this rank's shard of the wave
   int* verdict = all_verdict.data() + lo;
   // the reference's per-candidate contract -- preProcess, refinePatch, postProcess (seed.cpp:397-409, expand.cpp:225-237) -- as
@@ -281,12 +281,21 @@ void Pipeline::evaluate_range(std::vector<Candidate>& all, std::vector<int>& all
   int32_t A = 0, E = 0, VE = 0, refined = 0;
   { Tick tk(this, "gpu.evaluate");
     if (pmvsb_evaluate_batch(gpu_, P, coords.data(), normals.data(), ioff.data(), images.data(), opt_.quad, &A, &E, &VE, &refined)) die("evaluate_batch"); }
+  int nv = P;   // verdicts that come back
+  if (gather) {
+    // multi-GPU: every rank's accepted records all-gathered device to device (NCCL); from here on the whole wave is local
+    Tick tk(this, "gpu.allgather_wave");
+    if (pmvsb_evaluate_allgather(gpu_, lo, (int)all.size())) die("evaluate_allgather");
+    if (pmvsb_evaluate_counts(gpu_, &nv, &A, &E, &VE)) die("evaluate_counts");
+    cands = all.data(); verdict = all_verdict.data();
+    v.resize(nv);
+  }
   aindex.resize(std::max(A, 1)); acoords.resize((size_t)4 * std::max(A, 1)); anormals.resize((size_t)4 * std::max(A, 1)); ascal.resize((size_t)4 * std::max(A, 1));
   ati.resize(std::max(A, 1)); aoff.resize((size_t)A + 1); aim.resize(std::max(E, 1)); agr.resize((size_t)2 * std::max(E, 1)); avoff.resize((size_t)A + 1);
   avim.resize(std::max(VE, 1)); avgr.resize((size_t)2 * std::max(VE, 1));
   if (pmvsb_evaluate_fetch(gpu_, v.data(), aindex.data(), acoords.data(), anormals.data(), ascal.data(), ati.data(), aoff.data(), aim.data(), agr.data(),
                            avoff.data(), avim.data(), avgr.data())) die("evaluate_fetch");
-  for (int k = 0; k < P; ++k) verdict[k] = v[k];
+  for (int k = 0; k < nv; ++k) verdict[k] = v[k];
   parallel_for(A, threads_, [&](int j) {
     Patch& p = cands[aindex[j]].patch;
     for (int c = 0; c < 4; ++c) { p.coord[c] = acoords[4 * j + c]; p.normal[c] = anormals[4 * j + c]; }
@@ -311,8 +320,9 @@ void Pipeline::evaluate(std::vector<Candidate>& cands, std::vector<int>& verdict
   if (P == 0) return;
   int lo = 0, hi = P;
   Dist::shard(P, dist_.world, dist_.rank, lo, hi);
-  evaluate_range(cands, verdict, lo, hi);
-  if (dist_.world > 1) exchange_results(cands, verdict);
+  const bool nccl = dist_.world > 1 && !dist_.tcp_exchange;
+  evaluate_range(cands, verdict, lo, hi, nccl);
+  if (dist_.world > 1 && !nccl) exchange_results(cands, verdict);   // PMVSB_EXCHANGE=tcp: host-side exchange over the rendezvous sockets
 }
 
 // One message per rank and wave: the verdicts of its shard, then ONLY the accepted candidates' records (header, the
@@ -832,6 +842,7 @@ void Pipeline::write(const std::string& base, bool ply, bool patch, bool pset) {
   std::cerr << "wrote " << P << " patches to " << base << ".*" << std::endl;
   }
   for (const auto& kv : seconds_) std::cerr << "time " << kv.first << ' ' << kv.second << " s" << std::endl;
+  if (dist_.world > 1 && !dist_.tcp_exchange) exchanged_bytes_ = pmvsb_exchanged_bytes(gpu_);
   if (dist_.world > 1) std::cerr << "exchange " << dist_.world << " ranks, " << exchanged_bytes_ / 1.0e6 << " MB all-gathered over " << (dist_.tcp_exchange ? "tcp" : "nccl") << std::endl;
 }
 

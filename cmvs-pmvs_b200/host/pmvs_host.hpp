@@ -144,7 +144,7 @@ class Pipeline {
   struct Candidate { Patch patch; int parent = -1; int dir = -1; int cell = -1; int feature = -1; int order = 0; };
   // pre -> refine -> post (+ vimages at depth >= 1) for a batch; verdict[i] = 0 accepted, 1 failed in preProcess, 2 in postProcess
   void evaluate(std::vector<Candidate>& cands, std::vector<int>& verdict);
-  void evaluate_range(std::vector<Candidate>& cands, std::vector<int>& verdict, int lo, int hi);
+  void evaluate_range(std::vector<Candidate>& cands, std::vector<int>& verdict, int lo, int hi, bool gather);
   void exchange_results(std::vector<Candidate>& cands, std::vector<int>& verdict);
   void die(const std::string& where) const;
 

@@ -297,13 +297,19 @@ void Pipeline::load() {
   { Tick tk2(this, "load.wait_for_files"); reader.join(); }
   if (created != 0)
     fatal("pmvs-b200: cannot create a GPU context (CUDA device required; there is no CPU fallback) or bad options");
-  if (dist_.world > 1 && !dist_.tcp_exchange) {   // NCCL communicator over the GPUs of this run
-    Tick tk2(this, "load.nccl_init");
-    uint8_t id[128] = {0};
-    if (dist_.rank == 0 && pmvsb_comm_unique_id(gpu_, id)) die("comm_unique_id");
-    dist_.broadcast_from_root(id, sizeof(id));
-    if (pmvsb_comm_init(gpu_, dist_.rank, dist_.world, id)) die("comm_init");
-  }
+  // NCCL communicator over the GPUs of this run: brought up on its own thread while the images go to the GPU (ncclCommInitRank
+  // takes 0.5 - 1.5 s on a warm box); joined at the end of load()
+  std::thread nccl_init;
+  double nccl_seconds = 0.0;   // written by the thread, read after the join
+  const auto t_nccl = std::chrono::steady_clock::now();
+  if (dist_.world > 1 && !dist_.tcp_exchange)
+    nccl_init = std::thread([&]() {
+      uint8_t id[128] = {0};
+      if (dist_.rank == 0 && pmvsb_comm_unique_id(gpu_, id)) die("comm_unique_id");
+      dist_.broadcast_from_root(id, sizeof(id));
+      if (pmvsb_comm_init(gpu_, dist_.rank, dist_.world, id)) die("comm_init");
+      nccl_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_nccl).count();
+    });
   cams_.resize(num_);
   lw_.resize(num_); lh_.resize(num_);
   std::cerr << "Reading images: " << std::flush;
@@ -382,6 +388,10 @@ void Pipeline::load() {
       }
   }
   detect_features();
+  if (nccl_init.joinable()) {
+    { Tick tk2(this, "load.wait_for_nccl"); nccl_init.join(); }
+    seconds_["load.nccl_init(background)"] += nccl_seconds;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- features

@@ -317,6 +317,15 @@ int pmvsb_comm_init(pmvsb_ctx* ctx, int rank, int world, const uint8_t* id128);
 /* host buffers: send = bytes, recv = world * bytes in rank order; identity copy when no communicator (world = 1) */
 int pmvsb_allgather(pmvsb_ctx* ctx, const void* send, size_t bytes, void* recv);
 
+/* The wave exchange, device to device: after pmvsb_evaluate_batch on this rank's contiguous shard [shard_lo, shard_lo + P) of a
+ * wave of total_candidates, every rank calls this; the accepted candidates' records of all ranks (and all verdicts) are
+ * all-gathered by ONE ncclAllGather straight from device memory and pmvsb_evaluate_fetch then returns the WHOLE wave, `index`
+ * being wave-wide candidate numbers.  No-op without a communicator of more than one rank. */
+int pmvsb_evaluate_allgather(pmvsb_ctx* ctx, int shard_lo, int total_candidates);
+/* sizes of what pmvsb_evaluate_fetch will return (after pmvsb_evaluate_batch or pmvsb_evaluate_allgather) */
+int pmvsb_evaluate_counts(pmvsb_ctx* ctx, int32_t* candidates, int32_t* accepted, int32_t* entries, int32_t* ventries);
+double pmvsb_exchanged_bytes(const pmvsb_ctx* ctx);   /* bytes received through pmvsb_evaluate_allgather so far */
+
 int pmvsb_sync(pmvsb_ctx* ctx);
 /* the CUDA stream (cudaStream_t) the context launches on, for event timing by the caller */
 void* pmvsb_stream(pmvsb_ctx* ctx);
