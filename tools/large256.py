@@ -23,6 +23,27 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as g
 
 
+def render_clusters(clusters, V, width, height, prefix, device):
+    """renders the groups `clusters` (each its own relief object, seed 3 + c) and writes their images and cameras; returns the camera centres"""
+    synth = g.load_package().synth
+    centres = {}
+    for c in clusters:
+        scene = synth.dtu_scene(views=V, width=width, height=height, seed=3 + c)
+        synth.render(scene, device=device, rows_per_chunk=200)
+        for i, im in enumerate(scene.images):
+            gid = c * V + i
+            with open(prefix + "visualize/%08d.ppm" % gid, "wb") as f:
+                f.write(b"P6\n%d %d\n255\n" % (scene.width, scene.height))
+                f.write(np.ascontiguousarray(im).tobytes())
+            with open(prefix + "txt/%08d.txt" % gid, "w") as f:
+                f.write("CONTOUR\n")
+                for r in range(3):
+                    f.write(" ".join("%.9g" % float(v) for v in scene.P[i, r]) + "\n")
+        centres[c] = np.asarray(scene.C)[:, :3]
+        scene.images = None
+    return centres
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--clusters", type=int, default=8)
@@ -49,20 +70,15 @@ def main():
            "clusters": K, "views_per_cluster": V, "size": [a.width, a.height], "host_threads": cpu, "visible_gpus": ngpu, "runs": []}
     t0 = time.time()
     centres = {}
-    for c in only:
-        scene = synth.dtu_scene(views=V, width=a.width, height=a.height, seed=3 + c)
-        synth.render(scene, device="cuda:%d" % (c % ngpu) if ngpu else "cpu", rows_per_chunk=200)
-        for i, im in enumerate(scene.images):
-            gid = c * V + i
-            with open(prefix + "visualize/%08d.ppm" % gid, "wb") as f:
-                f.write(b"P6\n%d %d\n255\n" % (scene.width, scene.height))
-                f.write(np.ascontiguousarray(im).tobytes())
-            with open(prefix + "txt/%08d.txt" % gid, "w") as f:
-                f.write("CONTOUR\n")
-                for r in range(3):
-                    f.write(" ".join("%.9g" % float(v) for v in scene.P[i, r]) + "\n")
-        centres[c] = np.asarray(scene.C)[:, :3]
-        scene.images = None
+    workers = max(1, min(ngpu, len(only)))
+    if workers > 1:      # one rendering process per GPU, each takes every `workers`-th cluster
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(workers) as pool:
+            for part in pool.starmap(render_clusters, [(only[w::workers], V, a.width, a.height, prefix, "cuda:%d" % w) for w in range(workers)]):
+                centres.update(part)
+    else:
+        centres.update(render_clusters(only, V, a.width, a.height, prefix, "cuda:0" if ngpu else "cpu"))
     res["generate_seconds"] = time.time() - t0
     n = K * V
     with open(prefix + "vis.dat", "w") as f:        # an image sees the 12 nearest cameras of its own group
