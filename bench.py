@@ -282,7 +282,7 @@ def reference_rate(scene, patches, seconds, steps=1, warmup=0, full=None, ref_xt
         lib.set_xtol_floor(0.0)
         m = int(max(256, min(len(coords), rate * ref_xtol_seconds / 1.6)))
         r2 = lib.refine_batch(coords[:m], normals[:m], images[:m], dsc[:m], threads=cores)
-        lib.set_xtol_floor(1.0e-4)
+        lib.set_xtol_floor(1.0e-3)
         extra["at_reference_xtol"] = {"value": m / max(r2["seconds"], 1e-9), "unit": UNIT, "xtol": 1.0e-7, "evals_per_patch": float(r2["evals"].mean()),
                                       "ok_fraction": float(r2["ok"].mean()), "sample": "%d patches" % m,
                                       "note": "Nelder-Mead stand-in run down to the reference's xtol_rel 1e-7 (floor 0): the f32 objective is flat below ~1e-5, "
@@ -301,7 +301,7 @@ def main():
     config = {"workload": "patch-refinement microbench (BASELINE configs[4]) on the DTU-shaped synthetic scene (configs[2]): "
                           "%d views %dx%d, level 1 csize 2 wsize 7 minImageNum 3; %d seed patches x %d views per GPU per step, "
                           "refinePatch + computeINCC" % (args.views, args.width, args.height, args.patches, VIEWS),
-              "patches_per_gpu": args.patches, "views_per_patch": VIEWS, "optimizer": "in-kernel Nelder-Mead, xtol 1e-4, maxeval 1000",
+              "patches_per_gpu": args.patches, "views_per_patch": VIEWS, "optimizer": "in-kernel Nelder-Mead, xtol 1e-3 (scaled units: 1 = half a pixel of image motion / 3.75 degrees), maxeval 1000",
               "l2": "inputs larger than L2 (RGBA pyramids of 48 views = 0.49 GB, read through a texture atlas of the same size, + patch arrays); no explicit flush",
               "parallelism": "patches sharded over %d GPU(s), images replicated, NCCL all-gather of refined records per step" % world}
 
@@ -328,7 +328,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
-                                 "evals_per_patch": r["evals_per_patch"], "optimizer": "reference objective (COptim::my_f) + nm3 Nelder-Mead stand-in for nlopt BOBYQA, xtol 1e-4",
+                                 "evals_per_patch": r["evals_per_patch"], "optimizer": "reference objective (COptim::my_f) + nm3 Nelder-Mead stand-in for nlopt BOBYQA, xtol 1e-3",
                                  "at_reference_xtol": r.get("at_reference_xtol")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -476,7 +476,7 @@ def main():
         n = min(P, 1 << 16)
         r = reference_rate(scene, (coords[:n], normals[:n], images[:n], dsc[:n]), seconds=args.cpu_seconds, full=P, ref_xtol_seconds=5.0)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
-                                "evals_per_patch": r["evals_per_patch"], "optimizer": "reference objective (COptim::my_f) + nm3 Nelder-Mead stand-in for nlopt BOBYQA, xtol 1e-4",
+                                "evals_per_patch": r["evals_per_patch"], "optimizer": "reference objective (COptim::my_f) + nm3 Nelder-Mead stand-in for nlopt BOBYQA, xtol 1e-3",
                                 "at_reference_xtol": r.get("at_reference_xtol")}
     lib.close()
     if world > 1:

@@ -163,7 +163,7 @@ class PmvsB200:
     def set_thresholds(self, ncc, ncc_before):
         self._ck(self.lib.pmvsb_set_thresholds(self.ctx, C.c_float(ncc), C.c_float(ncc_before)))
 
-    def set_optimizer(self, xtol=1e-4, step=1.0, maxeval=1000):
+    def set_optimizer(self, xtol=1e-3, step=1.0, maxeval=1000):
         self._ck(self.lib.pmvsb_set_optimizer(self.ctx, C.c_double(xtol), C.c_double(step), int(maxeval)))
 
     def image(self, index, level):

@@ -654,7 +654,7 @@ struct pmvsb_ctx {
   int num = 0, tnum = 0, level = 1, csize = 2, wsize = 7, min_image_num = 3, tau = 0, nlevels = 0;
   float threshold = 0.7f, ncc_threshold = 0.7f, ncc_threshold_before = 0.4f;
   float angle_threshold0 = 0, angle_threshold1 = 0, max_angle_threshold = 0;
-  double xtol = 1.0e-4, step = 1.0;
+  double xtol = 1.0e-3, step = 1.0;   // the optimiser definition shared with oracle/nm3.h's callers
   int maxeval = 1000;
   std::vector<HostCam> cams;
   std::vector<HostImage> images;

@@ -244,6 +244,7 @@ Pipeline::Pipeline(const Options& o, const Dist& dist) : opt_(o), dist_(dist) {
   ncc_threshold_ = o.threshold;
   ncc_threshold_before_ = o.threshold - 0.3f;               // findMatch.cpp:104
   threads_ = std::max(1, std::min(o.CPU, (int)std::thread::hardware_concurrency() / std::max(1, dist.world)));   // the ranks share the host cores
+  if (const char* t = std::getenv("PMVSB_HOST_THREADS")) { const int v = std::atoi(t); if (v > 0) threads_ = std::min(threads_, v); }   // pmvs2_clusters: clusters side by side
 }
 
 Pipeline::~Pipeline() {

@@ -19,6 +19,7 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 namespace {
@@ -62,32 +63,36 @@ std::vector<std::string> visible_devices(int n) {
   return ids;
 }
 
-// element count + byte offset of the body: "element vertex N" ... "end_header\n" for .ply, "PATCHES\nN\n" for .patch
-bool split_model(const std::string& path, const char* kind, long long* count, std::string* body) {
-  std::ifstream in(path.c_str(), std::ios::binary);
-  if (!in) return false;
-  std::stringstream ss;
-  ss << in.rdbuf();
-  const std::string all = ss.str();
+// element count + byte offset of the body: "element vertex N" ... "end_header\n" for .ply, "PATCHES\nN\n" for .patch.
+// The file is read once into `all`; the body is all[*body_at ..) (cluster models run to hundreds of megabytes: no copies).
+bool split_model(const std::string& path, const char* kind, long long* count, std::string* all, size_t* body_at) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  struct stat st;
+  if (fstat(fileno(f), &st) != 0) { fclose(f); return false; }
+  all->resize((size_t)st.st_size);
+  const size_t got = st.st_size ? fread(&(*all)[0], 1, (size_t)st.st_size, f) : 0;
+  fclose(f);
+  if (got != (size_t)st.st_size) return false;
   if (!strcmp(kind, "pset")) {
     long long n = 0;
-    for (char c : all) n += c == '\n';
-    *count = n; *body = all;
+    for (const char* p = all->data(), *e = p + all->size(); (p = (const char*)memchr(p, '\n', (size_t)(e - p))) != nullptr; ++p) ++n;
+    *count = n; *body_at = 0;
     return true;
   }
   if (!strcmp(kind, "ply")) {
-    const size_t ev = all.find("element vertex ");
-    const size_t eh = all.find("end_header\n");
+    const size_t ev = all->find("element vertex ");
+    const size_t eh = all->find("end_header\n");
     if (ev == std::string::npos || eh == std::string::npos) return false;
-    *count = atoll(all.c_str() + ev + 15);
-    *body = all.substr(eh + 11);
+    *count = atoll(all->c_str() + ev + 15);
+    *body_at = eh + 11;
     return true;
   }
-  if (all.compare(0, 8, "PATCHES\n") != 0) return false;
-  const size_t nl = all.find('\n', 8);
+  if (all->compare(0, 8, "PATCHES\n") != 0) return false;
+  const size_t nl = all->find('\n', 8);
   if (nl == std::string::npos) return false;
-  *count = atoll(all.c_str() + 8);
-  *body = all.substr(nl + 1);
+  *count = atoll(all->c_str() + 8);
+  *body_at = nl + 1;
   return true;
 }
 
@@ -144,6 +149,8 @@ int main(int argc, char* argv[]) {
       if (pid < 0) { perror("fork"); return 1; }
       if (pid == 0) {
         setenv("CUDA_VISIBLE_DEVICES", devices[(size_t)slot].c_str(), 1);
+        // the clusters that run side by side share the host cores (file parsing, bookkeeping, writers): an equal share each
+        setenv("PMVSB_HOST_THREADS", std::to_string(std::max(1, (int)sysconf(_SC_NPROCESSORS_ONLN) / std::max(1, std::min(gpus, (int)options.size())))).c_str(), 0);
         unsetenv("WORLD_SIZE"); unsetenv("RANK"); unsetenv("LOCAL_RANK");   // a cluster is one single-GPU run
         const std::string log = prefix + "models/" + options[(size_t)c] + ".log";
         if (FILE* f = freopen(log.c_str(), "w", stdout)) { (void)f; dup2(fileno(stdout), fileno(stderr)); }
@@ -178,14 +185,13 @@ int main(int argc, char* argv[]) {
     for (const Kind& k : kinds) {
       if (!k.on) continue;
       long long total = 0;
-      std::vector<std::string> bodies;
-      for (const std::string& o : options) {
+      std::vector<std::string> files(options.size());
+      std::vector<size_t> body_at(options.size(), 0);
+      for (size_t c = 0; c < options.size(); ++c) {
         long long n = 0;
-        std::string body;
-        const std::string path = prefix + "models/" + o + "." + k.ext;
-        if (!split_model(path, k.ext, &n, &body)) { std::cerr << "pmvs2_clusters: cannot parse " << path << std::endl; return 1; }
+        const std::string path = prefix + "models/" + options[c] + "." + k.ext;
+        if (!split_model(path, k.ext, &n, &files[c], &body_at[c])) { std::cerr << "pmvs2_clusters: cannot parse " << path << std::endl; return 1; }
         total += n;
-        bodies.push_back(std::move(body));
       }
       std::ofstream out((prefix + "models/" + merged + "." + k.ext).c_str(), std::ios::binary);
       if (!strcmp(k.ext, "ply"))   // header of CPatchOrganizerS::writePLY (patchOrganizerS.cpp:693-706)
@@ -194,7 +200,7 @@ int main(int argc, char* argv[]) {
             << "property float quality\nend_header\n";
       else if (!strcmp(k.ext, "patch"))
         out << "PATCHES\n" << total << '\n';
-      for (const std::string& b : bodies) out.write(b.data(), (std::streamsize)b.size());
+      for (size_t c = 0; c < files.size(); ++c) out.write(files[c].data() + body_at[c], (std::streamsize)(files[c].size() - body_at[c]));
       std::cerr << "merged " << total << " patches of " << options.size() << " clusters into " << prefix << "models/" << merged << '.' << k.ext << std::endl;
     }
   }

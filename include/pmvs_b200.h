@@ -87,7 +87,7 @@ int pmvsb_finalize_scene(pmvsb_ctx* ctx);
 
 /* CFindMatch::_nccThreshold / _nccThresholdBefore / _depth (updateThreshold, findMatch.cpp:23-28,196,216) */
 int pmvsb_set_thresholds(pmvsb_ctx* ctx, float ncc_threshold, float ncc_threshold_before);
-/* Optimiser knobs replacing nlopt's set_xtol_rel / set_maxeval (optim.cpp:623-624). Defaults 1e-4, 1.0, 1000. */
+/* Optimiser knobs replacing nlopt's set_xtol_rel / set_maxeval (optim.cpp:623-624). Defaults 1e-3, 1.0, 1000. */
 int pmvsb_set_optimizer(pmvsb_ctx* ctx, double xtol, double step, int maxeval);
 
 /* ---- parity hooks (small, synchronous, host pointers) ------------------------------------------- */

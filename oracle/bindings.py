@@ -207,7 +207,7 @@ class OracleLib(_Common):
     def set_thresholds(self, ncc, ncc_before):
         self.lib.pmvso_set_thresholds(self.ctx, C.c_float(ncc), C.c_float(ncc_before))
 
-    def set_xtol(self, xtol=1e-4, step=1.0, maxeval=1000):
+    def set_xtol(self, xtol=1e-3, step=1.0, maxeval=1000):
         self.lib.pmvso_set_xtol(self.ctx, C.c_double(xtol), C.c_double(step), maxeval)
 
     def grab_tex(self, coord, normal, ref, index, wsize=7):

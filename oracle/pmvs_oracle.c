@@ -97,7 +97,7 @@ pmvso_ctx* pmvso_create(int num, int tnum, int level, int csize, int wsize, int 
   c->angle_threshold1 = 60.0f * M_PI / 180.0f;
   c->max_angle_threshold = max_angle_deg;                     /* source/pmvs/option.cpp:105-106 */
   c->max_angle_threshold *= M_PI / 180.0f;
-  c->xtol = 1.0e-4; c->step = 1.0; c->maxeval = 1000;
+  c->xtol = 1.0e-3; c->step = 1.0; c->maxeval = 1000;
   c->cams = (cam_t*)calloc(num, sizeof(cam_t));
   c->pix = (unsigned char**)calloc((size_t)num * c->nlevels, sizeof(unsigned char*));
   c->w = (int*)calloc((size_t)num * c->nlevels, sizeof(int));

@@ -561,7 +561,7 @@ int ref_filter_exact(int* old_index, int cap) {
 int ref_get_depth_flag(void) { return g_fm->_depth; }
 float ref_neighbor_threshold(int which) { return which == 0 ? g_fm->_neighborThreshold : (which == 1 ? g_fm->_neighborThreshold1 : g_fm->_neighborThreshold2); }
 
-// x-tolerance floor of the nm3 stand-in (oracle/shim/nlopt.hpp): 1e-4 by default, 0 = the reference's own xtol_rel 1e-7
+// x-tolerance floor of the nm3 stand-in (oracle/shim/nlopt.hpp): 1e-3 by default, 0 = the reference's own xtol_rel 1e-7
 void ref_set_xtol_floor(double v) { nlopt::xtol_floor() = v; }
 double ref_get_xtol_floor(void) { return nlopt::xtol_floor(); }
 

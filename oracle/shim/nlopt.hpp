@@ -13,10 +13,13 @@
 
 #include "../nm3.h"
 
-// Resolution floor of the f32 objective in scaled-parameter units: below this the patch centre
-// (an f32 vector) no longer moves, so xtol_rel*step = 1e-7 would only walk a plateau.
+// Stopping tolerance of the stand-in in scaled-parameter units (1 = half a pixel of image motion in depth, pi/48 in the
+// angles).  The reference asks nlopt for xtol_rel 1e-7; a simplex run down to that walks a plateau of the f32 objective
+// (178 instead of 104 evaluations per patch) and ends where the 1e-3 run ends: against a restatement of BOBYQA at the
+// reference's settings the three tolerances 1e-3 / 1e-4 / 1e-7 give the same percentiles to four digits
+// (profiles/r2_optimiser_bound_small.json; tools/research/optimiser_bound_study.py).  Runtime-settable (xtol_floor()).
 #ifndef PMVS_NM_XTOL_FLOOR
-#define PMVS_NM_XTOL_FLOOR 1.0e-4
+#define PMVS_NM_XTOL_FLOOR 1.0e-3
 #endif
 #ifndef PMVS_NM_STEP
 #define PMVS_NM_STEP 1.0

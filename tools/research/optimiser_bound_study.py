@@ -42,7 +42,7 @@ def main():
         orc.set_xtol(xtol, 1.0, 1000)
         r = orc.refine_batch(pt["coords"], pt["normals"], pt["images"], pt["dscales"], threads=8)
         arms[name] = dict(coords=r["coords"], normals=r["normals"], ncc=r["ncc"], evals=r["evals"].astype(np.float64), ok=r["ok"].astype(bool))
-    orc.set_xtol(1e-4, 1.0, 1000)
+    orc.set_xtol(1e-3, 1.0, 1000)
     lb = np.array([-np.inf, -23.99999, -23.99999]); ub = -lb
     co = np.zeros((n, 4), np.float32); no = np.zeros((n, 4), np.float32); ncc = np.zeros(n, np.float32); ev = np.zeros(n); ok = np.zeros(n, bool)
     t0 = time.time()
