@@ -230,9 +230,9 @@ def pipeline_wall_time(scene, impl, ranks=1):
 
 def measured_traffic(patches):
     """dram__bytes_read.sum + dram__bytes_write.sum of one k_refine launch from the committed `ncu --set full` capture
-    (profiles/r1_k_refine_dram.json); only valid for the launch size it was captured on."""
+    (profiles/r2_k_refine_dram.json); only valid for the launch size it was captured on."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_k_refine_dram.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_k_refine_dram.json")) as f:
             d = json.load(f)
         return float(d["dram_bytes_per_launch"]) if int(d["patches_per_launch"]) == int(patches) else None
     except Exception:
@@ -462,7 +462,7 @@ def main():
                 "traffic": measured_traffic(P), "kernel_ms": k_ms, "evals_per_patch": evals_sum / P, "tld4_per_launch": tld4,
                 "hbm_formula": hbm_formula,
                 "note": "texel gathers are served by L1TEX / L2 (DRAM traffic per launch = `traffic` bytes, 0.03 % of the algorithmic bytes), so the "
-                        "binding unit is the texture pipe (ncu: 75 % busy) next to instruction issue (76 %), profiles/r1_k_refine_g_v8_full_ncu_metrics.csv; "
+                        "binding unit is the texture pipe (ncu: 75 % busy) next to instruction issue (76 %), profiles/r2_k_refine_g_full_ncu_metrics.csv; "
                         "hbm_formula is SURVEY.md 8d's algorithmic-bytes fraction of the measured HBM copy bandwidth"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -214,7 +214,7 @@ void Pipeline::device_rebuild(int mode, const std::vector<uint8_t>* keep) {
 
 // the table's lists back into the host patches (what the next expansion round and the writers read), the patches that left
 // the table marked dead, the occupancy of _pgrids recounted
-void Pipeline::sync_table() {
+void Pipeline::sync_table(bool full) {
   Tick tk(this, "host.sync_table");
   int32_t P = 0, E = 0, VE = 0;
   if (pmvsb_store_counts(gpu_, &P, &E, &VE)) die("store_counts");
@@ -222,15 +222,18 @@ void Pipeline::sync_table() {
   std::vector<int32_t> seq(std::max(P, 1)), ti(std::max(P, 1)), off(P + 1), im(std::max(E, 1)), gr((size_t)2 * std::max(E, 1)), voff(P + 1),
       vim(std::max(VE, 1)), vgr((size_t)2 * std::max(VE, 1));
   if (pmvsb_store_download_lists(gpu_, seq.data(), ti.data(), off.data(), im.data(), gr.data())) die("store_download_lists");
-  if (pmvsb_store_download_vimages(gpu_, voff.data(), vim.data(), vgr.data())) die("store_download_vimages");
+  // between rounds the host only needs the image lists (parents of the next expansion) and the occupancy of _pgrids; the
+  // per-patch cells and visible-image lists are read by the writers only (full = true, once, from write())
+  if (full && pmvsb_store_download_vimages(gpu_, voff.data(), vim.data(), vgr.data())) die("store_download_vimages");
   for (Patch& p : patches_) p.alive = false;
   parallel_for(P, threads_, [&](int k) {
     if (seq[k] != table_ids_[k]) { std::cerr << "sync_table: the device and host numberings disagree" << std::endl; std::exit(1); }
     Patch& p = patches_[table_ids_[k]];
     p.alive = true;
     p.timages = ti[k];
-    const int n = off[k + 1] - off[k], nv = voff[k + 1] - voff[k];
     p.images.assign(im.begin() + off[k], im.begin() + off[k + 1]);
+    if (!full) return;
+    const int n = off[k + 1] - off[k], nv = voff[k + 1] - voff[k];
     p.grids.resize(n);
     for (int i = 0; i < n; ++i) p.grids[i] = {gr[(size_t)2 * (off[k] + i)], gr[(size_t)2 * (off[k] + i) + 1]};
     p.vimages.assign(vim.begin() + voff[k], vim.begin() + voff[k + 1]);
@@ -750,10 +753,11 @@ void Pipeline::filter_round() {   // filter.cpp:13-27
   filter_exact();
   filter_neighbor();
   filter_small_groups();
-  sync_table();
+  sync_table(false);
 }
 
 void Pipeline::run() {   // findMatch.cpp:187-220
+  patches_.reserve((size_t)1 << 21);   // the commit loops append patch records one by one: no re-allocation of a growing table
   seed_round();
   ++depth_;
   for (int t = 0; t < 3; ++t) {
@@ -789,6 +793,7 @@ void write_records(const std::string& path, const std::string& header, int P, in
 
 void Pipeline::write(const std::string& base, bool ply, bool patch, bool pset) {   // patchOrganizerS.cpp:89-132, 687-779
   if (!is_root()) return;   // every rank holds the same patches; one of them writes
+  if (table_ready_) sync_table(true);   // the writers read _vimages (.patch); the rounds did not need them on the host
   {
   Tick tk(this, "write.total");
   const std::vector<int> ids = table_ready_ ? table_ids_ : live_patches();

@@ -126,7 +126,7 @@ class Pipeline {
   std::vector<int> live_patches() const;    // ids of the live patches in creation order
   void device_rebuild(int mode, const std::vector<uint8_t>* keep);
   void apply_keep(const char* name, const std::vector<uint8_t>& keep);
-  void sync_table();
+  void sync_table(bool full);
   struct TableArrays;
   void marshal(const std::vector<int>& ids, TableArrays& t) const;
   void upload_table(const std::vector<int>& ids);
