@@ -303,7 +303,7 @@ def main():
                           "refinePatch + computeINCC" % (args.views, args.width, args.height, args.patches, VIEWS),
               "patches_per_gpu": args.patches, "views_per_patch": VIEWS, "optimizer": "in-kernel Nelder-Mead, xtol 1e-3 (scaled units: 1 = half a pixel of image motion / 3.75 degrees), maxeval 1000",
               "l2": "inputs larger than L2 (RGBA pyramids of 48 views = 0.49 GB, read through a texture atlas of the same size, + patch arrays); no explicit flush",
-              "parallelism": "patches sharded over %d GPU(s), images replicated, NCCL all-gather of refined records per step" % world}
+              "parallelism": "patches sharded over %d GPU(s), images replicated, refined records all-gathered every step" % world}
 
     if args.impl == "reference":
         if rank != 0:
@@ -360,15 +360,44 @@ def main():
     d_coords = torch.empty_like(d_coords0); d_normals = torch.empty_like(d_normals0)
     d_ncc = torch.empty(P, dtype=torch.float32, device=dev); d_evals = torch.empty(P, dtype=torch.int32, device=dev)
     d_ok = torch.empty(P, dtype=torch.uint8, device=dev)
-    rec = torch.empty(P, 12, dtype=torch.float32, device=dev)          # refined record exchanged per wave
-    rec_all = torch.empty(world * P, 12, dtype=torch.float32, device=dev) if world > 1 else None
+    # ---- the exchange of the refined records between the GPUs (north_star: accepted patches all-gathered over NVLink) ----------
+    # default "peer": one kernel after the refine kernel stores every patch's 48-byte record into this rank's slot of EVERY rank's
+    # mailbox (CUDA IPC mappings, peer stores over NVLink) and raises a flag there; a stream-ordered wait for all ranks' flags
+    # follows; no collective is launched.  PMVSB_BENCH_GATHER=nccl (or a box whose GPUs cannot map each other):
+    # pack + one NCCL all-gather after the kernel, as in round 1.
+    gather = "none"
+    rec = rec_all = None
+    if world > 1:
+        gather = os.environ.get("PMVSB_BENCH_GATHER", "peer")
+        if gather == "peer":
+            ok_t = torch.ones(1, dtype=torch.int32, device=dev)
+            handles = torch.zeros(world * 64, dtype=torch.uint8, device=dev)
+            try:
+                mine = lib.peer_export(rank, world, 2 * (P * 48 + 256))
+                dist.all_gather_into_tensor(handles, torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev))
+                lib.peer_open(bytes(handles.cpu().numpy().tobytes()))
+            except Exception as exc:      # every rank must learn about it: the ranks agree on the mode below
+                sys.stderr.write("bench.py: peer mailboxes unavailable on rank %d (%s)\n" % (rank, exc))
+                ok_t.zero_()
+            dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+            if int(ok_t.item()) == 0:
+                gather = "nccl"
+        if gather != "peer":
+            rec = torch.empty(P, 12, dtype=torch.float32, device=dev)          # refined record exchanged per wave
+            rec_all = torch.empty(world * P, 12, dtype=torch.float32, device=dev)
+    last_gather = [0, 0]   # device address of the gathered records of the last step, stride between ranks in floats
 
     def step_resident():
         d_coords.copy_(d_coords0); d_normals.copy_(d_normals0)
+        if gather == "peer":
+            last_gather[0], last_gather[1] = lib.refine_batch_dev_gather(P, VIEWS, d_coords.data_ptr(), d_normals.data_ptr(), d_images.data_ptr(), 0,
+                                                                         d_dsc.data_ptr(), d_ncc.data_ptr(), d_evals.data_ptr(), d_ok.data_ptr())
+            return
         lib.refine_batch_dev(P, VIEWS, d_coords.data_ptr(), d_normals.data_ptr(), d_images.data_ptr(), 0, d_dsc.data_ptr(),
                              d_ncc.data_ptr(), d_evals.data_ptr(), d_ok.data_ptr())
         if world > 1:
-            rec[:, 0:4] = d_coords; rec[:, 4:8] = d_normals; rec[:, 8] = d_ncc; rec[:, 9] = d_ok.to(torch.float32)
+            rec[:, 0:4] = d_coords; rec[:, 4:8] = d_normals; rec[:, 8] = d_ncc; rec[:, 9] = d_ok.to(torch.float32); rec[:, 10] = d_evals.to(torch.float32)
+            rec[:, 11] = 0.0
             dist.all_gather_into_tensor(rec_all, rec)
 
     def barrier():
@@ -405,6 +434,23 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = world * P * args.steps / (total_ms / 1000.0)
+
+    # the fused exchange checked against a plain NCCL all-gather of the same records (outside the timing): every rank must hold
+    # every rank's records of the last step, bit for bit
+    gather_verified = None
+    if gather == "peer":
+        class _DevView:      # zero-copy torch view of the mailbox slots (device memory owned by the library)
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        got = torch.as_tensor(_DevView(last_gather[0], world * last_gather[1]), device=dev).view(world, last_gather[1])[:, :P * 12].reshape(world * P, 12)
+        mine = torch.cat([d_coords, d_normals, d_ncc[:, None], d_ok.to(torch.float32)[:, None], d_evals.to(torch.float32)[:, None],
+                          torch.zeros(P, 1, dtype=torch.float32, device=dev)], dim=1).contiguous()
+        want = torch.empty(world * P, 12, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(want, mine)
+        same = torch.tensor([1 if torch.equal(got.view(torch.int32), want.view(torch.int32)) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        gather_verified = bool(int(same.item()))
+        del got, want, mine
 
     # ---- end to end through the host-pointer ABI call ------------------------------------------------
     h_coords = torch.from_numpy(coords).pin_memory(); h_normals = torch.from_numpy(normals).pin_memory()
@@ -471,6 +517,13 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches), "roofline": roofline,
             "quality": {"ok_fraction": ok_frac, "median_ncc": ncc_med}}
+    if world > 1:
+        line["exchange"] = {"mode": gather, "bytes_per_rank_per_step": P * 48 * world,
+                            "how": ("one kernel after the refine kernel packs the 48-byte records and stores them into every rank's mailbox (CUDA IPC mappings, peer stores "
+                                    "over NVLink), its last block raises the flags, stream-ordered waits (cuStreamWaitValue32); no collective launch"
+                                    + ("; PMVSB_GATHER_IN_KERNEL=1: the stores are issued by the refine kernel itself" if os.environ.get("PMVSB_GATHER_IN_KERNEL") == "1" else "")) if gather == "peer"
+                                   else "pack (torch) + one NCCL all_gather_into_tensor after the kernel",
+                            "verified_against_nccl_allgather": gather_verified}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = min(P, 1 << 16)

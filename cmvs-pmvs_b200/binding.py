@@ -26,7 +26,7 @@ SYMBOLS = [
     "pmvsb_download_depth_map", "pmvsb_depth_maps_add", "pmvsb_store_append", "pmvsb_store_update_vimages",
     "pmvsb_store_download_vimages", "pmvsb_download_cell_lists", "pmvsb_find_empty_blocks_store", "pmvsb_filter_neighbor_store", "pmvsb_check_batch", "pmvsb_set_vimages_store", "pmvsb_filter_exact_store", "pmvsb_compute_gains_store", "pmvsb_set_vimages_batch", "pmvsb_set_ref_image_batch",
     "pmvsb_patch_colors_batch", "pmvsb_refine_batch",
-    "pmvsb_refine_batch_dev", "pmvsb_detect_features", "pmvsb_comm_unique_id", "pmvsb_comm_init", "pmvsb_allgather", "pmvsb_sync", "pmvsb_stream", "pmvsb_set_stream", "pmvsb_launch_count", "pmvsb_last_refine_ms",
+    "pmvsb_refine_batch_dev", "pmvsb_refine_batch_dev_gather", "pmvsb_peer_export", "pmvsb_peer_open", "pmvsb_peer_close", "pmvsb_peer_needed", "pmvsb_detect_features", "pmvsb_comm_unique_id", "pmvsb_comm_init", "pmvsb_allgather", "pmvsb_sync", "pmvsb_stream", "pmvsb_set_stream", "pmvsb_launch_count", "pmvsb_last_refine_ms",
 ]
 
 
@@ -43,6 +43,8 @@ def load_library() -> C.CDLL:
     lib.pmvsb_stream.restype = C.c_void_p
     lib.pmvsb_launch_count.restype = C.c_uint64
     lib.pmvsb_last_refine_ms.restype = C.c_float
+    if hasattr(lib, "pmvsb_peer_needed"):      # (older builds loaded by tools/variant_bench.py do not have it)
+        lib.pmvsb_peer_needed.restype = C.c_size_t
     return lib
 
 
@@ -409,6 +411,31 @@ class PmvsB200:
         p = lambda v: C.c_void_p(int(v)) if v else None
         self._ck(self.lib.pmvsb_refine_batch_dev(self.ctx, int(P), int(stride), p(d_coords), p(d_normals), p(d_images), p(d_nimages),
                                                  p(d_dscales), p(d_ncc), p(d_evals), p(d_ok)))
+
+    def refine_batch_dev_gather(self, P, stride, d_coords, d_normals, d_images, d_nimages, d_dscales, d_ncc, d_evals, d_ok):
+        """refine_batch_dev with the all-gather of the refined records fused into the kernel (peer stores into every rank's
+        mailbox); returns (device address of rank 0's records of this call, stride between ranks in floats); asynchronous."""
+        p = lambda v: C.c_void_p(int(v)) if v else None
+        rec = C.c_void_p()
+        rstride = C.c_size_t()
+        self._ck(self.lib.pmvsb_refine_batch_dev_gather(self.ctx, int(P), int(stride), p(d_coords), p(d_normals), p(d_images), p(d_nimages),
+                                                        p(d_dscales), p(d_ncc), p(d_evals), p(d_ok), C.byref(rec), C.byref(rstride)))
+        return int(rec.value or 0), int(rstride.value)
+
+    def peer_export(self, rank, world, slot_bytes) -> bytes:
+        """(Re)allocates this rank's mailbox (one slot of slot_bytes per rank) and returns its 64-byte CUDA IPC handle."""
+        buf = (C.c_uint8 * 64)()
+        self._ck(self.lib.pmvsb_peer_export(self.ctx, int(rank), int(world), C.c_size_t(int(slot_bytes)), buf))
+        self._world = int(world)
+        return bytes(buf)
+
+    def peer_open(self, handles: bytes):
+        """handles = the world ranks' 64-byte handles back to back, in rank order"""
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        self._ck(self.lib.pmvsb_peer_open(self.ctx, buf))
+
+    def peer_close(self):
+        self._ck(self.lib.pmvsb_peer_close(self.ctx))
 
     def detect_features(self, index, gspeedup=16, cap=65536):
         xy = np.zeros((cap, 2), np.float32); resp = np.zeros(cap, np.float32); types = np.zeros(cap, np.int32)

@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sched.h>
 #include <nccl.h>
 
 #include <algorithm>
@@ -13,6 +14,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -358,12 +360,33 @@ __global__ void k_order_fill(int P, const int32_t* __restrict__ bin_of, int32_t*
 // K3 (v2): COptim::refinePatch for a whole frontier.  Each 8-lane group pulls patches from a global counter
 // and runs its own Nelder-Mead (state in shared memory, advanced by the group leader); the four groups of a
 // warp evaluate their objectives in lock step.
-template <int WSIZE, bool TEX>
+// GATHER: the all-gather of the refined records is part of the kernel.  When a patch leaves the optimiser its group leader stores
+// the 48-byte record (coord, normal, ncc, ok, evaluations) into this rank's slot of EVERY rank's mailbox -- its own memory and,
+// through the CUDA IPC mappings, the other GPUs' memory over NVLink -- so the exchange trickles out underneath the ~125
+// evaluations per patch of the groups still working and there is no collective after the kernel, only a flag (pmvsb_refine_batch_dev_gather).
+struct RecDst {
+  float4* rec[PMVSB_MAX_RANKS];   // this rank's record array in every rank's mailbox
+  int n;
+};
+// Out of line and fed from memory on purpose: the call sits on the once-per-patch path, and neither the 16 mailbox pointers nor
+// the record may cost the optimiser loop a register (the loop runs at the 64-register cap).  The leader lane has just written
+// the patch's results, so it reads its own stores back.
+__device__ __noinline__ void post_record(const RecDst* __restrict__ rd, int p, const float* coords, const float* normals, const float* ncc_out,
+                                         const int32_t* evals_out, const uint8_t* ok_out) {
+  const float4 c = reinterpret_cast<const float4*>(coords)[p], n = reinterpret_cast<const float4*>(normals)[p];
+  const float4 t = make_float4(ncc_out[p], ok_out[p] ? 1.0f : 0.0f, (float)evals_out[p], 0.0f);
+  const int nd = rd->n;
+  for (int d = 0; d < nd; ++d) {
+    float4* o = rd->rec[d] + (size_t)3 * p;
+    o[0] = c; o[1] = n; o[2] = t;
+  }
+}
+template <int WSIZE, bool TEX, bool GATHER = false>
 __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, int P, int stride, float* __restrict__ coords, float* __restrict__ normals,
                                                      const int32_t* __restrict__ images, const int32_t* __restrict__ nimages,
                                                      const float* __restrict__ dscales, float* __restrict__ ncc_out,
                                                      int32_t* __restrict__ evals_out, uint8_t* __restrict__ ok_out,
-                                                     int* __restrict__ counter, const int32_t* __restrict__ order) {
+                                                     int* __restrict__ counter, const int32_t* __restrict__ order, const RecDst* __restrict__ rd = nullptr) {
   // counter[0] = next entry of `order` to hand out, counter[1] = set to 1 when a patch names an image outside [0, num).
   // `order` = the patches sorted by reference image and 8x8-pixel tile (k_order_*); nullptr = identity.  Groups draw single
   // entries from the global counter (evaluation counts differ 2x between patches: any coarser or static hand-out loses more
@@ -406,7 +429,10 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
           bad |= (im < 0 || im >= s.num);
         }
         if (__any_sync(gmask, bad)) {
-          if (gl == 0) { atomicExch(counter + 1, 1); ncc_out[p] = -1.0f; evals_out[p] = 0; ok_out[p] = 0; }
+          if (gl == 0) {
+            atomicExch(counter + 1, 1); ncc_out[p] = -1.0f; evals_out[p] = 0; ok_out[p] = 0;
+            if (GATHER) post_record(rd, p, coords, normals, ncc_out, evals_out, ok_out);
+          }
           // this group stays without a patch for one trip and asks again on the next
         } else {
           group_ctx_init(s, gc, coord, normal, images + (size_t)p * stride, n, dscales[p], gl, gmask);
@@ -453,6 +479,7 @@ __global__ void __launch_bounds__(128, PMVS_MINBLOCKS) k_refine_g(SceneDev s, in
           ncc_out[p] = ncc;
           evals_out[p] = nm.cnt;
           ok_out[p] = ok ? 1 : 0;
+          if (GATHER) post_record(rd, p, coords, normals, ncc_out, evals_out, ok_out);   // (a failed patch keeps its input coordinates)
         }
         have = false;
         gc.size = 0;
@@ -707,6 +734,18 @@ struct pmvsb_ctx {
   int comm_rank = 0, comm_world = 1;
   char* comm_buf = nullptr;
   size_t comm_cap = 0;
+  // peer-memory wave exchange: one mailbox per rank (cudaMalloc), mapped into every other rank's address space through CUDA IPC;
+  // ranks STORE their messages straight into each other's mailboxes over NVLink (pmvsb_peer_export / pmvsb_peer_open)
+  struct PeerBox {
+    bool on = false;
+    char* own = nullptr;                       // this rank's mailbox: [kPeerHeader bytes of flags and sizes][world slots of slot_bytes]
+    char* base[PMVSB_MAX_RANKS] = {nullptr};   // every rank's mailbox as seen from here (base[rank] == own)
+    size_t slot_bytes = 0, needed = 0;
+    uint32_t seq = 0;                          // wave number, the value the flags take
+    int* d_done = nullptr;                     // block counter of k_wave_post
+    void* d_rec = nullptr;                     // two RecDst tables of pmvsb_refine_batch_dev_gather (by call parity)
+    uint32_t* h_board = nullptr;               // pinned copy of the mailbox header for the polls
+  } peer;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -917,6 +956,25 @@ struct DevBuf {
     return p ? cudaSuccess : cudaErrorMemoryAllocation;
   }
 };
+
+// peer-memory exchange (pmvsb_peer_*): unmap the peers' mailboxes / free this rank's
+static void peer_unmap(pmvsb_ctx* ctx) {
+  pmvsb_ctx::PeerBox& pb = ctx->peer;
+  for (int k = 0; k < PMVSB_MAX_RANKS; ++k) {
+    if (pb.base[k] && pb.base[k] != pb.own) cudaIpcCloseMemHandle(pb.base[k]);
+    pb.base[k] = nullptr;
+  }
+  pb.on = false;
+}
+static void peer_free(pmvsb_ctx* ctx) {
+  peer_unmap(ctx);
+  pmvsb_ctx::PeerBox& pb = ctx->peer;
+  cudaFree(pb.own); pb.own = nullptr;
+  cudaFree(pb.d_done); pb.d_done = nullptr;
+  cudaFree(pb.d_rec); pb.d_rec = nullptr;
+  if (pb.h_board) cudaFreeHost(pb.h_board);
+  pb.h_board = nullptr;
+}
 
 int check_ready(pmvsb_ctx* ctx) {
   if (!ctx) return PMVSB_EINVAL;
@@ -1203,6 +1261,7 @@ int pmvsb_destroy(pmvsb_ctx* ctx) {
   cudaFree(ctx->d_fgw.p); cudaFree(ctx->d_fgh.p); cudaFree(ctx->d_blocked.p); cudaFree(ctx->d_seed_out.p);
   store_free(ctx);
   if (ctx->comm && nccl_api()) nccl_api()->CommDestroy(ctx->comm);
+  peer_free(ctx);
   cudaFree(ctx->comm_buf);
   for (auto& b : ctx->pool) cudaFree(b.second);
   g_current = nullptr;
@@ -2740,8 +2799,9 @@ int pmvsb_post_process_batch(pmvsb_ctx* ctx, int P, int stride, const float* coo
   return check_view_overflow(ctx, "pre/post_process_batch", stride);
 }
 
-int pmvsb_refine_batch_dev(pmvsb_ctx* ctx, int P, int stride, float* d_coords, float* d_normals, const int32_t* d_images,
-                           const int32_t* d_nimages, const float* d_dscales, float* d_ncc, int32_t* d_evals, uint8_t* d_ok) {
+// gather != nullptr: the kernel also stores every patch's record into the mailboxes named there (pmvsb_refine_batch_dev_gather)
+static int refine_dev_impl(pmvsb_ctx* ctx, int P, int stride, float* d_coords, float* d_normals, const int32_t* d_images,
+                           const int32_t* d_nimages, const float* d_dscales, float* d_ncc, int32_t* d_evals, uint8_t* d_ok, const RecDst* gather) {
   int r = check_ready(ctx);
   if (r) return r;
   if (P < 0 || stride < 1 || !d_coords || !d_normals || !d_images || !d_dscales || !d_ncc || !d_evals || !d_ok)
@@ -2784,12 +2844,28 @@ int pmvsb_refine_batch_dev(pmvsb_ctx* ctx, int P, int stride, float* d_coords, f
   const int per_block = ctx->wsize == 9 ? 4 : 16;  // patches a CTA works on at a time
   const int needed = (P + per_block - 1) / per_block;
   if (grid > needed) grid = needed;
+  if (gather) {
+    if (ctx->scene.atlas == 0 || (ctx->wsize != 7 && ctx->wsize != 5))
+      return fail(ctx, PMVSB_EINVAL, "refine_batch_dev_gather: needs the texture-atlas path and wsize 5 or 7");
+    if (ctx->wsize == 5)
+      k_refine_g<5, true, true><<<grid, 128, 0, ctx->stream>>>(ctx->scene, P, stride, d_coords, d_normals, d_images, d_nimages, d_dscales, d_ncc, d_evals, d_ok,
+                                                                ctx->d_counter, d_order, gather);
+    else
+      k_refine_g<7, true, true><<<grid, 128, 0, ctx->stream>>>(ctx->scene, P, stride, d_coords, d_normals, d_images, d_nimages, d_dscales, d_ncc, d_evals, d_ok,
+                                                                ctx->d_counter, d_order, gather);
+    ++ctx->launches;
+  } else
   DISPATCH_GROUP(ctx, k_refine_g, k_refine, grid, grid, 128, ctx->scene, P, stride, d_coords, d_normals, d_images, d_nimages, d_dscales,
                  d_ncc, d_evals, d_ok, ctx->d_counter, d_order);
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->refine_timed = true;
   CK(cudaGetLastError());
   return PMVSB_OK;
+}
+
+int pmvsb_refine_batch_dev(pmvsb_ctx* ctx, int P, int stride, float* d_coords, float* d_normals, const int32_t* d_images,
+                           const int32_t* d_nimages, const float* d_dscales, float* d_ncc, int32_t* d_evals, uint8_t* d_ok) {
+  return refine_dev_impl(ctx, P, stride, d_coords, d_normals, d_images, d_nimages, d_dscales, d_ncc, d_evals, d_ok, nullptr);
 }
 
 
@@ -3240,26 +3316,291 @@ __global__ void k_add_scalar(int n, int32_t* __restrict__ a, int v) {
   if (i < n) a[i] += v;
 }
 
+// ---- peer-memory exchange (pmvsb_peer_*): mailboxes mapped between the ranks through CUDA IPC -------------------------
+// Mailbox of a rank: a header of kPeerHeader bytes -- 64 bytes per SOURCE rank: [0] sizes flag, [1] data flag, [2..5] the source's
+// (P, A, E, VE) of the current wave -- followed by one slot of slot_bytes per source rank.  Flags carry the wave number.
+constexpr size_t kPeerHeader = 4096;
+constexpr int kPeerEntryWords = 16;
+static_assert(PMVSB_MAX_RANKS * kPeerEntryWords * sizeof(uint32_t) <= kPeerHeader, "mailbox header too small");
+static_assert(sizeof(cudaIpcMemHandle_t) == PMVSB_PEER_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+static inline uint32_t* peer_entry(char* box, int src) { return reinterpret_cast<uint32_t*>(box) + (size_t)src * kPeerEntryWords; }
+static inline int32_t* peer_slot(char* box, size_t slot_bytes, int src) { return reinterpret_cast<int32_t*>(box + kPeerHeader + (size_t)src * slot_bytes); }
+
+struct PeerDst {
+  uint32_t* entry[PMVSB_MAX_RANKS];   // this rank's header entry in every rank's mailbox
+  int32_t* slot[PMVSB_MAX_RANKS];     // this rank's slot in every rank's mailbox
+  int n;
+};
+// sizes of this rank's message into every mailbox, then the flag (system-scope fence in between: a reader that sees the flag sees the sizes)
+__global__ void k_peer_post_sizes(PeerDst d, int p, int a, int e, int ve, uint32_t seq) {
+  const int k = threadIdx.x;
+  if (k >= d.n) return;
+  volatile uint32_t* en = d.entry[k];
+  en[2] = (uint32_t)p; en[3] = (uint32_t)a; en[4] = (uint32_t)e; en[5] = (uint32_t)ve;
+  __threadfence_system();
+  en[0] = seq;
+}
+// The wave's message, packed from the result arrays on the fly and STORED into every rank's mailbox (own memory for this rank,
+// peer memory over NVLink for the others) by one kernel; the last block to finish raises the data flag in every mailbox.
+// Message = the segments back to back; xform 1 adds `arg` (shard-local candidate index -> wave-wide), xform 2 turns CSR offsets
+// into lengths (the receiver re-scans them over the whole wave).
+struct WaveSeg { const int32_t* src; unsigned words; int xform; int arg; };
+struct WavePost {
+  WaveSeg seg[12];
+  unsigned start[13];
+  int nseg;
+  unsigned total;
+  uint32_t seq;
+  int* done;
+  PeerDst dst;
+};
+__global__ void __launch_bounds__(256) k_wave_post(const WavePost w) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < w.total; i += gridDim.x * blockDim.x) {
+    int sg = 0;
+#pragma unroll 1
+    while (sg + 1 < w.nseg && i >= w.start[sg + 1]) ++sg;
+    const WaveSeg& g = w.seg[sg];
+    const unsigned j = i - w.start[sg];
+    int32_t v = __ldg(g.src + j);
+    if (g.xform == 1) v += g.arg;
+    else if (g.xform == 2) v = __ldg(g.src + j + 1) - v;
+    for (int d = 0; d < w.dst.n; ++d) w.dst.slot[d][i] = v;
+  }
+  __threadfence_system();   // this thread's stores are visible system-wide before its block is counted
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(w.done, 1);
+    if (t == (int)gridDim.x - 1) {
+      *w.done = 0;
+      __threadfence_system();
+      for (int d = 0; d < w.dst.n; ++d) *(volatile uint32_t*)(w.dst.entry[d] + 1) = w.seq;
+    }
+  }
+}
+
+int pmvsb_peer_export(pmvsb_ctx* ctx, int rank, int world, size_t slot_bytes, uint8_t* handle64) {
+  if (!ctx || !handle64 || world < 1 || world > PMVSB_MAX_RANKS || rank < 0 || rank >= world || slot_bytes < 64)
+    return fail(ctx, PMVSB_EINVAL, "peer_export: bad argument (at most PMVSB_MAX_RANKS ranks)");
+  CK(cudaSetDevice(ctx->device));
+  pmvsb_ctx::PeerBox& pb = ctx->peer;
+  for (int k = 0; k < PMVSB_MAX_RANKS; ++k)
+    if (pb.base[k] && pb.base[k] != pb.own) return fail(ctx, PMVSB_ESTATE, "peer_export: peers are still mapped (pmvsb_peer_close first)");
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(pb.own); pb.own = nullptr;
+  slot_bytes = (slot_bytes + 255) & ~(size_t)255;
+  CK(cudaMalloc((void**)&pb.own, kPeerHeader + slot_bytes * (size_t)world));   // plain cudaMalloc: pool memory has no legacy IPC handle
+  CK(cudaMemset(pb.own, 0, kPeerHeader));
+  if (!pb.d_done) { CK(cudaMalloc((void**)&pb.d_done, sizeof(int))); CK(cudaMemset(pb.d_done, 0, sizeof(int))); }
+  if (!pb.h_board) CK(cudaHostAlloc((void**)&pb.h_board, kPeerHeader, cudaHostAllocDefault));
+  CK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, pb.own));
+  std::memcpy(handle64, &h, sizeof(h));
+  pb.slot_bytes = slot_bytes;
+  ctx->comm_rank = rank; ctx->comm_world = world;
+  return PMVSB_OK;
+}
+
+int pmvsb_peer_open(pmvsb_ctx* ctx, const uint8_t* handles) {
+  if (!ctx || !handles) return fail(ctx, PMVSB_EINVAL, "peer_open: null pointer");
+  pmvsb_ctx::PeerBox& pb = ctx->peer;
+  if (!pb.own) return fail(ctx, PMVSB_ESTATE, "peer_open: call pmvsb_peer_export first");
+  CK(cudaSetDevice(ctx->device));
+  peer_unmap(ctx);
+  for (int k = 0; k < ctx->comm_world; ++k) {
+    if (k == ctx->comm_rank) { pb.base[k] = pb.own; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + (size_t)k * sizeof(h), sizeof(h));
+    void* ptr = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      peer_unmap(ctx);
+      return fail(ctx, PMVSB_ECUDA, std::string("peer_open: cudaIpcOpenMemHandle (rank ") + std::to_string(k) + "): " + cudaGetErrorString(e));
+    }
+    pb.base[k] = (char*)ptr;
+  }
+  pb.on = ctx->comm_world > 1;
+  return PMVSB_OK;
+}
+
+int pmvsb_peer_close(pmvsb_ctx* ctx) {
+  if (!ctx) return PMVSB_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  peer_unmap(ctx);
+  return PMVSB_OK;
+}
+
+size_t pmvsb_peer_needed(const pmvsb_ctx* ctx) { return ctx ? ctx->peer.needed : 0; }
+
+// waits until header word `word` (0 = sizes, 1 = data) of every source rank has reached `seq`; the host polls a copy of its OWN
+// mailbox header (no kernel spins on the device, so two ranks may share a GPU, and a lost peer ends in an error, not a hang)
+static int peer_wait(pmvsb_ctx* ctx, int word, uint32_t seq) {
+  pmvsb_ctx::PeerBox& pb = ctx->peer;
+  const int W = ctx->comm_world;
+  static const double limit = [] { const char* v = std::getenv("PMVSB_PEER_TIMEOUT_S"); return v && *v ? std::atof(v) : 120.0; }();
+  const auto t0 = std::chrono::steady_clock::now();
+  for (long it = 0;; ++it) {
+    CK(cudaMemcpyAsync(pb.h_board, pb.own, sizeof(uint32_t) * kPeerEntryWords * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    bool all = true;
+    for (int k = 0; k < W; ++k) all = all && (int32_t)(pb.h_board[(size_t)k * kPeerEntryWords + word] - seq) >= 0;
+    if (all) return PMVSB_OK;
+    if ((it & 31) == 31 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit)
+      return fail(ctx, PMVSB_ESTATE, "evaluate_allgather: a peer rank did not post its message in time (PMVSB_PEER_TIMEOUT_S)");
+    if (it > 64) sched_yield();
+  }
+}
+
+// ---- refine + all-gather of the refined records in one kernel (the multi-GPU microbench step and any caller that wants every
+// rank to hold every rank's refined patches).  Each mailbox slot is used as two halves, by wave parity: a rank waits for the
+// flags of ALL ranks of wave k before it starts wave k + 1, so a peer is at most one wave ahead and writes the other half.
+constexpr int kRecordFloats = 12;   // coord[4], normal[4], ncc, ok, evaluations, 0
+constexpr int kPeerWordRecords = 6; // header word of the records flag
+__global__ void k_peer_flag(PeerDst d, int word, uint32_t seq) {
+  const int k = threadIdx.x;
+  if (k >= d.n) return;
+  __threadfence_system();
+  *(volatile uint32_t*)(d.entry[k] + word) = seq;
+}
+// The default form of the exchange: ONE kernel after the refine kernel packs the records from the result arrays and stores them
+// into every rank's mailbox (thread i writes float4 i of this rank's record array in all mailboxes: coalesced 16-byte peer
+// stores), the last block raises the flags.  Measured on B200 (1 048 576 patches, profiles/r2_peer_exchange.txt): the in-kernel
+// form (k_refine_g<., ., GATHER>) costs the refine kernel +1.0 % (125.6 vs 124.4 ms: the once-per-patch call perturbs the register
+// allocation of a loop that runs at the 64-register cap), more than the whole exchange takes as a kernel of its own.
+__global__ void __launch_bounds__(256) k_records_post(int P, const float4* __restrict__ coords, const float4* __restrict__ normals, const float* __restrict__ ncc,
+                                                      const uint8_t* __restrict__ ok, const int32_t* __restrict__ evals, const RecDst rd, PeerDst flags,
+                                                      int word, uint32_t seq, int* done) {
+  const int total = 3 * P;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int p = i / 3, part = i - 3 * p;
+    float4 v;
+    if (part == 0) v = coords[p];
+    else if (part == 1) v = normals[p];
+    else v = make_float4(ncc[p], ok[p] ? 1.0f : 0.0f, (float)evals[p], 0.0f);
+    for (int d = 0; d < rd.n; ++d) rd.rec[d][i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(done, 1);
+    if (t == (int)gridDim.x - 1) {
+      *done = 0;
+      __threadfence_system();
+      for (int d = 0; d < flags.n; ++d) *(volatile uint32_t*)(flags.entry[d] + word) = seq;
+    }
+  }
+}
+// cuStreamWaitValue32 through the runtime's driver entry point (no link against libcuda): the wait for the peers' flags is an
+// operation of the stream, the host does not block
+typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
+static StreamWaitValue32Fn stream_wait_value32() {
+  static StreamWaitValue32Fn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) { cudaGetLastError(); f = nullptr; }
+    return (StreamWaitValue32Fn)f;
+  }();
+  return fn;
+}
+
+int pmvsb_refine_batch_dev_gather(pmvsb_ctx* ctx, int P, int stride, float* d_coords, float* d_normals, const int32_t* d_images,
+                                  const int32_t* d_nimages, const float* d_dscales, float* d_ncc, int32_t* d_evals, uint8_t* d_ok,
+                                  const float** records, size_t* rank_stride_floats) {
+  int r = check_ready(ctx);
+  if (r) return r;
+  pmvsb_ctx::PeerBox& pb = ctx->peer;
+  if (!pb.own || (ctx->comm_world > 1 && !pb.on)) return fail(ctx, PMVSB_ESTATE, "refine_batch_dev_gather: call pmvsb_peer_export and pmvsb_peer_open first");
+  if (P < 0) return fail(ctx, PMVSB_EINVAL, "refine_batch_dev_gather: bad argument");
+  const size_t half = (pb.slot_bytes / 2) & ~(size_t)255;
+  if ((size_t)P * kRecordFloats * sizeof(float) > half) {
+    pb.needed = 2 * ((size_t)P * kRecordFloats * sizeof(float) + 256);
+    return fail(ctx, PMVSB_EGROW, "refine_batch_dev_gather: the records do not fit half a mailbox slot");
+  }
+  const int W = ctx->comm_world;
+  const uint32_t seq = ++pb.seq;
+  const size_t off = (seq & 1u) ? half : 0;
+  RecDst rd;
+  PeerDst dst;
+  rd.n = dst.n = W;
+  for (int k = 0; k < PMVSB_MAX_RANKS; ++k) {
+    char* box = k < W ? (k == ctx->comm_rank ? pb.own : pb.base[k]) : nullptr;
+    rd.rec[k] = box ? reinterpret_cast<float4*>(reinterpret_cast<char*>(peer_slot(box, pb.slot_bytes, ctx->comm_rank)) + off) : nullptr;
+    dst.entry[k] = box ? peer_entry(box, ctx->comm_rank) : nullptr;
+    dst.slot[k] = nullptr;
+  }
+  const char* in_kernel_env = std::getenv("PMVSB_GATHER_IN_KERNEL");
+  const bool in_kernel = in_kernel_env && *in_kernel_env == '1';
+  if (in_kernel) {
+    // A/B form: the refine kernel itself stores each finished patch's record (k_refine_g<., ., GATHER>), then one flag kernel
+    if (!pb.d_rec) CK(cudaMalloc((void**)&pb.d_rec, 2 * sizeof(RecDst)));
+    RecDst* d_rd = reinterpret_cast<RecDst*>(pb.d_rec) + (seq & 1u);   // (the previous call's kernel may still be reading the other one)
+    CK(cudaMemcpyAsync(d_rd, &rd, sizeof(RecDst), cudaMemcpyHostToDevice, ctx->stream));
+    if ((r = refine_dev_impl(ctx, P, stride, d_coords, d_normals, d_images, d_nimages, d_dscales, d_ncc, d_evals, d_ok, d_rd))) return r;
+    k_peer_flag<<<1, 32, 0, ctx->stream>>>(dst, kPeerWordRecords, seq);
+  } else {
+    if ((r = refine_dev_impl(ctx, P, stride, d_coords, d_normals, d_images, d_nimages, d_dscales, d_ncc, d_evals, d_ok, nullptr))) return r;
+    if (!pb.d_done) { CK(cudaMalloc((void**)&pb.d_done, sizeof(int))); CK(cudaMemsetAsync(pb.d_done, 0, sizeof(int), ctx->stream)); }
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((3ll * P + 255) / 256, (long long)ctx->sm_count * 8));
+    k_records_post<<<blocks, 256, 0, ctx->stream>>>(P, reinterpret_cast<const float4*>(d_coords), reinterpret_cast<const float4*>(d_normals), d_ncc, d_ok, d_evals,
+                                                    rd, dst, kPeerWordRecords, seq, pb.d_done);
+  }
+  ++ctx->launches;
+  CK(cudaGetLastError());
+  if (W > 1) {
+    StreamWaitValue32Fn wait = stream_wait_value32();
+    if (wait) {
+      for (int k = 0; k < W; ++k) {
+        if (k == ctx->comm_rank) continue;
+        const int e = wait(ctx->stream, (unsigned long long)(uintptr_t)(peer_entry(pb.own, k) + kPeerWordRecords), seq, 0u /* CU_STREAM_WAIT_VALUE_GEQ: (int32)(*addr - seq) >= 0 */);
+        if (e != 0) return fail(ctx, PMVSB_ECUDA, "refine_batch_dev_gather: cuStreamWaitValue32 failed (" + std::to_string(e) + ")");
+      }
+    } else if ((r = peer_wait(ctx, kPeerWordRecords, seq))) return r;
+  }
+  if (records) *records = reinterpret_cast<const float*>(reinterpret_cast<char*>(peer_slot(pb.own, pb.slot_bytes, 0)) + off);
+  if (rank_stride_floats) *rank_stride_floats = pb.slot_bytes / sizeof(float);
+  return PMVSB_OK;
+}
+
 int pmvsb_evaluate_allgather(pmvsb_ctx* ctx, int shard_lo, int total_candidates) {
   int r = check_ready(ctx);
   if (r) return r;
   pmvsb_ctx::EvalOut& ev = ctx->ev;
   if (shard_lo < 0 || total_candidates < shard_lo + ev.P) return fail(ctx, PMVSB_EINVAL, "evaluate_allgather: shard outside the wave");
   if (ctx->comm_world == 1) return PMVSB_OK;
-  if (!ctx->comm) return fail(ctx, PMVSB_ESTATE, "evaluate_allgather: call pmvsb_comm_init first");
-  NcclApi* api = nccl_api();
+  const bool peer = ctx->peer.on;
+  if (!peer && !ctx->comm) return fail(ctx, PMVSB_ESTATE, "evaluate_allgather: call pmvsb_peer_open or pmvsb_comm_init first");
+  NcclApi* api = peer ? nullptr : nccl_api();
   cudaStream_t q = ctx->stream;
   const int W = ctx->comm_world;
-  // sizes of every rank's message
-  DevBuf<int32_t> dmeta;
-  CK(dmeta.alloc((size_t)4 * (W + 1)));
-  const int32_t mine[4] = {ev.P, ev.A, ev.E, ev.VE};
-  CK(cudaMemcpyAsync(dmeta.p, mine, sizeof(mine), cudaMemcpyHostToDevice, q));
-  ncclResult_t nr = api->AllGather(dmeta.p, dmeta.p + 4, 4, ncclInt32, ctx->comm, q);
-  if (nr != ncclSuccess) return fail(ctx, PMVSB_ECUDA, std::string("ncclAllGather: ") + api->GetErrorString(nr));
+  pmvsb_ctx::PeerBox& pb = ctx->peer;
+  PeerDst dst;
+  dst.n = W;
+  for (int k = 0; k < PMVSB_MAX_RANKS; ++k) {
+    dst.entry[k] = peer && k < W ? peer_entry(pb.base[k], ctx->comm_rank) : nullptr;
+    dst.slot[k] = peer && k < W ? peer_slot(pb.base[k], pb.slot_bytes, ctx->comm_rank) : nullptr;
+  }
+  // ---- sizes of every rank's message
   std::vector<int32_t> meta((size_t)4 * W);
-  CK(cudaMemcpyAsync(meta.data(), dmeta.p + 4, sizeof(int32_t) * meta.size(), cudaMemcpyDeviceToHost, q));
-  CK(cudaStreamSynchronize(q));
+  DevBuf<int32_t> dmeta;
+  if (peer) {
+    ++pb.seq;
+    k_peer_post_sizes<<<1, 32, 0, q>>>(dst, ev.P, ev.A, ev.E, ev.VE, pb.seq);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    if ((r = peer_wait(ctx, 0, pb.seq))) return r;
+    for (int k = 0; k < W; ++k)
+      for (int c = 0; c < 4; ++c) meta[4 * k + c] = (int32_t)pb.h_board[(size_t)k * kPeerEntryWords + 2 + c];
+  } else {
+    CK(dmeta.alloc((size_t)4 * (W + 1)));
+    const int32_t mine[4] = {ev.P, ev.A, ev.E, ev.VE};
+    CK(cudaMemcpyAsync(dmeta.p, mine, sizeof(mine), cudaMemcpyHostToDevice, q));
+    ncclResult_t nr = api->AllGather(dmeta.p, dmeta.p + 4, 4, ncclInt32, ctx->comm, q);
+    if (nr != ncclSuccess) return fail(ctx, PMVSB_ECUDA, std::string("ncclAllGather: ") + api->GetErrorString(nr));
+    CK(cudaMemcpyAsync(meta.data(), dmeta.p + 4, sizeof(int32_t) * meta.size(), cudaMemcpyDeviceToHost, q));
+    CK(cudaStreamSynchronize(q));
+  }
   auto words = [](int P, int A, int E, int VE) { return (size_t)P + (size_t)4 * A + (size_t)12 * A + (size_t)3 * E + (size_t)3 * VE; };
   size_t longest = 0;
   long long tP = 0, tA = 0, tE = 0, tVE = 0;
@@ -3269,34 +3610,73 @@ int pmvsb_evaluate_allgather(pmvsb_ctx* ctx, int shard_lo, int total_candidates)
   }
   if (tP != total_candidates) return fail(ctx, PMVSB_EINVAL, "evaluate_allgather: the shards do not add up to the wave");
   longest = (longest + 3) & ~(size_t)3;
-  const size_t need = sizeof(int32_t) * longest * ((size_t)W + 1);
-  if (need > ctx->comm_cap) {
-    CK(cudaStreamSynchronize(q));
-    cudaFree(ctx->comm_buf); ctx->comm_buf = nullptr; ctx->comm_cap = 0;
-    CK(cudaMalloc((void**)&ctx->comm_buf, need + need / 2));
-    ctx->comm_cap = need + need / 2;
-  }
-  int32_t* send = reinterpret_cast<int32_t*>(ctx->comm_buf);
-  int32_t* recv = send + longest;
-  // ---- pack: [verdict P][index A][timages A][ilen A][vlen A][coords 4A][normals 4A][scal 4A][images E][grids 2E][vimages VE][vgrids 2VE]
-  {
-    const int P = ev.P, A = ev.A, E = ev.E, VE = ev.VE;
-    int32_t* w = send;
-    auto put = [&](const void* src, size_t n) { cudaError_t e = n ? cudaMemcpyAsync(w, src, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, q) : cudaSuccess; w += n; return e; };
-    CK(put(ev.verdict.p, (size_t)P));
-    if (A > 0) {
-      k_add_scalar<<<(A + 255) / 256, 256, 0, q>>>(A, ev.index.p, shard_lo);
-      CK(put(ev.index.p, (size_t)A)); CK(put(ev.timages.p, (size_t)A));
-      k_offsets_to_len<<<(A + 255) / 256, 256, 0, q>>>(A, ev.img_off.p, w);
-      k_offsets_to_len<<<(A + 255) / 256, 256, 0, q>>>(A, ev.vimg_off.p, w + A);
-      ctx->launches += 3;
-      w += 2 * (size_t)A;
-      CK(put(ev.coords.p, (size_t)4 * A)); CK(put(ev.normals.p, (size_t)4 * A)); CK(put(ev.scal.p, (size_t)4 * A));
-      CK(put(ev.images.p, (size_t)E)); CK(put(ev.grids.p, (size_t)2 * E)); CK(put(ev.vimages.p, (size_t)VE)); CK(put(ev.vgrids.p, (size_t)2 * VE));
+  const int32_t* recv = nullptr;   // rank k's message starts at recv + k * recv_stride
+  size_t recv_stride = 0;
+  if (peer) {
+    if (sizeof(int32_t) * longest > pb.slot_bytes) {   // every rank sees the same sizes, so every rank takes this exit
+      pb.needed = sizeof(int32_t) * longest;
+      return fail(ctx, PMVSB_EGROW, "evaluate_allgather: the wave's message outgrew the peer mailbox slots");
     }
+    // ---- pack + scatter: one kernel stores this rank's message into every rank's mailbox, the last block raises the flags
+    WavePost w;
+    const int P = ev.P, A = ev.A, E = ev.E, VE = ev.VE;
+    int n = 0;
+    unsigned at = 0;
+    auto seg = [&](const void* src, size_t cnt, int xform, int arg) {
+      if (cnt == 0) return;
+      w.seg[n] = {reinterpret_cast<const int32_t*>(src), (unsigned)cnt, xform, arg};
+      w.start[n] = at;
+      at += (unsigned)cnt;
+      ++n;
+    };
+    seg(ev.verdict.p, (size_t)P, 0, 0);
+    if (A > 0) {
+      seg(ev.index.p, (size_t)A, 1, shard_lo); seg(ev.timages.p, (size_t)A, 0, 0);
+      seg(ev.img_off.p, (size_t)A, 2, 0); seg(ev.vimg_off.p, (size_t)A, 2, 0);
+      seg(ev.coords.p, (size_t)4 * A, 0, 0); seg(ev.normals.p, (size_t)4 * A, 0, 0); seg(ev.scal.p, (size_t)4 * A, 0, 0);
+      seg(ev.images.p, (size_t)E, 0, 0); seg(ev.grids.p, (size_t)2 * E, 0, 0); seg(ev.vimages.p, (size_t)VE, 0, 0); seg(ev.vgrids.p, (size_t)2 * VE, 0, 0);
+    }
+    for (int k = n; k < 12; ++k) w.seg[k] = {nullptr, 0u, 0, 0};
+    for (int k = n; k < 13; ++k) w.start[k] = at;
+    w.nseg = n > 0 ? n : 1; w.total = at; w.seq = pb.seq; w.done = pb.d_done; w.dst = dst;
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>(((size_t)at + 255) / 256, (size_t)ctx->sm_count * 8));
+    k_wave_post<<<blocks, 256, 0, q>>>(w);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    if ((r = peer_wait(ctx, 1, pb.seq))) return r;
+    recv = peer_slot(pb.own, pb.slot_bytes, 0);
+    recv_stride = pb.slot_bytes / sizeof(int32_t);
+  } else {
+    const size_t need = sizeof(int32_t) * longest * ((size_t)W + 1);
+    if (need > ctx->comm_cap) {
+      CK(cudaStreamSynchronize(q));
+      cudaFree(ctx->comm_buf); ctx->comm_buf = nullptr; ctx->comm_cap = 0;
+      CK(cudaMalloc((void**)&ctx->comm_buf, need + need / 2));
+      ctx->comm_cap = need + need / 2;
+    }
+    int32_t* send = reinterpret_cast<int32_t*>(ctx->comm_buf);
+    // ---- pack: [verdict P][index A][timages A][ilen A][vlen A][coords 4A][normals 4A][scal 4A][images E][grids 2E][vimages VE][vgrids 2VE]
+    {
+      const int P = ev.P, A = ev.A, E = ev.E, VE = ev.VE;
+      int32_t* w = send;
+      auto put = [&](const void* src, size_t n) { cudaError_t e = n ? cudaMemcpyAsync(w, src, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, q) : cudaSuccess; w += n; return e; };
+      CK(put(ev.verdict.p, (size_t)P));
+      if (A > 0) {
+        k_add_scalar<<<(A + 255) / 256, 256, 0, q>>>(A, ev.index.p, shard_lo);
+        CK(put(ev.index.p, (size_t)A)); CK(put(ev.timages.p, (size_t)A));
+        k_offsets_to_len<<<(A + 255) / 256, 256, 0, q>>>(A, ev.img_off.p, w);
+        k_offsets_to_len<<<(A + 255) / 256, 256, 0, q>>>(A, ev.vimg_off.p, w + A);
+        ctx->launches += 3;
+        w += 2 * (size_t)A;
+        CK(put(ev.coords.p, (size_t)4 * A)); CK(put(ev.normals.p, (size_t)4 * A)); CK(put(ev.scal.p, (size_t)4 * A));
+        CK(put(ev.images.p, (size_t)E)); CK(put(ev.grids.p, (size_t)2 * E)); CK(put(ev.vimages.p, (size_t)VE)); CK(put(ev.vgrids.p, (size_t)2 * VE));
+      }
+    }
+    ncclResult_t nr = api->AllGather(send, send + longest, longest, ncclInt32, ctx->comm, q);
+    if (nr != ncclSuccess) return fail(ctx, PMVSB_ECUDA, std::string("ncclAllGather: ") + api->GetErrorString(nr));
+    recv = send + longest;
+    recv_stride = longest;
   }
-  nr = api->AllGather(send, recv, longest, ncclInt32, ctx->comm, q);
-  if (nr != ncclSuccess) return fail(ctx, PMVSB_ECUDA, std::string("ncclAllGather: ") + api->GetErrorString(nr));
   // ---- unpack into the arrays of the whole wave
   const size_t A1 = (size_t)std::max<long long>(tA, 1), E1 = (size_t)std::max<long long>(tE, 1), V1 = (size_t)std::max<long long>(tVE, 1);
   pmvsb_ctx::EvalOut& o = ctx->ev_all;
@@ -3308,7 +3688,7 @@ int pmvsb_evaluate_allgather(pmvsb_ctx* ctx, int shard_lo, int total_candidates)
   size_t aP = 0, aA = 0, aE = 0, aV = 0;
   for (int k = 0; k < W; ++k) {
     const int P = meta[4 * k], A = meta[4 * k + 1], E = meta[4 * k + 2], VE = meta[4 * k + 3];
-    const int32_t* w = recv + (size_t)k * longest;
+    const int32_t* w = recv + (size_t)k * recv_stride;
     auto get = [&](void* dst, size_t n) { cudaError_t e = n ? cudaMemcpyAsync(dst, w, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, q) : cudaSuccess; w += n; return e; };
     CK(get(o.verdict.p + aP, (size_t)P));
     CK(get(o.index.p + aA, (size_t)A)); CK(get(o.timages.p + aA, (size_t)A));
@@ -3324,7 +3704,7 @@ int pmvsb_evaluate_allgather(pmvsb_ctx* ctx, int shard_lo, int total_candidates)
   CK(cudaStreamSynchronize(q));
   o.P = (int)tP; o.A = (int)tA; o.E = (int)tE; o.VE = (int)tVE; o.refined = ev.refined;
   std::swap(ctx->ev, ctx->ev_all);
-  ctx->exchanged_bytes += (double)sizeof(int32_t) * longest * W;
+  ctx->exchanged_bytes += (double)sizeof(int32_t) * (peer ? (double)(words((int)tP, (int)tA, (int)tE, (int)tVE)) : (double)longest * W);
   return PMVSB_OK;
 }
 

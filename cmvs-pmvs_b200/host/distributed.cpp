@@ -4,9 +4,11 @@
 //   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \
 //          --no-python cmvs-pmvs_b200/bin/pmvs2 prefix option.txt PATCH PSET
 // Every rank reads the same files and keeps the same cell bookkeeping; the candidates of each seed / expansion wave are
-// cut into contiguous shards, one per GPU, and the results of the ACCEPTED candidates are exchanged with one NCCL all-gather
-// (pmvsb_allgather) per wave.  Rank 0 writes the models.  A persistent TCP star through rank 0 carries the 128-byte NCCL id,
-// the per-wave message sizes, and -- with PMVSB_EXCHANGE=tcp -- the wave exchange itself.
+// cut into contiguous shards, one per GPU, and the results of the ACCEPTED candidates are exchanged once per wave: by default
+// every rank stores its message straight into the other ranks' GPU memory (CUDA IPC mailboxes over NVLink, pmvsb_peer_*),
+// with PMVSB_EXCHANGE=nccl through one NCCL all-gather.  Waves below PMVSB_SHARD_MIN candidates are evaluated whole on every
+// rank: no exchange at all.  Rank 0 writes the models.  A persistent TCP star through rank 0 carries the bring-up (the 64-byte
+// IPC handles or the 128-byte NCCL id) and -- with PMVSB_EXCHANGE=tcp -- the wave exchange itself.
 #include <arpa/inet.h>
 #include <netdb.h>
 #include <netinet/in.h>
@@ -51,10 +53,17 @@ Dist Dist::from_env() {
   d.master_addr = a && *a ? a : "127.0.0.1";
   d.port = env_int("MASTER_PORT", 29500) + 1017;   // MASTER_PORT itself belongs to the launcher's store
   if (d.port <= 0 || d.port > 65535) { std::cerr << "pmvs2: MASTER_PORT + 1017 = " << d.port << " is not a TCP port" << std::endl; std::exit(1); }
-  // PMVSB_EXCHANGE=tcp: the wave exchange goes over the rendezvous sockets instead of NCCL (ranks that share one GPU:
-  // NCCL refuses two ranks on one device; used by the 2-ranks-on-1-GPU test)
+  // PMVSB_EXCHANGE = peer (default): the ranks store their wave messages into each other's GPU memory (CUDA IPC mailboxes over
+  // NVLink; also works for ranks that share one GPU); nccl: one ncclAllGather per wave (NCCL refuses two ranks on one device);
+  // tcp: over the rendezvous sockets, host-staged
   const char* e = std::getenv("PMVSB_EXCHANGE");
-  d.tcp_exchange = e && std::string(e) == "tcp";
+  const std::string mode = e ? e : "";
+  if (mode.empty() || mode == "peer" || mode == "p2p") d.exchange = kPeer;
+  else if (mode == "nccl") d.exchange = kNccl;
+  else if (mode == "tcp") d.exchange = kTcp;
+  else { std::cerr << "pmvs2: PMVSB_EXCHANGE must be peer, nccl or tcp" << std::endl; std::exit(1); }
+  d.tcp_exchange = d.exchange == kTcp;
+  d.shard_min = std::max(0, env_int("PMVSB_SHARD_MIN", d.shard_min));
   return d;
 }
 

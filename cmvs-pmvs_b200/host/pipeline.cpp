@@ -288,7 +288,20 @@ void Pipeline::evaluate_range(std::vector<Candidate>& all, std::vector<int>& all
   if (gather) {
     // multi-GPU: every rank's accepted records all-gathered device to device (NCCL); from here on the whole wave is local
     Tick tk(this, "gpu.allgather_wave");
-    if (pmvsb_evaluate_allgather(gpu_, lo, (int)all.size())) die("evaluate_allgather");
+    int rc = pmvsb_evaluate_allgather(gpu_, lo, (int)all.size());
+    if (rc == PMVSB_EGROW) {
+      // the wave's message is larger than the mailbox slots (every rank sees the same sizes and arrives here): all ranks unmap,
+      // meet, re-export larger mailboxes, map again and repeat the exchange
+      const size_t need = pmvsb_peer_needed(gpu_);
+      if (pmvsb_peer_close(gpu_)) die("peer_close");
+      char token = 0;
+      std::vector<char> tokens(dist_.world);
+      dist_.allgather(&token, 1, tokens.data());
+      if (!peer_bringup(need + need / 2)) die("peer mailboxes (re-export)");
+      if (is_root()) std::cerr << "peer mailboxes re-exported with " << need + need / 2 << " bytes per slot" << std::endl;
+      rc = pmvsb_evaluate_allgather(gpu_, lo, (int)all.size());
+    }
+    if (rc) die("evaluate_allgather");
     if (pmvsb_evaluate_counts(gpu_, &nv, &A, &E, &VE)) die("evaluate_counts");
     cands = all.data(); verdict = all_verdict.data();
     v.resize(nv);
@@ -321,11 +334,14 @@ void Pipeline::evaluate(std::vector<Candidate>& cands, std::vector<int>& verdict
   const int P = (int)cands.size();
   verdict.assign(P, 1);
   if (P == 0) return;
+  // a small wave is evaluated whole on every rank: the evaluation is deterministic, so all ranks hold the same results without
+  // any exchange, and an exchange would cost more than the split saves (PMVSB_SHARD_MIN)
+  if (dist_.world == 1 || P < dist_.shard_min) { evaluate_range(cands, verdict, 0, P, false); return; }
   int lo = 0, hi = P;
   Dist::shard(P, dist_.world, dist_.rank, lo, hi);
-  const bool nccl = dist_.world > 1 && !dist_.tcp_exchange;
-  evaluate_range(cands, verdict, lo, hi, nccl);
-  if (dist_.world > 1 && !nccl) exchange_results(cands, verdict);   // PMVSB_EXCHANGE=tcp: host-side exchange over the rendezvous sockets
+  const bool device = !dist_.tcp_exchange;   // peer mailboxes or NCCL: the exchange happens between the GPUs' memories
+  evaluate_range(cands, verdict, lo, hi, device);
+  if (!device) exchange_results(cands, verdict);   // PMVSB_EXCHANGE=tcp: host-side exchange over the rendezvous sockets
 }
 
 // One message per rank and wave: the verdicts of its shard, then ONLY the accepted candidates' records (header, the
@@ -848,7 +864,9 @@ void Pipeline::write(const std::string& base, bool ply, bool patch, bool pset) {
   }
   for (const auto& kv : seconds_) std::cerr << "time " << kv.first << ' ' << kv.second << " s" << std::endl;
   if (dist_.world > 1 && !dist_.tcp_exchange) exchanged_bytes_ = pmvsb_exchanged_bytes(gpu_);
-  if (dist_.world > 1) std::cerr << "exchange " << dist_.world << " ranks, " << exchanged_bytes_ / 1.0e6 << " MB all-gathered over " << (dist_.tcp_exchange ? "tcp" : "nccl") << std::endl;
+  if (dist_.world > 1) std::cerr << "exchange " << dist_.world << " ranks, " << exchanged_bytes_ / 1.0e6 << " MB all-gathered over "
+                                 << (dist_.exchange == Dist::kTcp ? "tcp" : dist_.exchange == Dist::kPeer ? "peer memory (CUDA IPC mailboxes)" : "nccl")
+                                 << ", waves below " << dist_.shard_min << " candidates evaluated whole on every rank" << std::endl;
 }
 
 }  // namespace pmvs

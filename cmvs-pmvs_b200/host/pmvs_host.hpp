@@ -60,7 +60,12 @@ Options parse_options(const std::string& prefix, const std::string& option);
 // one process per GPU (distributed.cpp); world = 1 is the ordinary single-GPU run
 struct Dist {
   int rank = 0, world = 1, local_rank = 0, port = 0;
-  bool tcp_exchange = false;      // PMVSB_EXCHANGE=tcp: wave exchange over the sockets below instead of NCCL
+  // how a wave's results travel between the ranks (PMVSB_EXCHANGE): peer = stores into each other's GPU memory over NVLink
+  // (CUDA IPC mailboxes, the default), nccl = one ncclAllGather per wave, tcp = over the rendezvous sockets below
+  enum Exchange { kPeer, kNccl, kTcp };
+  Exchange exchange = kPeer;
+  bool tcp_exchange = false;      // exchange == kTcp
+  int shard_min = 4096;           // PMVSB_SHARD_MIN: waves with fewer candidates are evaluated whole on every rank (no exchange)
   std::string master_addr;
   std::vector<int> fds;           // rank 0: one socket per peer (index = rank); peers: fds[0] = the socket to rank 0
   static Dist from_env();
@@ -146,6 +151,7 @@ class Pipeline {
   void evaluate(std::vector<Candidate>& cands, std::vector<int>& verdict);
   void evaluate_range(std::vector<Candidate>& cands, std::vector<int>& verdict, int lo, int hi, bool gather);
   void exchange_results(std::vector<Candidate>& cands, std::vector<int>& verdict);
+  bool peer_bringup(size_t slot_bytes);   // maps the ranks' mailboxes into each other (setup.cpp); the same answer on every rank
   void die(const std::string& where) const;
 
   Options opt_;

@@ -298,17 +298,28 @@ void Pipeline::load() {
   { Tick tk2(this, "load.wait_for_files"); reader.join(); }
   if (created != 0)
     fatal("pmvs-b200: cannot create a GPU context (CUDA device required; there is no CPU fallback) or bad options");
-  // NCCL communicator over the GPUs of this run: brought up on its own thread while the images go to the GPU (ncclCommInitRank
-  // takes 0.5 - 1.5 s on a warm box); joined at the end of load()
+  // The exchange between the GPUs of this run is brought up on its own thread while the images go to the GPU; joined at the end
+  // of load().  Peer mailboxes (default): export mine, gather every rank's 64-byte handle over the rendezvous sockets, map them
+  // -- tens of milliseconds.  NCCL (PMVSB_EXCHANGE=nccl, or when a rank cannot map a peer): ncclCommInitRank, 0.5 - 1.5 s.
   std::thread nccl_init;
   double nccl_seconds = 0.0;   // written by the thread, read after the join
   const auto t_nccl = std::chrono::steady_clock::now();
-  if (dist_.world > 1 && !dist_.tcp_exchange)
+  if (dist_.world > 1 && dist_.exchange != Dist::kTcp)
     nccl_init = std::thread([&]() {
-      uint8_t id[128] = {0};
-      if (dist_.rank == 0 && pmvsb_comm_unique_id(gpu_, id)) die("comm_unique_id");
-      dist_.broadcast_from_root(id, sizeof(id));
-      if (pmvsb_comm_init(gpu_, dist_.rank, dist_.world, id)) die("comm_init");
+      if (dist_.exchange == Dist::kPeer) {
+        const char* mb = std::getenv("PMVSB_PEER_SLOT_MB");
+        const size_t slot = std::max<size_t>(4096, (size_t)((mb && *mb ? std::atof(mb) : 64.0) * 1048576.0));   // grows on demand (PMVSB_EGROW)
+        if (!peer_bringup(slot)) {
+          if (is_root()) std::cerr << "pmvs2: the GPUs of this run cannot map each other's memory (" << pmvsb_last_error(gpu_) << "); falling back to NCCL" << std::endl;
+          dist_.exchange = Dist::kNccl;
+        }
+      }
+      if (dist_.exchange == Dist::kNccl) {
+        uint8_t id[128] = {0};
+        if (dist_.rank == 0 && pmvsb_comm_unique_id(gpu_, id)) die("comm_unique_id");
+        dist_.broadcast_from_root(id, sizeof(id));
+        if (pmvsb_comm_init(gpu_, dist_.rank, dist_.world, id)) die("comm_init");
+      }
       nccl_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_nccl).count();
     });
   cams_.resize(num_);
@@ -390,9 +401,27 @@ void Pipeline::load() {
   }
   detect_features();
   if (nccl_init.joinable()) {
-    { Tick tk2(this, "load.wait_for_nccl"); nccl_init.join(); }
-    seconds_["load.nccl_init(background)"] += nccl_seconds;
+    { Tick tk2(this, "load.wait_for_exchange"); nccl_init.join(); }
+    seconds_[dist_.exchange == Dist::kPeer ? "load.peer_mailboxes(background)" : "load.nccl_init(background)"] += nccl_seconds;
   }
+}
+
+// Every rank (re)allocates its mailbox with `slot_bytes` per rank, the 64-byte IPC handles go round the rendezvous sockets (which is
+// also the barrier: every mailbox exists before anybody maps it), every rank maps the others'.  All ranks return the same
+// answer: true only when every rank mapped every peer (a rank that failed still takes part in the two exchanges).
+bool Pipeline::peer_bringup(size_t slot_bytes) {
+  const int W = dist_.world;
+  uint8_t mine[PMVSB_PEER_HANDLE_BYTES] = {0};
+  int32_t ok = pmvsb_peer_export(gpu_, dist_.rank, W, slot_bytes, mine) == 0 ? 1 : 0;
+  std::vector<uint8_t> all((size_t)PMVSB_PEER_HANDLE_BYTES * W);
+  dist_.allgather(mine, sizeof(mine), all.data());
+  if (ok) ok = pmvsb_peer_open(gpu_, all.data()) == 0 ? 1 : 0;
+  std::vector<int32_t> oks(W, 0);
+  dist_.allgather(&ok, sizeof(ok), oks.data());
+  bool every = true;
+  for (int k = 0; k < W; ++k) every = every && oks[k] == 1;
+  if (!every) pmvsb_peer_close(gpu_);
+  return every;
 }
 
 // ---------------------------------------------------------------------------------------------- features

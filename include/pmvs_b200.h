@@ -43,6 +43,9 @@ extern "C" {
 
 #define PMVSB_MAX_TAU 8     /* views used by refinePatch / computeINCC (tau = min(2*minImageNum, num)) */
 #define PMVSB_MAX_VIEWS 64  /* views per patch accepted by set_inccs / pre- and post-process kernels */
+#define PMVSB_EGROW (-6)    /* a wave's message is larger than the peer mailbox slots: re-export with pmvsb_peer_needed() bytes and call again */
+#define PMVSB_MAX_RANKS 16  /* ranks of one peer-memory exchange (GPUs of one NVLink domain) */
+#define PMVSB_PEER_HANDLE_BYTES 64
 
 typedef struct pmvsb_ctx pmvsb_ctx;
 
@@ -317,10 +320,43 @@ int pmvsb_comm_init(pmvsb_ctx* ctx, int rank, int world, const uint8_t* id128);
 /* host buffers: send = bytes, recv = world * bytes in rank order; identity copy when no communicator (world = 1) */
 int pmvsb_allgather(pmvsb_ctx* ctx, const void* send, size_t bytes, void* recv);
 
+/* Peer-memory exchange (the default of a multi-GPU pmvs2 run; NCCL stays as the fallback).  Every rank owns a mailbox in its
+ * GPU's memory -- a header of flags plus one slot per rank -- which the other ranks map into their address space through CUDA
+ * IPC.  A wave's message is then written by ONE kernel straight into every rank's mailbox (peer stores over NVLink / NVSwitch,
+ * the message being packed from the result arrays on the fly), followed by a system-scope fence and a flag; the receiver
+ * waits for the flags of all ranks and unpacks from its own memory.  No communicator bring-up, no staging copies, no
+ * collective launch.
+ *   pmvsb_peer_export : (re)allocates this rank's mailbox with `slot_bytes` per rank and returns its 64-byte IPC handle;
+ *   pmvsb_peer_open   : handles = world * 64 bytes in rank order (any channel carries them); maps the peers' mailboxes.  After it
+ *                       pmvsb_evaluate_allgather uses the mailboxes.  Fails (PMVSB_ECUDA) where the GPUs cannot reach each other;
+ *   pmvsb_peer_close  : unmaps the peers' mailboxes (before a re-export: every rank closes, then every rank exports again);
+ *   pmvsb_peer_needed : slot size in bytes that the wave which returned PMVSB_EGROW needs.
+ * Ranks may share one GPU (the handles of another PROCESS on the same device open like any other). */
+int pmvsb_peer_export(pmvsb_ctx* ctx, int rank, int world, size_t slot_bytes, uint8_t* handle64);
+int pmvsb_peer_open(pmvsb_ctx* ctx, const uint8_t* handles);
+int pmvsb_peer_close(pmvsb_ctx* ctx);
+size_t pmvsb_peer_needed(const pmvsb_ctx* ctx);
+
+/* pmvsb_refine_batch_dev followed by the all-gather of the refined records over peer memory (what the reference's worker threads
+ * get for free from shared memory, source/pmvs/expand.cpp:225-237: every worker sees every accepted patch).  One kernel after
+ * the refine kernel packs each patch's 48-byte record -- coord[4], normal[4], ncc, ok, evaluations, 0 as floats -- from the
+ * result arrays and stores it into this rank's slot of EVERY rank's mailbox (coalesced 16-byte peer stores over NVLink), its
+ * last block raises a flag in every mailbox, and a stream-ordered wait for all ranks' flags is queued (cuStreamWaitValue32: the
+ * host does not block, no collective is launched).  PMVSB_GATHER_IN_KERNEL=1 moves the stores into the refine kernel itself
+ * (each finished patch's leader lane posts its record underneath the evaluations still running) -- measured 1 % slower, kept
+ * for A/B.  Work queued on the context's stream after this call sees the records of all ranks: rank k's record p at
+ * *records + k * *rank_stride_floats + 12 * p.  Slots are used as two halves by call parity, so the records of one call stay
+ * valid until the call after the next.  Needs pmvsb_peer_export (slot_bytes >= 2 * 48 * n; world 1 allowed) and, for
+ * world > 1, pmvsb_peer_open; every rank must call it the same number of times.  PMVSB_EGROW as above. */
+int pmvsb_refine_batch_dev_gather(pmvsb_ctx* ctx, int n, int stride, float* coords, float* normals, const int32_t* images,
+                                  const int32_t* nimages, const float* dscales, float* ncc, int32_t* evals, uint8_t* ok,
+                                  const float** records, size_t* rank_stride_floats);
+
 /* The wave exchange, device to device: after pmvsb_evaluate_batch on this rank's contiguous shard [shard_lo, shard_lo + P) of a
  * wave of total_candidates, every rank calls this; the accepted candidates' records of all ranks (and all verdicts) are
- * all-gathered by ONE ncclAllGather straight from device memory and pmvsb_evaluate_fetch then returns the WHOLE wave, `index`
- * being wave-wide candidate numbers.  No-op without a communicator of more than one rank. */
+ * all-gathered -- through the peer mailboxes when pmvsb_peer_open succeeded, else by ONE ncclAllGather straight from device
+ * memory -- and pmvsb_evaluate_fetch then returns the WHOLE wave, `index` being wave-wide candidate numbers.  No-op without a
+ * communicator of more than one rank.  PMVSB_EGROW: see pmvsb_peer_needed. */
 int pmvsb_evaluate_allgather(pmvsb_ctx* ctx, int shard_lo, int total_candidates);
 /* sizes of what pmvsb_evaluate_fetch will return (after pmvsb_evaluate_batch or pmvsb_evaluate_allgather) */
 int pmvsb_evaluate_counts(pmvsb_ctx* ctx, int32_t* candidates, int32_t* accepted, int32_t* entries, int32_t* ventries);

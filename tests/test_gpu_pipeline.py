@@ -94,46 +94,64 @@ def test_bad_input_exits_1(tmp_path):
     assert p.returncode == 1 and "Usage" in (p.stderr + p.stdout)
 
 
-def test_two_gpus_write_the_same_models(run, pkg, scene, tmp_path_factory):
-    """One process per GPU (WORLD_SIZE 2): wave shards + NCCL all-gather of the results.  Every candidate is evaluated
-    by exactly one rank with the same kernels, every rank commits the same wave: the models are byte-identical."""
+def _same_models(prefix1, prefix2):
+    for ext in (".patch", ".pset", ".ply"):
+        a = open(prefix1 + "models/option.txt" + ext, "rb").read()
+        b = open(prefix2 + "models/option.txt" + ext, "rb").read()
+        assert a == b, ext
+
+
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_two_gpus_write_the_same_models(exchange, run, pkg, scene, tmp_path_factory):
+    """One process per GPU (WORLD_SIZE 2): wave shards + the exchange of the accepted candidates' records between the GPUs' memories
+    (peer = every rank stores its message into the other's mailbox over NVLink, CUDA IPC; nccl = one ncclAllGather per wave).
+    Every candidate is evaluated by exactly one rank with the same kernels, every rank commits the same wave: the models are
+    byte-identical to the single-GPU run.  PMVSB_SHARD_MIN=0: every wave of this small scene is cut (the default leaves waves
+    below 4096 candidates whole)."""
     import sys
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     G, prefix1, _ = run
     scene.option["CPU"] = os.cpu_count() or 4
-    prefix2 = pkg.synth.write_scene(scene, str(tmp_path_factory.mktemp("pmvs2_scene_2gpu")))
+    prefix2 = pkg.synth.write_scene(scene, str(tmp_path_factory.mktemp("pmvs2_scene_2gpu_" + exchange)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29731", "--no-python", PMVS2, prefix2, "option.txt", "PATCH", "PSET"]
-    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+           "--master-port", "29731" if exchange == "peer" else "29735", "--no-python", PMVS2, prefix2, "option.txt", "PATCH", "PSET"]
+    env = dict(os.environ, PMVSB_EXCHANGE=exchange, PMVSB_SHARD_MIN="0")
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, env=env)
     assert p.returncode == 0, p.stderr[-3000:]
-    for ext in (".patch", ".pset", ".ply"):
-        a = open(prefix1 + "models/option.txt" + ext, "rb").read()
-        b = open(prefix2 + "models/option.txt" + ext, "rb").read()
-        assert a == b, ext
+    _same_models(prefix1, prefix2)
     assert "gpu.allgather_wave" in p.stderr
+    assert ("over peer memory" if exchange == "peer" else "over nccl") in p.stderr, p.stderr[-2000:]
 
 
-def test_two_ranks_on_one_gpu_write_the_same_models(run, pkg, scene, tmp_path_factory):
-    """The multi-rank path on ANY box: two pmvs2 processes share GPU 0 (each with its own context and table), every wave is cut
-    into two shards, the accepted candidates' records are exchanged (PMVSB_EXCHANGE=tcp: NCCL refuses two ranks on one device;
-    the message format and everything after it are the NCCL path's), both ranks commit the same wave.  The models must be
-    byte-identical to the single-process run."""
+@pytest.mark.parametrize("mode", ["peer", "peer-grow", "peer-mixed", "tcp"])
+def test_two_ranks_on_one_gpu_write_the_same_models(mode, run, pkg, scene, tmp_path_factory):
+    """The multi-rank path on ANY box: two pmvs2 processes share GPU 0 (each with its own context and table), the waves are cut
+    into two shards, the accepted candidates' records are exchanged, both ranks commit the same wave.  The models must be
+    byte-identical to the single-process run.
+      peer       : the default exchange -- CUDA IPC mailboxes, each rank's kernel stores its message into the other process's
+                   memory (the same code as between two GPUs; NCCL refuses two ranks on one device);
+      peer-grow  : mailboxes of 16 KB per slot, so the larger waves return PMVSB_EGROW and the ranks re-export and re-map;
+      peer-mixed : waves below 1500 candidates are evaluated whole on both ranks (no exchange), the others are cut;
+      tcp        : the host-staged exchange over the rendezvous sockets."""
     import sys
     G, prefix1, _ = run
     scene.option["CPU"] = max(1, (os.cpu_count() or 4) // 2)
-    prefix2 = pkg.synth.write_scene(scene, str(tmp_path_factory.mktemp("pmvs2_scene_2ranks")))
+    prefix2 = pkg.synth.write_scene(scene, str(tmp_path_factory.mktemp("pmvs2_scene_2ranks_" + mode.replace("-", "_"))))
+    port = {"peer": "29753", "peer-grow": "29757", "peer-mixed": "29761", "tcp": "29765"}[mode]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29753", "--no-python", PMVS2, prefix2, "option.txt", "PATCH", "PSET"]
-    env = dict(os.environ, PMVSB_EXCHANGE="tcp", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+           "--master-port", port, "--no-python", PMVS2, prefix2, "option.txt", "PATCH", "PSET"]
+    env = dict(os.environ, PMVSB_EXCHANGE="tcp" if mode == "tcp" else "peer", PMVSB_SHARD_MIN="1500" if mode == "peer-mixed" else "0",
+               PMVSB_PEER_TIMEOUT_S="60", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+    if mode == "peer-grow":
+        env["PMVSB_PEER_SLOT_MB"] = "0.015625"
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900, env=env)
     assert p.returncode == 0, p.stderr[-3000:]
-    for ext in (".patch", ".pset", ".ply"):
-        a = open(prefix1 + "models/option.txt" + ext, "rb").read()
-        b = open(prefix2 + "models/option.txt" + ext, "rb").read()
-        assert a == b, ext
-    assert "exchange 2 ranks" in p.stderr and "over tcp" in p.stderr
+    _same_models(prefix1, prefix2)
+    assert "exchange 2 ranks" in p.stderr and ("over tcp" if mode == "tcp" else "over peer memory") in p.stderr, p.stderr[-2000:]
+    if mode == "peer-grow":
+        assert "mailboxes re-exported" in p.stderr, p.stderr[-2000:]
 
 
 @pytest.mark.parametrize("name", ["oimages", "visdata", "sequence", "enumerated"])

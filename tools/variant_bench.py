@@ -55,6 +55,28 @@ def main():
             name, ["%.1f" % m for m in ms], P / (min(ms) / 1e3) / 1e6, float(d_ev.float().mean()), float(d_ok.float().mean()),
             float(np.abs(ncc - ref[0]).max()), float((cur[1] == ref[1]).mean()),
             "BIT-IDENTICAL to first (ncc, evals, coords, normals)" if same else "differs from first"), flush=True)
+        if hasattr(lib.lib, "pmvsb_refine_batch_dev_gather"):
+            # the same batch through the kernel variant that also posts every record to the mailboxes (world 1: its own memory)
+            lib.peer_export(0, 1, 2 * (P * 48 + 256))
+            for form in ("0", "1"):      # 0: one scatter kernel after the refine kernel (default), 1: stores inside the refine kernel
+                os.environ["PMVSB_GATHER_IN_KERNEL"] = form
+                gms, wall = [], []
+                for r in range(a.reps + 1):
+                    d_c.copy_(d_c0); d_n.copy_(d_n0)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    st = torch.cuda.ExternalStream(lib.stream())
+                    e0.record(st)
+                    lib.refine_batch_dev_gather(P, 5, d_c.data_ptr(), d_n.data_ptr(), d_im.data_ptr(), 0, d_ds.data_ptr(), d_ncc.data_ptr(), d_ev.data_ptr(), d_ok.data_ptr())
+                    e1.record(st)
+                    lib.sync()
+                    if r > 0:
+                        gms.append(lib.last_refine_ms()); wall.append(e0.elapsed_time(e1))
+                got = (d_ncc.cpu().numpy(), d_ev.cpu().numpy(), d_c.cpu().numpy(), d_n.cpu().numpy())
+                print("%-22s   + record gather, %s (world 1): refine kernel ms %s, whole call ms %s, %s" % (
+                      name, "stores inside the refine kernel" if form == "1" else "scatter kernel after it", ["%.2f" % m for m in gms], ["%.2f" % m for m in wall],
+                      "BIT-IDENTICAL to the plain kernel" if all(np.array_equal(x, y) for x, y in zip(got, cur)) else "differs from the plain kernel"), flush=True)
+            os.environ.pop("PMVSB_GATHER_IN_KERNEL", None)
         lib.close()
 
 
