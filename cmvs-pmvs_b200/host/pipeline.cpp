@@ -219,12 +219,19 @@ void Pipeline::sync_table(bool full) {
   int32_t P = 0, E = 0, VE = 0;
   if (pmvsb_store_counts(gpu_, &P, &E, &VE)) die("store_counts");
   if (P != (int)table_ids_.size()) { std::cerr << "sync_table: table size mismatch" << std::endl; std::exit(1); }
-  std::vector<int32_t> seq(std::max(P, 1)), ti(std::max(P, 1)), off(P + 1), im(std::max(E, 1)), gr((size_t)2 * std::max(E, 1)), voff(P + 1),
-      vim(std::max(VE, 1)), vgr((size_t)2 * std::max(VE, 1));
+  // staging reused from call to call (a fresh vector of this size is zero-filled and page-faulted in every time)
+  static std::vector<int32_t> seq, ti, off, im, gr, voff, vim, vgr;
+  auto room = [](std::vector<int32_t>& v, size_t n) { if (v.size() < n) v.resize(n + n / 4); };
+  room(seq, (size_t)std::max(P, 1)); room(ti, (size_t)std::max(P, 1)); room(off, (size_t)P + 1); room(im, (size_t)std::max(E, 1)); room(gr, (size_t)2 * std::max(E, 1));
+  { Tick tk2(this, "host.sync_table.download");
   if (pmvsb_store_download_lists(gpu_, seq.data(), ti.data(), off.data(), im.data(), gr.data())) die("store_download_lists");
   // between rounds the host only needs the image lists (parents of the next expansion) and the occupancy of _pgrids; the
   // per-patch cells and visible-image lists are read by the writers only (full = true, once, from write())
-  if (full && pmvsb_store_download_vimages(gpu_, voff.data(), vim.data(), vgr.data())) die("store_download_vimages");
+  if (full) {
+    room(voff, (size_t)P + 1); room(vim, (size_t)std::max(VE, 1)); room(vgr, (size_t)2 * std::max(VE, 1));
+    if (pmvsb_store_download_vimages(gpu_, voff.data(), vim.data(), vgr.data())) die("store_download_vimages");
+  } }
+  { Tick tk2(this, "host.sync_table.lists");
   for (Patch& p : patches_) p.alive = false;
   parallel_for(P, threads_, [&](int k) {
     if (seq[k] != table_ids_[k]) { std::cerr << "sync_table: the device and host numberings disagree" << std::endl; std::exit(1); }
@@ -240,9 +247,13 @@ void Pipeline::sync_table(bool full) {
     p.vgrids.resize(nv);
     for (int i = 0; i < nv; ++i) p.vgrids[i] = {vgr[(size_t)2 * (voff[k] + i)], vgr[(size_t)2 * (voff[k] + i) + 1]};
   }, 1024);
+  }
+  Tick tk3(this, "host.sync_table.occupancy");
   parallel_for(tnum_, threads_, [&](int t) { std::fill(grids_[t].occ.begin(), grids_[t].occ.end(), 0); }, 1);
-  for (int e = 0; e < E; ++e)
-    if (im[e] < tnum_) ++grids_[im[e]].occ[(size_t)gr[(size_t)2 * e + 1] * grids_[im[e]].gw + gr[(size_t)2 * e]];
+  // one relaxed atomic increment per (patch, image) entry: entries of one cell are far apart in the list, so the threads rarely meet
+  parallel_for(E, threads_, [&](int e) {
+    if (im[e] < tnum_) __atomic_fetch_add(&grids_[im[e]].occ[(size_t)gr[(size_t)2 * e + 1] * grids_[im[e]].gw + gr[(size_t)2 * e]], 1, __ATOMIC_RELAXED);
+  }, 1 << 16);
 }
 
 // CPatchOrganizerS::addPatch + updateDepthMaps for patches committed since the table was uploaded
@@ -598,7 +609,12 @@ void Pipeline::expand_round() {
   int wave_no = 0;
   size_t last_table_size = patches_.size();
   while (!frontier.empty()) {
-    std::stable_sort(frontier.begin(), frontier.end(), [&](int a, int b) { return patches_[a].tmp > patches_[b].tmp; });
+    { Tick tk2(this, "host.expand.sort_frontier");
+      // (key, id) pairs: the comparison reads contiguous memory instead of two Patch records per call
+      std::vector<std::pair<float, int>> keyed(frontier.size());
+      for (size_t k = 0; k < frontier.size(); ++k) keyed[k] = {patches_[frontier[k]].tmp, frontier[k]};
+      std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first > b.first; });
+      for (size_t k = 0; k < frontier.size(); ++k) frontier[k] = keyed[k].second; }
     std::vector<Candidate> wave;
     // findEmptyBlocks (expand.cpp:108-180): the neighbour search of every frontier patch is one kernel over the resident
     // table; it returns the directions that already have a neighbour and computeRadius
@@ -653,8 +669,12 @@ void Pipeline::expand_round() {
       }
     }, 256);
     }
-    for (auto& v : per_parent) for (auto& c : v) wave.push_back(std::move(c));
-    per_parent.clear();
+    { Tick tk2(this, "host.expand.concat");
+      size_t total = 0;
+      for (auto& v : per_parent) total += v.size();
+      wave.reserve(total);
+      for (auto& v : per_parent) for (auto& c : v) wave.push_back(std::move(c));
+      per_parent.clear(); }
     std::vector<int> verdict;
     evaluate(wave, verdict);
     // commit in parent-priority order; cells may have been taken by an earlier commit of this wave
