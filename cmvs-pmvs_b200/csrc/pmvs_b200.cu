@@ -705,6 +705,7 @@ struct pmvsb_ctx {
   DVec<float> d_fxy;
   DVec<int32_t> d_ftype, d_fcell_base, d_fcell_off, d_flist, d_fgw, d_fgh;
   DVec<uint8_t> d_blocked;
+  std::vector<uint8_t> h_blocked_shadow;   // what d_blocked holds (pmvsb_seed_candidates uploads only the blocks that changed)
   DVec<SeedHit> d_seed_out;
   // results of the last pmvsb_evaluate_batch, kept on the device until pmvsb_evaluate_fetch
   struct EvalOut {
@@ -2194,7 +2195,30 @@ int pmvsb_seed_candidates(pmvsb_ctx* ctx, int index, int nviews, const int32_t* 
   sd.fxy = ctx->d_fxy.p; sd.ftype = ctx->d_ftype.p; sd.fcell_base = ctx->d_fcell_base.p; sd.fcell_off = ctx->d_fcell_off.p; sd.flist = ctx->d_flist.p;
   sd.gw = ctx->d_fgw.p; sd.gh = ctx->d_fgh.p;
   const int allcells = ctx->h_fcell_base[ctx->num];
-  if ((r = dvec_put(ctx, ctx->d_blocked, 0, blocked, (size_t)allcells))) return r;
+  // `blocked` covers every cell of every image (24 MB for a 32-view 4000x3000 cluster) and changes in a few places between two
+  // calls of a seed round: the device copy is brought up to date from a host shadow, 16 KB blocks that differ travelling as runs
+  {
+    std::vector<uint8_t>& shadow = ctx->h_blocked_shadow;
+    if (shadow.size() != (size_t)allcells || !ctx->d_blocked.p || ctx->d_blocked.cap < (size_t)allcells) {
+      if ((r = dvec_put(ctx, ctx->d_blocked, 0, blocked, (size_t)allcells))) return r;
+      shadow.assign(blocked, blocked + allcells);
+    } else {
+      const size_t B = 16384;
+      size_t run_lo = 0, run_hi = 0;   // pending run [run_lo, run_hi)
+      for (size_t at = 0; at < (size_t)allcells; at += B) {
+        const size_t n = std::min(B, (size_t)allcells - at);
+        if (std::memcmp(shadow.data() + at, blocked + at, n) != 0) {
+          std::memcpy(shadow.data() + at, blocked + at, n);
+          if (run_hi == at && run_hi > run_lo) run_hi = at + n;
+          else {
+            if (run_hi > run_lo) CK(cudaMemcpyAsync(ctx->d_blocked.p + run_lo, shadow.data() + run_lo, run_hi - run_lo, cudaMemcpyHostToDevice, ctx->stream));
+            run_lo = at; run_hi = at + n;
+          }
+        }
+      }
+      if (run_hi > run_lo) CK(cudaMemcpyAsync(ctx->d_blocked.p + run_lo, shadow.data() + run_lo, run_hi - run_lo, cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
   DevBuf<int32_t> dfeat, dcount, dstart, dmisc;
   CK(dfeat.alloc(R)); CK(dcount.alloc(R)); CK(dstart.alloc(R)); CK(dmisc.alloc(4));
   CK(cudaMemcpyAsync(dfeat.p, feats.data(), sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice, ctx->stream));

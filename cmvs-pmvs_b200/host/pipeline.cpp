@@ -263,10 +263,11 @@ void Pipeline::append_table(const std::vector<int>& ids) {
   table_index_.resize(patches_.size(), -1);
   const int first = (int)table_ids_.size();
   for (int id : ids) { table_index_[id] = (int)table_ids_.size(); table_ids_.push_back(id); }
-  TableArrays t;
-  marshal(ids, t);
+  static TableArrays t;   // reused from wave to wave (marshal sizes every array)
+  { Tick tk2(this, "gpu.append_table.marshal"); marshal(ids, t); }
+  { Tick tk2(this, "gpu.append_table.store_append");
   if (pmvsb_store_append(gpu_, (int)ids.size(), t.coords.data(), t.normals.data(), t.ncc.data(), t.dsc.data(), t.ioff.data(), t.images.data(),
-                         t.grids.data(), t.voff.data(), t.vimages.data(), t.vgrids.data(), t.timages.data())) die("store_append");
+                         t.grids.data(), t.voff.data(), t.vimages.data(), t.vgrids.data(), t.timages.data())) die("store_append"); }
   if (pmvsb_store_set_seq(gpu_, first, (int)ids.size(), ids.data())) die("store_set_seq");
 }
 
@@ -492,6 +493,7 @@ void Pipeline::seed_round() {
       if ((int)sc_ref.size() < 4 * 65536) sc_ref.resize(4 * 65536);
       for (int attempt = 0; attempt < 3; ++attempt) {
         const int cap_ref = (int)sc_ref.size() / 4, cap = (int)sc_other.size();
+        Tick tk3(this, "gpu.seed.candidates.call");
         if (pmvsb_seed_candidates(gpu_, index, (int)indexes.size(), indexes.data(), blocked.data(), cap_ref, &nref, sc_ref.data(), sc_ref.data() + cap_ref,
                                   sc_ref.data() + 2 * cap_ref, sc_ref.data() + 3 * cap_ref, cap, &total, sc_coord.data(), sc_other.data(),
                                   sc_other_feat.data(), sc_resp.data())) die("seed_candidates");

@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--reference", type=int, default=-1, help="also time the reference binary on this cluster")
     ap.add_argument("--prefix", default="/tmp/pmvs_large256")
     ap.add_argument("--out", default="")
+    ap.add_argument("--logs", default="", help="directory that receives the per-cluster pmvs2 logs (phase clocks) of the last run")
     a = ap.parse_args()
     import torch
     ngpu = torch.cuda.device_count()
@@ -127,6 +128,12 @@ def main():
         with open(a.out, "w") as f:
             f.write(text + "\n")
     print(text)
+    if a.logs:
+        os.makedirs(a.logs, exist_ok=True)
+        for c in only:
+            src = prefix + "models/option-%04d.log" % c
+            if os.path.exists(src):
+                shutil.copy(src, os.path.join(a.logs, "large256_option-%04d.log" % c))
     shutil.rmtree(prefix, ignore_errors=True)
 
 
