@@ -1,7 +1,7 @@
 # round-2 measurement: tests, bench line (both arms), ncu launch list of the bench command, one --set full capture of the hot kernel,
 # the launch list of one pmvs2 run on the config-3 scene.  Numbers printed under ncu are never bench values.
 set -x
-python -m pytest tests -m gpu -q 2>&1 | tail -4
+python -m pytest tests -m gpu -q > gpurun_out/r2_final_tests.log 2>&1; tail -4 gpurun_out/r2_final_tests.log
 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err; echo "reference arm rc=$?"
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 600 --csv --log-file gpurun_out/r2_bench_launches_ncu.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-pipeline > gpurun_out/r2_ncu_launch.log 2>&1; echo "launch list rc=$?"
