@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--reference", type=int, default=-1, help="also time the reference binary on this cluster")
     ap.add_argument("--prefix", default="/tmp/pmvs_large256")
     ap.add_argument("--out", default="")
+    ap.add_argument("--settle", type=float, default=0.0, help="seconds to wait after the scene has been rendered, so that the timed runs do not start inside the renderers' teardown")
     ap.add_argument("--logs", default="", help="directory that receives the per-cluster pmvs2 logs (phase clocks) of the last run")
     a = ap.parse_args()
     import torch
@@ -103,6 +104,9 @@ def main():
         if c not in only:
             os.remove(prefix + "option-%04d" % c)
     gpus = [int(x) for x in a.gpus.split(",") if x] or sorted({1, max(1, ngpu)})
+    if a.settle > 0:
+        time.sleep(a.settle)
+    res["settle_seconds"] = a.settle
     for G in gpus:
         if G > max(1, ngpu):
             continue
