@@ -1,6 +1,7 @@
 """The other option shapes BASELINE.json names, stage by stage against the CPU oracle: wsize 5 and 9 (the KG<5> group kernels and
 the warp-per-patch k_refine<9> / k_score<9> dispatch arms) and config 2's shape, level 0 / csize 1 (the pyramid-level pick
-clamps at -level = 0, a cell is a pixel).  Same bars as tests/test_gpu_parity.py and tests/test_gpu_select.py."""
+clamps at -level = 0, a cell is a pixel).  Same bars as tests/test_gpu_parity.py and tests/test_gpu_select.py.  The oracle itself
+is pinned on the reference at these shapes and on these patches by tests/test_oracle_shapes.py (golden: pmvs_shapes.npz)."""
 import copy
 
 import numpy as np
