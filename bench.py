@@ -485,25 +485,33 @@ def main():
     # ---- end to end through the host-pointer ABI call ------------------------------------------------
     h_coords = torch.from_numpy(coords).pin_memory(); h_normals = torch.from_numpy(normals).pin_memory()
     h_images = torch.from_numpy(images).pin_memory(); h_dsc = torch.from_numpy(dsc).pin_memory()
-    w_coords = torch.empty_like(h_coords).pin_memory(); w_normals = torch.empty_like(h_normals).pin_memory()
     h_ncc = torch.empty(P, dtype=torch.float32).pin_memory(); h_evals = torch.empty(P, dtype=torch.int32).pin_memory()
     h_ok = torch.empty(P, dtype=torch.uint8).pin_memory()
     import ctypes as C
     vp = lambda tns: C.c_void_p(tns.data_ptr())
 
-    def step_e2e():
-        w_coords.copy_(h_coords); w_normals.copy_(h_normals)      # host-side reset of the in/out arrays
+    # coords / normals are in-out arguments of the call (the refined patch replaces the seed), so every step gets its OWN pre-staged
+    # pinned copy of the inputs: the timed region holds the call -- host-to-device copies, kernels, device-to-host copies -- and no
+    # bench-side housekeeping (a host-side reset of 33 MB per step cost 3 ms of the 127 ms).  Beyond 64 steps the sets are reused
+    # and reset in the loop.
+    e2e_steps = max(1, args.steps)      # the same number of timed steps as `value`
+    n_sets = min(e2e_steps + 1, 64)
+    w_sets = [(h_coords.clone().pin_memory(), h_normals.clone().pin_memory()) for _ in range(n_sets)]
+
+    def step_e2e(i):
+        w_coords, w_normals = w_sets[i % n_sets]
+        if i >= n_sets:
+            w_coords.copy_(h_coords); w_normals.copy_(h_normals)
         r = lib.lib.pmvsb_refine_batch(lib.ctx, P, VIEWS, vp(w_coords), vp(w_normals), vp(h_images), None, vp(h_dsc), vp(h_ncc),
                                        vp(h_evals), vp(h_ok))
         if r != 0:
             raise RuntimeError(lib.lib.pmvsb_last_error(lib.ctx).decode())
 
-    e2e_steps = max(1, args.steps)      # the same number of timed steps as `value`
-    step_e2e()
+    step_e2e(0)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
+    for i in range(e2e_steps):
+        step_e2e(1 + i)
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
