@@ -178,6 +178,7 @@ class OracleLib(_Common):
     def __init__(self, num, tnum=None, level=1, csize=2, wsize=7, min_image_num=3, threshold=0.7, max_angle_deg=10.0):
         self.lib = C.CDLL(build_oracle())
         self.lib.pmvso_create.restype = C.c_void_p
+        self.wsize = int(wsize)
         self.ctx = C.c_void_p(self.lib.pmvso_create(num, num if tnum is None else tnum, level, csize, wsize, min_image_num,
                                                     C.c_float(threshold), C.c_float(max_angle_deg)))
         self.num = num
@@ -210,8 +211,10 @@ class OracleLib(_Common):
     def set_xtol(self, xtol=1e-3, step=1.0, maxeval=1000):
         self.lib.pmvso_set_xtol(self.ctx, C.c_double(xtol), C.c_double(step), maxeval)
 
-    def grab_tex(self, coord, normal, ref, index, wsize=7):
-        """-> (flag, tex, newlevel)"""
+    def grab_tex(self, coord, normal, ref, index, wsize=None):
+        """-> (flag, tex, newlevel); the texture has 3 * wsize^2 floats (the context's wsize: the C side writes that many)"""
+        wsize = self.wsize if wsize is None else int(wsize)
+        assert wsize == self.wsize, "grab_tex: the texture size is the context's wsize"
         tex = np.zeros(3 * wsize * wsize, np.float32); nl = C.c_int(-1)
         flag = self.lib.pmvso_grab_tex(self.ctx, _f4(coord).ctypes.data_as(C.c_void_p), _f4(normal).ctypes.data_as(C.c_void_p),
                                        int(ref), int(index), tex.ctypes.data_as(C.c_void_p), C.byref(nl))
@@ -332,7 +335,9 @@ class RefLib(_Common):
     def _h(self):
         return ()
 
-    def grab_tex(self, coord, normal, ref, index, wsize=7):
+    def grab_tex(self, coord, normal, ref, index, wsize=None):
+        wsize = self.wsize if wsize is None else int(wsize)
+        assert wsize == self.wsize, "grab_tex: the texture size is the scene's wsize"
         tex = np.zeros(3 * wsize * wsize, np.float32)
         flag = self.lib.ref_grab_tex(_f4(coord).ctypes.data_as(C.c_void_p), _f4(normal).ctypes.data_as(C.c_void_p), int(ref), int(index),
                                      tex.ctypes.data_as(C.c_void_p))
